@@ -1,0 +1,108 @@
+"""Seeded synthetic inputs for the ORB front-end.
+
+Pure-integer numpy only, so that the same seed gives the same bytes everywhere (no cv2, no float
+filters).  Throughput frames are corner-dense (every pyramid level fills its quadtree quota); parity
+frames add flat, low-contrast, tie-heavy and odd-size content to hit the reference's quirks
+(empty cells, the minThFAST retry `ORBextractor.cc:843-846`, equal-score NMS / quadtree ties).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _box3(a: np.ndarray) -> np.ndarray:
+    """3×3 box filter with edge replication, integer arithmetic (sum // 9)."""
+    p = np.pad(a.astype(np.int32), 1, mode="edge")
+    s = np.zeros_like(a, dtype=np.int32)
+    for dy in range(3):
+        for dx in range(3):
+            s += p[dy:dy + a.shape[0], dx:dx + a.shape[1]]
+    return (s // 9).astype(np.uint8)
+
+
+def _rects(img: np.ndarray, rng: np.random.Generator, count: int, lo: int = 4, hi: int = 20) -> None:
+    h, w = img.shape
+    xs = rng.integers(0, w, size=count)
+    ys = rng.integers(0, h, size=count)
+    ws = rng.integers(lo, hi + 1, size=count)
+    hs = rng.integers(lo, hi + 1, size=count)
+    gs = rng.integers(0, 256, size=count)
+    for x, y, rw, rh, g in zip(xs, ys, ws, hs, gs):
+        img[y:y + rh, x:x + rw] = g
+
+
+def throughput_frame(seed: int, width: int = 640, height: int = 480) -> np.ndarray:
+    """Corner-dense frame: low-passed noise + ~W·H/1500 random grey rectangles (4–20 px)."""
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, size=(height, width), dtype=np.uint8)
+    img = _box3(_box3(img))
+    # stretch the (now narrow) histogram back with integer maths
+    img = np.clip((img.astype(np.int32) - 128) * 3 + 128, 0, 255).astype(np.uint8)
+    _rects(img, rng, max(1, width * height // 1500))
+    return np.ascontiguousarray(img)
+
+
+def parity_frame(seed: int, width: int = 640, height: int = 480) -> np.ndarray:
+    """Quadrants: corner-dense | flat ; low-contrast (amplitude 8–19) | regular dots (ties)."""
+    rng = np.random.default_rng(seed)
+    img = throughput_frame(seed, width, height)
+    hh, hw = height // 2, width // 2
+    # top-right: constant grey → empty cells
+    img[:hh, hw:] = int(rng.integers(40, 216))
+    # bottom-left: texture of amplitude 8..19 → empty at FAST 20, corners at FAST 7
+    base = int(rng.integers(60, 180))
+    amp = int(rng.integers(8, 20))
+    tex = rng.integers(0, 2, size=(height - hh, hw), dtype=np.uint8) * amp
+    blk = np.kron(rng.integers(0, 2, size=((height - hh + 5) // 6, (hw + 5) // 6), dtype=np.uint8),
+                  np.ones((6, 6), dtype=np.uint8))[: height - hh, :hw] * amp
+    img[hh:, :hw] = (base + np.where(rng.integers(0, 4, size=tex.shape) == 0, tex, blk)).astype(np.uint8)
+    # bottom-right: regular dots and a checkerboard → equal responses everywhere
+    quad = np.full((height - hh, width - hw), 100, dtype=np.uint8)
+    quad[4::9, 4::9] = 220
+    quad[5::9, 4::9] = 220
+    cb = (np.add.outer(np.arange(quad.shape[0]) // 8, np.arange(quad.shape[1]) // 8) & 1).astype(np.uint8)
+    half = quad.shape[0] // 2
+    quad[half:] = np.where(cb[half:] == 1, 200, 60)
+    img[hh:, hw:] = quad
+    return np.ascontiguousarray(img)
+
+
+def stereo_right(left: np.ndarray, seed: int, max_disp: int = 40) -> np.ndarray:
+    """Right image = left shifted by a per-row-band constant disparity (so matches exist)."""
+    rng = np.random.default_rng(seed + 1_000_000)
+    h, w = left.shape
+    right = np.empty_like(left)
+    band = 16
+    for y0 in range(0, h, band):
+        d = int(rng.integers(1, max_disp + 1))
+        rows = left[y0:y0 + band]
+        right[y0:y0 + band, : w - d] = rows[:, d:]
+        right[y0:y0 + band, w - d:] = rows[:, w - d - 1: w - d]
+    return right
+
+
+def descriptors(n: int, seed: int) -> np.ndarray:
+    """n i.i.d. uniform 256-bit descriptors, shape (n, 32) uint8."""
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+
+
+def knn_case(nq: int, ndb: int, seed: int = 1234, planted_frac: float = 0.01, dup_rows: int = 4):
+    """Config-4 style case: random DB, random queries, a fraction of queries planted as DB rows with
+    k∈[0,40] flipped bits, plus a few exact duplicate DB rows (tie handling: lower index first)."""
+    rng = np.random.default_rng(seed)
+    db = rng.integers(0, 256, size=(ndb, 32), dtype=np.uint8)
+    q = rng.integers(0, 256, size=(nq, 32), dtype=np.uint8)
+    n_plant = max(1, int(nq * planted_frac)) if ndb > 0 else 0
+    for i in range(n_plant):
+        src = int(rng.integers(0, ndb))
+        row = db[src].copy()
+        k = int(rng.integers(0, 41))
+        bits = rng.choice(256, size=k, replace=False)
+        for b in bits:
+            row[b >> 3] ^= np.uint8(1 << (b & 7))
+        q[i] = row
+        if i < dup_rows and ndb > 8:
+            # duplicate the source row at a later (and an earlier) index to exercise ties
+            db[min(ndb - 1, src + 1 + int(rng.integers(0, 5)))] = db[src]
+    return q, db

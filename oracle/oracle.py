@@ -1,0 +1,160 @@
+"""ctypes binding of liborb_oracle.so (the C++ CPU oracle).  TEST INFRASTRUCTURE, NOT PRODUCT.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_here = os.path.dirname(os.path.abspath(__file__))
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_here, "liborb_oracle.so")
+    src = os.path.join(_here, "orb_oracle.cpp")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _here, "liborb_oracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build())
+        vp, i32, f32, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+        L.orc_create.restype = vp
+        L.orc_create.argtypes = [i32, f32, i32, i32, i32]
+        L.orc_destroy.argtypes = [vp]
+        L.orc_params.argtypes = [vp] * 7
+        L.orc_extract.restype = i32
+        L.orc_extract.argtypes = [vp, vp, i32, i32, sz, vp, i32, i32, i32, vp, vp, i32, vp, vp]
+        L.orc_level_size.argtypes = [vp, i32, vp, vp]
+        L.orc_get_level.argtypes = [vp, i32, i32, vp, sz]
+        L.orc_get_blurred.argtypes = [vp, i32, vp, sz]
+        L.orc_get_candidates.restype = i32
+        L.orc_get_candidates.argtypes = [vp, i32, vp, i32]
+        L.orc_get_selected.restype = i32
+        L.orc_get_selected.argtypes = [vp, i32, vp, i32]
+        L.orc_resize_linear_u8.argtypes = [vp, i32, i32, sz, vp, i32, i32, sz]
+        L.orc_border_reflect101_u8.argtypes = [vp, i32, i32, sz, vp, sz, i32]
+        L.orc_gaussian7_u8.argtypes = [vp, i32, i32, sz, vp, sz]
+        L.orc_fast9_nms.restype = i32
+        L.orc_fast9_nms.argtypes = [vp, i32, i32, sz, i32, vp, i32]
+        L.orc_fast_atan2.restype = f32
+        L.orc_fast_atan2.argtypes = [f32, f32]
+        L.orc_cvround.restype = i32
+        L.orc_cvround.argtypes = [f32]
+        L.orc_sincos.argtypes = [f32, vp, vp]
+        L.orc_distribute.restype = i32
+        L.orc_distribute.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, i32]
+        L.orc_sort_nodes.argtypes = [vp, vp, i32, vp]
+        L.orc_descriptor_distance.restype = i32
+        L.orc_descriptor_distance.argtypes = [vp, vp]
+        L.orc_knn2.argtypes = [vp, i32, vp, C.c_int64, vp, vp, i32]
+        L.orc_ratio_test.argtypes = [vp, i32, C.c_double, vp]
+        L.orc_top2_lists.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
+        L.orc_rot_hist_filter.argtypes = [vp, vp, i32, vp]
+        L.orc_search_init.restype = i32
+        L.orc_search_init.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, vp, f32, i32, vp]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Extractor:
+    """Mirror of ORB_SLAM3::ORBextractor over the C++ oracle."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.L = lib()
+        self.nlevels = nlevels
+        self.nfeatures = nfeatures
+        self.h = self.L.orc_create(nfeatures, scale_factor, nlevels, ini_th, min_th)
+        if not self.h:
+            raise ValueError("bad extractor parameters")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_destroy(self.h)
+            self.h = None
+
+    def params(self):
+        n = self.nlevels
+        sf, inv, s2, is2 = (np.zeros(n, np.float32) for _ in range(4))
+        quota = np.zeros(n, np.int32)
+        umax = np.zeros(16, np.int32)
+        self.L.orc_params(self.h, _p(sf), _p(inv), _p(s2), _p(is2), _p(quota), _p(umax))
+        return dict(sf=sf, inv=inv, sigma2=s2, inv_sigma2=is2, quota=quota, umax=umax)
+
+    def extract(self, img, rects=(), lap=(0, 0), cap=None):
+        """→ (rc, kps, desc, mono_index) like ORBextractor::operator()."""
+        img = np.asarray(img)
+        assert img.dtype == np.uint8 and img.ndim == 2 and (img.size == 0 or img.strides[1] == 1)
+        cap = cap or (self.nfeatures + 64 * self.nlevels + 64)
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = C.c_int(0)
+        mono = C.c_int(0)
+        r = np.ascontiguousarray(np.asarray(rects, np.int32).reshape(-1, 4))
+        rc = self.L.orc_extract(self.h, _p(img), img.shape[0], img.shape[1], img.strides[0] if img.size else 0,
+                                _p(r), len(r), lap[0], lap[1], _p(kps), _p(desc), cap, C.byref(n), C.byref(mono))
+        if rc != 0:
+            return rc, None, None, mono.value
+        return 0, kps[: n.value].copy(), desc[: n.value].copy(), mono.value
+
+    def level_size(self, l):
+        w, h = C.c_int(), C.c_int()
+        self.L.orc_level_size(self.h, l, C.byref(w), C.byref(h))
+        return w.value, h.value
+
+    def level(self, l, padded=False):
+        w, h = self.level_size(l)
+        b = 38 if padded else 0
+        out = np.zeros((h + b, w + b), np.uint8)
+        self.L.orc_get_level(self.h, l, int(padded), _p(out), out.strides[0])
+        return out
+
+    def blurred(self, l):
+        w, h = self.level_size(l)
+        out = np.zeros((h, w), np.uint8)
+        rc = self.L.orc_get_blurred(self.h, l, _p(out), out.strides[0])
+        return out if rc == 0 else None
+
+    def candidates(self, l):
+        n = self.L.orc_get_candidates(self.h, l, None, 0)
+        out = np.zeros(max(n, 1), KP_DTYPE)
+        self.L.orc_get_candidates(self.h, l, _p(out), n)
+        return out[:n]
+
+    def selected(self, l):
+        n = self.L.orc_get_selected(self.h, l, None, 0)
+        out = np.zeros(max(n, 1), KP_DTYPE)
+        self.L.orc_get_selected(self.h, l, _p(out), n)
+        return out[:n]
+
+
+def knn2(q, db, nthreads=1):
+    q = np.ascontiguousarray(q, np.uint8)
+    db = np.ascontiguousarray(db, np.uint8)
+    idx = np.zeros((len(q), 2), np.int32)
+    dist = np.zeros((len(q), 2), np.int32)
+    lib().orc_knn2(_p(q), len(q), _p(db), len(db), _p(idx), _p(dist), nthreads)
+    return idx, dist
+
+
+def ratio_test(dist, ratio=0.7):
+    dist = np.ascontiguousarray(dist, np.int32)
+    keep = np.zeros(len(dist), np.uint8)
+    lib().orc_ratio_test(_p(dist), len(dist), ratio, _p(keep))
+    return keep.astype(bool)
