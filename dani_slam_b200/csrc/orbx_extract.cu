@@ -1,0 +1,1648 @@
+// orbx_extract.cu — B200 (sm_100a) ORB extractor: the ORBextractor::operator() pipeline of
+// /root/reference/src/ORBextractor.cc:1125-1207 as batched CUDA kernels behind the C ABI in
+// include/orbx.h.  All file:line citations are relative to /root/reference.
+//
+// Pipeline for a batch of B equally sized frames (one launch per stage, grid.y = frame):
+//   K1 k_pyr_level   ×(L-1)  ComputePyramid :1209-1234 — bilinear 8U resize, 11-bit fixed point
+//   K2 k_fast_cells          cell loop :781-869 — one warp per 35-px cell: FAST-9 score map in smem,
+//                            cell-local NMS, iniTh/minTh retry, row-major ordered candidate list
+//   K3 k_quadtree            DANI filter :871-907 + DistributeOctTree :555-779 — one block per
+//                            (frame, level): exact list-order emulation incl. libstdc++ sort ties
+//   K7 k_assemble            output ordering :1157-1204 (mono from the front, lapping from the back)
+//   K5 k_blur                GaussianBlur 7×7 σ=2 :1171-1172 — separable integer, REFLECT_101 halo tiles
+//   K4+K6 k_orient_desc      IC_Angle :76-103 + computeOrbDescriptor :107-146 — one warp per keypoint
+//
+// Everything is integer or individually rounded fp32 (no FMA contraction: __f*_rn intrinsics and
+// -fmad=false), so results are bit-identical to the CPU oracle.  No tensor cores: no stage is a
+// dense contraction.  The 19-px REFLECT_101 border of mvImagePyramid is never read by this path
+//  and is materialised lazily on the host by orbx_get_pyramid.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "glibc_sincosf.h"
+#include "orbx_internal.h"
+#include "stdsort_port.h"
+
+namespace {
+
+const int8_t h_pattern[1024] = {
+#include "orb_pattern.inc"
+};
+
+// ------------------------------------------------------------------------------------------------
+// kernel argument bundle
+// ------------------------------------------------------------------------------------------------
+struct ExParams {
+    const OrbxGeom *g;
+    const uint8_t *in0;       // level 0 source (caller's device frames, or the internal copy)
+    long long in0Stride;
+    int in0Pitch;
+    uint8_t *pyr;             // internal pyramid block, B × frameBytes
+    uint8_t *blur;            // blurred levels, same layout as pyr
+    const OrbxCell *cells;
+    const int2 *tabX;         // per level ≥1: {src index, a0 | a1<<16} per destination column
+    const int2 *tabY;
+    const int *tabXOff;       // offsets of each level's table
+    const int *tabYOff;
+    uint32_t *slots;          // per cell candidate slots: x | y<<8 | score<<16 (cell-ROI coords)
+    int *cellCnt;             // candidates per cell
+    float2 *ptXY;             // per slot: drifted (x,y) relative to the 16-px border
+    uint32_t *ptNode;         // per slot: quadtree node position, ORBX_NODE_ERASED when deleted
+    float4 *sel;              // per frame selTotal entries: x, y (level coords), response, -
+    int *selCnt;              // per frame × level
+    OrbxWork *work;           // per frame selTotal entries
+    int *workCnt;             // per frame
+    orbx_keypoint *kps;
+    uint8_t *desc;
+    int cap;
+    int *nOut;
+    int *monoIdx;
+    const int8_t *pattern;    // 1024 bytes
+};
+
+__device__ __forceinline__ const uint8_t *level_ptr(const ExParams &p, const OrbxGeom &g, int l, int b,
+                                                    int &pitch) {
+    if (l == 0) {
+        pitch = p.in0Pitch;
+        return p.in0 + (long long)b * p.in0Stride;
+    }
+    pitch = g.lv[l].pitch;
+    return p.pyr + (long long)b * g.frameBytes + g.lv[l].off;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: bilinear resize (cv::resize INTER_LINEAR 8UC1).  One thread = 4 output pixels.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pyr_level(ExParams p, int l) {
+    const OrbxGeom &g = *p.g;
+    const OrbxLevel &D = g.lv[l];
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int b = blockIdx.z;
+    if (x4 >= D.w || y >= D.h) return;
+    int sp;
+    const uint8_t *S = level_ptr(p, g, l - 1, b, sp);
+    const int sw = g.lv[l - 1].w, sh = g.lv[l - 1].h;
+    const int2 ty = p.tabY[p.tabYOff[l] + y];
+    const int sy0 = min(max(ty.x, 0), sh - 1), sy1 = min(max(ty.x + 1, 0), sh - 1);
+    const int b0 = (short)(ty.y & 0xffff), b1 = (short)(ty.y >> 16);
+    const uint8_t *R0 = S + (long long)sy0 * sp, *R1 = S + (long long)sy1 * sp;
+    const int2 *tx = p.tabX + p.tabXOff[l] + x4;
+    uint32_t out = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (x4 + i < D.w) {
+            const int2 t = tx[i];
+            const int s0 = t.x, s1 = min(t.x + 1, sw - 1);
+            const int a0 = (short)(t.y & 0xffff), a1 = (short)(t.y >> 16);
+            const int h0 = R0[s0] * a0 + R0[s1] * a1;
+            const int h1 = R1[s0] * a0 + R1[s1] * a1;
+            const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+            out |= (uint32_t)(v & 0xff) << (8 * i);
+        }
+    }
+    uint8_t *Dp = p.pyr + (long long)b * g.frameBytes + D.off + (long long)y * D.pitch + x4;
+    *reinterpret_cast<uint32_t *>(Dp) = out;  // pitch is a multiple of 128: in-row padding is writable
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: FAST-9_16 per cell (cv::FAST + NMS on the cell ROI)
+// ------------------------------------------------------------------------------------------------
+struct FastSmem {
+    int roiPitch, scorePitch;
+    int roiOff, scoreOff, queueOff, listOff, total;
+};
+__host__ __device__ inline FastSmem fast_smem_layout(int maxCw, int maxCh, int maxSlotCap) {
+    FastSmem s;
+    s.roiPitch = (maxCw + 3) & ~3;
+    s.scorePitch = (maxCw - 6 + 2 + 3) & ~3;
+    s.roiOff = 0;
+    s.scoreOff = s.roiOff + s.roiPitch * maxCh;
+    s.queueOff = (s.scoreOff + s.scorePitch * (maxCh - 6 + 2) + 3) & ~3;
+    s.listOff = (s.queueOff + 2 * (maxCw - 6) * (maxCh - 6) + 3) & ~3;
+    s.total = (s.listOff + 4 * maxSlotCap + 15) & ~15;
+    return s;
+}
+
+// does a 16-bit circular mask contain 9 contiguous set bits?
+__device__ __forceinline__ bool has_arc9(uint32_t m) {
+    uint32_t x = m | (m << 16);
+    uint32_t r = x & (x >> 1);
+    r &= r >> 2;
+    r &= r >> 4;       // runs of 8
+    r &= x >> 8;       // runs of 9
+    return (r & 0xffffu) != 0;
+}
+
+template <int WPB>
+__global__ void __launch_bounds__(WPB * 32) k_fast_cells(ExParams p, int maxSlotCap) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const OrbxGeom &g = *p.g;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * WPB + warp, b = blockIdx.y;
+    if (c >= g.nCellsTotal) return;  // warps are independent: no block-level barrier below
+    const OrbxCell cell = p.cells[c];
+    const FastSmem L = fast_smem_layout(g.maxCw, g.maxCh, maxSlotCap);
+    uint8_t *base = smem_raw + (size_t)warp * L.total;
+    uint8_t *roi = base + L.roiOff;
+    uint8_t *score = base + L.scoreOff;
+    uint16_t *queue = reinterpret_cast<uint16_t *>(base + L.queueOff);
+    uint32_t *list = reinterpret_cast<uint32_t *>(base + L.listOff);
+
+    int pitch;
+    const uint8_t *img = level_ptr(p, g, cell.level, b, pitch);
+    const int cw = cell.cw, ch = cell.ch;
+    const int iw = cw - 6, ih = ch - 6;
+    int *cntOut = p.cellCnt + (long long)b * g.nCellsTotal + c;
+    if (iw <= 0 || ih <= 0) {  // ROI smaller than 7×7: cv::FAST finds nothing
+        if (lane == 0) *cntOut = 0;
+        return;
+    }
+    // stage the ROI
+    const uint8_t *src = img + (long long)cell.y0 * pitch + cell.x0;
+    for (int y = 0; y < ch; ++y)
+        for (int x = lane; x < cw; x += 32) roi[y * L.roiPitch + x] = src[(long long)y * pitch + x];
+    // zero the score map (1-px frame of zeros = "outside the cell interior counts 0")
+    {
+        uint32_t *s32 = reinterpret_cast<uint32_t *>(score);
+        const int nw = (L.scorePitch * (ih + 2)) >> 2;
+        for (int i = lane; i < nw; i += 32) s32[i] = 0;
+    }
+    __syncwarp();
+
+    const int rp = L.roiPitch;
+    const int off[16] = {3 * rp,      3 * rp + 1,  2 * rp + 2,  rp + 3,  3,        -rp + 3,  -2 * rp + 2, -3 * rp + 1,
+                         -3 * rp,     -3 * rp - 1, -2 * rp - 2, -rp - 3, -3,       rp - 3,   2 * rp - 2,  3 * rp - 1};
+    const int t = g.lowTh;
+    const int npx = iw * ih;
+    const uint32_t recip = ((1u << 20) + iw - 1) / iw;  // floor(i/iw) == (i*recip)>>20 for i < 2^20/iw
+
+    // phase A: exact corner test (M > lowTh) for every interior pixel → queue of corner pixels
+    int nq = 0;
+    for (int i0 = 0; i0 < npx; i0 += 32) {
+        const int i = i0 + lane;
+        bool corner = false;
+        if (i < npx) {
+            const int y = (int)(((uint32_t)i * recip) >> 20), x = i - y * iw;
+            const uint8_t *c0 = roi + (y + 3) * rp + (x + 3);
+            const int v = c0[0];
+            const int hi = v + t, lo = v - t;
+            uint32_t mb = 0, md = 0;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int r = c0[off[k]];
+                mb |= (uint32_t)(r > hi) << k;
+                md |= (uint32_t)(r < lo) << k;
+            }
+            corner = has_arc9(mb) || has_arc9(md);
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, corner);
+        if (corner) queue[nq + __popc(bal & ((1u << lane) - 1))] = (uint16_t)i;
+        nq += __popc(bal);
+    }
+    __syncwarp();
+
+    // phase B: exact score M-1 for the queued corners (max over 9-arcs of min |diff|, both polarities)
+    for (int qi = lane; qi < nq; qi += 32) {
+        const int i = queue[qi];
+        const int y = (int)(((uint32_t)i * recip) >> 20), x = i - y * iw;
+        const uint8_t *c0 = roi + (y + 3) * rp + (x + 3);
+        const int v = c0[0];
+        int d[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) d[k] = v - (int)c0[off[k]];
+        int lo2[16], hi2[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { lo2[k] = min(d[k], d[(k + 1) & 15]); hi2[k] = max(d[k], d[(k + 1) & 15]); }
+        int lo4[16], hi4[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { lo4[k] = min(lo2[k], lo2[(k + 2) & 15]); hi4[k] = max(hi2[k], hi2[(k + 2) & 15]); }
+        int A = -256, Bm = 256;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int lo8 = min(lo4[k], lo4[(k + 4) & 15]), hi8 = max(hi4[k], hi4[(k + 4) & 15]);
+            A = max(A, min(lo8, d[(k + 8) & 15]));
+            Bm = min(Bm, max(hi8, d[(k + 8) & 15]));
+        }
+        const int M = max(A, -Bm);
+        score[(y + 1) * L.scorePitch + (x + 1)] = (uint8_t)(M - 1);
+    }
+    __syncwarp();
+
+    // phase C: cell-local 3×3 strict NMS, row-major ordered list; count survivors above iniTh
+    const int spitch = L.scorePitch;
+    int n = 0, nIni = 0;
+    for (int i0 = 0; i0 < npx; i0 += 32) {
+        const int i = i0 + lane;
+        bool keep = false;
+        int s = 0, x = 0, y = 0;
+        if (i < npx) {
+            y = (int)(((uint32_t)i * recip) >> 20);
+            x = i - y * iw;
+            const uint8_t *sc = score + (y + 1) * spitch + (x + 1);
+            s = sc[0];
+            keep = s > 0 && s > sc[-1] && s > sc[1] && s > sc[-spitch - 1] && s > sc[-spitch] &&
+                   s > sc[-spitch + 1] && s > sc[spitch - 1] && s > sc[spitch] && s > sc[spitch + 1];
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        const uint32_t balIni = __ballot_sync(0xffffffffu, keep && s >= g.iniTh);  // M-1 >= iniTh ⇔ M > iniTh
+        if (keep) list[n + __popc(bal & ((1u << lane) - 1))] = (uint32_t)(x + 3) | ((uint32_t)(y + 3) << 8) | ((uint32_t)s << 16);
+        n += __popc(bal);
+        nIni += __popc(balIni);
+    }
+    __syncwarp();
+    // retry rule (:843-846): if the iniTh pass is empty after NMS, the minTh pass is the result
+    const int th = nIni > 0 ? g.iniTh : g.minTh;
+    uint32_t *out = p.slots + (long long)b * g.slotsTotal + cell.slot;
+    int m = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        uint32_t e = 0;
+        bool keep = false;
+        if (i < n) {
+            e = list[i];
+            keep = (int)(e >> 16) >= th;
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) out[m + __popc(bal & ((1u << lane) - 1))] = e;
+        m += __popc(bal);
+    }
+    if (lane == 0) *cntOut = m;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: DANI filter + quadtree (DistributeOctTree), one block per (frame, level)
+// ------------------------------------------------------------------------------------------------
+#define QT_THREADS 256
+
+// block-wide exclusive scan of a[0..n) in place; returns the total.  All threads must call.
+__device__ int block_exclusive_scan(int *a, int n, int *scratch /* >= QT_THREADS+1 ints */) {
+    const int tid = threadIdx.x;
+    const int per = (n + QT_THREADS - 1) / QT_THREADS;
+    const int lo = min(tid * per, n), hi = min(lo + per, n);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += a[i];
+    scratch[tid] = sum;
+    __syncthreads();
+    if (tid < 32) {
+        // 256 partial sums: each lane of warp 0 scans 8 of them
+        int loc[QT_THREADS / 32];
+        int s = 0;
+#pragma unroll
+        for (int k = 0; k < QT_THREADS / 32; ++k) { loc[k] = s; s += scratch[tid * (QT_THREADS / 32) + k]; }
+        int incl = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (tid >= o) incl += v;
+        }
+        const int excl = incl - s;
+#pragma unroll
+        for (int k = 0; k < QT_THREADS / 32; ++k) scratch[tid * (QT_THREADS / 32) + k] = excl + loc[k];
+        if (tid == 31) scratch[QT_THREADS] = incl;
+    }
+    __syncthreads();
+    int run = scratch[tid];
+    for (int i = lo; i < hi; ++i) { const int v = a[i]; a[i] = run; run += v; }
+    const int total = scratch[QT_THREADS];
+    __syncthreads();
+    return total;
+}
+
+struct QtSmem {
+    int boxOff[2], cntOff[2], childCntOff, childPosOff, keptPosOff, pendOff, pendIdxOff, sortOff,
+        bestOff, prefixOff, scratchOff, total;
+};
+__host__ __device__ inline QtSmem qt_smem_layout(int nodeCap, int maxCellsLevel) {
+    QtSmem s;
+    int o = 0;
+    s.sortOff = o; o += 8 * nodeCap;               // 64-bit sort elements first (alignment)
+    s.boxOff[0] = o; o += 8 * nodeCap;             // short4 per node
+    s.boxOff[1] = o; o += 8 * nodeCap;
+    s.cntOff[0] = o; o += 4 * nodeCap;
+    s.cntOff[1] = o; o += 4 * nodeCap;
+    s.childCntOff = o; o += 16 * nodeCap;
+    s.childPosOff = o; o += 16 * nodeCap;
+    s.keptPosOff = o; o += 4 * nodeCap;
+    s.pendOff = o; o += 4 * nodeCap;
+    s.pendIdxOff = o; o += 4 * nodeCap;
+    s.bestOff = o; o += 4 * nodeCap;
+    s.prefixOff = o; o += 4 * (maxCellsLevel + 1);
+    s.scratchOff = o; o += 4 * (QT_THREADS + 2);
+    s.total = (o + 15) & ~15;
+    return s;
+}
+
+// quadrant of a point inside a node (DivideNode :480-536): children n1..n4 = 0..3
+__device__ __forceinline__ int qt_quadrant(short4 bx, float x, float y) {
+    const int hx = (int)ceilf(__fdiv_rn((float)(bx.y - bx.x), 2.f));
+    const int hy = (int)ceilf(__fdiv_rn((float)(bx.w - bx.z), 2.f));
+    const float xm = (float)(bx.x + hx), ym = (float)(bx.z + hy);
+    return (x < xm ? 0 : 1) + (y < ym ? 0 : 2);
+}
+__device__ __forceinline__ short4 qt_child_box(short4 bx, int q) {  // box = {x0, x1, y0, y1}
+    const int hx = (int)ceilf(__fdiv_rn((float)(bx.y - bx.x), 2.f));
+    const int hy = (int)ceilf(__fdiv_rn((float)(bx.w - bx.z), 2.f));
+    const short xm = (short)(bx.x + hx), ym = (short)(bx.z + hy);
+    short4 c;
+    c.x = (q & 1) ? xm : bx.x;
+    c.y = (q & 1) ? bx.y : xm;
+    c.z = (q & 2) ? ym : bx.z;
+    c.w = (q & 2) ? bx.w : ym;
+    return c;
+}
+
+__global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCapMax, int maxCellsLevel) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const OrbxGeom &g = *p.g;
+    const int l = blockIdx.x, b = blockIdx.y;
+    const OrbxLevel &LV = g.lv[l];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nWarps = QT_THREADS / 32;
+    const QtSmem S = qt_smem_layout(nodeCapMax, maxCellsLevel);
+    orbx_sort::elem_t *sortbuf = reinterpret_cast<orbx_sort::elem_t *>(smem_raw + S.sortOff);
+    short4 *box[2] = {reinterpret_cast<short4 *>(smem_raw + S.boxOff[0]), reinterpret_cast<short4 *>(smem_raw + S.boxOff[1])};
+    int *cnt[2] = {reinterpret_cast<int *>(smem_raw + S.cntOff[0]), reinterpret_cast<int *>(smem_raw + S.cntOff[1])};
+    int *childCnt = reinterpret_cast<int *>(smem_raw + S.childCntOff);
+    int *childPos = reinterpret_cast<int *>(smem_raw + S.childPosOff);
+    int *keptPos = reinterpret_cast<int *>(smem_raw + S.keptPosOff);
+    int *pend = reinterpret_cast<int *>(smem_raw + S.pendOff);
+    int *pendIdx = reinterpret_cast<int *>(smem_raw + S.pendIdxOff);
+    unsigned *best = reinterpret_cast<unsigned *>(smem_raw + S.bestOff);
+    int *prefix = reinterpret_cast<int *>(smem_raw + S.prefixOff);
+    int *scratch = reinterpret_cast<int *>(smem_raw + S.scratchOff);
+    __shared__ int sh_size, sh_nPend, sh_C;
+
+    const int nCells = LV.nCells;
+    const int N = LV.quota;
+    const int *cellCnt = p.cellCnt + (long long)b * g.nCellsTotal + LV.cellBase;
+    const OrbxCell *cells = p.cells + LV.cellBase;
+    uint32_t *slots = p.slots + (long long)b * g.slotsTotal;
+    float2 *ptXY = p.ptXY + (long long)b * g.slotsTotal;
+    uint32_t *ptNode = p.ptNode + (long long)b * g.slotsTotal;
+    float4 *sel = p.sel + (long long)b * g.selTotal + LV.selBase;
+    int *selCntOut = p.selCnt + b * g.nlevels + l;
+
+    // candidate order index = prefix over cells in processing order + rank inside the cell
+    for (int c = tid; c < nCells; c += QT_THREADS) prefix[c] = cellCnt[c];
+    __syncthreads();
+    const int nPts = block_exclusive_scan(prefix, nCells, scratch);
+    if (tid == 0) prefix[nCells] = nPts;
+    if (nPts == 0 || LV.nIni < 1) {
+        if (tid == 0) *selCntOut = 0;
+        return;
+    }
+    const int nIni = LV.nIni;
+    for (int i = tid; i < nIni; i += QT_THREADS) childCnt[i] = 0;
+    __syncthreads();
+
+    // ---- DANI dynamic-area deletion with its fp32 round trip (:871-907) + root binning
+    const float sc = LV.sf, inv = __fdiv_rn(1.f, sc);
+    const float hX = LV.hX;
+    const int nRects = g.nRects;
+    for (int c = warp; c < nCells; c += nWarps) {
+        const OrbxCell cell = cells[c];
+        const int n = cellCnt[c];
+        const int trips = nCells - cell.seq;  // filter passes this cell's keypoints live through
+        for (int k = lane; k < n; k += 32) {
+            const long long slot = cell.slot + k;
+            const uint32_t e = slots[slot];
+            float x = __fadd_rn((float)(e & 0xff), (float)(cell.cx * LV.wCell));  // pt.x += j*wCell (:863)
+            float y = __fadd_rn((float)((e >> 8) & 0xff), (float)(cell.cy * LV.hCell));
+            bool erased = false;
+            for (int t = 0; t < trips; ++t) {
+                const float xs = __fmul_rn(__fadd_rn(x, (float)ORBX_BORDER), sc);
+                const float ys = __fmul_rn(__fadd_rn(y, (float)ORBX_BORDER), sc);
+                if (nRects > 0) {
+                    const int px = __float2int_rn(xs), py = __float2int_rn(ys);  // Point2f → Point2i
+                    for (int r = 0; r < nRects; ++r) {
+                        const int rx = g.rects[4 * r], ry = g.rects[4 * r + 1];
+                        if (rx <= px && px < rx + g.rects[4 * r + 2] && ry <= py && py < ry + g.rects[4 * r + 3]) {
+                            erased = true;
+                            break;
+                        }
+                    }
+                    if (erased) break;
+                }
+                const float xn = __fsub_rn(__fmul_rn(xs, inv), (float)ORBX_BORDER);
+                const float yn = __fsub_rn(__fmul_rn(ys, inv), (float)ORBX_BORDER);
+                const bool fixed = (xn == x) && (yn == y);
+                x = xn;
+                y = yn;
+                if (fixed) break;  // later trips reproduce this one exactly
+            }
+            ptXY[slot] = make_float2(x, y);
+            if (erased) {
+                ptNode[slot] = ORBX_NODE_ERASED;
+            } else {
+                int bin = (int)__fdiv_rn(x, hX);  // vpIniNodes[kp.pt.x/hX] (:584)
+                bin = min(max(bin, 0), nIni - 1);
+                ptNode[slot] = (uint32_t)bin;
+                atomicAdd(&childCnt[bin], 1);
+            }
+        }
+    }
+    __syncthreads();
+    // initial list: non-empty roots in order (:565-601)
+    if (tid == 0) {
+        int m = 0;
+        for (int i = 0; i < nIni; ++i) {
+            keptPos[i] = -1;
+            if (childCnt[i] > 0) {
+                short4 bx;
+                bx.x = (short)(int)__fmul_rn(hX, (float)i);
+                bx.y = (short)(int)__fmul_rn(hX, (float)(i + 1));
+                bx.z = 0;
+                bx.w = (short)(LV.maxBY - ORBX_BORDER);
+                box[0][m] = bx;
+                cnt[0][m] = childCnt[i];
+                keptPos[i] = m++;
+            }
+        }
+        sh_size = m;
+    }
+    __syncthreads();
+    for (int c = warp; c < nCells; c += nWarps) {
+        const long long s0 = cells[c].slot;
+        const int n = cellCnt[c];
+        for (int k = lane; k < n; k += 32) {
+            const uint32_t nd = ptNode[s0 + k];
+            if (nd != ORBX_NODE_ERASED) ptNode[s0 + k] = (uint32_t)keptPos[nd];
+        }
+    }
+    __syncthreads();
+
+    int cur = 0;
+    int size = sh_size;
+    bool done = (size == 0);
+    bool phase2 = false;
+    int nPend = 0;
+    while (!done) {
+        const int prevSize = size;
+        const int nxt = cur ^ 1;
+        short4 *bxC = box[cur], *bxN = box[nxt];
+        int *cnC = cnt[cur], *cnN = cnt[nxt];
+        if (!phase2) {
+            // ---- full pass: split every node holding more than one point (:616-683)
+            for (int i = tid; i < 4 * size; i += QT_THREADS) childCnt[i] = 0;
+            __syncthreads();
+            for (int c = warp; c < nCells; c += nWarps) {
+                const long long s0 = cells[c].slot;
+                const int n = cellCnt[c];
+                for (int k = lane; k < n; k += 32) {
+                    const uint32_t nd = ptNode[s0 + k];
+                    if (nd == ORBX_NODE_ERASED || cnC[nd] <= 1) continue;
+                    const float2 xy = ptXY[s0 + k];
+                    const int q = qt_quadrant(bxC[nd], xy.x, xy.y);
+                    atomicAdd(&childCnt[4 * nd + q], 1);
+                    ptNode[s0 + k] = nd | ((uint32_t)q << 30);
+                }
+            }
+            __syncthreads();
+            // creation order = list order × child order; children go to the list front (reversed)
+            for (int i = tid; i < 4 * size; i += QT_THREADS) childPos[i] = childCnt[i] > 0 ? 1 : 0;
+            for (int i = tid; i < size; i += QT_THREADS) keptPos[i] = cnC[i] <= 1 ? 1 : 0;
+            __syncthreads();
+            const int C = block_exclusive_scan(childPos, 4 * size, scratch);
+            const int nKept = block_exclusive_scan(keptPos, size, scratch);
+            // write nodes
+            for (int i = tid; i < 4 * size; i += QT_THREADS) {
+                const int n = childCnt[i];
+                if (n > 0) {
+                    const int pos = C - 1 - childPos[i];
+                    bxN[pos] = qt_child_box(bxC[i >> 2], i & 3);
+                    cnN[pos] = n;
+                    childPos[i] = pos;
+                } else {
+                    childPos[i] = -1;
+                }
+            }
+            for (int i = tid; i < size; i += QT_THREADS) {
+                if (cnC[i] <= 1) {
+                    const int pos = C + keptPos[i];
+                    bxN[pos] = bxC[i];
+                    cnN[pos] = cnC[i];
+                    keptPos[i] = pos;
+                } else {
+                    keptPos[i] = -1;
+                }
+            }
+            __syncthreads();
+            // remap points
+            for (int c = warp; c < nCells; c += nWarps) {
+                const long long s0 = cells[c].slot;
+                const int n = cellCnt[c];
+                for (int k = lane; k < n; k += 32) {
+                    const uint32_t v = ptNode[s0 + k];
+                    if (v == ORBX_NODE_ERASED) continue;
+                    const uint32_t nd = v & 0x3fffffffu, q = v >> 30;
+                    ptNode[s0 + k] = (uint32_t)(cnC[nd] <= 1 ? keptPos[nd] : childPos[4 * nd + q]);
+                }
+            }
+            // expandable children in creation order (serial: ≤ 4·size entries, cheap next to the rest)
+            if (tid == 0) {
+                int np = 0;
+                for (int i = 0; i < 4 * size; ++i)
+                    if (childCnt[i] > 1) pend[np++] = childPos[i];
+                sh_nPend = np;
+            }
+            __syncthreads();
+            nPend = sh_nPend;
+            size = C + nKept;
+            cur = nxt;
+            if (size >= N || size == prevSize) done = true;
+            else if (size + 3 * nPend > N) phase2 = true;
+        } else {
+            // ---- "largest first" pass (:685-751): sort pending by (size, UL.x) exactly like std::sort
+            for (int i = tid; i < size; i += QT_THREADS) pendIdx[i] = -1;
+            for (int i = tid; i < 4 * nPend; i += QT_THREADS) childCnt[i] = 0;
+            __syncthreads();
+            for (int i = tid; i < nPend; i += QT_THREADS) {
+                const int pos = pend[i];
+                pendIdx[pos] = i;
+                const unsigned long long key = ((unsigned long long)(unsigned)cnC[pos] << 16) | (unsigned short)bxC[pos].x;
+                sortbuf[i] = (key << orbx_sort::kPayloadBits) | (unsigned long long)i;
+            }
+            __syncthreads();
+            if (tid == 0) orbx_sort::sort(sortbuf, nPend);
+            for (int c = warp; c < nCells; c += nWarps) {
+                const long long s0 = cells[c].slot;
+                const int n = cellCnt[c];
+                for (int k = lane; k < n; k += 32) {
+                    const uint32_t nd = ptNode[s0 + k];
+                    if (nd == ORBX_NODE_ERASED) continue;
+                    const int pi = pendIdx[nd];
+                    if (pi < 0) continue;
+                    const float2 xy = ptXY[s0 + k];
+                    const int q = qt_quadrant(bxC[nd], xy.x, xy.y);
+                    atomicAdd(&childCnt[4 * pi + q], 1);
+                    ptNode[s0 + k] = nd | ((uint32_t)q << 30);
+                }
+            }
+            __syncthreads();
+            // walk the sorted array from the back until the list reaches N nodes (:701-747)
+            if (tid == 0) {
+                int sz = size, c = 0;
+                for (int j = nPend - 1; j >= 0; --j) {
+                    const int pi = (int)(sortbuf[j] & ((1ull << orbx_sort::kPayloadBits) - 1));
+                    for (int q = 0; q < 4; ++q) {
+                        if (childCnt[4 * pi + q] > 0) { childPos[4 * pi + q] = c++; ++sz; }
+                        else childPos[4 * pi + q] = -1;
+                    }
+                    --sz;
+                    best[pi] = 1;  // processed marker, indexed by pending index
+                    if (sz >= N) {
+                        for (int jj = j - 1; jj >= 0; --jj) best[(int)(sortbuf[jj] & ((1ull << orbx_sort::kPayloadBits) - 1))] = 0;
+                        break;
+                    }
+                }
+                sh_C = c;
+                sh_size = sz;
+            }
+            __syncthreads();
+            const int C = sh_C;
+            // survivors of the old list keep their relative order behind the new children
+            for (int i = tid; i < size; i += QT_THREADS) {
+                const int pi = pendIdx[i];
+                keptPos[i] = (pi >= 0 && best[pi] == 1) ? 0 : 1;
+            }
+            __syncthreads();
+            block_exclusive_scan(keptPos, size, scratch);
+            for (int i = tid; i < size; i += QT_THREADS) {
+                const int pi = pendIdx[i];
+                if (pi >= 0 && best[pi] == 1) {
+                    keptPos[i] = -1;
+                } else {
+                    const int pos = C + keptPos[i];
+                    bxN[pos] = bxC[i];
+                    cnN[pos] = cnC[i];
+                    keptPos[i] = pos;
+                }
+            }
+            for (int i = tid; i < 4 * nPend; i += QT_THREADS) {
+                const int pi = i >> 2;
+                if (best[pi] == 1 && childCnt[i] > 0) {
+                    const int pos = C - 1 - childPos[i];
+                    bxN[pos] = qt_child_box(bxC[pend[pi]], i & 3);
+                    cnN[pos] = childCnt[i];
+                    childPos[i] = pos;
+                } else {
+                    childPos[i] = -1;
+                }
+            }
+            __syncthreads();
+            for (int c = warp; c < nCells; c += nWarps) {
+                const long long s0 = cells[c].slot;
+                const int n = cellCnt[c];
+                for (int k = lane; k < n; k += 32) {
+                    const uint32_t v = ptNode[s0 + k];
+                    if (v == ORBX_NODE_ERASED) continue;
+                    const uint32_t nd = v & 0x3fffffffu, q = v >> 30;
+                    const int pi = pendIdx[nd];
+                    ptNode[s0 + k] = (uint32_t)((pi >= 0 && best[pi] == 1) ? childPos[4 * pi + q] : keptPos[nd]);
+                }
+            }
+            __syncthreads();
+            // next pending list: expandable children in creation order = processing order × child order
+            if (tid == 0) {
+                int np = 0;
+                // processing order is the sorted array from the back; rebuild into scratch-free storage
+                // (pend is overwritten only after all reads of the old list above are complete)
+                int tmpCount = 0;
+                for (int j = nPend - 1; j >= 0; --j) {
+                    const int pi = (int)(sortbuf[j] & ((1ull << orbx_sort::kPayloadBits) - 1));
+                    if (best[pi] != 1) break;
+                    for (int q = 0; q < 4; ++q)
+                        if (childCnt[4 * pi + q] > 1) pendIdx[tmpCount++] = childPos[4 * pi + q];
+                }
+                for (int i = 0; i < tmpCount; ++i) pend[np++] = pendIdx[i];
+                sh_nPend = np;
+            }
+            __syncthreads();
+            nPend = sh_nPend;
+            size = sh_size;
+            cur = nxt;
+            if (size >= N || size == prevSize) done = true;
+        }
+        __syncthreads();
+    }
+
+    // ---- best response per node, first maximum in insertion order wins (:757-776)
+    for (int i = tid; i < size; i += QT_THREADS) best[i] = 0;
+    __syncthreads();
+    for (int c = warp; c < nCells; c += nWarps) {
+        const long long s0 = cells[c].slot;
+        const int n = cellCnt[c];
+        const int o0 = prefix[c];
+        for (int k = lane; k < n; k += 32) {
+            const uint32_t nd = ptNode[s0 + k];
+            if (nd == ORBX_NODE_ERASED) continue;
+            const unsigned key = ((slots[s0 + k] >> 16) << 24) | (0xffffffu - (unsigned)(o0 + k));
+            atomicMax(&best[nd], key);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < size; i += QT_THREADS) {
+        const int order = (int)(0xffffffu - (best[i] & 0xffffffu));
+        int lo = 0, hi = nCells;  // last cell with prefix[c] <= order
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (prefix[mid] <= order) lo = mid; else hi = mid;
+        }
+        const long long slot = cells[lo].slot + (order - prefix[lo]);
+        const float2 xy = ptXY[slot];
+        // :919-923 — add the border back; response = FAST score
+        sel[i] = make_float4(__fadd_rn(xy.x, (float)ORBX_BORDER), __fadd_rn(xy.y, (float)ORBX_BORDER),
+                             (float)(slots[slot] >> 16), 0.f);
+    }
+    if (tid == 0) *selCntOut = size;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7: output ordering (:1157-1204).  One block per frame.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_assemble(ExParams p) {
+    const OrbxGeom &g = *p.g;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    __shared__ int s_cnt[ORBX_MAX_LEVELS + 1];
+    __shared__ int s_warp[8];
+    __shared__ int s_run;
+    if (tid == 0) {
+        int t = 0;
+        for (int l = 0; l < g.nlevels; ++l) { s_cnt[l] = t; t += p.selCnt[b * g.nlevels + l]; }
+        s_cnt[g.nlevels] = t;
+        s_run = 0;
+        p.nOut[b] = t;
+    }
+    __syncthreads();
+    const int total = s_cnt[g.nlevels];
+    const bool fits = total <= p.cap;
+    const float4 *sel = p.sel + (long long)b * g.selTotal;
+    orbx_keypoint *kps = p.kps + (long long)b * p.cap;
+    OrbxWork *work = p.work + (long long)b * g.selTotal;
+    const float lap0 = (float)g.lap0, lap1 = (float)g.lap1;
+    for (int base = 0; base < total; base += 256) {
+        const int i = base + tid;
+        int l = 0;
+        bool mono = false, valid = i < total;
+        float4 s = make_float4(0, 0, 0, 0);
+        float x = 0, y = 0;
+        if (valid) {
+            while (i >= s_cnt[l + 1]) ++l;
+            s = sel[g.lv[l].selBase + (i - s_cnt[l])];
+            x = s.x; y = s.y;
+            if (l != 0) { x = __fmul_rn(x, g.lv[l].sf); y = __fmul_rn(y, g.lv[l].sf); }  // :1188-1190
+            mono = !(x >= lap0 && x <= lap1);                                              // :1192
+        }
+        // rank among mono keypoints in order
+        const unsigned bal = __ballot_sync(0xffffffffu, mono);
+        const int lane = tid & 31, warp = tid >> 5;
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        int before = s_run;
+        for (int w = 0; w < warp; ++w) before += s_warp[w];
+        const int monoRank = before + __popc(bal & ((1u << lane) - 1));
+        if (valid) {
+            const int out = mono ? monoRank : (total - 1 - (i - monoRank));  // lapping ones fill from the back
+            if (fits) {
+                orbx_keypoint k;
+                k.x = x; k.y = y;
+                k.size = (float)g.lv[l].patch_size;
+                k.angle = -1.f;
+                k.response = s.z;
+                k.octave = l;
+                k.class_id = -1;
+                kps[out] = k;
+            }
+            OrbxWork w;
+            w.level = l;
+            w.cx = __float2int_rn(s.x);
+            w.cy = __float2int_rn(s.y);
+            w.out = fits ? out : -1;
+            work[i] = w;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int t = 0;
+            for (int w = 0; w < 8; ++w) t += s_warp[w];
+            s_run += t;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        p.monoIdx[b] = s_run;
+        p.workCnt[b] = fits ? total : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: 7×7 Gaussian blur, σ=2, integer separable kernel, REFLECT_101 on the level
+// ------------------------------------------------------------------------------------------------
+#define BLUR_TW 64
+#define BLUR_TH 32
+struct BlurTile { short level, tx, ty, pad; };
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
+    return i;
+}
+
+__global__ void __launch_bounds__(256) k_blur(ExParams p, const BlurTile *tiles) {
+    __shared__ uint8_t s_in[BLUR_TH + 6][BLUR_TW + 8];
+    __shared__ uint16_t s_h[BLUR_TH + 6][BLUR_TW];
+    const OrbxGeom &g = *p.g;
+    const BlurTile T = tiles[blockIdx.x];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int l = T.level;
+    const OrbxLevel &LV = g.lv[l];
+    int pitch;
+    const uint8_t *src = level_ptr(p, g, l, b, pitch);
+    const int x0 = T.tx * BLUR_TW, y0 = T.ty * BLUR_TH;
+    const int w = LV.w, h = LV.h;
+    for (int i = tid; i < (BLUR_TH + 6) * (BLUR_TW + 6); i += 256) {
+        const int yy = i / (BLUR_TW + 6), xx = i - yy * (BLUR_TW + 6);
+        const int sy = reflect101(min(y0 + yy - 3, h + 2), h), sx = reflect101(min(x0 + xx - 3, w + 2), w);
+        s_in[yy][xx] = src[(long long)sy * pitch + sx];
+    }
+    __syncthreads();
+    for (int i = tid; i < (BLUR_TH + 6) * BLUR_TW; i += 256) {
+        const int yy = i / BLUR_TW, xx = i - yy * BLUR_TW;
+        const uint8_t *r = &s_in[yy][xx];
+        s_h[yy][xx] = (uint16_t)(18 * (r[0] + r[6]) + 34 * (r[1] + r[5]) + 48 * (r[2] + r[4]) + 56 * r[3]);
+    }
+    __syncthreads();
+    uint8_t *dst = p.blur + (long long)b * g.frameBytes + LV.off;
+    for (int i = tid; i < BLUR_TH * (BLUR_TW / 4); i += 256) {
+        const int yy = i / (BLUR_TW / 4), x4 = (i - yy * (BLUR_TW / 4)) * 4;
+        const int gy = y0 + yy, gx = x0 + x4;
+        if (gy >= h || gx >= w) continue;
+        uint32_t out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int xx = x4 + k;
+            const uint32_t v = 18u * (s_h[yy][xx] + s_h[yy + 6][xx]) + 34u * (s_h[yy + 1][xx] + s_h[yy + 5][xx]) +
+                               48u * (s_h[yy + 2][xx] + s_h[yy + 4][xx]) + 56u * s_h[yy + 3][xx];
+            out |= ((v + 32768u) >> 16) << (8 * k);
+        }
+        *reinterpret_cast<uint32_t *>(dst + (long long)gy * LV.pitch + gx) = out;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 + K6: orientation (IC_Angle :76-103, fastAtan2 A5) and rBRIEF (:107-146).  One warp per keypoint.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    const float scale = (float)(180.0 / 3.141592653589793238462643383279502884);
+    const float p1 = __fmul_rn(0.9997878412794807f, scale), p3 = __fmul_rn(-0.3258083974640975f, scale),
+                p5 = __fmul_rn(0.1555786518463281f, scale), p7 = __fmul_rn(-0.04432655554792128f, scale);
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float eps = (float)2.2204460492503131e-16;
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+template <int WPB>
+__global__ void __launch_bounds__(WPB * 32) k_orient_desc(ExParams p) {
+    const OrbxGeom &g = *p.g;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * WPB + warp, b = blockIdx.y;
+    if (i >= p.workCnt[b]) return;
+    const OrbxWork wk = p.work[(long long)b * g.selTotal + i];
+    if (wk.out < 0) return;
+    int pitch;
+    const uint8_t *img = level_ptr(p, g, wk.level, b, pitch);
+    // moments over the 31-row circular patch: lane = column u+15, lane 31 idle
+    const int u = lane - ORBX_HALF_PATCH;
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const uint8_t *c0 = img + (long long)wk.cy * pitch + wk.cx + u;
+        const int au = u < 0 ? -u : u;
+#pragma unroll 1
+        for (int v = -ORBX_HALF_PATCH; v <= ORBX_HALF_PATCH; ++v) {
+            const int av = v < 0 ? -v : v;
+            if (au <= g.umax[av]) {
+                const int val = c0[(long long)v * pitch];
+                m10 += u * val;
+                m01 += v * val;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+    }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+    // rBRIEF on the blurred level: lane computes descriptor byte `lane`
+    const float factorPI = (float)(3.141592653589793238462643383279502884 / 180.f);
+    const float rad = __fmul_rn(angle, factorPI);
+    const float ca = orbx_libm::cosf_glibc(rad), sa = orbx_libm::sinf_glibc(rad);
+    const OrbxLevel &LV = g.lv[wk.level];
+    const uint8_t *bl = p.blur + (long long)b * g.frameBytes + LV.off + (long long)wk.cy * LV.pitch + wk.cx;
+    const int bp = LV.pitch;
+    const int4 *pat4 = reinterpret_cast<const int4 *>(p.pattern) + lane * 2;
+    const int4 q0 = pat4[0], q1 = pat4[1];
+    const int words[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    int byte = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int wv = words[j];
+        const float x0 = (float)(signed char)(wv & 0xff), y0 = (float)(signed char)((wv >> 8) & 0xff);
+        const float x1 = (float)(signed char)((wv >> 16) & 0xff), y1 = (float)(signed char)((wv >> 24) & 0xff);
+        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, sa), __fmul_rn(y0, ca)));
+        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, ca), __fmul_rn(y0, sa)));
+        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, sa), __fmul_rn(y1, ca)));
+        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, ca), __fmul_rn(y1, sa)));
+        const int v0 = bl[(long long)r0 * bp + c0], v1 = bl[(long long)r1 * bp + c1];
+        byte |= (v0 < v1) << j;
+    }
+    // gather 4 bytes per lane group and store 8 words
+    uint32_t word = (uint32_t)byte;
+    word |= __shfl_down_sync(0xffffffffu, (uint32_t)byte, 1) << 8;
+    word |= __shfl_down_sync(0xffffffffu, (uint32_t)byte, 2) << 16;
+    word |= __shfl_down_sync(0xffffffffu, (uint32_t)byte, 3) << 24;
+    uint8_t *d = p.desc + ((long long)b * p.cap + wk.out) * 32;
+    if ((lane & 3) == 0) reinterpret_cast<uint32_t *>(d)[lane >> 2] = word;
+    if (lane == 0) p.kps[(long long)b * p.cap + wk.out].angle = angle;
+}
+
+// debug kernels ----------------------------------------------------------------------------------
+__global__ void k_dbg_sincos(const float *a, int n, float *s, float *c) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { s[i] = orbx_libm::sinf_glibc(a[i]); c[i] = orbx_libm::cosf_glibc(a[i]); }
+}
+__global__ void k_dbg_atan2(const float *y, const float *x, int n, float *o) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) o[i] = fast_atan2_deg(y[i], x[i]);
+}
+__global__ void k_dbg_sort(orbx_sort::elem_t *a, int n) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) orbx_sort::sort(a, n);
+}
+
+thread_local std::string tl_error;
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct orbx_extractor {
+    int device = 0;
+    int nfeatures = 0, nlevels = 0, iniTh = 0, minTh = 0;
+    double scaleFactor = 1.0;
+    int maxW = 0, maxH = 0, maxBatch = 0;
+    float sf[ORBX_MAX_LEVELS], inv[ORBX_MAX_LEVELS], sig2[ORBX_MAX_LEVELS], invsig2[ORBX_MAX_LEVELS];
+    int quota[ORBX_MAX_LEVELS];
+    int umax[ORBX_HALF_PATCH + 1];
+    cudaStream_t stream = nullptr;
+    std::string err;
+    long long launches = 0;
+
+    // geometry of the current image size
+    OrbxGeom geom;
+    int curRows = -1, curCols = -1;
+    int curLap0 = 0, curLap1 = 0;
+    std::vector<int> curRects;
+    bool geomDirty = true;
+    std::vector<OrbxCell> h_cells;
+    std::vector<BlurTile> h_tiles;
+    int maxSlotCap = 0, nodeCapMax = 0, maxCellsLevel = 0;
+    int lastBatch = 0;
+    bool lastIn0Internal = true;
+
+    // device buffers (sized for maxW × maxH × maxBatch at create)
+    OrbxGeom *d_geom = nullptr;
+    OrbxCell *d_cells = nullptr; size_t cellsCap = 0;
+    BlurTile *d_tiles = nullptr; size_t tilesCap = 0;
+    int2 *d_tabX = nullptr, *d_tabY = nullptr; size_t tabXCap = 0, tabYCap = 0;
+    int *d_tabXOff = nullptr, *d_tabYOff = nullptr;
+    int8_t *d_pattern = nullptr;
+    uint8_t *d_pyr = nullptr, *d_blur = nullptr; size_t pyrCap = 0;
+    uint32_t *d_slots = nullptr; uint32_t *d_ptNode = nullptr; float2 *d_ptXY = nullptr; size_t slotsCap = 0;
+    int *d_cellCnt = nullptr; size_t cellCntCap = 0;
+    float4 *d_sel = nullptr; OrbxWork *d_work = nullptr; size_t selCap = 0;
+    int *d_selCnt = nullptr, *d_workCnt = nullptr;
+    // staging for the host-buffer entry points
+    orbx_keypoint *d_kps = nullptr; uint8_t *d_desc = nullptr; size_t outCap = 0;
+    int *d_nOut = nullptr, *d_mono = nullptr;
+    int *h_nOut = nullptr, *h_mono = nullptr;  // pinned
+};
+
+namespace {
+
+#define CUDA_TRY(ex, call)                                                                              \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            (ex)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                             \
+            return ORBX_ERR_CUDA;                                                                       \
+        }                                                                                               \
+    } while (0)
+
+inline int cv_round_f(float v) { return (int)lrintf(v); }
+
+template <class T>
+int ensure(orbx_extractor *ex, T *&ptr, size_t &cap, size_t need) {
+    if (need <= cap && ptr) return ORBX_OK;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+    CUDA_TRY(ex, cudaMalloc((void **)&ptr, need * sizeof(T)));
+    cap = need;
+    return ORBX_OK;
+}
+
+// Level sizes, cell grid and quadtree roots for a rows×cols image — the host restatement of
+// :1213-1214 (level sizes), :789-822 (cell grid) and :558-560 (roots), fp32 where the reference is.
+int build_geometry(orbx_extractor *ex, int rows, int cols) {
+    OrbxGeom &G = ex->geom;
+    memset(&G, 0, sizeof(G));
+    G.nlevels = ex->nlevels; G.rows = rows; G.cols = cols;
+    G.iniTh = ex->iniTh; G.minTh = ex->minTh; G.lowTh = std::min(ex->iniTh, ex->minTh);
+    memcpy(G.umax, ex->umax, sizeof(G.umax));
+    ex->h_cells.clear();
+    ex->h_tiles.clear();
+    long long off = 0, slot = 0;
+    int cellBase = 0, selBase = 0;
+    ex->maxSlotCap = 1; ex->nodeCapMax = 8; ex->maxCellsLevel = 1;
+    G.maxCw = 7; G.maxCh = 7;
+    for (int l = 0; l < ex->nlevels; ++l) {
+        OrbxLevel &V = G.lv[l];
+        V.sf = ex->sf[l]; V.inv = ex->inv[l]; V.quota = ex->quota[l];
+        V.w = cv_round_f((float)cols * V.inv);
+        V.h = cv_round_f((float)rows * V.inv);
+        if (V.w <= 2 * ORBX_BORDER + 6 || V.h <= 2 * ORBX_BORDER + 6 || V.w > 32000 || V.h > 32000) {
+            ex->err = "image too small (or too large) for the pyramid: level " + std::to_string(l) + " is " +
+                      std::to_string(V.w) + "x" + std::to_string(V.h);
+            return ORBX_ERR_GEOMETRY;
+        }
+        V.pitch = orbx_align_up(V.w, 128);
+        V.off = off;
+        off += orbx_align_up_ll((long long)V.pitch * V.h, 256);
+        V.patch_size = (int)((float)ORBX_PATCH * V.sf);
+        V.maxBX = V.w - ORBX_EDGE + 3;
+        V.maxBY = V.h - ORBX_EDGE + 3;
+        const float width = (float)(V.maxBX - ORBX_BORDER), height = (float)(V.maxBY - ORBX_BORDER);
+        V.nCols = (int)(width / 35.f);
+        V.nRows = (int)(height / 35.f);
+        V.wCell = V.nCols > 0 ? (int)ceilf(width / (float)V.nCols) : 0;
+        V.hCell = V.nRows > 0 ? (int)ceilf(height / (float)V.nRows) : 0;
+        // rows/cols that survive the skip tests (:810, :819; quirk Q2) form a prefix
+        V.nRowsOK = 0;
+        for (int i = 0; i < V.nRows; ++i)
+            if (!((float)(ORBX_BORDER + i * V.hCell) >= (float)(V.maxBY - 3))) V.nRowsOK = i + 1; else break;
+        V.nColsOK = 0;
+        for (int j = 0; j < V.nCols; ++j)
+            if (!((float)(ORBX_BORDER + j * V.wCell) >= (float)(V.maxBX - 6))) V.nColsOK = j + 1; else break;
+        V.cellBase = cellBase;
+        V.nCells = V.nRowsOK * V.nColsOK;
+        V.slotCap = ((V.wCell + 1) / 2) * ((V.hCell + 1) / 2);  // strict 3×3 NMS ⇒ ≤ ⌈w/2⌉·⌈h/2⌉ survivors
+        V.slotBase = slot;
+        for (int i = 0; i < V.nRowsOK; ++i)
+            for (int j = 0; j < V.nColsOK; ++j) {
+                OrbxCell c;
+                const int iniX = ORBX_BORDER + j * V.wCell, iniY = ORBX_BORDER + i * V.hCell;
+                const int maxX = std::min(iniX + V.wCell + 6, V.maxBX), maxY = std::min(iniY + V.hCell + 6, V.maxBY);
+                c.level = (short)l; c.x0 = (short)iniX; c.y0 = (short)iniY;
+                c.cw = (short)(maxX - iniX); c.ch = (short)(maxY - iniY);
+                c.cx = (short)j; c.cy = (short)i;
+                c.seq = i * V.nColsOK + j;
+                c.slot = slot;
+                slot += V.slotCap;
+                ex->h_cells.push_back(c);
+                G.maxCw = std::max(G.maxCw, (int)c.cw);
+                G.maxCh = std::max(G.maxCh, (int)c.ch);
+            }
+        if (V.wCell + 6 > 255 || V.hCell + 6 > 255) { ex->err = "cell larger than 255 px"; return ORBX_ERR_GEOMETRY; }
+        cellBase += V.nCells;
+        ex->maxSlotCap = std::max(ex->maxSlotCap, V.slotCap);
+        ex->maxCellsLevel = std::max(ex->maxCellsLevel, V.nCells);
+        // quadtree roots (:558-560)
+        const int rw = V.maxBX - ORBX_BORDER, rh = V.maxBY - ORBX_BORDER;
+        V.nIni = (int)roundf((float)rw / (float)rh);
+        if (V.nIni < 1) { ex->err = "image too tall: quadtree would have no root node (reference faults)"; return ORBX_ERR_GEOMETRY; }
+        V.hX = (float)rw / (float)V.nIni;
+        V.nodeCap = std::max(4 * V.nIni, V.quota + 4) + 4;
+        ex->nodeCapMax = std::max(ex->nodeCapMax, V.nodeCap);
+        V.selBase = selBase;
+        V.selCap = V.nodeCap;
+        selBase += V.selCap;
+        for (int ty = 0; ty < (V.h + BLUR_TH - 1) / BLUR_TH; ++ty)
+            for (int tx = 0; tx < (V.w + BLUR_TW - 1) / BLUR_TW; ++tx) {
+                BlurTile t; t.level = (short)l; t.tx = (short)tx; t.ty = (short)ty; t.pad = 0;
+                ex->h_tiles.push_back(t);
+            }
+    }
+    G.frameBytes = off;
+    G.slotsTotal = slot;
+    G.nCellsTotal = cellBase;
+    G.selTotal = selBase;
+    return ORBX_OK;
+}
+
+int upload_tables(orbx_extractor *ex) {
+    OrbxGeom &G = ex->geom;
+    // resize tables: identical arithmetic to cv::resize's coefficient set-up
+    std::vector<int2> tx, ty;
+    std::vector<int> txo(ORBX_MAX_LEVELS, 0), tyo(ORBX_MAX_LEVELS, 0);
+    for (int l = 1; l < G.nlevels; ++l) {
+        const int sw = G.lv[l - 1].w, sh = G.lv[l - 1].h, dw = G.lv[l].w, dh = G.lv[l].h;
+        txo[l] = (int)tx.size();
+        tyo[l] = (int)ty.size();
+        const double kx = (double)sw / dw, ky = (double)sh / dh;
+        for (int d = 0; d < dw; ++d) {
+            float f = (float)((d + 0.5) * kx - 0.5);
+            int s = (int)floorf(f);
+            f -= s;
+            if (s < 0) { s = 0; f = 0.f; }
+            if (s >= sw - 1) { s = sw - 1; f = 0.f; }
+            const int a0 = (short)cv_round_f((1.f - f) * 2048.f), a1 = (short)cv_round_f(f * 2048.f);
+            tx.push_back(make_int2(s, (a0 & 0xffff) | (a1 << 16)));
+        }
+        for (int pad = 0; pad < 4; ++pad) tx.push_back(make_int2(0, 0));  // 4-pixel threads may peek past the end
+        for (int d = 0; d < dh; ++d) {
+            float f = (float)((d + 0.5) * ky - 0.5);
+            int s = (int)floorf(f);
+            f -= s;
+            const int b0 = (short)cv_round_f((1.f - f) * 2048.f), b1 = (short)cv_round_f(f * 2048.f);
+            ty.push_back(make_int2(s, (b0 & 0xffff) | (b1 << 16)));
+        }
+    }
+    int rc;
+    if ((rc = ensure(ex, ex->d_tabX, ex->tabXCap, std::max<size_t>(tx.size(), 1)))) return rc;
+    if ((rc = ensure(ex, ex->d_tabY, ex->tabYCap, std::max<size_t>(ty.size(), 1)))) return rc;
+    if ((rc = ensure(ex, ex->d_cells, ex->cellsCap, std::max<size_t>(ex->h_cells.size(), 1)))) return rc;
+    if ((rc = ensure(ex, ex->d_tiles, ex->tilesCap, std::max<size_t>(ex->h_tiles.size(), 1)))) return rc;
+    cudaStream_t s = ex->stream;
+    if (!tx.empty()) CUDA_TRY(ex, cudaMemcpyAsync(ex->d_tabX, tx.data(), tx.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
+    if (!ty.empty()) CUDA_TRY(ex, cudaMemcpyAsync(ex->d_tabY, ty.data(), ty.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(ex, cudaMemcpyAsync(ex->d_tabXOff, txo.data(), ORBX_MAX_LEVELS * sizeof(int), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(ex, cudaMemcpyAsync(ex->d_tabYOff, tyo.data(), ORBX_MAX_LEVELS * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (!ex->h_cells.empty())
+        CUDA_TRY(ex, cudaMemcpyAsync(ex->d_cells, ex->h_cells.data(), ex->h_cells.size() * sizeof(OrbxCell), cudaMemcpyHostToDevice, s));
+    if (!ex->h_tiles.empty())
+        CUDA_TRY(ex, cudaMemcpyAsync(ex->d_tiles, ex->h_tiles.data(), ex->h_tiles.size() * sizeof(BlurTile), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(ex, cudaStreamSynchronize(s));  // the host vectors above are about to go out of scope
+    return ORBX_OK;
+}
+
+int ensure_buffers(orbx_extractor *ex, int batch) {
+    const OrbxGeom &G = ex->geom;
+    int rc;
+    const size_t B = (size_t)batch;
+    size_t pyrNeed = B * (size_t)G.frameBytes;
+    if (pyrNeed > ex->pyrCap || !ex->d_pyr) {
+        if (ex->d_pyr) cudaFree(ex->d_pyr);
+        if (ex->d_blur) cudaFree(ex->d_blur);
+        ex->d_pyr = ex->d_blur = nullptr; ex->pyrCap = 0;
+        CUDA_TRY(ex, cudaMalloc((void **)&ex->d_pyr, pyrNeed));
+        CUDA_TRY(ex, cudaMalloc((void **)&ex->d_blur, pyrNeed));
+        ex->pyrCap = pyrNeed;
+    }
+    size_t slotsNeed = B * (size_t)G.slotsTotal;
+    if (slotsNeed > ex->slotsCap || !ex->d_slots) {
+        if (ex->d_slots) cudaFree(ex->d_slots);
+        if (ex->d_ptNode) cudaFree(ex->d_ptNode);
+        if (ex->d_ptXY) cudaFree(ex->d_ptXY);
+        ex->d_slots = ex->d_ptNode = nullptr; ex->d_ptXY = nullptr; ex->slotsCap = 0;
+        CUDA_TRY(ex, cudaMalloc((void **)&ex->d_slots, slotsNeed * sizeof(uint32_t)));
+        CUDA_TRY(ex, cudaMalloc((void **)&ex->d_ptNode, slotsNeed * sizeof(uint32_t)));
+        CUDA_TRY(ex, cudaMalloc((void **)&ex->d_ptXY, slotsNeed * sizeof(float2)));
+        ex->slotsCap = slotsNeed;
+    }
+    if ((rc = ensure(ex, ex->d_cellCnt, ex->cellCntCap, B * (size_t)std::max(G.nCellsTotal, 1)))) return rc;
+    size_t selNeed = B * (size_t)std::max(G.selTotal, 1);
+    if (selNeed > ex->selCap || !ex->d_sel) {
+        if (ex->d_sel) cudaFree(ex->d_sel);
+        if (ex->d_work) cudaFree(ex->d_work);
+        ex->d_sel = nullptr; ex->d_work = nullptr; ex->selCap = 0;
+        CUDA_TRY(ex, cudaMalloc((void **)&ex->d_sel, selNeed * sizeof(float4)));
+        CUDA_TRY(ex, cudaMalloc((void **)&ex->d_work, selNeed * sizeof(OrbxWork)));
+        ex->selCap = selNeed;
+    }
+    return ORBX_OK;
+}
+
+int prepare(orbx_extractor *ex, int rows, int cols, const int32_t *rects, int nRects, int lap0, int lap1, int batch) {
+    if (rows > ex->maxH || cols > ex->maxW) {
+        ex->err = "image larger than the max_width × max_height this handle was created for";
+        return ORBX_ERR_ARG;
+    }
+    if (nRects < 0 || nRects > ORBX_MAX_RECTS || (nRects > 0 && !rects)) {
+        ex->err = "n_rects out of range (max " + std::to_string(ORBX_MAX_RECTS) + ")";
+        return ORBX_ERR_ARG;
+    }
+    CUDA_TRY(ex, cudaSetDevice(ex->device));
+    int rc;
+    bool sizeChanged = rows != ex->curRows || cols != ex->curCols;
+    if (sizeChanged) {
+        if ((rc = build_geometry(ex, rows, cols))) { ex->curRows = ex->curCols = -1; return rc; }
+        if ((rc = upload_tables(ex))) { ex->curRows = ex->curCols = -1; return rc; }
+        ex->curRows = rows; ex->curCols = cols;
+        ex->geomDirty = true;
+    }
+    std::vector<int> r(rects ? rects : nullptr, rects ? rects + 4 * nRects : nullptr);
+    if (ex->geomDirty || lap0 != ex->curLap0 || lap1 != ex->curLap1 || r != ex->curRects) {
+        ex->geom.lap0 = lap0; ex->geom.lap1 = lap1; ex->geom.nRects = nRects;
+        for (int i = 0; i < 4 * nRects; ++i) ex->geom.rects[i] = rects[i];
+        // the previous batch may still be reading d_geom
+        CUDA_TRY(ex, cudaStreamSynchronize(ex->stream));
+        CUDA_TRY(ex, cudaMemcpyAsync(ex->d_geom, &ex->geom, sizeof(OrbxGeom), cudaMemcpyHostToDevice, ex->stream));
+        CUDA_TRY(ex, cudaStreamSynchronize(ex->stream));
+        ex->curLap0 = lap0; ex->curLap1 = lap1; ex->curRects = r;
+        ex->geomDirty = false;
+    }
+    return ensure_buffers(ex, batch);
+}
+
+// enqueue the whole pipeline for `batch` frames whose level 0 lives at (in0, stride, pitch)
+int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, int in0Pitch, int batch,
+                 orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int *d_nOut, int *d_mono) {
+    const OrbxGeom &G = ex->geom;
+    ExParams P;
+    P.g = ex->d_geom;
+    P.in0 = in0; P.in0Stride = in0Stride; P.in0Pitch = in0Pitch;
+    P.pyr = ex->d_pyr; P.blur = ex->d_blur;
+    P.cells = ex->d_cells;
+    P.tabX = ex->d_tabX; P.tabY = ex->d_tabY; P.tabXOff = ex->d_tabXOff; P.tabYOff = ex->d_tabYOff;
+    P.slots = ex->d_slots; P.cellCnt = ex->d_cellCnt; P.ptXY = ex->d_ptXY; P.ptNode = ex->d_ptNode;
+    P.sel = ex->d_sel; P.selCnt = ex->d_selCnt; P.work = ex->d_work; P.workCnt = ex->d_workCnt;
+    P.kps = d_kps; P.desc = d_desc; P.cap = cap; P.nOut = d_nOut; P.monoIdx = d_mono;
+    P.pattern = ex->d_pattern;
+    cudaStream_t s = ex->stream;
+    // K1
+    for (int l = 1; l < G.nlevels; ++l) {
+        dim3 blk(32, 8), grd((G.lv[l].w + 127) / 128, (G.lv[l].h + 7) / 8, batch);
+        k_pyr_level<<<grd, blk, 0, s>>>(P, l);
+        ++ex->launches;
+    }
+    // K2
+    {
+        const int WPB = 4;
+        const FastSmem L = fast_smem_layout(G.maxCw, G.maxCh, ex->maxSlotCap);
+        const size_t smem = (size_t)L.total * WPB;
+        if (smem > 48 * 1024) {
+            CUDA_TRY(ex, cudaFuncSetAttribute(k_fast_cells<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+        dim3 grd((G.nCellsTotal + WPB - 1) / WPB, batch);
+        if (G.nCellsTotal > 0) {
+            k_fast_cells<WPB><<<grd, WPB * 32, smem, s>>>(P, ex->maxSlotCap);
+            ++ex->launches;
+        }
+    }
+    // K3
+    {
+        const QtSmem L = qt_smem_layout(ex->nodeCapMax, ex->maxCellsLevel);
+        if (L.total > 200 * 1024) { ex->err = "nfeatures too large for the quadtree kernel's shared memory"; return ORBX_ERR_ARG; }
+        if (L.total > 48 * 1024)
+            CUDA_TRY(ex, cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        dim3 grd(G.nlevels, batch);
+        k_quadtree<<<grd, QT_THREADS, L.total, s>>>(P, ex->nodeCapMax, ex->maxCellsLevel);
+        ++ex->launches;
+    }
+    // K7
+    k_assemble<<<batch, 256, 0, s>>>(P);
+    ++ex->launches;
+    // K5
+    {
+        dim3 grd((unsigned)ex->h_tiles.size(), batch);
+        k_blur<<<grd, 256, 0, s>>>(P, ex->d_tiles);
+        ++ex->launches;
+    }
+    // K4 + K6
+    {
+        const int WPB = 8;
+        dim3 grd((G.selTotal + WPB - 1) / WPB, batch);
+        k_orient_desc<WPB><<<grd, WPB * 32, 0, s>>>(P);
+        ++ex->launches;
+    }
+    CUDA_TRY(ex, cudaGetLastError());
+    ex->lastBatch = batch;
+    return ORBX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int orbx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char *orbx_last_error(const orbx_extractor *ex) { return ex ? ex->err.c_str() : tl_error.c_str(); }
+
+orbx_extractor *orbx_create(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th, int device,
+                            int max_width, int max_height, int max_batch) {
+    if (nlevels < 1 || nlevels > ORBX_MAX_LEVELS || nfeatures < 0 || !(scale_factor > 1.0f) || ini_th < 0 ||
+        ini_th > 255 || min_th < 0 || min_th > 255 || max_width <= 0 || max_height <= 0 || max_batch <= 0) {
+        tl_error = "orbx_create: bad parameter";
+        return nullptr;
+    }
+    int ndev = orbx_device_count();
+    if (device < 0 || device >= ndev) {
+        tl_error = "orbx_create: no such CUDA device (liborbx has no CPU fallback)";
+        return nullptr;
+    }
+    orbx_extractor *ex = new orbx_extractor;
+    ex->device = device; ex->nfeatures = nfeatures; ex->nlevels = nlevels; ex->iniTh = ini_th; ex->minTh = min_th;
+    ex->scaleFactor = scale_factor;
+    ex->maxW = max_width; ex->maxH = max_height; ex->maxBatch = max_batch;
+    // ctor maths of the reference (:415-447)
+    ex->sf[0] = 1.f; ex->sig2[0] = 1.f;
+    for (int i = 1; i < nlevels; ++i) {
+        ex->sf[i] = (float)(ex->sf[i - 1] * ex->scaleFactor);
+        ex->sig2[i] = ex->sf[i] * ex->sf[i];
+    }
+    for (int i = 0; i < nlevels; ++i) { ex->inv[i] = 1.0f / ex->sf[i]; ex->invsig2[i] = 1.0f / ex->sig2[i]; }
+    float factor = (float)(1.0f / ex->scaleFactor);
+    float want = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
+    int sum = 0;
+    for (int l = 0; l < nlevels - 1; ++l) {
+        ex->quota[l] = cv_round_f(want);
+        sum += ex->quota[l];
+        want *= factor;
+    }
+    ex->quota[nlevels - 1] = std::max(nfeatures - sum, 0);
+    // umax (:453-468)
+    {
+        int v, v0;
+        const int vmax = (int)floorf(ORBX_HALF_PATCH * sqrtf(2.f) / 2 + 1);
+        const int vmin = (int)ceilf(ORBX_HALF_PATCH * sqrtf(2.f) / 2);
+        const double hp2 = ORBX_HALF_PATCH * ORBX_HALF_PATCH;
+        for (v = 0; v <= vmax; ++v) ex->umax[v] = (int)lrint(sqrt(hp2 - v * v));
+        for (v = ORBX_HALF_PATCH, v0 = 0; v >= vmin; --v) {
+            while (ex->umax[v0] == ex->umax[v0 + 1]) ++v0;
+            ex->umax[v] = v0;
+            ++v0;
+        }
+    }
+    auto fail = [&](const std::string &m) { tl_error = m; orbx_destroy(ex); return (orbx_extractor *)nullptr; };
+#define CREATE_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+    CREATE_TRY(cudaSetDevice(device));
+    CREATE_TRY(cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaMalloc((void **)&ex->d_geom, sizeof(OrbxGeom)));
+    CREATE_TRY(cudaMalloc((void **)&ex->d_tabXOff, ORBX_MAX_LEVELS * sizeof(int)));
+    CREATE_TRY(cudaMalloc((void **)&ex->d_tabYOff, ORBX_MAX_LEVELS * sizeof(int)));
+    CREATE_TRY(cudaMalloc((void **)&ex->d_pattern, 1024));
+    CREATE_TRY(cudaMemcpy(ex->d_pattern, h_pattern, 1024, cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMalloc((void **)&ex->d_selCnt, (size_t)max_batch * ORBX_MAX_LEVELS * sizeof(int)));
+    CREATE_TRY(cudaMalloc((void **)&ex->d_workCnt, (size_t)max_batch * sizeof(int)));
+    CREATE_TRY(cudaMalloc((void **)&ex->d_nOut, (size_t)max_batch * sizeof(int)));
+    CREATE_TRY(cudaMalloc((void **)&ex->d_mono, (size_t)max_batch * sizeof(int)));
+    CREATE_TRY(cudaHostAlloc((void **)&ex->h_nOut, (size_t)max_batch * sizeof(int), cudaHostAllocDefault));
+    CREATE_TRY(cudaHostAlloc((void **)&ex->h_mono, (size_t)max_batch * sizeof(int), cudaHostAllocDefault));
+#undef CREATE_TRY
+    // size all image-dependent buffers for the largest image now, so the hot path never allocates
+    int rc = build_geometry(ex, max_height, max_width);
+    if (rc == ORBX_OK) rc = upload_tables(ex);
+    if (rc == ORBX_OK) rc = ensure_buffers(ex, max_batch);
+    if (rc != ORBX_OK) return fail("orbx_create: " + ex->err);
+    ex->curRows = max_height; ex->curCols = max_width; ex->geomDirty = true;
+    return ex;
+}
+
+void orbx_destroy(orbx_extractor *ex) {
+    if (!ex) return;
+    cudaSetDevice(ex->device);
+    if (ex->stream) cudaStreamSynchronize(ex->stream);
+    void *ptrs[] = {ex->d_geom, ex->d_cells, ex->d_tiles, ex->d_tabX, ex->d_tabY, ex->d_tabXOff, ex->d_tabYOff,
+                    ex->d_pattern, ex->d_pyr, ex->d_blur, ex->d_slots, ex->d_ptNode, ex->d_ptXY, ex->d_cellCnt,
+                    ex->d_sel, ex->d_work, ex->d_selCnt, ex->d_workCnt, ex->d_kps, ex->d_desc, ex->d_nOut, ex->d_mono};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (ex->h_nOut) cudaFreeHost(ex->h_nOut);
+    if (ex->h_mono) cudaFreeHost(ex->h_mono);
+    if (ex->stream) cudaStreamDestroy(ex->stream);
+    delete ex;
+}
+
+int orbx_params(const orbx_extractor *ex, float *sf, float *inv, float *sig2, float *invsig2, int32_t *quota) {
+    if (!ex) return ORBX_ERR_ARG;
+    for (int i = 0; i < ex->nlevels; ++i) {
+        if (sf) sf[i] = ex->sf[i];
+        if (inv) inv[i] = ex->inv[i];
+        if (sig2) sig2[i] = ex->sig2[i];
+        if (invsig2) invsig2[i] = ex->invsig2[i];
+        if (quota) quota[i] = ex->quota[i];
+    }
+    return ORBX_OK;
+}
+
+int orbx_extract_batch_device(orbx_extractor *ex, const uint8_t *d_images, size_t frame_stride, int batch, int rows,
+                              int cols, size_t step, const int32_t *rects, int n_rects, int lap0, int lap1,
+                              orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int32_t *d_n_out, int32_t *d_mono) {
+    if (!ex) return ORBX_ERR_ARG;
+    if (!d_images || rows <= 0 || cols <= 0 || batch <= 0) { ex->err = "empty image"; return ORBX_EMPTY; }
+    if (batch > ex->maxBatch || !d_kps || !d_desc || !d_n_out || !d_mono || cap <= 0) {
+        ex->err = "orbx_extract_batch_device: bad argument (batch > max_batch, null output or cap <= 0)";
+        return ORBX_ERR_ARG;
+    }
+    int rc = prepare(ex, rows, cols, rects, n_rects, lap0, lap1, batch);
+    if (rc) return rc;
+    ex->lastIn0Internal = false;
+    return run_pipeline(ex, d_images, (long long)frame_stride, (int)step, batch, d_kps, d_desc, cap, d_n_out, d_mono);
+}
+
+int orbx_extract_batch(orbx_extractor *ex, const uint8_t *const *images, int batch, int rows, int cols, size_t step,
+                       const int32_t *rects, int n_rects, int lap0, int lap1, orbx_keypoint *kps, uint8_t *desc,
+                       int cap, int32_t *n_out, int32_t *mono_index) {
+    if (!ex) return ORBX_ERR_ARG;
+    if (!images || rows <= 0 || cols <= 0 || batch <= 0) { ex->err = "empty image"; return ORBX_EMPTY; }
+    for (int b = 0; b < batch; ++b) if (!images[b]) { ex->err = "empty image"; return ORBX_EMPTY; }
+    if (!kps || !desc || !n_out || !mono_index || cap <= 0) { ex->err = "orbx_extract_batch: null output or cap <= 0"; return ORBX_ERR_ARG; }
+    int result = ORBX_OK;
+    for (int b0 = 0; b0 < batch; b0 += ex->maxBatch) {
+        const int nb = std::min(ex->maxBatch, batch - b0);
+        int rc = prepare(ex, rows, cols, rects, n_rects, lap0, lap1, nb);
+        if (rc) return rc;
+        const OrbxGeom &G = ex->geom;
+        // staging for outputs
+        const size_t need = (size_t)nb * cap;
+        if (need > ex->outCap || !ex->d_kps) {
+            if (ex->d_kps) cudaFree(ex->d_kps);
+            if (ex->d_desc) cudaFree(ex->d_desc);
+            ex->d_kps = nullptr; ex->d_desc = nullptr; ex->outCap = 0;
+            CUDA_TRY(ex, cudaMalloc((void **)&ex->d_kps, need * sizeof(orbx_keypoint)));
+            CUDA_TRY(ex, cudaMalloc((void **)&ex->d_desc, need * 32));
+            ex->outCap = need;
+        }
+        cudaStream_t s = ex->stream;
+        // H2D straight into the level-0 planes of the internal pyramid
+        bool contiguous = true;
+        for (int b = 1; b < nb && contiguous; ++b)
+            contiguous = images[b0 + b] == images[b0] + (size_t)b * rows * step;
+        if (contiguous && step == (size_t)cols && G.lv[0].pitch == cols) {
+            // frames are back to back and rows are dense: one strided copy for the whole batch
+            CUDA_TRY(ex, cudaMemcpy2DAsync(ex->d_pyr + G.lv[0].off, (size_t)G.frameBytes, images[b0], (size_t)rows * cols,
+                                           (size_t)rows * cols, nb, cudaMemcpyHostToDevice, s));
+        } else {
+            for (int b = 0; b < nb; ++b)
+                CUDA_TRY(ex, cudaMemcpy2DAsync(ex->d_pyr + (size_t)b * G.frameBytes + G.lv[0].off, G.lv[0].pitch, images[b0 + b], step,
+                                               cols, rows, cudaMemcpyHostToDevice, s));
+        }
+        ex->lastIn0Internal = true;
+        rc = run_pipeline(ex, ex->d_pyr + G.lv[0].off, G.frameBytes, G.lv[0].pitch, nb, ex->d_kps, ex->d_desc, cap, ex->d_nOut, ex->d_mono);
+        if (rc) return rc;
+        CUDA_TRY(ex, cudaMemcpyAsync(ex->h_nOut, ex->d_nOut, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(ex, cudaMemcpyAsync(ex->h_mono, ex->d_mono, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(ex, cudaStreamSynchronize(s));
+        int maxN = 0;
+        for (int b = 0; b < nb; ++b) {
+            n_out[b0 + b] = ex->h_nOut[b];
+            mono_index[b0 + b] = ex->h_mono[b];
+            if (ex->h_nOut[b] > cap) result = ORBX_ERR_CAPACITY;
+            maxN = std::max(maxN, std::min(ex->h_nOut[b], cap));
+        }
+        if (maxN > 0) {
+            // one strided copy per array: rows of maxN records out of the cap-strided device arrays
+            CUDA_TRY(ex, cudaMemcpy2DAsync(kps + (size_t)b0 * cap, (size_t)cap * sizeof(orbx_keypoint), ex->d_kps,
+                                           (size_t)cap * sizeof(orbx_keypoint), (size_t)maxN * sizeof(orbx_keypoint), nb,
+                                           cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(ex, cudaMemcpy2DAsync(desc + (size_t)b0 * cap * 32, (size_t)cap * 32, ex->d_desc, (size_t)cap * 32,
+                                           (size_t)maxN * 32, nb, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(ex, cudaStreamSynchronize(s));
+        }
+    }
+    if (result == ORBX_ERR_CAPACITY) ex->err = "keypoint capacity too small for at least one frame (see n_out)";
+    return result;
+}
+
+int orbx_extract(orbx_extractor *ex, const uint8_t *image, int rows, int cols, size_t step, const int32_t *rects,
+                 int n_rects, int lap0, int lap1, orbx_keypoint *kps, uint8_t *desc, int cap, int *n_out,
+                 int *mono_index) {
+    if (!ex) return ORBX_ERR_ARG;
+    if (n_out) *n_out = 0;
+    if (mono_index) *mono_index = -1;
+    if (!image || rows <= 0 || cols <= 0) { ex->err = "empty image"; return ORBX_EMPTY; }
+    int32_t n = 0, m = 0;
+    const uint8_t *imgs[1] = {image};
+    int rc = orbx_extract_batch(ex, imgs, 1, rows, cols, step, rects, n_rects, lap0, lap1, kps, desc, cap, &n, &m);
+    if (n_out) *n_out = n;
+    if (mono_index) *mono_index = m;
+    return rc;
+}
+
+int orbx_sync(orbx_extractor *ex) {
+    if (!ex) return ORBX_ERR_ARG;
+    CUDA_TRY(ex, cudaStreamSynchronize(ex->stream));
+    return ORBX_OK;
+}
+void *orbx_stream(orbx_extractor *ex) { return ex ? (void *)ex->stream : nullptr; }
+long long orbx_launch_count(const orbx_extractor *ex) { return ex ? ex->launches : 0; }
+
+int orbx_level_size(const orbx_extractor *ex, int level, int *w, int *h) {
+    if (!ex || level < 0 || level >= ex->nlevels || ex->curRows < 0) return ORBX_ERR_ARG;
+    if (w) *w = ex->geom.lv[level].w;
+    if (h) *h = ex->geom.lv[level].h;
+    return ORBX_OK;
+}
+
+static int copy_plane(orbx_extractor *ex, const uint8_t *d_src, int pitch, int w, int h, int padded, uint8_t *dst,
+                      size_t dst_step) {
+    CUDA_TRY(ex, cudaStreamSynchronize(ex->stream));
+    if (!padded) {
+        CUDA_TRY(ex, cudaMemcpy2D(dst, dst_step, d_src, pitch, w, h, cudaMemcpyDeviceToHost));
+        return ORBX_OK;
+    }
+    // copy the level into the middle of the padded plane, then reflect (BORDER_REFLECT_101, :1224-1230)
+    const int E = ORBX_EDGE;
+    CUDA_TRY(ex, cudaMemcpy2D(dst + (size_t)E * dst_step + E, dst_step, d_src, pitch, w, h, cudaMemcpyDeviceToHost));
+    auto refl = [](int i, int n) { if (n == 1) return 0; while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i; return i; };
+    for (int y = 0; y < h; ++y) {
+        uint8_t *row = dst + (size_t)(y + E) * dst_step + E;
+        for (int x = -E; x < 0; ++x) row[x] = row[refl(x, w)];
+        for (int x = w; x < w + E; ++x) row[x] = row[refl(x, w)];
+    }
+    for (int y = -E; y < h + E; ++y) {
+        if (y >= 0 && y < h) continue;
+        memcpy(dst + (size_t)(y + E) * dst_step, dst + (size_t)(refl(y, h) + E) * dst_step, w + 2 * E);
+    }
+    return ORBX_OK;
+}
+
+int orbx_get_pyramid(orbx_extractor *ex, int frame, int level, int padded, uint8_t *dst, size_t dst_step) {
+    if (!ex || !dst || level < 0 || level >= ex->nlevels || frame < 0 || frame >= ex->lastBatch) return ORBX_ERR_ARG;
+    const OrbxGeom &G = ex->geom;
+    if (level == 0 && !ex->lastIn0Internal) { ex->err = "level 0 of a device-resident batch is the caller's own buffer"; return ORBX_ERR_ARG; }
+    cudaSetDevice(ex->device);
+    return copy_plane(ex, ex->d_pyr + (size_t)frame * G.frameBytes + G.lv[level].off, G.lv[level].pitch, G.lv[level].w,
+                      G.lv[level].h, padded, dst, dst_step);
+}
+
+int orbx_get_blurred(orbx_extractor *ex, int frame, int level, uint8_t *dst, size_t dst_step) {
+    if (!ex || !dst || level < 0 || level >= ex->nlevels || frame < 0 || frame >= ex->lastBatch) return ORBX_ERR_ARG;
+    const OrbxGeom &G = ex->geom;
+    cudaSetDevice(ex->device);
+    return copy_plane(ex, ex->d_blur + (size_t)frame * G.frameBytes + G.lv[level].off, G.lv[level].pitch, G.lv[level].w,
+                      G.lv[level].h, 0, dst, dst_step);
+}
+
+int orbx_get_candidates(orbx_extractor *ex, int frame, int level, orbx_keypoint *out, int cap) {
+    if (!ex || level < 0 || level >= ex->nlevels || frame < 0 || frame >= ex->lastBatch) return ORBX_ERR_ARG;
+    const OrbxGeom &G = ex->geom;
+    const OrbxLevel &V = G.lv[level];
+    cudaSetDevice(ex->device);
+    CUDA_TRY(ex, cudaStreamSynchronize(ex->stream));
+    std::vector<int> cnt(std::max(V.nCells, 1));
+    if (V.nCells) CUDA_TRY(ex, cudaMemcpy(cnt.data(), ex->d_cellCnt + (size_t)frame * G.nCellsTotal + V.cellBase, V.nCells * sizeof(int), cudaMemcpyDeviceToHost));
+    const size_t nslots = (size_t)V.nCells * V.slotCap;
+    std::vector<uint32_t> slots(std::max<size_t>(nslots, 1)), node(std::max<size_t>(nslots, 1));
+    std::vector<float2> xy(std::max<size_t>(nslots, 1));
+    if (nslots) {
+        const size_t o = (size_t)frame * G.slotsTotal + V.slotBase;
+        CUDA_TRY(ex, cudaMemcpy(slots.data(), ex->d_slots + o, nslots * 4, cudaMemcpyDeviceToHost));
+        CUDA_TRY(ex, cudaMemcpy(node.data(), ex->d_ptNode + o, nslots * 4, cudaMemcpyDeviceToHost));
+        CUDA_TRY(ex, cudaMemcpy(xy.data(), ex->d_ptXY + o, nslots * 8, cudaMemcpyDeviceToHost));
+    }
+    int n = 0;
+    for (int c = 0; c < V.nCells; ++c)
+        for (int k = 0; k < cnt[c]; ++k) {
+            const size_t s = (size_t)c * V.slotCap + k;
+            if (node[s] == ORBX_NODE_ERASED) continue;
+            if (out && n < cap) {
+                orbx_keypoint kp;
+                kp.x = xy[s].x; kp.y = xy[s].y; kp.size = 7.f; kp.angle = -1.f;
+                kp.response = (float)(slots[s] >> 16); kp.octave = 0; kp.class_id = -1;
+                out[n] = kp;
+            }
+            ++n;
+        }
+    return n;
+}
+
+int orbx_get_selected(orbx_extractor *ex, int frame, int level, orbx_keypoint *out, int cap) {
+    if (!ex || level < 0 || level >= ex->nlevels || frame < 0 || frame >= ex->lastBatch) return ORBX_ERR_ARG;
+    const OrbxGeom &G = ex->geom;
+    const OrbxLevel &V = G.lv[level];
+    cudaSetDevice(ex->device);
+    CUDA_TRY(ex, cudaStreamSynchronize(ex->stream));
+    int n = 0;
+    CUDA_TRY(ex, cudaMemcpy(&n, ex->d_selCnt + frame * G.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<float4> s(std::max(n, 1));
+    if (n) CUDA_TRY(ex, cudaMemcpy(s.data(), ex->d_sel + (size_t)frame * G.selTotal + V.selBase, n * sizeof(float4), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n && i < cap && out; ++i) {
+        orbx_keypoint kp;
+        kp.x = s[i].x; kp.y = s[i].y; kp.size = (float)V.patch_size; kp.angle = -1.f; kp.response = s[i].z;
+        kp.octave = level; kp.class_id = -1;
+        out[i] = kp;
+    }
+    return n;
+}
+
+void *orbx_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void orbx_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ---- test hooks ----
+void orbx_debug_sort_nodes(const int32_t *sizes, const int32_t *ulx, int n, int32_t *perm_out) {
+    std::vector<orbx_sort::elem_t> a(n);
+    for (int i = 0; i < n; ++i)
+        a[i] = ((((unsigned long long)(unsigned)sizes[i] << 16) | (unsigned short)ulx[i]) << orbx_sort::kPayloadBits) | (unsigned)i;
+    orbx_sort::sort(a.data(), n);
+    for (int i = 0; i < n; ++i) perm_out[i] = (int32_t)(a[i] & ((1ull << orbx_sort::kPayloadBits) - 1));
+}
+
+int orbx_debug_sort_nodes_device(int device, const int32_t *sizes, const int32_t *ulx, int n, int32_t *perm_out) {
+    if (cudaSetDevice(device) != cudaSuccess) return ORBX_ERR_CUDA;
+    std::vector<orbx_sort::elem_t> a(std::max(n, 1));
+    for (int i = 0; i < n; ++i)
+        a[i] = ((((unsigned long long)(unsigned)sizes[i] << 16) | (unsigned short)ulx[i]) << orbx_sort::kPayloadBits) | (unsigned)i;
+    orbx_sort::elem_t *d = nullptr;
+    if (cudaMalloc((void **)&d, a.size() * 8) != cudaSuccess) return ORBX_ERR_CUDA;
+    cudaMemcpy(d, a.data(), a.size() * 8, cudaMemcpyHostToDevice);
+    k_dbg_sort<<<1, 32>>>(d, n);
+    cudaError_t e = cudaMemcpy(a.data(), d, a.size() * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return ORBX_ERR_CUDA;
+    for (int i = 0; i < n; ++i) perm_out[i] = (int32_t)(a[i] & ((1ull << orbx_sort::kPayloadBits) - 1));
+    return ORBX_OK;
+}
+
+int orbx_debug_sincos_device(int device, const float *angles, int n, float *sin_out, float *cos_out) {
+    if (cudaSetDevice(device) != cudaSuccess) return ORBX_ERR_CUDA;
+    float *d = nullptr;
+    if (cudaMalloc((void **)&d, (size_t)n * 12) != cudaSuccess) return ORBX_ERR_CUDA;
+    cudaMemcpy(d, angles, (size_t)n * 4, cudaMemcpyHostToDevice);
+    k_dbg_sincos<<<(n + 255) / 256, 256>>>(d, n, d + n, d + 2 * (size_t)n);
+    cudaMemcpy(sin_out, d + n, (size_t)n * 4, cudaMemcpyDeviceToHost);
+    cudaError_t e = cudaMemcpy(cos_out, d + 2 * (size_t)n, (size_t)n * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return e == cudaSuccess ? ORBX_OK : ORBX_ERR_CUDA;
+}
+
+int orbx_debug_atan2_device(int device, const float *y, const float *x, int n, float *deg_out) {
+    if (cudaSetDevice(device) != cudaSuccess) return ORBX_ERR_CUDA;
+    float *d = nullptr;
+    if (cudaMalloc((void **)&d, (size_t)n * 12) != cudaSuccess) return ORBX_ERR_CUDA;
+    cudaMemcpy(d, y, (size_t)n * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(d + n, x, (size_t)n * 4, cudaMemcpyHostToDevice);
+    k_dbg_atan2<<<(n + 255) / 256, 256>>>(d, d + n, n, d + 2 * (size_t)n);
+    cudaError_t e = cudaMemcpy(deg_out, d + 2 * (size_t)n, (size_t)n * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return e == cudaSuccess ? ORBX_OK : ORBX_ERR_CUDA;
+}
+
+}  // extern "C"

@@ -1,0 +1,447 @@
+// orbx_match.cu — B200 (sm_100a) Hamming matching inner loops of the reference's ORBmatcher and of
+// Frame::ComputeStereoFishEyeMatches (file:line relative to /root/reference):
+//   DescriptorDistance            src/ORBmatcher.cc:2054-2070   256-bit XOR + popcount
+//   BFMatcher.knnMatch(k=2)       src/Frame.cc:1078             brute-force top-2, ties → lower index
+//   Lowe ratio                    src/Frame.cc:1085             (float)d0 < (float)d1 * 0.7 (double)
+//   best/second loops             src/ORBmatcher.cc:84-140 etc. explicit candidate lists
+//   rotation histogram filter     src/ORBmatcher.cc:345-352, :2008-2049
+//
+// The brute-force kernel is POPC-pipe bound, not HBM bound (the DB streams once per 1024 queries):
+// each thread keeps R query descriptors in registers, the block stages DB rows in shared memory and
+// every thread reads them as broadcast uint4; the running top-2 is two packed (dist<<23 | row) keys so
+// the update is branch-free min/max and the tie rule (lower train index first) falls out of the key
+// order.  Per-chunk partial top-2s are merged by one warp per query with a shuffle reduction.
+#include <cuda_runtime.h>
+#include <limits.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "orbx_internal.h"
+
+namespace {
+
+#define KNN_THREADS 256
+#define KNN_DBT 128          // DB rows staged per shared-memory tile
+#define KNN_IDX_BITS 23      // rows per chunk < 2^23 so that dist (≤256, 9 bits) fits above
+#define KNN_KEY_NONE 0xffffffffu
+
+__device__ __forceinline__ int ham256(const uint4 &a0, const uint4 &a1, const uint4 &b0, const uint4 &b1) {
+    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+// grid: (nChunks, nQueryTiles).  Thread t of query tile y owns queries y*THREADS*R + r*THREADS + t.
+template <int R>
+__global__ void __launch_bounds__(KNN_THREADS) k_knn2_partial(const uint4 *__restrict__ q, int nq,
+                                                              const uint4 *__restrict__ db, long long ndb,
+                                                              long long chunkRows, uint2 *__restrict__ partial) {
+    __shared__ uint4 tile[KNN_DBT * 2];
+    const int tid = threadIdx.x;
+    const long long c0 = (long long)blockIdx.x * chunkRows;
+    const long long c1 = min(c0 + chunkRows, ndb);
+    const int qbase = blockIdx.y * (KNN_THREADS * R);
+    uint4 qa[R], qb[R];
+    uint32_t k0[R], k1[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int qi = qbase + r * KNN_THREADS + tid;
+        if (qi < nq) { qa[r] = q[2 * (long long)qi]; qb[r] = q[2 * (long long)qi + 1]; }
+        else { qa[r] = make_uint4(0, 0, 0, 0); qb[r] = qa[r]; }
+        k0[r] = KNN_KEY_NONE; k1[r] = KNN_KEY_NONE;
+    }
+    for (long long t0 = c0; t0 < c1; t0 += KNN_DBT) {
+        const int rows = (int)min((long long)KNN_DBT, c1 - t0);
+        __syncthreads();
+        for (int i = tid; i < rows * 2; i += KNN_THREADS) tile[i] = db[2 * t0 + i];
+        __syncthreads();
+        uint32_t jkey = (uint32_t)(t0 - c0);
+#pragma unroll 4
+        for (int j = 0; j < rows; ++j, ++jkey) {
+            const uint4 d0 = tile[2 * j], d1 = tile[2 * j + 1];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint32_t key = ((uint32_t)ham256(qa[r], qb[r], d0, d1) << KNN_IDX_BITS) + jkey;
+                const uint32_t hi = max(key, k0[r]);
+                k0[r] = min(key, k0[r]);
+                k1[r] = min(k1[r], hi);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int qi = qbase + r * KNN_THREADS + tid;
+        if (qi < nq) partial[(long long)blockIdx.x * nq + qi] = make_uint2(k0[r], k1[r]);
+    }
+}
+
+__device__ __forceinline__ void top2_insert(unsigned long long k, unsigned long long &a, unsigned long long &b) {
+    const unsigned long long hi = k > a ? k : a;
+    a = k < a ? k : a;
+    b = b < hi ? b : hi;
+}
+
+// one warp per query: lanes stride over the chunks, shuffle-reduce the two smallest (dist, idx) keys
+__global__ void __launch_bounds__(256) k_knn2_merge_partials(const uint2 *__restrict__ partial, int nq, int nChunks,
+                                                             long long chunkRows, long long idxBase,
+                                                             int32_t *__restrict__ idx, int32_t *__restrict__ dist) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= nq) return;
+    const unsigned long long NONE = ~0ull;
+    unsigned long long a = NONE, b = NONE;
+    for (int c = lane; c < nChunks; c += 32) {
+        const uint2 p = partial[(long long)c * nq + warp];
+        const unsigned long long base = (unsigned long long)(idxBase + (long long)c * chunkRows);
+        if (p.x != KNN_KEY_NONE) top2_insert(((unsigned long long)(p.x >> KNN_IDX_BITS) << 32) | (base + (p.x & ((1u << KNN_IDX_BITS) - 1))), a, b);
+        if (p.y != KNN_KEY_NONE) top2_insert(((unsigned long long)(p.y >> KNN_IDX_BITS) << 32) | (base + (p.y & ((1u << KNN_IDX_BITS) - 1))), a, b);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long oa = __shfl_xor_sync(0xffffffffu, a, o), ob = __shfl_xor_sync(0xffffffffu, b, o);
+        top2_insert(oa, a, b);
+        top2_insert(ob, a, b);
+    }
+    if (lane == 0) {
+        idx[2 * warp] = a == NONE ? -1 : (int32_t)(a & 0xffffffffu);
+        dist[2 * warp] = a == NONE ? INT_MAX : (int32_t)(a >> 32);
+        idx[2 * warp + 1] = b == NONE ? -1 : (int32_t)(b & 0xffffffffu);
+        dist[2 * warp + 1] = b == NONE ? INT_MAX : (int32_t)(b >> 32);
+    }
+}
+
+// merge of per-shard (idx, dist) top-2 lists, e.g. after an all-gather across GPUs
+__global__ void __launch_bounds__(256) k_knn2_merge_shards(const int32_t *__restrict__ idxAll, const int32_t *__restrict__ distAll,
+                                                           int nShards, int nq, int32_t *__restrict__ idx, int32_t *__restrict__ dist) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= nq) return;
+    const unsigned long long NONE = ~0ull;
+    unsigned long long a = NONE, b = NONE;
+    for (int e = lane; e < 2 * nShards; e += 32) {
+        const long long o = ((long long)(e >> 1) * nq + warp) * 2 + (e & 1);
+        const int32_t i = idxAll[o], d = distAll[o];
+        if (i >= 0) top2_insert(((unsigned long long)(uint32_t)d << 32) | (uint32_t)i, a, b);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long oa = __shfl_xor_sync(0xffffffffu, a, o), ob = __shfl_xor_sync(0xffffffffu, b, o);
+        top2_insert(oa, a, b);
+        top2_insert(ob, a, b);
+    }
+    if (lane == 0) {
+        idx[2 * warp] = a == NONE ? -1 : (int32_t)(a & 0xffffffffu);
+        dist[2 * warp] = a == NONE ? INT_MAX : (int32_t)(a >> 32);
+        idx[2 * warp + 1] = b == NONE ? -1 : (int32_t)(b & 0xffffffffu);
+        dist[2 * warp + 1] = b == NONE ? INT_MAX : (int32_t)(b >> 32);
+    }
+}
+
+__global__ void k_ratio(const int32_t *dist, int nq, double ratio, uint8_t *keep) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const int d0 = dist[2 * i], d1 = dist[2 * i + 1];
+    keep[i] = (d1 != INT_MAX) && ((double)(float)d0 < __dmul_rn((double)(float)d1, ratio));
+}
+
+// best / second-best over explicit candidate lists; one thread per query
+__global__ void k_top2_lists(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ db, const int32_t *__restrict__ cand,
+                             const int32_t *__restrict__ off, int32_t *bestIdx, int32_t *bestDist, int32_t *secondDist) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const uint4 a0 = q[2 * (long long)i], a1 = q[2 * (long long)i + 1];
+    int b = 256, s = 256, bi = -1;
+    for (int c = off[i]; c < off[i + 1]; ++c) {
+        const int t = cand[c];
+        const int d = ham256(a0, a1, db[2 * (long long)t], db[2 * (long long)t + 1]);
+        if (d < b) { s = b; b = d; bi = t; }
+        else if (d < s) s = d;
+    }
+    bestIdx[i] = bi; bestDist[i] = b; secondDist[i] = s;
+}
+
+// rotation histogram + three maxima (one block)
+__global__ void __launch_bounds__(256) k_rot_hist(const float *a, const float *b, int n, uint8_t *keep) {
+    __shared__ int hist[30];
+    __shared__ int sel[3];
+    const int tid = threadIdx.x;
+    if (tid < 30) hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {
+        float rot = __fsub_rn(a[i], b[i]);
+        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+        int bin = (int)roundf(__fmul_rn(rot, 1.0f / 30));  // quirk Q10: degrees × 1/30, half away from zero
+        if (bin == 30) bin = 0;
+        bin = min(max(bin, 0), 29);
+        keep[i] = (uint8_t)bin;
+        atomicAdd(&hist[bin], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {  // ComputeThreeMaxima (:2008-2049)
+        int m1 = 0, m2 = 0, m3 = 0, i1 = -1, i2 = -1, i3 = -1;
+        for (int i = 0; i < 30; ++i) {
+            const int s = hist[i];
+            if (s > m1) { m3 = m2; m2 = m1; m1 = s; i3 = i2; i2 = i1; i1 = i; }
+            else if (s > m2) { m3 = m2; m2 = s; i3 = i2; i2 = i; }
+            else if (s > m3) { m3 = s; i3 = i; }
+        }
+        if ((float)m2 < __fmul_rn(0.1f, (float)m1)) { i2 = -1; i3 = -1; }
+        else if ((float)m3 < __fmul_rn(0.1f, (float)m1)) { i3 = -1; }
+        sel[0] = i1; sel[1] = i2; sel[2] = i3;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {
+        const int bin = keep[i];
+        keep[i] = (bin == sel[0] || bin == sel[1] || bin == sel[2]) ? 1 : 0;
+    }
+}
+
+thread_local std::string tl_merr;
+
+}  // namespace
+
+struct orbx_matcher {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint2 *d_partial = nullptr; size_t partialCap = 0;
+    uint8_t *d_buf = nullptr; size_t bufCap = 0;  // staging for the host-buffer entry points
+    int nSM = 148;
+};
+
+namespace {
+#define MCUDA_TRY(m, call)                                                                \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            (m)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                \
+            return ORBX_ERR_CUDA;                                                         \
+        }                                                                                 \
+    } while (0)
+
+int stage(orbx_matcher *m, size_t bytes) {
+    if (bytes <= m->bufCap && m->d_buf) return ORBX_OK;
+    if (m->d_buf) cudaFree(m->d_buf);
+    m->d_buf = nullptr; m->bufCap = 0;
+    MCUDA_TRY(m, cudaMalloc((void **)&m->d_buf, bytes));
+    m->bufCap = bytes;
+    return ORBX_OK;
+}
+inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
+}  // namespace
+
+extern "C" {
+
+orbx_matcher *orbx_matcher_create(int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {
+        cudaGetLastError();
+        tl_merr = "orbx_matcher_create: no such CUDA device (liborbx has no CPU fallback)";
+        return nullptr;
+    }
+    orbx_matcher *m = new orbx_matcher;
+    m->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        tl_merr = "orbx_matcher_create: cannot create a stream";
+        delete m;
+        return nullptr;
+    }
+    cudaDeviceGetAttribute(&m->nSM, cudaDevAttrMultiProcessorCount, device);
+    return m;
+}
+
+void orbx_matcher_destroy(orbx_matcher *m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    if (m->d_partial) cudaFree(m->d_partial);
+    if (m->d_buf) cudaFree(m->d_buf);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+const char *orbx_matcher_last_error(const orbx_matcher *m) { return m ? m->err.c_str() : tl_merr.c_str(); }
+void *orbx_matcher_stream(orbx_matcher *m) { return m ? (void *)m->stream : nullptr; }
+int orbx_matcher_sync(orbx_matcher *m) {
+    if (!m) return ORBX_ERR_ARG;
+    MCUDA_TRY(m, cudaStreamSynchronize(m->stream));
+    return ORBX_OK;
+}
+
+int orbx_hamming_knn2_device(orbx_matcher *m, const uint8_t *d_q, int nq, const uint8_t *d_db, int64_t ndb,
+                             int64_t idx_base, int32_t *d_idx, int32_t *d_dist) {
+    if (!m) return ORBX_ERR_ARG;
+    if (nq < 0 || ndb < 0 || (nq > 0 && (!d_q || !d_idx || !d_dist)) || (ndb > 0 && !d_db) ||
+        idx_base < 0 || idx_base + ndb > (int64_t)INT_MAX) {
+        m->err = "orbx_hamming_knn2_device: bad argument";
+        return ORBX_ERR_ARG;
+    }
+    if (nq == 0) return ORBX_OK;
+    MCUDA_TRY(m, cudaSetDevice(m->device));
+    // queries per block tile: R·256; pick R so small problems still spread over the SMs
+    const int R = nq > 2 * KNN_THREADS ? 4 : (nq > KNN_THREADS ? 2 : 1);
+    const int qTiles = (nq + KNN_THREADS * R - 1) / (KNN_THREADS * R);
+    // DB chunks: about 4 resident blocks per SM overall, chunk length a multiple of the smem tile
+    long long targetChunks = std::max(1LL, (long long)m->nSM * 4 / qTiles);
+    long long chunkRows = std::max<long long>(KNN_DBT, (ndb + targetChunks - 1) / targetChunks);
+    chunkRows = (chunkRows + KNN_DBT - 1) / KNN_DBT * KNN_DBT;
+    chunkRows = std::min<long long>(chunkRows, (1LL << KNN_IDX_BITS) - KNN_DBT);
+    const int nChunks = (int)std::max<long long>(1, (ndb + chunkRows - 1) / chunkRows);
+    const size_t need = (size_t)nChunks * nq;
+    if (need > m->partialCap || !m->d_partial) {
+        if (m->d_partial) { MCUDA_TRY(m, cudaStreamSynchronize(m->stream)); cudaFree(m->d_partial); }
+        m->d_partial = nullptr; m->partialCap = 0;
+        MCUDA_TRY(m, cudaMalloc((void **)&m->d_partial, need * sizeof(uint2)));
+        m->partialCap = need;
+    }
+    dim3 grd(nChunks, qTiles);
+    const uint4 *q4 = reinterpret_cast<const uint4 *>(d_q), *db4 = reinterpret_cast<const uint4 *>(d_db);
+    if (R == 4) k_knn2_partial<4><<<grd, KNN_THREADS, 0, m->stream>>>(q4, nq, db4, ndb, chunkRows, m->d_partial);
+    else if (R == 2) k_knn2_partial<2><<<grd, KNN_THREADS, 0, m->stream>>>(q4, nq, db4, ndb, chunkRows, m->d_partial);
+    else k_knn2_partial<1><<<grd, KNN_THREADS, 0, m->stream>>>(q4, nq, db4, ndb, chunkRows, m->d_partial);
+    k_knn2_merge_partials<<<(nq * 32 + 255) / 256, 256, 0, m->stream>>>(m->d_partial, nq, nChunks, chunkRows, idx_base, d_idx, d_dist);
+    MCUDA_TRY(m, cudaGetLastError());
+    return ORBX_OK;
+}
+
+int orbx_knn2_merge_device(orbx_matcher *m, const int32_t *d_idx_all, const int32_t *d_dist_all, int n_shards, int nq,
+                           int32_t *d_idx, int32_t *d_dist) {
+    if (!m || n_shards < 1 || nq < 0 || (nq > 0 && (!d_idx_all || !d_dist_all || !d_idx || !d_dist))) {
+        if (m) m->err = "orbx_knn2_merge_device: bad argument";
+        return ORBX_ERR_ARG;
+    }
+    if (nq == 0) return ORBX_OK;
+    MCUDA_TRY(m, cudaSetDevice(m->device));
+    k_knn2_merge_shards<<<(nq * 32 + 255) / 256, 256, 0, m->stream>>>(d_idx_all, d_dist_all, n_shards, nq, d_idx, d_dist);
+    MCUDA_TRY(m, cudaGetLastError());
+    return ORBX_OK;
+}
+
+int orbx_hamming_knn2(orbx_matcher *m, const uint8_t *query, int nq, const uint8_t *train, int64_t ndb, int32_t *idx,
+                      int32_t *dist) {
+    if (!m) return ORBX_ERR_ARG;
+    if (nq < 0 || ndb < 0 || (nq > 0 && (!query || !idx || !dist)) || (ndb > 0 && !train)) {
+        m->err = "orbx_hamming_knn2: bad argument";
+        return ORBX_ERR_ARG;
+    }
+    if (nq == 0) return ORBX_OK;
+    MCUDA_TRY(m, cudaSetDevice(m->device));
+    const size_t qB = al256((size_t)nq * 32), dB = al256((size_t)ndb * 32 + 32), oB = al256((size_t)nq * 8);
+    int rc = stage(m, qB + dB + 2 * oB);
+    if (rc) return rc;
+    uint8_t *dq = m->d_buf, *dd = dq + qB;
+    int32_t *di = reinterpret_cast<int32_t *>(dd + dB), *ddist = reinterpret_cast<int32_t *>(dd + dB + oB);
+    MCUDA_TRY(m, cudaMemcpyAsync(dq, query, (size_t)nq * 32, cudaMemcpyHostToDevice, m->stream));
+    if (ndb > 0) MCUDA_TRY(m, cudaMemcpyAsync(dd, train, (size_t)ndb * 32, cudaMemcpyHostToDevice, m->stream));
+    rc = orbx_hamming_knn2_device(m, dq, nq, dd, ndb, 0, di, ddist);
+    if (rc) return rc;
+    MCUDA_TRY(m, cudaMemcpyAsync(idx, di, (size_t)nq * 8, cudaMemcpyDeviceToHost, m->stream));
+    MCUDA_TRY(m, cudaMemcpyAsync(dist, ddist, (size_t)nq * 8, cudaMemcpyDeviceToHost, m->stream));
+    MCUDA_TRY(m, cudaStreamSynchronize(m->stream));
+    return ORBX_OK;
+}
+
+int orbx_ratio_test_device(orbx_matcher *m, const int32_t *d_dist, int nq, double ratio, uint8_t *d_keep) {
+    if (!m) return ORBX_ERR_ARG;
+    if (nq <= 0) return ORBX_OK;
+    k_ratio<<<(nq + 255) / 256, 256, 0, m->stream>>>(d_dist, nq, ratio, d_keep);
+    MCUDA_TRY(m, cudaGetLastError());
+    return ORBX_OK;
+}
+
+int orbx_ratio_test(orbx_matcher *m, const int32_t *dist, int nq, double ratio, uint8_t *keep) {
+    if (!m) return ORBX_ERR_ARG;
+    if (nq < 0 || (nq > 0 && (!dist || !keep))) { m->err = "orbx_ratio_test: bad argument"; return ORBX_ERR_ARG; }
+    if (nq == 0) return ORBX_OK;
+    MCUDA_TRY(m, cudaSetDevice(m->device));
+    const size_t dB = al256((size_t)nq * 8);
+    int rc = stage(m, dB + al256(nq));
+    if (rc) return rc;
+    int32_t *dd = (int32_t *)m->d_buf;
+    uint8_t *dk = m->d_buf + dB;
+    MCUDA_TRY(m, cudaMemcpyAsync(dd, dist, (size_t)nq * 8, cudaMemcpyHostToDevice, m->stream));
+    rc = orbx_ratio_test_device(m, dd, nq, ratio, dk);
+    if (rc) return rc;
+    MCUDA_TRY(m, cudaMemcpyAsync(keep, dk, nq, cudaMemcpyDeviceToHost, m->stream));
+    MCUDA_TRY(m, cudaStreamSynchronize(m->stream));
+    return ORBX_OK;
+}
+
+int orbx_hamming_top2_lists(orbx_matcher *m, const uint8_t *query, int nq, const uint8_t *train, int64_t ndb,
+                            const int32_t *cand, const int32_t *cand_off, int32_t *best_idx, int32_t *best_dist,
+                            int32_t *second_dist) {
+    if (!m) return ORBX_ERR_ARG;
+    if (nq < 0 || ndb < 0 || (nq > 0 && (!query || !cand_off || !best_idx || !best_dist || !second_dist))) {
+        m->err = "orbx_hamming_top2_lists: bad argument";
+        return ORBX_ERR_ARG;
+    }
+    if (nq == 0) return ORBX_OK;
+    const int nc = cand_off[nq];
+    for (int i = 0; i < nc; ++i)
+        if (cand[i] < 0 || cand[i] >= ndb) { m->err = "orbx_hamming_top2_lists: candidate index out of range"; return ORBX_ERR_ARG; }
+    MCUDA_TRY(m, cudaSetDevice(m->device));
+    const size_t qB = al256((size_t)nq * 32), dB = al256((size_t)ndb * 32 + 32), cB = al256((size_t)std::max(nc, 1) * 4),
+                 oB = al256((size_t)(nq + 1) * 4);
+    int rc = stage(m, qB + dB + cB + 4 * oB);
+    if (rc) return rc;
+    uint8_t *p = m->d_buf;
+    uint8_t *dq = p; p += qB;
+    uint8_t *dd = p; p += dB;
+    int32_t *dc = (int32_t *)p; p += cB;
+    int32_t *doff = (int32_t *)p; p += oB;
+    int32_t *dbi = (int32_t *)p; p += oB;
+    int32_t *dbd = (int32_t *)p; p += oB;
+    int32_t *dsd = (int32_t *)p;
+    cudaStream_t s = m->stream;
+    MCUDA_TRY(m, cudaMemcpyAsync(dq, query, (size_t)nq * 32, cudaMemcpyHostToDevice, s));
+    if (ndb > 0) MCUDA_TRY(m, cudaMemcpyAsync(dd, train, (size_t)ndb * 32, cudaMemcpyHostToDevice, s));
+    if (nc > 0) MCUDA_TRY(m, cudaMemcpyAsync(dc, cand, (size_t)nc * 4, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(doff, cand_off, (size_t)(nq + 1) * 4, cudaMemcpyHostToDevice, s));
+    k_top2_lists<<<(nq + 127) / 128, 128, 0, s>>>((const uint4 *)dq, nq, (const uint4 *)dd, dc, doff, dbi, dbd, dsd);
+    MCUDA_TRY(m, cudaGetLastError());
+    MCUDA_TRY(m, cudaMemcpyAsync(best_idx, dbi, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(best_dist, dbd, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(second_dist, dsd, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+    MCUDA_TRY(m, cudaStreamSynchronize(s));
+    return ORBX_OK;
+}
+
+int orbx_rot_hist_filter_device(orbx_matcher *m, const float *d_a, const float *d_b, int n, uint8_t *d_keep) {
+    if (!m) return ORBX_ERR_ARG;
+    if (n <= 0) return ORBX_OK;
+    k_rot_hist<<<1, 256, 0, m->stream>>>(d_a, d_b, n, d_keep);
+    MCUDA_TRY(m, cudaGetLastError());
+    return ORBX_OK;
+}
+
+int orbx_rot_hist_filter(orbx_matcher *m, const float *angle_a, const float *angle_b, int n, uint8_t *keep) {
+    if (!m) return ORBX_ERR_ARG;
+    if (n < 0 || (n > 0 && (!angle_a || !angle_b || !keep))) { m->err = "orbx_rot_hist_filter: bad argument"; return ORBX_ERR_ARG; }
+    if (n == 0) return ORBX_OK;
+    MCUDA_TRY(m, cudaSetDevice(m->device));
+    const size_t aB = al256((size_t)n * 4);
+    int rc = stage(m, 2 * aB + al256(n));
+    if (rc) return rc;
+    float *da = (float *)m->d_buf, *db = (float *)(m->d_buf + aB);
+    uint8_t *dk = m->d_buf + 2 * aB;
+    MCUDA_TRY(m, cudaMemcpyAsync(da, angle_a, (size_t)n * 4, cudaMemcpyHostToDevice, m->stream));
+    MCUDA_TRY(m, cudaMemcpyAsync(db, angle_b, (size_t)n * 4, cudaMemcpyHostToDevice, m->stream));
+    rc = orbx_rot_hist_filter_device(m, da, db, n, dk);
+    if (rc) return rc;
+    MCUDA_TRY(m, cudaMemcpyAsync(keep, dk, n, cudaMemcpyDeviceToHost, m->stream));
+    MCUDA_TRY(m, cudaStreamSynchronize(m->stream));
+    return ORBX_OK;
+}
+
+int orbx_descriptor_distance(const uint8_t *a, const uint8_t *b) {
+    int d = 0;
+    for (int i = 0; i < 32; i += 8) {
+        unsigned long long x, y;
+        __builtin_memcpy(&x, a + i, 8);
+        __builtin_memcpy(&y, b + i, 8);
+        d += __builtin_popcountll(x ^ y);
+    }
+    return d;
+}
+
+}  // extern "C"

@@ -1,0 +1,338 @@
+"""ctypes host-side mirror of the reference's ORBextractor / ORBmatcher over liborbx.so.
+
+The class and method names follow `/root/reference/include/ORBextractor.h:43-110` and
+`include/ORBmatcher.h:36-103` so that tests read like calls into the reference.  All compute happens in
+the hand-written sm_100a CUDA library behind the C ABI of `include/orbx.h`; there is no CPU fallback —
+if the library is missing or no GPU is visible, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_pkg = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_pkg, "liborbx.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+OK, EMPTY, ERR_CAPACITY, ERR_GEOMETRY, ERR_ARG, ERR_CUDA = 0, -1, -2, -3, -4, -5
+
+
+class OrbxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"liborbx error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load liborbx.so (built by `make -C dani_slam_b200/csrc` or `__graft_entry__.build()`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OrbxError(ERR_CUDA, f"{LIB_PATH} not built: run __graft_entry__.build() (there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32, sz, f64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t, C.c_double
+    L.orbx_device_count.restype = i32
+    L.orbx_create.restype = vp
+    L.orbx_create.argtypes = [i32, f32, i32, i32, i32, i32, i32, i32, i32]
+    L.orbx_destroy.argtypes = [vp]
+    L.orbx_last_error.restype = C.c_char_p
+    L.orbx_last_error.argtypes = [vp]
+    L.orbx_params.argtypes = [vp] * 6
+    L.orbx_extract.argtypes = [vp, vp, i32, i32, sz, vp, i32, i32, i32, vp, vp, i32, vp, vp]
+    L.orbx_extract_batch.argtypes = [vp, vp, i32, i32, i32, sz, vp, i32, i32, i32, vp, vp, i32, vp, vp]
+    L.orbx_extract_batch_device.argtypes = [vp, vp, sz, i32, i32, i32, sz, vp, i32, i32, i32, vp, vp, i32, vp, vp]
+    L.orbx_sync.argtypes = [vp]
+    L.orbx_stream.restype = vp
+    L.orbx_stream.argtypes = [vp]
+    L.orbx_launch_count.restype = C.c_longlong
+    L.orbx_launch_count.argtypes = [vp]
+    L.orbx_level_size.argtypes = [vp, i32, vp, vp]
+    L.orbx_get_pyramid.argtypes = [vp, i32, i32, i32, vp, sz]
+    L.orbx_get_blurred.argtypes = [vp, i32, i32, vp, sz]
+    L.orbx_get_candidates.argtypes = [vp, i32, i32, vp, i32]
+    L.orbx_get_selected.argtypes = [vp, i32, i32, vp, i32]
+    L.orbx_host_alloc.restype = vp
+    L.orbx_host_alloc.argtypes = [sz]
+    L.orbx_host_free.argtypes = [vp]
+    L.orbx_matcher_create.restype = vp
+    L.orbx_matcher_create.argtypes = [i32]
+    L.orbx_matcher_destroy.argtypes = [vp]
+    L.orbx_matcher_last_error.restype = C.c_char_p
+    L.orbx_matcher_last_error.argtypes = [vp]
+    L.orbx_matcher_stream.restype = vp
+    L.orbx_matcher_stream.argtypes = [vp]
+    L.orbx_matcher_sync.argtypes = [vp]
+    L.orbx_hamming_knn2.argtypes = [vp, vp, i32, vp, i64, vp, vp]
+    L.orbx_hamming_knn2_device.argtypes = [vp, vp, i32, vp, i64, i64, vp, vp]
+    L.orbx_knn2_merge_device.argtypes = [vp, vp, vp, i32, i32, vp, vp]
+    L.orbx_ratio_test.argtypes = [vp, vp, i32, f64, vp]
+    L.orbx_ratio_test_device.argtypes = [vp, vp, i32, f64, vp]
+    L.orbx_hamming_top2_lists.argtypes = [vp, vp, i32, vp, i64, vp, vp, vp, vp, vp]
+    L.orbx_rot_hist_filter.argtypes = [vp, vp, vp, i32, vp]
+    L.orbx_rot_hist_filter_device.argtypes = [vp, vp, vp, i32, vp]
+    L.orbx_descriptor_distance.restype = i32
+    L.orbx_descriptor_distance.argtypes = [vp, vp]
+    L.orbx_debug_sort_nodes.argtypes = [vp, vp, i32, vp]
+    L.orbx_debug_sort_nodes_device.argtypes = [i32, vp, vp, i32, vp]
+    L.orbx_debug_sincos_device.argtypes = [i32, vp, i32, vp, vp]
+    L.orbx_debug_atan2_device.argtypes = [i32, vp, vp, i32, vp]
+    _lib = L
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class ORBextractor:
+    """`ORB_SLAM3::ORBextractor` (include/ORBextractor.h:43-110) on one B200.
+
+    `ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)`; calling the object is
+    `operator()(image, mask, keypoints, descriptors, vLappingArea)` and returns
+    `(monoIndex, keypoints, descriptors)`.  `mvDynamicArea` is the public rect list of the reference.
+    """
+
+    HARRIS_SCORE, FAST_SCORE = 0, 1
+
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, device=0, max_width=640,
+                 max_height=480, max_batch=1):
+        self.L = lib()
+        self.nfeatures, self.scaleFactor, self.nlevels = int(nfeatures), float(scaleFactor), int(nlevels)
+        self.iniThFAST, self.minThFAST = int(iniThFAST), int(minThFAST)  # floats are truncated like the C++ ctor
+        self.device, self.max_batch = device, max_batch
+        self.mvDynamicArea: list = []
+        self.h = self.L.orbx_create(self.nfeatures, self.scaleFactor, self.nlevels, self.iniThFAST,
+                                    self.minThFAST, device, max_width, max_height, max_batch)
+        if not self.h:
+            raise OrbxError(ERR_CUDA, self.L.orbx_last_error(None).decode())
+        self.cap = self.nfeatures + 8 * self.nlevels + 64
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.orbx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def _err(self, rc):
+        return OrbxError(rc, self.L.orbx_last_error(self.h).decode())
+
+    # ---- getters (include/ORBextractor.h:58-78)
+    def _params(self):
+        n = self.nlevels
+        sf, inv, s2, is2 = (np.zeros(n, np.float32) for _ in range(4))
+        q = np.zeros(n, np.int32)
+        self.L.orbx_params(self.h, _p(sf), _p(inv), _p(s2), _p(is2), _p(q))
+        return sf, inv, s2, is2, q
+
+    def GetLevels(self):
+        return self.nlevels
+
+    def GetScaleFactor(self):
+        return self.scaleFactor
+
+    def GetScaleFactors(self):
+        return self._params()[0]
+
+    def GetInverseScaleFactors(self):
+        return self._params()[1]
+
+    def GetScaleSigmaSquares(self):
+        return self._params()[2]
+
+    def GetInverseScaleSigmaSquares(self):
+        return self._params()[3]
+
+    def features_per_level(self):
+        return self._params()[4]
+
+    def _rects(self):
+        r = np.ascontiguousarray(np.asarray(self.mvDynamicArea, np.int32).reshape(-1, 4))
+        return r, len(r)
+
+    # ---- operator() (src/ORBextractor.cc:1125-1207)
+    def __call__(self, image, mask=None, vLappingArea=(0, 0)):
+        image = np.asarray(image)
+        if image.size == 0:
+            return -1, np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
+        assert image.dtype == np.uint8 and image.ndim == 2, "CV_8UC1 expected (reference asserts, :1133)"
+        if image.strides[1] != 1:
+            image = np.ascontiguousarray(image)
+        kps = np.zeros(self.cap, KP_DTYPE)
+        desc = np.zeros((self.cap, 32), np.uint8)
+        n, mono = C.c_int(0), C.c_int(0)
+        r, nr = self._rects()
+        rc = self.L.orbx_extract(self.h, _p(image), image.shape[0], image.shape[1], image.strides[0], _p(r), nr,
+                                 int(vLappingArea[0]), int(vLappingArea[1]), _p(kps), _p(desc), self.cap,
+                                 C.byref(n), C.byref(mono))
+        if rc == EMPTY:
+            return -1, np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
+        if rc != OK:
+            raise self._err(rc)
+        return mono.value, kps[: n.value].copy(), desc[: n.value].copy()
+
+    def extract_batch(self, images, vLappingArea=(0, 0)):
+        """Frame-batch form: images = array (B, H, W) uint8 (host).  Returns (n[B], mono[B], kps[B,cap], desc[B,cap,32])."""
+        images = np.ascontiguousarray(images)
+        assert images.dtype == np.uint8 and images.ndim == 3
+        B, H, W = images.shape
+        ptrs = (C.c_void_p * B)(*[images.ctypes.data + b * H * W for b in range(B)])
+        kps = np.zeros((B, self.cap), KP_DTYPE)
+        desc = np.zeros((B, self.cap, 32), np.uint8)
+        n = np.zeros(B, np.int32)
+        mono = np.zeros(B, np.int32)
+        r, nr = self._rects()
+        rc = self.L.orbx_extract_batch(self.h, ptrs, B, H, W, W, _p(r), nr, int(vLappingArea[0]),
+                                       int(vLappingArea[1]), _p(kps), _p(desc), self.cap, _p(n), _p(mono))
+        if rc != OK:
+            raise self._err(rc)
+        return n, mono, kps, desc
+
+    def extract_batch_device(self, d_images_ptr, frame_stride, B, H, W, step, d_kps_ptr, d_desc_ptr, cap, d_n_ptr,
+                             d_mono_ptr, vLappingArea=(0, 0)):
+        """Device-resident batch on raw device pointers (ints); asynchronous on `stream()`."""
+        r, nr = self._rects()
+        rc = self.L.orbx_extract_batch_device(self.h, d_images_ptr, frame_stride, B, H, W, step, _p(r), nr,
+                                              int(vLappingArea[0]), int(vLappingArea[1]), d_kps_ptr, d_desc_ptr, cap,
+                                              d_n_ptr, d_mono_ptr)
+        if rc != OK:
+            raise self._err(rc)
+
+    def sync(self):
+        rc = self.L.orbx_sync(self.h)
+        if rc != OK:
+            raise self._err(rc)
+
+    def stream(self):
+        return self.L.orbx_stream(self.h)
+
+    def launch_count(self):
+        return self.L.orbx_launch_count(self.h)
+
+    # ---- mvImagePyramid (include/ORBextractor.h:83) and stage taps
+    def level_size(self, level):
+        w, h = C.c_int(), C.c_int()
+        self.L.orbx_level_size(self.h, level, C.byref(w), C.byref(h))
+        return w.value, h.value
+
+    def mvImagePyramid(self, level, frame=0, padded=False):
+        w, h = self.level_size(level)
+        b = 38 if padded else 0
+        out = np.zeros((h + b, w + b), np.uint8)
+        rc = self.L.orbx_get_pyramid(self.h, frame, level, int(padded), _p(out), out.strides[0])
+        if rc != OK:
+            raise self._err(rc)
+        return out
+
+    def blurred(self, level, frame=0):
+        w, h = self.level_size(level)
+        out = np.zeros((h, w), np.uint8)
+        rc = self.L.orbx_get_blurred(self.h, frame, level, _p(out), out.strides[0])
+        if rc != OK:
+            raise self._err(rc)
+        return out
+
+    def candidates(self, level, frame=0):
+        n = self.L.orbx_get_candidates(self.h, frame, level, None, 0)
+        if n < 0:
+            raise self._err(n)
+        out = np.zeros(max(n, 1), KP_DTYPE)
+        self.L.orbx_get_candidates(self.h, frame, level, _p(out), n)
+        return out[:n]
+
+    def selected(self, level, frame=0):
+        n = self.L.orbx_get_selected(self.h, frame, level, None, 0)
+        if n < 0:
+            raise self._err(n)
+        out = np.zeros(max(n, 1), KP_DTYPE)
+        self.L.orbx_get_selected(self.h, frame, level, _p(out), n)
+        return out[:n]
+
+
+class ORBmatcher:
+    """Matching inner loops of `ORB_SLAM3::ORBmatcher` (include/ORBmatcher.h:36-103) and of
+    `Frame::ComputeStereoFishEyeMatches` (src/Frame.cc:1060-1100) on one B200."""
+
+    TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30  # src/ORBmatcher.cc:35-37
+
+    def __init__(self, nnratio=0.6, checkOri=True, device=0):
+        self.L = lib()
+        self.mfNNratio, self.mbCheckOrientation = np.float32(nnratio), bool(checkOri)
+        self.device = device
+        self.h = self.L.orbx_matcher_create(device)
+        if not self.h:
+            raise OrbxError(ERR_CUDA, self.L.orbx_matcher_last_error(None).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.orbx_matcher_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def _chk(self, rc):
+        if rc != OK:
+            raise OrbxError(rc, self.L.orbx_matcher_last_error(self.h).decode())
+
+    @staticmethod
+    def DescriptorDistance(a, b) -> int:
+        a = np.ascontiguousarray(a, np.uint8)
+        b = np.ascontiguousarray(b, np.uint8)
+        assert a.size == 32 and b.size == 32
+        return lib().orbx_descriptor_distance(_p(a), _p(b))
+
+    def knnMatch(self, query, train):
+        """BFMatcher(NORM_HAMMING).knnMatch(query, train, k=2) → (idx[nq,2], dist[nq,2])."""
+        q = np.ascontiguousarray(query, np.uint8).reshape(-1, 32)
+        t = np.ascontiguousarray(train, np.uint8).reshape(-1, 32)
+        idx = np.zeros((len(q), 2), np.int32)
+        dist = np.zeros((len(q), 2), np.int32)
+        self._chk(self.L.orbx_hamming_knn2(self.h, _p(q), len(q), _p(t), len(t), _p(idx), _p(dist)))
+        return idx, dist
+
+    def ratio_test(self, dist, ratio=0.7):
+        dist = np.ascontiguousarray(dist, np.int32).reshape(-1, 2)
+        keep = np.zeros(len(dist), np.uint8)
+        self._chk(self.L.orbx_ratio_test(self.h, _p(dist), len(dist), float(ratio), _p(keep)))
+        return keep.astype(bool)
+
+    def top2_lists(self, query, train, cand, cand_off):
+        q = np.ascontiguousarray(query, np.uint8).reshape(-1, 32)
+        t = np.ascontiguousarray(train, np.uint8).reshape(-1, 32)
+        cand = np.ascontiguousarray(cand, np.int32)
+        off = np.ascontiguousarray(cand_off, np.int32)
+        assert len(off) == len(q) + 1
+        bi, bd, sd = (np.zeros(len(q), np.int32) for _ in range(3))
+        self._chk(self.L.orbx_hamming_top2_lists(self.h, _p(q), len(q), _p(t), len(t), _p(cand), _p(off), _p(bi), _p(bd), _p(sd)))
+        return bi, bd, sd
+
+    def rot_hist_filter(self, angle_a, angle_b):
+        a = np.ascontiguousarray(angle_a, np.float32)
+        b = np.ascontiguousarray(angle_b, np.float32)
+        keep = np.zeros(len(a), np.uint8)
+        self._chk(self.L.orbx_rot_hist_filter(self.h, _p(a), _p(b), len(a), _p(keep)))
+        return keep.astype(bool)
+
+    # device-pointer forms (ints), asynchronous on stream()
+    def knn2_device(self, d_q, nq, d_db, ndb, idx_base, d_idx, d_dist):
+        self._chk(self.L.orbx_hamming_knn2_device(self.h, d_q, nq, d_db, ndb, idx_base, d_idx, d_dist))
+
+    def merge_device(self, d_idx_all, d_dist_all, n_shards, nq, d_idx, d_dist):
+        self._chk(self.L.orbx_knn2_merge_device(self.h, d_idx_all, d_dist_all, n_shards, nq, d_idx, d_dist))
+
+    def sync(self):
+        self._chk(self.L.orbx_matcher_sync(self.h))
+
+    def stream(self):
+        return self.L.orbx_matcher_stream(self.h)

@@ -1,0 +1,162 @@
+/* orbx.h — C ABI of the B200-native ORB front-end (liborbx.so, hand-written sm_100a CUDA).
+ *
+ * This is the drop-in boundary for ONE hot path of DANI-SLAM: what the reference's
+ * `ORB_SLAM3::ORBextractor` / `ORB_SLAM3::ORBmatcher` classes compute (file:line below are relative to
+ * /root/reference).  The adapter headers include/ORBextractor.h and include/ORBmatcher.h keep the
+ * reference's C++ signatures and forward to these entry points; INTEGRATION.md shows the binding.
+ * Plain pointers and sizes only; no torch / OpenCV types.  No CPU fallback exists: every compute entry
+ * point returns ORBX_ERR_CUDA when no usable device is present.
+ *
+ * Return convention: 0 = ok, -1 = empty image (the reference's `return -1`, src/ORBextractor.cc:1129),
+ * other negative values = errors (see ORBX_ERR_*); the message is available via orbx_last_error().
+ */
+#ifndef ORBX_H
+#define ORBX_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORBX_OK 0
+#define ORBX_EMPTY (-1)         /* empty input image: reference returns -1 (ORBextractor.cc:1129-1130) */
+#define ORBX_ERR_CAPACITY (-2)  /* caller's keypoint/descriptor capacity too small; n_out holds the need */
+#define ORBX_ERR_GEOMETRY (-3)  /* image too small / too tall for the pyramid (reference would fault) */
+#define ORBX_ERR_ARG (-4)       /* bad argument (null pointer, size beyond what the handle was made for) */
+#define ORBX_ERR_CUDA (-5)      /* CUDA runtime error, or no device */
+
+/* Layout-identical to cv::KeyPoint (7×4 bytes): pt.x, pt.y, size, angle, response, octave, class_id. */
+typedef struct {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} orbx_keypoint;
+
+typedef struct orbx_extractor orbx_extractor;
+
+/* ---------------------------------------------------------------------------------------------
+ * Extractor — replaces ORBextractor (include/ORBextractor.h:43-110, src/ORBextractor.cc).
+ * ------------------------------------------------------------------------------------------- */
+
+/* Number of CUDA devices visible (0 when none / driver missing). */
+int orbx_device_count(void);
+
+/* ORBextractor::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)
+ * (src/ORBextractor.cc:409-469) plus the device resources the handle owns: `device` ordinal, the
+ * largest image (max_width × max_height) and the largest batch it will be asked to process.
+ * Returns NULL on failure (orbx_last_error(NULL) tells why). */
+orbx_extractor *orbx_create(int nfeatures, float scale_factor, int nlevels, int ini_th_fast,
+                            int min_th_fast, int device, int max_width, int max_height, int max_batch);
+void orbx_destroy(orbx_extractor *ex);
+
+/* Last error text of this handle (or of the calling thread's last failed create when ex==NULL). */
+const char *orbx_last_error(const orbx_extractor *ex);
+
+/* GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares / GetInverseScaleSigmaSquares
+ * (include/ORBextractor.h:64-78) and mnFeaturesPerLevel; arrays of nlevels entries, any may be NULL. */
+int orbx_params(const orbx_extractor *ex, float *scale_factors, float *inv_scale_factors,
+                float *level_sigma2, float *inv_level_sigma2, int32_t *features_per_level);
+
+/* ORBextractor::operator()(image, mask, keypoints, descriptors, vLappingArea)
+ * (src/ORBextractor.cc:1125-1207) for one HOST image (8-bit, 1 channel, `step` bytes per row).
+ * rects_xywh = mvDynamicArea (include/ORBextractor.h:84) as n_rects×{x,y,w,h} in level-0 pixels;
+ * lap0/lap1 = vLappingArea[0..1].  Writes *n_out keypoints (28-byte records) and *n_out×32 descriptor
+ * bytes into caller buffers of capacity `cap` rows; *mono_index = the reference's return value. */
+int orbx_extract(orbx_extractor *ex, const uint8_t *image, int rows, int cols, size_t step,
+                 const int32_t *rects_xywh, int n_rects, int lap0, int lap1, orbx_keypoint *keypoints,
+                 uint8_t *descriptors, int cap, int *n_out, int *mono_index);
+
+/* Frame-batch form of the same call (the throughput path): `batch` HOST images of identical size,
+ * images[b] pointing at rows×cols bytes with `step`.  Outputs are batch×cap keypoints, batch×cap×32
+ * descriptor bytes, n_out[batch], mono_index[batch].  Host↔device copies are inside the call.
+ * Host buffers should be page-locked (orbx_host_alloc) for full PCIe rate; pageable works. */
+int orbx_extract_batch(orbx_extractor *ex, const uint8_t *const *images, int batch, int rows, int cols,
+                       size_t step, const int32_t *rects_xywh, int n_rects, int lap0, int lap1,
+                       orbx_keypoint *keypoints, uint8_t *descriptors, int cap, int32_t *n_out,
+                       int32_t *mono_index);
+
+/* Device-resident batch: d_images = `batch` frames already in HBM (frame b at d_images + b*frame_stride,
+ * rows of `step` bytes); outputs are DEVICE buffers of the same shapes as above.  Runs asynchronously on
+ * the handle's stream; orbx_sync() waits.  Return code covers launch errors only; per-frame overflow
+ * is reported by n_out[b] > cap after sync. */
+int orbx_extract_batch_device(orbx_extractor *ex, const uint8_t *d_images, size_t frame_stride,
+                              int batch, int rows, int cols, size_t step, const int32_t *rects_xywh,
+                              int n_rects, int lap0, int lap1, orbx_keypoint *d_keypoints,
+                              uint8_t *d_descriptors, int cap, int32_t *d_n_out, int32_t *d_mono_index);
+int orbx_sync(orbx_extractor *ex);
+/* The handle's cudaStream_t (as void*), so callers can record CUDA events on the launching stream. */
+void *orbx_stream(orbx_extractor *ex);
+/* Number of kernel launches issued by the handle since creation (bench `gpu_launches`). */
+long long orbx_launch_count(const orbx_extractor *ex);
+
+/* mvImagePyramid[level] (include/ORBextractor.h:83) of frame `frame` of the last call, copied to host.
+ * padded!=0 → (w+38)×(h+38) plane with the REFLECT_101 border of src/ORBextractor.cc:1224-1230
+ * (materialised lazily; the hot path never reads it); else the w×h level itself. */
+int orbx_level_size(const orbx_extractor *ex, int level, int *width, int *height);
+int orbx_get_pyramid(orbx_extractor *ex, int frame, int level, int padded, uint8_t *dst, size_t dst_step);
+
+/* Stage taps of the last call, for stage-level parity tests: the 7×7 Gaussian-blurred level
+ * (src/ORBextractor.cc:1171-1172), the per-level candidates entering DistributeOctTree (:909-916, after
+ * the DANI filter) and the per-level selected keypoints (after :919-934).  Return the count. */
+int orbx_get_blurred(orbx_extractor *ex, int frame, int level, uint8_t *dst, size_t dst_step);
+int orbx_get_candidates(orbx_extractor *ex, int frame, int level, orbx_keypoint *out, int cap);
+int orbx_get_selected(orbx_extractor *ex, int frame, int level, orbx_keypoint *out, int cap);
+
+/* Page-locked host memory helpers (cudaHostAlloc / cudaFreeHost). */
+void *orbx_host_alloc(size_t bytes);
+void orbx_host_free(void *p);
+
+/* ---------------------------------------------------------------------------------------------
+ * Matcher inner loops — replace ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:2054-2070), the
+ * best/second-best loops (:84-140, :273-325, :675-724, :812-864), ComputeThreeMaxima + the rotation
+ * histogram (:2008-2049, :345-352) and Frame::BFmatcher.knnMatch(k=2) + Lowe ratio
+ * (src/Frame.cc:45,1078-1085).  Descriptors are rows of 32 bytes.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct orbx_matcher orbx_matcher;
+/* Device context for matching (stream + scratch); cheap, but not free: adapters cache one per thread. */
+orbx_matcher *orbx_matcher_create(int device);
+void orbx_matcher_destroy(orbx_matcher *m);
+const char *orbx_matcher_last_error(const orbx_matcher *m);
+void *orbx_matcher_stream(orbx_matcher *m);
+int orbx_matcher_sync(orbx_matcher *m);
+
+/* BFMatcher(NORM_HAMMING).knnMatch(query, train, k=2): idx/dist are nq×2 (ascending distance, ties →
+ * lower train index first); missing neighbours (ndb<2) are idx=-1, dist=INT32_MAX.  HOST buffers. */
+int orbx_hamming_knn2(orbx_matcher *m, const uint8_t *query, int nq, const uint8_t *train, int64_t ndb,
+                      int32_t *idx, int32_t *dist);
+/* Same on DEVICE buffers, asynchronous on the matcher's stream.  idx_base is added to every train
+ * index (global index of this shard's first row) so DB-sharded callers can merge shards directly. */
+int orbx_hamming_knn2_device(orbx_matcher *m, const uint8_t *d_query, int nq, const uint8_t *d_train,
+                             int64_t ndb, int64_t idx_base, int32_t *d_idx, int32_t *d_dist);
+/* Merge per-shard top-2 lists (DEVICE, n_shards×nq×2, as produced by an all-gather of the above) into
+ * the global top-2 by lexicographic (dist, idx) order — equals the unsharded result bit for bit. */
+int orbx_knn2_merge_device(orbx_matcher *m, const int32_t *d_idx_all, const int32_t *d_dist_all,
+                           int n_shards, int nq, int32_t *d_idx, int32_t *d_dist);
+/* Frame.cc:1085: keep[i] = (two neighbours) && (float)d0 < (float)d1 * ratio(double).  HOST / DEVICE buffers. */
+int orbx_ratio_test(orbx_matcher *m, const int32_t *dist, int nq, double ratio, uint8_t *keep);
+int orbx_ratio_test_device(orbx_matcher *m, const int32_t *d_dist, int nq, double ratio, uint8_t *d_keep);
+
+/* Best / second-best over explicit candidate lists (the a12 loops): query i is compared with train
+ * rows cand[cand_off[i] .. cand_off[i+1]); strict '<' (first candidate wins ties); defaults 256.
+ * HOST buffers. */
+int orbx_hamming_top2_lists(orbx_matcher *m, const uint8_t *query, int nq, const uint8_t *train, int64_t ndb,
+                            const int32_t *cand, const int32_t *cand_off, int32_t *best_idx,
+                            int32_t *best_dist, int32_t *second_dist);
+/* Rotation-consistency filter: bin = round((a-b [+360]) / 30) (quirk Q10), keep matches in the three
+ * fullest bins subject to the 0.1·max rule.  HOST / DEVICE buffers; n matches. */
+int orbx_rot_hist_filter(orbx_matcher *m, const float *angle_a, const float *angle_b, int n, uint8_t *keep);
+int orbx_rot_hist_filter_device(orbx_matcher *m, const float *d_angle_a, const float *d_angle_b, int n, uint8_t *d_keep);
+/* ORBmatcher::DescriptorDistance for one pair on the host (inline popcount; no device involved). */
+int orbx_descriptor_distance(const uint8_t *a, const uint8_t *b);
+
+/* Test hook: the device/host port of libstdc++ std::sort used by the quadtree (see stdsort_port.h),
+ * run on the host; perm_out = resulting order of original indices. */
+void orbx_debug_sort_nodes(const int32_t *sizes, const int32_t *ulx, int n, int32_t *perm_out);
+/* Test hooks that run single device kernels on arrays (return 0 / ORBX_ERR_CUDA). */
+int orbx_debug_sort_nodes_device(int device, const int32_t *sizes, const int32_t *ulx, int n, int32_t *perm_out);
+int orbx_debug_sincos_device(int device, const float *angles, int n, float *sin_out, float *cos_out);
+int orbx_debug_atan2_device(int device, const float *y, const float *x, int n, float *deg_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
