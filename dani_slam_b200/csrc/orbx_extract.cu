@@ -985,6 +985,11 @@ struct orbx_extractor {
     orbx_keypoint *d_kps = nullptr; uint8_t *d_desc = nullptr; size_t outCap = 0;
     int *d_nOut = nullptr, *d_mono = nullptr;
     int *h_nOut = nullptr, *h_mono = nullptr;  // pinned
+    // optional per-stage timing (bench roofline): events at the 6 stage boundaries
+    bool profiling = false, evPending = false;
+    cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double stageMs[6] = {0, 0, 0, 0, 0, 0};
+    long long stageCalls = 0;
 };
 
 namespace {
@@ -1214,6 +1219,19 @@ int prepare(orbx_extractor *ex, int rows, int cols, const int32_t *rects, int nR
     return ensure_buffers(ex, batch);
 }
 
+int harvest_stage_times(orbx_extractor *ex) {
+    if (!ex->evPending) return ORBX_OK;
+    CUDA_TRY(ex, cudaEventSynchronize(ex->ev[6]));
+    for (int i = 0; i < 6; ++i) {
+        float ms = 0.f;
+        CUDA_TRY(ex, cudaEventElapsedTime(&ms, ex->ev[i], ex->ev[i + 1]));
+        ex->stageMs[i] += ms;
+    }
+    ++ex->stageCalls;
+    ex->evPending = false;
+    return ORBX_OK;
+}
+
 // enqueue the whole pipeline for `batch` frames whose level 0 lives at (in0, stride, pitch)
 int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, int in0Pitch, int batch,
                  orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int *d_nOut, int *d_mono) {
@@ -1229,12 +1247,19 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
     P.kps = d_kps; P.desc = d_desc; P.cap = cap; P.nOut = d_nOut; P.monoIdx = d_mono;
     P.pattern = ex->d_pattern;
     cudaStream_t s = ex->stream;
+    const bool prof = ex->profiling;
+    if (prof) {
+        int rc = harvest_stage_times(ex);
+        if (rc) return rc;
+        CUDA_TRY(ex, cudaEventRecord(ex->ev[0], s));
+    }
     // K1
     for (int l = 1; l < G.nlevels; ++l) {
         dim3 blk(32, 8), grd((G.lv[l].w + 127) / 128, (G.lv[l].h + 7) / 8, batch);
         k_pyr_level<<<grd, blk, 0, s>>>(P, l);
         ++ex->launches;
     }
+    if (prof) CUDA_TRY(ex, cudaEventRecord(ex->ev[1], s));
     // K2
     {
         const int WPB = 4;
@@ -1249,6 +1274,7 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
             ++ex->launches;
         }
     }
+    if (prof) CUDA_TRY(ex, cudaEventRecord(ex->ev[2], s));
     // K3
     {
         const QtSmem L = qt_smem_layout(ex->nodeCapMax, ex->maxCellsLevel);
@@ -1259,15 +1285,18 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
         k_quadtree<<<grd, QT_THREADS, L.total, s>>>(P, ex->nodeCapMax, ex->maxCellsLevel);
         ++ex->launches;
     }
+    if (prof) CUDA_TRY(ex, cudaEventRecord(ex->ev[3], s));
     // K7
     k_assemble<<<batch, 256, 0, s>>>(P);
     ++ex->launches;
+    if (prof) CUDA_TRY(ex, cudaEventRecord(ex->ev[4], s));
     // K5
     {
         dim3 grd((unsigned)ex->h_tiles.size(), batch);
         k_blur<<<grd, 256, 0, s>>>(P, ex->d_tiles);
         ++ex->launches;
     }
+    if (prof) CUDA_TRY(ex, cudaEventRecord(ex->ev[5], s));
     // K4 + K6
     {
         const int WPB = 8;
@@ -1275,6 +1304,7 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
         k_orient_desc<WPB><<<grd, WPB * 32, 0, s>>>(P);
         ++ex->launches;
     }
+    if (prof) { CUDA_TRY(ex, cudaEventRecord(ex->ev[6], s)); ex->evPending = true; }
     CUDA_TRY(ex, cudaGetLastError());
     ex->lastBatch = batch;
     return ORBX_OK;
@@ -1372,6 +1402,7 @@ void orbx_destroy(orbx_extractor *ex) {
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ex->h_nOut) cudaFreeHost(ex->h_nOut);
     if (ex->h_mono) cudaFreeHost(ex->h_mono);
+    for (int i = 0; i < 7; ++i) if (ex->ev[i]) cudaEventDestroy(ex->ev[i]);
     if (ex->stream) cudaStreamDestroy(ex->stream);
     delete ex;
 }
@@ -1488,6 +1519,33 @@ int orbx_sync(orbx_extractor *ex) {
     return ORBX_OK;
 }
 void *orbx_stream(orbx_extractor *ex) { return ex ? (void *)ex->stream : nullptr; }
+
+int orbx_set_profiling(orbx_extractor *ex, int on) {
+    if (!ex) return ORBX_ERR_ARG;
+    CUDA_TRY(ex, cudaSetDevice(ex->device));
+    if (on && !ex->ev[0])
+        for (int i = 0; i < 7; ++i) CUDA_TRY(ex, cudaEventCreate(&ex->ev[i]));
+    if (!on) { int rc = harvest_stage_times(ex); if (rc) return rc; }
+    ex->profiling = on != 0;
+    return ORBX_OK;
+}
+
+int orbx_get_stage_ms(orbx_extractor *ex, double *ms6, long long *calls) {
+    if (!ex || !ms6) return ORBX_ERR_ARG;
+    int rc = harvest_stage_times(ex);
+    if (rc) return rc;
+    for (int i = 0; i < 6; ++i) ms6[i] = ex->stageMs[i];
+    if (calls) *calls = ex->stageCalls;
+    return ORBX_OK;
+}
+
+int orbx_reset_stage_ms(orbx_extractor *ex) {
+    if (!ex) return ORBX_ERR_ARG;
+    int rc = harvest_stage_times(ex);
+    for (int i = 0; i < 6; ++i) ex->stageMs[i] = 0;
+    ex->stageCalls = 0;
+    return rc;
+}
 long long orbx_launch_count(const orbx_extractor *ex) { return ex ? ex->launches : 0; }
 
 int orbx_level_size(const orbx_extractor *ex, int level, int *w, int *h) {

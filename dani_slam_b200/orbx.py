@@ -55,6 +55,9 @@ def lib() -> C.CDLL:
     L.orbx_stream.argtypes = [vp]
     L.orbx_launch_count.restype = C.c_longlong
     L.orbx_launch_count.argtypes = [vp]
+    L.orbx_set_profiling.argtypes = [vp, i32]
+    L.orbx_get_stage_ms.argtypes = [vp, vp, vp]
+    L.orbx_reset_stage_ms.argtypes = [vp]
     L.orbx_level_size.argtypes = [vp, i32, vp, vp]
     L.orbx_get_pyramid.argtypes = [vp, i32, i32, i32, vp, sz]
     L.orbx_get_blurred.argtypes = [vp, i32, i32, vp, sz]
@@ -218,6 +221,23 @@ class ORBextractor:
 
     def launch_count(self):
         return self.L.orbx_launch_count(self.h)
+
+    STAGES = ("pyramid", "fast_cells", "quadtree", "assemble", "blur", "orient_desc")
+
+    def set_profiling(self, on):
+        rc = self.L.orbx_set_profiling(self.h, int(bool(on)))
+        if rc != OK:
+            raise self._err(rc)
+
+    def stage_ms(self, reset=False):
+        ms = (C.c_double * 6)()
+        calls = C.c_longlong(0)
+        rc = self.L.orbx_get_stage_ms(self.h, ms, C.byref(calls))
+        if rc != OK:
+            raise self._err(rc)
+        if reset:
+            self.L.orbx_reset_stage_ms(self.h)
+        return dict(zip(self.STAGES, list(ms))), calls.value
 
     # ---- mvImagePyramid (include/ORBextractor.h:83) and stage taps
     def level_size(self, level):

@@ -88,6 +88,14 @@ void *orbx_stream(orbx_extractor *ex);
 /* Number of kernel launches issued by the handle since creation (bench `gpu_launches`). */
 long long orbx_launch_count(const orbx_extractor *ex);
 
+/* Per-stage device timing for bench.py's roofline: when on, CUDA events are recorded on the handle's
+ * stream at the six stage boundaries of every batch call (pyramid, FAST cells, quadtree, assemble, blur,
+ * orientation+rBRIEF); orbx_get_stage_ms returns the accumulated milliseconds per stage and the number of
+ * batch calls they cover.  Off by default (the timed `value` region never runs with it on). */
+int orbx_set_profiling(orbx_extractor *ex, int on);
+int orbx_get_stage_ms(orbx_extractor *ex, double *ms6, long long *calls);
+int orbx_reset_stage_ms(orbx_extractor *ex);
+
 /* mvImagePyramid[level] (include/ORBextractor.h:83) of frame `frame` of the last call, copied to host.
  * padded!=0 → (w+38)×(h+38) plane with the REFLECT_101 border of src/ORBextractor.cc:1224-1230
  * (materialised lazily; the hot path never reads it); else the w×h level itself. */

@@ -54,6 +54,7 @@ def lib() -> C.CDLL:
         L.orc_cvround.restype = i32
         L.orc_cvround.argtypes = [f32]
         L.orc_sincos.argtypes = [f32, vp, vp]
+        L.orc_sincos_array.argtypes = [vp, C.c_int64, vp, vp, i32]
         L.orc_distribute.restype = i32
         L.orc_distribute.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, i32]
         L.orc_sort_nodes.argtypes = [vp, vp, i32, vp]
@@ -157,4 +158,39 @@ def ratio_test(dist, ratio=0.7):
     dist = np.ascontiguousarray(dist, np.int32)
     keep = np.zeros(len(dist), np.uint8)
     lib().orc_ratio_test(_p(dist), len(dist), ratio, _p(keep))
+    return keep.astype(bool)
+
+
+def sincos_array(a, nthreads=8):
+    a = np.ascontiguousarray(a, np.float32)
+    s = np.empty_like(a)
+    c = np.empty_like(a)
+    lib().orc_sincos_array(_p(a), a.size, _p(s), _p(c), nthreads)
+    return s, c
+
+
+def fast_atan2(y, x):
+    return float(lib().orc_fast_atan2(float(y), float(x)))
+
+
+def sort_nodes(sizes, ulx):
+    sizes = np.ascontiguousarray(sizes, np.int32)
+    ulx = np.ascontiguousarray(ulx, np.int32)
+    perm = np.zeros(len(sizes), np.int32)
+    lib().orc_sort_nodes(_p(sizes), _p(ulx), len(sizes), _p(perm))
+    return perm
+
+
+def top2_lists(q, db, cand, off):
+    q = np.ascontiguousarray(q, np.uint8); db = np.ascontiguousarray(db, np.uint8)
+    cand = np.ascontiguousarray(cand, np.int32); off = np.ascontiguousarray(off, np.int32)
+    bi, bd, sd = (np.zeros(len(q), np.int32) for _ in range(3))
+    lib().orc_top2_lists(_p(q), len(q), _p(db), _p(cand), _p(off), _p(bi), _p(bd), _p(sd))
+    return bi, bd, sd
+
+
+def rot_hist_filter(a, b):
+    a = np.ascontiguousarray(a, np.float32); b = np.ascontiguousarray(b, np.float32)
+    keep = np.zeros(len(a), np.uint8)
+    lib().orc_rot_hist_filter(_p(a), _p(b), len(a), _p(keep))
     return keep.astype(bool)

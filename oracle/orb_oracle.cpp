@@ -650,6 +650,14 @@ int orc_fast9_nms(const uint8_t *roi, int w, int h, size_t step, int threshold, 
 float orc_fast_atan2(float y, float x) { return fast_atan2(y, x); }
 int orc_cvround(float v) { return rnd(v); }
 void orc_sincos(float angle_rad, float *s, float *c) { *s = std::sin(angle_rad); *c = std::cos(angle_rad); }
+void orc_sincos_array(const float *a, int64_t n, float *s, float *c, int nthreads) {
+    // the host libm's sinf/cosf over an array (the definition the device port is swept against)
+    auto work = [&](int64_t lo, int64_t hi) { for (int64_t i = lo; i < hi; ++i) { s[i] = std::sin(a[i]); c[i] = std::cos(a[i]); } };
+    if (nthreads <= 1) { work(0, n); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t) th.emplace_back(work, n * t / nthreads, n * (t + 1) / nthreads);
+    for (auto &t : th) t.join();
+}
 
 int orc_distribute(const orc_keypoint *in, int n, int minX, int maxX, int minY, int maxY, int N,
                    orc_keypoint *out, int cap) {

@@ -56,6 +56,7 @@ int orc_fast9_nms(const uint8_t *roi, int w, int h, size_t step, int threshold, 
 float orc_fast_atan2(float y, float x);
 int orc_cvround(float v);
 void orc_sincos(float angle_rad, float *s, float *c);
+void orc_sincos_array(const float *a, int64_t n, float *s, float *c, int nthreads);
 /* quadtree on an explicit candidate list (ORBextractor.cc:555-779); returns number kept */
 int orc_distribute(const orc_keypoint *in, int n, int minX, int maxX, int minY, int maxY, int N,
                    orc_keypoint *out, int cap);

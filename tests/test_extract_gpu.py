@@ -1,0 +1,177 @@
+"""GPU parity tests of the extractor: CUDA path (through the C ABI) vs the CPU oracle and the golden
+vectors — bit-exact for pyramid pixels, candidates, selected keypoints, final 28-byte keypoint records
+(angles included: same fp32 formulation, so the 1e-3° tolerance of north_star is met with 0 difference),
+descriptors and the mono index."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import golden_cases, golden_frame, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _xyz(k):
+    return np.stack([k["x"], k["y"], k["response"]], axis=1).astype(np.float32)
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_cuda_matches_golden_and_oracle_stage_by_stage(orbx_mod, oracle_mod, name):
+    g = load_golden(name)
+    img = golden_frame(g)
+    nf, lap = int(g["nfeatures"]), tuple(int(v) for v in g["lap"])
+    ex = orbx_mod.ORBextractor(nf, 1.2, 8, 20, 7, max_width=img.shape[1], max_height=img.shape[0], max_batch=1)
+    ex.mvDynamicArea = [tuple(int(v) for v in r) for r in g["rects"]]
+    mono, k, d = ex(img, None, lap)
+    ref = oracle_mod.Extractor(nf, 1.2, 8, 20, 7)
+    rc, rk, rd, rmono = ref.extract(img, rects=g["rects"], lap=lap, cap=nf + 200)
+    for l in range(8):
+        assert sha(ex.mvImagePyramid(l, padded=True)) == str(g["pyr_sha"][l]), f"pyramid level {l}"
+        assert np.array_equal(ex.mvImagePyramid(l), ref.level(l))
+        if str(g["blur_sha"][l]):
+            assert sha(ex.blurred(l)) == str(g["blur_sha"][l]), f"blurred level {l}"
+        assert sha(_xyz(ex.candidates(l))) == str(g["cand_sha"][l]), f"candidates level {l}"
+        assert sha(_xyz(ex.selected(l))) == str(g["sel_sha"][l]), f"selected level {l}"
+    assert mono == int(g["mono"]) == rmono
+    assert k.tobytes() == g["kps"].tobytes() == rk.tobytes()
+    assert np.array_equal(d, g["desc"]) and np.array_equal(d, rd)
+    # angle tolerance stated by north_star (met exactly)
+    assert np.max(np.abs(k["angle"] - rk["angle"]), initial=0) <= 1e-3
+
+
+def test_batch_equals_per_frame_oracle(orbx_mod, oracle_mod):
+    from dani_slam_b200 import synth
+    B = 12
+    imgs = np.stack([synth.parity_frame(100 + i) if i % 3 == 0 else synth.throughput_frame(100 + i) for i in range(B)])
+    ex = orbx_mod.ORBextractor(1000, 1.2, 8, 20, 7, max_width=640, max_height=480, max_batch=5)  # forces chunking 5+5+2
+    n, mono, kps, desc = ex.extract_batch(imgs, (0, 0))
+    ref = oracle_mod.Extractor(1000, 1.2, 8, 20, 7)
+    seen = set()
+    for b in range(B):
+        rc, rk, rd, rmono = ref.extract(imgs[b])
+        assert n[b] == len(rk) and mono[b] == rmono
+        assert kps[b, : n[b]].tobytes() == rk.tobytes(), f"frame {b}"
+        assert np.array_equal(desc[b, : n[b]], rd), f"frame {b}"
+        seen.add(sha(rd))
+    assert len(seen) == B  # the frames really are different
+
+
+def test_device_resident_batch_api(orbx_mod, oracle_mod):
+    import torch
+    from dani_slam_b200 import synth
+    B, H, W, cap = 6, 480, 752, 1400
+    imgs = np.stack([synth.throughput_frame(200 + i, W, H) for i in range(B)])
+    dev = torch.device("cuda", 0)
+    d_img = torch.from_numpy(imgs).to(dev)
+    d_k = torch.zeros((B, cap, 7), dtype=torch.float32, device=dev)
+    d_d = torch.zeros((B, cap, 32), dtype=torch.uint8, device=dev)
+    d_n = torch.zeros(B, dtype=torch.int32, device=dev)
+    d_m = torch.zeros(B, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    ex = orbx_mod.ORBextractor(1200, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=B)
+    ex.extract_batch_device(d_img.data_ptr(), H * W, B, H, W, W, d_k.data_ptr(), d_d.data_ptr(), cap, d_n.data_ptr(), d_m.data_ptr())
+    ex.sync()
+    n, m = d_n.cpu().numpy(), d_m.cpu().numpy()
+    k = d_k.cpu().numpy().view(np.uint8).reshape(B, cap, 28)
+    dd = d_d.cpu().numpy()
+    ref = oracle_mod.Extractor(1200, 1.2, 8, 20, 7)
+    for b in range(B):
+        rc, rk, rd, rmono = ref.extract(imgs[b])
+        assert n[b] == len(rk) and m[b] == rmono
+        assert k[b, : n[b]].tobytes() == rk.tobytes()
+        assert np.array_equal(dd[b, : n[b]], rd)
+
+
+def test_edge_cases_and_error_codes(orbx_mod, oracle_mod):
+    from dani_slam_b200 import synth
+    ex = orbx_mod.ORBextractor(1000, 1.2, 8, 20, 7, max_width=640, max_height=480, max_batch=2)
+    mono, k, d = ex(np.zeros((0, 0), np.uint8))
+    assert mono == -1 and len(k) == 0                                    # empty image → -1 (:1129)
+    mono, k, d = ex(np.full((240, 320), 77, np.uint8))
+    assert mono == 0 and len(k) == 0 and d.shape == (0, 32)              # no keypoints → empty outputs (:1147)
+    with pytest.raises(orbx_mod.OrbxError) as e:                          # pyramid level too small
+        ex(np.zeros((60, 60), np.uint8))
+    assert e.value.code == orbx_mod.ERR_GEOMETRY
+    with pytest.raises(orbx_mod.OrbxError) as e:                          # larger than the handle's max size
+        ex(np.zeros((481, 640), np.uint8))
+    assert e.value.code == orbx_mod.ERR_ARG
+    ex.cap = 100                                                          # capacity error reports the need
+    with pytest.raises(orbx_mod.OrbxError) as e:
+        ex(synth.throughput_frame(1))
+    assert e.value.code == orbx_mod.ERR_CAPACITY
+    ex.cap = 1200
+    # the handle keeps working after errors and after a size change
+    for (w, h, seed) in [(640, 480, 4), (401, 333, 5), (640, 480, 6)]:
+        img = synth.parity_frame(seed, w, h)
+        mono, k, d = ex(img, None, (0, 1000))
+        rc, rk, rd, rmono = oracle_mod.Extractor(1000, 1.2, 8, 20, 7).extract(img, lap=(0, 1000))
+        assert mono == rmono and k.tobytes() == rk.tobytes() and np.array_equal(d, rd)
+
+
+def test_strided_input_and_other_parameters(orbx_mod, oracle_mod):
+    from dani_slam_b200 import synth
+    big = synth.throughput_frame(9, 800, 600)
+    view = big[50:530, 80:720]                                            # non-contiguous rows (step 800)
+    for (nf, sfac, nl, ini, mn) in [(1000, 1.2, 8, 20, 7), (500, 1.5, 4, 30, 10), (300, 1.1, 3, 12, 12), (2000, 1.2, 1, 20, 7)]:
+        ex = orbx_mod.ORBextractor(nf, sfac, nl, ini, mn, max_width=640, max_height=480)
+        mono, k, d = ex(view)
+        rc, rk, rd, rmono = oracle_mod.Extractor(nf, sfac, nl, ini, mn).extract(np.ascontiguousarray(view), cap=nf + 300)
+        assert rc == 0 and mono == rmono and k.tobytes() == rk.tobytes() and np.array_equal(d, rd), (nf, sfac, nl)
+        p = oracle_mod.Extractor(nf, sfac, nl, ini, mn).params()
+        assert np.array_equal(ex.GetScaleFactors(), p["sf"]) and np.array_equal(ex.GetInverseScaleFactors(), p["inv"])
+        assert np.array_equal(ex.GetScaleSigmaSquares(), p["sigma2"]) and np.array_equal(ex.GetInverseScaleSigmaSquares(), p["inv_sigma2"])
+        assert np.array_equal(ex.features_per_level(), p["quota"])
+
+
+def test_dynamic_area_and_lapping_variants(orbx_mod, oracle_mod):
+    from dani_slam_b200 import synth
+    img = synth.throughput_frame(31)
+    ex = orbx_mod.ORBextractor(1000, 1.2, 8, 20, 7, max_width=640, max_height=480)
+    ref = oracle_mod.Extractor(1000, 1.2, 8, 20, 7)
+    cases = [([], (0, 0)), ([(0, 0, 640, 480)], (0, 0)), ([(200, 100, 300, 250)], (100, 400)),
+             ([(10, 10, 5, 5), (600, 440, 40, 40), (320, 0, 1, 480)], (0, 1000)), ([(-50, -50, 100, 100)], (639, 639))]
+    for rects, lap in cases:
+        ex.mvDynamicArea = rects
+        mono, k, d = ex(img, None, lap)
+        rc, rk, rd, rmono = ref.extract(img, rects=rects, lap=lap)
+        assert mono == rmono and k.tobytes() == rk.tobytes() and np.array_equal(d, rd), (rects, lap)
+    ex.mvDynamicArea = [(0, 0, 640, 480)]
+    mono, k, d = ex(img)
+    assert len(k) == 0                                                    # everything deleted
+
+
+def test_tie_heavy_and_regular_patterns(orbx_mod, oracle_mod):
+    """Regular dot grids / checkerboards: equal FAST scores everywhere → NMS ties, quadtree (size, UL.x)
+    ties resolved by libstdc++'s std::sort order, first-maximum ties in best-per-node."""
+    H, W = 480, 640
+    frames = []
+    a = np.full((H, W), 90, np.uint8); a[5::11, 5::11] = 230; a[6::11, 5::11] = 230; frames.append(a)
+    yy, xx = np.mgrid[0:H, 0:W]
+    frames.append((((yy // 7 + xx // 7) & 1) * 140 + 50).astype(np.uint8))
+    c = np.full((H, W), 128, np.uint8); c[::13, ::17] = 10; c[3::13, 5::17] = 250; frames.append(c)
+    ex = orbx_mod.ORBextractor(1000, 1.2, 8, 20, 7, max_width=W, max_height=H)
+    ref = oracle_mod.Extractor(1000, 1.2, 8, 20, 7)
+    for i, f in enumerate(frames):
+        mono, k, d = ex(f)
+        rc, rk, rd, rmono = ref.extract(f)
+        assert len(rk) > 100, i
+        assert mono == rmono and k.tobytes() == rk.tobytes() and np.array_equal(d, rd), i
+
+
+def test_full_size_4k_frame(orbx_mod, oracle_mod):
+    """BASELINE config 5 size: one 3840×2160 frame, nFeatures=8000 — full parity plus structural properties."""
+    from dani_slam_b200 import synth
+    img = synth.throughput_frame(1, 3840, 2160)
+    ex = orbx_mod.ORBextractor(8000, 1.2, 8, 20, 7, max_width=3840, max_height=2160)
+    ex.cap = 8200
+    mono, k, d = ex(img)
+    assert 8000 <= len(k) <= 8000 + 16                                   # every level fills its quota (+≤2 each)
+    assert np.all(np.diff(k["octave"]) >= 0)                             # level-major order when nothing laps
+    assert (k["x"] >= 19).all() and (k["x"] <= 3840 - 19).all()
+    rc, rk, rd, rmono = oracle_mod.Extractor(8000, 1.2, 8, 20, 7).extract(img, cap=8200)
+    assert rc == 0 and mono == rmono and k.tobytes() == rk.tobytes() and np.array_equal(d, rd)

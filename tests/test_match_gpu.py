@@ -1,0 +1,124 @@
+"""GPU parity tests of the Hamming matching kernels vs the CPU oracle and the cv2 golden vectors."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+INT_MAX = 2**31 - 1
+
+
+def test_knn2_golden_cv2_bfmatcher(orbx_mod):
+    from dani_slam_b200 import synth
+    g = np.load(os.path.join(GOLDEN, "knn_cv2_s1234.npz"))
+    q, db = synth.knn_case(int(g["nq"]), int(g["ndb"]), seed=int(g["seed"]), planted_frac=0.1)
+    m = orbx_mod.ORBmatcher(0.7, True)
+    idx, dist = m.knnMatch(q, db)
+    assert np.array_equal(idx, g["idx"]) and np.array_equal(dist, g["dist"])
+    assert np.array_equal(m.ratio_test(dist, 0.7), g["keep"])
+
+
+@pytest.mark.parametrize("nq,ndb", [(1, 1), (3, 2), (5, 0), (64, 127), (64, 128), (64, 129), (257, 1000), (513, 4097),
+                                    (2000, 30000), (1025, 77777)])
+def test_knn2_vs_oracle_sizes_and_ties(orbx_mod, oracle_mod, nq, ndb):
+    from dani_slam_b200 import synth
+    q, db = synth.knn_case(nq, max(ndb, 1), seed=nq + ndb, planted_frac=0.3, dup_rows=8)
+    db = db[:ndb]
+    if ndb > 10:
+        db[ndb // 2] = db[3]                                              # exact duplicate rows: tie on distance
+        q[0] = db[3]
+    m = orbx_mod.ORBmatcher()
+    idx, dist = m.knnMatch(q, db)
+    ridx, rdist = oracle_mod.knn2(q, db, nthreads=8)
+    assert np.array_equal(idx, ridx) and np.array_equal(dist, rdist)
+    assert np.array_equal(m.ratio_test(dist), oracle_mod.ratio_test(dist))
+    if ndb < 2:
+        assert (idx[:, 1] == -1).all() and (dist[:, 1] == INT_MAX).all()
+
+
+def test_all_identical_rows_pick_lowest_indices(orbx_mod):
+    db = np.tile(np.arange(32, dtype=np.uint8), (5000, 1))
+    q = db[:10].copy()
+    idx, dist = orbx_mod.ORBmatcher().knnMatch(q, db)
+    assert (idx == np.array([0, 1])).all() and (dist == 0).all()
+
+
+def test_sharded_merge_equals_unsharded_on_one_gpu(orbx_mod, oracle_mod):
+    """DB split into G shards, per-shard top-2 with global indices, merge kernel == unsharded search.
+    (The cross-GPU all-gather itself is covered by tests/test_sharded_gloo.py and bench.py --gpus N.)"""
+    import torch
+    from dani_slam_b200 import synth
+    from dani_slam_b200.sharded import shard_bounds
+    nq, ndb = 300, 50001
+    q, db = synth.knn_case(nq, ndb, seed=99, planted_frac=0.2, dup_rows=8)
+    db[40000] = db[7]; q[5] = db[7]
+    dev = torch.device("cuda", 0)
+    dq, ddb = torch.from_numpy(q).to(dev), torch.from_numpy(db).to(dev)
+    m = orbx_mod.ORBmatcher()
+    ridx, rdist = oracle_mod.knn2(q, db, nthreads=8)
+    for G in [1, 2, 3, 8]:
+        ia = torch.empty((G, nq, 2), dtype=torch.int32, device=dev)
+        da = torch.empty((G, nq, 2), dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        for g in range(G):
+            lo, hi = shard_bounds(ndb, g, G)
+            m.knn2_device(dq.data_ptr(), nq, ddb[lo:hi].data_ptr(), hi - lo, lo, ia[g].data_ptr(), da[g].data_ptr())
+        oi = torch.empty((nq, 2), dtype=torch.int32, device=dev)
+        od = torch.empty((nq, 2), dtype=torch.int32, device=dev)
+        m.merge_device(ia.data_ptr(), da.data_ptr(), G, nq, oi.data_ptr(), od.data_ptr())
+        m.sync()
+        assert np.array_equal(oi.cpu().numpy(), ridx) and np.array_equal(od.cpu().numpy(), rdist), G
+
+
+def test_top2_lists_vs_oracle(orbx_mod, oracle_mod):
+    rng = np.random.default_rng(5)
+    from dani_slam_b200 import synth
+    q, db = synth.knn_case(400, 3000, seed=8, planted_frac=0.5)
+    lens = rng.integers(0, 60, 400)
+    lens[:5] = 0
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    cand = rng.integers(0, 3000, off[-1]).astype(np.int32)
+    bi, bd, sd = orbx_mod.ORBmatcher().top2_lists(q, db, cand, off)
+    rbi, rbd, rsd = oracle_mod.top2_lists(q, db, cand, off)
+    assert np.array_equal(bi, rbi) and np.array_equal(bd, rbd) and np.array_equal(sd, rsd)
+    assert (bi[:5] == -1).all() and (bd[:5] == 256).all()
+
+
+def test_rot_hist_filter_vs_oracle(orbx_mod, oracle_mod):
+    rng = np.random.default_rng(6)
+    m = orbx_mod.ORBmatcher()
+    for n in [0, 1, 7, 300, 5000]:
+        a = rng.uniform(0, 360, n).astype(np.float32)
+        b = (a - rng.choice([0, 3, 29, 45, 200, 359.5], n, p=[.5, .2, .1, .1, .05, .05])).astype(np.float32)
+        b = np.where(b < 0, b + 360, b).astype(np.float32)
+        if n > 10:
+            a[:4] = [15.0, 45.0, 359.99, 0.0]; b[:4] = [0.0, 0.0, 0.0, 359.99]    # .5 bin edges, wrap-around
+        assert np.array_equal(m.rot_hist_filter(a, b), oracle_mod.rot_hist_filter(a, b)), n
+
+
+def test_descriptor_distance(orbx_mod, oracle_mod):
+    import ctypes as C
+    rng = np.random.default_rng(2)
+    a = rng.integers(0, 256, (50, 32), dtype=np.uint8)
+    b = rng.integers(0, 256, (50, 32), dtype=np.uint8)
+    for i in range(50):
+        assert orbx_mod.ORBmatcher.DescriptorDistance(a[i], b[i]) == int(np.unpackbits(a[i] ^ b[i]).sum())
+
+
+def test_large_db_properties(orbx_mod, oracle_mod):
+    """Config-4 shape at reduced DB size (2000 × 2M): planted rows are found at the planted distance, top-2 is
+    sorted, and a random sample of queries equals the oracle's full scan."""
+    from dani_slam_b200 import synth
+    nq, ndb = 2000, 2_000_000
+    q, db = synth.knn_case(nq, ndb, seed=1234, planted_frac=0.01, dup_rows=4)
+    idx, dist = orbx_mod.ORBmatcher().knnMatch(q, db)
+    assert (dist[:, 0] <= dist[:, 1]).all() and (idx >= 0).all() and (idx < ndb).all()
+    d0 = np.unpackbits(q ^ db[idx[:, 0]], axis=1).sum(axis=1)
+    d1 = np.unpackbits(q ^ db[idx[:, 1]], axis=1).sum(axis=1)
+    assert np.array_equal(d0, dist[:, 0]) and np.array_equal(d1, dist[:, 1])
+    assert (dist[:20, 0] <= 40).all()                                     # planted with ≤40 flipped bits
+    sample = np.r_[0:8, 1000:1008]
+    ridx, rdist = oracle_mod.knn2(q[sample], db, nthreads=8)
+    assert np.array_equal(idx[sample], ridx) and np.array_equal(dist[sample], rdist)
