@@ -113,32 +113,84 @@ __global__ void __launch_bounds__(256) k_pyr_level(ExParams p, int l) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2: FAST-9_16 per cell (cv::FAST + NMS on the cell ROI)
+// K2: FAST-9_16 per cell (cv::FAST + NMS on the cell ROI).  One warp per cell.
+//
+// The exact FAST score of EVERY interior pixel is computed without any data-dependent branch, two
+// pixels per instruction, with Blackwell's packed 3-input min/max (VIMNMX3.U16x2, the DPX family):
+//   M = max( v − min_k max(ring[k..k+8]),  max_k min(ring[k..k+8]) − v )      (k circular over 16)
+// which equals OpenCV's max-over-arcs-of-min|diff| (A4) because min_arc(v−r) = v − max_arc(r).
+// A window of 9 is max3(max3(r0,r1,r2), max3(r3,r4,r5), max3(r6,r7,r8)): 32 instructions per polarity
+// for all 16 arcs.  A lane owns 4 horizontally adjacent pixels (two u16x2 pairs); ring samples are
+// carved out of three aligned 32-bit shared-memory words per row with PRMT.
 // ------------------------------------------------------------------------------------------------
 struct FastSmem {
     int roiPitch, scorePitch;
-    int roiOff, scoreOff, queueOff, listOff, total;
+    int roiOff, scoreOff, listOff, total;
 };
 __host__ __device__ inline FastSmem fast_smem_layout(int maxCw, int maxCh, int maxSlotCap) {
     FastSmem s;
-    s.roiPitch = (maxCw + 3) & ~3;
-    s.scorePitch = (maxCw - 6 + 2 + 3) & ~3;
+    const int G = (maxCw - 6 + 3) / 4;      // 4-pixel groups per interior row
+    s.roiPitch = 4 * G + 8;                 // ROI column x lives at byte x+1; a group reads bytes 4g..4g+11
+    s.scorePitch = 4 * G + 8;               // interior column c lives at byte c+4
     s.roiOff = 0;
     s.scoreOff = s.roiOff + s.roiPitch * maxCh;
-    s.queueOff = (s.scoreOff + s.scorePitch * (maxCh - 6 + 2) + 3) & ~3;
-    s.listOff = (s.queueOff + 2 * (maxCw - 6) * (maxCh - 6) + 3) & ~3;
+    s.listOff = s.scoreOff + s.scorePitch * (maxCh - 6 + 2);
     s.total = (s.listOff + 4 * maxSlotCap + 15) & ~15;
     return s;
 }
 
-// does a 16-bit circular mask contain 9 contiguous set bits?
-__device__ __forceinline__ bool has_arc9(uint32_t m) {
-    uint32_t x = m | (m << 16);
-    uint32_t r = x & (x >> 1);
-    r &= r >> 2;
-    r &= r >> 4;       // runs of 8
-    r &= x >> 8;       // runs of 9
-    return (r & 0xffffu) != 0;
+struct Row3 { uint32_t w0, w1, w2; };
+__device__ __forceinline__ Row3 ld_row3(const uint8_t *p) {
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(p);
+    Row3 r; r.w0 = q[0]; r.w1 = q[1]; r.w2 = q[2];
+    return r;
+}
+// bytes (B, B+1) of the 12-byte span {w0,w1,w2} as a zero-extended u16x2
+template <int B>
+__device__ __forceinline__ uint32_t pair_at(const Row3 &r) {
+    static_assert(B >= 0 && B <= 10, "pair outside the 12-byte span");
+    if constexpr (B <= 2) return __byte_perm(r.w0, 0u, 0x4040u + B + ((B + 1) << 8));
+    else if constexpr (B == 3) return __byte_perm(__byte_perm(r.w0, r.w1, 0x5432u), 0u, 0x4241u);
+    else if constexpr (B <= 6) return __byte_perm(r.w1, 0u, 0x4040u + (B - 4) + ((B - 3) << 8));
+    else if constexpr (B == 7) return __byte_perm(__byte_perm(r.w1, r.w2, 0x5432u), 0u, 0x4241u);
+    else return __byte_perm(r.w2, 0u, 0x4040u + (B - 8) + ((B - 7) << 8));
+}
+
+// exact FAST measure minus lowTh, clamped at 0, for the pixel pair P (0/1) of a 4-pixel group
+template <int P>
+__device__ __forceinline__ uint32_t fast_pair_score(const Row3 (&R)[7], uint32_t negT2) {
+    // ring order k=0..15 = (dx,dy): (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
+    // R[i] is the row dy = i-3; byte index of pixel pair P at horizontal offset dx is 4+2P+dx
+    constexpr int C = 4 + 2 * P;
+    uint32_t r[16];
+    r[0] = pair_at<C + 0>(R[6]);  r[1] = pair_at<C + 1>(R[6]);  r[2] = pair_at<C + 2>(R[5]);  r[3] = pair_at<C + 3>(R[4]);
+    r[4] = pair_at<C + 3>(R[3]);  r[5] = pair_at<C + 3>(R[2]);  r[6] = pair_at<C + 2>(R[1]);  r[7] = pair_at<C + 1>(R[0]);
+    r[8] = pair_at<C + 0>(R[0]);  r[9] = pair_at<C - 1>(R[0]);  r[10] = pair_at<C - 2>(R[1]); r[11] = pair_at<C - 3>(R[2]);
+    r[12] = pair_at<C - 3>(R[3]); r[13] = pair_at<C - 3>(R[4]); r[14] = pair_at<C - 2>(R[5]); r[15] = pair_at<C - 1>(R[6]);
+    const uint32_t v2 = pair_at<C>(R[3]);
+    uint32_t tmx[16], tmn[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        tmx[k] = __vimax3_u16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+        tmn[k] = __vimin3_u16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+    }
+    uint32_t nmx[16], nmn[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        nmx[k] = __vimax3_u16x2(tmx[k], tmx[(k + 3) & 15], tmx[(k + 6) & 15]);   // max of ring[k..k+8]
+        nmn[k] = __vimin3_u16x2(tmn[k], tmn[(k + 3) & 15], tmn[(k + 6) & 15]);   // min of ring[k..k+8]
+    }
+    uint32_t lo = __vimin3_u16x2(nmx[0], nmx[1], nmx[2]), hi = __vimax3_u16x2(nmn[0], nmn[1], nmn[2]);
+#pragma unroll
+    for (int k = 3; k < 15; k += 2) {
+        lo = __vimin3_u16x2(lo, nmx[k], nmx[k + 1]);
+        hi = __vimax3_u16x2(hi, nmn[k], nmn[k + 1]);
+    }
+    lo = __vminu2(lo, nmx[15]);
+    hi = __vmaxu2(hi, nmn[15]);
+    const uint32_t A = __vsub2(v2, lo), B = __vsub2(hi, v2);          // signed 16-bit per half
+    const uint32_t M = __vmaxs2(A, B);
+    return __viaddmax_s16x2(M, negT2, 0u);                            // max(M - lowTh, 0) per half
 }
 
 template <int WPB>
@@ -153,7 +205,6 @@ __global__ void __launch_bounds__(WPB * 32) k_fast_cells(ExParams p, int maxSlot
     uint8_t *base = smem_raw + (size_t)warp * L.total;
     uint8_t *roi = base + L.roiOff;
     uint8_t *score = base + L.scoreOff;
-    uint16_t *queue = reinterpret_cast<uint16_t *>(base + L.queueOff);
     uint32_t *list = reinterpret_cast<uint32_t *>(base + L.listOff);
 
     int pitch;
@@ -165,97 +216,83 @@ __global__ void __launch_bounds__(WPB * 32) k_fast_cells(ExParams p, int maxSlot
         if (lane == 0) *cntOut = 0;
         return;
     }
-    // stage the ROI
+    const int rp = L.roiPitch, sp = L.scorePitch;
+    // stage the ROI: column x at byte x+1 so that every 4-pixel group is word aligned
     const uint8_t *src = img + (long long)cell.y0 * pitch + cell.x0;
     for (int y = 0; y < ch; ++y)
-        for (int x = lane; x < cw; x += 32) roi[y * L.roiPitch + x] = src[(long long)y * pitch + x];
-    // zero the score map (1-px frame of zeros = "outside the cell interior counts 0")
+        for (int x = lane; x < cw; x += 32) roi[y * rp + x + 1] = src[(long long)y * pitch + x];
+    // zero the score map (its 1-px frame of zeros = "outside the cell interior counts 0")
     {
         uint32_t *s32 = reinterpret_cast<uint32_t *>(score);
-        const int nw = (L.scorePitch * (ih + 2)) >> 2;
+        const int nw = (sp * (ih + 2)) >> 2;
         for (int i = lane; i < nw; i += 32) s32[i] = 0;
     }
     __syncwarp();
 
-    const int rp = L.roiPitch;
-    const int off[16] = {3 * rp,      3 * rp + 1,  2 * rp + 2,  rp + 3,  3,        -rp + 3,  -2 * rp + 2, -3 * rp + 1,
-                         -3 * rp,     -3 * rp - 1, -2 * rp - 2, -rp - 3, -3,       rp - 3,   2 * rp - 2,  3 * rp - 1};
+    const int G = (iw + 3) >> 2;             // groups per row (≤ 19 for cells ≤ 75 px wide)
+    const int RP = 32 / G;                   // interior rows handled per warp pass
+    const int lr = lane / G, lg = lane - lr * G;
+    const bool laneOn = lr < RP;
+    const int nValid = min(max(iw - 4 * lg, 0), 4);
+    const uint32_t colMask = nValid >= 4 ? 0xffffffffu : ((1u << (8 * nValid)) - 1u);
     const int t = g.lowTh;
-    const int npx = iw * ih;
-    const uint32_t recip = ((1u << 20) + iw - 1) / iw;  // floor(i/iw) == (i*recip)>>20 for i < 2^20/iw
+    const uint32_t negT2 = ((uint32_t)(-t) & 0xffffu) * 0x10001u;
 
-    // phase A: exact corner test (M > lowTh) for every interior pixel → queue of corner pixels
-    int nq = 0;
-    for (int i0 = 0; i0 < npx; i0 += 32) {
-        const int i = i0 + lane;
-        bool corner = false;
-        if (i < npx) {
-            const int y = (int)(((uint32_t)i * recip) >> 20), x = i - y * iw;
-            const uint8_t *c0 = roi + (y + 3) * rp + (x + 3);
-            const int v = c0[0];
-            const int hi = v + t, lo = v - t;
-            uint32_t mb = 0, md = 0;
+    // pass 1: score map (value = M - lowTh clamped at 0; real score = value + lowTh - 1)
+    for (int y0 = 0; y0 < ih; y0 += RP) {
+        const int yi = y0 + lr;
+        if (laneOn && yi < ih) {
+            const uint8_t *rowp = roi + yi * rp + 4 * lg;  // ROI row (yi+3)+dy = yi + i for i = 0..6
+            Row3 R[7];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const int r = c0[off[k]];
-                mb |= (uint32_t)(r > hi) << k;
-                md |= (uint32_t)(r < lo) << k;
-            }
-            corner = has_arc9(mb) || has_arc9(md);
+            for (int i = 0; i < 7; ++i) R[i] = ld_row3(rowp + i * rp);
+            const uint32_t s0 = fast_pair_score<0>(R, negT2), s1 = fast_pair_score<1>(R, negT2);
+            const uint32_t word = __byte_perm(s0, s1, 0x6420u) & colMask;
+            *reinterpret_cast<uint32_t *>(score + (yi + 1) * sp + 4 * lg + 4) = word;
         }
-        const uint32_t bal = __ballot_sync(0xffffffffu, corner);
-        if (corner) queue[nq + __popc(bal & ((1u << lane) - 1))] = (uint16_t)i;
-        nq += __popc(bal);
     }
     __syncwarp();
 
-    // phase B: exact score M-1 for the queued corners (max over 9-arcs of min |diff|, both polarities)
-    for (int qi = lane; qi < nq; qi += 32) {
-        const int i = queue[qi];
-        const int y = (int)(((uint32_t)i * recip) >> 20), x = i - y * iw;
-        const uint8_t *c0 = roi + (y + 3) * rp + (x + 3);
-        const int v = c0[0];
-        int d[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) d[k] = v - (int)c0[off[k]];
-        int lo2[16], hi2[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) { lo2[k] = min(d[k], d[(k + 1) & 15]); hi2[k] = max(d[k], d[(k + 1) & 15]); }
-        int lo4[16], hi4[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) { lo4[k] = min(lo2[k], lo2[(k + 2) & 15]); hi4[k] = max(hi2[k], hi2[(k + 2) & 15]); }
-        int A = -256, Bm = 256;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const int lo8 = min(lo4[k], lo4[(k + 4) & 15]), hi8 = max(hi4[k], hi4[(k + 4) & 15]);
-            A = max(A, min(lo8, d[(k + 8) & 15]));
-            Bm = min(Bm, max(hi8, d[(k + 8) & 15]));
-        }
-        const int M = max(A, -Bm);
-        score[(y + 1) * L.scorePitch + (x + 1)] = (uint8_t)(M - 1);
-    }
-    __syncwarp();
-
-    // phase C: cell-local 3×3 strict NMS, row-major ordered list; count survivors above iniTh
-    const int spitch = L.scorePitch;
+    // pass 2: cell-local 3×3 strict NMS → row-major ordered list; count survivors above iniTh
+    const int iniRel = g.iniTh - t + 1;      // value >= iniRel  ⇔  M > iniTh
     int n = 0, nIni = 0;
-    for (int i0 = 0; i0 < npx; i0 += 32) {
-        const int i = i0 + lane;
-        bool keep = false;
-        int s = 0, x = 0, y = 0;
-        if (i < npx) {
-            y = (int)(((uint32_t)i * recip) >> 20);
-            x = i - y * iw;
-            const uint8_t *sc = score + (y + 1) * spitch + (x + 1);
-            s = sc[0];
-            keep = s > 0 && s > sc[-1] && s > sc[1] && s > sc[-spitch - 1] && s > sc[-spitch] &&
-                   s > sc[-spitch + 1] && s > sc[spitch - 1] && s > sc[spitch] && s > sc[spitch + 1];
+    for (int y0 = 0; y0 < ih; y0 += RP) {
+        const int yi = y0 + lr;
+        uint32_t flags = 0, vals = 0;        // flags: bit i = pixel i of the group survives
+        if (laneOn && yi < ih) {
+            const uint8_t *rowp = score + yi * sp + 4 * lg;   // score rows yi, yi+1 (centre), yi+2
+            const Row3 T = ld_row3(rowp), Cn = ld_row3(rowp + sp), Bt = ld_row3(rowp + 2 * sp);
+            vals = Cn.w1;
+            if (vals != 0) {
+                // pair 0 centre bytes (4,5), pair 1 centre bytes (6,7)
+                const uint32_t tL0 = pair_at<3>(T), tM0 = pair_at<4>(T), tR0 = pair_at<5>(T), tM1 = pair_at<6>(T), tR1 = pair_at<7>(T);
+                const uint32_t bL0 = pair_at<3>(Bt), bM0 = pair_at<4>(Bt), bR0 = pair_at<5>(Bt), bM1 = pair_at<6>(Bt), bR1 = pair_at<7>(Bt);
+                const uint32_t cL0 = pair_at<3>(Cn), cM0 = pair_at<4>(Cn), cR0 = pair_at<5>(Cn), cM1 = pair_at<6>(Cn), cR1 = pair_at<7>(Cn);
+                const uint32_t n0 = __vimax3_u16x2(__vimax3_u16x2(tL0, tM0, tR0), __vimax3_u16x2(bL0, bM0, bR0), __vmaxu2(cL0, cR0));
+                const uint32_t n1 = __vimax3_u16x2(__vimax3_u16x2(tR0, tM1, tR1), __vimax3_u16x2(bR0, bM1, bR1), __vmaxu2(cR0, cR1));
+                const uint32_t d0 = __vsub2(n0, cM0), d1 = __vsub2(n1, cM1);   // negative half ⇔ centre > all 8 neighbours
+                flags = ((d0 >> 15) & 1u) | ((d0 >> 30) & 2u) | ((d1 >> 13) & 4u) | ((d1 >> 28) & 8u);
+            }
         }
-        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-        const uint32_t balIni = __ballot_sync(0xffffffffu, keep && s >= g.iniTh);  // M-1 >= iniTh ⇔ M > iniTh
-        if (keep) list[n + __popc(bal & ((1u << lane) - 1))] = (uint32_t)(x + 3) | ((uint32_t)(y + 3) << 8) | ((uint32_t)s << 16);
-        n += __popc(bal);
-        nIni += __popc(balIni);
+        // a group of 4 adjacent pixels holds at most 2 local maxima
+        const int cntLane = __popc(flags);
+        uint32_t iniFlags = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if ((flags >> i) & 1u) iniFlags |= (uint32_t)((int)((vals >> (8 * i)) & 0xff) >= iniRel) << i;
+        const int cntIni = __popc(iniFlags);
+        const uint32_t lt = (1u << lane) - 1u;
+        const uint32_t b0 = __ballot_sync(0xffffffffu, cntLane & 1), b1 = __ballot_sync(0xffffffffu, cntLane & 2);
+        const uint32_t i0 = __ballot_sync(0xffffffffu, cntIni & 1), i1 = __ballot_sync(0xffffffffu, cntIni & 2);
+        int at = n + __popc(b0 & lt) + 2 * __popc(b1 & lt);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if ((flags >> i) & 1u) {
+                const uint32_t s = ((vals >> (8 * i)) & 0xff) + (uint32_t)(t - 1);   // FAST score = M - 1
+                list[at++] = (uint32_t)(4 * lg + i + 3) | ((uint32_t)(yi + 3) << 8) | (s << 16);
+            }
+        n += __popc(b0) + 2 * __popc(b1);
+        nIni += __popc(i0) + 2 * __popc(i1);
     }
     __syncwarp();
     // retry rule (:843-846): if the iniTh pass is empty after NMS, the minTh pass is the result
