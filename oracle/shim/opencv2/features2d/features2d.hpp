@@ -1,0 +1,2 @@
+// shim: see ../opencv.hpp
+#include "../opencv.hpp"

@@ -1,0 +1,61 @@
+// Drives include/ORBextractor.h (the drop-in adapter, reference signatures) and include/ORBmatcher_orbx.h
+// exactly like Frame::ExtractORB does (src/Frame.cc:420-427), against the opencv2 shim, and compares the
+// result with the reference's own ORBextractor.cc (oracle/_ref) when that library is linked in.
+// Usage: adapter_check <width> <height> <seed>   (prints "OK n mono" or a diagnostic; exit code 0/1)
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "ORBextractor.h"
+#include "ORBmatcher_orbx.h"
+
+extern "C" {
+void *ref_create(int, float, int, int, int);
+void ref_destroy(void *);
+int ref_extract(void *, const uint8_t *, int, int, size_t, const int32_t *, int, int, int, orc_keypoint *, uint8_t *, int, int *, int *);
+}
+
+int main(int argc, char **argv) {
+    const int W = argc > 1 ? atoi(argv[1]) : 640, H = argc > 2 ? atoi(argv[2]) : 480;
+    unsigned s = argc > 3 ? (unsigned)atoi(argv[3]) : 1u;
+    cv::Mat img(H, W, CV_8UC1);
+    // blocky random texture: plenty of corners
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            unsigned h = (unsigned)(x / 5) * 73856093u ^ (unsigned)(y / 5) * 19349663u ^ s * 83492791u;
+            h ^= h >> 13; h *= 0x5bd1e995u; h ^= h >> 15;
+            img.at<uchar>(y, x) = (uchar)(h & 0xff);
+        }
+    ORB_SLAM3::ORBextractor ex(1000, 1.2f, 8, 20, 7);
+    ex.mvDynamicArea.push_back(cv::Rect2i(40, 30, 100, 80));
+    std::vector<cv::KeyPoint> keys;
+    cv::Mat desc, mask;
+    std::vector<int> lap = {0, 1000};
+    const int mono = ex(img, mask, keys, desc, lap);
+    if (mono < 0) { printf("FAIL extractor returned %d\n", mono); return 1; }
+    ex.MaterializePyramid();
+    if (ex.mvImagePyramid[1].cols != cvRound((float)W * ex.GetInverseScaleFactors()[1])) { printf("FAIL pyramid size\n"); return 1; }
+
+    void *ref = ref_create(1000, 1.2f, 8, 20, 7);
+    std::vector<orc_keypoint> rk(1200);
+    std::vector<uint8_t> rd(1200 * 32);
+    int rn = 0, rmono = 0;
+    const int32_t rect[4] = {40, 30, 100, 80};
+    ref_extract(ref, img.data, H, W, (size_t)img.step, rect, 1, 0, 1000, rk.data(), rd.data(), 1200, &rn, &rmono);
+    ref_destroy(ref);
+    if (rn != (int)keys.size() || rmono != mono) { printf("FAIL count %d vs %zu, mono %d vs %d\n", rn, keys.size(), rmono, mono); return 1; }
+    if (memcmp(rk.data(), keys.data(), (size_t)rn * 28) != 0) { printf("FAIL keypoints differ\n"); return 1; }
+    for (int i = 0; i < rn; ++i)
+        if (memcmp(&rd[(size_t)i * 32], desc.ptr(i), 32) != 0) { printf("FAIL descriptor %d differs\n", i); return 1; }
+
+    // matcher: left/right style kNN on the extracted descriptors against themselves shifted by one
+    ORB_SLAM3::ORBmatcherDevice m(0.7f, true);
+    std::vector<int> idx, dist;
+    if (!m.KnnMatch2(desc.ptr(0), rn, desc.ptr(0), rn, idx, dist)) { printf("FAIL knn\n"); return 1; }
+    for (int i = 0; i < rn; ++i)
+        if (dist[2 * i] != 0) { printf("FAIL self match %d\n", i); return 1; }
+    if (ORB_SLAM3::ORBmatcherDevice::DescriptorDistance(desc.ptr(0), desc.ptr(0)) != 0) { printf("FAIL distance\n"); return 1; }
+    printf("OK %d %d\n", rn, mono);
+    return 0;
+}
