@@ -355,7 +355,7 @@ __device__ int block_exclusive_scan(int *a, int n, int *scratch /* >= QT_THREADS
 
 struct QtSmem {
     int boxOff[2], cntOff[2], childCntOff, childPosOff, keptPosOff, pendOff, pendIdxOff, sortOff,
-        bestOff, prefixOff, scratchOff, total;
+        bestOff, prefixOff, scratchOff, tmp4Off, total;
 };
 __host__ __device__ inline QtSmem qt_smem_layout(int nodeCap, int maxCellsLevel) {
     QtSmem s;
@@ -373,6 +373,7 @@ __host__ __device__ inline QtSmem qt_smem_layout(int nodeCap, int maxCellsLevel)
     s.bestOff = o; o += 4 * nodeCap;
     s.prefixOff = o; o += 4 * (maxCellsLevel + 1);
     s.scratchOff = o; o += 4 * (QT_THREADS + 2);
+    s.tmp4Off = o; o += 16 * nodeCap;
     s.total = (o + 15) & ~15;
     return s;
 }
@@ -396,13 +397,16 @@ __device__ __forceinline__ short4 qt_child_box(short4 bx, int q) {  // box = {x0
     return c;
 }
 
+// Per-point state lives in two DENSE per-(frame, level) arrays indexed by the candidate's order index
+// (prefix over cells in processing order + rank inside the cell — the position it would have in the
+// reference's vToDistributeKeys):  ptXY[i] = drifted (x, y);  ptNode[i] = node position (bits 15:0) |
+// FAST score (bits 23:16) | quadrant scratch (bits 31:30), or ORBX_NODE_ERASED.
 __global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCapMax, int maxCellsLevel) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const OrbxGeom &g = *p.g;
     const int l = blockIdx.x, b = blockIdx.y;
     const OrbxLevel &LV = g.lv[l];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nWarps = QT_THREADS / 32;
+    const int tid = threadIdx.x;
     const QtSmem S = qt_smem_layout(nodeCapMax, maxCellsLevel);
     orbx_sort::elem_t *sortbuf = reinterpret_cast<orbx_sort::elem_t *>(smem_raw + S.sortOff);
     short4 *box[2] = {reinterpret_cast<short4 *>(smem_raw + S.boxOff[0]), reinterpret_cast<short4 *>(smem_raw + S.boxOff[1])};
@@ -415,19 +419,19 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCap
     unsigned *best = reinterpret_cast<unsigned *>(smem_raw + S.bestOff);
     int *prefix = reinterpret_cast<int *>(smem_raw + S.prefixOff);
     int *scratch = reinterpret_cast<int *>(smem_raw + S.scratchOff);
-    __shared__ int sh_size, sh_nPend, sh_C;
+    int *tmp4 = reinterpret_cast<int *>(smem_raw + S.tmp4Off);
+    __shared__ int sh_size, sh_C;
 
     const int nCells = LV.nCells;
     const int N = LV.quota;
     const int *cellCnt = p.cellCnt + (long long)b * g.nCellsTotal + LV.cellBase;
     const OrbxCell *cells = p.cells + LV.cellBase;
-    uint32_t *slots = p.slots + (long long)b * g.slotsTotal;
-    float2 *ptXY = p.ptXY + (long long)b * g.slotsTotal;
-    uint32_t *ptNode = p.ptNode + (long long)b * g.slotsTotal;
+    const uint32_t *slots = p.slots + (long long)b * g.slotsTotal;
+    float2 *ptXY = p.ptXY + (long long)b * g.slotsTotal + LV.slotBase;
+    uint32_t *ptNode = p.ptNode + (long long)b * g.slotsTotal + LV.slotBase;
     float4 *sel = p.sel + (long long)b * g.selTotal + LV.selBase;
     int *selCntOut = p.selCnt + b * g.nlevels + l;
 
-    // candidate order index = prefix over cells in processing order + rank inside the cell
     for (int c = tid; c < nCells; c += QT_THREADS) prefix[c] = cellCnt[c];
     __syncthreads();
     const int nPts = block_exclusive_scan(prefix, nCells, scratch);
@@ -444,46 +448,47 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCap
     const float sc = LV.sf, inv = __fdiv_rn(1.f, sc);
     const float hX = LV.hX;
     const int nRects = g.nRects;
-    for (int c = warp; c < nCells; c += nWarps) {
-        const OrbxCell cell = cells[c];
-        const int n = cellCnt[c];
+    for (int i = tid; i < nPts; i += QT_THREADS) {
+        int lo = 0, hi = nCells;  // last cell with prefix[c] <= i
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (prefix[mid] <= i) lo = mid; else hi = mid;
+        }
+        const OrbxCell cell = cells[lo];
+        const uint32_t e = slots[cell.slot + (i - prefix[lo])];
         const int trips = nCells - cell.seq;  // filter passes this cell's keypoints live through
-        for (int k = lane; k < n; k += 32) {
-            const long long slot = cell.slot + k;
-            const uint32_t e = slots[slot];
-            float x = __fadd_rn((float)(e & 0xff), (float)(cell.cx * LV.wCell));  // pt.x += j*wCell (:863)
-            float y = __fadd_rn((float)((e >> 8) & 0xff), (float)(cell.cy * LV.hCell));
-            bool erased = false;
-            for (int t = 0; t < trips; ++t) {
-                const float xs = __fmul_rn(__fadd_rn(x, (float)ORBX_BORDER), sc);
-                const float ys = __fmul_rn(__fadd_rn(y, (float)ORBX_BORDER), sc);
-                if (nRects > 0) {
-                    const int px = __float2int_rn(xs), py = __float2int_rn(ys);  // Point2f → Point2i
-                    for (int r = 0; r < nRects; ++r) {
-                        const int rx = g.rects[4 * r], ry = g.rects[4 * r + 1];
-                        if (rx <= px && px < rx + g.rects[4 * r + 2] && ry <= py && py < ry + g.rects[4 * r + 3]) {
-                            erased = true;
-                            break;
-                        }
+        float x = __fadd_rn((float)(e & 0xff), (float)(cell.cx * LV.wCell));  // pt.x += j*wCell (:863)
+        float y = __fadd_rn((float)((e >> 8) & 0xff), (float)(cell.cy * LV.hCell));
+        bool erased = false;
+        for (int t = 0; t < trips; ++t) {
+            const float xs = __fmul_rn(__fadd_rn(x, (float)ORBX_BORDER), sc);
+            const float ys = __fmul_rn(__fadd_rn(y, (float)ORBX_BORDER), sc);
+            if (nRects > 0) {
+                const int px = __float2int_rn(xs), py = __float2int_rn(ys);  // Point2f → Point2i
+                for (int r = 0; r < nRects; ++r) {
+                    const int rx = g.rects[4 * r], ry = g.rects[4 * r + 1];
+                    if (rx <= px && px < rx + g.rects[4 * r + 2] && ry <= py && py < ry + g.rects[4 * r + 3]) {
+                        erased = true;
+                        break;
                     }
-                    if (erased) break;
                 }
-                const float xn = __fsub_rn(__fmul_rn(xs, inv), (float)ORBX_BORDER);
-                const float yn = __fsub_rn(__fmul_rn(ys, inv), (float)ORBX_BORDER);
-                const bool fixed = (xn == x) && (yn == y);
-                x = xn;
-                y = yn;
-                if (fixed) break;  // later trips reproduce this one exactly
+                if (erased) break;
             }
-            ptXY[slot] = make_float2(x, y);
-            if (erased) {
-                ptNode[slot] = ORBX_NODE_ERASED;
-            } else {
-                int bin = (int)__fdiv_rn(x, hX);  // vpIniNodes[kp.pt.x/hX] (:584)
-                bin = min(max(bin, 0), nIni - 1);
-                ptNode[slot] = (uint32_t)bin;
-                atomicAdd(&childCnt[bin], 1);
-            }
+            const float xn = __fsub_rn(__fmul_rn(xs, inv), (float)ORBX_BORDER);
+            const float yn = __fsub_rn(__fmul_rn(ys, inv), (float)ORBX_BORDER);
+            const bool fixed = (xn == x) && (yn == y);
+            x = xn;
+            y = yn;
+            if (fixed) break;  // later trips reproduce this one exactly
+        }
+        ptXY[i] = make_float2(x, y);
+        if (erased) {
+            ptNode[i] = ORBX_NODE_ERASED;
+        } else {
+            int bin = (int)__fdiv_rn(x, hX);  // vpIniNodes[kp.pt.x/hX] (:584)
+            bin = min(max(bin, 0), nIni - 1);
+            ptNode[i] = (uint32_t)bin | ((e >> 16) << 16);
+            atomicAdd(&childCnt[bin], 1);
         }
     }
     __syncthreads();
@@ -506,18 +511,16 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCap
         sh_size = m;
     }
     __syncthreads();
-    for (int c = warp; c < nCells; c += nWarps) {
-        const long long s0 = cells[c].slot;
-        const int n = cellCnt[c];
-        for (int k = lane; k < n; k += 32) {
-            const uint32_t nd = ptNode[s0 + k];
-            if (nd != ORBX_NODE_ERASED) ptNode[s0 + k] = (uint32_t)keptPos[nd];
+    int size = sh_size;
+    if (size != nIni) {  // some root was empty: renumber
+        for (int i = tid; i < nPts; i += QT_THREADS) {
+            const uint32_t v = ptNode[i];
+            if (v != ORBX_NODE_ERASED) ptNode[i] = (v & 0x00ff0000u) | (uint32_t)keptPos[v & 0xffffu];
         }
+        __syncthreads();
     }
-    __syncthreads();
 
     int cur = 0;
-    int size = sh_size;
     bool done = (size == 0);
     bool phase2 = false;
     int nPend = 0;
@@ -530,26 +533,25 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCap
             // ---- full pass: split every node holding more than one point (:616-683)
             for (int i = tid; i < 4 * size; i += QT_THREADS) childCnt[i] = 0;
             __syncthreads();
-            for (int c = warp; c < nCells; c += nWarps) {
-                const long long s0 = cells[c].slot;
-                const int n = cellCnt[c];
-                for (int k = lane; k < n; k += 32) {
-                    const uint32_t nd = ptNode[s0 + k];
-                    if (nd == ORBX_NODE_ERASED || cnC[nd] <= 1) continue;
-                    const float2 xy = ptXY[s0 + k];
-                    const int q = qt_quadrant(bxC[nd], xy.x, xy.y);
-                    atomicAdd(&childCnt[4 * nd + q], 1);
-                    ptNode[s0 + k] = nd | ((uint32_t)q << 30);
-                }
+            for (int i = tid; i < nPts; i += QT_THREADS) {
+                const uint32_t v = ptNode[i];
+                if (v == ORBX_NODE_ERASED) continue;
+                const uint32_t nd = v & 0xffffu;
+                if (cnC[nd] <= 1) continue;
+                const float2 xy = ptXY[i];
+                const int q = qt_quadrant(bxC[nd], xy.x, xy.y);
+                atomicAdd(&childCnt[4 * nd + q], 1);
+                ptNode[i] = (v & 0x00ffffffu) | ((uint32_t)q << 30);
             }
             __syncthreads();
             // creation order = list order × child order; children go to the list front (reversed)
-            for (int i = tid; i < 4 * size; i += QT_THREADS) childPos[i] = childCnt[i] > 0 ? 1 : 0;
+            for (int i = tid; i < 4 * size; i += QT_THREADS) {
+                childPos[i] = childCnt[i] > 0 ? 1 : 0;
+            }
             for (int i = tid; i < size; i += QT_THREADS) keptPos[i] = cnC[i] <= 1 ? 1 : 0;
             __syncthreads();
             const int C = block_exclusive_scan(childPos, 4 * size, scratch);
             const int nKept = block_exclusive_scan(keptPos, size, scratch);
-            // write nodes
             for (int i = tid; i < 4 * size; i += QT_THREADS) {
                 const int n = childCnt[i];
                 if (n > 0) {
@@ -572,26 +574,19 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCap
                 }
             }
             __syncthreads();
-            // remap points
-            for (int c = warp; c < nCells; c += nWarps) {
-                const long long s0 = cells[c].slot;
-                const int n = cellCnt[c];
-                for (int k = lane; k < n; k += 32) {
-                    const uint32_t v = ptNode[s0 + k];
-                    if (v == ORBX_NODE_ERASED) continue;
-                    const uint32_t nd = v & 0x3fffffffu, q = v >> 30;
-                    ptNode[s0 + k] = (uint32_t)(cnC[nd] <= 1 ? keptPos[nd] : childPos[4 * nd + q]);
-                }
+            for (int i = tid; i < nPts; i += QT_THREADS) {
+                const uint32_t v = ptNode[i];
+                if (v == ORBX_NODE_ERASED) continue;
+                const uint32_t nd = v & 0xffffu, q = v >> 30;
+                ptNode[i] = (v & 0x00ff0000u) | (uint32_t)(cnC[nd] <= 1 ? keptPos[nd] : childPos[4 * nd + q]);
             }
-            // expandable children in creation order (serial: ≤ 4·size entries, cheap next to the rest)
-            if (tid == 0) {
-                int np = 0;
-                for (int i = 0; i < 4 * size; ++i)
-                    if (childCnt[i] > 1) pend[np++] = childPos[i];
-                sh_nPend = np;
-            }
+            // expandable children (more than one point) in creation order: scan over (list position, child)
+            for (int i = tid; i < 4 * prevSize; i += QT_THREADS) tmp4[i] = childCnt[i] > 1 ? 1 : 0;
             __syncthreads();
-            nPend = sh_nPend;
+            nPend = block_exclusive_scan(tmp4, 4 * prevSize, scratch);
+            for (int i = tid; i < 4 * prevSize; i += QT_THREADS)
+                if (childCnt[i] > 1) pend[tmp4[i]] = childPos[i];
+            __syncthreads();
             size = C + nKept;
             cur = nxt;
             if (size >= N || size == prevSize) done = true;
@@ -608,20 +603,17 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCap
                 sortbuf[i] = (key << orbx_sort::kPayloadBits) | (unsigned long long)i;
             }
             __syncthreads();
-            if (tid == 0) orbx_sort::sort(sortbuf, nPend);
-            for (int c = warp; c < nCells; c += nWarps) {
-                const long long s0 = cells[c].slot;
-                const int n = cellCnt[c];
-                for (int k = lane; k < n; k += 32) {
-                    const uint32_t nd = ptNode[s0 + k];
-                    if (nd == ORBX_NODE_ERASED) continue;
-                    const int pi = pendIdx[nd];
-                    if (pi < 0) continue;
-                    const float2 xy = ptXY[s0 + k];
-                    const int q = qt_quadrant(bxC[nd], xy.x, xy.y);
-                    atomicAdd(&childCnt[4 * pi + q], 1);
-                    ptNode[s0 + k] = nd | ((uint32_t)q << 30);
-                }
+            if (tid == 0) orbx_sort::sort(sortbuf, nPend);   // overlaps with the classification below
+            for (int i = tid; i < nPts; i += QT_THREADS) {
+                const uint32_t v = ptNode[i];
+                if (v == ORBX_NODE_ERASED) continue;
+                const uint32_t nd = v & 0xffffu;
+                const int pi = pendIdx[nd];
+                if (pi < 0) continue;
+                const float2 xy = ptXY[i];
+                const int q = qt_quadrant(bxC[nd], xy.x, xy.y);
+                atomicAdd(&childCnt[4 * pi + q], 1);
+                ptNode[i] = (v & 0x00ffffffu) | ((uint32_t)q << 30);
             }
             __syncthreads();
             // walk the sorted array from the back until the list reaches N nodes (:701-747)
@@ -675,35 +667,28 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCap
                 }
             }
             __syncthreads();
-            for (int c = warp; c < nCells; c += nWarps) {
-                const long long s0 = cells[c].slot;
-                const int n = cellCnt[c];
-                for (int k = lane; k < n; k += 32) {
-                    const uint32_t v = ptNode[s0 + k];
-                    if (v == ORBX_NODE_ERASED) continue;
-                    const uint32_t nd = v & 0x3fffffffu, q = v >> 30;
-                    const int pi = pendIdx[nd];
-                    ptNode[s0 + k] = (uint32_t)((pi >= 0 && best[pi] == 1) ? childPos[4 * pi + q] : keptPos[nd]);
-                }
+            for (int i = tid; i < nPts; i += QT_THREADS) {
+                const uint32_t v = ptNode[i];
+                if (v == ORBX_NODE_ERASED) continue;
+                const uint32_t nd = v & 0xffffu, q = v >> 30;
+                const int pi = pendIdx[nd];
+                ptNode[i] = (v & 0x00ff0000u) | (uint32_t)((pi >= 0 && best[pi] == 1) ? childPos[4 * pi + q] : keptPos[nd]);
             }
             __syncthreads();
             // next pending list: expandable children in creation order = processing order × child order
             if (tid == 0) {
                 int np = 0;
-                // processing order is the sorted array from the back; rebuild into scratch-free storage
-                // (pend is overwritten only after all reads of the old list above are complete)
-                int tmpCount = 0;
                 for (int j = nPend - 1; j >= 0; --j) {
                     const int pi = (int)(sortbuf[j] & ((1ull << orbx_sort::kPayloadBits) - 1));
                     if (best[pi] != 1) break;
                     for (int q = 0; q < 4; ++q)
-                        if (childCnt[4 * pi + q] > 1) pendIdx[tmpCount++] = childPos[4 * pi + q];
+                        if (childCnt[4 * pi + q] > 1) pendIdx[np++] = childPos[4 * pi + q];
                 }
-                for (int i = 0; i < tmpCount; ++i) pend[np++] = pendIdx[i];
-                sh_nPend = np;
+                for (int i = 0; i < np; ++i) pend[i] = pendIdx[i];
+                sh_C = np;
             }
             __syncthreads();
-            nPend = sh_nPend;
+            nPend = sh_C;
             size = sh_size;
             cur = nxt;
             if (size >= N || size == prevSize) done = true;
@@ -714,30 +699,17 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCap
     // ---- best response per node, first maximum in insertion order wins (:757-776)
     for (int i = tid; i < size; i += QT_THREADS) best[i] = 0;
     __syncthreads();
-    for (int c = warp; c < nCells; c += nWarps) {
-        const long long s0 = cells[c].slot;
-        const int n = cellCnt[c];
-        const int o0 = prefix[c];
-        for (int k = lane; k < n; k += 32) {
-            const uint32_t nd = ptNode[s0 + k];
-            if (nd == ORBX_NODE_ERASED) continue;
-            const unsigned key = ((slots[s0 + k] >> 16) << 24) | (0xffffffu - (unsigned)(o0 + k));
-            atomicMax(&best[nd], key);
-        }
+    for (int i = tid; i < nPts; i += QT_THREADS) {
+        const uint32_t v = ptNode[i];
+        if (v == ORBX_NODE_ERASED) continue;
+        atomicMax(&best[v & 0xffffu], (((v >> 16) & 0xffu) << 24) | (0xffffffu - (unsigned)i));
     }
     __syncthreads();
     for (int i = tid; i < size; i += QT_THREADS) {
         const int order = (int)(0xffffffu - (best[i] & 0xffffffu));
-        int lo = 0, hi = nCells;  // last cell with prefix[c] <= order
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (prefix[mid] <= order) lo = mid; else hi = mid;
-        }
-        const long long slot = cells[lo].slot + (order - prefix[lo]);
-        const float2 xy = ptXY[slot];
+        const float2 xy = ptXY[order];
         // :919-923 — add the border back; response = FAST score
-        sel[i] = make_float4(__fadd_rn(xy.x, (float)ORBX_BORDER), __fadd_rn(xy.y, (float)ORBX_BORDER),
-                             (float)(slots[slot] >> 16), 0.f);
+        sel[i] = make_float4(__fadd_rn(xy.x, (float)ORBX_BORDER), __fadd_rn(xy.y, (float)ORBX_BORDER), (float)(best[i] >> 24), 0.f);
     }
     if (tid == 0) *selCntOut = size;
 }
@@ -820,10 +792,16 @@ __global__ void __launch_bounds__(256) k_assemble(ExParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K5: 7×7 Gaussian blur, σ=2, integer separable kernel, REFLECT_101 on the level
+// K5: 7×7 Gaussian blur, σ=2, integer separable kernel, REFLECT_101 on the level.
+// A thread owns 4 adjacent pixels (one 32-bit store) and marches down BLUR_RH rows: per input row it
+// reads three aligned words, forms the horizontal sums with two DP4A per pixel (taps 18,34,48,56 |
+// 48,34,18,0) and keeps the last 7 rows of sums in registers (fully unrolled ring), so the vertical
+// pass needs no shared memory and no barrier.
 // ------------------------------------------------------------------------------------------------
-#define BLUR_TW 64
-#define BLUR_TH 32
+#define BLUR_TW 256          // pixels per block row-strip (64 threads × 4 px)
+#define BLUR_RH 16           // output rows per thread
+#define BLUR_STRIPS 2        // row strips per block (blockDim.y)
+#define BLUR_TH (BLUR_RH * BLUR_STRIPS)
 struct BlurTile { short level, tx, ty, pad; };
 
 __device__ __forceinline__ int reflect101(int i, int n) {
@@ -832,44 +810,103 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i;
 }
 
-__global__ void __launch_bounds__(256) k_blur(ExParams p, const BlurTile *tiles) {
-    __shared__ uint8_t s_in[BLUR_TH + 6][BLUR_TW + 8];
-    __shared__ uint16_t s_h[BLUR_TH + 6][BLUR_TW];
+__global__ void __launch_bounds__(64 * BLUR_STRIPS) k_blur(ExParams p, const BlurTile *tiles) {
     const OrbxGeom &g = *p.g;
     const BlurTile T = tiles[blockIdx.x];
-    const int b = blockIdx.y, tid = threadIdx.x;
+    const int b = blockIdx.y;
     const int l = T.level;
     const OrbxLevel &LV = g.lv[l];
     int pitch;
     const uint8_t *src = level_ptr(p, g, l, b, pitch);
-    const int x0 = T.tx * BLUR_TW, y0 = T.ty * BLUR_TH;
     const int w = LV.w, h = LV.h;
-    for (int i = tid; i < (BLUR_TH + 6) * (BLUR_TW + 6); i += 256) {
-        const int yy = i / (BLUR_TW + 6), xx = i - yy * (BLUR_TW + 6);
-        const int sy = reflect101(min(y0 + yy - 3, h + 2), h), sx = reflect101(min(x0 + xx - 3, w + 2), w);
-        s_in[yy][xx] = src[(long long)sy * pitch + sx];
-    }
-    __syncthreads();
-    for (int i = tid; i < (BLUR_TH + 6) * BLUR_TW; i += 256) {
-        const int yy = i / BLUR_TW, xx = i - yy * BLUR_TW;
-        const uint8_t *r = &s_in[yy][xx];
-        s_h[yy][xx] = (uint16_t)(18 * (r[0] + r[6]) + 34 * (r[1] + r[5]) + 48 * (r[2] + r[4]) + 56 * r[3]);
-    }
-    __syncthreads();
-    uint8_t *dst = p.blur + (long long)b * g.frameBytes + LV.off;
-    for (int i = tid; i < BLUR_TH * (BLUR_TW / 4); i += 256) {
-        const int yy = i / (BLUR_TW / 4), x4 = (i - yy * (BLUR_TW / 4)) * 4;
-        const int gy = y0 + yy, gx = x0 + x4;
-        if (gy >= h || gx >= w) continue;
-        uint32_t out = 0;
+    const int x = T.tx * BLUR_TW + threadIdx.x * 4;
+    const int y0 = T.ty * BLUR_TH + threadIdx.y * BLUR_RH;
+    if (x >= w || y0 >= h) return;
+    const bool aligned = ((((unsigned long long)src | (unsigned)pitch) & 3ull) == 0);
+    // Three aligned words cover the 12-byte window x-4..x+7.  At the image edges the words are clamped into
+    // the row and the REFLECT_101 bytes are produced by per-thread PRMT selectors computed once (every
+    // reflected source byte lies inside the two neighbouring words), so edge lanes cost 3 extra PRMT per row.
+    const int lastWord = (w - 1) >> 2;
+    const int ib = x >> 2, ia = max(ib - 1, 0), ic = min(ib + 1, lastWord);
+    const bool edge = (x < 4) || (x + 7 >= w);
+    uint32_t selw[3] = {0x3210u, 0x3210u, 0x3210u};
+    bool hiPair[3] = {false, false, true};   // word k comes from PRMT(lo, hi): lo/hi = (A,B) or (B,C)
+    bool generic = !aligned;
+    if (edge && aligned) {
+        const int needMaxJ = min(x + 3, w - 1) + 3 - (x - 4);   // last window byte any valid output pixel taps
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int xx = x4 + k;
-            const uint32_t v = 18u * (s_h[yy][xx] + s_h[yy + 6][xx]) + 34u * (s_h[yy + 1][xx] + s_h[yy + 5][xx]) +
-                               48u * (s_h[yy + 2][xx] + s_h[yy + 4][xx]) + 56u * s_h[yy + 3][xx];
-            out |= ((v + 32768u) >> 16) << (8 * k);
+        for (int k = 0; k < 3; ++k) {
+            bool found = false;
+#pragma unroll
+            for (int pr = 0; pr < 2; ++pr) {
+                const int wa = pr == 0 ? ia : ib, wb = pr == 0 ? ib : ic;
+                bool ok = true;
+                uint32_t sel = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int j = 4 * k + i;
+                    uint32_t nib = 0;
+                    if (j >= 1 && j <= needMaxJ) {
+                        const int sidx = reflect101(x - 4 + j, w);
+                        if ((sidx >> 2) == wa) nib = (uint32_t)(sidx & 3);
+                        else if ((sidx >> 2) == wb) nib = 4u + (uint32_t)(sidx & 3);
+                        else ok = false;
+                    }
+                    sel |= nib << (4 * i);
+                }
+                if (ok && !found) { found = true; selw[k] = sel; hiPair[k] = pr == 1; }
+            }
+            if (!found) generic = true;
         }
-        *reinterpret_cast<uint32_t *>(dst + (long long)gy * LV.pitch + gx) = out;
+    }
+    const uint32_t KLO = 18u | (34u << 8) | (48u << 16) | (56u << 24), KHI = 48u | (34u << 8) | (18u << 16);
+    uint8_t *dst = p.blur + (long long)b * g.frameBytes + LV.off + x;
+    uint32_t ring[7][4];
+#pragma unroll
+    for (int r = 0; r < BLUR_RH + 6; ++r) {
+        const int sy = reflect101(min(y0 + r - 3, h + 2), h);
+        const uint8_t *row = src + (long long)sy * pitch;
+        uint32_t w0, w1, w2;
+        if (!generic) {
+            const uint32_t *q = reinterpret_cast<const uint32_t *>(row);
+            const uint32_t A = q[ia], Bw = q[ib], Cw = q[ic];
+            if (edge) {
+                w0 = __byte_perm(hiPair[0] ? Bw : A, hiPair[0] ? Cw : Bw, selw[0]);
+                w1 = __byte_perm(hiPair[1] ? Bw : A, hiPair[1] ? Cw : Bw, selw[1]);
+                w2 = __byte_perm(hiPair[2] ? Bw : A, hiPair[2] ? Cw : Bw, selw[2]);
+            } else {
+                w0 = A; w1 = Bw; w2 = Cw;
+            }
+        } else {  // unaligned caller buffer: gather the 12 bytes x-4..x+7 with reflection
+            uint32_t ww[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                uint32_t v = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v |= (uint32_t)row[reflect101(min(x - 4 + 4 * k + j, w + 6), w)] << (8 * j);
+                ww[k] = v;
+            }
+            w0 = ww[0]; w1 = ww[1]; w2 = ww[2];
+        }
+        // pixel i sits at byte 4+i of {w0,w1,w2}; taps are bytes 1+i .. 7+i
+        uint32_t *hr = ring[r % 7];
+        hr[0] = __dp4a(__byte_perm(w0, w1, 0x4321u), KLO, __dp4a(__byte_perm(w1, w2, 0x4321u), KHI, 0u));
+        hr[1] = __dp4a(__byte_perm(w0, w1, 0x5432u), KLO, __dp4a(__byte_perm(w1, w2, 0x5432u), KHI, 0u));
+        hr[2] = __dp4a(__byte_perm(w0, w1, 0x6543u), KLO, __dp4a(__byte_perm(w1, w2, 0x6543u), KHI, 0u));
+        hr[3] = __dp4a(w1, KLO, __dp4a(w2, KHI, 0u));
+        if (r >= 6) {
+            const int gy = y0 + r - 6;
+            if (gy < h) {
+                uint32_t out = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t v = 18u * (ring[(r - 6) % 7][i] + ring[r % 7][i]) + 34u * (ring[(r - 5) % 7][i] + ring[(r - 1) % 7][i]) +
+                                       48u * (ring[(r - 4) % 7][i] + ring[(r - 2) % 7][i]) + 56u * ring[(r - 3) % 7][i];
+                    out |= ((v + 32768u) >> 16) << (8 * i);
+                }
+                *reinterpret_cast<uint32_t *>(dst + (long long)gy * LV.pitch) = out;
+            }
+        }
     }
 }
 
@@ -1124,6 +1161,7 @@ int build_geometry(orbx_extractor *ex, int rows, int cols) {
         if (V.nIni < 1) { ex->err = "image too tall: quadtree would have no root node (reference faults)"; return ORBX_ERR_GEOMETRY; }
         V.hX = (float)rw / (float)V.nIni;
         V.nodeCap = std::max(4 * V.nIni, V.quota + 4) + 4;
+        if (V.nodeCap > 60000) { ex->err = "nfeatures too large (quadtree node index is 16-bit)"; return ORBX_ERR_ARG; }
         ex->nodeCapMax = std::max(ex->nodeCapMax, V.nodeCap);
         V.selBase = selBase;
         V.selCap = V.nodeCap;
@@ -1330,7 +1368,7 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
     // K5
     {
         dim3 grd((unsigned)ex->h_tiles.size(), batch);
-        k_blur<<<grd, 256, 0, s>>>(P, ex->d_tiles);
+        k_blur<<<grd, dim3(64, BLUR_STRIPS), 0, s>>>(P, ex->d_tiles);
         ++ex->launches;
     }
     if (prof) CUDA_TRY(ex, cudaEventRecord(ex->ev[5], s));
@@ -1640,28 +1678,26 @@ int orbx_get_candidates(orbx_extractor *ex, int frame, int level, orbx_keypoint 
     CUDA_TRY(ex, cudaStreamSynchronize(ex->stream));
     std::vector<int> cnt(std::max(V.nCells, 1));
     if (V.nCells) CUDA_TRY(ex, cudaMemcpy(cnt.data(), ex->d_cellCnt + (size_t)frame * G.nCellsTotal + V.cellBase, V.nCells * sizeof(int), cudaMemcpyDeviceToHost));
-    const size_t nslots = (size_t)V.nCells * V.slotCap;
-    std::vector<uint32_t> slots(std::max<size_t>(nslots, 1)), node(std::max<size_t>(nslots, 1));
-    std::vector<float2> xy(std::max<size_t>(nslots, 1));
-    if (nslots) {
+    size_t total = 0;
+    for (int c = 0; c < V.nCells; ++c) total += cnt[c];
+    std::vector<uint32_t> node(std::max<size_t>(total, 1));
+    std::vector<float2> xy(std::max<size_t>(total, 1));
+    if (total) {  // dense per-level arrays, indexed by candidate order (see k_quadtree)
         const size_t o = (size_t)frame * G.slotsTotal + V.slotBase;
-        CUDA_TRY(ex, cudaMemcpy(slots.data(), ex->d_slots + o, nslots * 4, cudaMemcpyDeviceToHost));
-        CUDA_TRY(ex, cudaMemcpy(node.data(), ex->d_ptNode + o, nslots * 4, cudaMemcpyDeviceToHost));
-        CUDA_TRY(ex, cudaMemcpy(xy.data(), ex->d_ptXY + o, nslots * 8, cudaMemcpyDeviceToHost));
+        CUDA_TRY(ex, cudaMemcpy(node.data(), ex->d_ptNode + o, total * 4, cudaMemcpyDeviceToHost));
+        CUDA_TRY(ex, cudaMemcpy(xy.data(), ex->d_ptXY + o, total * 8, cudaMemcpyDeviceToHost));
     }
     int n = 0;
-    for (int c = 0; c < V.nCells; ++c)
-        for (int k = 0; k < cnt[c]; ++k) {
-            const size_t s = (size_t)c * V.slotCap + k;
-            if (node[s] == ORBX_NODE_ERASED) continue;
-            if (out && n < cap) {
-                orbx_keypoint kp;
-                kp.x = xy[s].x; kp.y = xy[s].y; kp.size = 7.f; kp.angle = -1.f;
-                kp.response = (float)(slots[s] >> 16); kp.octave = 0; kp.class_id = -1;
-                out[n] = kp;
-            }
-            ++n;
+    for (size_t s = 0; s < total; ++s) {
+        if (node[s] == ORBX_NODE_ERASED) continue;
+        if (out && n < cap) {
+            orbx_keypoint kp;
+            kp.x = xy[s].x; kp.y = xy[s].y; kp.size = 7.f; kp.angle = -1.f;
+            kp.response = (float)((node[s] >> 16) & 0xff); kp.octave = 0; kp.class_id = -1;
+            out[n] = kp;
         }
+        ++n;
+    }
     return n;
 }
 
