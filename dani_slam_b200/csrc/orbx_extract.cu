@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(WPB * 32) k_fast_cells(ExParams p, int maxSlot
 // ------------------------------------------------------------------------------------------------
 // K3: DANI filter + quadtree (DistributeOctTree), one block per (frame, level)
 // ------------------------------------------------------------------------------------------------
-#define QT_THREADS 256
+#define QT_THREADS 128
 
 // block-wide exclusive scan of a[0..n) in place; returns the total.  All threads must call.
 __device__ int block_exclusive_scan(int *a, int n, int *scratch /* >= QT_THREADS+1 ints */) {
@@ -395,6 +395,31 @@ __device__ __forceinline__ short4 qt_child_box(short4 bx, int q) {  // box = {x0
     c.z = (q & 2) ? ym : bx.z;
     c.w = (q & 2) ? bx.w : ym;
     return c;
+}
+
+// Visit every live candidate of the level with 4 loads in flight per thread (the passes are bound by
+// L2 latency, not bandwidth): f(index, nodeWord, xy).
+template <bool NEED_XY, class F>
+__device__ __forceinline__ void qt_for_points(const uint32_t *ptNode, const float2 *ptXY, int nPts, F f) {
+    for (int i0 = threadIdx.x; i0 < nPts; i0 += 4 * QT_THREADS) {
+        uint32_t v[4];
+        float2 xy[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * QT_THREADS;
+            v[u] = i < nPts ? ptNode[i] : ORBX_NODE_ERASED;
+        }
+        if (NEED_XY) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * QT_THREADS;
+                xy[u] = i < nPts ? ptXY[i] : make_float2(0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (v[u] != ORBX_NODE_ERASED) f(i0 + u * QT_THREADS, v[u], xy[u]);
+    }
 }
 
 // Per-point state lives in two DENSE per-(frame, level) arrays indexed by the candidate's order index
@@ -513,10 +538,9 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCap
     __syncthreads();
     int size = sh_size;
     if (size != nIni) {  // some root was empty: renumber
-        for (int i = tid; i < nPts; i += QT_THREADS) {
-            const uint32_t v = ptNode[i];
-            if (v != ORBX_NODE_ERASED) ptNode[i] = (v & 0x00ff0000u) | (uint32_t)keptPos[v & 0xffffu];
-        }
+        qt_for_points<false>(ptNode, ptXY, nPts, [&](int i, uint32_t v, float2) {
+            ptNode[i] = (v & 0x00ff0000u) | (uint32_t)keptPos[v & 0xffffu];
+        });
         __syncthreads();
     }
 
@@ -533,16 +557,13 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCap
             // ---- full pass: split every node holding more than one point (:616-683)
             for (int i = tid; i < 4 * size; i += QT_THREADS) childCnt[i] = 0;
             __syncthreads();
-            for (int i = tid; i < nPts; i += QT_THREADS) {
-                const uint32_t v = ptNode[i];
-                if (v == ORBX_NODE_ERASED) continue;
+            qt_for_points<true>(ptNode, ptXY, nPts, [&](int i, uint32_t v, float2 xy) {
                 const uint32_t nd = v & 0xffffu;
-                if (cnC[nd] <= 1) continue;
-                const float2 xy = ptXY[i];
+                if (cnC[nd] <= 1) return;
                 const int q = qt_quadrant(bxC[nd], xy.x, xy.y);
                 atomicAdd(&childCnt[4 * nd + q], 1);
                 ptNode[i] = (v & 0x00ffffffu) | ((uint32_t)q << 30);
-            }
+            });
             __syncthreads();
             // creation order = list order × child order; children go to the list front (reversed)
             for (int i = tid; i < 4 * size; i += QT_THREADS) {
@@ -574,12 +595,10 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCap
                 }
             }
             __syncthreads();
-            for (int i = tid; i < nPts; i += QT_THREADS) {
-                const uint32_t v = ptNode[i];
-                if (v == ORBX_NODE_ERASED) continue;
+            qt_for_points<false>(ptNode, ptXY, nPts, [&](int i, uint32_t v, float2) {
                 const uint32_t nd = v & 0xffffu, q = v >> 30;
                 ptNode[i] = (v & 0x00ff0000u) | (uint32_t)(cnC[nd] <= 1 ? keptPos[nd] : childPos[4 * nd + q]);
-            }
+            });
             // expandable children (more than one point) in creation order: scan over (list position, child)
             for (int i = tid; i < 4 * prevSize; i += QT_THREADS) tmp4[i] = childCnt[i] > 1 ? 1 : 0;
             __syncthreads();
@@ -604,17 +623,14 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCap
             }
             __syncthreads();
             if (tid == 0) orbx_sort::sort(sortbuf, nPend);   // overlaps with the classification below
-            for (int i = tid; i < nPts; i += QT_THREADS) {
-                const uint32_t v = ptNode[i];
-                if (v == ORBX_NODE_ERASED) continue;
+            qt_for_points<true>(ptNode, ptXY, nPts, [&](int i, uint32_t v, float2 xy) {
                 const uint32_t nd = v & 0xffffu;
                 const int pi = pendIdx[nd];
-                if (pi < 0) continue;
-                const float2 xy = ptXY[i];
+                if (pi < 0) return;
                 const int q = qt_quadrant(bxC[nd], xy.x, xy.y);
                 atomicAdd(&childCnt[4 * pi + q], 1);
                 ptNode[i] = (v & 0x00ffffffu) | ((uint32_t)q << 30);
-            }
+            });
             __syncthreads();
             // walk the sorted array from the back until the list reaches N nodes (:701-747)
             if (tid == 0) {
@@ -667,13 +683,11 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCap
                 }
             }
             __syncthreads();
-            for (int i = tid; i < nPts; i += QT_THREADS) {
-                const uint32_t v = ptNode[i];
-                if (v == ORBX_NODE_ERASED) continue;
+            qt_for_points<false>(ptNode, ptXY, nPts, [&](int i, uint32_t v, float2) {
                 const uint32_t nd = v & 0xffffu, q = v >> 30;
                 const int pi = pendIdx[nd];
                 ptNode[i] = (v & 0x00ff0000u) | (uint32_t)((pi >= 0 && best[pi] == 1) ? childPos[4 * pi + q] : keptPos[nd]);
-            }
+            });
             __syncthreads();
             // next pending list: expandable children in creation order = processing order × child order
             if (tid == 0) {
@@ -699,11 +713,9 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCap
     // ---- best response per node, first maximum in insertion order wins (:757-776)
     for (int i = tid; i < size; i += QT_THREADS) best[i] = 0;
     __syncthreads();
-    for (int i = tid; i < nPts; i += QT_THREADS) {
-        const uint32_t v = ptNode[i];
-        if (v == ORBX_NODE_ERASED) continue;
+    qt_for_points<false>(ptNode, ptXY, nPts, [&](int i, uint32_t v, float2) {
         atomicMax(&best[v & 0xffffu], (((v >> 16) & 0xffu) << 24) | (0xffffffu - (unsigned)i));
-    }
+    });
     __syncthreads();
     for (int i = tid; i < size; i += QT_THREADS) {
         const int order = (int)(0xffffffu - (best[i] & 0xffffffu));
@@ -950,7 +962,7 @@ __global__ void __launch_bounds__(WPB * 32) k_orient_desc(ExParams p) {
     if (lane < 31) {
         const uint8_t *c0 = img + (long long)wk.cy * pitch + wk.cx + u;
         const int au = u < 0 ? -u : u;
-#pragma unroll 1
+#pragma unroll
         for (int v = -ORBX_HALF_PATCH; v <= ORBX_HALF_PATCH; ++v) {
             const int av = v < 0 ? -v : v;
             if (au <= g.umax[av]) {

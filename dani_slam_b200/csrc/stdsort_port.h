@@ -118,12 +118,16 @@ ORBX_SORT_HD void move_median_to_first(elem_t *a, int result, int x, int y, int 
 }
 
 ORBX_SORT_HD int unguarded_partition(elem_t *a, int first, int last, int pivot) {
+    const elem_t pv = a[pivot];  // the pivot slot lies outside [first, last) and is never written here
     while (true) {
-        while (less(a[first], a[pivot])) ++first;
+        elem_t x = a[first];
+        while (less(x, pv)) x = a[++first];
         --last;
-        while (less(a[pivot], a[last])) --last;
+        elem_t y = a[last];
+        while (less(pv, y)) y = a[--last];
         if (!(first < last)) return first;
-        swp(a, first, last);
+        a[first] = y;
+        a[last] = x;
         ++first;
     }
 }
