@@ -1039,7 +1039,8 @@ struct orbx_extractor {
     float sf[ORBX_MAX_LEVELS], inv[ORBX_MAX_LEVELS], sig2[ORBX_MAX_LEVELS], invsig2[ORBX_MAX_LEVELS];
     int quota[ORBX_MAX_LEVELS];
     int umax[ORBX_HALF_PATCH + 1];
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, sH2D = nullptr, sD2H = nullptr;
+    cudaEvent_t evIn[4] = {nullptr, nullptr, nullptr, nullptr}, evOut[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;
     long long launches = 0;
 
@@ -1320,17 +1321,21 @@ int harvest_stage_times(orbx_extractor *ex) {
 }
 
 // enqueue the whole pipeline for `batch` frames whose level 0 lives at (in0, stride, pitch)
+// (in0 and the four output pointers already point at frame `first`; internal per-frame buffers are offset here)
 int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, int in0Pitch, int batch,
-                 orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int *d_nOut, int *d_mono) {
+                 orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int *d_nOut, int *d_mono, int first = 0) {
     const OrbxGeom &G = ex->geom;
     ExParams P;
+    const size_t f = (size_t)first;
     P.g = ex->d_geom;
     P.in0 = in0; P.in0Stride = in0Stride; P.in0Pitch = in0Pitch;
-    P.pyr = ex->d_pyr; P.blur = ex->d_blur;
+    P.pyr = ex->d_pyr + f * G.frameBytes; P.blur = ex->d_blur + f * G.frameBytes;
     P.cells = ex->d_cells;
     P.tabX = ex->d_tabX; P.tabY = ex->d_tabY; P.tabXOff = ex->d_tabXOff; P.tabYOff = ex->d_tabYOff;
-    P.slots = ex->d_slots; P.cellCnt = ex->d_cellCnt; P.ptXY = ex->d_ptXY; P.ptNode = ex->d_ptNode;
-    P.sel = ex->d_sel; P.selCnt = ex->d_selCnt; P.work = ex->d_work; P.workCnt = ex->d_workCnt;
+    P.slots = ex->d_slots + f * G.slotsTotal; P.cellCnt = ex->d_cellCnt + f * G.nCellsTotal;
+    P.ptXY = ex->d_ptXY + f * G.slotsTotal; P.ptNode = ex->d_ptNode + f * G.slotsTotal;
+    P.sel = ex->d_sel + f * G.selTotal; P.selCnt = ex->d_selCnt + f * G.nlevels;
+    P.work = ex->d_work + f * G.selTotal; P.workCnt = ex->d_workCnt + f;
     P.kps = d_kps; P.desc = d_desc; P.cap = cap; P.nOut = d_nOut; P.monoIdx = d_mono;
     P.pattern = ex->d_pattern;
     cudaStream_t s = ex->stream;
@@ -1393,7 +1398,7 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
     }
     if (prof) { CUDA_TRY(ex, cudaEventRecord(ex->ev[6], s)); ex->evPending = true; }
     CUDA_TRY(ex, cudaGetLastError());
-    ex->lastBatch = batch;
+    ex->lastBatch = first + batch;
     return ORBX_OK;
 }
 
@@ -1458,6 +1463,12 @@ orbx_extractor *orbx_create(int nfeatures, float scale_factor, int nlevels, int 
 #define CREATE_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
     CREATE_TRY(cudaSetDevice(device));
     CREATE_TRY(cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaStreamCreateWithFlags(&ex->sH2D, cudaStreamNonBlocking));
+    CREATE_TRY(cudaStreamCreateWithFlags(&ex->sD2H, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) {
+        CREATE_TRY(cudaEventCreateWithFlags(&ex->evIn[i], cudaEventDisableTiming));
+        CREATE_TRY(cudaEventCreateWithFlags(&ex->evOut[i], cudaEventDisableTiming));
+    }
     CREATE_TRY(cudaMalloc((void **)&ex->d_geom, sizeof(OrbxGeom)));
     CREATE_TRY(cudaMalloc((void **)&ex->d_tabXOff, ORBX_MAX_LEVELS * sizeof(int)));
     CREATE_TRY(cudaMalloc((void **)&ex->d_tabYOff, ORBX_MAX_LEVELS * sizeof(int)));
@@ -1490,6 +1501,9 @@ void orbx_destroy(orbx_extractor *ex) {
     if (ex->h_nOut) cudaFreeHost(ex->h_nOut);
     if (ex->h_mono) cudaFreeHost(ex->h_mono);
     for (int i = 0; i < 7; ++i) if (ex->ev[i]) cudaEventDestroy(ex->ev[i]);
+    for (int i = 0; i < 4; ++i) { if (ex->evIn[i]) cudaEventDestroy(ex->evIn[i]); if (ex->evOut[i]) cudaEventDestroy(ex->evOut[i]); }
+    if (ex->sH2D) cudaStreamDestroy(ex->sH2D);
+    if (ex->sD2H) cudaStreamDestroy(ex->sD2H);
     if (ex->stream) cudaStreamDestroy(ex->stream);
     delete ex;
 }
@@ -1544,41 +1558,52 @@ int orbx_extract_batch(orbx_extractor *ex, const uint8_t *const *images, int bat
             CUDA_TRY(ex, cudaMalloc((void **)&ex->d_desc, need * 32));
             ex->outCap = need;
         }
-        cudaStream_t s = ex->stream;
-        // H2D straight into the level-0 planes of the internal pyramid
-        bool contiguous = true;
-        for (int b = 1; b < nb && contiguous; ++b)
-            contiguous = images[b0 + b] == images[b0] + (size_t)b * rows * step;
-        if (contiguous && step == (size_t)cols && G.lv[0].pitch == cols) {
-            // frames are back to back and rows are dense: one strided copy for the whole batch
-            CUDA_TRY(ex, cudaMemcpy2DAsync(ex->d_pyr + G.lv[0].off, (size_t)G.frameBytes, images[b0], (size_t)rows * cols,
-                                           (size_t)rows * cols, nb, cudaMemcpyHostToDevice, s));
-        } else {
-            for (int b = 0; b < nb; ++b)
-                CUDA_TRY(ex, cudaMemcpy2DAsync(ex->d_pyr + (size_t)b * G.frameBytes + G.lv[0].off, G.lv[0].pitch, images[b0 + b], step,
-                                               cols, rows, cudaMemcpyHostToDevice, s));
+        // Software pipeline over chunks of the batch: H2D of chunk k+1 and D2H of chunk k-1 overlap the kernels
+        // of chunk k (three streams, events between them).  PCIe moves 307 KB in and ~64 KB out per frame, about
+        // half of the kernel time at 640x480, so the copies hide completely behind the compute stream.
+        const int nChunks = nb >= 64 ? 4 : 1;
+        const int chunk = (nb + nChunks - 1) / nChunks;
+        cudaStream_t sC = ex->stream, sIn = ex->sH2D, sOut = ex->sD2H;
+        // earlier asynchronous work of this handle must be finished before its buffers are refilled
+        CUDA_TRY(ex, cudaEventRecord(ex->evOut[0], sC));
+        CUDA_TRY(ex, cudaStreamWaitEvent(sIn, ex->evOut[0], 0));
+        int k = 0;
+        for (int c0 = 0; c0 < nb; c0 += chunk, ++k) {
+            const int cn = std::min(chunk, nb - c0);
+            bool contiguous = true;
+            for (int b = 1; b < cn && contiguous; ++b)
+                contiguous = images[b0 + c0 + b] == images[b0 + c0] + (size_t)b * rows * step;
+            uint8_t *lvl0 = ex->d_pyr + (size_t)c0 * G.frameBytes + G.lv[0].off;
+            if (contiguous && step == (size_t)cols && G.lv[0].pitch == cols) {
+                // frames are back to back and rows are dense: one strided copy for the whole chunk
+                CUDA_TRY(ex, cudaMemcpy2DAsync(lvl0, (size_t)G.frameBytes, images[b0 + c0], (size_t)rows * cols, (size_t)rows * cols, cn,
+                                               cudaMemcpyHostToDevice, sIn));
+            } else {
+                for (int b = 0; b < cn; ++b)
+                    CUDA_TRY(ex, cudaMemcpy2DAsync(lvl0 + (size_t)b * G.frameBytes, G.lv[0].pitch, images[b0 + c0 + b], step, cols, rows,
+                                                   cudaMemcpyHostToDevice, sIn));
+            }
+            CUDA_TRY(ex, cudaEventRecord(ex->evIn[k], sIn));
+            CUDA_TRY(ex, cudaStreamWaitEvent(sC, ex->evIn[k], 0));
+            ex->lastIn0Internal = true;
+            rc = run_pipeline(ex, lvl0, G.frameBytes, G.lv[0].pitch, cn, ex->d_kps + (size_t)c0 * cap, ex->d_desc + (size_t)c0 * cap * 32, cap,
+                              ex->d_nOut + c0, ex->d_mono + c0, c0);
+            if (rc) return rc;
+            CUDA_TRY(ex, cudaEventRecord(ex->evOut[k], sC));
+            CUDA_TRY(ex, cudaStreamWaitEvent(sOut, ex->evOut[k], 0));
+            CUDA_TRY(ex, cudaMemcpyAsync(ex->h_nOut + c0, ex->d_nOut + c0, cn * sizeof(int), cudaMemcpyDeviceToHost, sOut));
+            CUDA_TRY(ex, cudaMemcpyAsync(ex->h_mono + c0, ex->d_mono + c0, cn * sizeof(int), cudaMemcpyDeviceToHost, sOut));
+            CUDA_TRY(ex, cudaMemcpyAsync(kps + ((size_t)b0 + c0) * cap, ex->d_kps + (size_t)c0 * cap, (size_t)cn * cap * sizeof(orbx_keypoint),
+                                         cudaMemcpyDeviceToHost, sOut));
+            CUDA_TRY(ex, cudaMemcpyAsync(desc + ((size_t)b0 + c0) * cap * 32, ex->d_desc + (size_t)c0 * cap * 32, (size_t)cn * cap * 32,
+                                         cudaMemcpyDeviceToHost, sOut));
         }
-        ex->lastIn0Internal = true;
-        rc = run_pipeline(ex, ex->d_pyr + G.lv[0].off, G.frameBytes, G.lv[0].pitch, nb, ex->d_kps, ex->d_desc, cap, ex->d_nOut, ex->d_mono);
-        if (rc) return rc;
-        CUDA_TRY(ex, cudaMemcpyAsync(ex->h_nOut, ex->d_nOut, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(ex, cudaMemcpyAsync(ex->h_mono, ex->d_mono, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(ex, cudaStreamSynchronize(s));
-        int maxN = 0;
+        CUDA_TRY(ex, cudaStreamSynchronize(sOut));
+        CUDA_TRY(ex, cudaStreamSynchronize(sC));
         for (int b = 0; b < nb; ++b) {
             n_out[b0 + b] = ex->h_nOut[b];
             mono_index[b0 + b] = ex->h_mono[b];
             if (ex->h_nOut[b] > cap) result = ORBX_ERR_CAPACITY;
-            maxN = std::max(maxN, std::min(ex->h_nOut[b], cap));
-        }
-        if (maxN > 0) {
-            // one strided copy per array: rows of maxN records out of the cap-strided device arrays
-            CUDA_TRY(ex, cudaMemcpy2DAsync(kps + (size_t)b0 * cap, (size_t)cap * sizeof(orbx_keypoint), ex->d_kps,
-                                           (size_t)cap * sizeof(orbx_keypoint), (size_t)maxN * sizeof(orbx_keypoint), nb,
-                                           cudaMemcpyDeviceToHost, s));
-            CUDA_TRY(ex, cudaMemcpy2DAsync(desc + (size_t)b0 * cap * 32, (size_t)cap * 32, ex->d_desc, (size_t)cap * 32,
-                                           (size_t)maxN * 32, nb, cudaMemcpyDeviceToHost, s));
-            CUDA_TRY(ex, cudaStreamSynchronize(s));
         }
     }
     if (result == ORBX_ERR_CAPACITY) ex->err = "keypoint capacity too small for at least one frame (see n_out)";
