@@ -229,24 +229,24 @@ __global__ void __launch_bounds__(WPB * 32) k_fast_cells(ExParams p, int maxSlot
     }
     __syncwarp();
 
-    const int G = (iw + 3) >> 2;             // groups per row (≤ 19 for cells ≤ 75 px wide)
-    const int RP = 32 / G;                   // interior rows handled per warp pass
-    const int lr = lane / G, lg = lane - lr * G;
-    const bool laneOn = lr < RP;
-    const int nValid = min(max(iw - 4 * lg, 0), 4);
-    const uint32_t colMask = nValid >= 4 ? 0xffffffffu : ((1u << (8 * nValid)) - 1u);
+    const int G = (iw + 3) >> 2;             // 4-pixel groups per interior row (≤ 19 for cells ≤ 75 px wide)
+    const int nGroups = G * ih;              // groups of the cell in row-major order: lane work items
+    const uint32_t rcpG = (65536u + G - 1) / G;   // (i*rcpG)>>16 == i/G for i < 3449 (cells are ≤ 19×69 groups)
     const int t = g.lowTh;
     const uint32_t negT2 = ((uint32_t)(-t) & 0xffffu) * 0x10001u;
 
     // pass 1: score map (value = M - lowTh clamped at 0; real score = value + lowTh - 1)
-    for (int y0 = 0; y0 < ih; y0 += RP) {
-        const int yi = y0 + lr;
-        if (laneOn && yi < ih) {
+    for (int i0 = 0; i0 < nGroups; i0 += 32) {
+        const int gi = i0 + lane;
+        if (gi < nGroups) {
+            const int yi = (int)(((uint32_t)gi * rcpG) >> 16), lg = gi - yi * G;
             const uint8_t *rowp = roi + yi * rp + 4 * lg;  // ROI row (yi+3)+dy = yi + i for i = 0..6
             Row3 R[7];
 #pragma unroll
             for (int i = 0; i < 7; ++i) R[i] = ld_row3(rowp + i * rp);
             const uint32_t s0 = fast_pair_score<0>(R, negT2), s1 = fast_pair_score<1>(R, negT2);
+            const int nValid = min(iw - 4 * lg, 4);
+            const uint32_t colMask = nValid >= 4 ? 0xffffffffu : ((1u << (8 * nValid)) - 1u);
             const uint32_t word = __byte_perm(s0, s1, 0x6420u) & colMask;
             *reinterpret_cast<uint32_t *>(score + (yi + 1) * sp + 4 * lg + 4) = word;
         }
@@ -256,10 +256,11 @@ __global__ void __launch_bounds__(WPB * 32) k_fast_cells(ExParams p, int maxSlot
     // pass 2: cell-local 3×3 strict NMS → row-major ordered list; count survivors above iniTh
     const int iniRel = g.iniTh - t + 1;      // value >= iniRel  ⇔  M > iniTh
     int n = 0, nIni = 0;
-    for (int y0 = 0; y0 < ih; y0 += RP) {
-        const int yi = y0 + lr;
+    for (int i0 = 0; i0 < nGroups; i0 += 32) {
+        const int gi = i0 + lane;
+        const int yi = (int)(((uint32_t)gi * rcpG) >> 16), lg = gi - yi * G;
         uint32_t flags = 0, vals = 0;        // flags: bit i = pixel i of the group survives
-        if (laneOn && yi < ih) {
+        if (gi < nGroups) {
             const uint8_t *rowp = score + yi * sp + 4 * lg;   // score rows yi, yi+1 (centre), yi+2
             const Row3 T = ld_row3(rowp), Cn = ld_row3(rowp + sp), Bt = ld_row3(rowp + 2 * sp);
             vals = Cn.w1;
@@ -283,7 +284,7 @@ __global__ void __launch_bounds__(WPB * 32) k_fast_cells(ExParams p, int maxSlot
         const int cntIni = __popc(iniFlags);
         const uint32_t lt = (1u << lane) - 1u;
         const uint32_t b0 = __ballot_sync(0xffffffffu, cntLane & 1), b1 = __ballot_sync(0xffffffffu, cntLane & 2);
-        const uint32_t i0 = __ballot_sync(0xffffffffu, cntIni & 1), i1 = __ballot_sync(0xffffffffu, cntIni & 2);
+        const uint32_t q0 = __ballot_sync(0xffffffffu, cntIni & 1), q1 = __ballot_sync(0xffffffffu, cntIni & 2);
         int at = n + __popc(b0 & lt) + 2 * __popc(b1 & lt);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(WPB * 32) k_fast_cells(ExParams p, int maxSlot
                 list[at++] = (uint32_t)(4 * lg + i + 3) | ((uint32_t)(yi + 3) << 8) | (s << 16);
             }
         n += __popc(b0) + 2 * __popc(b1);
-        nIni += __popc(i0) + 2 * __popc(i1);
+        nIni += __popc(q0) + 2 * __popc(q1);
     }
     __syncwarp();
     // retry rule (:843-846): if the iniTh pass is empty after NMS, the minTh pass is the result
