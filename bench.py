@@ -63,7 +63,7 @@ def make_frames(count: int, first_index: int) -> np.ndarray:
 class ClockSampler(threading.Thread):
     """Samples SM clocks and throttle reasons with NVML while the timed region runs."""
 
-    def __init__(self, index: int, period: float = 0.1):
+    def __init__(self, index: int, period: float = 0.01):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()
