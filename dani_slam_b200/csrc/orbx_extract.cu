@@ -78,38 +78,77 @@ __device__ __forceinline__ const uint8_t *level_ptr(const ExParams &p, const Orb
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1: bilinear resize (cv::resize INTER_LINEAR 8UC1).  One thread = 4 output pixels.
+// K1: bilinear resize (cv::resize INTER_LINEAR 8UC1), separable inside a block:
+// phase 1 forms the horizontal sums (S[sx]*a0 + S[sx+1]*a1) >> 4 (they fit 16 bits) once per needed source
+// row into shared memory — a destination column keeps its source offset and coefficients in registers;
+// phase 2 combines two of those rows per output row, 4 pixels per thread, one 32-bit store.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_pyr_level(ExParams p, int l) {
-    const OrbxGeom &g = *p.g;
-    const OrbxLevel &D = g.lv[l];
-    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int b = blockIdx.z;
-    if (x4 >= D.w || y >= D.h) return;
-    int sp;
-    const uint8_t *S = level_ptr(p, g, l - 1, b, sp);
-    const int sw = g.lv[l - 1].w, sh = g.lv[l - 1].h;
-    const int2 ty = p.tabY[p.tabYOff[l] + y];
-    const int sy0 = min(max(ty.x, 0), sh - 1), sy1 = min(max(ty.x + 1, 0), sh - 1);
-    const int b0 = (short)(ty.y & 0xffff), b1 = (short)(ty.y >> 16);
-    const uint8_t *R0 = S + (long long)sy0 * sp, *R1 = S + (long long)sy1 * sp;
-    const int2 *tx = p.tabX + p.tabXOff[l] + x4;
-    uint32_t out = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        if (x4 + i < D.w) {
-            const int2 t = tx[i];
+#define PYR_TW 128
+#define PYR_TH 16
+struct PyrArgs {             // everything by value: no dependent global loads before the pixel loads
+    const uint8_t *src; long long srcStride; int sp, sw, sh;
+    uint8_t *dst; long long dstStride; int dp, dw, dh;
+    const int2 *tabX, *tabY;
+    int tilesX;
+};
+__global__ void __launch_bounds__(256) k_pyr_level(PyrArgs a) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];   // uint16 H[rows][PYR_TW], rows = source rows one tile needs
+    uint16_t (*H)[PYR_TW] = reinterpret_cast<uint16_t (*)[PYR_TW]>(smem_raw);
+    const int b = blockIdx.y;
+    const int ty = blockIdx.x / a.tilesX, tx = blockIdx.x - ty * a.tilesX;
+    const int x0 = tx * PYR_TW, y0 = ty * PYR_TH;
+    const int tid = threadIdx.x;
+    const uint8_t *S = a.src + (long long)b * a.srcStride;
+    const int sp = a.sp, sw = a.sw, sh = a.sh;
+    const int yLast = min(y0 + PYR_TH, a.dh) - 1;
+    const int r0 = min(max(a.tabY[y0].x, 0), sh - 1);
+    const int r1 = min(max(a.tabY[yLast].x + 1, 0), sh - 1);
+    const int nR = r1 - r0 + 1;
+    // phase 1: thread owns destination column dx, walks the needed source rows
+    {
+        const int dx = tid & (PYR_TW - 1);
+        const int gx = x0 + dx;
+        if (gx < a.dw) {
+            const int2 t = a.tabX[gx];
             const int s0 = t.x, s1 = min(t.x + 1, sw - 1);
             const int a0 = (short)(t.y & 0xffff), a1 = (short)(t.y >> 16);
-            const int h0 = R0[s0] * a0 + R0[s1] * a1;
-            const int h1 = R1[s0] * a0 + R1[s1] * a1;
-            const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
-            out |= (uint32_t)(v & 0xff) << (8 * i);
+            const uint8_t *q = S + (long long)r0 * sp;
+#pragma unroll 4
+            for (int r = tid >> 7; r < nR; r += 256 / PYR_TW) {
+                const uint8_t *row = q + (long long)r * sp;
+                H[r][dx] = (uint16_t)((row[s0] * a0 + row[s1] * a1) >> 4);
+            }
         }
     }
-    uint8_t *Dp = p.pyr + (long long)b * g.frameBytes + D.off + (long long)y * D.pitch + x4;
-    *reinterpret_cast<uint32_t *>(Dp) = out;  // pitch is a multiple of 128: in-row padding is writable
+    __syncthreads();
+    // phase 2: thread owns 4 destination columns, two output rows
+    {
+        const int cx = (tid & 31) * 4;
+        const int gx = x0 + cx;
+        if (gx < a.dw) {
+            uint8_t *Dp = a.dst + (long long)b * a.dstStride + gx;
+#pragma unroll
+            for (int k = 0; k < PYR_TH / 8; ++k) {
+                const int yy = (tid >> 5) + 8 * k, gy = y0 + yy;
+                if (gy < a.dh) {
+                    const int2 ty2 = a.tabY[gy];
+                    const int i0 = min(max(ty2.x, 0), sh - 1) - r0, i1 = min(max(ty2.x + 1, 0), sh - 1) - r0;
+                    const int b0 = (short)(ty2.y & 0xffff), b1 = (short)(ty2.y >> 16);
+                    const uint2 u0 = *reinterpret_cast<const uint2 *>(&H[i0][cx]);
+                    const uint2 u1 = *reinterpret_cast<const uint2 *>(&H[i1][cx]);
+                    const int h0[4] = {(int)(u0.x & 0xffff), (int)(u0.x >> 16), (int)(u0.y & 0xffff), (int)(u0.y >> 16)};
+                    const int h1[4] = {(int)(u1.x & 0xffff), (int)(u1.x >> 16), (int)(u1.y & 0xffff), (int)(u1.y >> 16)};
+                    uint32_t out = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int v = (((b0 * h0[i]) >> 16) + ((b1 * h1[i]) >> 16) + 2) >> 2;
+                        out |= (uint32_t)(v & 0xff) << (8 * i);
+                    }
+                    *reinterpret_cast<uint32_t *>(Dp + (long long)gy * a.dp) = out;  // pitch multiple of 128: padding is writable
+                }
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -806,15 +845,16 @@ __global__ void __launch_bounds__(256) k_assemble(ExParams p) {
 
 // ------------------------------------------------------------------------------------------------
 // K5: 7×7 Gaussian blur, σ=2, integer separable kernel, REFLECT_101 on the level.
-// A thread owns 4 adjacent pixels (one 32-bit store) and marches down BLUR_RH rows: per input row it
-// reads three aligned words, forms the horizontal sums with two DP4A per pixel (taps 18,34,48,56 |
-// 48,34,18,0) and keeps the last 7 rows of sums in registers (fully unrolled ring), so the vertical
-// pass needs no shared memory and no barrier.
+// The block stages its input tile (+3-row / +16-byte halo) with 16-byte loads into shared memory; a thread
+// then owns 4 adjacent pixels (one 32-bit store) and marches down BLUR_RH rows: per input row it reads
+// three aligned shared-memory words, forms the horizontal sums with two DP4A per pixel (taps 18,34,48,56 |
+// 48,34,18,0) and keeps the last 7 rows of sums in registers (fully unrolled ring) for the vertical pass.
 // ------------------------------------------------------------------------------------------------
 #define BLUR_TW 256          // pixels per block row-strip (64 threads × 4 px)
 #define BLUR_RH 16           // output rows per thread
 #define BLUR_STRIPS 2        // row strips per block (blockDim.y)
 #define BLUR_TH (BLUR_RH * BLUR_STRIPS)
+#define BLUR_SP (BLUR_TW + 32)   // tile pitch: columns x0-16 .. x0+271
 struct BlurTile { short level, tx, ty, pad; };
 
 __device__ __forceinline__ int reflect101(int i, int n) {
@@ -824,6 +864,7 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 }
 
 __global__ void __launch_bounds__(64 * BLUR_STRIPS) k_blur(ExParams p, const BlurTile *tiles) {
+    __shared__ __align__(16) uint8_t tile[(BLUR_TH + 6) * BLUR_SP];
     const OrbxGeom &g = *p.g;
     const BlurTile T = tiles[blockIdx.x];
     const int b = blockIdx.y;
@@ -832,10 +873,36 @@ __global__ void __launch_bounds__(64 * BLUR_STRIPS) k_blur(ExParams p, const Blu
     int pitch;
     const uint8_t *src = level_ptr(p, g, l, b, pitch);
     const int w = LV.w, h = LV.h;
-    const int x = T.tx * BLUR_TW + threadIdx.x * 4;
-    const int y0 = T.ty * BLUR_TH + threadIdx.y * BLUR_RH;
+    const int tx0 = T.tx * BLUR_TW, ty0 = T.ty * BLUR_TH;
+    const int tid = threadIdx.y * 64 + threadIdx.x;
+    const bool aligned = ((((unsigned long long)src | (unsigned)pitch) & 15ull) == 0);
+    // stage rows ty0-3 .. ty0+BLUR_TH+2 (reflected), columns tx0-16 .. tx0+BLUR_TW+15 (clipped to the row)
+    {
+        const int nChunks = BLUR_SP / 16;
+        const int rowBytes = aligned ? min(pitch, (w + 15) & ~15) : w;   // bytes of a row that may be read
+        for (int i = tid; i < (BLUR_TH + 6) * nChunks; i += 64 * BLUR_STRIPS) {
+            const int r = i / nChunks, c = i - r * nChunks;
+            const int gx = tx0 - 16 + 16 * c;
+            const int sy = reflect101(min(ty0 + r - 3, h + 2), h);
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (gx >= 0 && gx < rowBytes) {
+                const uint8_t *q = src + (long long)sy * pitch + gx;
+                if (aligned) {
+                    v = *reinterpret_cast<const uint4 *>(q);
+                } else {
+                    uint32_t ww[4] = {0, 0, 0, 0};
+                    for (int j = 0; j < 16; ++j)
+                        if (gx + j < w) ww[j >> 2] |= (uint32_t)q[j] << (8 * (j & 3));
+                    v = make_uint4(ww[0], ww[1], ww[2], ww[3]);
+                }
+            }
+            *reinterpret_cast<uint4 *>(&tile[r * BLUR_SP + 16 * c]) = v;
+        }
+    }
+    __syncthreads();
+    const int x = tx0 + threadIdx.x * 4;
+    const int y0 = ty0 + threadIdx.y * BLUR_RH;
     if (x >= w || y0 >= h) return;
-    const bool aligned = ((((unsigned long long)src | (unsigned)pitch) & 3ull) == 0);
     // Three aligned words cover the 12-byte window x-4..x+7.  At the image edges the words are clamped into
     // the row and the REFLECT_101 bytes are produced by per-thread PRMT selectors computed once (every
     // reflected source byte lies inside the two neighbouring words), so edge lanes cost 3 extra PRMT per row.
@@ -844,8 +911,7 @@ __global__ void __launch_bounds__(64 * BLUR_STRIPS) k_blur(ExParams p, const Blu
     const bool edge = (x < 4) || (x + 7 >= w);
     uint32_t selw[3] = {0x3210u, 0x3210u, 0x3210u};
     bool hiPair[3] = {false, false, true};   // word k comes from PRMT(lo, hi): lo/hi = (A,B) or (B,C)
-    bool generic = !aligned;
-    if (edge && aligned) {
+    if (edge) {
         const int needMaxJ = min(x + 3, w - 1) + 3 - (x - 4);   // last window byte any valid output pixel taps
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -869,37 +935,25 @@ __global__ void __launch_bounds__(64 * BLUR_STRIPS) k_blur(ExParams p, const Blu
                 }
                 if (ok && !found) { found = true; selw[k] = sel; hiPair[k] = pr == 1; }
             }
-            if (!found) generic = true;
         }
     }
     const uint32_t KLO = 18u | (34u << 8) | (48u << 16) | (56u << 24), KHI = 48u | (34u << 8) | (18u << 16);
     uint8_t *dst = p.blur + (long long)b * g.frameBytes + LV.off + x;
+    // word offsets inside the tile (tile column 0 = image column tx0-16)
+    const int wbase = (16 - tx0) >> 2;
+    const uint32_t *trow = reinterpret_cast<const uint32_t *>(tile) + threadIdx.y * BLUR_RH * (BLUR_SP / 4);
+    const int oa = ia + wbase, ob = ib + wbase, oc = ic + wbase;
     uint32_t ring[7][4];
 #pragma unroll
     for (int r = 0; r < BLUR_RH + 6; ++r) {
-        const int sy = reflect101(min(y0 + r - 3, h + 2), h);
-        const uint8_t *row = src + (long long)sy * pitch;
+        const uint32_t A = trow[r * (BLUR_SP / 4) + oa], Bw = trow[r * (BLUR_SP / 4) + ob], Cw = trow[r * (BLUR_SP / 4) + oc];
         uint32_t w0, w1, w2;
-        if (!generic) {
-            const uint32_t *q = reinterpret_cast<const uint32_t *>(row);
-            const uint32_t A = q[ia], Bw = q[ib], Cw = q[ic];
-            if (edge) {
-                w0 = __byte_perm(hiPair[0] ? Bw : A, hiPair[0] ? Cw : Bw, selw[0]);
-                w1 = __byte_perm(hiPair[1] ? Bw : A, hiPair[1] ? Cw : Bw, selw[1]);
-                w2 = __byte_perm(hiPair[2] ? Bw : A, hiPair[2] ? Cw : Bw, selw[2]);
-            } else {
-                w0 = A; w1 = Bw; w2 = Cw;
-            }
-        } else {  // unaligned caller buffer: gather the 12 bytes x-4..x+7 with reflection
-            uint32_t ww[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                uint32_t v = 0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) v |= (uint32_t)row[reflect101(min(x - 4 + 4 * k + j, w + 6), w)] << (8 * j);
-                ww[k] = v;
-            }
-            w0 = ww[0]; w1 = ww[1]; w2 = ww[2];
+        if (edge) {
+            w0 = __byte_perm(hiPair[0] ? Bw : A, hiPair[0] ? Cw : Bw, selw[0]);
+            w1 = __byte_perm(hiPair[1] ? Bw : A, hiPair[1] ? Cw : Bw, selw[1]);
+            w2 = __byte_perm(hiPair[2] ? Bw : A, hiPair[2] ? Cw : Bw, selw[2]);
+        } else {
+            w0 = A; w1 = Bw; w2 = Cw;
         }
         // pixel i sits at byte 4+i of {w0,w1,w2}; taps are bytes 1+i .. 7+i
         uint32_t *hr = ring[r % 7];
@@ -1051,6 +1105,7 @@ struct orbx_extractor {
     int curLap0 = 0, curLap1 = 0;
     std::vector<int> curRects;
     bool geomDirty = true;
+    int h_tabXOff[ORBX_MAX_LEVELS] = {0}, h_tabYOff[ORBX_MAX_LEVELS] = {0};
     std::vector<OrbxCell> h_cells;
     std::vector<BlurTile> h_tiles;
     int maxSlotCap = 0, nodeCapMax = 0, maxCellsLevel = 0;
@@ -1221,6 +1276,7 @@ int upload_tables(orbx_extractor *ex) {
             ty.push_back(make_int2(s, (b0 & 0xffff) | (b1 << 16)));
         }
     }
+    for (int l = 0; l < ORBX_MAX_LEVELS; ++l) { ex->h_tabXOff[l] = txo[l]; ex->h_tabYOff[l] = tyo[l]; }
     int rc;
     if ((rc = ensure(ex, ex->d_tabX, ex->tabXCap, std::max<size_t>(tx.size(), 1)))) return rc;
     if ((rc = ensure(ex, ex->d_tabY, ex->tabYCap, std::max<size_t>(ty.size(), 1)))) return rc;
@@ -1348,8 +1404,18 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
     }
     // K1
     for (int l = 1; l < G.nlevels; ++l) {
-        dim3 blk(32, 8), grd((G.lv[l].w + 127) / 128, (G.lv[l].h + 7) / 8, batch);
-        k_pyr_level<<<grd, blk, 0, s>>>(P, l);
+        const int tilesX = (G.lv[l].w + PYR_TW - 1) / PYR_TW, tilesY = (G.lv[l].h + PYR_TH - 1) / PYR_TH;
+        const int srcRows = (int)ceil((PYR_TH - 1) * (double)G.lv[l - 1].h / G.lv[l].h) + 4;
+        const size_t smem = (size_t)srcRows * PYR_TW * sizeof(uint16_t);
+        if (smem > 48 * 1024) { ex->err = "scale factor too large for the pyramid kernel"; return ORBX_ERR_ARG; }
+        PyrArgs A;
+        if (l == 1) { A.src = P.in0; A.srcStride = P.in0Stride; A.sp = P.in0Pitch; }
+        else { A.src = P.pyr + G.lv[l - 1].off; A.srcStride = G.frameBytes; A.sp = G.lv[l - 1].pitch; }
+        A.sw = G.lv[l - 1].w; A.sh = G.lv[l - 1].h;
+        A.dst = P.pyr + G.lv[l].off; A.dstStride = G.frameBytes; A.dp = G.lv[l].pitch; A.dw = G.lv[l].w; A.dh = G.lv[l].h;
+        A.tabX = ex->d_tabX + ex->h_tabXOff[l]; A.tabY = ex->d_tabY + ex->h_tabYOff[l];
+        A.tilesX = tilesX;
+        k_pyr_level<<<dim3(tilesX * tilesY, batch), 256, smem, s>>>(A);
         ++ex->launches;
     }
     if (prof) CUDA_TRY(ex, cudaEventRecord(ex->ev[1], s));
