@@ -89,34 +89,62 @@ struct PyrArgs {             // everything by value: no dependent global loads b
     const uint8_t *src; long long srcStride; int sp, sw, sh;
     uint8_t *dst; long long dstStride; int dp, dw, dh;
     const int2 *tabX, *tabY;
-    int tilesX;
+    int tilesX, srcRows, srcPitch;   // shared-memory source tile: srcRows × srcPitch bytes (pitch multiple of 16)
 };
 __global__ void __launch_bounds__(256) k_pyr_level(PyrArgs a) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];   // uint16 H[rows][PYR_TW], rows = source rows one tile needs
-    uint16_t (*H)[PYR_TW] = reinterpret_cast<uint16_t (*)[PYR_TW]>(smem_raw);
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t *T = smem_raw;                                                        // source tile
+    uint16_t (*H)[PYR_TW] = reinterpret_cast<uint16_t (*)[PYR_TW]>(smem_raw + a.srcRows * a.srcPitch);   // horizontal sums
     const int b = blockIdx.y;
     const int ty = blockIdx.x / a.tilesX, tx = blockIdx.x - ty * a.tilesX;
     const int x0 = tx * PYR_TW, y0 = ty * PYR_TH;
     const int tid = threadIdx.x;
     const uint8_t *S = a.src + (long long)b * a.srcStride;
     const int sp = a.sp, sw = a.sw, sh = a.sh;
-    const int yLast = min(y0 + PYR_TH, a.dh) - 1;
+    const int yLast = min(y0 + PYR_TH, a.dh) - 1, xLast = min(x0 + PYR_TW, a.dw) - 1;
     const int r0 = min(max(a.tabY[y0].x, 0), sh - 1);
     const int r1 = min(max(a.tabY[yLast].x + 1, 0), sh - 1);
-    const int nR = r1 - r0 + 1;
-    // phase 1: thread owns destination column dx, walks the needed source rows
+    const int nR = min(r1 - r0 + 1, a.srcRows);
+    const int c0a = a.tabX[x0].x & ~15;
+    const int cLast = min(a.tabX[xLast].x + 1, sw - 1);
+    const int nChunks = min((cLast - c0a) / 16 + 1, a.srcPitch / 16);
+    const bool aligned = ((((unsigned long long)S | (unsigned)sp) & 15ull) == 0);
+    // phase 0: stage the source tile with 16-byte loads
+    {
+        const int rowBytes = aligned ? min(sp, (sw + 15) & ~15) : sw;
+        for (int i = tid; i < nR * nChunks; i += 256) {
+            const int r = i / nChunks, c = i - r * nChunks;
+            const int gx = c0a + 16 * c;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (gx < rowBytes) {
+                const uint8_t *q = S + (long long)(r0 + r) * sp + gx;
+                if (aligned) {
+                    v = *reinterpret_cast<const uint4 *>(q);
+                } else {
+                    uint32_t ww[4] = {0, 0, 0, 0};
+                    for (int j = 0; j < 16; ++j)
+                        if (gx + j < sw) ww[j >> 2] |= (uint32_t)q[j] << (8 * (j & 3));
+                    v = make_uint4(ww[0], ww[1], ww[2], ww[3]);
+                }
+            }
+            *reinterpret_cast<uint4 *>(T + r * a.srcPitch + 16 * c) = v;
+        }
+    }
+    __syncthreads();
+    // phase 1: thread owns destination column dx, walks the staged source rows
     {
         const int dx = tid & (PYR_TW - 1);
         const int gx = x0 + dx;
         if (gx < a.dw) {
             const int2 t = a.tabX[gx];
-            const int s0 = t.x, s1 = min(t.x + 1, sw - 1);
-            const int a0 = (short)(t.y & 0xffff), a1 = (short)(t.y >> 16);
-            const uint8_t *q = S + (long long)r0 * sp;
+            const int s0 = t.x - c0a, s1 = min(t.x + 1, sw - 1) - c0a;
+            const uint32_t coef = (uint32_t)t.y;   // a0 | a1<<16
+            const uint8_t *col = T + (tid >> 7) * a.srcPitch;
+            const int step = 2 * a.srcPitch;
 #pragma unroll 4
-            for (int r = tid >> 7; r < nR; r += 256 / PYR_TW) {
-                const uint8_t *row = q + (long long)r * sp;
-                H[r][dx] = (uint16_t)((row[s0] * a0 + row[s1] * a1) >> 4);
+            for (int r = tid >> 7; r < nR; r += 256 / PYR_TW, col += step) {
+                const uint32_t px = (uint32_t)col[s0] | ((uint32_t)col[s1] << 8);
+                H[r][dx] = (uint16_t)(__dp2a_lo(coef, px, 0u) >> 4);   // (S[s0]*a0 + S[s1]*a1) >> 4
             }
         }
     }
@@ -1406,7 +1434,8 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
     for (int l = 1; l < G.nlevels; ++l) {
         const int tilesX = (G.lv[l].w + PYR_TW - 1) / PYR_TW, tilesY = (G.lv[l].h + PYR_TH - 1) / PYR_TH;
         const int srcRows = (int)ceil((PYR_TH - 1) * (double)G.lv[l - 1].h / G.lv[l].h) + 4;
-        const size_t smem = (size_t)srcRows * PYR_TW * sizeof(uint16_t);
+        const int srcPitch = 16 * ((int)ceil(((PYR_TW - 1) * (double)G.lv[l - 1].w / G.lv[l].w + 18.0) / 16.0) + 1);
+        const size_t smem = (size_t)srcRows * (srcPitch + PYR_TW * sizeof(uint16_t));
         if (smem > 48 * 1024) { ex->err = "scale factor too large for the pyramid kernel"; return ORBX_ERR_ARG; }
         PyrArgs A;
         if (l == 1) { A.src = P.in0; A.srcStride = P.in0Stride; A.sp = P.in0Pitch; }
@@ -1414,7 +1443,7 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
         A.sw = G.lv[l - 1].w; A.sh = G.lv[l - 1].h;
         A.dst = P.pyr + G.lv[l].off; A.dstStride = G.frameBytes; A.dp = G.lv[l].pitch; A.dw = G.lv[l].w; A.dh = G.lv[l].h;
         A.tabX = ex->d_tabX + ex->h_tabXOff[l]; A.tabY = ex->d_tabY + ex->h_tabYOff[l];
-        A.tilesX = tilesX;
+        A.tilesX = tilesX; A.srcRows = srcRows; A.srcPitch = srcPitch;
         k_pyr_level<<<dim3(tilesX * tilesY, batch), 256, smem, s>>>(A);
         ++ex->launches;
     }
