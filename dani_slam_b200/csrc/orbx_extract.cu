@@ -1122,7 +1122,8 @@ struct orbx_extractor {
     float sf[ORBX_MAX_LEVELS], inv[ORBX_MAX_LEVELS], sig2[ORBX_MAX_LEVELS], invsig2[ORBX_MAX_LEVELS];
     int quota[ORBX_MAX_LEVELS];
     int umax[ORBX_HALF_PATCH + 1];
-    cudaStream_t stream = nullptr, sH2D = nullptr, sD2H = nullptr;
+    cudaStream_t stream = nullptr, sH2D = nullptr, sD2H = nullptr, sSideA = nullptr, sSideB = nullptr;
+    cudaEvent_t evFork = nullptr, evJoin[2] = {nullptr, nullptr};
     cudaEvent_t evIn[4] = {nullptr, nullptr, nullptr, nullptr}, evOut[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;
     long long launches = 0;
@@ -1408,7 +1409,8 @@ int harvest_stage_times(orbx_extractor *ex) {
 // enqueue the whole pipeline for `batch` frames whose level 0 lives at (in0, stride, pitch)
 // (in0 and the four output pointers already point at frame `first`; internal per-frame buffers are offset here)
 int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, int in0Pitch, int batch,
-                 orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int *d_nOut, int *d_mono, int first = 0) {
+                 orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int *d_nOut, int *d_mono, int first = 0,
+                 cudaStream_t onStream = nullptr) {
     const OrbxGeom &G = ex->geom;
     ExParams P;
     const size_t f = (size_t)first;
@@ -1423,8 +1425,8 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
     P.work = ex->d_work + f * G.selTotal; P.workCnt = ex->d_workCnt + f;
     P.kps = d_kps; P.desc = d_desc; P.cap = cap; P.nOut = d_nOut; P.monoIdx = d_mono;
     P.pattern = ex->d_pattern;
-    cudaStream_t s = ex->stream;
-    const bool prof = ex->profiling;
+    cudaStream_t s = onStream ? onStream : ex->stream;
+    const bool prof = ex->profiling && !onStream;
     if (prof) {
         int rc = harvest_stage_times(ex);
         if (rc) return rc;
@@ -1494,7 +1496,34 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
     }
     if (prof) { CUDA_TRY(ex, cudaEventRecord(ex->ev[6], s)); ex->evPending = true; }
     CUDA_TRY(ex, cudaGetLastError());
-    ex->lastBatch = first + batch;
+    ex->lastBatch = std::max(ex->lastBatch, first + batch);
+    return ORBX_OK;
+}
+
+// Device-resident batch: split into sub-batches issued round-robin on two side streams, so the latency-bound
+// kernels of one sub-batch (quadtree, orientation gathers) overlap the ALU-bound FAST kernel of the next.
+// With per-stage profiling on, everything stays on the main stream (stage times are then serial times).
+int run_batch(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, int in0Pitch, int batch, orbx_keypoint *d_kps,
+              uint8_t *d_desc, int cap, int *d_nOut, int *d_mono) {
+    ex->lastBatch = 0;
+    const int nSub = ex->profiling ? 1 : (batch >= 128 ? 4 : (batch >= 32 ? 2 : 1));
+    if (nSub == 1) return run_pipeline(ex, in0, in0Stride, in0Pitch, batch, d_kps, d_desc, cap, d_nOut, d_mono);
+    cudaStream_t side[2] = {ex->sSideA, ex->sSideB};
+    CUDA_TRY(ex, cudaEventRecord(ex->evFork, ex->stream));
+    CUDA_TRY(ex, cudaStreamWaitEvent(side[0], ex->evFork, 0));
+    CUDA_TRY(ex, cudaStreamWaitEvent(side[1], ex->evFork, 0));
+    const int sub = (batch + nSub - 1) / nSub;
+    int k = 0;
+    for (int c0 = 0; c0 < batch; c0 += sub, ++k) {
+        const int cn = std::min(sub, batch - c0);
+        int rc = run_pipeline(ex, in0 + (long long)c0 * in0Stride, in0Stride, in0Pitch, cn, d_kps + (size_t)c0 * cap,
+                              d_desc + (size_t)c0 * cap * 32, cap, d_nOut + c0, d_mono + c0, c0, side[k & 1]);
+        if (rc) return rc;
+    }
+    for (int i = 0; i < 2; ++i) {
+        CUDA_TRY(ex, cudaEventRecord(ex->evJoin[i], side[i]));
+        CUDA_TRY(ex, cudaStreamWaitEvent(ex->stream, ex->evJoin[i], 0));
+    }
     return ORBX_OK;
 }
 
@@ -1561,6 +1590,11 @@ orbx_extractor *orbx_create(int nfeatures, float scale_factor, int nlevels, int 
     CREATE_TRY(cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking));
     CREATE_TRY(cudaStreamCreateWithFlags(&ex->sH2D, cudaStreamNonBlocking));
     CREATE_TRY(cudaStreamCreateWithFlags(&ex->sD2H, cudaStreamNonBlocking));
+    CREATE_TRY(cudaStreamCreateWithFlags(&ex->sSideA, cudaStreamNonBlocking));
+    CREATE_TRY(cudaStreamCreateWithFlags(&ex->sSideB, cudaStreamNonBlocking));
+    CREATE_TRY(cudaEventCreateWithFlags(&ex->evFork, cudaEventDisableTiming));
+    CREATE_TRY(cudaEventCreateWithFlags(&ex->evJoin[0], cudaEventDisableTiming));
+    CREATE_TRY(cudaEventCreateWithFlags(&ex->evJoin[1], cudaEventDisableTiming));
     for (int i = 0; i < 4; ++i) {
         CREATE_TRY(cudaEventCreateWithFlags(&ex->evIn[i], cudaEventDisableTiming));
         CREATE_TRY(cudaEventCreateWithFlags(&ex->evOut[i], cudaEventDisableTiming));
@@ -1598,6 +1632,10 @@ void orbx_destroy(orbx_extractor *ex) {
     if (ex->h_mono) cudaFreeHost(ex->h_mono);
     for (int i = 0; i < 7; ++i) if (ex->ev[i]) cudaEventDestroy(ex->ev[i]);
     for (int i = 0; i < 4; ++i) { if (ex->evIn[i]) cudaEventDestroy(ex->evIn[i]); if (ex->evOut[i]) cudaEventDestroy(ex->evOut[i]); }
+    if (ex->evFork) cudaEventDestroy(ex->evFork);
+    for (int i = 0; i < 2; ++i) if (ex->evJoin[i]) cudaEventDestroy(ex->evJoin[i]);
+    if (ex->sSideA) { cudaStreamSynchronize(ex->sSideA); cudaStreamDestroy(ex->sSideA); }
+    if (ex->sSideB) { cudaStreamSynchronize(ex->sSideB); cudaStreamDestroy(ex->sSideB); }
     if (ex->sH2D) cudaStreamDestroy(ex->sH2D);
     if (ex->sD2H) cudaStreamDestroy(ex->sD2H);
     if (ex->stream) cudaStreamDestroy(ex->stream);
@@ -1628,7 +1666,7 @@ int orbx_extract_batch_device(orbx_extractor *ex, const uint8_t *d_images, size_
     int rc = prepare(ex, rows, cols, rects, n_rects, lap0, lap1, batch);
     if (rc) return rc;
     ex->lastIn0Internal = false;
-    return run_pipeline(ex, d_images, (long long)frame_stride, (int)step, batch, d_kps, d_desc, cap, d_n_out, d_mono);
+    return run_batch(ex, d_images, (long long)frame_stride, (int)step, batch, d_kps, d_desc, cap, d_n_out, d_mono);
 }
 
 int orbx_extract_batch(orbx_extractor *ex, const uint8_t *const *images, int batch, int rows, int cols, size_t step,
@@ -1679,13 +1717,15 @@ int orbx_extract_batch(orbx_extractor *ex, const uint8_t *const *images, int bat
                     CUDA_TRY(ex, cudaMemcpy2DAsync(lvl0 + (size_t)b * G.frameBytes, G.lv[0].pitch, images[b0 + c0 + b], step, cols, rows,
                                                    cudaMemcpyHostToDevice, sIn));
             }
+            cudaStream_t sK = (nChunks > 1 && !ex->profiling) ? ((k & 1) ? ex->sSideB : ex->sSideA) : sC;   // chunks alternate streams
             CUDA_TRY(ex, cudaEventRecord(ex->evIn[k], sIn));
-            CUDA_TRY(ex, cudaStreamWaitEvent(sC, ex->evIn[k], 0));
+            CUDA_TRY(ex, cudaStreamWaitEvent(sK, ex->evIn[k], 0));
             ex->lastIn0Internal = true;
+            if (c0 == 0) ex->lastBatch = 0;
             rc = run_pipeline(ex, lvl0, G.frameBytes, G.lv[0].pitch, cn, ex->d_kps + (size_t)c0 * cap, ex->d_desc + (size_t)c0 * cap * 32, cap,
-                              ex->d_nOut + c0, ex->d_mono + c0, c0);
+                              ex->d_nOut + c0, ex->d_mono + c0, c0, sK == sC ? nullptr : sK);
             if (rc) return rc;
-            CUDA_TRY(ex, cudaEventRecord(ex->evOut[k], sC));
+            CUDA_TRY(ex, cudaEventRecord(ex->evOut[k], sK));
             CUDA_TRY(ex, cudaStreamWaitEvent(sOut, ex->evOut[k], 0));
             CUDA_TRY(ex, cudaMemcpyAsync(ex->h_nOut + c0, ex->d_nOut + c0, cn * sizeof(int), cudaMemcpyDeviceToHost, sOut));
             CUDA_TRY(ex, cudaMemcpyAsync(ex->h_mono + c0, ex->d_mono + c0, cn * sizeof(int), cudaMemcpyDeviceToHost, sOut));
@@ -1695,6 +1735,8 @@ int orbx_extract_batch(orbx_extractor *ex, const uint8_t *const *images, int bat
                                          cudaMemcpyDeviceToHost, sOut));
         }
         CUDA_TRY(ex, cudaStreamSynchronize(sOut));
+        CUDA_TRY(ex, cudaStreamSynchronize(ex->sSideA));
+        CUDA_TRY(ex, cudaStreamSynchronize(ex->sSideB));
         CUDA_TRY(ex, cudaStreamSynchronize(sC));
         for (int b = 0; b < nb; ++b) {
             n_out[b0 + b] = ex->h_nOut[b];
