@@ -196,6 +196,98 @@ __global__ void __launch_bounds__(256) k_rot_hist(const float *a, const float *b
     }
 }
 
+// ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:644-759) with the candidate lists given explicitly.
+// Queries must be replayed in order (earlier matches lock train keypoints through vMatchedDistance and can be
+// stolen later), so ONE warp walks the queries sequentially; the 32 lanes share the candidate
+// scan of the current query (distance + lock test per candidate) and shuffle-reduce the two smallest
+// (distance, list position) keys, which reproduces the strict-'<' first-wins order of the scalar loop.
+__global__ void __launch_bounds__(32) k_search_init(const uint4 *__restrict__ d1, const float *__restrict__ ang1,
+                                                    const int32_t *__restrict__ oct1, int n1, const uint4 *__restrict__ d2,
+                                                    const float *__restrict__ ang2, int n2, const int32_t *__restrict__ cand,
+                                                    const int32_t *__restrict__ off, float nnratio, int checkOri,
+                                                    int32_t *m12, int32_t *m21, int32_t *matchedDist, int8_t *binOf,
+                                                    int32_t *nMatchesOut) {
+    const int lane = threadIdx.x;
+    __shared__ int hist[30];
+    for (int i = lane; i < 30; i += 32) hist[i] = 0;
+    for (int i = lane; i < n1; i += 32) { m12[i] = -1; binOf[i] = -1; }
+    for (int i = lane; i < n2; i += 32) { m21[i] = -1; matchedDist[i] = INT_MAX; }
+    __syncwarp();
+    int nmatches = 0;
+    const unsigned long long NONE = ~0ull;
+    for (int i1 = 0; i1 < n1; ++i1) {
+        if (oct1[i1] > 0) continue;                       // level1 > 0 (:662-664)
+        const int c0 = off[i1], c1 = off[i1 + 1];
+        if (c0 == c1) continue;
+        const uint4 qa = d1[2 * (long long)i1], qb = d1[2 * (long long)i1 + 1];
+        unsigned long long a = NONE, b = NONE;
+        for (int c = c0 + lane; c < c1; c += 32) {
+            const int i2 = cand[c];
+            const int dist = ham256(qa, qb, d2[2 * (long long)i2], d2[2 * (long long)i2 + 1]);
+            if (matchedDist[i2] <= dist) continue;        // :685-686
+            top2_insert(((unsigned long long)(unsigned)dist << 32) | (unsigned)(c - c0), a, b);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long oa = __shfl_xor_sync(0xffffffffu, a, o), ob = __shfl_xor_sync(0xffffffffu, b, o);
+            top2_insert(oa, a, b);
+            top2_insert(ob, a, b);
+        }
+        if (a != NONE) {
+            const int best = (int)(a >> 32);
+            const int best2 = b == NONE ? INT_MAX : (int)(b >> 32);
+            const int bestIdx2 = cand[c0 + (int)(a & 0xffffffffu)];
+            if (best <= 50 && (float)best < __fmul_rn((float)best2, nnratio)) {   // TH_LOW, fp32 ratio (:698-700)
+                const int prev = m21[bestIdx2];
+                if (prev >= 0) --nmatches;
+                ++nmatches;
+                int bin = -1;
+                if (checkOri) {
+                    float rot = __fsub_rn(ang1[i1], ang2[bestIdx2]);
+                    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                    bin = (int)roundf(__fmul_rn(rot, 1.0f / 30));
+                    if (bin == 30) bin = 0;
+                    bin = min(max(bin, 0), 29);
+                }
+                __syncwarp();   // every lane has read m21/ang before lane 0 updates the bookkeeping
+                if (lane == 0) {
+                    if (prev >= 0) m12[prev] = -1;
+                    m12[i1] = bestIdx2;
+                    m21[bestIdx2] = i1;
+                    matchedDist[bestIdx2] = best;
+                    if (checkOri) { binOf[i1] = (int8_t)bin; ++hist[bin]; }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (checkOri) {
+        __shared__ int sel[3];
+        if (lane == 0) {  // ComputeThreeMaxima (:2008-2049); stale (stolen) entries count, as in the reference
+            int mx1 = 0, mx2 = 0, mx3 = 0, i1 = -1, i2 = -1, i3 = -1;
+            for (int i = 0; i < 30; ++i) {
+                const int sz = hist[i];
+                if (sz > mx1) { mx3 = mx2; mx2 = mx1; mx1 = sz; i3 = i2; i2 = i1; i1 = i; }
+                else if (sz > mx2) { mx3 = mx2; mx2 = sz; i3 = i2; i2 = i; }
+                else if (sz > mx3) { mx3 = sz; i3 = i; }
+            }
+            if ((float)mx2 < __fmul_rn(0.1f, (float)mx1)) { i2 = -1; i3 = -1; }
+            else if ((float)mx3 < __fmul_rn(0.1f, (float)mx1)) { i3 = -1; }
+            sel[0] = i1; sel[1] = i2; sel[2] = i3;
+        }
+        __syncwarp();
+        int dropped = 0;
+        for (int i = lane; i < n1; i += 32) {
+            const int bin = binOf[i];
+            if (bin >= 0 && bin != sel[0] && bin != sel[1] && bin != sel[2] && m12[i] >= 0) { m12[i] = -1; ++dropped; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dropped += __shfl_xor_sync(0xffffffffu, dropped, o);
+        nmatches -= dropped;
+    }
+    if (lane == 0) *nMatchesOut = nmatches;
+}
+
 thread_local std::string tl_merr;
 
 }  // namespace
@@ -402,6 +494,55 @@ int orbx_hamming_top2_lists(orbx_matcher *m, const uint8_t *query, int nq, const
     MCUDA_TRY(m, cudaMemcpyAsync(best_idx, dbi, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
     MCUDA_TRY(m, cudaMemcpyAsync(best_dist, dbd, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
     MCUDA_TRY(m, cudaMemcpyAsync(second_dist, dsd, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+    MCUDA_TRY(m, cudaStreamSynchronize(s));
+    return ORBX_OK;
+}
+
+int orbx_search_for_initialization(orbx_matcher *m, const uint8_t *desc1, const float *angle1, const int32_t *octave1, int n1,
+                                   const uint8_t *desc2, const float *angle2, int n2, const int32_t *cand,
+                                   const int32_t *cand_off, float nnratio, int check_orientation, int32_t *matches12,
+                                   int32_t *n_matches) {
+    if (!m) return ORBX_ERR_ARG;
+    if (n1 < 0 || n2 < 0 || (n1 > 0 && (!desc1 || !angle1 || !octave1 || !cand_off || !matches12)) || (n2 > 0 && (!desc2 || !angle2)) || !n_matches) {
+        m->err = "orbx_search_for_initialization: bad argument";
+        return ORBX_ERR_ARG;
+    }
+    *n_matches = 0;
+    if (n1 == 0) return ORBX_OK;
+    const int nc = cand_off[n1];
+    for (int i = 0; i < nc; ++i)
+        if (cand[i] < 0 || cand[i] >= n2) { m->err = "orbx_search_for_initialization: candidate index out of range"; return ORBX_ERR_ARG; }
+    MCUDA_TRY(m, cudaSetDevice(m->device));
+    const size_t d1B = al256((size_t)n1 * 32), d2B = al256((size_t)n2 * 32 + 32), a1B = al256((size_t)n1 * 4), a2B = al256((size_t)n2 * 4 + 4),
+                 cB = al256((size_t)std::max(nc, 1) * 4), oB = al256((size_t)(n1 + 1) * 4);
+    int rc = stage(m, d1B + d2B + 2 * a1B + a2B + cB + oB + a1B /*m12*/ + 2 * a2B /*m21, matchedDist*/ + al256(n1) + 256);
+    if (rc) return rc;
+    uint8_t *p = m->d_buf;
+    uint8_t *dd1 = p; p += d1B;
+    uint8_t *dd2 = p; p += d2B;
+    float *da1 = (float *)p; p += a1B;
+    int32_t *do1 = (int32_t *)p; p += a1B;
+    float *da2 = (float *)p; p += a2B;
+    int32_t *dc = (int32_t *)p; p += cB;
+    int32_t *doff = (int32_t *)p; p += oB;
+    int32_t *dm12 = (int32_t *)p; p += a1B;
+    int32_t *dm21 = (int32_t *)p; p += a2B;
+    int32_t *dmd = (int32_t *)p; p += a2B;
+    int8_t *dbin = (int8_t *)p; p += al256(n1);
+    int32_t *dn = (int32_t *)p;
+    cudaStream_t s = m->stream;
+    MCUDA_TRY(m, cudaMemcpyAsync(dd1, desc1, (size_t)n1 * 32, cudaMemcpyHostToDevice, s));
+    if (n2 > 0) MCUDA_TRY(m, cudaMemcpyAsync(dd2, desc2, (size_t)n2 * 32, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(da1, angle1, (size_t)n1 * 4, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(do1, octave1, (size_t)n1 * 4, cudaMemcpyHostToDevice, s));
+    if (n2 > 0) MCUDA_TRY(m, cudaMemcpyAsync(da2, angle2, (size_t)n2 * 4, cudaMemcpyHostToDevice, s));
+    if (nc > 0) MCUDA_TRY(m, cudaMemcpyAsync(dc, cand, (size_t)nc * 4, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(doff, cand_off, (size_t)(n1 + 1) * 4, cudaMemcpyHostToDevice, s));
+    k_search_init<<<1, 32, 0, s>>>((const uint4 *)dd1, da1, do1, n1, (const uint4 *)dd2, da2, n2, dc, doff, nnratio, check_orientation,
+                                   dm12, dm21, dmd, dbin, dn);
+    MCUDA_TRY(m, cudaGetLastError());
+    MCUDA_TRY(m, cudaMemcpyAsync(matches12, dm12, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(n_matches, dn, 4, cudaMemcpyDeviceToHost, s));
     MCUDA_TRY(m, cudaStreamSynchronize(s));
     return ORBX_OK;
 }

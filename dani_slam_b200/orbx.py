@@ -81,6 +81,7 @@ def lib() -> C.CDLL:
     L.orbx_ratio_test_device.argtypes = [vp, vp, i32, f64, vp]
     L.orbx_hamming_top2_lists.argtypes = [vp, vp, i32, vp, i64, vp, vp, vp, vp, vp]
     L.orbx_rot_hist_filter.argtypes = [vp, vp, vp, i32, vp]
+    L.orbx_search_for_initialization.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, f32, i32, vp, vp]
     L.orbx_rot_hist_filter_device.argtypes = [vp, vp, vp, i32, vp]
     L.orbx_descriptor_distance.restype = i32
     L.orbx_descriptor_distance.argtypes = [vp, vp]
@@ -343,6 +344,23 @@ class ORBmatcher:
         keep = np.zeros(len(a), np.uint8)
         self._chk(self.L.orbx_rot_hist_filter(self.h, _p(a), _p(b), len(a), _p(keep)))
         return keep.astype(bool)
+
+    def SearchForInitialization(self, desc1, angle1, octave1, desc2, angle2, cand, cand_off):
+        """ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:644-759) over explicit candidate lists
+        → (nmatches, vnMatches12)."""
+        d1 = np.ascontiguousarray(desc1, np.uint8).reshape(-1, 32)
+        d2 = np.ascontiguousarray(desc2, np.uint8).reshape(-1, 32)
+        a1 = np.ascontiguousarray(angle1, np.float32)
+        a2 = np.ascontiguousarray(angle2, np.float32)
+        o1 = np.ascontiguousarray(octave1, np.int32)
+        cand = np.ascontiguousarray(cand, np.int32)
+        off = np.ascontiguousarray(cand_off, np.int32)
+        assert len(off) == len(d1) + 1 and len(a1) == len(d1) and len(a2) == len(d2)
+        m12 = np.full(len(d1), -1, np.int32)
+        n = C.c_int32(0)
+        self._chk(self.L.orbx_search_for_initialization(self.h, _p(d1), _p(a1), _p(o1), len(d1), _p(d2), _p(a2), len(d2), _p(cand), _p(off),
+                                                        float(self.mfNNratio), int(self.mbCheckOrientation), _p(m12), C.byref(n)))
+        return n.value, m12
 
     # device-pointer forms (ints), asynchronous on stream()
     def knn2_device(self, d_q, nq, d_db, ndb, idx_base, d_idx, d_dist):

@@ -153,6 +153,15 @@ int orbx_hamming_top2_lists(orbx_matcher *m, const uint8_t *query, int nq, const
  * fullest bins subject to the 0.1·max rule.  HOST / DEVICE buffers; n matches. */
 int orbx_rot_hist_filter(orbx_matcher *m, const float *angle_a, const float *angle_b, int n, uint8_t *keep);
 int orbx_rot_hist_filter_device(orbx_matcher *m, const float *d_angle_a, const float *d_angle_b, int n, uint8_t *d_keep);
+/* ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:644-759) with the per-query candidate lists
+ * (the output of F2.GetFeaturesInArea(vbPrevMatched[i1], windowSize, 0, 0), src/ORBmatcher.cc:666) given
+ * explicitly: query order, the vMatchedDistance lock, match stealing, TH_LOW, the fp32 ratio test and the
+ * rotation-histogram purge are replayed exactly.  matches12[n1] = vnMatches12; *n_matches = return value.
+ * HOST buffers. */
+int orbx_search_for_initialization(orbx_matcher *m, const uint8_t *desc1, const float *angle1, const int32_t *octave1,
+                                   int n1, const uint8_t *desc2, const float *angle2, int n2, const int32_t *cand,
+                                   const int32_t *cand_off, float nnratio, int check_orientation, int32_t *matches12,
+                                   int32_t *n_matches);
 /* ORBmatcher::DescriptorDistance for one pair on the host (inline popcount; no device involved). */
 int orbx_descriptor_distance(const uint8_t *a, const uint8_t *b);
 

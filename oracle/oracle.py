@@ -194,3 +194,13 @@ def rot_hist_filter(a, b):
     keep = np.zeros(len(a), np.uint8)
     lib().orc_rot_hist_filter(_p(a), _p(b), len(a), _p(keep))
     return keep.astype(bool)
+
+
+def search_init(d1, a1, o1, d2, a2, cand, off, nnratio=0.9, check_ori=True):
+    d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)
+    a1 = np.ascontiguousarray(a1, np.float32); a2 = np.ascontiguousarray(a2, np.float32)
+    o1 = np.ascontiguousarray(o1, np.int32)
+    cand = np.ascontiguousarray(cand, np.int32); off = np.ascontiguousarray(off, np.int32)
+    m12 = np.zeros(len(d1), np.int32)
+    n = lib().orc_search_init(_p(d1), _p(a1), _p(o1), len(d1), _p(d2), _p(a2), len(d2), _p(cand), _p(off), float(nnratio), int(check_ori), _p(m12))
+    return n, m12

@@ -122,3 +122,41 @@ def test_large_db_properties(orbx_mod, oracle_mod):
     sample = np.r_[0:8, 1000:1008]
     ridx, rdist = oracle_mod.knn2(q[sample], db, nthreads=8)
     assert np.array_equal(idx[sample], ridx) and np.array_equal(dist[sample], rdist)
+
+
+def _init_case(n1, n2, seed, dense):
+    """Two keypoint sets where set 1 holds noisy copies of set-2 descriptors; candidate lists overlap heavily
+    so that train keypoints get locked and stolen (src/ORBmatcher.cc:683-710)."""
+    rng = np.random.default_rng(seed)
+    d2 = rng.integers(0, 256, (n2, 32), dtype=np.uint8)
+    src = rng.integers(0, n2, n1)
+    d1 = d2[src].copy()
+    for i in range(n1):
+        k = int(rng.integers(0, 70))
+        for bit in rng.choice(256, size=k, replace=False):
+            d1[i, bit >> 3] ^= np.uint8(1 << (bit & 7))
+    a2 = rng.uniform(0, 360, n2).astype(np.float32)
+    a1 = ((a2[src] + rng.choice([0.0, 2.0, 31.0, 200.0], n1, p=[0.6, 0.2, 0.1, 0.1])) % 360).astype(np.float32)
+    o1 = rng.choice([0, 0, 0, 1, 3], n1).astype(np.int32)
+    lists = []
+    for i in range(n1):
+        m = int(rng.integers(0, dense))
+        c = rng.integers(0, n2, m).tolist()
+        if rng.random() < 0.8:
+            c.insert(int(rng.integers(0, len(c) + 1)), int(src[i]))
+        if rng.random() < 0.3 and c:
+            c.append(c[0])                                                # duplicate candidate entries
+        lists.append(c)
+    off = np.concatenate([[0], np.cumsum([len(c) for c in lists])]).astype(np.int32)
+    cand = np.array([x for c in lists for x in c], np.int32)
+    return d1, a1, o1, d2, a2, cand, off
+
+
+@pytest.mark.parametrize("n1,n2,dense,ratio,ori", [(500, 300, 40, 0.9, True), (2000, 2500, 60, 0.9, True), (800, 50, 30, 0.6, False),
+                                                    (64, 64, 100, 0.9, True), (5000, 5000, 50, 0.9, True)])
+def test_search_for_initialization_vs_oracle(orbx_mod, oracle_mod, n1, n2, dense, ratio, ori):
+    d1, a1, o1, d2, a2, cand, off = _init_case(n1, n2, n1 + n2, dense)
+    n, m12 = orbx_mod.ORBmatcher(ratio, ori).SearchForInitialization(d1, a1, o1, d2, a2, cand, off)
+    rn, rm12 = oracle_mod.search_init(d1, a1, o1, d2, a2, cand, off, ratio, ori)
+    assert n == rn and np.array_equal(m12, rm12)
+    assert rn > 0 and (rm12 >= 0).sum() == rn
