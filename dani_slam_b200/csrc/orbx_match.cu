@@ -288,6 +288,162 @@ __global__ void __launch_bounds__(32) k_search_init(const uint4 *__restrict__ d1
     if (lane == 0) *nMatchesOut = nmatches;
 }
 
+// ---- Frame grid: AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea (src/Frame.cc:387-418, :659-738) ----
+#define GRID_COLS 64
+#define GRID_ROWS 48
+#define GRID_CELLS (GRID_COLS * GRID_ROWS)
+
+__device__ __forceinline__ int grid_cell_of(float x, float y, float minX, float minY, float wInv, float hInv) {
+    const int px = (int)roundf(__fmul_rn(__fsub_rn(x, minX), wInv)), py = (int)roundf(__fmul_rn(__fsub_rn(y, minY), hInv));
+    if (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) return -1;
+    return px * GRID_ROWS + py;
+}
+__global__ void k_grid_count(const float2 *xy, int n, float minX, float minY, float wInv, float hInv, int *cellCnt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = grid_cell_of(xy[i].x, xy[i].y, minX, minY, wInv, hInv);
+    if (c >= 0) atomicAdd(&cellCnt[c], 1);
+}
+// single block: exclusive scan of a[0..n) into out[0..n], out[n] = total
+__global__ void __launch_bounds__(1024) k_scan_excl(const int *a, int n, int *out) {
+    __shared__ int warpSum[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < n ? a[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((threadIdx.x & 31) >= o) incl += t;
+        }
+        if ((threadIdx.x & 31) == 31) warpSum[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = warpSum[threadIdx.x], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (threadIdx.x >= o) wi += t;
+            }
+            warpSum[threadIdx.x] = wi - w;
+        }
+        __syncthreads();
+        const int excl = carry + warpSum[threadIdx.x >> 5] + incl - v;
+        if (i < n) out[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = carry;
+}
+__global__ void k_grid_fill(const float2 *xy, int n, float minX, float minY, float wInv, float hInv, const int *cellOff, int *cellFill, int *items) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = grid_cell_of(xy[i].x, xy[i].y, minX, minY, wInv, hInv);
+    if (c >= 0) items[cellOff[c] + atomicAdd(&cellFill[c], 1)] = i;
+}
+// push_back order inside a cell is ascending keypoint index: sort each (short) cell list
+__global__ void k_grid_sort_cells(const int *cellOff, int *items) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= GRID_CELLS) return;
+    const int lo = cellOff[c], hi = cellOff[c + 1];
+    for (int i = lo + 1; i < hi; ++i) {
+        const int v = items[i];
+        int j = i - 1;
+        while (j >= lo && items[j] > v) { items[j + 1] = items[j]; --j; }
+        items[j + 1] = v;
+    }
+}
+// one thread per query; FILL=false counts, FILL=true writes the list (reference order: ix, iy, insertion)
+template <bool FILL>
+__global__ void k_area_query(const float2 *xy, const int32_t *octave, const int *cellOff, const int *items, float minX, float minY,
+                             float wInv, float hInv, const float *queries, int nq, int minLevel, int maxLevel, int *cnt,
+                             const int *outOff, int32_t *out) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const float x = queries[3 * q], y = queries[3 * q + 1], r = queries[3 * q + 2];
+    const int x0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, minX), r), wInv)));
+    const int x1 = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, minX), r), wInv)));
+    const int y0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, minY), r), hInv)));
+    const int y1 = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, minY), r), hInv)));
+    int n = 0;
+    int at = FILL ? outOff[q] : 0;
+    if (!(x0 >= GRID_COLS || x1 < 0 || y0 >= GRID_ROWS || y1 < 0)) {
+        const bool checkLevels = (minLevel > 0) || (maxLevel >= 0);
+        for (int ix = x0; ix <= x1; ++ix)
+            for (int iy = y0; iy <= y1; ++iy) {
+                const int c = ix * GRID_ROWS + iy;
+                for (int k = cellOff[c]; k < cellOff[c + 1]; ++k) {
+                    const int j = items[k];
+                    if (checkLevels) {
+                        const int o = octave[j];
+                        if (o < minLevel) continue;
+                        if (maxLevel >= 0 && o > maxLevel) continue;
+                    }
+                    const float2 pj = xy[j];
+                    if (fabsf(__fsub_rn(pj.x, x)) < r && fabsf(__fsub_rn(pj.y, y)) < r) {
+                        if (FILL) out[at++] = j;
+                        ++n;
+                    }
+                }
+            }
+    }
+    if (!FILL) cnt[q] = n;
+}
+
+// ---- stereo association tail (src/Frame.cc:862-914) over the kNN + ratio matches; one block ----
+__global__ void __launch_bounds__(256) k_stereo_tail(const float *uL, const float *uR, int nL, int nR, const int32_t *idx,
+                                                     const int32_t *dist, const uint8_t *keep, float mbf, float mb, float *uRight,
+                                                     float *depth, int *keptOut) {
+    __shared__ int hist[257];
+    __shared__ float thDist;
+    __shared__ int total, dropped;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 257; i += 256) hist[i] = 0;
+    if (tid == 0) { total = 0; dropped = 0; }
+    __syncthreads();
+    const float maxD = __fdiv_rn(mbf, mb);
+    for (int i = tid; i < nL; i += 256) {
+        float ur = -1.f, dp = -1.f;
+        if (keep[i]) {
+            const int iR = idx[2 * i];
+            if (iR >= 0 && iR < nR) {
+                float disparity = __fsub_rn(uL[i], uR[iR]);
+                if (disparity >= 0.f && disparity < maxD) {
+                    if (disparity <= 0.f) disparity = 0.01f;
+                    dp = __fdiv_rn(mbf, disparity);
+                    ur = uR[iR];
+                    atomicAdd(&hist[min(max(dist[2 * i], 0), 256)], 1);
+                    atomicAdd(&total, 1);
+                }
+            }
+        }
+        uRight[i] = ur; depth[i] = dp;
+    }
+    __syncthreads();
+    if (tid == 0) {  // median of the sorted distances = element [size/2]
+        float th = 3.4e38f;
+        if (total > 0) {
+            const int k = total / 2;
+            int acc = 0, med = 0;
+            for (int d = 0; d <= 256; ++d) { acc += hist[d]; if (acc > k) { med = d; break; } }
+            th = __fmul_rn(1.5f, (float)med);
+        }
+        thDist = th;
+    }
+    __syncthreads();
+    for (int i = tid; i < nL; i += 256) {
+        if (uRight[i] != -1.f || depth[i] != -1.f) {
+            if (!((float)dist[2 * i] < thDist)) { uRight[i] = -1.f; depth[i] = -1.f; atomicAdd(&dropped, 1); }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) *keptOut = total - dropped;
+}
+
 thread_local std::string tl_merr;
 
 }  // namespace
@@ -543,6 +699,109 @@ int orbx_search_for_initialization(orbx_matcher *m, const uint8_t *desc1, const 
     MCUDA_TRY(m, cudaGetLastError());
     MCUDA_TRY(m, cudaMemcpyAsync(matches12, dm12, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
     MCUDA_TRY(m, cudaMemcpyAsync(n_matches, dn, 4, cudaMemcpyDeviceToHost, s));
+    MCUDA_TRY(m, cudaStreamSynchronize(s));
+    return ORBX_OK;
+}
+
+int orbx_features_in_area(orbx_matcher *m, const float *keypoints_xy, const int32_t *octave, int n, float min_x, float min_y,
+                          float max_x, float max_y, const float *queries_xyr, int nq, int min_level, int max_level,
+                          int32_t *cand_off, int32_t *cand, int cap, int32_t *total_out) {
+    if (!m) return ORBX_ERR_ARG;
+    if (n < 0 || nq < 0 || (n > 0 && (!keypoints_xy || !octave)) || (nq > 0 && !queries_xyr) || !cand_off || !total_out || !(max_x > min_x) || !(max_y > min_y)) {
+        m->err = "orbx_features_in_area: bad argument";
+        return ORBX_ERR_ARG;
+    }
+    MCUDA_TRY(m, cudaSetDevice(m->device));
+    const float wInv = (float)GRID_COLS / (float)(max_x - min_x), hInv = (float)GRID_ROWS / (float)(max_y - min_y);
+    const size_t xyB = al256((size_t)std::max(n, 1) * 8), ocB = al256((size_t)std::max(n, 1) * 4), cellB = al256((GRID_CELLS + 1) * 4),
+                 itB = al256((size_t)std::max(n, 1) * 4), qB = al256((size_t)std::max(nq, 1) * 12), qcB = al256((size_t)(nq + 1) * 4);
+    int rc = stage(m, xyB + ocB + 3 * cellB + itB + qB + 2 * qcB);
+    if (rc) return rc;
+    uint8_t *p = m->d_buf;
+    float2 *dxy = (float2 *)p; p += xyB;
+    int32_t *doc = (int32_t *)p; p += ocB;
+    int *dCnt = (int *)p; p += cellB;
+    int *dOff = (int *)p; p += cellB;
+    int *dFill = (int *)p; p += cellB;
+    int *dItems = (int *)p; p += itB;
+    float *dq = (float *)p; p += qB;
+    int *dqCnt = (int *)p; p += qcB;
+    int *dqOff = (int *)p; p += qcB;
+    cudaStream_t s = m->stream;
+    if (n > 0) {
+        MCUDA_TRY(m, cudaMemcpyAsync(dxy, keypoints_xy, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+        MCUDA_TRY(m, cudaMemcpyAsync(doc, octave, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    }
+    if (nq > 0) MCUDA_TRY(m, cudaMemcpyAsync(dq, queries_xyr, (size_t)nq * 12, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemsetAsync(dCnt, 0, 2 * cellB + cellB, s));   // dCnt, dOff, dFill are contiguous
+    if (n > 0) k_grid_count<<<(n + 255) / 256, 256, 0, s>>>(dxy, n, min_x, min_y, wInv, hInv, dCnt);
+    k_scan_excl<<<1, 1024, 0, s>>>(dCnt, GRID_CELLS, dOff);
+    if (n > 0) {
+        k_grid_fill<<<(n + 255) / 256, 256, 0, s>>>(dxy, n, min_x, min_y, wInv, hInv, dOff, dFill, dItems);
+        k_grid_sort_cells<<<(GRID_CELLS + 255) / 256, 256, 0, s>>>(dOff, dItems);
+    }
+    int total = 0;
+    if (nq > 0) {
+        k_area_query<false><<<(nq + 127) / 128, 128, 0, s>>>(dxy, doc, dOff, dItems, min_x, min_y, wInv, hInv, dq, nq, min_level, max_level, dqCnt, nullptr, nullptr);
+        k_scan_excl<<<1, 1024, 0, s>>>(dqCnt, nq, dqOff);
+        MCUDA_TRY(m, cudaMemcpyAsync(cand_off, dqOff, (size_t)(nq + 1) * 4, cudaMemcpyDeviceToHost, s));
+        MCUDA_TRY(m, cudaStreamSynchronize(s));
+        total = cand_off[nq];
+    } else {
+        cand_off[0] = 0;
+    }
+    *total_out = total;
+    if (total > 0 && cand && cap >= total) {
+        // the candidate array lives after the staged inputs: grow the staging buffer if needed (contents are kept
+        // by re-running the cheap build when the buffer moves)
+        int32_t *dOut = nullptr;
+        MCUDA_TRY(m, cudaMalloc((void **)&dOut, (size_t)total * 4));
+        k_area_query<true><<<(nq + 127) / 128, 128, 0, s>>>(dxy, doc, dOff, dItems, min_x, min_y, wInv, hInv, dq, nq, min_level, max_level, nullptr, dqOff, dOut);
+        cudaError_t e = cudaMemcpyAsync(cand, dOut, (size_t)total * 4, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        cudaFree(dOut);
+        if (e != cudaSuccess) { m->err = std::string("orbx_features_in_area: ") + cudaGetErrorString(e); return ORBX_ERR_CUDA; }
+    } else if (total > 0 && cand) {
+        m->err = "orbx_features_in_area: candidate capacity too small (see total_out)";
+        return ORBX_ERR_CAPACITY;
+    }
+    MCUDA_TRY(m, cudaGetLastError());
+    return ORBX_OK;
+}
+
+int orbx_stereo_tail(orbx_matcher *m, const float *u_left, const float *u_right, int n_left, int n_right, const int32_t *idx,
+                     const int32_t *dist, const uint8_t *keep, float mbf, float mb, float *mvu_right, float *mv_depth, int32_t *n_kept) {
+    if (!m) return ORBX_ERR_ARG;
+    if (n_left < 0 || n_right < 0 || (n_left > 0 && (!u_left || !idx || !dist || !keep || !mvu_right || !mv_depth)) || (n_right > 0 && !u_right) || !n_kept) {
+        m->err = "orbx_stereo_tail: bad argument";
+        return ORBX_ERR_ARG;
+    }
+    *n_kept = 0;
+    if (n_left == 0) return ORBX_OK;
+    MCUDA_TRY(m, cudaSetDevice(m->device));
+    const size_t lB = al256((size_t)n_left * 4), rB = al256((size_t)std::max(n_right, 1) * 4), iB = al256((size_t)n_left * 8), kB = al256(n_left);
+    int rc = stage(m, 3 * lB + rB + 2 * iB + kB + 256);
+    if (rc) return rc;
+    uint8_t *p = m->d_buf;
+    float *duL = (float *)p; p += lB;
+    float *duR = (float *)p; p += rB;
+    int32_t *di = (int32_t *)p; p += iB;
+    int32_t *dd = (int32_t *)p; p += iB;
+    uint8_t *dk = p; p += kB;
+    float *dur = (float *)p; p += lB;
+    float *ddp = (float *)p; p += lB;
+    int *dn = (int *)p;
+    cudaStream_t s = m->stream;
+    MCUDA_TRY(m, cudaMemcpyAsync(duL, u_left, (size_t)n_left * 4, cudaMemcpyHostToDevice, s));
+    if (n_right > 0) MCUDA_TRY(m, cudaMemcpyAsync(duR, u_right, (size_t)n_right * 4, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(di, idx, (size_t)n_left * 8, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(dd, dist, (size_t)n_left * 8, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(dk, keep, (size_t)n_left, cudaMemcpyHostToDevice, s));
+    k_stereo_tail<<<1, 256, 0, s>>>(duL, duR, n_left, n_right, di, dd, dk, mbf, mb, dur, ddp, dn);
+    MCUDA_TRY(m, cudaGetLastError());
+    MCUDA_TRY(m, cudaMemcpyAsync(mvu_right, dur, (size_t)n_left * 4, cudaMemcpyDeviceToHost, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(mv_depth, ddp, (size_t)n_left * 4, cudaMemcpyDeviceToHost, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(n_kept, dn, 4, cudaMemcpyDeviceToHost, s));
     MCUDA_TRY(m, cudaStreamSynchronize(s));
     return ORBX_OK;
 }

@@ -81,6 +81,8 @@ def lib() -> C.CDLL:
     L.orbx_ratio_test_device.argtypes = [vp, vp, i32, f64, vp]
     L.orbx_hamming_top2_lists.argtypes = [vp, vp, i32, vp, i64, vp, vp, vp, vp, vp]
     L.orbx_rot_hist_filter.argtypes = [vp, vp, vp, i32, vp]
+    L.orbx_features_in_area.argtypes = [vp, vp, vp, i32, f32, f32, f32, f32, vp, i32, i32, i32, vp, vp, i32, vp]
+    L.orbx_stereo_tail.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, f32, f32, vp, vp, vp]
     L.orbx_search_for_initialization.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, f32, i32, vp, vp]
     L.orbx_rot_hist_filter_device.argtypes = [vp, vp, vp, i32, vp]
     L.orbx_descriptor_distance.restype = i32
@@ -361,6 +363,30 @@ class ORBmatcher:
         self._chk(self.L.orbx_search_for_initialization(self.h, _p(d1), _p(a1), _p(o1), len(d1), _p(d2), _p(a2), len(d2), _p(cand), _p(off),
                                                         float(self.mfNNratio), int(self.mbCheckOrientation), _p(m12), C.byref(n)))
         return n.value, m12
+
+    def GetFeaturesInArea(self, keypoints_xy, octave, bounds, queries_xyr, minLevel=-1, maxLevel=-1):
+        """Batched Frame::GetFeaturesInArea over the 64×48 grid (src/Frame.cc:387-418, :659-738) → (cand_off, cand)."""
+        xy = np.ascontiguousarray(keypoints_xy, np.float32).reshape(-1, 2)
+        oc = np.ascontiguousarray(octave, np.int32)
+        q = np.ascontiguousarray(queries_xyr, np.float32).reshape(-1, 3)
+        off = np.zeros(len(q) + 1, np.int32)
+        tot = C.c_int32(0)
+        b = [float(v) for v in bounds]
+        self._chk(self.L.orbx_features_in_area(self.h, _p(xy), _p(oc), len(xy), b[0], b[1], b[2], b[3], _p(q), len(q), minLevel, maxLevel, _p(off), None, 0, C.byref(tot)))
+        cand = np.zeros(max(tot.value, 1), np.int32)
+        if tot.value:
+            self._chk(self.L.orbx_features_in_area(self.h, _p(xy), _p(oc), len(xy), b[0], b[1], b[2], b[3], _p(q), len(q), minLevel, maxLevel, _p(off), _p(cand), tot.value, C.byref(tot)))
+        return off, cand[: tot.value]
+
+    def StereoTail(self, uL, uR, idx, dist, keep, mbf, mb):
+        """Tail of Frame::ComputeStereoMatches (src/Frame.cc:862-914) over kNN+ratio matches → (n_kept, mvuRight, mvDepth)."""
+        uL = np.ascontiguousarray(uL, np.float32); uR = np.ascontiguousarray(uR, np.float32)
+        idx = np.ascontiguousarray(idx, np.int32); dist = np.ascontiguousarray(dist, np.int32)
+        keep = np.ascontiguousarray(keep, np.uint8)
+        ur = np.zeros(len(uL), np.float32); dp = np.zeros(len(uL), np.float32)
+        n = C.c_int32(0)
+        self._chk(self.L.orbx_stereo_tail(self.h, _p(uL), _p(uR), len(uL), len(uR), _p(idx), _p(dist), _p(keep), float(mbf), float(mb), _p(ur), _p(dp), C.byref(n)))
+        return n.value, ur, dp
 
     # device-pointer forms (ints), asynchronous on stream()
     def knn2_device(self, d_q, nq, d_db, ndb, idx_base, d_idx, d_dist):

@@ -72,7 +72,7 @@ def stereo_right(left: np.ndarray, seed: int, max_disp: int = 40) -> np.ndarray:
     rng = np.random.default_rng(seed + 1_000_000)
     h, w = left.shape
     right = np.empty_like(left)
-    band = 16
+    band = 94
     for y0 in range(0, h, band):
         d = int(rng.integers(1, max_disp + 1))
         rows = left[y0:y0 + band]

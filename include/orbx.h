@@ -162,6 +162,21 @@ int orbx_search_for_initialization(orbx_matcher *m, const uint8_t *desc1, const 
                                    int n1, const uint8_t *desc2, const float *angle2, int n2, const int32_t *cand,
                                    const int32_t *cand_off, float nnratio, int check_orientation, int32_t *matches12,
                                    int32_t *n_matches);
+/* Frame::AssignFeaturesToGrid + Frame::GetFeaturesInArea (src/Frame.cc:387-418, :659-738; 64×48 grid,
+ * include/Frame.h:52-53) for a batch of queries: keypoints_xy = n×{x,y} (mvKeysUn), octave[n], image bounds
+ * (mnMinX, mnMinY, mnMaxX, mnMaxY), queries = nq×{x, y, r}.  cand_off[nq+1] and cand[*total_out] are the
+ * vIndices lists in the reference's order (cell column, cell row, insertion order).  Call with cand=NULL to
+ * size the output.  HOST buffers. */
+int orbx_features_in_area(orbx_matcher *m, const float *keypoints_xy, const int32_t *octave, int n, float min_x, float min_y,
+                          float max_x, float max_y, const float *queries_xyr, int nq, int min_level, int max_level,
+                          int32_t *cand_off, int32_t *cand, int cap, int32_t *total_out);
+/* Stereo association tail of Frame::ComputeStereoMatches (src/Frame.cc:862-914) fed by the Hamming kNN + Lowe
+ * ratio of src/Frame.cc:1078-1085: for left keypoint i with keep[i], iR = idx[2i], distance = dist[2i]; disparity
+ * gate 0 <= uL-uR < mbf/mb, depth = mbf/disparity, then the 1.5·median distance cut.  mvu_right / mv_depth are
+ * n_left arrays (-1 = no stereo); *n_kept = stereo points that survive.  HOST buffers. */
+int orbx_stereo_tail(orbx_matcher *m, const float *u_left, const float *u_right, int n_left, int n_right, const int32_t *idx,
+                     const int32_t *dist, const uint8_t *keep, float mbf, float mb, float *mvu_right, float *mv_depth,
+                     int32_t *n_kept);
 /* ORBmatcher::DescriptorDistance for one pair on the host (inline popcount; no device involved). */
 int orbx_descriptor_distance(const uint8_t *a, const uint8_t *b);
 

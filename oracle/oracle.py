@@ -64,6 +64,10 @@ def lib() -> C.CDLL:
         L.orc_ratio_test.argtypes = [vp, i32, C.c_double, vp]
         L.orc_top2_lists.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
         L.orc_rot_hist_filter.argtypes = [vp, vp, i32, vp]
+        L.orc_features_in_area.restype = i32
+        L.orc_features_in_area.argtypes = [vp, vp, i32, f32, f32, f32, f32, vp, i32, i32, i32, vp, vp, i32]
+        L.orc_stereo_tail.restype = i32
+        L.orc_stereo_tail.argtypes = [vp, vp, i32, i32, vp, vp, vp, f32, f32, vp, vp]
         L.orc_search_init.restype = i32
         L.orc_search_init.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, vp, f32, i32, vp]
         _lib = L
@@ -204,3 +208,21 @@ def search_init(d1, a1, o1, d2, a2, cand, off, nnratio=0.9, check_ori=True):
     m12 = np.zeros(len(d1), np.int32)
     n = lib().orc_search_init(_p(d1), _p(a1), _p(o1), len(d1), _p(d2), _p(a2), len(d2), _p(cand), _p(off), float(nnratio), int(check_ori), _p(m12))
     return n, m12
+
+
+def features_in_area(xy, octave, bounds, queries, min_level=-1, max_level=-1):
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2); octave = np.ascontiguousarray(octave, np.int32)
+    queries = np.ascontiguousarray(queries, np.float32).reshape(-1, 3)
+    off = np.zeros(len(queries) + 1, np.int32)
+    total = lib().orc_features_in_area(_p(xy), _p(octave), len(xy), *[float(b) for b in bounds], _p(queries), len(queries), min_level, max_level, _p(off), None, 0)
+    cand = np.zeros(max(total, 1), np.int32)
+    lib().orc_features_in_area(_p(xy), _p(octave), len(xy), *[float(b) for b in bounds], _p(queries), len(queries), min_level, max_level, _p(off), _p(cand), total)
+    return off, cand[:total]
+
+
+def stereo_tail(uL, uR, idx, dist, keep, mbf, mb):
+    uL = np.ascontiguousarray(uL, np.float32); uR = np.ascontiguousarray(uR, np.float32)
+    idx = np.ascontiguousarray(idx, np.int32); dist = np.ascontiguousarray(dist, np.int32); keep = np.ascontiguousarray(keep, np.uint8)
+    ur = np.zeros(len(uL), np.float32); dp = np.zeros(len(uL), np.float32)
+    n = lib().orc_stereo_tail(_p(uL), _p(uR), len(uL), len(uR), _p(idx), _p(dist), _p(keep), float(mbf), float(mb), _p(ur), _p(dp))
+    return n, ur, dp

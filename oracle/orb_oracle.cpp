@@ -819,4 +819,82 @@ int orc_search_init(const uint8_t *d1, const float *ang1, const int32_t *oct1, i
     return nmatches;
 }
 
+
+// ---- Frame grid (src/Frame.cc:387-418 AssignFeaturesToGrid, :727-738 PosInGrid, :659-725 GetFeaturesInArea) ----
+// 64×48 cells (include/Frame.h:52-53) over [minX,maxX)×[minY,maxY); queries are (x, y, r) triples; candidate
+// lists come out in the reference's order: cell column, then cell row, then insertion order inside the cell.
+int orc_features_in_area(const float *xy, const int32_t *octave, int n, float minX, float minY, float maxX, float maxY,
+                         const float *queries, int nq, int minLevel, int maxLevel, int32_t *cand_off, int32_t *cand, int cap) {
+    const int COLS = 64, ROWS = 48;
+    const float wInv = static_cast<float>(COLS) / static_cast<float>(maxX - minX);
+    const float hInv = static_cast<float>(ROWS) / static_cast<float>(maxY - minY);
+    std::vector<std::vector<int>> grid(COLS * ROWS);
+    for (int i = 0; i < n; ++i) {
+        const int px = (int)std::round((xy[2 * i] - minX) * wInv), py = (int)std::round((xy[2 * i + 1] - minY) * hInv);
+        if (px < 0 || px >= COLS || py < 0 || py >= ROWS) continue;
+        grid[px * ROWS + py].push_back(i);
+    }
+    int total = 0;
+    cand_off[0] = 0;
+    for (int q = 0; q < nq; ++q) {
+        const float x = queries[3 * q], y = queries[3 * q + 1], r = queries[3 * q + 2];
+        const int x0 = std::max(0, (int)std::floor((x - minX - r) * wInv)), x1 = std::min(COLS - 1, (int)std::ceil((x - minX + r) * wInv));
+        const int y0 = std::max(0, (int)std::floor((y - minY - r) * hInv)), y1 = std::min(ROWS - 1, (int)std::ceil((y - minY + r) * hInv));
+        if (!(x0 >= COLS || x1 < 0 || y0 >= ROWS || y1 < 0)) {
+            const bool checkLevels = (minLevel > 0) || (maxLevel >= 0);
+            for (int ix = x0; ix <= x1; ++ix)
+                for (int iy = y0; iy <= y1; ++iy)
+                    for (int j : grid[ix * ROWS + iy]) {
+                        if (checkLevels) {
+                            if (octave[j] < minLevel) continue;
+                            if (maxLevel >= 0 && octave[j] > maxLevel) continue;
+                        }
+                        const float dx = xy[2 * j] - x, dy = xy[2 * j + 1] - y;
+                        if (std::fabs(dx) < r && std::fabs(dy) < r) {
+                            if (total < cap) cand[total] = j;
+                            ++total;
+                        }
+                    }
+        }
+        cand_off[q + 1] = total;
+    }
+    return total;
+}
+
+// ---- stereo association tail (src/Frame.cc:862-914) fed by the Hamming kNN + Lowe ratio of :1078-1085 ----
+// For every left keypoint i with keep[i]: iR = idx[2i], distance = (float)dist[2i]; disparity gate [0, mbf/mb),
+// depth = mbf/disparity (0.01 when disparity <= 0), then the 1.5·median distance cut.  uRight/depth are N_left
+// arrays (−1 = no stereo).  NOTE: the reference feeds this tail from LightGlue (score 1−distance); the build pairs
+// it with the Hamming kNN instead and both oracle and CUDA restate exactly this composition.
+int orc_stereo_tail(const float *uL, const float *uR, int nL, int nR, const int32_t *idx, const int32_t *dist,
+                    const uint8_t *keep, float mbf, float mb, float *uRight, float *depth) {
+    for (int i = 0; i < nL; ++i) { uRight[i] = -1.f; depth[i] = -1.f; }
+    const float minD = 0, maxD = mbf / mb;
+    std::vector<std::pair<float, int>> v;
+    for (int i = 0; i < nL; ++i) {
+        if (!keep[i]) continue;
+        const int iR = idx[2 * i];
+        if (iR < 0 || iR >= nR) continue;
+        float disparity = uL[i] - uR[iR];
+        if (disparity >= minD && disparity < maxD) {
+            if (disparity <= 0) disparity = 0.01f;
+            depth[i] = mbf / disparity;
+            uRight[i] = uR[iR];
+            v.push_back(std::make_pair((float)dist[2 * i], i));
+        }
+    }
+    if (v.empty()) return 0;
+    std::sort(v.begin(), v.end());
+    const float median = v[v.size() / 2].first;
+    const float thDist = 1.5f * median;
+    int kept = (int)v.size();
+    for (int i = (int)v.size() - 1; i >= 0; --i) {
+        if (v[i].first < thDist) break;
+        uRight[v[i].second] = -1;
+        depth[v[i].second] = -1;
+        --kept;
+    }
+    return kept;
+}
+
 }  // extern "C"

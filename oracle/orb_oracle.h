@@ -82,6 +82,13 @@ int orc_search_init(const uint8_t *d1, const float *ang1, const int32_t *oct1, i
                     const uint8_t *d2, const float *ang2, int n2, const int32_t *cand,
                     const int32_t *cand_off, float nnratio, int check_ori, int32_t *matches12);
 
+/* Frame grid: AssignFeaturesToGrid + GetFeaturesInArea (src/Frame.cc:387-418, :659-738); returns total candidates */
+int orc_features_in_area(const float *xy, const int32_t *octave, int n, float minX, float minY, float maxX, float maxY,
+                         const float *queries, int nq, int minLevel, int maxLevel, int32_t *cand_off, int32_t *cand, int cap);
+/* stereo association tail (src/Frame.cc:862-914) over kNN+ratio matches; returns number of stereo points kept */
+int orc_stereo_tail(const float *uL, const float *uR, int nL, int nR, const int32_t *idx, const int32_t *dist,
+                    const uint8_t *keep, float mbf, float mb, float *uRight, float *depth);
+
 #ifdef __cplusplus
 }
 #endif

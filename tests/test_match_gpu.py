@@ -160,3 +160,52 @@ def test_search_for_initialization_vs_oracle(orbx_mod, oracle_mod, n1, n2, dense
     rn, rm12 = oracle_mod.search_init(d1, a1, o1, d2, a2, cand, off, ratio, ori)
     assert n == rn and np.array_equal(m12, rm12)
     assert rn > 0 and (rm12 >= 0).sum() == rn
+
+
+@pytest.mark.parametrize("n,nq,r,levels", [(1000, 400, 15.0, (-1, -1)), (5000, 2000, 100.0, (0, 0)), (300, 50, 3.0, (1, 4)), (0, 10, 20.0, (-1, -1)),
+                                           (2000, 1000, 0.5, (-1, 2))])
+def test_features_in_area_grid_vs_oracle(orbx_mod, oracle_mod, n, nq, r, levels):
+    """Frame::AssignFeaturesToGrid + GetFeaturesInArea (64×48 grid): same candidate lists, same order."""
+    rng = np.random.default_rng(n + nq)
+    W, H = 640.0, 480.0
+    xy = np.stack([rng.uniform(-5, W + 5, n), rng.uniform(-5, H + 5, n)], axis=1).astype(np.float32)
+    if n > 20:
+        xy[:10] = np.round(xy[:10])                                       # integer coordinates sit on .5 cell roundings
+        xy[10:20, 0] = np.arange(10) * (W / 64) + (W / 128)               # exactly half-cell positions
+    oc = rng.integers(0, 8, n).astype(np.int32)
+    q = np.stack([rng.uniform(-20, W + 20, nq), rng.uniform(-20, H + 20, nq), np.full(nq, r)], axis=1).astype(np.float32)
+    off, cand = orbx_mod.ORBmatcher().GetFeaturesInArea(xy, oc, (0.0, 0.0, W, H), q, *levels)
+    roff, rcand = oracle_mod.features_in_area(xy, oc, (0.0, 0.0, W, H), q, *levels)
+    assert np.array_equal(off, roff) and np.array_equal(cand, rcand)
+    if n >= 1000 and r >= 15:
+        assert len(cand) > 0
+
+
+def test_config2_stereo_pair_extract_match_tail(orbx_mod, oracle_mod):
+    """BASELINE config 2: KITTI-shaped 1241×376 stereo pair, nFeatures=2000 — left/right extraction, Hamming kNN
+    (k=2) + Lowe 0.7 (src/Frame.cc:1078-1085), stereo tail (src/Frame.cc:862-914; mbf/mb from KITTI00-02.yaml).
+    Every stage equals the oracle's."""
+    from dani_slam_b200 import synth
+    W, H, nf = 1241, 376, 2000
+    left = synth.throughput_frame(11, W, H)
+    right = synth.stereo_right(left, 11)
+    exL = orbx_mod.ORBextractor(nf, 1.2, 8, 20, 7, max_width=W, max_height=H)
+    exR = orbx_mod.ORBextractor(nf, 1.2, 8, 20, 7, max_width=W, max_height=H)
+    ml, kl, dl = exL(left)
+    mr, kr, dr = exR(right)
+    ref = oracle_mod.Extractor(nf, 1.2, 8, 20, 7)
+    _, rkl, rdl, _ = ref.extract(left, cap=nf + 200)
+    _, rkr, rdr, _ = ref.extract(right, cap=nf + 200)
+    assert kl.tobytes() == rkl.tobytes() and kr.tobytes() == rkr.tobytes() and np.array_equal(dl, rdl) and np.array_equal(dr, rdr)
+    m = orbx_mod.ORBmatcher(0.7, True)
+    idx, dist = m.knnMatch(dl, dr)
+    ridx, rdist = oracle_mod.knn2(rdl, rdr, nthreads=8)
+    assert np.array_equal(idx, ridx) and np.array_equal(dist, rdist)
+    keep = m.ratio_test(dist, 0.7)
+    assert np.array_equal(keep, oracle_mod.ratio_test(rdist, 0.7))
+    fx, b = 718.856, 0.53716                                              # Examples/Stereo/KITTI00-02.yaml: Camera1.fx, Stereo.b
+    mbf, mb = fx * b, b
+    n, ur, dp = m.StereoTail(kl["x"], kr["x"], idx, dist, keep, mbf, mb)
+    rn, rur, rdp = oracle_mod.stereo_tail(rkl["x"], rkr["x"], ridx, rdist, keep, mbf, mb)
+    assert n == rn and np.array_equal(ur, rur) and np.array_equal(dp, rdp)
+    assert n > 100                                                         # the shifted right image really yields stereo points
