@@ -33,6 +33,18 @@ __device__ __forceinline__ int ham256(const uint4 &a0, const uint4 &a1, const ui
            __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
 }
 
+// 256-bit Hamming distance with a carry-save adder front end: three full adders (2 LOP3 each) fold seven of the
+// eight XOR words into two "ones" words and three "twos" words, so a pair costs 5 POPC instead of 8 — the POPC
+// pipe (16 lanes/clk/SM) is the binding unit of the brute-force kernel, LOP3 runs on the wider ALU pipe.
+__device__ __forceinline__ int ham256_csa(const uint4 &a0, const uint4 &a1, const uint4 &b0, const uint4 &b1) {
+    const uint32_t x0 = a0.x ^ b0.x, x1 = a0.y ^ b0.y, x2 = a0.z ^ b0.z, x3 = a0.w ^ b0.w;
+    const uint32_t x4 = a1.x ^ b1.x, x5 = a1.y ^ b1.y, x6 = a1.z ^ b1.z, x7 = a1.w ^ b1.w;
+    const uint32_t s1 = x0 ^ x1 ^ x2, c1 = (x0 & x1) | (x2 & (x0 ^ x1));
+    const uint32_t s2 = x3 ^ x4 ^ x5, c2 = (x3 & x4) | (x5 & (x3 ^ x4));
+    const uint32_t s3 = s1 ^ s2 ^ x6, c3 = (s1 & s2) | (x6 & (s1 ^ s2));
+    return __popc(s3) + __popc(x7) + 2 * (__popc(c1) + __popc(c2) + __popc(c3));
+}
+
 // grid: (nChunks, nQueryTiles).  Thread t of query tile y owns queries y*THREADS*R + r*THREADS + t.
 template <int R>
 __global__ void __launch_bounds__(KNN_THREADS) k_knn2_partial(const uint4 *__restrict__ q, int nq,
@@ -63,7 +75,7 @@ __global__ void __launch_bounds__(KNN_THREADS) k_knn2_partial(const uint4 *__res
             const uint4 d0 = tile[2 * j], d1 = tile[2 * j + 1];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const uint32_t key = ((uint32_t)ham256(qa[r], qb[r], d0, d1) << KNN_IDX_BITS) + jkey;
+                const uint32_t key = ((uint32_t)ham256_csa(qa[r], qb[r], d0, d1) << KNN_IDX_BITS) + jkey;
                 const uint32_t hi = max(key, k0[r]);
                 k0[r] = min(key, k0[r]);
                 k1[r] = min(k1[r], hi);
