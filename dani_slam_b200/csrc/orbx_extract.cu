@@ -446,16 +446,15 @@ __host__ __device__ inline QtSmem qt_smem_layout(int nodeCap, int maxCellsLevel)
     return s;
 }
 
-// quadrant of a point inside a node (DivideNode :480-536): children n1..n4 = 0..3
+// quadrant of a point inside a node (DivideNode :480-536): children n1..n4 = 0..3.
+// halfX = ceil(static_cast<float>(UR.x-UL.x)/2) of a non-negative int < 2^24 is exactly (w+1)>>1.
 __device__ __forceinline__ int qt_quadrant(short4 bx, float x, float y) {
-    const int hx = (int)ceilf(__fdiv_rn((float)(bx.y - bx.x), 2.f));
-    const int hy = (int)ceilf(__fdiv_rn((float)(bx.w - bx.z), 2.f));
+    const int hx = (bx.y - bx.x + 1) >> 1, hy = (bx.w - bx.z + 1) >> 1;
     const float xm = (float)(bx.x + hx), ym = (float)(bx.z + hy);
     return (x < xm ? 0 : 1) + (y < ym ? 0 : 2);
 }
 __device__ __forceinline__ short4 qt_child_box(short4 bx, int q) {  // box = {x0, x1, y0, y1}
-    const int hx = (int)ceilf(__fdiv_rn((float)(bx.y - bx.x), 2.f));
-    const int hy = (int)ceilf(__fdiv_rn((float)(bx.w - bx.z), 2.f));
+    const int hx = (bx.y - bx.x + 1) >> 1, hy = (bx.w - bx.z + 1) >> 1;
     const short xm = (short)(bx.x + hx), ym = (short)(bx.z + hy);
     short4 c;
     c.x = (q & 1) ? xm : bx.x;
@@ -494,10 +493,11 @@ __device__ __forceinline__ void qt_for_points(const uint32_t *ptNode, const floa
 // (prefix over cells in processing order + rank inside the cell — the position it would have in the
 // reference's vToDistributeKeys):  ptXY[i] = drifted (x, y);  ptNode[i] = node position (bits 15:0) |
 // FAST score (bits 23:16) | quadrant scratch (bits 31:30), or ORBX_NODE_ERASED.
-__global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCapMax, int maxCellsLevel) {
+__global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCapMax, int maxCellsLevel, const int *onlyFlagged) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const OrbxGeom &g = *p.g;
     const int l = blockIdx.x, b = blockIdx.y;
+    if (onlyFlagged && !onlyFlagged[b * g.nlevels + l]) return;   // the histogram kernel already produced this (frame, level)
     const OrbxLevel &LV = g.lv[l];
     const int tid = threadIdx.x;
     const QtSmem S = qt_smem_layout(nodeCapMax, maxCellsLevel);
@@ -792,6 +792,395 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCap
         sel[i] = make_float4(__fadd_rn(xy.x, (float)ORBX_BORDER), __fadd_rn(xy.y, (float)ORBX_BORDER), (float)(best[i] >> 24), 0.f);
     }
     if (tid == 0) *selCntOut = size;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 (fast path): the same DistributeOctTree emulation, but the candidates are classified ONCE.
+// The quadtree geometry is data independent (a node's children are its box cut at the ceil-halves), so every
+// candidate's path down to depth QT_DMAX is computed in a single pass and counted in a per-(frame, level)
+// histogram of the depth-QT_DMAX cells; the coarser levels are sums of four.  The list emulation then reads a
+// child's point count from that table instead of re-classifying all points in every pass, and the points are
+// attached to their final nodes by walking their own path through a table of final nodes.  If a node at depth
+// QT_DMAX would have to be split (rare: tightly clustered corners) the block raises a flag and the general
+// kernel k_quadtree handles that (frame, level).
+// ------------------------------------------------------------------------------------------------
+#define QT_DMAX 6
+#define QT_TREE 5461                      // Σ_{d=0..6} 4^d nodes per root
+#define QT_MAX_INI 12
+__host__ __device__ __forceinline__ int qt_off(int nIni, int d) { return nIni * (((1 << (2 * d)) - 1) / 3); }
+
+__global__ void __launch_bounds__(QT_THREADS) k_quadtree_hist(ExParams p, int nodeCapMax, int maxCellsLevel, int maxIni,
+                                                               unsigned *histAll, int *deepFlag, long long *dbg) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const OrbxGeom &g = *p.g;
+    const int l = blockIdx.x, b = blockIdx.y;
+    const OrbxLevel &LV = g.lv[l];
+    const int tid = threadIdx.x;
+    const QtSmem S = qt_smem_layout(nodeCapMax, maxCellsLevel);
+    orbx_sort::elem_t *sortbuf = reinterpret_cast<orbx_sort::elem_t *>(smem_raw + S.sortOff);
+    short4 *box[2] = {reinterpret_cast<short4 *>(smem_raw + S.boxOff[0]), reinterpret_cast<short4 *>(smem_raw + S.boxOff[1])};
+    int *cnt[2] = {reinterpret_cast<int *>(smem_raw + S.cntOff[0]), reinterpret_cast<int *>(smem_raw + S.cntOff[1])};
+    int *childCnt = reinterpret_cast<int *>(smem_raw + S.childCntOff);
+    int *childPos = reinterpret_cast<int *>(smem_raw + S.childPosOff);
+    int *keptPos = reinterpret_cast<int *>(smem_raw + S.keptPosOff);
+    int *pend = reinterpret_cast<int *>(smem_raw + S.pendOff);
+    int *pendIdx = reinterpret_cast<int *>(smem_raw + S.pendIdxOff);
+    unsigned *best = reinterpret_cast<unsigned *>(smem_raw + S.bestOff);
+    int *prefix = reinterpret_cast<int *>(smem_raw + S.prefixOff);
+    int *scratch = reinterpret_cast<int *>(smem_raw + S.scratchOff);
+    int *tmp4 = reinterpret_cast<int *>(smem_raw + S.tmp4Off);
+    // node identity (depth<<24 | index inside the depth) lives in the two halves of tmp4's sibling: reuse `pend`-sized
+    // arrays would alias, so ids get their own storage behind the legacy layout, followed by the final-node table
+    unsigned *nid[2] = {reinterpret_cast<unsigned *>(smem_raw + S.total), reinterpret_cast<unsigned *>(smem_raw + S.total + 4 * nodeCapMax)};
+    unsigned short *finalPos = reinterpret_cast<unsigned short *>(smem_raw + S.total + 8 * nodeCapMax);
+    __shared__ int sh_size, sh_C, sh_deep;
+
+    const int nCells = LV.nCells;
+    const int N = LV.quota;
+    const int nIni = LV.nIni;
+    const int *cellCnt = p.cellCnt + (long long)b * g.nCellsTotal + LV.cellBase;
+    const OrbxCell *cells = p.cells + LV.cellBase;
+    const uint32_t *slots = p.slots + (long long)b * g.slotsTotal;
+    float2 *ptXY = p.ptXY + (long long)b * g.slotsTotal + LV.slotBase;
+    uint32_t *ptNode = p.ptNode + (long long)b * g.slotsTotal + LV.slotBase;
+    float4 *sel = p.sel + (long long)b * g.selTotal + LV.selBase;
+    int *selCntOut = p.selCnt + b * g.nlevels + l;
+    unsigned *hist = histAll + ((long long)b * g.nlevels + l) * (long long)maxIni * QT_TREE;
+    int *deepOut = deepFlag + b * g.nlevels + l;
+
+    int dbgN = 0;
+#define QT_MARK() do { if (dbg && tid == 0 && l == 0 && b == 0 && dbgN < 30) dbg[dbgN++] = clock64(); } while (0)
+    QT_MARK();
+    if (tid == 0) sh_deep = 0;
+    for (int c = tid; c < nCells; c += QT_THREADS) prefix[c] = cellCnt[c];
+    __syncthreads();
+    const int nPts = block_exclusive_scan(prefix, nCells, scratch);
+    if (tid == 0) prefix[nCells] = nPts;
+    if (nPts == 0 || nIni < 1) {
+        if (tid == 0) { *selCntOut = 0; *deepOut = 0; }
+        return;
+    }
+    if (nIni > QT_MAX_INI) {  // very wide images: the general kernel handles them
+        if (tid == 0) *deepOut = 1;
+        return;
+    }
+    QT_MARK();
+    const int treeN = nIni * QT_TREE;
+    for (int i = tid; i < treeN; i += QT_THREADS) { hist[i] = 0; finalPos[i] = 0; }
+    __syncthreads();
+    QT_MARK();
+
+    // ---- one pass over the candidates: DANI round trips (:871-907), root bin (:584), path to depth QT_DMAX
+    const float sc = LV.sf, inv = __fdiv_rn(1.f, sc);
+    const float hX = LV.hX;
+    const int nRects = g.nRects;
+    const int offLeaf = qt_off(nIni, QT_DMAX);
+    const int rootH = LV.maxBY - ORBX_BORDER;
+    // per-cell facts in shared memory (slot base relative to the level, cell column/row): the only long-latency
+    // access left in the loop is the packed candidate itself, and four of those are in flight per thread
+    int2 *cellInfo = reinterpret_cast<int2 *>(childCnt);   // 16·nodeCap bytes; free until the first pass
+    const bool cellsInSmem = (size_t)nCells * sizeof(int2) <= (size_t)16 * nodeCapMax;
+    if (cellsInSmem)
+        for (int c = tid; c < nCells; c += QT_THREADS) {
+            const OrbxCell cell = cells[c];
+            cellInfo[c] = make_int2((int)(cell.slot - LV.slotBase), (int)cell.cx | ((int)cell.cy << 16));
+        }
+    __syncthreads();
+    const uint32_t *lslots = slots + LV.slotBase;
+    for (int i0 = tid; i0 < nPts; i0 += 4 * QT_THREADS) {
+        int cidx[4];
+        int2 info[4];
+        uint32_t ent[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * QT_THREADS;
+            int lo = 0, hi = nCells;  // last cell with prefix[c] <= i
+            if (i < nPts)
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (prefix[mid] <= i) lo = mid; else hi = mid;
+                }
+            cidx[u] = lo;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (cellsInSmem) info[u] = cellInfo[cidx[u]];
+            else { const OrbxCell cell = cells[cidx[u]]; info[u] = make_int2((int)(cell.slot - LV.slotBase), (int)cell.cx | ((int)cell.cy << 16)); }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * QT_THREADS;
+            ent[u] = i < nPts ? lslots[info[u].x + (i - prefix[cidx[u]])] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * QT_THREADS;
+            if (i >= nPts) continue;
+            const uint32_t e = ent[u];
+            const int trips = nCells - cidx[u];   // processing-order index of an OK cell == its index inside the level
+            float x = __fadd_rn((float)(e & 0xff), (float)((info[u].y & 0xffff) * LV.wCell));
+            float y = __fadd_rn((float)((e >> 8) & 0xff), (float)((info[u].y >> 16) * LV.hCell));
+            bool erased = false;
+            for (int t = 0; t < trips; ++t) {
+                const float xs = __fmul_rn(__fadd_rn(x, (float)ORBX_BORDER), sc);
+                const float ys = __fmul_rn(__fadd_rn(y, (float)ORBX_BORDER), sc);
+                if (nRects > 0) {
+                    const int px = __float2int_rn(xs), py = __float2int_rn(ys);
+                    for (int r = 0; r < nRects; ++r) {
+                        const int rx = g.rects[4 * r], ry = g.rects[4 * r + 1];
+                        if (rx <= px && px < rx + g.rects[4 * r + 2] && ry <= py && py < ry + g.rects[4 * r + 3]) {
+                            erased = true;
+                            break;
+                        }
+                    }
+                    if (erased) break;
+                }
+                const float xn = __fsub_rn(__fmul_rn(xs, inv), (float)ORBX_BORDER);
+                const float yn = __fsub_rn(__fmul_rn(ys, inv), (float)ORBX_BORDER);
+                const bool fixed = (xn == x) && (yn == y);
+                x = xn;
+                y = yn;
+                if (fixed) break;
+            }
+            ptXY[i] = make_float2(x, y);
+            if (erased) {
+                ptNode[i] = ORBX_NODE_ERASED;
+                continue;
+            }
+            int bin = (int)__fdiv_rn(x, hX);
+            bin = min(max(bin, 0), nIni - 1);
+            short4 bx;
+            bx.x = (short)(int)__fmul_rn(hX, (float)bin);
+            bx.y = (short)(int)__fmul_rn(hX, (float)(bin + 1));
+            bx.z = 0;
+            bx.w = (short)rootH;
+            unsigned code = (unsigned)bin;
+#pragma unroll
+            for (int d = 0; d < QT_DMAX; ++d) {
+                const int q = qt_quadrant(bx, x, y);
+                bx = qt_child_box(bx, q);
+                code = code * 4u + (unsigned)q;
+            }
+            ptNode[i] = code | ((e >> 16) << 16);
+            atomicAdd(&hist[offLeaf + code], 1u);
+        }
+    }
+    __syncthreads();
+    QT_MARK();
+    // coarser levels = sums of four children (reads bypass L1: the counts were produced by atomics)
+    for (int d = QT_DMAX - 1; d >= 0; --d) {
+        const int n = nIni << (2 * d), o = qt_off(nIni, d), oc = qt_off(nIni, d + 1);
+        for (int i = tid; i < n; i += QT_THREADS)
+            hist[o + i] = __ldcg(&hist[oc + 4 * i]) + __ldcg(&hist[oc + 4 * i + 1]) + __ldcg(&hist[oc + 4 * i + 2]) + __ldcg(&hist[oc + 4 * i + 3]);
+        __syncthreads();
+    }
+    QT_MARK();
+    // initial list: non-empty roots in order (:565-601)
+    if (tid == 0) {
+        int m = 0;
+        for (int i = 0; i < nIni; ++i) {
+            const int c = (int)__ldcg(&hist[i]);
+            if (c > 0) {
+                short4 bx;
+                bx.x = (short)(int)__fmul_rn(hX, (float)i);
+                bx.y = (short)(int)__fmul_rn(hX, (float)(i + 1));
+                bx.z = 0;
+                bx.w = (short)rootH;
+                box[0][m] = bx;
+                cnt[0][m] = c;
+                nid[0][m] = (unsigned)i;   // depth 0
+                ++m;
+            }
+        }
+        sh_size = m;
+    }
+    __syncthreads();
+    int size = sh_size;
+
+    int cur = 0;
+    bool done = (size == 0);
+    bool phase2 = false;
+    int nPend = 0;
+    while (!done) {
+        const int prevSize = size;
+        const int nxt = cur ^ 1;
+        short4 *bxC = box[cur], *bxN = box[nxt];
+        int *cnC = cnt[cur], *cnN = cnt[nxt];
+        unsigned *idC = nid[cur], *idN = nid[nxt];
+        if (!phase2) {
+            // ---- full pass: split every node holding more than one point (:616-683); child counts from the table
+            for (int i = tid; i < 4 * size; i += QT_THREADS) {
+                const int pn = i >> 2;
+                int c = 0;
+                if (cnC[pn] > 1) {
+                    const unsigned id = idC[pn], d = id >> 24, ix = id & 0xffffffu;
+                    if (d >= QT_DMAX) sh_deep = 1;
+                    else c = (int)__ldcg(&hist[qt_off(nIni, d + 1) + 4 * ix + (i & 3)]);
+                }
+                childCnt[i] = c;
+                childPos[i] = c > 0 ? 1 : 0;
+            }
+            for (int i = tid; i < size; i += QT_THREADS) keptPos[i] = cnC[i] <= 1 ? 1 : 0;
+            __syncthreads();
+            if (sh_deep) break;
+            const int C = block_exclusive_scan(childPos, 4 * size, scratch);
+            const int nKept = block_exclusive_scan(keptPos, size, scratch);
+            for (int i = tid; i < 4 * size; i += QT_THREADS) {
+                const int n = childCnt[i];
+                if (n > 0) {
+                    const int pos = C - 1 - childPos[i];
+                    const unsigned id = idC[i >> 2];
+                    bxN[pos] = qt_child_box(bxC[i >> 2], i & 3);
+                    cnN[pos] = n;
+                    idN[pos] = (((id >> 24) + 1u) << 24) | ((id & 0xffffffu) * 4u + (unsigned)(i & 3));
+                    childPos[i] = pos;
+                } else {
+                    childPos[i] = -1;
+                }
+            }
+            for (int i = tid; i < size; i += QT_THREADS) {
+                if (cnC[i] <= 1) {
+                    const int pos = C + keptPos[i];
+                    bxN[pos] = bxC[i];
+                    cnN[pos] = cnC[i];
+                    idN[pos] = idC[i];
+                }
+            }
+            // expandable children (more than one point) in creation order: scan over (list position, child)
+            for (int i = tid; i < 4 * size; i += QT_THREADS) tmp4[i] = childCnt[i] > 1 ? 1 : 0;
+            __syncthreads();
+            nPend = block_exclusive_scan(tmp4, 4 * size, scratch);
+            for (int i = tid; i < 4 * size; i += QT_THREADS)
+                if (childCnt[i] > 1) pend[tmp4[i]] = childPos[i];
+            __syncthreads();
+            size = C + nKept;
+            cur = nxt;
+            if (size >= N || size == prevSize) done = true;
+            else if (size + 3 * nPend > N) phase2 = true;
+        } else {
+            // ---- "largest first" pass (:685-751): sort pending by (size, UL.x) exactly like std::sort
+            for (int i = tid; i < size; i += QT_THREADS) pendIdx[i] = -1;
+            __syncthreads();
+            for (int i = tid; i < nPend; i += QT_THREADS) {
+                const int pos = pend[i];
+                pendIdx[pos] = i;
+                const unsigned long long key = ((unsigned long long)(unsigned)cnC[pos] << 16) | (unsigned short)bxC[pos].x;
+                sortbuf[i] = (key << orbx_sort::kPayloadBits) | (unsigned long long)i;
+                const unsigned id = idC[pos], d = id >> 24, ix = id & 0xffffffu;
+                if (d >= QT_DMAX) {
+                    sh_deep = 1;
+                } else {
+                    const int o = qt_off(nIni, d + 1) + 4 * ix;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) childCnt[4 * i + q] = (int)__ldcg(&hist[o + q]);
+                }
+            }
+            __syncthreads();
+            if (sh_deep) break;
+            // walk the sorted array from the back until the list reaches N nodes (:701-747)
+            if (tid == 0) {
+                orbx_sort::sort(sortbuf, nPend);
+                int sz = size, c = 0;
+                for (int j = nPend - 1; j >= 0; --j) {
+                    const int pi = (int)(sortbuf[j] & ((1ull << orbx_sort::kPayloadBits) - 1));
+                    for (int q = 0; q < 4; ++q) {
+                        if (childCnt[4 * pi + q] > 0) { childPos[4 * pi + q] = c++; ++sz; }
+                        else childPos[4 * pi + q] = -1;
+                    }
+                    --sz;
+                    best[pi] = 1;  // processed marker, indexed by pending index
+                    if (sz >= N) {
+                        for (int jj = j - 1; jj >= 0; --jj) best[(int)(sortbuf[jj] & ((1ull << orbx_sort::kPayloadBits) - 1))] = 0;
+                        break;
+                    }
+                }
+                sh_C = c;
+                sh_size = sz;
+            }
+            __syncthreads();
+            const int C = sh_C;
+            for (int i = tid; i < size; i += QT_THREADS) {
+                const int pi = pendIdx[i];
+                keptPos[i] = (pi >= 0 && best[pi] == 1) ? 0 : 1;
+            }
+            __syncthreads();
+            block_exclusive_scan(keptPos, size, scratch);
+            for (int i = tid; i < size; i += QT_THREADS) {
+                const int pi = pendIdx[i];
+                if (!(pi >= 0 && best[pi] == 1)) {
+                    const int pos = C + keptPos[i];
+                    bxN[pos] = bxC[i];
+                    cnN[pos] = cnC[i];
+                    idN[pos] = idC[i];
+                }
+            }
+            for (int i = tid; i < 4 * nPend; i += QT_THREADS) {
+                const int pi = i >> 2;
+                if (best[pi] == 1 && childCnt[i] > 0) {
+                    const int pos = C - 1 - childPos[i];
+                    const unsigned id = idC[pend[pi]];
+                    bxN[pos] = qt_child_box(bxC[pend[pi]], i & 3);
+                    cnN[pos] = childCnt[i];
+                    idN[pos] = (((id >> 24) + 1u) << 24) | ((id & 0xffffffu) * 4u + (unsigned)(i & 3));
+                    childPos[i] = pos;
+                } else {
+                    childPos[i] = -1;
+                }
+            }
+            __syncthreads();
+            // next pending list: expandable children in creation order = processing order × child order
+            if (tid == 0) {
+                int np = 0;
+                for (int j = nPend - 1; j >= 0; --j) {
+                    const int pi = (int)(sortbuf[j] & ((1ull << orbx_sort::kPayloadBits) - 1));
+                    if (best[pi] != 1) break;
+                    for (int q = 0; q < 4; ++q)
+                        if (childCnt[4 * pi + q] > 1) pendIdx[np++] = childPos[4 * pi + q];
+                }
+                for (int i = 0; i < np; ++i) pend[i] = pendIdx[i];
+                sh_C = np;
+            }
+            __syncthreads();
+            nPend = sh_C;
+            size = sh_size;
+            cur = nxt;
+            if (size >= N || size == prevSize) done = true;
+        }
+        __syncthreads();
+        QT_MARK();
+    }
+    if (sh_deep) {  // a node deeper than the table would have to be split: hand over to the general kernel
+        if (tid == 0) *deepOut = 1;
+        return;
+    }
+
+    // ---- attach the points to the final nodes and keep the best response per node (:757-776)
+    for (int i = tid; i < size; i += QT_THREADS) {
+        best[i] = 0;
+        const unsigned id = nid[cur][i];
+        finalPos[qt_off(nIni, id >> 24) + (id & 0xffffffu)] = (unsigned short)(i + 1);
+    }
+    __syncthreads();
+    qt_for_points<false>(ptNode, ptXY, nPts, [&](int i, uint32_t v, float2) {
+        const unsigned leaf = v & 0xffffu;
+#pragma unroll
+        for (int d = 0; d <= QT_DMAX; ++d) {
+            const unsigned pos = finalPos[qt_off(nIni, d) + (leaf >> (2 * (QT_DMAX - d)))];
+            if (pos) {
+                atomicMax(&best[pos - 1], (((v >> 16) & 0xffu) << 24) | (0xffffffu - (unsigned)i));
+                break;
+            }
+        }
+    });
+    __syncthreads();
+    for (int i = tid; i < size; i += QT_THREADS) {
+        const int order = (int)(0xffffffu - (best[i] & 0xffffffu));
+        const float2 xy = ptXY[order];
+        sel[i] = make_float4(__fadd_rn(xy.x, (float)ORBX_BORDER), __fadd_rn(xy.y, (float)ORBX_BORDER), (float)(best[i] >> 24), 0.f);
+    }
+    QT_MARK();
+    if (dbg && tid == 0 && l == 0 && b == 0) dbg[31] = dbgN;
+    if (tid == 0) { *selCntOut = size; *deepOut = 0; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1137,7 +1526,11 @@ struct orbx_extractor {
     int h_tabXOff[ORBX_MAX_LEVELS] = {0}, h_tabYOff[ORBX_MAX_LEVELS] = {0};
     std::vector<OrbxCell> h_cells;
     std::vector<BlurTile> h_tiles;
-    int maxSlotCap = 0, nodeCapMax = 0, maxCellsLevel = 0;
+    int maxSlotCap = 0, nodeCapMax = 0, maxCellsLevel = 0, maxIni = 1;
+    bool useHistQuadtree = true;
+    unsigned *d_hist = nullptr; size_t histCap = 0;
+    int *d_deep = nullptr;
+    long long *d_dbg = nullptr;
     int lastBatch = 0;
     bool lastIn0Internal = true;
 
@@ -1200,7 +1593,7 @@ int build_geometry(orbx_extractor *ex, int rows, int cols) {
     ex->h_tiles.clear();
     long long off = 0, slot = 0;
     int cellBase = 0, selBase = 0;
-    ex->maxSlotCap = 1; ex->nodeCapMax = 8; ex->maxCellsLevel = 1;
+    ex->maxSlotCap = 1; ex->nodeCapMax = 8; ex->maxCellsLevel = 1; ex->maxIni = 1;
     G.maxCw = 7; G.maxCh = 7;
     for (int l = 0; l < ex->nlevels; ++l) {
         OrbxLevel &V = G.lv[l];
@@ -1258,6 +1651,7 @@ int build_geometry(orbx_extractor *ex, int rows, int cols) {
         V.nIni = (int)roundf((float)rw / (float)rh);
         if (V.nIni < 1) { ex->err = "image too tall: quadtree would have no root node (reference faults)"; return ORBX_ERR_GEOMETRY; }
         V.hX = (float)rw / (float)V.nIni;
+        ex->maxIni = std::max(ex->maxIni, std::min(V.nIni, QT_MAX_INI));
         V.nodeCap = std::max(4 * V.nIni, V.quota + 4) + 4;
         if (V.nodeCap > 60000) { ex->err = "nfeatures too large (quadtree node index is 16-bit)"; return ORBX_ERR_ARG; }
         ex->nodeCapMax = std::max(ex->nodeCapMax, V.nodeCap);
@@ -1349,6 +1743,7 @@ int ensure_buffers(orbx_extractor *ex, int batch) {
         ex->slotsCap = slotsNeed;
     }
     if ((rc = ensure(ex, ex->d_cellCnt, ex->cellCntCap, B * (size_t)std::max(G.nCellsTotal, 1)))) return rc;
+    if ((rc = ensure(ex, ex->d_hist, ex->histCap, B * (size_t)G.nlevels * (size_t)ex->maxIni * QT_TREE))) return rc;
     size_t selNeed = B * (size_t)std::max(G.selTotal, 1);
     if (selNeed > ex->selCap || !ex->d_sel) {
         if (ex->d_sel) cudaFree(ex->d_sel);
@@ -1472,7 +1867,18 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
         if (L.total > 48 * 1024)
             CUDA_TRY(ex, cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
         dim3 grd(G.nlevels, batch);
-        k_quadtree<<<grd, QT_THREADS, L.total, s>>>(P, ex->nodeCapMax, ex->maxCellsLevel);
+        const size_t smemH = (size_t)L.total + 8 * (size_t)ex->nodeCapMax + 2 * (size_t)ex->maxIni * QT_TREE;
+        if (ex->useHistQuadtree && smemH <= 200 * 1024) {
+            if (smemH > 48 * 1024)
+                CUDA_TRY(ex, cudaFuncSetAttribute(k_quadtree_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemH));
+            k_quadtree_hist<<<grd, QT_THREADS, smemH, s>>>(P, ex->nodeCapMax, ex->maxCellsLevel, ex->maxIni,
+                                                          ex->d_hist + f * G.nlevels * (size_t)ex->maxIni * QT_TREE, ex->d_deep + f * G.nlevels,
+                                                          first == 0 ? ex->d_dbg : nullptr);
+            ++ex->launches;
+            k_quadtree<<<grd, QT_THREADS, L.total, s>>>(P, ex->nodeCapMax, ex->maxCellsLevel, ex->d_deep + f * G.nlevels);
+        } else {
+            k_quadtree<<<grd, QT_THREADS, L.total, s>>>(P, ex->nodeCapMax, ex->maxCellsLevel, nullptr);
+        }
         ++ex->launches;
     }
     if (prof) CUDA_TRY(ex, cudaEventRecord(ex->ev[3], s));
@@ -1606,6 +2012,9 @@ orbx_extractor *orbx_create(int nfeatures, float scale_factor, int nlevels, int 
     CREATE_TRY(cudaMemcpy(ex->d_pattern, h_pattern, 1024, cudaMemcpyHostToDevice));
     CREATE_TRY(cudaMalloc((void **)&ex->d_selCnt, (size_t)max_batch * ORBX_MAX_LEVELS * sizeof(int)));
     CREATE_TRY(cudaMalloc((void **)&ex->d_workCnt, (size_t)max_batch * sizeof(int)));
+    CREATE_TRY(cudaMalloc((void **)&ex->d_deep, (size_t)max_batch * ORBX_MAX_LEVELS * sizeof(int)));
+    ex->useHistQuadtree = getenv("ORBX_LEGACY_QUADTREE") == nullptr;
+    if (getenv("ORBX_DEBUG_TIMELINE")) { CREATE_TRY(cudaMalloc((void **)&ex->d_dbg, 32 * sizeof(long long))); CREATE_TRY(cudaMemset(ex->d_dbg, 0, 32 * sizeof(long long))); }
     CREATE_TRY(cudaMalloc((void **)&ex->d_nOut, (size_t)max_batch * sizeof(int)));
     CREATE_TRY(cudaMalloc((void **)&ex->d_mono, (size_t)max_batch * sizeof(int)));
     CREATE_TRY(cudaHostAlloc((void **)&ex->h_nOut, (size_t)max_batch * sizeof(int), cudaHostAllocDefault));
@@ -1626,7 +2035,7 @@ void orbx_destroy(orbx_extractor *ex) {
     if (ex->stream) cudaStreamSynchronize(ex->stream);
     void *ptrs[] = {ex->d_geom, ex->d_cells, ex->d_tiles, ex->d_tabX, ex->d_tabY, ex->d_tabXOff, ex->d_tabYOff,
                     ex->d_pattern, ex->d_pyr, ex->d_blur, ex->d_slots, ex->d_ptNode, ex->d_ptXY, ex->d_cellCnt,
-                    ex->d_sel, ex->d_work, ex->d_selCnt, ex->d_workCnt, ex->d_kps, ex->d_desc, ex->d_nOut, ex->d_mono};
+                    ex->d_sel, ex->d_work, ex->d_selCnt, ex->d_workCnt, ex->d_hist, ex->d_deep, ex->d_dbg, ex->d_kps, ex->d_desc, ex->d_nOut, ex->d_mono};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ex->h_nOut) cudaFreeHost(ex->h_nOut);
     if (ex->h_mono) cudaFreeHost(ex->h_mono);
@@ -1769,6 +2178,14 @@ int orbx_sync(orbx_extractor *ex) {
     return ORBX_OK;
 }
 void *orbx_stream(orbx_extractor *ex) { return ex ? (void *)ex->stream : nullptr; }
+
+// developer hook (ORBX_DEBUG_TIMELINE=1): clock64 stamps of the level-0 quadtree block of frame 0; out[31] = count
+int orbx_debug_timeline(orbx_extractor *ex, long long *out32) {
+    if (!ex || !out32 || !ex->d_dbg) return ORBX_ERR_ARG;
+    CUDA_TRY(ex, cudaStreamSynchronize(ex->stream));
+    CUDA_TRY(ex, cudaMemcpy(out32, ex->d_dbg, 32 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}
 
 int orbx_set_profiling(orbx_extractor *ex, int on) {
     if (!ex) return ORBX_ERR_ARG;

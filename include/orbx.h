@@ -180,6 +180,10 @@ int orbx_stereo_tail(orbx_matcher *m, const float *u_left, const float *u_right,
 /* ORBmatcher::DescriptorDistance for one pair on the host (inline popcount; no device involved). */
 int orbx_descriptor_distance(const uint8_t *a, const uint8_t *b);
 
+/* Developer hook (set ORBX_DEBUG_TIMELINE=1 before orbx_create): clock64 stamps taken by the level-0 quadtree
+ * block of frame 0 at its phase boundaries; out32[31] = number of stamps. */
+int orbx_debug_timeline(orbx_extractor *ex, long long *out32);
+
 /* Test hook: the device/host port of libstdc++ std::sort used by the quadtree (see stdsort_port.h),
  * run on the host; perm_out = resulting order of original indices. */
 void orbx_debug_sort_nodes(const int32_t *sizes, const int32_t *ulx, int n, int32_t *perm_out);
