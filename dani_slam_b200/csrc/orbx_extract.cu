@@ -441,6 +441,7 @@ __host__ __device__ inline QtSmem qt_smem_layout(int nodeCap, int maxCellsLevel)
     s.bestOff = o; o += 4 * nodeCap;
     s.prefixOff = o; o += 4 * (maxCellsLevel + 1);
     s.scratchOff = o; o += 4 * (QT_THREADS + 2);
+    o = (o + 15) & ~15;                            // tmp4 doubles as a 64-bit buffer for the rank sort
     s.tmp4Off = o; o += 16 * nodeCap;
     s.total = (o + 15) & ~15;
     return s;
@@ -1077,9 +1078,31 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree_hist(ExParams p, int no
             }
             __syncthreads();
             if (sh_deep) break;
+            // std::sort = serial introsort partitioning (thread 0) + its final insertion sort, which is a stable sort
+            // of the partitioned order and is done here as a parallel rank sort
+            QT_MARK();
+            if (tid == 0) orbx_sort::introsort_loop_only(sortbuf, nPend);
+            __syncthreads();
+            QT_MARK();
+            {
+                orbx_sort::elem_t *sorted = reinterpret_cast<orbx_sort::elem_t *>(tmp4);
+                for (int i = tid; i < nPend; i += QT_THREADS) {
+                    const orbx_sort::elem_t e = sortbuf[i];
+                    const unsigned long long k = e >> orbx_sort::kPayloadBits;
+                    int rank = 0;
+                    for (int j = 0; j < nPend; ++j) {
+                        const unsigned long long kj = sortbuf[j] >> orbx_sort::kPayloadBits;
+                        rank += (kj < k) || (kj == k && j < i);
+                    }
+                    sorted[rank] = e;
+                }
+                __syncthreads();
+                for (int i = tid; i < nPend; i += QT_THREADS) sortbuf[i] = sorted[i];
+                __syncthreads();
+            }
+            QT_MARK();
             // walk the sorted array from the back until the list reaches N nodes (:701-747)
             if (tid == 0) {
-                orbx_sort::sort(sortbuf, nPend);
                 int sz = size, c = 0;
                 for (int j = nPend - 1; j >= 0; --j) {
                     const int pi = (int)(sortbuf[j] & ((1ull << orbx_sort::kPayloadBits) - 1));
@@ -1098,6 +1121,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree_hist(ExParams p, int no
                 sh_size = sz;
             }
             __syncthreads();
+            QT_MARK();
             const int C = sh_C;
             for (int i = tid; i < size; i += QT_THREADS) {
                 const int pi = pendIdx[i];
@@ -1128,6 +1152,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree_hist(ExParams p, int no
                 }
             }
             __syncthreads();
+            QT_MARK();
             // next pending list: expandable children in creation order = processing order × child order
             if (tid == 0) {
                 int np = 0;
@@ -1492,8 +1517,21 @@ __global__ void k_dbg_atan2(const float *y, const float *x, int n, float *o) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) o[i] = fast_atan2_deg(y[i], x[i]);
 }
-__global__ void k_dbg_sort(orbx_sort::elem_t *a, int n) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) orbx_sort::sort(a, n);
+// same two-phase evaluation as k_quadtree_hist: serial partitioning + stable rank sort (single thread here)
+__global__ void k_dbg_sort(orbx_sort::elem_t *a, orbx_sort::elem_t *tmp, int n) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        orbx_sort::introsort_loop_only(a, n);
+        for (int i = 0; i < n; ++i) {
+            const unsigned long long k = a[i] >> orbx_sort::kPayloadBits;
+            int rank = 0;
+            for (int j = 0; j < n; ++j) {
+                const unsigned long long kj = a[j] >> orbx_sort::kPayloadBits;
+                rank += (kj < k) || (kj == k && j < i);
+            }
+            tmp[rank] = a[i];
+        }
+        for (int i = 0; i < n; ++i) a[i] = tmp[i];
+    }
 }
 
 thread_local std::string tl_error;
@@ -2324,7 +2362,9 @@ void orbx_debug_sort_nodes(const int32_t *sizes, const int32_t *ulx, int n, int3
     std::vector<orbx_sort::elem_t> a(n);
     for (int i = 0; i < n; ++i)
         a[i] = ((((unsigned long long)(unsigned)sizes[i] << 16) | (unsigned short)ulx[i]) << orbx_sort::kPayloadBits) | (unsigned)i;
-    orbx_sort::sort(a.data(), n);
+    // evaluated the way the quadtree kernel does it: partitioning phase, then a stable sort by key
+    orbx_sort::introsort_loop_only(a.data(), n);
+    std::stable_sort(a.begin(), a.end(), [](orbx_sort::elem_t x, orbx_sort::elem_t y) { return orbx_sort::less(x, y); });
     for (int i = 0; i < n; ++i) perm_out[i] = (int32_t)(a[i] & ((1ull << orbx_sort::kPayloadBits) - 1));
 }
 
@@ -2334,9 +2374,9 @@ int orbx_debug_sort_nodes_device(int device, const int32_t *sizes, const int32_t
     for (int i = 0; i < n; ++i)
         a[i] = ((((unsigned long long)(unsigned)sizes[i] << 16) | (unsigned short)ulx[i]) << orbx_sort::kPayloadBits) | (unsigned)i;
     orbx_sort::elem_t *d = nullptr;
-    if (cudaMalloc((void **)&d, a.size() * 8) != cudaSuccess) return ORBX_ERR_CUDA;
+    if (cudaMalloc((void **)&d, a.size() * 16) != cudaSuccess) return ORBX_ERR_CUDA;
     cudaMemcpy(d, a.data(), a.size() * 8, cudaMemcpyHostToDevice);
-    k_dbg_sort<<<1, 32>>>(d, n);
+    k_dbg_sort<<<1, 32>>>(d, d + a.size(), n);
     cudaError_t e = cudaMemcpy(a.data(), d, a.size() * 8, cudaMemcpyDeviceToHost);
     cudaFree(d);
     if (e != cudaSuccess) return ORBX_ERR_CUDA;

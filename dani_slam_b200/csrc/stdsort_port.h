@@ -132,6 +132,35 @@ ORBX_SORT_HD int unguarded_partition(elem_t *a, int first, int last, int pivot) 
     }
 }
 
+// __introsort_loop only: the partitioning phase (explicit stack replaces the recursion on the right partition).
+// What std::sort does afterwards, __final_insertion_sort, is a STABLE sort of whatever order this phase leaves
+// (insertion with strict '<' never reorders equal keys), so callers may finish with any stable sort by key —
+// the quadtree kernel does that part in parallel.
+ORBX_SORT_HD void introsort_loop_only(elem_t *a, int n) {
+    if (n <= kThreshold) return;
+    int lg = 0;
+    for (int t = n; t > 1; t >>= 1) ++lg;  // std::__lg(n)
+    int stk_first[64], stk_last[64], stk_depth[64];
+    int sp = 0;
+    stk_first[0] = 0; stk_last[0] = n; stk_depth[0] = 2 * lg; sp = 1;
+    while (sp > 0) {
+        --sp;
+        int first = stk_first[sp], last = stk_last[sp], depth = stk_depth[sp];
+        while (last - first > kThreshold) {
+            if (depth == 0) {
+                heap_sort(a, first, last);
+                break;
+            }
+            --depth;
+            const int mid = first + (last - first) / 2;
+            move_median_to_first(a, first, first + 1, mid, last - 1);
+            const int cut = unguarded_partition(a, first + 1, last, first);
+            stk_first[sp] = cut; stk_last[sp] = last; stk_depth[sp] = depth; ++sp;
+            last = cut;
+        }
+    }
+}
+
 // std::sort(a, a+n) under less(); explicit stack replaces the recursion on the right partition
 ORBX_SORT_HD void sort(elem_t *a, int n) {
     if (n <= 0) return;
