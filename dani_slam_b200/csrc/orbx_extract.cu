@@ -1541,6 +1541,7 @@ thread_local std::string tl_error;
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+#define ORBX_MAX_CHUNKS 8
 struct orbx_extractor {
     int device = 0;
     int nfeatures = 0, nlevels = 0, iniTh = 0, minTh = 0;
@@ -1551,7 +1552,7 @@ struct orbx_extractor {
     int umax[ORBX_HALF_PATCH + 1];
     cudaStream_t stream = nullptr, sH2D = nullptr, sD2H = nullptr, sSideA = nullptr, sSideB = nullptr;
     cudaEvent_t evFork = nullptr, evJoin[2] = {nullptr, nullptr};
-    cudaEvent_t evIn[4] = {nullptr, nullptr, nullptr, nullptr}, evOut[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t evIn[ORBX_MAX_CHUNKS] = {}, evOut[ORBX_MAX_CHUNKS] = {};
     std::string err;
     long long launches = 0;
 
@@ -2039,7 +2040,7 @@ orbx_extractor *orbx_create(int nfeatures, float scale_factor, int nlevels, int 
     CREATE_TRY(cudaEventCreateWithFlags(&ex->evFork, cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreateWithFlags(&ex->evJoin[0], cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreateWithFlags(&ex->evJoin[1], cudaEventDisableTiming));
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < ORBX_MAX_CHUNKS; ++i) {
         CREATE_TRY(cudaEventCreateWithFlags(&ex->evIn[i], cudaEventDisableTiming));
         CREATE_TRY(cudaEventCreateWithFlags(&ex->evOut[i], cudaEventDisableTiming));
     }
@@ -2078,7 +2079,7 @@ void orbx_destroy(orbx_extractor *ex) {
     if (ex->h_nOut) cudaFreeHost(ex->h_nOut);
     if (ex->h_mono) cudaFreeHost(ex->h_mono);
     for (int i = 0; i < 7; ++i) if (ex->ev[i]) cudaEventDestroy(ex->ev[i]);
-    for (int i = 0; i < 4; ++i) { if (ex->evIn[i]) cudaEventDestroy(ex->evIn[i]); if (ex->evOut[i]) cudaEventDestroy(ex->evOut[i]); }
+    for (int i = 0; i < ORBX_MAX_CHUNKS; ++i) { if (ex->evIn[i]) cudaEventDestroy(ex->evIn[i]); if (ex->evOut[i]) cudaEventDestroy(ex->evOut[i]); }
     if (ex->evFork) cudaEventDestroy(ex->evFork);
     for (int i = 0; i < 2; ++i) if (ex->evJoin[i]) cudaEventDestroy(ex->evJoin[i]);
     if (ex->sSideA) { cudaStreamSynchronize(ex->sSideA); cudaStreamDestroy(ex->sSideA); }
@@ -2142,7 +2143,7 @@ int orbx_extract_batch(orbx_extractor *ex, const uint8_t *const *images, int bat
         // Software pipeline over chunks of the batch: H2D of chunk k+1 and D2H of chunk k-1 overlap the kernels
         // of chunk k (three streams, events between them).  PCIe moves 307 KB in and ~64 KB out per frame, about
         // half of the kernel time at 640x480, so the copies hide completely behind the compute stream.
-        const int nChunks = nb >= 64 ? 4 : 1;
+        const int nChunks = nb >= 256 ? ORBX_MAX_CHUNKS : (nb >= 64 ? 4 : 1);
         const int chunk = (nb + nChunks - 1) / nChunks;
         cudaStream_t sC = ex->stream, sIn = ex->sH2D, sOut = ex->sD2H;
         // earlier asynchronous work of this handle must be finished before its buffers are refilled
