@@ -330,8 +330,8 @@ def main():
     dom_gbs = dom_bytes / (per_call[dominant] / 1000.0) / 1e9 if per_call[dominant] > 0 else 0.0
     traffic = None
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = prof.get(dominant)
+        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))   # ncu dram bytes per frame
+        traffic = prof.get(dominant) * B if prof.get(dominant) is not None else None
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": dom_gbs, "peak": peak_gbs, "unit": "GB/s",
