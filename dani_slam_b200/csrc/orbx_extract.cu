@@ -286,8 +286,29 @@ __global__ void __launch_bounds__(WPB * 32) k_fast_cells(ExParams p, int maxSlot
     const int rp = L.roiPitch, sp = L.scorePitch;
     // stage the ROI: column x at byte x+1 so that every 4-pixel group is word aligned
     const uint8_t *src = img + (long long)cell.y0 * pitch + cell.x0;
-    for (int y = 0; y < ch; ++y)
-        for (int x = lane; x < cw; x += 32) roi[y * rp + x + 1] = src[(long long)y * pitch + x];
+    if (((((unsigned long long)img) | (unsigned)pitch) & 3ull) == 0) {
+        // aligned 32-bit loads: shared-memory word k of a row holds image columns x0-1+4k .. x0+2+4k, i.e. the two
+        // aligned global words around it funnel-shifted by the (cell-uniform) misalignment; (row, word) items are
+        // flattened over the lanes and four items are in flight per lane
+        const int mis = (cell.x0 - 1) & 3;
+        const uint32_t *gsrc = reinterpret_cast<const uint32_t *>(src - 1 - mis);
+        const int pitchW = pitch >> 2;
+        const int nW = (cw + 4) >> 2;
+        const int items = nW * ch;
+        const uint32_t rcpW = (65536u + nW - 1) / nW;   // (i*rcpW)>>16 == i/nW for i < 3449 (cells are ≤ 20 words × 76 rows)
+        uint32_t *roi32 = reinterpret_cast<uint32_t *>(roi);
+        const int rpW = rp >> 2;
+#pragma unroll 4
+        for (int i = lane; i < items; i += 32) {
+            const int y = (int)(((uint32_t)i * rcpW) >> 16), k = i - y * nW;
+            const uint32_t *q = gsrc + (long long)y * pitchW + k;
+            const uint32_t a = q[0], bq = q[1];
+            roi32[y * rpW + k] = __funnelshift_r(a, bq, 8 * mis);
+        }
+    } else {
+        for (int y = 0; y < ch; ++y)
+            for (int x = lane; x < cw; x += 32) roi[y * rp + x + 1] = src[(long long)y * pitch + x];
+    }
     // zero the score map (its 1-px frame of zeros = "outside the cell interior counts 0")
     {
         uint32_t *s32 = reinterpret_cast<uint32_t *>(score);
