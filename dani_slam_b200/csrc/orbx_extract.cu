@@ -65,6 +65,7 @@ struct ExParams {
     int *nOut;
     int *monoIdx;
     const int8_t *pattern;    // 1024 bytes
+    const float4 *patternF;   // 256 × (x0, y0, x1, y1)
 };
 
 __device__ __forceinline__ const uint8_t *level_ptr(const ExParams &p, const OrbxGeom &g, int l, int b,
@@ -1474,21 +1475,24 @@ __global__ void __launch_bounds__(WPB * 32) k_orient_desc(ExParams p) {
     if (wk.out < 0) return;
     int pitch;
     const uint8_t *img = level_ptr(p, g, wk.level, b, pitch);
-    // moments over the 31-row circular patch: lane = column u+15, lane 31 idle
+    // moments over the 31-row circular patch: lane = column u+15, lane 31 idle.  The row half-widths are the
+    // reference's umax table for HALF_PATCH_SIZE=15 (checked against the ctor maths in orbx_create).
+    constexpr int UMAX[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
     const int u = lane - ORBX_HALF_PATCH;
     int m10 = 0, m01 = 0;
     if (lane < 31) {
-        const uint8_t *c0 = img + (long long)wk.cy * pitch + wk.cx + u;
+        const uint8_t *pr = img + (long long)(wk.cy - ORBX_HALF_PATCH) * pitch + wk.cx + u;
         const int au = u < 0 ? -u : u;
+        int colSum = 0;   // Σ val over the rows this column belongs to, and Σ v·val
 #pragma unroll
-        for (int v = -ORBX_HALF_PATCH; v <= ORBX_HALF_PATCH; ++v) {
-            const int av = v < 0 ? -v : v;
-            if (au <= g.umax[av]) {
-                const int val = c0[(long long)v * pitch];
-                m10 += u * val;
+        for (int v = -ORBX_HALF_PATCH; v <= ORBX_HALF_PATCH; ++v, pr += pitch) {
+            if (au <= UMAX[v < 0 ? -v : v]) {
+                const int val = *pr;
+                colSum += val;
                 m01 += v * val;
             }
         }
+        m10 = u * colSum;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -1496,27 +1500,27 @@ __global__ void __launch_bounds__(WPB * 32) k_orient_desc(ExParams p) {
         m01 += __shfl_xor_sync(0xffffffffu, m01, o);
     }
     const float angle = fast_atan2_deg((float)m01, (float)m10);
-    // rBRIEF on the blurred level: lane computes descriptor byte `lane`
+    // rBRIEF on the blurred level: lane computes descriptor byte `lane` (tests 8·lane … 8·lane+7)
     const float factorPI = (float)(3.141592653589793238462643383279502884 / 180.f);
     const float rad = __fmul_rn(angle, factorPI);
     const float ca = orbx_libm::cosf_glibc(rad), sa = orbx_libm::sinf_glibc(rad);
     const OrbxLevel &LV = g.lv[wk.level];
     const uint8_t *bl = p.blur + (long long)b * g.frameBytes + LV.off + (long long)wk.cy * LV.pitch + wk.cx;
     const int bp = LV.pitch;
-    const int4 *pat4 = reinterpret_cast<const int4 *>(p.pattern) + lane * 2;
+    const int4 *pat4 = reinterpret_cast<const int4 *>(p.pattern) + lane * 2;   // 8 tests × (x0, y0, x1, y1) int8
     const int4 q0 = pat4[0], q1 = pat4[1];
     const int words[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
     int byte = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int wv = words[j];
-        const float x0 = (float)(signed char)(wv & 0xff), y0 = (float)(signed char)((wv >> 8) & 0xff);
-        const float x1 = (float)(signed char)((wv >> 16) & 0xff), y1 = (float)(signed char)((wv >> 24) & 0xff);
-        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, sa), __fmul_rn(y0, ca)));
-        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, ca), __fmul_rn(y0, sa)));
-        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, sa), __fmul_rn(y1, ca)));
-        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, ca), __fmul_rn(y1, sa)));
-        const int v0 = bl[(long long)r0 * bp + c0], v1 = bl[(long long)r1 * bp + c1];
+        const float tx0 = (float)(signed char)(wv & 0xff), ty0 = (float)(signed char)((wv >> 8) & 0xff);
+        const float tx1 = (float)(signed char)((wv >> 16) & 0xff), ty1 = (float)(signed char)((wv >> 24) & 0xff);
+        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(tx0, sa), __fmul_rn(ty0, ca)));
+        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(tx0, ca), __fmul_rn(ty0, sa)));
+        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(tx1, sa), __fmul_rn(ty1, ca)));
+        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(tx1, ca), __fmul_rn(ty1, sa)));
+        const int v0 = bl[r0 * bp + c0], v1 = bl[r1 * bp + c1];
         byte |= (v0 < v1) << j;
     }
     // gather 4 bytes per lane group and store 8 words
@@ -1601,6 +1605,7 @@ struct orbx_extractor {
     int2 *d_tabX = nullptr, *d_tabY = nullptr; size_t tabXCap = 0, tabYCap = 0;
     int *d_tabXOff = nullptr, *d_tabYOff = nullptr;
     int8_t *d_pattern = nullptr;
+    float4 *d_patternF = nullptr;
     uint8_t *d_pyr = nullptr, *d_blur = nullptr; size_t pyrCap = 0;
     uint32_t *d_slots = nullptr; uint32_t *d_ptNode = nullptr; float2 *d_ptXY = nullptr; size_t slotsCap = 0;
     int *d_cellCnt = nullptr; size_t cellCntCap = 0;
@@ -1880,6 +1885,7 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
     P.work = ex->d_work + f * G.selTotal; P.workCnt = ex->d_workCnt + f;
     P.kps = d_kps; P.desc = d_desc; P.cap = cap; P.nOut = d_nOut; P.monoIdx = d_mono;
     P.pattern = ex->d_pattern;
+    P.patternF = ex->d_patternF;
     cudaStream_t s = onStream ? onStream : ex->stream;
     const bool prof = ex->profiling && !onStream;
     if (prof) {
@@ -2070,6 +2076,15 @@ orbx_extractor *orbx_create(int nfeatures, float scale_factor, int nlevels, int 
     CREATE_TRY(cudaMalloc((void **)&ex->d_tabYOff, ORBX_MAX_LEVELS * sizeof(int)));
     CREATE_TRY(cudaMalloc((void **)&ex->d_pattern, 1024));
     CREATE_TRY(cudaMemcpy(ex->d_pattern, h_pattern, 1024, cudaMemcpyHostToDevice));
+    {
+        std::vector<float> pf(1024);
+        for (int i = 0; i < 1024; ++i) pf[i] = (float)h_pattern[i];
+        CREATE_TRY(cudaMalloc((void **)&ex->d_patternF, 1024 * sizeof(float)));
+        CREATE_TRY(cudaMemcpy(ex->d_patternF, pf.data(), 1024 * sizeof(float), cudaMemcpyHostToDevice));
+        static const int kUmax15[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+        for (int i = 0; i <= ORBX_HALF_PATCH; ++i)
+            if (ex->umax[i] != kUmax15[i]) return fail("orbx_create: umax table differs from the compiled-in HALF_PATCH_SIZE=15 table");
+    }
     CREATE_TRY(cudaMalloc((void **)&ex->d_selCnt, (size_t)max_batch * ORBX_MAX_LEVELS * sizeof(int)));
     CREATE_TRY(cudaMalloc((void **)&ex->d_workCnt, (size_t)max_batch * sizeof(int)));
     CREATE_TRY(cudaMalloc((void **)&ex->d_deep, (size_t)max_batch * ORBX_MAX_LEVELS * sizeof(int)));
@@ -2094,7 +2109,7 @@ void orbx_destroy(orbx_extractor *ex) {
     cudaSetDevice(ex->device);
     if (ex->stream) cudaStreamSynchronize(ex->stream);
     void *ptrs[] = {ex->d_geom, ex->d_cells, ex->d_tiles, ex->d_tabX, ex->d_tabY, ex->d_tabXOff, ex->d_tabYOff,
-                    ex->d_pattern, ex->d_pyr, ex->d_blur, ex->d_slots, ex->d_ptNode, ex->d_ptXY, ex->d_cellCnt,
+                    ex->d_pattern, ex->d_patternF, ex->d_pyr, ex->d_blur, ex->d_slots, ex->d_ptNode, ex->d_ptXY, ex->d_cellCnt,
                     ex->d_sel, ex->d_work, ex->d_selCnt, ex->d_workCnt, ex->d_hist, ex->d_deep, ex->d_dbg, ex->d_kps, ex->d_desc, ex->d_nOut, ex->d_mono};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ex->h_nOut) cudaFreeHost(ex->h_nOut);
