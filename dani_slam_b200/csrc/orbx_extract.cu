@@ -2254,6 +2254,19 @@ int orbx_sync(orbx_extractor *ex) {
 }
 void *orbx_stream(orbx_extractor *ex) { return ex ? (void *)ex->stream : nullptr; }
 
+// test hook: how many (frame, level) pairs of the last batch call fell back from the histogram quadtree kernel to
+// the general one (deep trees); -1 when the histogram kernel is not in use
+int orbx_debug_deep_count(orbx_extractor *ex) {
+    if (!ex || !ex->d_deep) return ORBX_ERR_ARG;
+    if (!ex->useHistQuadtree) return -1;
+    if (cudaSetDevice(ex->device) != cudaSuccess || cudaStreamSynchronize(ex->stream) != cudaSuccess) return ORBX_ERR_CUDA;
+    std::vector<int> f((size_t)std::max(ex->lastBatch, 1) * ex->nlevels);
+    if (cudaMemcpy(f.data(), ex->d_deep, f.size() * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return ORBX_ERR_CUDA;
+    int n = 0;
+    for (int v : f) n += v != 0;
+    return n;
+}
+
 // developer hook (ORBX_DEBUG_TIMELINE=1): clock64 stamps of the level-0 quadtree block of frame 0; out[31] = count
 int orbx_debug_timeline(orbx_extractor *ex, long long *out32) {
     if (!ex || !out32 || !ex->d_dbg) return ORBX_ERR_ARG;

@@ -180,6 +180,10 @@ int orbx_stereo_tail(orbx_matcher *m, const float *u_left, const float *u_right,
 /* ORBmatcher::DescriptorDistance for one pair on the host (inline popcount; no device involved). */
 int orbx_descriptor_distance(const uint8_t *a, const uint8_t *b);
 
+/* Test hook: number of (frame, level) pairs of the last batch call that the histogram quadtree kernel handed to
+ * the general quadtree kernel (trees deeper than its table); -1 if the histogram kernel is disabled. */
+int orbx_debug_deep_count(orbx_extractor *ex);
+
 /* Developer hook (set ORBX_DEBUG_TIMELINE=1 before orbx_create): clock64 stamps taken by the level-0 quadtree
  * block of frame 0 at its phase boundaries; out32[31] = number of stamps. */
 int orbx_debug_timeline(orbx_extractor *ex, long long *out32);

@@ -175,3 +175,50 @@ def test_full_size_4k_frame(orbx_mod, oracle_mod):
     assert (k["x"] >= 19).all() and (k["x"] <= 3840 - 19).all()
     rc, rk, rd, rmono = oracle_mod.Extractor(8000, 1.2, 8, 20, 7).extract(img, cap=8200)
     assert rc == 0 and mono == rmono and k.tobytes() == rk.tobytes() and np.array_equal(d, rd)
+
+
+def test_clustered_corners_deep_quadtree_fallback(orbx_mod, oracle_mod):
+    """Corners confined to tiny regions force the quadtree far deeper than the histogram table of the fast
+    kernel (QT_DMAX levels), so the flagged (frame, level) pairs are redone by the general kernel; also a frame
+    with a single textured blob, and one with two corners only."""
+    from dani_slam_b200 import synth
+    H, W = 480, 640
+    rng = np.random.default_rng(77)
+    frames = []
+    a = np.full((H, W), 120, np.uint8)
+    a[200:236, 300:340] = rng.integers(0, 256, (36, 40), dtype=np.uint8)          # one 40×36 noise blob
+    frames.append(a)
+    b = np.full((H, W), 90, np.uint8)
+    for (y, x) in [(60, 70), (61, 400), (300, 90), (420, 600), (240, 320)]:
+        b[y:y + 14, x:x + 14] = rng.integers(0, 256, (14, 14), dtype=np.uint8)    # five tiny blobs
+    frames.append(b)
+    c = np.full((H, W), 50, np.uint8)
+    c[100:110, 100:110] = 250                                                      # a lone bright square
+    c[300:305, 500:520] = 0
+    frames.append(c)
+    d = synth.throughput_frame(5)
+    d[:, :] = np.where(np.add.outer(np.arange(H), np.arange(W)) % 97 < 90, 128, d)  # thin diagonal stripes of texture
+    frames.append(np.ascontiguousarray(d))
+    ex = orbx_mod.ORBextractor(1000, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=4)
+    ref = oracle_mod.Extractor(1000, 1.2, 8, 20, 7)
+    n, mono, kps, desc = ex.extract_batch(np.stack(frames))
+    for i, f in enumerate(frames):
+        rc, rk, rd, rmono = ref.extract(f)
+        assert n[i] == len(rk) and mono[i] == rmono, i
+        assert kps[i, : n[i]].tobytes() == rk.tobytes() and np.array_equal(desc[i, : n[i]], rd), i
+    assert n[0] >= 10 and n[2] >= 4
+    ex.L.orbx_debug_deep_count.argtypes = [__import__('ctypes').c_void_p]
+    assert ex.L.orbx_debug_deep_count(ex.h) > 0                                   # the fallback kernel really ran
+    ex.extract_batch(np.stack([synth.throughput_frame(1), synth.throughput_frame(2)]))
+    assert ex.L.orbx_debug_deep_count(ex.h) == 0                                  # dense frames stay on the fast path
+
+
+def test_legacy_quadtree_kernel_gives_the_same_result(orbx_mod, oracle_mod, monkeypatch):
+    """ORBX_LEGACY_QUADTREE=1 routes every (frame, level) through the general quadtree kernel."""
+    from dani_slam_b200 import synth
+    monkeypatch.setenv("ORBX_LEGACY_QUADTREE", "1")
+    img = synth.parity_frame(61)
+    ex = orbx_mod.ORBextractor(1000, 1.2, 8, 20, 7, max_width=640, max_height=480)
+    mono, k, d = ex(img, None, (0, 1000))
+    rc, rk, rd, rmono = oracle_mod.Extractor(1000, 1.2, 8, 20, 7).extract(img, lap=(0, 1000))
+    assert mono == rmono and k.tobytes() == rk.tobytes() and np.array_equal(d, rd)
