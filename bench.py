@@ -30,20 +30,42 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
-W_IMG, H_IMG, NFEAT = 640, 480, 1000
 LEVELS, SCALE, INI_TH, MIN_TH = 8, 1.2, 20, 7
-# level sizes of the 640×480 pyramid and the stage-streaming byte model
-LEVEL_PX = [640 * 480, 533 * 400, 444 * 333, 370 * 278, 309 * 231, 257 * 193, 214 * 161, 179 * 134]
-SUM_P = sum(LEVEL_PX)
-B_ALG_FRAME = (sum(LEVEL_PX[:7]) + sum(LEVEL_PX[1:])) + SUM_P + 2 * SUM_P + NFEAT * (749 + 512) + NFEAT * (32 + 28)
-STAGE_BYTES = {  # algorithmic bytes per frame of each stage (read once + write once)
-    "pyramid": sum(LEVEL_PX[:7]) + sum(LEVEL_PX[1:]),
-    "fast_cells": SUM_P,
-    "quadtree": 0,
-    "assemble": NFEAT * 28,
-    "blur": 2 * SUM_P,
-    "orient_desc": NFEAT * (749 + 512) + NFEAT * 32,
+# BASELINE.json configs (frame shape, nFeatures, default frames per GPU per step).  `tum1` is the configuration the
+# headline metric is quoted on (640×480, 1000 keypoints, TUM1.yaml); the others are extra measurements.
+WORKLOADS = {
+    "tum1": (640, 480, 1000, 512),
+    "euroc": (752, 480, 1200, 512),
+    "kitti": (1241, 376, 2000, 256),
+    "4k": (3840, 2160, 8000, 16),
 }
+W_IMG, H_IMG, NFEAT = 640, 480, 1000
+LEVEL_PX, SUM_P, B_ALG_FRAME, STAGE_BYTES = [], 0, 0, {}
+
+
+def set_workload(name: str):
+    """level sizes (fp32 cvRound of size·1/1.2^l) and the stage-streaming byte model."""
+    global W_IMG, H_IMG, NFEAT, LEVEL_PX, SUM_P, B_ALG_FRAME, STAGE_BYTES
+    W_IMG, H_IMG, NFEAT, batch = WORKLOADS[name]
+    sf, LEVEL_PX = np.float32(1.0), []
+    for l in range(LEVELS):
+        inv = np.float32(1.0) / sf
+        LEVEL_PX.append(int(np.rint(np.float32(W_IMG) * inv)) * int(np.rint(np.float32(H_IMG) * inv)))
+        sf = np.float32(float(sf) * float(np.float32(SCALE)))
+    SUM_P = sum(LEVEL_PX)
+    B_ALG_FRAME = (sum(LEVEL_PX[:-1]) + sum(LEVEL_PX[1:])) + SUM_P + 2 * SUM_P + NFEAT * (749 + 512) + NFEAT * (32 + 28)
+    STAGE_BYTES = {  # algorithmic bytes per frame of each stage (read once + write once)
+        "pyramid": sum(LEVEL_PX[:-1]) + sum(LEVEL_PX[1:]),
+        "fast_cells": SUM_P,
+        "quadtree": 0,
+        "assemble": NFEAT * 28,
+        "blur": 2 * SUM_P,
+        "orient_desc": NFEAT * (749 + 512) + NFEAT * 32,
+    }
+    return batch
+
+
+set_workload("tum1")
 
 
 def make_frames(count: int, first_index: int) -> np.ndarray:
@@ -168,7 +190,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "orb_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * tot_t / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"tum1_{W_IMG}x{H_IMG}_nf{NFEAT}_8lv_fast20_7", "frames_per_step": tot_frames / max(args.steps, 1)},
+        "config": {"workload": f"{args.workload}_{W_IMG}x{H_IMG}_nf{NFEAT}_8lv_fast20_7", "frames_per_step": tot_frames / max(args.steps, 1)},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind,
                          "sample": f"{tot_frames} frames of the bench workload over {args.steps} steps of {per_step}s, one frame per thread"},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -185,11 +207,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=512, help="frames per GPU per step")
+    ap.add_argument("--workload", default="tum1", choices=sorted(WORKLOADS), help="tum1 = the headline configuration")
+    ap.add_argument("--batch", type=int, default=0, help="frames per GPU per step (default: per workload)")
     ap.add_argument("--no-match", action="store_true", help="skip the Hamming kNN section")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--match-db", type=int, default=10_000_000)
     args = ap.parse_args()
+    default_batch = set_workload(args.workload)
+    if args.batch <= 0:
+        args.batch = default_batch
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -331,7 +357,7 @@ def main():
     traffic = None
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))   # ncu dram bytes per frame
-        traffic = prof.get(dominant) * B if prof.get(dominant) is not None else None
+        traffic = prof.get(dominant) * B if (prof.get(dominant) is not None and args.workload == "tum1") else None
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": dom_gbs, "peak": peak_gbs, "unit": "GB/s",
@@ -394,9 +420,9 @@ def main():
             "metric": "orb_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": f"tum1_{W_IMG}x{H_IMG}_nf{NFEAT}_8lv_fast20_7", "frames_per_gpu_per_step": B,
+            "config": {"workload": f"{args.workload}_{W_IMG}x{H_IMG}_nf{NFEAT}_8lv_fast20_7", "frames_per_gpu_per_step": B,
                        "global_batch": world * B, "parallelism": f"frame-batch x{world} (no collective)",
-                       "l2": f"inputs {B * H_IMG * W_IMG / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
+                       "l2": f"inputs {B * H_IMG * W_IMG / 1e6:.0f} MB + {B * SUM_P * 2 / 1e6:.0f} MB of pyramid planes touched per step > 126 MB L2 (no flush needed)",
                        "keypoints_per_frame": n_avg},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -1533,6 +1533,14 @@ __global__ void __launch_bounds__(WPB * 32) k_orient_desc(ExParams p) {
     if (lane == 0) p.kps[(long long)b * p.cap + wk.out].angle = angle;
 }
 
+// packed host layout (rows of `cols` bytes, frames back to back) → pitched level-0 planes of the internal pyramid
+__global__ void k_repitch(const uint8_t *__restrict__ packed, int rows, int cols, uint8_t *__restrict__ dst, long long frameBytes, int pitch) {
+    const int b = blockIdx.z, y = blockIdx.y;
+    const uint8_t *s = packed + ((long long)b * rows + y) * cols;
+    uint8_t *d = dst + (long long)b * frameBytes + (long long)y * pitch;
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < cols; x += gridDim.x * blockDim.x) d[x] = s[x];
+}
+
 // debug kernels ----------------------------------------------------------------------------------
 __global__ void k_dbg_sincos(const float *a, int n, float *s, float *c) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1595,6 +1603,7 @@ struct orbx_extractor {
     unsigned *d_hist = nullptr; size_t histCap = 0;
     int *d_deep = nullptr;
     long long *d_dbg = nullptr;
+    uint8_t *d_stage = nullptr; size_t stageCap = 0;   // packed H2D staging when the level-0 pitch is padded
     int lastBatch = 0;
     bool lastIn0Internal = true;
 
@@ -2110,7 +2119,7 @@ void orbx_destroy(orbx_extractor *ex) {
     if (ex->stream) cudaStreamSynchronize(ex->stream);
     void *ptrs[] = {ex->d_geom, ex->d_cells, ex->d_tiles, ex->d_tabX, ex->d_tabY, ex->d_tabXOff, ex->d_tabYOff,
                     ex->d_pattern, ex->d_patternF, ex->d_pyr, ex->d_blur, ex->d_slots, ex->d_ptNode, ex->d_ptXY, ex->d_cellCnt,
-                    ex->d_sel, ex->d_work, ex->d_selCnt, ex->d_workCnt, ex->d_hist, ex->d_deep, ex->d_dbg, ex->d_kps, ex->d_desc, ex->d_nOut, ex->d_mono};
+                    ex->d_sel, ex->d_work, ex->d_selCnt, ex->d_workCnt, ex->d_hist, ex->d_deep, ex->d_dbg, ex->d_stage, ex->d_kps, ex->d_desc, ex->d_nOut, ex->d_mono};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ex->h_nOut) cudaFreeHost(ex->h_nOut);
     if (ex->h_mono) cudaFreeHost(ex->h_mono);
@@ -2196,6 +2205,20 @@ int orbx_extract_batch(orbx_extractor *ex, const uint8_t *const *images, int bat
                 // frames are back to back and rows are dense: one strided copy for the whole chunk
                 CUDA_TRY(ex, cudaMemcpy2DAsync(lvl0, (size_t)G.frameBytes, images[b0 + c0], (size_t)rows * cols, (size_t)rows * cols, cn,
                                                cudaMemcpyHostToDevice, sIn));
+            } else if (contiguous && step == (size_t)cols) {
+                // dense host frames but a padded device pitch: one flat copy into a staging area, then a re-pitch kernel
+                const size_t bytes = (size_t)cn * rows * cols;
+                if ((size_t)nb * rows * cols > ex->stageCap || !ex->d_stage) {
+                    CUDA_TRY(ex, cudaStreamSynchronize(sIn));
+                    if (ex->d_stage) cudaFree(ex->d_stage);
+                    ex->d_stage = nullptr; ex->stageCap = 0;
+                    CUDA_TRY(ex, cudaMalloc((void **)&ex->d_stage, (size_t)nb * rows * cols));
+                    ex->stageCap = (size_t)nb * rows * cols;
+                }
+                uint8_t *stg = ex->d_stage + (size_t)c0 * rows * cols;
+                CUDA_TRY(ex, cudaMemcpyAsync(stg, images[b0 + c0], bytes, cudaMemcpyHostToDevice, sIn));
+                k_repitch<<<dim3((cols + 1023) / 1024, rows, cn), 256, 0, sIn>>>(stg, rows, cols, lvl0, G.frameBytes, G.lv[0].pitch);
+                ++ex->launches;
             } else {
                 for (int b = 0; b < cn; ++b)
                     CUDA_TRY(ex, cudaMemcpy2DAsync(lvl0 + (size_t)b * G.frameBytes, G.lv[0].pitch, images[b0 + c0 + b], step, cols, rows,
