@@ -37,7 +37,7 @@ WORKLOADS = {
     "tum1": (640, 480, 1000, 512),
     "euroc": (752, 480, 1200, 512),
     "kitti": (1241, 376, 2000, 256),
-    "4k": (3840, 2160, 8000, 16),
+    "4k": (3840, 2160, 8000, 64),
 }
 W_IMG, H_IMG, NFEAT = 640, 480, 1000
 LEVEL_PX, SUM_P, B_ALG_FRAME, STAGE_BYTES = [], 0, 0, {}

@@ -407,12 +407,14 @@ __global__ void __launch_bounds__(WPB * 32) k_fast_cells(ExParams p, int maxSlot
 // ------------------------------------------------------------------------------------------------
 // K3: DANI filter + quadtree (DistributeOctTree), one block per (frame, level)
 // ------------------------------------------------------------------------------------------------
-#define QT_THREADS 128
+#define QT_THREADS 128   // default block size; large-nFeatures handles use QT_THREADS_BIG
+#define QT_THREADS_BIG 512
 
 // block-wide exclusive scan of a[0..n) in place; returns the total.  All threads must call.
-__device__ int block_exclusive_scan(int *a, int n, int *scratch /* >= QT_THREADS+1 ints */) {
+template <int NT>
+__device__ int block_exclusive_scan(int *a, int n, int *scratch /* >= NT+1 ints */) {
     const int tid = threadIdx.x;
-    const int per = (n + QT_THREADS - 1) / QT_THREADS;
+    const int per = (n + NT - 1) / NT;
     const int lo = min(tid * per, n), hi = min(lo + per, n);
     int sum = 0;
     for (int i = lo; i < hi; ++i) sum += a[i];
@@ -420,10 +422,10 @@ __device__ int block_exclusive_scan(int *a, int n, int *scratch /* >= QT_THREADS
     __syncthreads();
     if (tid < 32) {
         // 256 partial sums: each lane of warp 0 scans 8 of them
-        int loc[QT_THREADS / 32];
+        int loc[NT / 32];
         int s = 0;
 #pragma unroll
-        for (int k = 0; k < QT_THREADS / 32; ++k) { loc[k] = s; s += scratch[tid * (QT_THREADS / 32) + k]; }
+        for (int k = 0; k < NT / 32; ++k) { loc[k] = s; s += scratch[tid * (NT / 32) + k]; }
         int incl = s;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -432,13 +434,13 @@ __device__ int block_exclusive_scan(int *a, int n, int *scratch /* >= QT_THREADS
         }
         const int excl = incl - s;
 #pragma unroll
-        for (int k = 0; k < QT_THREADS / 32; ++k) scratch[tid * (QT_THREADS / 32) + k] = excl + loc[k];
-        if (tid == 31) scratch[QT_THREADS] = incl;
+        for (int k = 0; k < NT / 32; ++k) scratch[tid * (NT / 32) + k] = excl + loc[k];
+        if (tid == 31) scratch[NT] = incl;
     }
     __syncthreads();
     int run = scratch[tid];
     for (int i = lo; i < hi; ++i) { const int v = a[i]; a[i] = run; run += v; }
-    const int total = scratch[QT_THREADS];
+    const int total = scratch[NT];
     __syncthreads();
     return total;
 }
@@ -462,7 +464,7 @@ __host__ __device__ inline QtSmem qt_smem_layout(int nodeCap, int maxCellsLevel)
     s.pendIdxOff = o; o += 4 * nodeCap;
     s.bestOff = o; o += 4 * nodeCap;
     s.prefixOff = o; o += 4 * (maxCellsLevel + 1);
-    s.scratchOff = o; o += 4 * (QT_THREADS + 2);
+    s.scratchOff = o; o += 4 * (QT_THREADS_BIG + 2);
     o = (o + 15) & ~15;                            // tmp4 doubles as a 64-bit buffer for the rank sort
     s.tmp4Off = o; o += 16 * nodeCap;
     s.total = (o + 15) & ~15;
@@ -489,26 +491,26 @@ __device__ __forceinline__ short4 qt_child_box(short4 bx, int q) {  // box = {x0
 
 // Visit every live candidate of the level with 4 loads in flight per thread (the passes are bound by
 // L2 latency, not bandwidth): f(index, nodeWord, xy).
-template <bool NEED_XY, class F>
+template <bool NEED_XY, int NT, class F>
 __device__ __forceinline__ void qt_for_points(const uint32_t *ptNode, const float2 *ptXY, int nPts, F f) {
-    for (int i0 = threadIdx.x; i0 < nPts; i0 += 4 * QT_THREADS) {
+    for (int i0 = threadIdx.x; i0 < nPts; i0 += 4 * NT) {
         uint32_t v[4];
         float2 xy[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * QT_THREADS;
+            const int i = i0 + u * NT;
             v[u] = i < nPts ? ptNode[i] : ORBX_NODE_ERASED;
         }
         if (NEED_XY) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u * QT_THREADS;
+                const int i = i0 + u * NT;
                 xy[u] = i < nPts ? ptXY[i] : make_float2(0.f, 0.f);
             }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-            if (v[u] != ORBX_NODE_ERASED) f(i0 + u * QT_THREADS, v[u], xy[u]);
+            if (v[u] != ORBX_NODE_ERASED) f(i0 + u * NT, v[u], xy[u]);
     }
 }
 
@@ -516,7 +518,8 @@ __device__ __forceinline__ void qt_for_points(const uint32_t *ptNode, const floa
 // (prefix over cells in processing order + rank inside the cell — the position it would have in the
 // reference's vToDistributeKeys):  ptXY[i] = drifted (x, y);  ptNode[i] = node position (bits 15:0) |
 // FAST score (bits 23:16) | quadrant scratch (bits 31:30), or ORBX_NODE_ERASED.
-__global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCapMax, int maxCellsLevel, const int *onlyFlagged) {
+template <int NT>
+__global__ void __launch_bounds__(NT) k_quadtree(ExParams p, int nodeCapMax, int maxCellsLevel, const int *onlyFlagged) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const OrbxGeom &g = *p.g;
     const int l = blockIdx.x, b = blockIdx.y;
@@ -548,23 +551,23 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCap
     float4 *sel = p.sel + (long long)b * g.selTotal + LV.selBase;
     int *selCntOut = p.selCnt + b * g.nlevels + l;
 
-    for (int c = tid; c < nCells; c += QT_THREADS) prefix[c] = cellCnt[c];
+    for (int c = tid; c < nCells; c += NT) prefix[c] = cellCnt[c];
     __syncthreads();
-    const int nPts = block_exclusive_scan(prefix, nCells, scratch);
+    const int nPts = block_exclusive_scan<NT>(prefix, nCells, scratch);
     if (tid == 0) prefix[nCells] = nPts;
     if (nPts == 0 || LV.nIni < 1) {
         if (tid == 0) *selCntOut = 0;
         return;
     }
     const int nIni = LV.nIni;
-    for (int i = tid; i < nIni; i += QT_THREADS) childCnt[i] = 0;
+    for (int i = tid; i < nIni; i += NT) childCnt[i] = 0;
     __syncthreads();
 
     // ---- DANI dynamic-area deletion with its fp32 round trip (:871-907) + root binning
     const float sc = LV.sf, inv = __fdiv_rn(1.f, sc);
     const float hX = LV.hX;
     const int nRects = g.nRects;
-    for (int i = tid; i < nPts; i += QT_THREADS) {
+    for (int i = tid; i < nPts; i += NT) {
         int lo = 0, hi = nCells;  // last cell with prefix[c] <= i
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
@@ -629,7 +632,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCap
     __syncthreads();
     int size = sh_size;
     if (size != nIni) {  // some root was empty: renumber
-        qt_for_points<false>(ptNode, ptXY, nPts, [&](int i, uint32_t v, float2) {
+        qt_for_points<false, NT>(ptNode, ptXY, nPts, [&](int i, uint32_t v, float2) {
             ptNode[i] = (v & 0x00ff0000u) | (uint32_t)keptPos[v & 0xffffu];
         });
         __syncthreads();
@@ -646,9 +649,9 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCap
         int *cnC = cnt[cur], *cnN = cnt[nxt];
         if (!phase2) {
             // ---- full pass: split every node holding more than one point (:616-683)
-            for (int i = tid; i < 4 * size; i += QT_THREADS) childCnt[i] = 0;
+            for (int i = tid; i < 4 * size; i += NT) childCnt[i] = 0;
             __syncthreads();
-            qt_for_points<true>(ptNode, ptXY, nPts, [&](int i, uint32_t v, float2 xy) {
+            qt_for_points<true, NT>(ptNode, ptXY, nPts, [&](int i, uint32_t v, float2 xy) {
                 const uint32_t nd = v & 0xffffu;
                 if (cnC[nd] <= 1) return;
                 const int q = qt_quadrant(bxC[nd], xy.x, xy.y);
@@ -657,14 +660,14 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCap
             });
             __syncthreads();
             // creation order = list order × child order; children go to the list front (reversed)
-            for (int i = tid; i < 4 * size; i += QT_THREADS) {
+            for (int i = tid; i < 4 * size; i += NT) {
                 childPos[i] = childCnt[i] > 0 ? 1 : 0;
             }
-            for (int i = tid; i < size; i += QT_THREADS) keptPos[i] = cnC[i] <= 1 ? 1 : 0;
+            for (int i = tid; i < size; i += NT) keptPos[i] = cnC[i] <= 1 ? 1 : 0;
             __syncthreads();
-            const int C = block_exclusive_scan(childPos, 4 * size, scratch);
-            const int nKept = block_exclusive_scan(keptPos, size, scratch);
-            for (int i = tid; i < 4 * size; i += QT_THREADS) {
+            const int C = block_exclusive_scan<NT>(childPos, 4 * size, scratch);
+            const int nKept = block_exclusive_scan<NT>(keptPos, size, scratch);
+            for (int i = tid; i < 4 * size; i += NT) {
                 const int n = childCnt[i];
                 if (n > 0) {
                     const int pos = C - 1 - childPos[i];
@@ -675,7 +678,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCap
                     childPos[i] = -1;
                 }
             }
-            for (int i = tid; i < size; i += QT_THREADS) {
+            for (int i = tid; i < size; i += NT) {
                 if (cnC[i] <= 1) {
                     const int pos = C + keptPos[i];
                     bxN[pos] = bxC[i];
@@ -686,15 +689,15 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCap
                 }
             }
             __syncthreads();
-            qt_for_points<false>(ptNode, ptXY, nPts, [&](int i, uint32_t v, float2) {
+            qt_for_points<false, NT>(ptNode, ptXY, nPts, [&](int i, uint32_t v, float2) {
                 const uint32_t nd = v & 0xffffu, q = v >> 30;
                 ptNode[i] = (v & 0x00ff0000u) | (uint32_t)(cnC[nd] <= 1 ? keptPos[nd] : childPos[4 * nd + q]);
             });
             // expandable children (more than one point) in creation order: scan over (list position, child)
-            for (int i = tid; i < 4 * prevSize; i += QT_THREADS) tmp4[i] = childCnt[i] > 1 ? 1 : 0;
+            for (int i = tid; i < 4 * prevSize; i += NT) tmp4[i] = childCnt[i] > 1 ? 1 : 0;
             __syncthreads();
-            nPend = block_exclusive_scan(tmp4, 4 * prevSize, scratch);
-            for (int i = tid; i < 4 * prevSize; i += QT_THREADS)
+            nPend = block_exclusive_scan<NT>(tmp4, 4 * prevSize, scratch);
+            for (int i = tid; i < 4 * prevSize; i += NT)
                 if (childCnt[i] > 1) pend[tmp4[i]] = childPos[i];
             __syncthreads();
             size = C + nKept;
@@ -703,10 +706,10 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCap
             else if (size + 3 * nPend > N) phase2 = true;
         } else {
             // ---- "largest first" pass (:685-751): sort pending by (size, UL.x) exactly like std::sort
-            for (int i = tid; i < size; i += QT_THREADS) pendIdx[i] = -1;
-            for (int i = tid; i < 4 * nPend; i += QT_THREADS) childCnt[i] = 0;
+            for (int i = tid; i < size; i += NT) pendIdx[i] = -1;
+            for (int i = tid; i < 4 * nPend; i += NT) childCnt[i] = 0;
             __syncthreads();
-            for (int i = tid; i < nPend; i += QT_THREADS) {
+            for (int i = tid; i < nPend; i += NT) {
                 const int pos = pend[i];
                 pendIdx[pos] = i;
                 const unsigned long long key = ((unsigned long long)(unsigned)cnC[pos] << 16) | (unsigned short)bxC[pos].x;
@@ -714,7 +717,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCap
             }
             __syncthreads();
             if (tid == 0) orbx_sort::sort(sortbuf, nPend);   // overlaps with the classification below
-            qt_for_points<true>(ptNode, ptXY, nPts, [&](int i, uint32_t v, float2 xy) {
+            qt_for_points<true, NT>(ptNode, ptXY, nPts, [&](int i, uint32_t v, float2 xy) {
                 const uint32_t nd = v & 0xffffu;
                 const int pi = pendIdx[nd];
                 if (pi < 0) return;
@@ -745,13 +748,13 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCap
             __syncthreads();
             const int C = sh_C;
             // survivors of the old list keep their relative order behind the new children
-            for (int i = tid; i < size; i += QT_THREADS) {
+            for (int i = tid; i < size; i += NT) {
                 const int pi = pendIdx[i];
                 keptPos[i] = (pi >= 0 && best[pi] == 1) ? 0 : 1;
             }
             __syncthreads();
-            block_exclusive_scan(keptPos, size, scratch);
-            for (int i = tid; i < size; i += QT_THREADS) {
+            block_exclusive_scan<NT>(keptPos, size, scratch);
+            for (int i = tid; i < size; i += NT) {
                 const int pi = pendIdx[i];
                 if (pi >= 0 && best[pi] == 1) {
                     keptPos[i] = -1;
@@ -762,7 +765,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCap
                     keptPos[i] = pos;
                 }
             }
-            for (int i = tid; i < 4 * nPend; i += QT_THREADS) {
+            for (int i = tid; i < 4 * nPend; i += NT) {
                 const int pi = i >> 2;
                 if (best[pi] == 1 && childCnt[i] > 0) {
                     const int pos = C - 1 - childPos[i];
@@ -774,7 +777,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCap
                 }
             }
             __syncthreads();
-            qt_for_points<false>(ptNode, ptXY, nPts, [&](int i, uint32_t v, float2) {
+            qt_for_points<false, NT>(ptNode, ptXY, nPts, [&](int i, uint32_t v, float2) {
                 const uint32_t nd = v & 0xffffu, q = v >> 30;
                 const int pi = pendIdx[nd];
                 ptNode[i] = (v & 0x00ff0000u) | (uint32_t)((pi >= 0 && best[pi] == 1) ? childPos[4 * pi + q] : keptPos[nd]);
@@ -802,13 +805,13 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCap
     }
 
     // ---- best response per node, first maximum in insertion order wins (:757-776)
-    for (int i = tid; i < size; i += QT_THREADS) best[i] = 0;
+    for (int i = tid; i < size; i += NT) best[i] = 0;
     __syncthreads();
-    qt_for_points<false>(ptNode, ptXY, nPts, [&](int i, uint32_t v, float2) {
+    qt_for_points<false, NT>(ptNode, ptXY, nPts, [&](int i, uint32_t v, float2) {
         atomicMax(&best[v & 0xffffu], (((v >> 16) & 0xffu) << 24) | (0xffffffu - (unsigned)i));
     });
     __syncthreads();
-    for (int i = tid; i < size; i += QT_THREADS) {
+    for (int i = tid; i < size; i += NT) {
         const int order = (int)(0xffffffu - (best[i] & 0xffffffu));
         const float2 xy = ptXY[order];
         // :919-923 — add the border back; response = FAST score
@@ -832,7 +835,8 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(ExParams p, int nodeCap
 #define QT_MAX_INI 12
 __host__ __device__ __forceinline__ int qt_off(int nIni, int d) { return nIni * (((1 << (2 * d)) - 1) / 3); }
 
-__global__ void __launch_bounds__(QT_THREADS) k_quadtree_hist(ExParams p, int nodeCapMax, int maxCellsLevel, int maxIni,
+template <int NT>
+__global__ void __launch_bounds__(NT) k_quadtree_hist(ExParams p, int nodeCapMax, int maxCellsLevel, int maxIni,
                                                                unsigned *histAll, int *deepFlag, long long *dbg) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const OrbxGeom &g = *p.g;
@@ -875,9 +879,9 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree_hist(ExParams p, int no
 #define QT_MARK() do { if (dbg && tid == 0 && l == 0 && b == 0 && dbgN < 30) dbg[dbgN++] = clock64(); } while (0)
     QT_MARK();
     if (tid == 0) sh_deep = 0;
-    for (int c = tid; c < nCells; c += QT_THREADS) prefix[c] = cellCnt[c];
+    for (int c = tid; c < nCells; c += NT) prefix[c] = cellCnt[c];
     __syncthreads();
-    const int nPts = block_exclusive_scan(prefix, nCells, scratch);
+    const int nPts = block_exclusive_scan<NT>(prefix, nCells, scratch);
     if (tid == 0) prefix[nCells] = nPts;
     if (nPts == 0 || nIni < 1) {
         if (tid == 0) { *selCntOut = 0; *deepOut = 0; }
@@ -889,7 +893,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree_hist(ExParams p, int no
     }
     QT_MARK();
     const int treeN = nIni * QT_TREE;
-    for (int i = tid; i < treeN; i += QT_THREADS) { hist[i] = 0; finalPos[i] = 0; }
+    for (int i = tid; i < treeN; i += NT) { hist[i] = 0; finalPos[i] = 0; }
     __syncthreads();
     QT_MARK();
 
@@ -904,19 +908,19 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree_hist(ExParams p, int no
     int2 *cellInfo = reinterpret_cast<int2 *>(childCnt);   // 16·nodeCap bytes; free until the first pass
     const bool cellsInSmem = (size_t)nCells * sizeof(int2) <= (size_t)16 * nodeCapMax;
     if (cellsInSmem)
-        for (int c = tid; c < nCells; c += QT_THREADS) {
+        for (int c = tid; c < nCells; c += NT) {
             const OrbxCell cell = cells[c];
             cellInfo[c] = make_int2((int)(cell.slot - LV.slotBase), (int)cell.cx | ((int)cell.cy << 16));
         }
     __syncthreads();
     const uint32_t *lslots = slots + LV.slotBase;
-    for (int i0 = tid; i0 < nPts; i0 += 4 * QT_THREADS) {
+    for (int i0 = tid; i0 < nPts; i0 += 4 * NT) {
         int cidx[4];
         int2 info[4];
         uint32_t ent[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * QT_THREADS;
+            const int i = i0 + u * NT;
             int lo = 0, hi = nCells;  // last cell with prefix[c] <= i
             if (i < nPts)
                 while (hi - lo > 1) {
@@ -932,12 +936,12 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree_hist(ExParams p, int no
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * QT_THREADS;
+            const int i = i0 + u * NT;
             ent[u] = i < nPts ? lslots[info[u].x + (i - prefix[cidx[u]])] : 0u;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * QT_THREADS;
+            const int i = i0 + u * NT;
             if (i >= nPts) continue;
             const uint32_t e = ent[u];
             const int trips = nCells - cidx[u];   // processing-order index of an OK cell == its index inside the level
@@ -993,7 +997,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree_hist(ExParams p, int no
     // coarser levels = sums of four children (reads bypass L1: the counts were produced by atomics)
     for (int d = QT_DMAX - 1; d >= 0; --d) {
         const int n = nIni << (2 * d), o = qt_off(nIni, d), oc = qt_off(nIni, d + 1);
-        for (int i = tid; i < n; i += QT_THREADS)
+        for (int i = tid; i < n; i += NT)
             hist[o + i] = __ldcg(&hist[oc + 4 * i]) + __ldcg(&hist[oc + 4 * i + 1]) + __ldcg(&hist[oc + 4 * i + 2]) + __ldcg(&hist[oc + 4 * i + 3]);
         __syncthreads();
     }
@@ -1032,7 +1036,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree_hist(ExParams p, int no
         unsigned *idC = nid[cur], *idN = nid[nxt];
         if (!phase2) {
             // ---- full pass: split every node holding more than one point (:616-683); child counts from the table
-            for (int i = tid; i < 4 * size; i += QT_THREADS) {
+            for (int i = tid; i < 4 * size; i += NT) {
                 const int pn = i >> 2;
                 int c = 0;
                 if (cnC[pn] > 1) {
@@ -1043,12 +1047,12 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree_hist(ExParams p, int no
                 childCnt[i] = c;
                 childPos[i] = c > 0 ? 1 : 0;
             }
-            for (int i = tid; i < size; i += QT_THREADS) keptPos[i] = cnC[i] <= 1 ? 1 : 0;
+            for (int i = tid; i < size; i += NT) keptPos[i] = cnC[i] <= 1 ? 1 : 0;
             __syncthreads();
             if (sh_deep) break;
-            const int C = block_exclusive_scan(childPos, 4 * size, scratch);
-            const int nKept = block_exclusive_scan(keptPos, size, scratch);
-            for (int i = tid; i < 4 * size; i += QT_THREADS) {
+            const int C = block_exclusive_scan<NT>(childPos, 4 * size, scratch);
+            const int nKept = block_exclusive_scan<NT>(keptPos, size, scratch);
+            for (int i = tid; i < 4 * size; i += NT) {
                 const int n = childCnt[i];
                 if (n > 0) {
                     const int pos = C - 1 - childPos[i];
@@ -1061,7 +1065,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree_hist(ExParams p, int no
                     childPos[i] = -1;
                 }
             }
-            for (int i = tid; i < size; i += QT_THREADS) {
+            for (int i = tid; i < size; i += NT) {
                 if (cnC[i] <= 1) {
                     const int pos = C + keptPos[i];
                     bxN[pos] = bxC[i];
@@ -1070,10 +1074,10 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree_hist(ExParams p, int no
                 }
             }
             // expandable children (more than one point) in creation order: scan over (list position, child)
-            for (int i = tid; i < 4 * size; i += QT_THREADS) tmp4[i] = childCnt[i] > 1 ? 1 : 0;
+            for (int i = tid; i < 4 * size; i += NT) tmp4[i] = childCnt[i] > 1 ? 1 : 0;
             __syncthreads();
-            nPend = block_exclusive_scan(tmp4, 4 * size, scratch);
-            for (int i = tid; i < 4 * size; i += QT_THREADS)
+            nPend = block_exclusive_scan<NT>(tmp4, 4 * size, scratch);
+            for (int i = tid; i < 4 * size; i += NT)
                 if (childCnt[i] > 1) pend[tmp4[i]] = childPos[i];
             __syncthreads();
             size = C + nKept;
@@ -1082,9 +1086,9 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree_hist(ExParams p, int no
             else if (size + 3 * nPend > N) phase2 = true;
         } else {
             // ---- "largest first" pass (:685-751): sort pending by (size, UL.x) exactly like std::sort
-            for (int i = tid; i < size; i += QT_THREADS) pendIdx[i] = -1;
+            for (int i = tid; i < size; i += NT) pendIdx[i] = -1;
             __syncthreads();
-            for (int i = tid; i < nPend; i += QT_THREADS) {
+            for (int i = tid; i < nPend; i += NT) {
                 const int pos = pend[i];
                 pendIdx[pos] = i;
                 const unsigned long long key = ((unsigned long long)(unsigned)cnC[pos] << 16) | (unsigned short)bxC[pos].x;
@@ -1108,7 +1112,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree_hist(ExParams p, int no
             QT_MARK();
             {
                 orbx_sort::elem_t *sorted = reinterpret_cast<orbx_sort::elem_t *>(tmp4);
-                for (int i = tid; i < nPend; i += QT_THREADS) {
+                for (int i = tid; i < nPend; i += NT) {
                     const orbx_sort::elem_t e = sortbuf[i];
                     const unsigned long long k = e >> orbx_sort::kPayloadBits;
                     int rank = 0;
@@ -1119,7 +1123,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree_hist(ExParams p, int no
                     sorted[rank] = e;
                 }
                 __syncthreads();
-                for (int i = tid; i < nPend; i += QT_THREADS) sortbuf[i] = sorted[i];
+                for (int i = tid; i < nPend; i += NT) sortbuf[i] = sorted[i];
                 __syncthreads();
             }
             QT_MARK();
@@ -1145,13 +1149,13 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree_hist(ExParams p, int no
             __syncthreads();
             QT_MARK();
             const int C = sh_C;
-            for (int i = tid; i < size; i += QT_THREADS) {
+            for (int i = tid; i < size; i += NT) {
                 const int pi = pendIdx[i];
                 keptPos[i] = (pi >= 0 && best[pi] == 1) ? 0 : 1;
             }
             __syncthreads();
-            block_exclusive_scan(keptPos, size, scratch);
-            for (int i = tid; i < size; i += QT_THREADS) {
+            block_exclusive_scan<NT>(keptPos, size, scratch);
+            for (int i = tid; i < size; i += NT) {
                 const int pi = pendIdx[i];
                 if (!(pi >= 0 && best[pi] == 1)) {
                     const int pos = C + keptPos[i];
@@ -1160,7 +1164,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree_hist(ExParams p, int no
                     idN[pos] = idC[i];
                 }
             }
-            for (int i = tid; i < 4 * nPend; i += QT_THREADS) {
+            for (int i = tid; i < 4 * nPend; i += NT) {
                 const int pi = i >> 2;
                 if (best[pi] == 1 && childCnt[i] > 0) {
                     const int pos = C - 1 - childPos[i];
@@ -1202,13 +1206,13 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree_hist(ExParams p, int no
     }
 
     // ---- attach the points to the final nodes and keep the best response per node (:757-776)
-    for (int i = tid; i < size; i += QT_THREADS) {
+    for (int i = tid; i < size; i += NT) {
         best[i] = 0;
         const unsigned id = nid[cur][i];
         finalPos[qt_off(nIni, id >> 24) + (id & 0xffffffu)] = (unsigned short)(i + 1);
     }
     __syncthreads();
-    qt_for_points<false>(ptNode, ptXY, nPts, [&](int i, uint32_t v, float2) {
+    qt_for_points<false, NT>(ptNode, ptXY, nPts, [&](int i, uint32_t v, float2) {
         const unsigned leaf = v & 0xffffu;
 #pragma unroll
         for (int d = 0; d <= QT_DMAX; ++d) {
@@ -1220,7 +1224,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree_hist(ExParams p, int no
         }
     });
     __syncthreads();
-    for (int i = tid; i < size; i += QT_THREADS) {
+    for (int i = tid; i < size; i += NT) {
         const int order = (int)(0xffffffu - (best[i] & 0xffffffu));
         const float2 xy = ptXY[order];
         sel[i] = make_float4(__fadd_rn(xy.x, (float)ORBX_BORDER), __fadd_rn(xy.y, (float)ORBX_BORDER), (float)(best[i] >> 24), 0.f);
@@ -1939,22 +1943,32 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
     {
         const QtSmem L = qt_smem_layout(ex->nodeCapMax, ex->maxCellsLevel);
         if (L.total > 200 * 1024) { ex->err = "nfeatures too large for the quadtree kernel's shared memory"; return ORBX_ERR_ARG; }
-        if (L.total > 48 * 1024)
-            CUDA_TRY(ex, cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
         dim3 grd(G.nlevels, batch);
         const size_t smemH = (size_t)L.total + 8 * (size_t)ex->nodeCapMax + 2 * (size_t)ex->maxIni * QT_TREE;
-        if (ex->useHistQuadtree && smemH <= 200 * 1024) {
-            if (smemH > 48 * 1024)
-                CUDA_TRY(ex, cudaFuncSetAttribute(k_quadtree_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemH));
-            k_quadtree_hist<<<grd, QT_THREADS, smemH, s>>>(P, ex->nodeCapMax, ex->maxCellsLevel, ex->maxIni,
-                                                          ex->d_hist + f * G.nlevels * (size_t)ex->maxIni * QT_TREE, ex->d_deep + f * G.nlevels,
-                                                          first == 0 ? ex->d_dbg : nullptr);
-            ++ex->launches;
-            k_quadtree<<<grd, QT_THREADS, L.total, s>>>(P, ex->nodeCapMax, ex->maxCellsLevel, ex->d_deep + f * G.nlevels);
+        const bool useHist = ex->useHistQuadtree && smemH <= 200 * 1024;
+        unsigned *hist = ex->d_hist + f * G.nlevels * (size_t)ex->maxIni * QT_TREE;
+        int *deep = ex->d_deep + f * G.nlevels;
+        // large quotas (4K / thousands of features per level): few, long blocks → 512 threads each
+        const bool big = ex->nodeCapMax > 600;
+        if (big) {
+            if (L.total > 48 * 1024) CUDA_TRY(ex, cudaFuncSetAttribute(k_quadtree<QT_THREADS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+            if (useHist) {
+                if (smemH > 48 * 1024) CUDA_TRY(ex, cudaFuncSetAttribute(k_quadtree_hist<QT_THREADS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemH));
+                k_quadtree_hist<QT_THREADS_BIG><<<grd, QT_THREADS_BIG, smemH, s>>>(P, ex->nodeCapMax, ex->maxCellsLevel, ex->maxIni, hist, deep, first == 0 ? ex->d_dbg : nullptr);
+                ++ex->launches;
+            }
+            k_quadtree<QT_THREADS_BIG><<<grd, QT_THREADS_BIG, L.total, s>>>(P, ex->nodeCapMax, ex->maxCellsLevel, useHist ? deep : nullptr);
         } else {
-            k_quadtree<<<grd, QT_THREADS, L.total, s>>>(P, ex->nodeCapMax, ex->maxCellsLevel, nullptr);
+            if (L.total > 48 * 1024) CUDA_TRY(ex, cudaFuncSetAttribute(k_quadtree<QT_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+            if (useHist) {
+                if (smemH > 48 * 1024) CUDA_TRY(ex, cudaFuncSetAttribute(k_quadtree_hist<QT_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemH));
+                k_quadtree_hist<QT_THREADS><<<grd, QT_THREADS, smemH, s>>>(P, ex->nodeCapMax, ex->maxCellsLevel, ex->maxIni, hist, deep, first == 0 ? ex->d_dbg : nullptr);
+                ++ex->launches;
+            }
+            k_quadtree<QT_THREADS><<<grd, QT_THREADS, L.total, s>>>(P, ex->nodeCapMax, ex->maxCellsLevel, useHist ? deep : nullptr);
         }
         ++ex->launches;
+        if (!useHist) CUDA_TRY(ex, cudaMemsetAsync(deep, 0, (size_t)batch * G.nlevels * sizeof(int), s));
     }
     if (prof) CUDA_TRY(ex, cudaEventRecord(ex->ev[3], s));
     // K7
