@@ -1368,61 +1368,36 @@ __global__ void __launch_bounds__(64 * BLUR_STRIPS) k_blur(ExParams p, const Blu
         }
     }
     __syncthreads();
-    const int x = tx0 + threadIdx.x * 4;
-    const int y0 = ty0 + threadIdx.y * BLUR_RH;
-    if (x >= w || y0 >= h) return;
-    // Three aligned words cover the 12-byte window x-4..x+7.  At the image edges the words are clamped into
-    // the row and the REFLECT_101 bytes are produced by per-thread PRMT selectors computed once (every
-    // reflected source byte lies inside the two neighbouring words), so edge lanes cost 3 extra PRMT per row.
-    const int lastWord = (w - 1) >> 2;
-    const int ib = x >> 2, ia = max(ib - 1, 0), ic = min(ib + 1, lastWord);
-    const bool edge = (x < 4) || (x + 7 >= w);
-    uint32_t selw[3] = {0x3210u, 0x3210u, 0x3210u};
-    bool hiPair[3] = {false, false, true};   // word k comes from PRMT(lo, hi): lo/hi = (A,B) or (B,C)
-    if (edge) {
-        const int needMaxJ = min(x + 3, w - 1) + 3 - (x - 4);   // last window byte any valid output pixel taps
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            bool found = false;
-#pragma unroll
-            for (int pr = 0; pr < 2; ++pr) {
-                const int wa = pr == 0 ? ia : ib, wb = pr == 0 ? ib : ic;
-                bool ok = true;
-                uint32_t sel = 0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int j = 4 * k + i;
-                    uint32_t nib = 0;
-                    if (j >= 1 && j <= needMaxJ) {
-                        const int sidx = reflect101(x - 4 + j, w);
-                        if ((sidx >> 2) == wa) nib = (uint32_t)(sidx & 3);
-                        else if ((sidx >> 2) == wb) nib = 4u + (uint32_t)(sidx & 3);
-                        else ok = false;
-                    }
-                    sel |= nib << (4 * i);
+    // REFLECT_101 at the left / right image edge: patch the three halo columns of every staged row in place, so
+    // the main loop reads plain aligned words everywhere
+    {
+        const bool leftTile = tx0 == 0, rightTile = (w + 2 >= tx0 - 16) && (w < tx0 + BLUR_TW + 16);
+        if (leftTile || rightTile) {
+            for (int i = tid; i < (BLUR_TH + 6) * 6; i += 64 * BLUR_STRIPS) {
+                const int r = i / 6, k = i - r * 6;
+                uint8_t *trow8 = &tile[r * BLUR_SP];
+                if (k < 3) {
+                    if (leftTile) trow8[16 - (k + 1)] = trow8[16 + min(k + 1, w - 1)];               // x = -(k+1) ← x = k+1
+                } else if (rightTile) {
+                    const int j = k - 3, xd = w + j, xs = max(w - 2 - j, 0);                        // x = w+j ← x = w-2-j
+                    const int cd = xd - (tx0 - 16), cs = xs - (tx0 - 16);
+                    if (cd >= 0 && cd < BLUR_SP && cs >= 0 && cs < BLUR_SP) trow8[cd] = trow8[cs];
                 }
-                if (ok && !found) { found = true; selw[k] = sel; hiPair[k] = pr == 1; }
             }
         }
     }
+    __syncthreads();
+    const int x = tx0 + threadIdx.x * 4;
+    const int y0 = ty0 + threadIdx.y * BLUR_RH;
+    if (x >= w || y0 >= h) return;
     const uint32_t KLO = 18u | (34u << 8) | (48u << 16) | (56u << 24), KHI = 48u | (34u << 8) | (18u << 16);
     uint8_t *dst = p.blur + (long long)b * g.frameBytes + LV.off + x;
-    // word offsets inside the tile (tile column 0 = image column tx0-16)
-    const int wbase = (16 - tx0) >> 2;
-    const uint32_t *trow = reinterpret_cast<const uint32_t *>(tile) + threadIdx.y * BLUR_RH * (BLUR_SP / 4);
-    const int oa = ia + wbase, ob = ib + wbase, oc = ic + wbase;
+    // the 12-byte window x-4 .. x+7 of a staged row = three aligned words (tile column 0 = image column tx0-16)
+    const uint32_t *trow = reinterpret_cast<const uint32_t *>(tile) + threadIdx.y * BLUR_RH * (BLUR_SP / 4) + ((x - 4 - (tx0 - 16)) >> 2);
     uint32_t ring[7][4];
 #pragma unroll
     for (int r = 0; r < BLUR_RH + 6; ++r) {
-        const uint32_t A = trow[r * (BLUR_SP / 4) + oa], Bw = trow[r * (BLUR_SP / 4) + ob], Cw = trow[r * (BLUR_SP / 4) + oc];
-        uint32_t w0, w1, w2;
-        if (edge) {
-            w0 = __byte_perm(hiPair[0] ? Bw : A, hiPair[0] ? Cw : Bw, selw[0]);
-            w1 = __byte_perm(hiPair[1] ? Bw : A, hiPair[1] ? Cw : Bw, selw[1]);
-            w2 = __byte_perm(hiPair[2] ? Bw : A, hiPair[2] ? Cw : Bw, selw[2]);
-        } else {
-            w0 = A; w1 = Bw; w2 = Cw;
-        }
+        const uint32_t w0 = trow[r * (BLUR_SP / 4)], w1 = trow[r * (BLUR_SP / 4) + 1], w2 = trow[r * (BLUR_SP / 4) + 2];
         // pixel i sits at byte 4+i of {w0,w1,w2}; taps are bytes 1+i .. 7+i
         uint32_t *hr = ring[r % 7];
         hr[0] = __dp4a(__byte_perm(w0, w1, 0x4321u), KLO, __dp4a(__byte_perm(w1, w2, 0x4321u), KHI, 0u));
