@@ -85,7 +85,7 @@ __device__ __forceinline__ const uint8_t *level_ptr(const ExParams &p, const Orb
 // phase 2 combines two of those rows per output row, 4 pixels per thread, one 32-bit store.
 // ------------------------------------------------------------------------------------------------
 #define PYR_TW 128
-#define PYR_TH 16
+#define PYR_TH 32
 struct PyrArgs {             // everything by value: no dependent global loads before the pixel loads
     const uint8_t *src; long long srcStride; int sp, sw, sh;
     uint8_t *dst; long long dstStride; int dp, dw, dh;
