@@ -226,7 +226,7 @@ __device__ __forceinline__ uint32_t pair_at(const Row3 &r) {
 
 // exact FAST measure minus lowTh, clamped at 0, for the pixel pair P (0/1) of a 4-pixel group
 template <int P>
-__device__ __forceinline__ uint32_t fast_pair_score(const Row3 (&R)[7], uint32_t negT2) {
+__device__ __forceinline__ uint32_t fast_pair_score(const Row3 (&R)[7], uint32_t biasT2) {
     // ring order k=0..15 = (dx,dy): (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
     // R[i] is the row dy = i-3; byte index of pixel pair P at horizontal offset dx is 4+2P+dx
     constexpr int C = 4 + 2 * P;
@@ -256,9 +256,12 @@ __device__ __forceinline__ uint32_t fast_pair_score(const Row3 (&R)[7], uint32_t
     }
     lo = __vminu2(lo, nmx[15]);
     hi = __vmaxu2(hi, nmn[15]);
-    const uint32_t A = __vsub2(v2, lo), B = __vsub2(hi, v2);          // signed 16-bit per half
-    const uint32_t M = __vmaxs2(A, B);
-    return __viaddmax_s16x2(M, negT2, 0u);                            // max(M - lowTh, 0) per half
+    // Both differences are taken with a +256 bias per half so that no borrow can cross the halves: plain 32-bit
+    // adds (which the compiler may place on the FMA pipe as IMAD) replace the packed 16x2 subtractions that would
+    // compete with VIMNMX3 for the ALU pipe.  biasT2 = (256 + lowTh) per half.
+    const uint32_t A = (v2 + 0x01000100u) - lo, B = (hi + 0x01000100u) - v2;   // M + 256 candidates, each in [1, 511]
+    const uint32_t M = __vmaxu2(A, B);
+    return __vmaxu2(M, biasT2) - biasT2;                                      // max(M - lowTh, 0) per half
 }
 
 template <int WPB>
@@ -322,7 +325,7 @@ __global__ void __launch_bounds__(WPB * 32) k_fast_cells(ExParams p, int maxSlot
     const int nGroups = G * ih;              // groups of the cell in row-major order: lane work items
     const uint32_t rcpG = (65536u + G - 1) / G;   // (i*rcpG)>>16 == i/G for i < 3449 (cells are ≤ 19×69 groups)
     const int t = g.lowTh;
-    const uint32_t negT2 = ((uint32_t)(-t) & 0xffffu) * 0x10001u;
+    const uint32_t biasT2 = (uint32_t)(256 + t) * 0x10001u;
 
     // pass 1: score map (value = M - lowTh clamped at 0; real score = value + lowTh - 1)
     for (int i0 = 0; i0 < nGroups; i0 += 32) {
@@ -333,7 +336,7 @@ __global__ void __launch_bounds__(WPB * 32) k_fast_cells(ExParams p, int maxSlot
             Row3 R[7];
 #pragma unroll
             for (int i = 0; i < 7; ++i) R[i] = ld_row3(rowp + i * rp);
-            const uint32_t s0 = fast_pair_score<0>(R, negT2), s1 = fast_pair_score<1>(R, negT2);
+            const uint32_t s0 = fast_pair_score<0>(R, biasT2), s1 = fast_pair_score<1>(R, biasT2);
             const int nValid = min(iw - 4 * lg, 4);
             const uint32_t colMask = nValid >= 4 ? 0xffffffffu : ((1u << (8 * nValid)) - 1u);
             const uint32_t word = __byte_perm(s0, s1, 0x6420u) & colMask;
@@ -360,7 +363,8 @@ __global__ void __launch_bounds__(WPB * 32) k_fast_cells(ExParams p, int maxSlot
                 const uint32_t cL0 = pair_at<3>(Cn), cM0 = pair_at<4>(Cn), cR0 = pair_at<5>(Cn), cM1 = pair_at<6>(Cn), cR1 = pair_at<7>(Cn);
                 const uint32_t n0 = __vimax3_u16x2(__vimax3_u16x2(tL0, tM0, tR0), __vimax3_u16x2(bL0, bM0, bR0), __vmaxu2(cL0, cR0));
                 const uint32_t n1 = __vimax3_u16x2(__vimax3_u16x2(tR0, tM1, tR1), __vimax3_u16x2(bR0, bM1, bR1), __vmaxu2(cR0, cR1));
-                const uint32_t d0 = __vsub2(n0, cM0), d1 = __vsub2(n1, cM1);   // negative half ⇔ centre > all 8 neighbours
+                // centre > all 8 neighbours ⇔ bit 15 of (centre + 0x7fff - neighbourMax) per half; no borrow crosses halves
+                const uint32_t d0 = (cM0 + 0x7fff7fffu) - n0, d1 = (cM1 + 0x7fff7fffu) - n1;
                 flags = ((d0 >> 15) & 1u) | ((d0 >> 30) & 2u) | ((d1 >> 13) & 4u) | ((d1 >> 28) & 8u);
             }
         }
