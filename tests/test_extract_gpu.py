@@ -222,3 +222,42 @@ def test_legacy_quadtree_kernel_gives_the_same_result(orbx_mod, oracle_mod, monk
     mono, k, d = ex(img, None, (0, 1000))
     rc, rk, rd, rmono = oracle_mod.Extractor(1000, 1.2, 8, 20, 7).extract(img, lap=(0, 1000))
     assert mono == rmono and k.tobytes() == rk.tobytes() and np.array_equal(d, rd)
+
+
+def test_left_right_extractors_run_concurrently_in_two_threads(orbx_mod, oracle_mod):
+    """The reference extracts the left and right image in two std::threads with two extractor instances
+    (src/Frame.cc:124-127); handles share no mutable state, so results must not depend on the interleaving."""
+    import threading
+    from dani_slam_b200 import synth
+    left = [synth.throughput_frame(300 + i, 752, 480) for i in range(6)]
+    right = [synth.stereo_right(f, 300 + i) for i, f in enumerate(left)]
+    exL = orbx_mod.ORBextractor(1200, 1.2, 8, 20, 7, max_width=752, max_height=480)
+    exR = orbx_mod.ORBextractor(1200, 1.2, 8, 20, 7, max_width=752, max_height=480)
+    out = {"L": [], "R": []}
+
+    def run(ex, frames, key):
+        for _ in range(3):                                   # repeat to widen the overlap window
+            res = [ex(f) for f in frames]
+        out[key] = res
+
+    tl = threading.Thread(target=run, args=(exL, left, "L"))
+    tr = threading.Thread(target=run, args=(exR, right, "R"))
+    tl.start(); tr.start(); tl.join(); tr.join()
+    ref = oracle_mod.Extractor(1200, 1.2, 8, 20, 7)
+    for frames, key in ((left, "L"), (right, "R")):
+        for f, (mono, k, d) in zip(frames, out[key]):
+            rc, rk, rd, rmono = ref.extract(f)
+            assert mono == rmono and k.tobytes() == rk.tobytes() and np.array_equal(d, rd)
+
+
+def test_other_pyramid_shapes(orbx_mod, oracle_mod):
+    """Level counts, scale factors and thresholds away from the TUM1 defaults (incl. a single level, 12 levels,
+    scale 2.0 which exercises the wide-source path of the pyramid kernel, and minTh > iniTh)."""
+    from dani_slam_b200 import synth
+    img = synth.parity_frame(71, 800, 600)
+    for (nf, sfac, nl, ini, mn) in [(1500, 1.2, 12, 20, 7), (800, 2.0, 4, 20, 7), (600, 1.05, 6, 15, 5), (1000, 1.2, 8, 7, 20), (50, 1.3, 5, 40, 40),
+                                    (0, 1.2, 8, 20, 7)]:
+        ex = orbx_mod.ORBextractor(nf, sfac, nl, ini, mn, max_width=800, max_height=600)
+        mono, k, d = ex(img)
+        rc, rk, rd, rmono = oracle_mod.Extractor(nf, sfac, nl, ini, mn).extract(img, cap=nf + 400)
+        assert rc == 0 and mono == rmono and k.tobytes() == rk.tobytes() and np.array_equal(d, rd), (nf, sfac, nl, ini, mn)
