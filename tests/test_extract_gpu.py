@@ -261,3 +261,26 @@ def test_other_pyramid_shapes(orbx_mod, oracle_mod):
         mono, k, d = ex(img)
         rc, rk, rd, rmono = oracle_mod.Extractor(nf, sfac, nl, ini, mn).extract(img, cap=nf + 400)
         assert rc == 0 and mono == rmono and k.tobytes() == rk.tobytes() and np.array_equal(d, rd), (nf, sfac, nl, ini, mn)
+
+
+def test_many_seeded_frames_statistical_parity(orbx_mod, oracle_mod):
+    """256 seeded frames (throughput + parity generators, three lapping windows): every keypoint record and
+    descriptor equals the oracle's.  Rare paths (rounding of rotated taps at .5, std::sort tie permutations at the
+    quota cut, drift on split lines) only show up at this scale."""
+    from concurrent.futures import ThreadPoolExecutor
+    from dani_slam_b200 import synth
+    B = 256
+    imgs = np.stack([synth.parity_frame(1000 + i) if i % 4 == 3 else synth.throughput_frame(1000 + i) for i in range(B)])
+    ex = orbx_mod.ORBextractor(1000, 1.2, 8, 20, 7, max_width=640, max_height=480, max_batch=B)
+    for lap in [(0, 0), (0, 1000), (250, 400)]:
+        n, mono, kps, desc = ex.extract_batch(imgs, lap)
+
+        def check(b):
+            rc, rk, rd, rmono = oracle_mod.Extractor(1000, 1.2, 8, 20, 7).extract(imgs[b], lap=lap)
+            return (n[b] == len(rk) and mono[b] == rmono and kps[b, : n[b]].tobytes() == rk.tobytes()
+                    and np.array_equal(desc[b, : n[b]], rd))
+
+        step = 1 if lap == (0, 0) else 4              # full set once, a quarter for the other lapping windows
+        with ThreadPoolExecutor(16) as pool:
+            ok = list(pool.map(check, range(0, B, step)))
+        assert all(ok), (lap, [i * step for i, v in enumerate(ok) if not v][:10])
