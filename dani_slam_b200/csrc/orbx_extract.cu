@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(256) k_pyr_level(PyrArgs a) {
 // ------------------------------------------------------------------------------------------------
 struct FastSmem {
     int roiPitch, scorePitch;
-    int roiOff, scoreOff, listOff, total;
+    int roiOff, scoreOff, listOff, queueOff, total;
 };
 __host__ __device__ inline FastSmem fast_smem_layout(int maxCw, int maxCh, int maxSlotCap) {
     FastSmem s;
@@ -203,7 +203,8 @@ __host__ __device__ inline FastSmem fast_smem_layout(int maxCw, int maxCh, int m
     s.roiOff = 0;
     s.scoreOff = s.roiOff + s.roiPitch * maxCh;
     s.listOff = s.scoreOff + s.scorePitch * (maxCh - 6 + 2);
-    s.total = (s.listOff + 4 * maxSlotCap + 15) & ~15;
+    s.queueOff = s.listOff + 4 * maxSlotCap;             // u16 per 4-pixel group: groups whose score word is non-zero
+    s.total = (s.queueOff + 2 * G * (maxCh - 6) + 15) & ~15;
     return s;
 }
 
@@ -277,6 +278,7 @@ __global__ void __launch_bounds__(WPB * 32) k_fast_cells(ExParams p, int maxSlot
     uint8_t *roi = base + L.roiOff;
     uint8_t *score = base + L.scoreOff;
     uint32_t *list = reinterpret_cast<uint32_t *>(base + L.listOff);
+    uint16_t *queue = reinterpret_cast<uint16_t *>(base + L.queueOff);
 
     int pitch;
     const uint8_t *img = level_ptr(p, g, cell.level, b, pitch);
@@ -328,8 +330,10 @@ __global__ void __launch_bounds__(WPB * 32) k_fast_cells(ExParams p, int maxSlot
     const uint32_t biasT2 = (uint32_t)(256 + t) * 0x10001u;
 
     // pass 1: score map (value = M - lowTh clamped at 0; real score = value + lowTh - 1)
+    int nQ = 0;   // groups that contain at least one corner, in row-major order
     for (int i0 = 0; i0 < nGroups; i0 += 32) {
         const int gi = i0 + lane;
+        uint32_t word = 0;
         if (gi < nGroups) {
             const int yi = (int)(((uint32_t)gi * rcpG) >> 16), lg = gi - yi * G;
             const uint8_t *rowp = roi + yi * rp + 4 * lg;  // ROI row (yi+3)+dy = yi + i for i = 0..6
@@ -339,24 +343,28 @@ __global__ void __launch_bounds__(WPB * 32) k_fast_cells(ExParams p, int maxSlot
             const uint32_t s0 = fast_pair_score<0>(R, biasT2), s1 = fast_pair_score<1>(R, biasT2);
             const int nValid = min(iw - 4 * lg, 4);
             const uint32_t colMask = nValid >= 4 ? 0xffffffffu : ((1u << (8 * nValid)) - 1u);
-            const uint32_t word = __byte_perm(s0, s1, 0x6420u) & colMask;
+            word = __byte_perm(s0, s1, 0x6420u) & colMask;
             *reinterpret_cast<uint32_t *>(score + (yi + 1) * sp + 4 * lg + 4) = word;
         }
+        const uint32_t bal = __ballot_sync(0xffffffffu, word != 0);
+        if (word != 0) queue[nQ + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)gi;
+        nQ += __popc(bal);
     }
     __syncwarp();
 
     // pass 2: cell-local 3×3 strict NMS → row-major ordered list; count survivors above iniTh
     const int iniRel = g.iniTh - t + 1;      // value >= iniRel  ⇔  M > iniTh
     int n = 0, nIni = 0;
-    for (int i0 = 0; i0 < nGroups; i0 += 32) {
-        const int gi = i0 + lane;
+    for (int i0 = 0; i0 < nQ; i0 += 32) {        // only the groups with corners: ≈ a quarter of all groups
+        const int qi = i0 + lane;
+        const int gi = qi < nQ ? (int)queue[qi] : 0;
         const int yi = (int)(((uint32_t)gi * rcpG) >> 16), lg = gi - yi * G;
         uint32_t flags = 0, vals = 0;        // flags: bit i = pixel i of the group survives
-        if (gi < nGroups) {
+        if (qi < nQ) {
             const uint8_t *rowp = score + yi * sp + 4 * lg;   // score rows yi, yi+1 (centre), yi+2
             const Row3 T = ld_row3(rowp), Cn = ld_row3(rowp + sp), Bt = ld_row3(rowp + 2 * sp);
             vals = Cn.w1;
-            if (vals != 0) {
+            {
                 // pair 0 centre bytes (4,5), pair 1 centre bytes (6,7)
                 const uint32_t tL0 = pair_at<3>(T), tM0 = pair_at<4>(T), tR0 = pair_at<5>(T), tM1 = pair_at<6>(T), tR1 = pair_at<7>(T);
                 const uint32_t bL0 = pair_at<3>(Bt), bM0 = pair_at<4>(Bt), bR0 = pair_at<5>(Bt), bM1 = pair_at<6>(Bt), bR1 = pair_at<7>(Bt);
