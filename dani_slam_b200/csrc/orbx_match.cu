@@ -36,12 +36,23 @@ __device__ __forceinline__ int ham256(const uint4 &a0, const uint4 &a1, const ui
 // 256-bit Hamming distance with a carry-save adder front end: three full adders (2 LOP3 each) fold seven of the
 // eight XOR words into two "ones" words and three "twos" words, so a pair costs 5 POPC instead of 8 — the POPC
 // pipe (16 lanes/clk/SM) is the binding unit of the brute-force kernel, LOP3 runs on the wider ALU pipe.
+__device__ __forceinline__ uint32_t lop3_xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t lop3_maj(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 __device__ __forceinline__ int ham256_csa(const uint4 &a0, const uint4 &a1, const uint4 &b0, const uint4 &b1) {
     const uint32_t x0 = a0.x ^ b0.x, x1 = a0.y ^ b0.y, x2 = a0.z ^ b0.z, x3 = a0.w ^ b0.w;
     const uint32_t x4 = a1.x ^ b1.x, x5 = a1.y ^ b1.y, x6 = a1.z ^ b1.z, x7 = a1.w ^ b1.w;
-    const uint32_t s1 = x0 ^ x1 ^ x2, c1 = (x0 & x1) | (x2 & (x0 ^ x1));
-    const uint32_t s2 = x3 ^ x4 ^ x5, c2 = (x3 & x4) | (x5 & (x3 ^ x4));
-    const uint32_t s3 = s1 ^ s2 ^ x6, c3 = (s1 & s2) | (x6 & (s1 ^ s2));
+    // each full adder is exactly two LOP3: sum = xor3 (0x96), carry = majority (0xE8)
+    const uint32_t s1 = lop3_xor3(x0, x1, x2), c1 = lop3_maj(x0, x1, x2);
+    const uint32_t s2 = lop3_xor3(x3, x4, x5), c2 = lop3_maj(x3, x4, x5);
+    const uint32_t s3 = lop3_xor3(s1, s2, x6), c3 = lop3_maj(s1, s2, x6);
     return __popc(s3) + __popc(x7) + 2 * (__popc(c1) + __popc(c2) + __popc(c3));
 }
 
