@@ -833,29 +833,145 @@ __global__ void __launch_bounds__(NT) k_quadtree(ExParams p, int nodeCapMax, int
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3 (fast path): the same DistributeOctTree emulation, but the candidates are classified ONCE.
+// K3 (fast path): the same DistributeOctTree emulation split into throughput-parallel and serial parts.
 // The quadtree geometry is data independent (a node's children are its box cut at the ceil-halves), so every
-// candidate's path down to depth QT_DMAX is computed in a single pass and counted in a per-(frame, level)
-// histogram of the depth-QT_DMAX cells; the coarser levels are sums of four.  The list emulation then reads a
-// child's point count from that table instead of re-classifying all points in every pass, and the points are
-// attached to their final nodes by walking their own path through a table of final nodes.  If a node at depth
-// QT_DMAX would have to be split (rare: tightly clustered corners) the block raises a flag and the general
-// kernel k_quadtree handles that (frame, level).
+// candidate's path down to depth QT_DMAX is computed ONCE and counted in a per-(frame, level) histogram of the
+// depth-QT_DMAX cells; the coarser levels are sums of four.
+//   k_qt_prefix    (level, frame)  prefix over the level's cell counts = candidate order index; clears the tables
+//   k_qt_classify  warp per cell   DANI round trips (:871-907), root bin (:584), path code, histogram atomics
+//   k_qt_nodes     (level, frame)  list emulation on node COUNTS only (reads a child's count from the table);
+//                                  std::sort = introsort partitioning + parallel stable rank sort; writes the table
+//                                  of final nodes; raises the `deep` flag if a depth-QT_DMAX node must be split
+//   k_quadtree     (flagged only)  the general kernel redoes flagged (frame, level) pairs from the raw slots
+//   k_qt_attach    warp per cell   every candidate walks its own path to its final node; atomicMax of
+//                                  (response, first-in-order) per node (:757-776)
+//   k_qt_select    (level, frame)  writes the selected keypoints in list order (:919-923)
 // ------------------------------------------------------------------------------------------------
 #define QT_DMAX 6
 #define QT_TREE 5461                      // Σ_{d=0..6} 4^d nodes per root
 #define QT_MAX_INI 12
 __host__ __device__ __forceinline__ int qt_off(int nIni, int d) { return nIni * (((1 << (2 * d)) - 1) / 3); }
 
+struct QtTables {               // per-handle device tables of the fast path (indexed by frame, then level)
+    unsigned *hist;             // [frame][level][maxIni·QT_TREE] point counts per tree node
+    unsigned short *finalPos;   // same shape: list position + 1 of final nodes, 0 elsewhere
+    unsigned *best;             // [frame][selTotal] best (response<<24 | 0xffffff-order) per final node
+    int *cellPrefix;            // [frame][nCellsTotal] exclusive prefix of the cell counts inside their level
+    int *deep;                  // [frame][level] 1 = the general kernel must redo this pair
+    int maxIni;
+};
+
 template <int NT>
-__global__ void __launch_bounds__(NT) k_quadtree_hist(ExParams p, int nodeCapMax, int maxCellsLevel, int maxIni,
-                                                               unsigned *histAll, int *deepFlag, long long *dbg) {
+__global__ void __launch_bounds__(NT) k_qt_prefix(ExParams p, QtTables t, int maxCellsLevel) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    int *prefix = reinterpret_cast<int *>(smem_raw);
+    int *scratch = prefix + maxCellsLevel + 1;
+    const OrbxGeom &g = *p.g;
+    const int l = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const OrbxLevel &LV = g.lv[l];
+    const int nCells = LV.nCells;
+    const int *cellCnt = p.cellCnt + (long long)b * g.nCellsTotal + LV.cellBase;
+    for (int c = tid; c < nCells; c += NT) prefix[c] = cellCnt[c];
+    __syncthreads();
+    block_exclusive_scan<NT>(prefix, nCells, scratch);
+    int *out = t.cellPrefix + (long long)b * g.nCellsTotal + LV.cellBase;
+    for (int c = tid; c < nCells; c += NT) out[c] = prefix[c];
+    const long long tb = ((long long)b * g.nlevels + l) * (long long)t.maxIni * QT_TREE;
+    const int treeN = min(LV.nIni, t.maxIni) * QT_TREE;
+    for (int i = tid; i < treeN; i += NT) t.hist[tb + i] = 0;
+    unsigned *best = t.best + (long long)b * g.selTotal + LV.selBase;
+    for (int i = tid; i < LV.selCap; i += NT) best[i] = 0;
+    if (tid == 0) t.deep[b * g.nlevels + l] = (LV.nIni > QT_MAX_INI) ? 1 : 0;
+}
+
+#define QT_CLS_BLOCKS 8
+// grid (QT_CLS_BLOCKS, level, frame): one thread per candidate (grid-stride inside the level), the candidate's cell is
+// found by a binary search over the level's cell prefix, so all lanes stay busy whatever the cell occupancies are
+__global__ void __launch_bounds__(128) k_qt_classify(ExParams p, QtTables t) {
+    const OrbxGeom &g = *p.g;
+    const int l = blockIdx.y, b = blockIdx.z;
+    const OrbxLevel &LV = g.lv[l];
+    const int nCells = LV.nCells;
+    if (nCells == 0) return;
+    const int *cellCnt = p.cellCnt + (long long)b * g.nCellsTotal + LV.cellBase;
+    const int *prefix = t.cellPrefix + (long long)b * g.nCellsTotal + LV.cellBase;
+    const int nPts = prefix[nCells - 1] + cellCnt[nCells - 1];
+    const OrbxCell *cells = p.cells + LV.cellBase;
+    const uint32_t *slots = p.slots + (long long)b * g.slotsTotal;
+    float2 *ptXY = p.ptXY + (long long)b * g.slotsTotal + LV.slotBase;
+    uint32_t *ptNode = p.ptNode + (long long)b * g.slotsTotal + LV.slotBase;
+    const int nIni = LV.nIni;
+    const bool tabled = nIni <= QT_MAX_INI;
+    unsigned *hist = t.hist + ((long long)b * g.nlevels + l) * (long long)t.maxIni * QT_TREE + qt_off(nIni, QT_DMAX);
+    const float sc = LV.sf, inv = __fdiv_rn(1.f, sc);
+    const float hX = LV.hX;
+    const int nRects = g.nRects;
+    const int rootH = LV.maxBY - ORBX_BORDER;
+    for (int i = blockIdx.x * 128 + threadIdx.x; i < nPts; i += QT_CLS_BLOCKS * 128) {
+        int lo = 0, hi = nCells;  // last cell with prefix[c] <= i
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (prefix[mid] <= i) lo = mid; else hi = mid;
+        }
+        const OrbxCell cell = cells[lo];
+        const uint32_t e = slots[cell.slot + (i - prefix[lo])];
+        const int trips = nCells - cell.seq;   // filter passes this cell's keypoints live through (:871-907)
+        float x = __fadd_rn((float)(e & 0xff), (float)(cell.cx * LV.wCell));  // pt.x += j*wCell (:863)
+        float y = __fadd_rn((float)((e >> 8) & 0xff), (float)(cell.cy * LV.hCell));
+        bool erased = false;
+        for (int tr = 0; tr < trips; ++tr) {
+            const float xs = __fmul_rn(__fadd_rn(x, (float)ORBX_BORDER), sc);
+            const float ys = __fmul_rn(__fadd_rn(y, (float)ORBX_BORDER), sc);
+            if (nRects > 0) {
+                const int px = __float2int_rn(xs), py = __float2int_rn(ys);  // Point2f → Point2i
+                for (int r = 0; r < nRects; ++r) {
+                    const int rx = g.rects[4 * r], ry = g.rects[4 * r + 1];
+                    if (rx <= px && px < rx + g.rects[4 * r + 2] && ry <= py && py < ry + g.rects[4 * r + 3]) {
+                        erased = true;
+                        break;
+                    }
+                }
+                if (erased) break;
+            }
+            const float xn = __fsub_rn(__fmul_rn(xs, inv), (float)ORBX_BORDER);
+            const float yn = __fsub_rn(__fmul_rn(ys, inv), (float)ORBX_BORDER);
+            const bool fixed = (xn == x) && (yn == y);
+            x = xn;
+            y = yn;
+            if (fixed) break;  // later trips reproduce this one exactly
+        }
+        ptXY[i] = make_float2(x, y);
+        if (erased) {
+            ptNode[i] = ORBX_NODE_ERASED;
+            continue;
+        }
+        int bin = (int)__fdiv_rn(x, hX);  // vpIniNodes[kp.pt.x/hX] (:584)
+        bin = min(max(bin, 0), nIni - 1);
+        short4 bx;
+        bx.x = (short)(int)__fmul_rn(hX, (float)bin);
+        bx.y = (short)(int)__fmul_rn(hX, (float)(bin + 1));
+        bx.z = 0;
+        bx.w = (short)rootH;
+        unsigned code = (unsigned)bin;
+#pragma unroll
+        for (int d = 0; d < QT_DMAX; ++d) {
+            const int q = qt_quadrant(bx, x, y);
+            bx = qt_child_box(bx, q);
+            code = code * 4u + (unsigned)q;
+        }
+        ptNode[i] = (code & 0xffffu) | ((e >> 16) << 16);
+        if (tabled) atomicAdd(&hist[code], 1u);
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) k_qt_nodes(ExParams p, QtTables t, int nodeCapMax) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const OrbxGeom &g = *p.g;
     const int l = blockIdx.x, b = blockIdx.y;
     const OrbxLevel &LV = g.lv[l];
     const int tid = threadIdx.x;
-    const QtSmem S = qt_smem_layout(nodeCapMax, maxCellsLevel);
+    const QtSmem S = qt_smem_layout(nodeCapMax, 0);
     orbx_sort::elem_t *sortbuf = reinterpret_cast<orbx_sort::elem_t *>(smem_raw + S.sortOff);
     short4 *box[2] = {reinterpret_cast<short4 *>(smem_raw + S.boxOff[0]), reinterpret_cast<short4 *>(smem_raw + S.boxOff[1])};
     int *cnt[2] = {reinterpret_cast<int *>(smem_raw + S.cntOff[0]), reinterpret_cast<int *>(smem_raw + S.cntOff[1])};
@@ -865,147 +981,24 @@ __global__ void __launch_bounds__(NT) k_quadtree_hist(ExParams p, int nodeCapMax
     int *pend = reinterpret_cast<int *>(smem_raw + S.pendOff);
     int *pendIdx = reinterpret_cast<int *>(smem_raw + S.pendIdxOff);
     unsigned *best = reinterpret_cast<unsigned *>(smem_raw + S.bestOff);
-    int *prefix = reinterpret_cast<int *>(smem_raw + S.prefixOff);
     int *scratch = reinterpret_cast<int *>(smem_raw + S.scratchOff);
     int *tmp4 = reinterpret_cast<int *>(smem_raw + S.tmp4Off);
-    // node identity (depth<<24 | index inside the depth) lives in the two halves of tmp4's sibling: reuse `pend`-sized
-    // arrays would alias, so ids get their own storage behind the legacy layout, followed by the final-node table
     unsigned *nid[2] = {reinterpret_cast<unsigned *>(smem_raw + S.total), reinterpret_cast<unsigned *>(smem_raw + S.total + 4 * nodeCapMax)};
-    unsigned short *finalPos = reinterpret_cast<unsigned short *>(smem_raw + S.total + 8 * nodeCapMax);
     __shared__ int sh_size, sh_C, sh_deep;
 
-    const int nCells = LV.nCells;
     const int N = LV.quota;
     const int nIni = LV.nIni;
-    const int *cellCnt = p.cellCnt + (long long)b * g.nCellsTotal + LV.cellBase;
-    const OrbxCell *cells = p.cells + LV.cellBase;
-    const uint32_t *slots = p.slots + (long long)b * g.slotsTotal;
-    float2 *ptXY = p.ptXY + (long long)b * g.slotsTotal + LV.slotBase;
-    uint32_t *ptNode = p.ptNode + (long long)b * g.slotsTotal + LV.slotBase;
-    float4 *sel = p.sel + (long long)b * g.selTotal + LV.selBase;
     int *selCntOut = p.selCnt + b * g.nlevels + l;
-    unsigned *hist = histAll + ((long long)b * g.nlevels + l) * (long long)maxIni * QT_TREE;
-    int *deepOut = deepFlag + b * g.nlevels + l;
-
-    int dbgN = 0;
-#define QT_MARK() do { if (dbg && tid == 0 && l == 0 && b == 0 && dbgN < 30) dbg[dbgN++] = clock64(); } while (0)
-    QT_MARK();
-    if (tid == 0) sh_deep = 0;
-    for (int c = tid; c < nCells; c += NT) prefix[c] = cellCnt[c];
-    __syncthreads();
-    const int nPts = block_exclusive_scan<NT>(prefix, nCells, scratch);
-    if (tid == 0) prefix[nCells] = nPts;
-    if (nPts == 0 || nIni < 1) {
-        if (tid == 0) { *selCntOut = 0; *deepOut = 0; }
-        return;
-    }
-    if (nIni > QT_MAX_INI) {  // very wide images: the general kernel handles them
-        if (tid == 0) *deepOut = 1;
-        return;
-    }
-    QT_MARK();
-    const int treeN = nIni * QT_TREE;
-    for (int i = tid; i < treeN; i += NT) { hist[i] = 0; finalPos[i] = 0; }
-    __syncthreads();
-    QT_MARK();
-
-    // ---- one pass over the candidates: DANI round trips (:871-907), root bin (:584), path to depth QT_DMAX
-    const float sc = LV.sf, inv = __fdiv_rn(1.f, sc);
+    int *deepOut = t.deep + b * g.nlevels + l;
+    if (nIni > QT_MAX_INI || nIni < 1) return;   // flagged by k_qt_prefix: the general kernel handles it
+    const long long tb = ((long long)b * g.nlevels + l) * (long long)t.maxIni * QT_TREE;
+    unsigned *hist = t.hist + tb;
+    unsigned short *finalPos = t.finalPos + tb;
     const float hX = LV.hX;
-    const int nRects = g.nRects;
-    const int offLeaf = qt_off(nIni, QT_DMAX);
     const int rootH = LV.maxBY - ORBX_BORDER;
-    // per-cell facts in shared memory (slot base relative to the level, cell column/row): the only long-latency
-    // access left in the loop is the packed candidate itself, and four of those are in flight per thread
-    int2 *cellInfo = reinterpret_cast<int2 *>(childCnt);   // 16·nodeCap bytes; free until the first pass
-    const bool cellsInSmem = (size_t)nCells * sizeof(int2) <= (size_t)16 * nodeCapMax;
-    if (cellsInSmem)
-        for (int c = tid; c < nCells; c += NT) {
-            const OrbxCell cell = cells[c];
-            cellInfo[c] = make_int2((int)(cell.slot - LV.slotBase), (int)cell.cx | ((int)cell.cy << 16));
-        }
+    if (tid == 0) sh_deep = 0;
     __syncthreads();
-    const uint32_t *lslots = slots + LV.slotBase;
-    for (int i0 = tid; i0 < nPts; i0 += 4 * NT) {
-        int cidx[4];
-        int2 info[4];
-        uint32_t ent[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * NT;
-            int lo = 0, hi = nCells;  // last cell with prefix[c] <= i
-            if (i < nPts)
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (prefix[mid] <= i) lo = mid; else hi = mid;
-                }
-            cidx[u] = lo;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (cellsInSmem) info[u] = cellInfo[cidx[u]];
-            else { const OrbxCell cell = cells[cidx[u]]; info[u] = make_int2((int)(cell.slot - LV.slotBase), (int)cell.cx | ((int)cell.cy << 16)); }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * NT;
-            ent[u] = i < nPts ? lslots[info[u].x + (i - prefix[cidx[u]])] : 0u;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * NT;
-            if (i >= nPts) continue;
-            const uint32_t e = ent[u];
-            const int trips = nCells - cidx[u];   // processing-order index of an OK cell == its index inside the level
-            float x = __fadd_rn((float)(e & 0xff), (float)((info[u].y & 0xffff) * LV.wCell));
-            float y = __fadd_rn((float)((e >> 8) & 0xff), (float)((info[u].y >> 16) * LV.hCell));
-            bool erased = false;
-            for (int t = 0; t < trips; ++t) {
-                const float xs = __fmul_rn(__fadd_rn(x, (float)ORBX_BORDER), sc);
-                const float ys = __fmul_rn(__fadd_rn(y, (float)ORBX_BORDER), sc);
-                if (nRects > 0) {
-                    const int px = __float2int_rn(xs), py = __float2int_rn(ys);
-                    for (int r = 0; r < nRects; ++r) {
-                        const int rx = g.rects[4 * r], ry = g.rects[4 * r + 1];
-                        if (rx <= px && px < rx + g.rects[4 * r + 2] && ry <= py && py < ry + g.rects[4 * r + 3]) {
-                            erased = true;
-                            break;
-                        }
-                    }
-                    if (erased) break;
-                }
-                const float xn = __fsub_rn(__fmul_rn(xs, inv), (float)ORBX_BORDER);
-                const float yn = __fsub_rn(__fmul_rn(ys, inv), (float)ORBX_BORDER);
-                const bool fixed = (xn == x) && (yn == y);
-                x = xn;
-                y = yn;
-                if (fixed) break;
-            }
-            ptXY[i] = make_float2(x, y);
-            if (erased) {
-                ptNode[i] = ORBX_NODE_ERASED;
-                continue;
-            }
-            int bin = (int)__fdiv_rn(x, hX);
-            bin = min(max(bin, 0), nIni - 1);
-            short4 bx;
-            bx.x = (short)(int)__fmul_rn(hX, (float)bin);
-            bx.y = (short)(int)__fmul_rn(hX, (float)(bin + 1));
-            bx.z = 0;
-            bx.w = (short)rootH;
-            unsigned code = (unsigned)bin;
-#pragma unroll
-            for (int d = 0; d < QT_DMAX; ++d) {
-                const int q = qt_quadrant(bx, x, y);
-                bx = qt_child_box(bx, q);
-                code = code * 4u + (unsigned)q;
-            }
-            ptNode[i] = code | ((e >> 16) << 16);
-            atomicAdd(&hist[offLeaf + code], 1u);
-        }
-    }
-    __syncthreads();
-    QT_MARK();
+
     // coarser levels = sums of four children (reads bypass L1: the counts were produced by atomics)
     for (int d = QT_DMAX - 1; d >= 0; --d) {
         const int n = nIni << (2 * d), o = qt_off(nIni, d), oc = qt_off(nIni, d + 1);
@@ -1013,7 +1006,6 @@ __global__ void __launch_bounds__(NT) k_quadtree_hist(ExParams p, int nodeCapMax
             hist[o + i] = __ldcg(&hist[oc + 4 * i]) + __ldcg(&hist[oc + 4 * i + 1]) + __ldcg(&hist[oc + 4 * i + 2]) + __ldcg(&hist[oc + 4 * i + 3]);
         __syncthreads();
     }
-    QT_MARK();
     // initial list: non-empty roots in order (:565-601)
     if (tid == 0) {
         int m = 0;
@@ -1118,11 +1110,9 @@ __global__ void __launch_bounds__(NT) k_quadtree_hist(ExParams p, int nodeCapMax
             if (sh_deep) break;
             // std::sort = serial introsort partitioning (thread 0) + its final insertion sort, which is a stable sort
             // of the partitioned order and is done here as a parallel rank sort
-            QT_MARK();
-            if (tid == 0) orbx_sort::introsort_loop_only(sortbuf, nPend);
+                    if (tid == 0) orbx_sort::introsort_loop_only(sortbuf, nPend);
             __syncthreads();
-            QT_MARK();
-            {
+                    {
                 orbx_sort::elem_t *sorted = reinterpret_cast<orbx_sort::elem_t *>(tmp4);
                 for (int i = tid; i < nPend; i += NT) {
                     const orbx_sort::elem_t e = sortbuf[i];
@@ -1138,28 +1128,38 @@ __global__ void __launch_bounds__(NT) k_quadtree_hist(ExParams p, int nodeCapMax
                 for (int i = tid; i < nPend; i += NT) sortbuf[i] = sorted[i];
                 __syncthreads();
             }
-            QT_MARK();
-            // walk the sorted array from the back until the list reaches N nodes (:701-747)
-            if (tid == 0) {
-                int sz = size, c = 0;
-                for (int j = nPend - 1; j >= 0; --j) {
-                    const int pi = (int)(sortbuf[j] & ((1ull << orbx_sort::kPayloadBits) - 1));
-                    for (int q = 0; q < 4; ++q) {
-                        if (childCnt[4 * pi + q] > 0) { childPos[4 * pi + q] = c++; ++sz; }
-                        else childPos[4 * pi + q] = -1;
-                    }
-                    --sz;
-                    best[pi] = 1;  // processed marker, indexed by pending index
-                    if (sz >= N) {
-                        for (int jj = j - 1; jj >= 0; --jj) best[(int)(sortbuf[jj] & ((1ull << orbx_sort::kPayloadBits) - 1))] = 0;
-                        break;
-                    }
-                }
-                sh_C = c;
-                sh_size = sz;
+                    // walk the sorted array from the back until the list reaches N nodes (:701-747), in parallel: processing
+            // step r handles sorted element nPend-1-r; a scan over the children counts gives every step its creation
+            // index base and the list size after it, the first step reaching N is the break point
+            if (tid == 0) sh_C = nPend - 1;   // break step (all processed unless some step reaches N)
+            for (int r = tid; r < nPend; r += NT) {
+                const int pi = (int)(sortbuf[nPend - 1 - r] & ((1ull << orbx_sort::kPayloadBits) - 1));
+                tmp4[r] = (childCnt[4 * pi] > 0) + (childCnt[4 * pi + 1] > 0) + (childCnt[4 * pi + 2] > 0) + (childCnt[4 * pi + 3] > 0);
             }
             __syncthreads();
-            QT_MARK();
+            block_exclusive_scan<NT>(tmp4, nPend, scratch);
+            for (int r = tid; r < nPend; r += NT) {
+                const int pi = (int)(sortbuf[nPend - 1 - r] & ((1ull << orbx_sort::kPayloadBits) - 1));
+                const int kk = (childCnt[4 * pi] > 0) + (childCnt[4 * pi + 1] > 0) + (childCnt[4 * pi + 2] > 0) + (childCnt[4 * pi + 3] > 0);
+                if (size + tmp4[r] + kk - (r + 1) >= N) atomicMin(&sh_C, r);
+            }
+            __syncthreads();
+            const int rBreak = sh_C;
+            __syncthreads();
+            for (int r = tid; r < nPend; r += NT) {
+                const int pi = (int)(sortbuf[nPend - 1 - r] & ((1ull << orbx_sort::kPayloadBits) - 1));
+                const bool proc = r <= rBreak;
+                best[pi] = proc ? 1u : 0u;  // processed marker, indexed by pending index
+                int c = tmp4[r];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const bool has = childCnt[4 * pi + q] > 0;
+                    childPos[4 * pi + q] = (proc && has) ? c : -1;
+                    c += has;
+                }
+                if (r == rBreak) { sh_C = c; sh_size = size + c - (r + 1); }
+            }
+            __syncthreads();
             const int C = sh_C;
             for (int i = tid; i < size; i += NT) {
                 const int pi = pendIdx[i];
@@ -1190,19 +1190,18 @@ __global__ void __launch_bounds__(NT) k_quadtree_hist(ExParams p, int nodeCapMax
                 }
             }
             __syncthreads();
-            QT_MARK();
-            // next pending list: expandable children in creation order = processing order × child order
-            if (tid == 0) {
-                int np = 0;
-                for (int j = nPend - 1; j >= 0; --j) {
-                    const int pi = (int)(sortbuf[j] & ((1ull << orbx_sort::kPayloadBits) - 1));
-                    if (best[pi] != 1) break;
-                    for (int q = 0; q < 4; ++q)
-                        if (childCnt[4 * pi + q] > 1) pendIdx[np++] = childPos[4 * pi + q];
-                }
-                for (int i = 0; i < np; ++i) pend[i] = pendIdx[i];
-                sh_C = np;
-            }
+                    // next pending list: expandable children in creation order (creation index c = C-1-position)
+            for (int i = tid; i < C; i += NT) tmp4[i] = 0;
+            __syncthreads();
+            for (int i = tid; i < 4 * nPend; i += NT)
+                if (childPos[i] >= 0 && childCnt[i] > 1) tmp4[C - 1 - childPos[i]] = 1;
+            __syncthreads();
+            const int nNext = block_exclusive_scan<NT>(tmp4, C, scratch);
+            for (int i = tid; i < 4 * nPend; i += NT)
+                if (childPos[i] >= 0 && childCnt[i] > 1) pendIdx[tmp4[C - 1 - childPos[i]]] = childPos[i];
+            __syncthreads();
+            for (int i = tid; i < nNext; i += NT) pend[i] = pendIdx[i];
+            if (tid == 0) sh_C = nNext;
             __syncthreads();
             nPend = sh_C;
             size = sh_size;
@@ -1210,40 +1209,63 @@ __global__ void __launch_bounds__(NT) k_quadtree_hist(ExParams p, int nodeCapMax
             if (size >= N || size == prevSize) done = true;
         }
         __syncthreads();
-        QT_MARK();
-    }
+        }
     if (sh_deep) {  // a node deeper than the table would have to be split: hand over to the general kernel
         if (tid == 0) *deepOut = 1;
         return;
     }
 
-    // ---- attach the points to the final nodes and keep the best response per node (:757-776)
-    for (int i = tid; i < size; i += NT) {
-        best[i] = 0;
-        const unsigned id = nid[cur][i];
-        finalPos[qt_off(nIni, id >> 24) + (id & 0xffffffu)] = (unsigned short)(i + 1);
-    }
-    __syncthreads();
-    qt_for_points<false, NT>(ptNode, ptXY, nPts, [&](int i, uint32_t v, float2) {
-        const unsigned leaf = v & 0xffffu;
-#pragma unroll
-        for (int d = 0; d <= QT_DMAX; ++d) {
-            const unsigned pos = finalPos[qt_off(nIni, d) + (leaf >> (2 * (QT_DMAX - d)))];
-            if (pos) {
-                atomicMax(&best[pos - 1], (((v >> 16) & 0xffu) << 24) | (0xffffffu - (unsigned)i));
-                break;
-            }
+
+    // leaf → final node table for k_qt_attach: a final node at depth d owns 4^(QT_DMAX-d) consecutive leaves (leaves under
+    // dropped empty children hold no candidate and are never looked up, so the table needs no clearing)
+    {
+        const int warp = tid >> 5, lane = tid & 31, nWarps = NT / 32;
+        for (int i = warp; i < size; i += nWarps) {
+            const unsigned id = nid[cur][i], d = id >> 24, ix = id & 0xffffffu;
+            const int span = 1 << (2 * (QT_DMAX - d));
+            unsigned short *dst = finalPos + (size_t)ix * span;
+            for (int k = lane; k < span; k += 32) dst[k] = (unsigned short)(i + 1);
         }
-    });
-    __syncthreads();
-    for (int i = tid; i < size; i += NT) {
-        const int order = (int)(0xffffffu - (best[i] & 0xffffffu));
-        const float2 xy = ptXY[order];
-        sel[i] = make_float4(__fadd_rn(xy.x, (float)ORBX_BORDER), __fadd_rn(xy.y, (float)ORBX_BORDER), (float)(best[i] >> 24), 0.f);
     }
-    QT_MARK();
-    if (dbg && tid == 0 && l == 0 && b == 0) dbg[31] = dbgN;
-    if (tid == 0) { *selCntOut = size; *deepOut = 0; }
+    if (tid == 0) *selCntOut = size;
+}
+
+// grid (QT_CLS_BLOCKS, level, frame): every candidate looks up the final node of its depth-QT_DMAX leaf
+__global__ void __launch_bounds__(128) k_qt_attach(ExParams p, QtTables t) {
+    const OrbxGeom &g = *p.g;
+    const int l = blockIdx.y, b = blockIdx.z;
+    if (t.deep[b * g.nlevels + l]) return;           // redone by the general kernel
+    const OrbxLevel &LV = g.lv[l];
+    const int nCells = LV.nCells;
+    if (nCells == 0) return;
+    const int nPts = t.cellPrefix[(long long)b * g.nCellsTotal + LV.cellBase + nCells - 1] + p.cellCnt[(long long)b * g.nCellsTotal + LV.cellBase + nCells - 1];
+    const uint32_t *ptNode = p.ptNode + (long long)b * g.slotsTotal + LV.slotBase;
+    const unsigned short *finalPos = t.finalPos + ((long long)b * g.nlevels + l) * (long long)t.maxIni * QT_TREE;
+    unsigned *best = t.best + (long long)b * g.selTotal + LV.selBase;
+    for (int i = blockIdx.x * 128 + threadIdx.x; i < nPts; i += QT_CLS_BLOCKS * 128) {
+        const uint32_t v = ptNode[i];
+        if (v == ORBX_NODE_ERASED) continue;
+        const unsigned pos = finalPos[v & 0xffffu];
+        // first maximum in insertion order wins: larger key = larger response, then smaller order index
+        if (pos) atomicMax(&best[pos - 1], (((v >> 16) & 0xffu) << 24) | (0xffffffu - (unsigned)i));
+    }
+}
+
+__global__ void __launch_bounds__(128) k_qt_select(ExParams p, QtTables t) {
+    const OrbxGeom &g = *p.g;
+    const int l = blockIdx.x, b = blockIdx.y;
+    if (t.deep[b * g.nlevels + l]) return;           // the general kernel wrote this level's list itself
+    const OrbxLevel &LV = g.lv[l];
+    const int size = p.selCnt[b * g.nlevels + l];
+    const unsigned *best = t.best + (long long)b * g.selTotal + LV.selBase;
+    const float2 *ptXY = p.ptXY + (long long)b * g.slotsTotal + LV.slotBase;
+    float4 *sel = p.sel + (long long)b * g.selTotal + LV.selBase;
+    for (int i = threadIdx.x; i < size; i += 128) {
+        const unsigned k = best[i];
+        const float2 xy = ptXY[0xffffffu - (k & 0xffffffu)];
+        // :919-923 — add the border back; response = FAST score
+        sel[i] = make_float4(__fadd_rn(xy.x, (float)ORBX_BORDER), __fadd_rn(xy.y, (float)ORBX_BORDER), (float)(k >> 24), 0.f);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1592,6 +1614,9 @@ struct orbx_extractor {
     int maxSlotCap = 0, nodeCapMax = 0, maxCellsLevel = 0, maxIni = 1;
     bool useHistQuadtree = true;
     unsigned *d_hist = nullptr; size_t histCap = 0;
+    unsigned short *d_finalPos = nullptr; size_t finalPosCap = 0;
+    unsigned *d_best = nullptr; size_t bestCap = 0;
+    int *d_cellPrefix = nullptr; size_t cellPrefixCap = 0;
     int *d_deep = nullptr;
     long long *d_dbg = nullptr;
     uint8_t *d_stage = nullptr; size_t stageCap = 0;   // packed H2D staging when the level-0 pitch is padded
@@ -1809,6 +1834,9 @@ int ensure_buffers(orbx_extractor *ex, int batch) {
     }
     if ((rc = ensure(ex, ex->d_cellCnt, ex->cellCntCap, B * (size_t)std::max(G.nCellsTotal, 1)))) return rc;
     if ((rc = ensure(ex, ex->d_hist, ex->histCap, B * (size_t)G.nlevels * (size_t)ex->maxIni * QT_TREE))) return rc;
+    if ((rc = ensure(ex, ex->d_finalPos, ex->finalPosCap, B * (size_t)G.nlevels * (size_t)ex->maxIni * QT_TREE))) return rc;
+    if ((rc = ensure(ex, ex->d_best, ex->bestCap, B * (size_t)std::max(G.selTotal, 1)))) return rc;
+    if ((rc = ensure(ex, ex->d_cellPrefix, ex->cellPrefixCap, B * (size_t)std::max(G.nCellsTotal, 1)))) return rc;
     size_t selNeed = B * (size_t)std::max(G.selTotal, 1);
     if (selNeed > ex->selCap || !ex->d_sel) {
         if (ex->d_sel) cudaFree(ex->d_sel);
@@ -1931,31 +1959,49 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
         const QtSmem L = qt_smem_layout(ex->nodeCapMax, ex->maxCellsLevel);
         if (L.total > 200 * 1024) { ex->err = "nfeatures too large for the quadtree kernel's shared memory"; return ORBX_ERR_ARG; }
         dim3 grd(G.nlevels, batch);
-        const size_t smemH = (size_t)L.total + 8 * (size_t)ex->nodeCapMax + 2 * (size_t)ex->maxIni * QT_TREE;
-        const bool useHist = ex->useHistQuadtree && smemH <= 200 * 1024;
-        unsigned *hist = ex->d_hist + f * G.nlevels * (size_t)ex->maxIni * QT_TREE;
-        int *deep = ex->d_deep + f * G.nlevels;
-        // large quotas (4K / thousands of features per level): few, long blocks → 512 threads each
-        const bool big = ex->nodeCapMax > 600;
+        const QtSmem LN = qt_smem_layout(ex->nodeCapMax, 0);
+        const size_t smemN = (size_t)LN.total + 8 * (size_t)ex->nodeCapMax;          // + node identities
+        const bool useHist = ex->useHistQuadtree && smemN <= 200 * 1024;
+        const bool big = ex->nodeCapMax > 600;   // large quotas (4K): few, long blocks → 512 threads each
+        QtTables T;
+        T.maxIni = ex->maxIni;
+        T.hist = ex->d_hist + f * G.nlevels * (size_t)ex->maxIni * QT_TREE;
+        T.finalPos = ex->d_finalPos + f * G.nlevels * (size_t)ex->maxIni * QT_TREE;
+        T.best = ex->d_best + f * G.selTotal;
+        T.cellPrefix = ex->d_cellPrefix + f * G.nCellsTotal;
+        T.deep = ex->d_deep + f * G.nlevels;
+        if (useHist) {
+            const size_t smemP = (size_t)(ex->maxCellsLevel + 1 + QT_THREADS + 2) * sizeof(int);
+            if (smemP > 48 * 1024) CUDA_TRY(ex, cudaFuncSetAttribute(k_qt_prefix<QT_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemP));
+            k_qt_prefix<QT_THREADS><<<grd, QT_THREADS, smemP, s>>>(P, T, ex->maxCellsLevel);
+            dim3 grdC(QT_CLS_BLOCKS, G.nlevels, batch);
+            k_qt_classify<<<grdC, 128, 0, s>>>(P, T);
+            if (big) {
+                if (smemN > 48 * 1024) CUDA_TRY(ex, cudaFuncSetAttribute(k_qt_nodes<QT_THREADS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemN));
+                k_qt_nodes<QT_THREADS_BIG><<<grd, QT_THREADS_BIG, smemN, s>>>(P, T, ex->nodeCapMax);
+            } else {
+                if (smemN > 48 * 1024) CUDA_TRY(ex, cudaFuncSetAttribute(k_qt_nodes<QT_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemN));
+                k_qt_nodes<QT_THREADS><<<grd, QT_THREADS, smemN, s>>>(P, T, ex->nodeCapMax);
+            }
+            ex->launches += 3;
+        }
+        // general kernel: everything when the fast path is off, otherwise only the flagged (frame, level) pairs
         if (big) {
             if (L.total > 48 * 1024) CUDA_TRY(ex, cudaFuncSetAttribute(k_quadtree<QT_THREADS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-            if (useHist) {
-                if (smemH > 48 * 1024) CUDA_TRY(ex, cudaFuncSetAttribute(k_quadtree_hist<QT_THREADS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemH));
-                k_quadtree_hist<QT_THREADS_BIG><<<grd, QT_THREADS_BIG, smemH, s>>>(P, ex->nodeCapMax, ex->maxCellsLevel, ex->maxIni, hist, deep, first == 0 ? ex->d_dbg : nullptr);
-                ++ex->launches;
-            }
-            k_quadtree<QT_THREADS_BIG><<<grd, QT_THREADS_BIG, L.total, s>>>(P, ex->nodeCapMax, ex->maxCellsLevel, useHist ? deep : nullptr);
+            k_quadtree<QT_THREADS_BIG><<<grd, QT_THREADS_BIG, L.total, s>>>(P, ex->nodeCapMax, ex->maxCellsLevel, useHist ? T.deep : nullptr);
         } else {
             if (L.total > 48 * 1024) CUDA_TRY(ex, cudaFuncSetAttribute(k_quadtree<QT_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-            if (useHist) {
-                if (smemH > 48 * 1024) CUDA_TRY(ex, cudaFuncSetAttribute(k_quadtree_hist<QT_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemH));
-                k_quadtree_hist<QT_THREADS><<<grd, QT_THREADS, smemH, s>>>(P, ex->nodeCapMax, ex->maxCellsLevel, ex->maxIni, hist, deep, first == 0 ? ex->d_dbg : nullptr);
-                ++ex->launches;
-            }
-            k_quadtree<QT_THREADS><<<grd, QT_THREADS, L.total, s>>>(P, ex->nodeCapMax, ex->maxCellsLevel, useHist ? deep : nullptr);
+            k_quadtree<QT_THREADS><<<grd, QT_THREADS, L.total, s>>>(P, ex->nodeCapMax, ex->maxCellsLevel, useHist ? T.deep : nullptr);
         }
         ++ex->launches;
-        if (!useHist) CUDA_TRY(ex, cudaMemsetAsync(deep, 0, (size_t)batch * G.nlevels * sizeof(int), s));
+        if (useHist) {
+            dim3 grdC(QT_CLS_BLOCKS, G.nlevels, batch);
+            k_qt_attach<<<grdC, 128, 0, s>>>(P, T);
+            k_qt_select<<<grd, 128, 0, s>>>(P, T);
+            ex->launches += 2;
+        } else {
+            CUDA_TRY(ex, cudaMemsetAsync(T.deep, 0, (size_t)batch * G.nlevels * sizeof(int), s));
+        }
     }
     if (prof) CUDA_TRY(ex, cudaEventRecord(ex->ev[3], s));
     // K7
@@ -2120,7 +2166,7 @@ void orbx_destroy(orbx_extractor *ex) {
     if (ex->stream) cudaStreamSynchronize(ex->stream);
     void *ptrs[] = {ex->d_geom, ex->d_cells, ex->d_tiles, ex->d_tabX, ex->d_tabY, ex->d_tabXOff, ex->d_tabYOff,
                     ex->d_pattern, ex->d_patternF, ex->d_pyr, ex->d_blur, ex->d_slots, ex->d_ptNode, ex->d_ptXY, ex->d_cellCnt,
-                    ex->d_sel, ex->d_work, ex->d_selCnt, ex->d_workCnt, ex->d_hist, ex->d_deep, ex->d_dbg, ex->d_stage, ex->d_kps, ex->d_desc, ex->d_nOut, ex->d_mono};
+                    ex->d_sel, ex->d_work, ex->d_selCnt, ex->d_workCnt, ex->d_hist, ex->d_finalPos, ex->d_best, ex->d_cellPrefix, ex->d_deep, ex->d_dbg, ex->d_stage, ex->d_kps, ex->d_desc, ex->d_nOut, ex->d_mono};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ex->h_nOut) cudaFreeHost(ex->h_nOut);
     if (ex->h_mono) cudaFreeHost(ex->h_mono);
