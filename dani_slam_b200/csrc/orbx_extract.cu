@@ -1159,6 +1159,7 @@ __global__ void __launch_bounds__(NT) k_qt_nodes(ExParams p, QtTables t, int nod
                 }
                 if (r == rBreak) { sh_C = c; sh_size = size + c - (r + 1); }
             }
+            if (tid == 0 && nPend == 0) { sh_C = 0; sh_size = size; }   // nothing left to expand: the list stays as it is
             __syncthreads();
             const int C = sh_C;
             for (int i = tid; i < size; i += NT) {
