@@ -6,8 +6,9 @@
 //   K1 k_pyr_level   ×(L-1)  ComputePyramid :1209-1234 — bilinear 8U resize, 11-bit fixed point
 //   K2 k_fast_cells          cell loop :781-869 — one warp per 35-px cell: FAST-9 score map in smem,
 //                            cell-local NMS, iniTh/minTh retry, row-major ordered candidate list
-//   K3 k_quadtree            DANI filter :871-907 + DistributeOctTree :555-779 — one block per
-//                            (frame, level): exact list-order emulation incl. libstdc++ sort ties
+//   K3 k_qt_* / k_quadtree   DANI filter :871-907 + DistributeOctTree :555-779 — candidates classified once
+//                            into a quadtree histogram, exact list-order emulation on node counts incl.
+//                            libstdc++ sort ties, general single-kernel version as fallback
 //   K7 k_assemble            output ordering :1157-1204 (mono from the front, lapping from the back)
 //   K5 k_blur                GaussianBlur 7×7 σ=2 :1171-1172 — separable integer, REFLECT_101 halo tiles
 //   K4+K6 k_orient_desc      IC_Angle :76-103 + computeOrbDescriptor :107-146 — one warp per keypoint
