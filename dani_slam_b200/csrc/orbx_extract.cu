@@ -192,9 +192,11 @@ __global__ void __launch_bounds__(256) k_pyr_level(PyrArgs a) {
 // for all 16 arcs.  A lane owns 4 horizontally adjacent pixels (two u16x2 pairs); ring samples are
 // carved out of three aligned 32-bit shared-memory words per row with PRMT.
 // ------------------------------------------------------------------------------------------------
+#define FAST_BOTH_CAP 256   // two-sided pixels wait here; flushed (B side evaluated) whenever fewer than 128 slots remain
 struct FastSmem {
     int roiPitch, scorePitch;
-    int roiOff, scoreOff, listOff, queueOff, total;
+    int roiOff, scoreOff, listOff, queueOff, total;     // v1 kernel
+    int entryOff, bothOff, total2;                      // two-phase kernel
 };
 __host__ __device__ inline FastSmem fast_smem_layout(int maxCw, int maxCh, int maxSlotCap) {
     FastSmem s;
@@ -206,6 +208,11 @@ __host__ __device__ inline FastSmem fast_smem_layout(int maxCw, int maxCh, int m
     s.listOff = s.scoreOff + s.scorePitch * (maxCh - 6 + 2);
     s.queueOff = s.listOff + 4 * maxSlotCap;             // u16 per 4-pixel group: groups whose score word is non-zero
     s.total = (s.queueOff + 2 * G * (maxCh - 6) + 15) & ~15;
+    // two-phase kernel: u16 entry per interior pixel (worst case: every pixel passes the compass test), twice
+    const int nPix = 4 * G * (maxCh - 6);
+    s.entryOff = (s.listOff + 3) & ~3;
+    s.bothOff = s.entryOff + 2 * nPix + 4;
+    s.total2 = (s.bothOff + 2 * FAST_BOTH_CAP + 15) & ~15;
     return s;
 }
 
@@ -267,7 +274,7 @@ __device__ __forceinline__ uint32_t fast_pair_score(const Row3 (&R)[7], uint32_t
 }
 
 template <int WPB>
-__global__ void __launch_bounds__(WPB * 32) k_fast_cells(ExParams p, int maxSlotCap) {
+__global__ void __launch_bounds__(WPB * 32) k_fast_cells_v1(ExParams p, int maxSlotCap) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const OrbxGeom &g = *p.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -413,6 +420,246 @@ __global__ void __launch_bounds__(WPB * 32) k_fast_cells(ExParams p, int maxSlot
         const uint32_t bal = __ballot_sync(0xffffffffu, keep);
         if (keep) out[m + __popc(bal & ((1u << lane) - 1))] = e;
         m += __popc(bal);
+    }
+    if (lane == 0) *cntOut = m;
+}
+
+// ---- two-phase FAST: compass pre-test on every pixel, exact measure only for the pixels that pass ----
+// An arc of 9 contiguous ring pixels contains at least one of every opposite pair {k, k+8}, so
+//   A = max_arcs min_k (v - r_k) <= min(max(v-r0, v-r8), max(v-r4, v-r12))   (and the same for B with r - v):
+// a pixel whose compass bound is <= t on both sides cannot be a corner at threshold t (the high-speed test of the
+// FAST paper, here in exact score form).  About a third of the pixels of a corner-dense frame pass; they are
+// compacted into a per-cell queue of (pixel, side) entries and the exact measure is evaluated two entries per lane:
+// for side B the ring and the centre are complemented (255 - x), which turns B into the same min-of-window-max form
+// as A, so one packed u16x2 op sequence serves any mix of sides.
+struct FastEntryRing { uint32_t x[16]; uint32_t v; };
+
+__device__ __forceinline__ uint32_t fast_window_minmax(const uint32_t (&r)[16]) {
+    uint32_t tmx[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) tmx[k] = __vimax3_u16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+    uint32_t nmx[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) nmx[k] = __vimax3_u16x2(tmx[k], tmx[(k + 3) & 15], tmx[(k + 6) & 15]);   // max of ring[k..k+8]
+    uint32_t lo = __vimin3_u16x2(nmx[0], nmx[1], nmx[2]);
+#pragma unroll
+    for (int k = 3; k < 15; k += 2) lo = __vimin3_u16x2(lo, nmx[k], nmx[k + 1]);
+    return __vminu2(lo, nmx[15]);
+}
+
+// exact measure for the entries of q[0..nE): writes max(M_side - t, 0) into the score map.  PUSH: compact the
+// offsets of the non-zero results, in order, into q itself (in place: position <= entries consumed) and return
+// their count.  Entry: bits 0-13 ROI byte offset of the pixel, bit 14 "other side already in the map", bit 15 side.
+template <bool PUSH>
+__device__ __forceinline__ int fast_exact_entries(const uint8_t *roi, uint8_t *score, uint16_t *q, int nE, int rp, uint32_t biasT2, int lane) {
+    int nN = 0;
+    const int rp2 = 2 * rp, rp3 = 3 * rp;
+    for (int i0 = 0; i0 < nE; i0 += 64) {
+        // lane i takes entries i0+i and i0+32+i: the 32 entries one LDS serves are consecutive in row-major order
+        // (they span ~3 ROI rows), which keeps shared-memory bank conflicts low
+        const int j0 = i0 + lane, j1 = j0 + 32;
+        const bool ok0 = j0 < nE, ok1 = j1 < nE;
+        const uint32_t e0 = q[ok0 ? j0 : 0], e1 = ok1 ? (uint32_t)q[j1] : e0;
+        if (PUSH) __syncwarp();                       // all lanes hold their entries before anyone compacts into q
+        const int o0 = (int)(e0 & 0x3fffu), o1 = (int)(e1 & 0x3fffu);
+        // x = r*sg + c per half: side A (bit 15 clear) keeps r, side B takes 255 - r
+        const int sg0 = (e0 & 0x8000u) ? -1 : 1, sg1 = (e1 & 0x8000u) ? -65536 : 65536;
+        const uint32_t cc = ((e0 & 0x8000u) ? 255u : 0u) | ((e1 & 0x8000u) ? (255u << 16) : 0u);
+        const uint8_t *p0 = roi + o0, *p1 = roi + o1;
+        uint32_t r[16];
+#define ORBX_RING(k, dx, dyoff) r[k] = (uint32_t)((int)p1[(dyoff) + (dx)] * sg1 + ((int)p0[(dyoff) + (dx)] * sg0 + (int)cc));
+        ORBX_RING(0, 0, rp3)   ORBX_RING(1, 1, rp3)   ORBX_RING(2, 2, rp2)    ORBX_RING(3, 3, rp)
+        ORBX_RING(4, 3, 0)     ORBX_RING(5, 3, -rp)   ORBX_RING(6, 2, -rp2)   ORBX_RING(7, 1, -rp3)
+        ORBX_RING(8, 0, -rp3)  ORBX_RING(9, -1, -rp3) ORBX_RING(10, -2, -rp2) ORBX_RING(11, -3, -rp)
+        ORBX_RING(12, -3, 0)   ORBX_RING(13, -3, rp)  ORBX_RING(14, -2, rp2)  ORBX_RING(15, -1, rp3)
+        const uint32_t v2 = (uint32_t)((int)p1[0] * sg1 + ((int)p0[0] * sg0 + (int)cc));
+#undef ORBX_RING
+        const uint32_t lo = fast_window_minmax(r);
+        const uint32_t M = (v2 + 0x01000100u) - lo;              // M_side + 256 per half, in [1, 511]
+        const uint32_t val2 = __vmaxu2(M, biasT2) - biasT2;      // max(M_side - t, 0)
+        uint32_t val0 = val2 & 0xffffu, val1 = val2 >> 16;
+        uint8_t *s0 = score + o0 - rp2, *s1 = score + o1 - rp2;  // score pitch == ROI pitch, two rows up
+        if (e0 & 0x4000u) val0 = max(val0, (uint32_t)*s0);
+        if (e1 & 0x4000u) val1 = max(val1, (uint32_t)*s1);
+        if (ok0) *s0 = (uint8_t)val0;
+        if (ok1) *s1 = (uint8_t)val1;
+        if (PUSH) {
+            const bool k0 = ok0 && val0 != 0, k1 = ok1 && val1 != 0;
+            const uint32_t b0 = __ballot_sync(0xffffffffu, k0), b1 = __ballot_sync(0xffffffffu, k1);
+            const uint32_t lt = (1u << lane) - 1u;
+            const int n0 = __popc(b0);
+            if (k0) q[nN + __popc(b0 & lt)] = (uint16_t)o0;
+            if (k1) q[nN + n0 + __popc(b1 & lt)] = (uint16_t)o1;
+            nN += n0 + __popc(b1);
+        }
+    }
+    return nN;
+}
+
+template <int WPB>
+__global__ void __launch_bounds__(WPB * 32) k_fast_cells(ExParams p, int maxSlotCap) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const OrbxGeom &g = *p.g;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * WPB + warp, b = blockIdx.y;
+    if (c >= g.nCellsTotal) return;  // warps are independent: no block-level barrier below
+    const OrbxCell cell = p.cells[c];
+    const FastSmem L = fast_smem_layout(g.maxCw, g.maxCh, maxSlotCap);
+    uint8_t *base = smem_raw + (size_t)warp * L.total2;
+    uint8_t *roi = base + L.roiOff;
+    uint8_t *score = base + L.scoreOff;
+    uint16_t *queue = reinterpret_cast<uint16_t *>(base + L.entryOff);
+    uint16_t *both = reinterpret_cast<uint16_t *>(base + L.bothOff);
+
+    int pitch;
+    const uint8_t *img = level_ptr(p, g, cell.level, b, pitch);
+    const int cw = cell.cw, ch = cell.ch;
+    const int iw = cw - 6, ih = ch - 6;
+    int *cntOut = p.cellCnt + (long long)b * g.nCellsTotal + c;
+    if (iw <= 0 || ih <= 0) {  // ROI smaller than 7×7: cv::FAST finds nothing
+        if (lane == 0) *cntOut = 0;
+        return;
+    }
+    const int rp = L.roiPitch;   // == score pitch
+    // stage the ROI: column x at byte x+1 so that every 4-pixel group is word aligned
+    const uint8_t *src = img + (long long)cell.y0 * pitch + cell.x0;
+    if (((((unsigned long long)img) | (unsigned)pitch) & 3ull) == 0) {
+        // aligned 32-bit loads: shared-memory word k of a row holds image columns x0-1+4k .. x0+2+4k, i.e. the two
+        // aligned global words around it funnel-shifted by the (cell-uniform) misalignment; (row, word) items are
+        // flattened over the lanes and four items are in flight per lane
+        const int mis = (cell.x0 - 1) & 3;
+        const uint32_t *gsrc = reinterpret_cast<const uint32_t *>(src - 1 - mis);
+        const int pitchW = pitch >> 2;
+        const int nW = (cw + 4) >> 2;
+        const int items = nW * ch;
+        const uint32_t rcpW = (65536u + nW - 1) / nW;   // (i*rcpW)>>16 == i/nW for i < 3449 (cells are ≤ 20 words × 76 rows)
+        uint32_t *roi32 = reinterpret_cast<uint32_t *>(roi);
+        const int rpW = rp >> 2;
+#pragma unroll 4
+        for (int i = lane; i < items; i += 32) {
+            const int y = (int)(((uint32_t)i * rcpW) >> 16), k = i - y * nW;
+            const uint32_t *q = gsrc + (long long)y * pitchW + k;
+            const uint32_t a = q[0], bq = q[1];
+            roi32[y * rpW + k] = __funnelshift_r(a, bq, 8 * mis);
+        }
+    } else {
+        for (int y = 0; y < ch; ++y)
+            for (int x = lane; x < cw; x += 32) roi[y * rp + x + 1] = src[(long long)y * pitch + x];
+    }
+    // zero the score map: pixels that never pass the compass test and the 1-px frame ("outside the cell interior
+    // counts 0") must read 0 in the NMS
+    {
+        uint32_t *s32 = reinterpret_cast<uint32_t *>(score);
+        const int nw = (rp * (ih + 2)) >> 2;
+        for (int i = lane; i < nw; i += 32) s32[i] = 0;
+    }
+    __syncwarp();
+
+    const int G = (iw + 3) >> 2;             // 4-pixel groups per interior row (≤ 19 for cells ≤ 75 px wide)
+    const int nGroups = G * ih;              // groups of the cell in row-major order: lane work items
+    const uint32_t rcpG = (65536u + G - 1) / G;   // (i*rcpG)>>16 == i/G for i < 3449 (cells are ≤ 19×69 groups)
+    const uint32_t rcpRp = (uint32_t)((0x100000000ull + (unsigned)rp - 1) / (unsigned)rp);   // umulhi(o, rcpRp) == o/rp
+    const uint32_t lt = (1u << lane) - 1u;
+    const int rp3 = 3 * rp;
+    const int stepRows = 32 / G, stepGroups = 32 - stepRows * G;          // 32 groups further on
+    const int stepOff = stepRows * rp + 4 * stepGroups, wrapOff = rp - 4 * G;
+    const int nValidLast = iw - 4 * (G - 1);                               // valid pixels of a row's last group (1..4)
+    const uint32_t lastMask = nValidLast >= 4 ? 0x80808080u : (0x80808080u & ((1u << (8 * nValidLast)) - 1u));
+    uint32_t *out = p.slots + (long long)b * g.slotsTotal + cell.slot;
+    int m = 0;
+    // the reference runs cv::FAST at iniThFAST and, when that leaves nothing after NMS, again at minThFAST (:826-846)
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const int t = attempt == 0 ? g.iniTh : g.minTh;
+        if (attempt == 1 && !(g.minTh < g.iniTh)) break;   // a higher threshold cannot un-suppress anything: stays empty
+        const uint32_t biasT2 = (uint32_t)(256 + t) * 0x10001u;
+        const uint32_t kT = (uint32_t)(0x8000 - t - 1) * 0x10001u;
+
+        // phase 1: compass test, entries in row-major pixel order.  Lane state (lg, off) of group gi = i0 + lane is
+        // advanced incrementally: +32 groups = +stepRows rows and +stepGroups groups, with one conditional row wrap.
+        int nE = 0, nB = 0;
+        int lg = lane - (int)(((uint32_t)lane * rcpG) >> 16) * G;
+        int off = ((int)(((uint32_t)lane * rcpG) >> 16) + 3) * rp + 4 * lg + 4;    // ROI byte of the group's first pixel
+        for (int i0 = 0; i0 < nGroups; i0 += 32) {
+            if (nB > FAST_BOTH_CAP - 128) {           // warp-uniform: make room for this iteration's two-sided pixels
+                __syncwarp();
+                fast_exact_entries<false>(roi, score, both, nB, rp, biasT2, lane);
+                __syncwarp();
+                nB = 0;
+            }
+            uint32_t pm = 0, tq = 0, bo = 0;     // per pixel i: bit 8i+7 (pass / side B) and 8i+6 (two-sided)
+            if (i0 + lane < nGroups) {
+                const uint8_t *cp = roi + off;
+                Row3 Cn = ld_row3(cp - 4), Tp, Bt;
+                Tp.w1 = *reinterpret_cast<const uint32_t *>(cp - rp3);
+                Bt.w1 = *reinterpret_cast<const uint32_t *>(cp + rp3);
+                Tp.w0 = Tp.w2 = Bt.w0 = Bt.w2 = 0;
+                uint32_t XA[2], XB[2];
+#pragma unroll
+                for (int P = 0; P < 2; ++P) {
+                    const uint32_t v2 = P ? pair_at<6>(Cn) : pair_at<4>(Cn);
+                    const uint32_t r0 = P ? pair_at<6>(Bt) : pair_at<4>(Bt), r8 = P ? pair_at<6>(Tp) : pair_at<4>(Tp);
+                    const uint32_t r4 = P ? pair_at<9>(Cn) : pair_at<7>(Cn), r12 = P ? pair_at<3>(Cn) : pair_at<1>(Cn);
+                    const uint32_t hiMin = __vmaxu2(__vminu2(r0, r8), __vminu2(r4, r12));   // A-side bound: v - hiMin
+                    const uint32_t loMax = __vminu2(__vmaxu2(r0, r8), __vmaxu2(r4, r12));   // B-side bound: loMax - v
+                    XA[P] = (v2 + kT) - hiMin;       // bit 15 of a half ⇔ bound > t (no borrow crosses the halves)
+                    XB[P] = (loMax + kT) - v2;
+                }
+                const uint32_t colMask = lg == G - 1 ? lastMask : 0x80808080u;
+                const uint32_t pA = __byte_perm(XA[0], XA[1], 0x7531u);       // high bytes of the four halves: px0..px3
+                const uint32_t pB = __byte_perm(XB[0], XB[1], 0x7531u);
+                pm = (pA | pB) & colMask;
+                bo = pA & pB & colMask;
+                tq = (pm & ~pA) | (bo >> 1);         // entry flag bits of pixel i at 8i+7 (side) and 8i+6 (two-sided)
+            }
+            const int cnt = __popc(pm);
+            const uint32_t b0 = __ballot_sync(0xffffffffu, cnt & 1), b1 = __ballot_sync(0xffffffffu, cnt & 2), b2 = __ballot_sync(0xffffffffu, cnt & 4);
+            uint16_t *qa = queue + nE + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
+            if (pm & 0x80u) *qa++ = (uint16_t)((uint32_t)off | ((tq << 8) & 0xc000u));
+            if (pm & 0x8000u) *qa++ = (uint16_t)((uint32_t)(off + 1) | (tq & 0xc000u));
+            if (pm & 0x800000u) *qa++ = (uint16_t)((uint32_t)(off + 2) | ((tq >> 8) & 0xc000u));
+            if (pm & 0x80000000u) *qa = (uint16_t)((uint32_t)(off + 3) | ((tq >> 16) & 0xc000u));
+            nE += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+            if (__any_sync(0xffffffffu, bo != 0)) {   // rare: pixels that pass on both sides get their B side done first
+                const int cb = __popc(bo);
+                const uint32_t c0 = __ballot_sync(0xffffffffu, cb & 1), c1 = __ballot_sync(0xffffffffu, cb & 2), c2 = __ballot_sync(0xffffffffu, cb & 4);
+                int ab = nB + __popc(c0 & lt) + 2 * __popc(c1 & lt) + 4 * __popc(c2 & lt);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if ((bo >> (8 * i + 7)) & 1u) both[ab++] = (uint16_t)((uint32_t)(off + i) | 0x8000u);
+                nB += __popc(c0) + 2 * __popc(c1) + 4 * __popc(c2);
+            }
+            lg += stepGroups; off += stepOff;
+            if (lg >= G) { lg -= G; off += wrapOff; }
+        }
+        __syncwarp();
+        // phase 2: exact measure of the entries (B sides of two-sided pixels first, then everything else)
+        if (nB > 0) {
+            fast_exact_entries<false>(roi, score, both, nB, rp, biasT2, lane);
+            __syncwarp();
+        }
+        const int nN = fast_exact_entries<true>(roi, score, queue, nE, rp, biasT2, lane);
+        __syncwarp();
+        // phase 3: cell-local 3×3 strict NMS of the corners, survivors in row-major order straight to the slots
+        for (int i0 = 0; i0 < nN; i0 += 32) {
+            const int i = i0 + lane;
+            bool keep = false;
+            uint32_t e = 0;
+            if (i < nN) {
+                const int o = (int)queue[i];
+                const uint8_t *sc = score + o - 2 * rp;
+                const uint32_t cv = sc[0];
+                const uint32_t n8 = __vimax3_u32(__vimax3_u32(sc[-rp - 1], sc[-rp], sc[-rp + 1]), __vimax3_u32(sc[rp - 1], sc[rp], sc[rp + 1]),
+                                                 max((uint32_t)sc[-1], (uint32_t)sc[1]));
+                keep = cv > n8;
+                const int y = (int)__umulhi((uint32_t)o, rcpRp), x = o - y * rp - 1;     // ROI coordinates
+                e = (uint32_t)x | ((uint32_t)y << 8) | ((cv + (uint32_t)(t - 1)) << 16);  // FAST score = M - 1
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+            if (keep) out[m + __popc(bal & lt)] = e;
+            m += __popc(bal);
+        }
+        if (m > 0) break;
+        __syncwarp();
     }
     if (lane == 0) *cntOut = m;
 }
@@ -1615,6 +1862,7 @@ struct orbx_extractor {
     std::vector<BlurTile> h_tiles;
     int maxSlotCap = 0, nodeCapMax = 0, maxCellsLevel = 0, maxIni = 1;
     bool useHistQuadtree = true;
+    bool fastV1 = false;            // ORBX_FAST_V1: single-phase FAST kernel (every pixel gets the exact measure)
     unsigned *d_hist = nullptr; size_t histCap = 0;
     unsigned short *d_finalPos = nullptr; size_t finalPosCap = 0;
     unsigned *d_best = nullptr; size_t bestCap = 0;
@@ -1945,13 +2193,16 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
     {
         const int WPB = 4;
         const FastSmem L = fast_smem_layout(G.maxCw, G.maxCh, ex->maxSlotCap);
-        const size_t smem = (size_t)L.total * WPB;
+        const bool v1 = ex->fastV1;
+        const size_t smem = (size_t)(v1 ? L.total : L.total2) * WPB;
         if (smem > 48 * 1024) {
-            CUDA_TRY(ex, cudaFuncSetAttribute(k_fast_cells<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (v1) CUDA_TRY(ex, cudaFuncSetAttribute(k_fast_cells_v1<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            else CUDA_TRY(ex, cudaFuncSetAttribute(k_fast_cells<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
         dim3 grd((G.nCellsTotal + WPB - 1) / WPB, batch);
         if (G.nCellsTotal > 0) {
-            k_fast_cells<WPB><<<grd, WPB * 32, smem, s>>>(P, ex->maxSlotCap);
+            if (v1) k_fast_cells_v1<WPB><<<grd, WPB * 32, smem, s>>>(P, ex->maxSlotCap);
+            else k_fast_cells<WPB><<<grd, WPB * 32, smem, s>>>(P, ex->maxSlotCap);
             ++ex->launches;
         }
     }
@@ -2147,6 +2398,7 @@ orbx_extractor *orbx_create(int nfeatures, float scale_factor, int nlevels, int 
     CREATE_TRY(cudaMalloc((void **)&ex->d_workCnt, (size_t)max_batch * sizeof(int)));
     CREATE_TRY(cudaMalloc((void **)&ex->d_deep, (size_t)max_batch * ORBX_MAX_LEVELS * sizeof(int)));
     ex->useHistQuadtree = getenv("ORBX_LEGACY_QUADTREE") == nullptr;
+    ex->fastV1 = getenv("ORBX_FAST_V1") != nullptr;
     if (getenv("ORBX_DEBUG_TIMELINE")) { CREATE_TRY(cudaMalloc((void **)&ex->d_dbg, 32 * sizeof(long long))); CREATE_TRY(cudaMemset(ex->d_dbg, 0, 32 * sizeof(long long))); }
     CREATE_TRY(cudaMalloc((void **)&ex->d_nOut, (size_t)max_batch * sizeof(int)));
     CREATE_TRY(cudaMalloc((void **)&ex->d_mono, (size_t)max_batch * sizeof(int)));
