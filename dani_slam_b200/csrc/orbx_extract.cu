@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -1836,7 +1837,8 @@ thread_local std::string tl_error;
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-#define ORBX_MAX_CHUNKS 8
+#define ORBX_MAX_CHUNKS 20
+#define ORBX_MAX_SIDE 4
 struct orbx_extractor {
     int device = 0;
     int nfeatures = 0, nlevels = 0, iniTh = 0, minTh = 0;
@@ -1845,8 +1847,9 @@ struct orbx_extractor {
     float sf[ORBX_MAX_LEVELS], inv[ORBX_MAX_LEVELS], sig2[ORBX_MAX_LEVELS], invsig2[ORBX_MAX_LEVELS];
     int quota[ORBX_MAX_LEVELS];
     int umax[ORBX_HALF_PATCH + 1];
-    cudaStream_t stream = nullptr, sH2D = nullptr, sD2H = nullptr, sSideA = nullptr, sSideB = nullptr;
-    cudaEvent_t evFork = nullptr, evJoin[2] = {nullptr, nullptr};
+    cudaStream_t stream = nullptr, sH2D = nullptr, sD2H = nullptr, sSide[ORBX_MAX_SIDE] = {};
+    int nSide = 2, nSub = 4, nSteady = 8;     // side streams in use, sub-batches of the device path, steady chunks of the host path
+    cudaEvent_t evFork = nullptr, evJoin[ORBX_MAX_SIDE] = {};
     cudaEvent_t evIn[ORBX_MAX_CHUNKS] = {}, evOut[ORBX_MAX_CHUNKS] = {};
     std::string err;
     long long launches = 0;
@@ -2287,21 +2290,21 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
 int run_batch(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, int in0Pitch, int batch, orbx_keypoint *d_kps,
               uint8_t *d_desc, int cap, int *d_nOut, int *d_mono) {
     ex->lastBatch = 0;
-    const int nSub = ex->profiling ? 1 : (batch >= 128 ? 4 : (batch >= 32 ? 2 : 1));
+    const int nSub = ex->profiling ? 1 : (batch >= 128 ? ex->nSub : (batch >= 32 ? 2 : 1));
     if (nSub == 1) return run_pipeline(ex, in0, in0Stride, in0Pitch, batch, d_kps, d_desc, cap, d_nOut, d_mono);
-    cudaStream_t side[2] = {ex->sSideA, ex->sSideB};
+    cudaStream_t *side = ex->sSide;
+    const int nSide = ex->nSide;
     CUDA_TRY(ex, cudaEventRecord(ex->evFork, ex->stream));
-    CUDA_TRY(ex, cudaStreamWaitEvent(side[0], ex->evFork, 0));
-    CUDA_TRY(ex, cudaStreamWaitEvent(side[1], ex->evFork, 0));
+    for (int i = 0; i < nSide; ++i) CUDA_TRY(ex, cudaStreamWaitEvent(side[i], ex->evFork, 0));
     const int sub = (batch + nSub - 1) / nSub;
     int k = 0;
     for (int c0 = 0; c0 < batch; c0 += sub, ++k) {
         const int cn = std::min(sub, batch - c0);
         int rc = run_pipeline(ex, in0 + (long long)c0 * in0Stride, in0Stride, in0Pitch, cn, d_kps + (size_t)c0 * cap,
-                              d_desc + (size_t)c0 * cap * 32, cap, d_nOut + c0, d_mono + c0, c0, side[k & 1]);
+                              d_desc + (size_t)c0 * cap * 32, cap, d_nOut + c0, d_mono + c0, c0, side[k % nSide]);
         if (rc) return rc;
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < nSide; ++i) {
         CUDA_TRY(ex, cudaEventRecord(ex->evJoin[i], side[i]));
         CUDA_TRY(ex, cudaStreamWaitEvent(ex->stream, ex->evJoin[i], 0));
     }
@@ -2371,14 +2374,16 @@ orbx_extractor *orbx_create(int nfeatures, float scale_factor, int nlevels, int 
     CREATE_TRY(cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking));
     CREATE_TRY(cudaStreamCreateWithFlags(&ex->sH2D, cudaStreamNonBlocking));
     CREATE_TRY(cudaStreamCreateWithFlags(&ex->sD2H, cudaStreamNonBlocking));
-    CREATE_TRY(cudaStreamCreateWithFlags(&ex->sSideA, cudaStreamNonBlocking));
-    CREATE_TRY(cudaStreamCreateWithFlags(&ex->sSideB, cudaStreamNonBlocking));
+    for (int i = 0; i < ORBX_MAX_SIDE; ++i) CREATE_TRY(cudaStreamCreateWithFlags(&ex->sSide[i], cudaStreamNonBlocking));
+    if (const char *e = getenv("ORBX_NSIDE")) ex->nSide = std::min(ORBX_MAX_SIDE, std::max(1, atoi(e)));        // developer knobs
+    if (const char *e = getenv("ORBX_NSUB")) ex->nSub = std::min(16, std::max(1, atoi(e)));
+    if (const char *e = getenv("ORBX_NSTEADY")) ex->nSteady = std::min(ORBX_MAX_CHUNKS - 2, std::max(1, atoi(e)));
     CREATE_TRY(cudaEventCreateWithFlags(&ex->evFork, cudaEventDisableTiming));
-    CREATE_TRY(cudaEventCreateWithFlags(&ex->evJoin[0], cudaEventDisableTiming));
-    CREATE_TRY(cudaEventCreateWithFlags(&ex->evJoin[1], cudaEventDisableTiming));
+    for (int i = 0; i < ORBX_MAX_SIDE; ++i) CREATE_TRY(cudaEventCreateWithFlags(&ex->evJoin[i], cudaEventDisableTiming));
     for (int i = 0; i < ORBX_MAX_CHUNKS; ++i) {
-        CREATE_TRY(cudaEventCreateWithFlags(&ex->evIn[i], cudaEventDisableTiming));
-        CREATE_TRY(cudaEventCreateWithFlags(&ex->evOut[i], cudaEventDisableTiming));
+        const unsigned evFlags = getenv("ORBX_DEBUG_CHUNKS") ? cudaEventDefault : cudaEventDisableTiming;
+        CREATE_TRY(cudaEventCreateWithFlags(&ex->evIn[i], evFlags));
+        CREATE_TRY(cudaEventCreateWithFlags(&ex->evOut[i], evFlags));
     }
     CREATE_TRY(cudaMalloc((void **)&ex->d_geom, sizeof(OrbxGeom)));
     CREATE_TRY(cudaMalloc((void **)&ex->d_tabXOff, ORBX_MAX_LEVELS * sizeof(int)));
@@ -2427,9 +2432,8 @@ void orbx_destroy(orbx_extractor *ex) {
     for (int i = 0; i < 7; ++i) if (ex->ev[i]) cudaEventDestroy(ex->ev[i]);
     for (int i = 0; i < ORBX_MAX_CHUNKS; ++i) { if (ex->evIn[i]) cudaEventDestroy(ex->evIn[i]); if (ex->evOut[i]) cudaEventDestroy(ex->evOut[i]); }
     if (ex->evFork) cudaEventDestroy(ex->evFork);
-    for (int i = 0; i < 2; ++i) if (ex->evJoin[i]) cudaEventDestroy(ex->evJoin[i]);
-    if (ex->sSideA) { cudaStreamSynchronize(ex->sSideA); cudaStreamDestroy(ex->sSideA); }
-    if (ex->sSideB) { cudaStreamSynchronize(ex->sSideB); cudaStreamDestroy(ex->sSideB); }
+    for (int i = 0; i < ORBX_MAX_SIDE; ++i) if (ex->evJoin[i]) cudaEventDestroy(ex->evJoin[i]);
+    for (int i = 0; i < ORBX_MAX_SIDE; ++i) if (ex->sSide[i]) { cudaStreamSynchronize(ex->sSide[i]); cudaStreamDestroy(ex->sSide[i]); }
     if (ex->sH2D) cudaStreamDestroy(ex->sH2D);
     if (ex->sD2H) cudaStreamDestroy(ex->sD2H);
     if (ex->stream) cudaStreamDestroy(ex->stream);
@@ -2489,15 +2493,27 @@ int orbx_extract_batch(orbx_extractor *ex, const uint8_t *const *images, int bat
         // Software pipeline over chunks of the batch: H2D of chunk k+1 and D2H of chunk k-1 overlap the kernels
         // of chunk k (three streams, events between them).  PCIe moves 307 KB in and ~64 KB out per frame, about
         // half of the kernel time at 640x480, so the copies hide completely behind the compute stream.
-        const int nChunks = nb >= 256 ? ORBX_MAX_CHUNKS : (nb >= 64 ? 4 : 1);
-        const int chunk = (nb + nChunks - 1) / nChunks;
+        // The first two chunks are short (1/32 and 3/32 of the batch) so that the kernels start after a brief copy;
+        // the rest is split evenly.
+        int chunkLen[ORBX_MAX_CHUNKS];
+        int nChunks = 0;
+        if (nb >= 256) {
+            chunkLen[nChunks++] = nb / 32;
+            chunkLen[nChunks++] = nb * 3 / 32;
+            int left = nb - chunkLen[0] - chunkLen[1];
+            for (int i = ex->nSteady; i > 0; --i) { const int c = (left + i - 1) / i; chunkLen[nChunks++] = c; left -= c; }
+        } else {
+            const int parts = nb >= 64 ? 4 : 1;
+            int left = nb;
+            for (int i = parts; i > 0; --i) { const int c = (left + i - 1) / i; chunkLen[nChunks++] = c; left -= c; }
+        }
         cudaStream_t sC = ex->stream, sIn = ex->sH2D, sOut = ex->sD2H;
         // earlier asynchronous work of this handle must be finished before its buffers are refilled
         CUDA_TRY(ex, cudaEventRecord(ex->evOut[0], sC));
         CUDA_TRY(ex, cudaStreamWaitEvent(sIn, ex->evOut[0], 0));
-        int k = 0;
-        for (int c0 = 0; c0 < nb; c0 += chunk, ++k) {
-            const int cn = std::min(chunk, nb - c0);
+        for (int k = 0, c0 = 0; k < nChunks; c0 += chunkLen[k], ++k) {
+            const int cn = chunkLen[k];
+            if (cn <= 0) continue;
             bool contiguous = true;
             for (int b = 1; b < cn && contiguous; ++b)
                 contiguous = images[b0 + c0 + b] == images[b0 + c0] + (size_t)b * rows * step;
@@ -2525,7 +2541,7 @@ int orbx_extract_batch(orbx_extractor *ex, const uint8_t *const *images, int bat
                     CUDA_TRY(ex, cudaMemcpy2DAsync(lvl0 + (size_t)b * G.frameBytes, G.lv[0].pitch, images[b0 + c0 + b], step, cols, rows,
                                                    cudaMemcpyHostToDevice, sIn));
             }
-            cudaStream_t sK = (nChunks > 1 && !ex->profiling) ? ((k & 1) ? ex->sSideB : ex->sSideA) : sC;   // chunks alternate streams
+            cudaStream_t sK = (nChunks > 1 && !ex->profiling) ? ex->sSide[k % ex->nSide] : sC;   // chunks rotate over the side streams
             CUDA_TRY(ex, cudaEventRecord(ex->evIn[k], sIn));
             CUDA_TRY(ex, cudaStreamWaitEvent(sK, ex->evIn[k], 0));
             ex->lastIn0Internal = true;
@@ -2543,9 +2559,19 @@ int orbx_extract_batch(orbx_extractor *ex, const uint8_t *const *images, int bat
                                          cudaMemcpyDeviceToHost, sOut));
         }
         CUDA_TRY(ex, cudaStreamSynchronize(sOut));
-        CUDA_TRY(ex, cudaStreamSynchronize(ex->sSideA));
-        CUDA_TRY(ex, cudaStreamSynchronize(ex->sSideB));
+        for (int i = 0; i < ex->nSide; ++i) CUDA_TRY(ex, cudaStreamSynchronize(ex->sSide[i]));
         CUDA_TRY(ex, cudaStreamSynchronize(sC));
+        if (getenv("ORBX_DEBUG_CHUNKS") && nChunks > 1) {   // developer aid: when each chunk's copy-in and kernels finished
+            fprintf(stderr, "[orbx chunks]");
+            for (int k = 1; k < nChunks; ++k) {
+                float a = 0, c = 0;
+                cudaEventElapsedTime(&a, ex->evIn[0], ex->evIn[k]);
+                cudaEventElapsedTime(&c, ex->evIn[0], ex->evOut[k]);
+                fprintf(stderr, " %d:in+%.2f,out+%.2f", chunkLen[k], a, c);
+            }
+            float c0ms = 0; cudaEventElapsedTime(&c0ms, ex->evIn[0], ex->evOut[0]);
+            fprintf(stderr, " (chunk0 %d out+%.2f)\n", chunkLen[0], c0ms);
+        }
         for (int b = 0; b < nb; ++b) {
             n_out[b0 + b] = ex->h_nOut[b];
             mono_index[b0 + b] = ex->h_mono[b];
