@@ -106,3 +106,61 @@ def knn_case(nq: int, ndb: int, seed: int = 1234, planted_frac: float = 0.01, du
             # duplicate the source row at a later (and an earlier) index to exercise ties
             db[min(ndb - 1, src + 1 + int(rng.integers(0, 5)))] = db[src]
     return q, db
+
+
+def vocabulary(k: int = 10, L: int = 3, seed: int = 7, ragged: float = 0.0, stop_frac: float = 0.05, flips: int = 40,
+               scoring: int = 0, weighting: int = 0, min_leaf_level: int = 1) -> dict:
+    """Synthetic DBoW2-style vocabulary tree in the node-stream form of the reference's text format
+    (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1378-1420): node i+1 has `parent[i]` (0 = root), a leaf flag, a
+    256-bit descriptor and a weight; ids are assigned in stream order, children of a node in the order they appear.
+    Children are their parent's descriptor with `flips` random bits flipped (so that descents are meaningful and
+    ties between siblings occur), laid out breadth first like a trained ORBvoc.  `ragged` makes that fraction of
+    the inner nodes at levels >= min_leaf_level leaves early; `stop_frac` of the words get weight 0 (stopped)."""
+    rng = np.random.default_rng(seed)
+    parent, leaf, desc, weight = [], [], [], []
+    frontier = [(0, np.zeros(32, np.uint8), 0)]           # (node id, descriptor, level)
+    frontier[0] = (0, rng.integers(0, 256, 32, dtype=np.uint8), 0)
+    next_id = 1
+    while frontier:
+        new_frontier = []
+        for nid, d, lvl in frontier:
+            nch = k if rng.random() > 0.15 else int(rng.integers(2, k + 1))    # not every node is full
+            for _ in range(nch):
+                cd = d.copy()
+                for b in rng.choice(256, size=int(rng.integers(0, flips + 1)), replace=False):
+                    cd[b >> 3] ^= np.uint8(1 << (b & 7))
+                is_leaf = (lvl + 1 == L) or (lvl + 1 >= min_leaf_level and rng.random() < ragged)
+                parent.append(nid); leaf.append(1 if is_leaf else 0); desc.append(cd)
+                if is_leaf:
+                    weight.append(0.0 if rng.random() < stop_frac else float(rng.uniform(0.05, 9.0)))
+                else:
+                    weight.append(0.0)
+                    new_frontier.append((next_id, cd, lvl + 1))
+                next_id += 1
+        frontier = new_frontier
+    return dict(k=k, L=L, scoring=scoring, weighting=weighting, parent=np.asarray(parent, np.int32), is_leaf=np.asarray(leaf, np.uint8),
+                desc=np.stack(desc).astype(np.uint8), weight=np.asarray(weight, np.float64))
+
+
+def write_vocabulary_text(voc: dict, path: str) -> None:
+    """The reference's ORBvoc.txt format (TemplatedVocabulary::saveToTextFile, TemplatedVocabulary.h:1428-1451): header
+    "k L scoring weighting", then per node "parent isLeaf d0 … d31 weight".  No trailing newline: the reference's
+    `while(!f.eof())` loader reads a phantom node from a final empty line."""
+    lines = ["%d %d %d %d" % (voc["k"], voc["L"], voc["scoring"], voc["weighting"])]
+    for p_, l_, d_, w_ in zip(voc["parent"], voc["is_leaf"], voc["desc"], voc["weight"]):
+        lines.append("%d %d %s %s" % (p_, l_, " ".join(str(int(x)) for x in d_), repr(float(w_))))
+    with open(path, "w") as f:
+        f.write("\n".join(lines))
+
+
+def vocabulary_queries(voc: dict, n: int, seed: int = 11, flips: int = 60) -> np.ndarray:
+    """n descriptors near random vocabulary nodes (so that all branches get traffic) plus some pure noise."""
+    rng = np.random.default_rng(seed)
+    src = voc["desc"][rng.integers(0, len(voc["desc"]), size=n)].copy()
+    for i in range(n):
+        if i % 7 == 0:
+            src[i] = rng.integers(0, 256, 32, dtype=np.uint8)
+            continue
+        for b in rng.choice(256, size=int(rng.integers(0, flips + 1)), replace=False):
+            src[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    return src

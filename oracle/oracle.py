@@ -20,8 +20,8 @@ _lib = None
 
 def build(force: bool = False) -> str:
     so = os.path.join(_here, "liborb_oracle.so")
-    src = os.path.join(_here, "orb_oracle.cpp")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(_here, f) for f in ("orb_oracle.cpp", "bow_oracle.cpp", "orb_oracle.h")]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _here, "liborb_oracle.so"], stdout=subprocess.DEVNULL)
     return so
 
@@ -70,6 +70,19 @@ def lib() -> C.CDLL:
         L.orc_stereo_tail.argtypes = [vp, vp, i32, i32, vp, vp, vp, f32, f32, vp, vp]
         L.orc_search_init.restype = i32
         L.orc_search_init.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, vp, f32, i32, vp]
+        L.orc_vocab_from_nodes.restype = vp
+        L.orc_vocab_from_nodes.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32]
+        L.orc_vocab_load_text.restype = vp
+        L.orc_vocab_load_text.argtypes = [C.c_char_p]
+        L.orc_vocab_free.argtypes = [vp]
+        L.orc_vocab_words.restype = i32
+        L.orc_vocab_words.argtypes = [vp]
+        L.orc_vocab_nodes.restype = i32
+        L.orc_vocab_nodes.argtypes = [vp]
+        L.orc_bow_transform.restype = i32
+        L.orc_bow_transform.argtypes = [vp, vp, i32, i32] + [vp] * 9
+        L.orc_bow_score_l1.restype = C.c_double
+        L.orc_bow_score_l1.argtypes = [vp, vp, i32, vp, vp, i32]
         _lib = L
     return _lib
 
@@ -226,3 +239,48 @@ def stereo_tail(uL, uR, idx, dist, keep, mbf, mb):
     ur = np.zeros(len(uL), np.float32); dp = np.zeros(len(uL), np.float32)
     n = lib().orc_stereo_tail(_p(uL), _p(uR), len(uL), len(uR), _p(idx), _p(dist), _p(keep), float(mbf), float(mb), _p(ur), _p(dp))
     return n, ur, dp
+
+
+class Vocabulary:
+    """DBoW2 vocabulary tree + transform (bow_oracle.cpp).  Build from a node stream (dict from synth.vocabulary) or a
+    text file in the reference's ORBvoc.txt format."""
+
+    def __init__(self, voc=None, path=None):
+        L = lib()
+        if path is not None:
+            self.h = L.orc_vocab_load_text(str(path).encode())
+        else:
+            par = np.ascontiguousarray(voc["parent"], np.int32); leaf = np.ascontiguousarray(voc["is_leaf"], np.uint8)
+            desc = np.ascontiguousarray(voc["desc"], np.uint8); w = np.ascontiguousarray(voc["weight"], np.float64)
+            self.h = L.orc_vocab_from_nodes(_p(par), _p(leaf), _p(desc), _p(w), len(par), int(voc["k"]), int(voc["L"]),
+                                            int(voc["scoring"]), int(voc["weighting"]))
+        if not self.h:
+            raise ValueError("bad vocabulary")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_vocab_free(self.h)
+            self.h = None
+
+    @property
+    def n_words(self):
+        return lib().orc_vocab_words(self.h)
+
+    def transform(self, desc, levelsup=4):
+        """→ dict(word_id[n], node_id[n], bow_ids, bow_vals, fv_nodes, fv_off, fv_idx) in std::map order."""
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        m = max(n, 1)
+        wid = np.zeros(m, np.uint32); nid = np.zeros(m, np.uint32)
+        bi = np.zeros(m, np.uint32); bv = np.zeros(m, np.float64)
+        fn = np.zeros(m, np.uint32); fo = np.zeros(m + 1, np.int32); fi = np.zeros(m, np.uint32)
+        nb, nf = C.c_int(0), C.c_int(0)
+        lib().orc_bow_transform(self.h, _p(desc), n, int(levelsup), _p(wid), _p(nid), _p(bi), _p(bv), C.byref(nb), _p(fn), _p(fo), _p(fi), C.byref(nf))
+        nb, nf = nb.value, nf.value
+        return dict(word_id=wid[:n], node_id=nid[:n], bow_ids=bi[:nb], bow_vals=bv[:nb], fv_nodes=fn[:nf], fv_off=fo[:nf + 1], fv_idx=fi[:fo[nf]])
+
+
+def bow_score_l1(ids1, v1, ids2, v2):
+    ids1 = np.ascontiguousarray(ids1, np.uint32); ids2 = np.ascontiguousarray(ids2, np.uint32)
+    v1 = np.ascontiguousarray(v1, np.float64); v2 = np.ascontiguousarray(v2, np.float64)
+    return lib().orc_bow_score_l1(_p(ids1), _p(v1), len(ids1), _p(ids2), _p(v2), len(ids2))

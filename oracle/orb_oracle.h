@@ -89,6 +89,19 @@ int orc_features_in_area(const float *xy, const int32_t *octave, int n, float mi
 int orc_stereo_tail(const float *uL, const float *uR, int nL, int nR, const int32_t *idx, const int32_t *dist,
                     const uint8_t *keep, float mbf, float mb, float *uRight, float *depth);
 
+/* ---- bag of words (bow_oracle.cpp): DBoW2 TemplatedVocabulary::transform as Frame::ComputeBoW calls it ---- */
+/* node stream like loadFromTextFile (TemplatedVocabulary.h:1378-1420): node i+1 has parent[i] (0 = root), leaf flag, 32-byte descriptor, weight */
+void *orc_vocab_from_nodes(const int32_t *parent, const uint8_t *is_leaf, const uint8_t *desc, const double *weight, int n_nodes,
+                           int k, int L, int scoring, int weighting);
+void *orc_vocab_load_text(const char *path);
+void orc_vocab_free(void *v);
+int orc_vocab_words(void *v);
+int orc_vocab_nodes(void *v);
+/* per feature word/node id; BowVector as (ids, vals) and FeatureVector as CSR, both in std::map order */
+int orc_bow_transform(void *v, const uint8_t *desc, int n, int levelsup, uint32_t *word_id, uint32_t *node_id, uint32_t *bow_ids,
+                      double *bow_vals, int *n_bow, uint32_t *fv_nodes, int32_t *fv_off, uint32_t *fv_idx, int *n_fv);
+double orc_bow_score_l1(const uint32_t *ids1, const double *v1, int n1, const uint32_t *ids2, const double *v2, int n2);
+
 #ifdef __cplusplus
 }
 #endif

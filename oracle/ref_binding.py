@@ -71,3 +71,70 @@ class Extractor:
         out = np.zeros((h.value, w.value), np.uint8)
         self.L.ref_level(self.h, l, _p(out), out.strides[0], None, None)
         return out
+
+
+# ---- the reference's vendored DBoW2 (oracle/_ref/libref_bow.so) ----
+SO_BOW = os.path.join(_here, "_ref", "libref_bow.so")
+_lib_bow = None
+
+
+def bow_available() -> bool:
+    return os.path.exists(SO_BOW)
+
+
+def lib_bow():
+    global _lib_bow
+    if _lib_bow is None:
+        _build_oracle()
+        L = C.CDLL(SO_BOW)
+        vp, i32 = C.c_void_p, C.c_int
+        L.ref_vocab_load_text.restype = vp
+        L.ref_vocab_load_text.argtypes = [C.c_char_p]
+        L.ref_vocab_free.argtypes = [vp]
+        L.ref_vocab_size.restype = i32
+        L.ref_vocab_size.argtypes = [vp]
+        L.ref_bow_transform.restype = i32
+        L.ref_bow_transform.argtypes = [vp, vp, i32, i32] + [vp] * 7
+        L.ref_bow_words.argtypes = [vp, vp, i32, vp]
+        L.ref_bow_score.restype = C.c_double
+        L.ref_bow_score.argtypes = [vp, vp, vp, i32, vp, vp, i32]
+        _lib_bow = L
+    return _lib_bow
+
+
+class Vocabulary:
+    """The reference's ORBVocabulary (DBoW2::TemplatedVocabulary<FORB>) loaded with its own loadFromTextFile."""
+
+    def __init__(self, path):
+        self.L = lib_bow()
+        self.h = self.L.ref_vocab_load_text(str(path).encode())
+        if not self.h:
+            raise ValueError("reference loadFromTextFile failed")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ref_vocab_free(self.h)
+            self.h = None
+
+    @property
+    def n_words(self):
+        return self.L.ref_vocab_size(self.h)
+
+    def transform(self, desc, levelsup=4):
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        m = max(n, 1)
+        bi = np.zeros(m, np.uint32); bv = np.zeros(m, np.float64)
+        fn = np.zeros(m, np.uint32); fo = np.zeros(m + 1, np.int32); fi = np.zeros(m, np.uint32)
+        wid = np.zeros(m, np.uint32)
+        nb, nf = C.c_int(0), C.c_int(0)
+        self.L.ref_bow_transform(self.h, _p(desc), n, int(levelsup), _p(bi), _p(bv), C.byref(nb), _p(fn), _p(fo), _p(fi), C.byref(nf))
+        if n:
+            self.L.ref_bow_words(self.h, _p(desc), n, _p(wid))
+        nb, nf = nb.value, nf.value
+        return dict(word_id=wid[:n], bow_ids=bi[:nb], bow_vals=bv[:nb], fv_nodes=fn[:nf], fv_off=fo[:nf + 1], fv_idx=fi[:fo[nf]])
+
+    def score(self, ids1, v1, ids2, v2):
+        ids1 = np.ascontiguousarray(ids1, np.uint32); ids2 = np.ascontiguousarray(ids2, np.uint32)
+        v1 = np.ascontiguousarray(v1, np.float64); v2 = np.ascontiguousarray(v2, np.float64)
+        return self.L.ref_bow_score(self.h, _p(ids1), _p(v1), len(ids1), _p(ids2), _p(v2), len(ids2))

@@ -13,7 +13,10 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <iostream>
 #include <memory>
+#include <sstream>
+#include <string>
 #include <vector>
 
 #include "../../orb_oracle.h"
@@ -21,6 +24,8 @@
 #define CV_PI 3.1415926535897932384626433832795
 #define CV_8U 0
 #define CV_8UC1 0
+#define CV_32F 5
+#define CV_32FC1 5
 
 typedef unsigned char uchar;
 
@@ -88,11 +93,11 @@ public:
     uchar *data;
     MatStep step;
     Mat() : rows(0), cols(0), data(nullptr), step(0) {}
-    Mat(int r, int c, int /*type*/) { alloc(r, c); }
+    Mat(int r, int c, int type) { alloc(r, c, type); }
     Mat(Size s, int /*type*/) { alloc(s.height, s.width); }
     Mat(int r, int c, int /*type*/, void *ext, size_t st) : rows(r), cols(c), data((uchar *)ext), step(st) {}
     static Mat zeros(int r, int c, int t) { Mat m(r, c, t); if (m.buf) std::fill(m.buf->begin(), m.buf->end(), 0); return m; }
-    void create(int r, int c, int /*type*/) { if (r != rows || c != cols || !data) alloc(r, c); }
+    void create(int r, int c, int type) { if (r != rows || c != cols || !data) alloc(r, c, type); }
     void release() { buf.reset(); data = nullptr; rows = cols = 0; step = 0; }
     bool empty() const { return !data || rows == 0 || cols == 0; }
     int type() const { return CV_8UC1; }
@@ -118,9 +123,10 @@ public:
 
 private:
     std::shared_ptr<std::vector<uchar>> buf;
-    void alloc(int r, int c) {
-        rows = r; cols = c; step = (size_t)c;
-        buf = std::make_shared<std::vector<uchar>>((size_t)r * c + 1);
+    void alloc(int r, int c, int type = CV_8UC1) {
+        const size_t es = type == CV_32F ? 4 : 1;   // DBoW2's FORB::toMat32F is the only non-8U user (compiled, never called)
+        rows = r; cols = c; step = (size_t)c * es;
+        buf = std::make_shared<std::vector<uchar>>((size_t)r * c * es + 1);
         data = buf->data();
     }
     Mat view(int y, int x, int h, int w) const {
@@ -178,6 +184,28 @@ inline void GaussianBlur(const Mat &src, Mat &dst, Size, double, double, int) {
     for (int y = 0; y < src.rows; ++y) memcpy(dst.data + (size_t)y * dst.step, &out[(size_t)y * src.cols], src.cols);
 }
 inline float fastAtan2(float y, float x) { return orc_fast_atan2(y, x); }
+
+// cv::FileStorage / cv::FileNode: named by DBoW2's YAML save()/load(), which the oracle build never calls (the
+// vocabulary is read with the reference's own loadFromTextFile).  These stubs only have to compile.
+class FileNode {
+public:
+    FileNode operator[](const std::string &) const { return FileNode(); }
+    FileNode operator[](const char *) const { return FileNode(); }
+    FileNode operator[](int) const { return FileNode(); }
+    size_t size() const { return 0; }
+    operator int() const { return 0; }
+    operator double() const { return 0.0; }
+    operator std::string() const { return std::string(); }
+};
+class FileStorage {
+public:
+    enum { READ = 0, WRITE = 1 };
+    FileStorage(const std::string &, int) {}
+    bool isOpened() const { return false; }
+    FileNode operator[](const std::string &) const { return FileNode(); }
+    FileNode operator[](const char *) const { return FileNode(); }
+};
+template <typename T> inline FileStorage &operator<<(FileStorage &fs, const T &) { return fs; }
 
 struct KeyPointsFilter {  // only referenced by the reference's dead ComputeKeyPointsOld (never called)
     static void retainBest(std::vector<KeyPoint> &, int) {}
