@@ -87,6 +87,19 @@ def lib() -> C.CDLL:
     L.orbx_rot_hist_filter_device.argtypes = [vp, vp, vp, i32, vp]
     L.orbx_descriptor_distance.restype = i32
     L.orbx_descriptor_distance.argtypes = [vp, vp]
+    L.orbx_vocab_create_from_nodes.restype = vp
+    L.orbx_vocab_create_from_nodes.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32]
+    L.orbx_vocab_load_text.restype = vp
+    L.orbx_vocab_load_text.argtypes = [C.c_char_p, i32]
+    L.orbx_vocab_destroy.argtypes = [vp]
+    L.orbx_vocab_last_error.restype = C.c_char_p
+    L.orbx_vocab_last_error.argtypes = [vp]
+    L.orbx_vocab_info.argtypes = [vp, vp, vp, vp, vp]
+    L.orbx_vocab_stream.restype = vp
+    L.orbx_vocab_stream.argtypes = [vp]
+    L.orbx_vocab_sync.argtypes = [vp]
+    L.orbx_bow_transform.argtypes = [vp, vp, i32, i32] + [vp] * 9
+    L.orbx_bow_transform_batch_device.argtypes = [vp, vp, C.c_size_t, vp, i32, i32, i32] + [vp] * 9
     L.orbx_debug_sort_nodes.argtypes = [vp, vp, i32, vp]
     L.orbx_debug_sort_nodes_device.argtypes = [i32, vp, vp, i32, vp]
     L.orbx_debug_sincos_device.argtypes = [i32, vp, i32, vp, vp]
@@ -400,3 +413,84 @@ class ORBmatcher:
 
     def stream(self):
         return self.L.orbx_matcher_stream(self.h)
+
+
+class ORBVocabulary:
+    """`ORB_SLAM3::ORBVocabulary` = `DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>` (include/ORBVocabulary.h:29) for
+    the calls the tracking front-end makes on it: `loadFromTextFile` and `transform(features, BowVector, FeatureVector,
+    levelsup)` (src/Frame.cc:739-747).  The tree lives on one B200."""
+
+    def __init__(self, device=0):
+        self.L = lib()
+        self.device = device
+        self.h = None
+
+    def _chk(self, rc):
+        if rc != OK:
+            raise OrbxError(rc, self.L.orbx_vocab_last_error(self.h).decode())
+
+    def _adopt(self, h):
+        self.close()
+        if not h:
+            raise OrbxError(ERR_ARG, self.L.orbx_vocab_last_error(None).decode())
+        self.h = h
+
+    def loadFromTextFile(self, path) -> bool:
+        try:
+            self._adopt(self.L.orbx_vocab_load_text(str(path).encode(), self.device))
+        except OrbxError:
+            return False      # the reference returns false on a malformed file
+        return True
+
+    def from_nodes(self, voc):
+        """Node stream (dict as produced by dani_slam_b200.synth.vocabulary)."""
+        par = np.ascontiguousarray(voc["parent"], np.int32); leaf = np.ascontiguousarray(voc["is_leaf"], np.uint8)
+        desc = np.ascontiguousarray(voc["desc"], np.uint8); w = np.ascontiguousarray(voc["weight"], np.float64)
+        self._adopt(self.L.orbx_vocab_create_from_nodes(_p(par), _p(leaf), _p(desc), _p(w), len(par), int(voc["k"]), int(voc["L"]),
+                                                        int(voc["scoring"]), int(voc["weighting"]), self.device))
+        return self
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.orbx_vocab_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def info(self):
+        k, L_, nn, nw = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+        self._chk(self.L.orbx_vocab_info(self.h, C.byref(k), C.byref(L_), C.byref(nn), C.byref(nw)))
+        return dict(k=k.value, L=L_.value, n_nodes=nn.value, n_words=nw.value)
+
+    def size(self):
+        return self.info()["n_words"]
+
+    def empty(self):
+        return self.h is None or self.size() == 0
+
+    def transform(self, descriptors, levelsup=4):
+        """→ dict(word_id, node_id, bow_ids, bow_vals, fv_nodes, fv_off, fv_idx): BowVector and FeatureVector in map order."""
+        desc = np.ascontiguousarray(descriptors, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        m = max(n, 1)
+        wid = np.zeros(m, np.uint32); nid = np.zeros(m, np.uint32)
+        bi = np.zeros(m, np.uint32); bv = np.zeros(m, np.float64)
+        fn = np.zeros(m, np.uint32); fo = np.zeros(m + 1, np.int32); fi = np.zeros(m, np.uint32)
+        nb, nf = C.c_int(0), C.c_int(0)
+        self._chk(self.L.orbx_bow_transform(self.h, _p(desc), n, int(levelsup), _p(wid), _p(nid), _p(bi), _p(bv), C.byref(nb), _p(fn), _p(fo),
+                                            _p(fi), C.byref(nf)))
+        nb, nf = nb.value, nf.value
+        return dict(word_id=wid[:n], node_id=nid[:n], bow_ids=bi[:nb], bow_vals=bv[:nb], fv_nodes=fn[:nf], fv_off=fo[:nf + 1], fv_idx=fi[:fo[nf]])
+
+    def transform_batch_device(self, d_desc, desc_stride, d_n, batch, cap, levelsup, d_word, d_node, d_bow_ids, d_bow_vals, d_n_bow, d_fv_nodes,
+                               d_fv_off, d_fv_idx, d_n_fv):
+        """Raw device pointers (ints); asynchronous on the vocabulary's stream."""
+        self._chk(self.L.orbx_bow_transform_batch_device(self.h, d_desc, desc_stride, d_n, batch, cap, int(levelsup), d_word, d_node, d_bow_ids,
+                                                         d_bow_vals, d_n_bow, d_fv_nodes, d_fv_off, d_fv_idx, d_n_fv))
+
+    def sync(self):
+        self._chk(self.L.orbx_vocab_sync(self.h))
+
+    def stream(self):
+        return self.L.orbx_vocab_stream(self.h)

@@ -180,6 +180,45 @@ int orbx_stereo_tail(orbx_matcher *m, const float *u_left, const float *u_right,
 /* ORBmatcher::DescriptorDistance for one pair on the host (inline popcount; no device involved). */
 int orbx_descriptor_distance(const uint8_t *a, const uint8_t *b);
 
+/* ---------------------------------------------------------------------------------------------
+ * Bag-of-words transform of ORB descriptors.  Replaces, for this step, the reference's
+ * vendored DBoW2 as Frame::ComputeBoW / KeyFrame::ComputeBoW drive it (src/Frame.cc:739-747, src/KeyFrame.cc:
+ * mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, 4)):
+ *   TemplatedVocabulary::loadFromTextFile  Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1338-1423
+ *   TemplatedVocabulary::transform         :1127-1194 (image) and :1218-1262 (one descriptor down the tree)
+ *   BowVector::addWeight/normalize         Thirdparty/DBoW2/DBoW2/BowVector.cpp:32-85
+ *   FeatureVector::addFeature              Thirdparty/DBoW2/DBoW2/FeatureVector.cpp:30-46
+ * Scoring / weighting codes are DBoW2's (BowVector.h:39-56): scoring 0 L1_NORM … 5 DOT_PRODUCT, weighting 0 TF_IDF,
+ * 1 TF, 2 IDF, 3 BINARY.  Results are bit-identical to DBoW2's, doubles included.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct orbx_vocab orbx_vocab;
+/* Vocabulary from a node stream in the order of the reference's text format: node i+1 (node 0 is the root) has
+ * parent[i], a leaf flag (leaves get word ids in stream order), a 32-byte descriptor and a weight.  The tree is
+ * uploaded to `device` once and stays resident.  NULL on error (orbx_vocab_last_error(NULL)). */
+orbx_vocab *orbx_vocab_create_from_nodes(const int32_t *parent, const uint8_t *is_leaf, const uint8_t *desc, const double *weight,
+                                         int n_nodes, int k, int L, int scoring, int weighting, int device);
+/* Same from a file in the ORBvoc.txt format ("k L scoring weighting", then "parent isLeaf d0 … d31 weight" per
+ * node).  Blank lines are ignored (the reference's eof loop reads a phantom node from a trailing one). */
+orbx_vocab *orbx_vocab_load_text(const char *path, int device);
+void orbx_vocab_destroy(orbx_vocab *v);
+const char *orbx_vocab_last_error(const orbx_vocab *v);
+int orbx_vocab_info(const orbx_vocab *v, int *k, int *L, int *n_nodes, int *n_words);
+void *orbx_vocab_stream(orbx_vocab *v);
+int orbx_vocab_sync(orbx_vocab *v);
+/* transform(features, BowVector, FeatureVector, levelsup) for one image, HOST buffers.  word_id / node_id (n each,
+ * may be NULL) are the per-feature word and the ancestor at level L - levelsup (0 = root when that level is <= 0 or
+ * below the leaf, where the reference reads an uninitialised value).  The BowVector comes back as (bow_ids,
+ * bow_vals) and the FeatureVector as CSR (fv_nodes, fv_off, fv_idx), both in std::map order; arrays hold n entries
+ * (fv_off n+1).  Calls on one handle serialise (the reference shares one const vocabulary between its threads). */
+int orbx_bow_transform(orbx_vocab *v, const uint8_t *desc, int n, int levelsup, uint32_t *word_id, uint32_t *node_id, uint32_t *bow_ids,
+                       double *bow_vals, int32_t *n_bow, uint32_t *fv_nodes, int32_t *fv_off, uint32_t *fv_idx, int32_t *n_fv);
+/* Batched form on DEVICE buffers, asynchronous on the vocabulary's stream: image b has d_n[b] (<= cap) descriptors
+ * at d_desc + b*desc_stride_bytes — the layout orbx_extract_batch_device writes — and its outputs start at row
+ * b*cap of every array (d_fv_off: b*(cap+1)). */
+int orbx_bow_transform_batch_device(orbx_vocab *v, const uint8_t *d_desc, size_t desc_stride_bytes, const int32_t *d_n, int batch, int cap,
+                                    int levelsup, uint32_t *d_word_id, uint32_t *d_node_id, uint32_t *d_bow_ids, double *d_bow_vals,
+                                    int32_t *d_n_bow, uint32_t *d_fv_nodes, int32_t *d_fv_off, uint32_t *d_fv_idx, int32_t *d_n_fv);
+
 /* Test hook: number of (frame, level) pairs of the last batch call that the histogram quadtree kernel handed to
  * the general quadtree kernel (trees deeper than its table); -1 if the histogram kernel is disabled. */
 int orbx_debug_deep_count(orbx_extractor *ex);
