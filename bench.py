@@ -212,6 +212,8 @@ def main():
     ap.add_argument("--no-match", action="store_true", help="skip the Hamming kNN section")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--match-db", type=int, default=10_000_000)
+    ap.add_argument("--no-bow", action="store_true", help="skip the bag-of-words section")
+    ap.add_argument("--bow-levels", type=int, default=6, help="depth of the synthetic k=10 vocabulary (ORBvoc: 6)")
     args = ap.parse_args()
     default_batch = set_workload(args.workload)
     if args.batch <= 0:
@@ -407,6 +409,59 @@ def main():
                  "popc_per_s": 8 * gpairs * 1e9}
         del d_db
 
+    # ---------------- bag-of-words transform of the extracted descriptors (`bow`) ----------------
+    bow = None
+    if not args.no_bow:
+        from dani_slam_b200 import synth as _synth
+        voc = _synth.vocabulary_complete(10, args.bow_levels, seed=7)
+        vdev = orbx.ORBVocabulary(local_rank).from_nodes(voc)
+        i32 = torch.int32
+        b_word = torch.zeros(B * cap, dtype=i32, device=dev); b_node = torch.zeros_like(b_word)
+        b_ids = torch.zeros_like(b_word); b_vals = torch.zeros(B * cap, dtype=torch.float64, device=dev)
+        b_fn = torch.zeros_like(b_word); b_fi = torch.zeros_like(b_word); b_fo = torch.zeros(B * (cap + 1), dtype=i32, device=dev)
+        b_nb = torch.zeros(B, dtype=i32, device=dev); b_nf = torch.zeros(B, dtype=i32, device=dev)
+        vstream = torch.cuda.ExternalStream(vdev.stream(), device=dev)
+
+        def step_bow():
+            vdev.transform_batch_device(d_desc.data_ptr(), cap * 32, d_n.data_ptr(), B, cap, 4, b_word.data_ptr(), b_node.data_ptr(), b_ids.data_ptr(),
+                                        b_vals.data_ptr(), b_nb.data_ptr(), b_fn.data_ptr(), b_fo.data_ptr(), b_fi.data_ptr(), b_nf.data_ptr())
+
+        torch.cuda.synchronize(dev)
+        for _ in range(3):
+            step_bow()
+        vdev.sync()
+        barrier()
+        Kb = max(3, min(K, 10))
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record(vstream)
+        for _ in range(Kb):
+            step_bow()
+        w1.record(vstream)
+        w1.synchronize()
+        barrier()
+        ms_b = max_over_ranks(w0.elapsed_time(w1))
+        n_desc = float(d_n.sum().item())
+        feats = sum_over_ranks(n_desc) * Kb / (ms_b / 1000.0)
+        bow = {"metric": "bow_descriptors_per_s", "value": feats, "unit": "descriptors/s", "frames_per_s": world * B * Kb / (ms_b / 1000.0),
+               "ms_per_step": ms_b / Kb, "steps": Kb, "scaling": "weak",
+               "vocabulary": f"synthetic complete tree k=10 L={args.bow_levels} ({len(voc['parent']) + 1} nodes, {int(voc['is_leaf'].sum())} words), TF-IDF, L1, levelsup 4",
+               "words_per_frame": float(b_nb.float().mean().item()), "cpu_baseline": None}
+        if world == 1 and not args.no_cpu:
+            from oracle import oracle as _orc
+            from concurrent.futures import ThreadPoolExecutor
+            cores = os.cpu_count() or 1
+            ov = _orc.Vocabulary(voc=voc)
+            h_desc = d_desc[: min(B, 4 * cores)].cpu().numpy(); h_n = d_n[: min(B, 4 * cores)].cpu().numpy()
+            t0 = time.time(); done = 0
+            with ThreadPoolExecutor(cores) as pool:
+                while time.time() - t0 < 5.0:
+                    list(pool.map(lambda b_: ov.transform(h_desc[b_, : h_n[b_]], 4), range(len(h_n))))
+                    done += int(h_n.sum())
+            dt = time.time() - t0
+            bow["cpu_baseline"] = {"value": done / dt, "unit": "descriptors/s", "cores": cores, "kind": "port",
+                                   "sample": f"{done} descriptors in {dt:.1f}s, one frame per thread on {cores} threads (oracle/bow_oracle.cpp)"}
+        del vdev
+
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
     cpu_baseline = None
     if world == 1 and not args.no_cpu:
@@ -432,6 +487,7 @@ def main():
             "roofline_pipeline": roofline_pipeline,
             "cpu_baseline": cpu_baseline,
             "match": match,
+            "bow": bow,
         }
         print(json.dumps(line), flush=True)
     if dist_on:

@@ -142,6 +142,30 @@ def vocabulary(k: int = 10, L: int = 3, seed: int = 7, ragged: float = 0.0, stop
                 desc=np.stack(desc).astype(np.uint8), weight=np.asarray(weight, np.float64))
 
 
+def vocabulary_complete(k: int = 10, L: int = 6, seed: int = 7, flips: int = 48, stop_frac: float = 0.0, scoring: int = 0,
+                        weighting: int = 0) -> dict:
+    """Complete k-ary tree of depth L in breadth-first order (the shape of ORBvoc.txt: k = 10, L = 6, 1.1 M nodes),
+    generated level by level with numpy: a child is its parent XOR a random mask of about `flips` bits."""
+    rng = np.random.default_rng(seed)
+    root = rng.integers(0, 256, (1, 32), dtype=np.uint8)
+    parents, descs, leafs = [], [], []
+    cur, first_id = root, 0
+    for lvl in range(1, L + 1):
+        n = cur.shape[0] * k
+        mask = np.packbits(rng.random((n, 256)) < flips / 256.0, axis=1)
+        child = np.repeat(cur, k, axis=0) ^ mask
+        parents.append(np.repeat(np.arange(first_id, first_id + cur.shape[0], dtype=np.int32), k))
+        descs.append(child)
+        leafs.append(np.full(n, 1 if lvl == L else 0, np.uint8))
+        first_id = 1 + sum(len(p_) for p_ in parents[:-1])
+        cur = child
+    parent = np.concatenate(parents); desc = np.concatenate(descs); leaf = np.concatenate(leafs)
+    weight = np.where(leaf == 1, rng.uniform(0.05, 9.0, len(leaf)), 0.0)
+    if stop_frac > 0:
+        weight = np.where(rng.random(len(leaf)) < stop_frac, 0.0, weight)
+    return dict(k=k, L=L, scoring=scoring, weighting=weighting, parent=parent.astype(np.int32), is_leaf=leaf, desc=desc, weight=weight.astype(np.float64))
+
+
 def write_vocabulary_text(voc: dict, path: str) -> None:
     """The reference's ORBvoc.txt format (TemplatedVocabulary::saveToTextFile, TemplatedVocabulary.h:1428-1451): header
     "k L scoring weighting", then per node "parent isLeaf d0 … d31 weight".  No trailing newline: the reference's
