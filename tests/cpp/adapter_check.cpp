@@ -1,19 +1,28 @@
 // Drives include/ORBextractor.h (the drop-in adapter, reference signatures) and include/ORBmatcher_orbx.h
 // exactly like Frame::ExtractORB does (src/Frame.cc:420-427), against the opencv2 shim, and compares the
 // result with the reference's own ORBextractor.cc (oracle/_ref) when that library is linked in.
-// Usage: adapter_check <width> <height> <seed>   (prints "OK n mono" or a diagnostic; exit code 0/1)
+// With a 4th argument (a vocabulary in the ORBvoc text format) it also runs include/ORBVocabulary_orbx.h like
+// Frame::ComputeBoW (src/Frame.cc:739-747) and compares with the reference's own DBoW2 (oracle/_ref/libref_bow.so).
+// Usage: adapter_check <width> <height> <seed> [vocabulary.txt]   (prints "OK n mono" or a diagnostic; exit code 0/1)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <vector>
 
 #include "ORBextractor.h"
 #include "ORBmatcher_orbx.h"
+#include "ORBVocabulary_orbx.h"
 
 extern "C" {
 void *ref_create(int, float, int, int, int);
 void ref_destroy(void *);
 int ref_extract(void *, const uint8_t *, int, int, size_t, const int32_t *, int, int, int, orc_keypoint *, uint8_t *, int, int *, int *);
+#ifdef WITH_REF_BOW
+void *ref_vocab_load_text(const char *);
+void ref_vocab_free(void *);
+int ref_bow_transform(void *, const uint8_t *, int, int, uint32_t *, double *, int *, uint32_t *, int32_t *, uint32_t *, int *);
+#endif
 }
 
 int main(int argc, char **argv) {
@@ -56,6 +65,33 @@ int main(int argc, char **argv) {
     for (int i = 0; i < rn; ++i)
         if (dist[2 * i] != 0) { printf("FAIL self match %d\n", i); return 1; }
     if (ORB_SLAM3::ORBmatcherDevice::DescriptorDistance(desc.ptr(0), desc.ptr(0)) != 0) { printf("FAIL distance\n"); return 1; }
+    // vocabulary: BowVector / FeatureVector of the extracted descriptors, levelsup 4 as in Frame::ComputeBoW
+    if (argc > 4) {
+        typedef std::map<unsigned int, double> BowVector;                         // DBoW2::BowVector's base
+        typedef std::map<unsigned int, std::vector<unsigned int> > FeatureVector; // DBoW2::FeatureVector's base
+        ORB_SLAM3::ORBVocabularyDevice voc;
+        if (!voc.loadFromTextFile(argv[4]) || voc.empty()) { printf("FAIL vocabulary load: %s\n", voc.LastError()); return 1; }
+        BowVector bv; FeatureVector fv;
+        if (!voc.transform(desc.ptr(0), rn, bv, fv, 4)) { printf("FAIL transform: %s\n", voc.LastError()); return 1; }
+        if (bv.empty() || fv.empty()) { printf("FAIL empty bag of words\n"); return 1; }
+#ifdef WITH_REF_BOW
+        void *rv = ref_vocab_load_text(argv[4]);
+        if (!rv) { printf("FAIL reference vocabulary load\n"); return 1; }
+        std::vector<uint32_t> ids(rn), nodes(rn), fidx(rn);
+        std::vector<double> vals(rn);
+        std::vector<int32_t> off(rn + 1);
+        int nb = 0, nf = 0;
+        ref_bow_transform(rv, desc.ptr(0), rn, 4, ids.data(), vals.data(), &nb, nodes.data(), off.data(), fidx.data(), &nf);
+        ref_vocab_free(rv);
+        if (nb != (int)bv.size() || nf != (int)fv.size()) { printf("FAIL bow sizes %d/%zu %d/%zu\n", nb, bv.size(), nf, fv.size()); return 1; }
+        int i = 0;
+        for (BowVector::const_iterator it = bv.begin(); it != bv.end(); ++it, ++i)
+            if (it->first != ids[i] || memcmp(&it->second, &vals[i], 8) != 0) { printf("FAIL bow entry %d\n", i); return 1; }
+        i = 0;
+        for (FeatureVector::const_iterator it = fv.begin(); it != fv.end(); ++it, ++i)
+            if (it->first != nodes[i] || it->second != std::vector<unsigned int>(fidx.begin() + off[i], fidx.begin() + off[i + 1])) { printf("FAIL feature vector entry %d\n", i); return 1; }
+#endif
+    }
     printf("OK %d %d\n", rn, mono);
     return 0;
 }

@@ -1,4 +1,5 @@
-"""The C++ drop-in adapters (include/ORBextractor.h with the reference's signatures, include/ORBmatcher_orbx.h):
+"""The C++ drop-in adapters (include/ORBextractor.h with the reference's signatures, include/ORBmatcher_orbx.h,
+include/ORBVocabulary_orbx.h):
 compile check on the CPU, and on the GPU a C++ program that calls them like Frame::ExtractORB does and
 compares with the reference's own ORBextractor.cc (oracle/_ref)."""
 import os
@@ -23,8 +24,13 @@ def test_cpp_adapter_matches_reference_source(tmp_path, orbx_mod):
         pytest.skip("oracle/_ref not built")
     exe = str(tmp_path / "adapter_check")
     libdirs = [os.path.join(ROOT, "dani_slam_b200"), ref_dir, os.path.join(ROOT, "oracle")]
-    subprocess.check_call(["g++", "-std=c++17", "-O2"] + INC + [SRC, "-o", exe] + ["-L" + d for d in libdirs] +
-                          ["-lorbx", "-lref_orb", "-lorb_oracle", "-Wl,-rpath," + ":".join(libdirs)])
-    for args in (["640", "480", "1"], ["752", "480", "2"], ["401", "333", "3"]):
+    with_bow = os.path.exists(os.path.join(ref_dir, "libref_bow.so"))
+    subprocess.check_call(["g++", "-std=c++17", "-O2"] + (["-DWITH_REF_BOW"] if with_bow else []) + INC + [SRC, "-o", exe] +
+                          ["-L" + d for d in libdirs] + ["-lorbx", "-lref_orb"] + (["-lref_bow"] if with_bow else []) +
+                          ["-lorb_oracle", "-Wl,-rpath," + ":".join(libdirs)])
+    from dani_slam_b200 import synth
+    voc_path = str(tmp_path / "voc.txt")
+    synth.write_vocabulary_text(synth.vocabulary(k=10, L=4, seed=13), voc_path)
+    for args in (["640", "480", "1", voc_path], ["752", "480", "2"], ["401", "333", "3", voc_path]):
         r = subprocess.run([exe] + args, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
         assert r.returncode == 0 and r.stdout.strip().startswith("OK"), r.stdout
