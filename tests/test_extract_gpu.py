@@ -163,6 +163,38 @@ def test_tie_heavy_and_regular_patterns(orbx_mod, oracle_mod):
         assert mono == rmono and k.tobytes() == rk.tobytes() and np.array_equal(d, rd), i
 
 
+def test_fast_two_sided_pixels_and_dense_corner_fields(orbx_mod, oracle_mod):
+    """The two-phase FAST kernel's rare paths: steep ramps and saddles make (almost) every pixel pass the compass
+    pre-test on BOTH sides (its bounded two-sided queue then flushes every iteration); salt-and-pepper fields make
+    most pixels corners (queues at their worst-case length); low-amplitude copies of them only fire at minThFAST."""
+    H, W = 300, 420
+    yy, xx = np.mgrid[0:H, 0:W]
+    rng = np.random.default_rng(5)
+    frames = [
+        ((11 * xx + 9 * yy) % 256).astype(np.uint8),                                   # sawtooth ramp: two-sided everywhere
+        ((13 * xx - 12 * yy) % 256).astype(np.uint8),
+        (128 + 100 * np.sin(xx / 2.0) * np.sin(yy / 2.0)).astype(np.uint8),            # saddles between the bumps
+        rng.choice(np.array([0, 255], np.uint8), size=(H, W)),                          # salt and pepper
+        rng.integers(0, 256, (H, W), dtype=np.uint8),                                   # white noise
+        (100 + ((11 * xx + 9 * yy) % 16)).astype(np.uint8),                            # amplitude 15: only the minTh pass
+        (100 + rng.integers(0, 2, (H, W)) * 12).astype(np.uint8),                       # amplitude 12 salt and pepper
+        np.where((xx // 3 + yy // 3) % 2 == 0, 40, 215).astype(np.uint8),               # 3-px checkerboard
+    ]
+    ex = orbx_mod.ORBextractor(1500, 1.2, 8, 20, 7, max_width=W, max_height=H)
+    ref = oracle_mod.Extractor(1500, 1.2, 8, 20, 7)
+    for i, f in enumerate(frames):
+        mono, k, d = ex(f)
+        rc, rk, rd, rmono = ref.extract(f, cap=2000)
+        for l in range(8):
+            assert sha(_xyz(ex.candidates(l))) == sha(_xyz(ref.candidates(l))), (i, l)
+        assert mono == rmono and k.tobytes() == rk.tobytes() and np.array_equal(d, rd), i
+    # and in one batch (different cells of a launch take different paths)
+    n, mono, kps, desc = ex.__class__(1500, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=len(frames)).extract_batch(np.stack(frames))
+    for i, f in enumerate(frames):
+        rc, rk, rd, rmono = ref.extract(f, cap=2000)
+        assert n[i] == len(rk) and kps[i, : n[i]].tobytes() == rk.tobytes() and np.array_equal(desc[i, : n[i]], rd), i
+
+
 def test_full_size_4k_frame(orbx_mod, oracle_mod):
     """BASELINE config 5 size: one 3840×2160 frame, nFeatures=8000 — full parity plus structural properties."""
     from dani_slam_b200 import synth
