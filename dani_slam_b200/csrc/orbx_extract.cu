@@ -24,6 +24,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -497,15 +498,18 @@ __device__ __forceinline__ int fast_exact_entries(const uint8_t *roi, uint8_t *s
     return nN;
 }
 
+// One launch per pyramid level (cells cellBase .. cellBase+nCellsL of the cell table): shared memory is sized for that
+// level's own cell size, which is what bounds the number of resident warps.
 template <int WPB>
-__global__ void __launch_bounds__(WPB * 32) k_fast_cells(ExParams p, int maxSlotCap) {
+__global__ void __launch_bounds__(WPB * 32) k_fast_cells(ExParams p, int cellBase, int nCellsL, int maxCw, int maxCh) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const OrbxGeom &g = *p.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c = blockIdx.x * WPB + warp, b = blockIdx.y;
-    if (c >= g.nCellsTotal) return;  // warps are independent: no block-level barrier below
+    const int cl = blockIdx.x * WPB + warp, b = blockIdx.y;
+    if (cl >= nCellsL) return;  // warps are independent: no block-level barrier below
+    const int c = cellBase + cl;
     const OrbxCell cell = p.cells[c];
-    const FastSmem L = fast_smem_layout(g.maxCw, g.maxCh, maxSlotCap);
+    const FastSmem L = fast_smem_layout(maxCw, maxCh, 1);
     uint8_t *base = smem_raw + (size_t)warp * L.total2;
     uint8_t *roi = base + L.roiOff;
     uint8_t *score = base + L.scoreOff;
@@ -1865,6 +1869,7 @@ struct orbx_extractor {
     std::vector<BlurTile> h_tiles;
     int maxSlotCap = 0, nodeCapMax = 0, maxCellsLevel = 0, maxIni = 1;
     bool useHistQuadtree = true;
+    int dbgCalls = 0;
     bool fastV1 = false;            // ORBX_FAST_V1: single-phase FAST kernel (every pixel gets the exact measure)
     unsigned *d_hist = nullptr; size_t histCap = 0;
     unsigned short *d_finalPos = nullptr; size_t finalPosCap = 0;
@@ -1986,6 +1991,10 @@ int build_geometry(orbx_extractor *ex, int rows, int cols) {
                 G.maxCh = std::max(G.maxCh, (int)c.ch);
             }
         if (V.wCell + 6 > 255 || V.hCell + 6 > 255) { ex->err = "cell larger than 255 px"; return ORBX_ERR_GEOMETRY; }
+        if (fast_smem_layout(V.wCell + 6, V.hCell + 6, 1).roiPitch * (V.hCell + 6) > 16383) {   // FAST queue entries hold a 14-bit ROI offset
+            ex->err = "cell ROI larger than 16383 bytes";
+            return ORBX_ERR_GEOMETRY;
+        }
         cellBase += V.nCells;
         ex->maxSlotCap = std::max(ex->maxSlotCap, V.slotCap);
         ex->maxCellsLevel = std::max(ex->maxCellsLevel, V.nCells);
@@ -2195,18 +2204,42 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
     // K2
     {
         const int WPB = 4;
-        const FastSmem L = fast_smem_layout(G.maxCw, G.maxCh, ex->maxSlotCap);
-        const bool v1 = ex->fastV1;
-        const size_t smem = (size_t)(v1 ? L.total : L.total2) * WPB;
-        if (smem > 48 * 1024) {
-            if (v1) CUDA_TRY(ex, cudaFuncSetAttribute(k_fast_cells_v1<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            else CUDA_TRY(ex, cudaFuncSetAttribute(k_fast_cells<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        }
-        dim3 grd((G.nCellsTotal + WPB - 1) / WPB, batch);
-        if (G.nCellsTotal > 0) {
-            if (v1) k_fast_cells_v1<WPB><<<grd, WPB * 32, smem, s>>>(P, ex->maxSlotCap);
-            else k_fast_cells<WPB><<<grd, WPB * 32, smem, s>>>(P, ex->maxSlotCap);
-            ++ex->launches;
+        if (ex->fastV1) {
+            const FastSmem L = fast_smem_layout(G.maxCw, G.maxCh, ex->maxSlotCap);
+            const size_t smem = (size_t)L.total * WPB;
+            if (smem > 48 * 1024) CUDA_TRY(ex, cudaFuncSetAttribute(k_fast_cells_v1<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            dim3 grd((G.nCellsTotal + WPB - 1) / WPB, batch);
+            if (G.nCellsTotal > 0) {
+                k_fast_cells_v1<WPB><<<grd, WPB * 32, smem, s>>>(P, ex->maxSlotCap);
+                ++ex->launches;
+            }
+        } else {
+            // Consecutive levels whose cells need about the same shared memory (within 20 %) share a launch: the small
+            // top levels have much taller cells (2 rows of cells cover the level) and would otherwise set the per-warp
+            // footprint, hence the resident warps, for everybody.
+            int l0 = 0;
+            while (l0 < G.nlevels) {
+                int cwMax = 0, chMax = 0, l1 = l0, nC = 0;
+                size_t lo = 0, hi = 0;
+                for (; l1 < G.nlevels; ++l1) {
+                    const OrbxLevel &V = G.lv[l1];
+                    if (V.nCells <= 0) continue;
+                    const size_t need = (size_t)fast_smem_layout(V.wCell + 6, V.hCell + 6, 1).total2;
+                    if (nC > 0 && (std::max(hi, need) * 5 > std::min(lo, need) * 6)) break;
+                    lo = nC ? std::min(lo, need) : need; hi = std::max(hi, need);
+                    cwMax = std::max(cwMax, V.wCell + 6); chMax = std::max(chMax, V.hCell + 6);
+                    nC += V.nCells;
+                }
+                if (nC > 0) {
+                    int cellBase = -1;
+                    for (int l = l0; l < l1 && cellBase < 0; ++l) if (G.lv[l].nCells > 0) cellBase = G.lv[l].cellBase;
+                    const size_t smem = (size_t)fast_smem_layout(cwMax, chMax, 1).total2 * WPB;
+                    if (smem > 48 * 1024) CUDA_TRY(ex, cudaFuncSetAttribute(k_fast_cells<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    k_fast_cells<WPB><<<dim3((nC + WPB - 1) / WPB, batch), WPB * 32, smem, s>>>(P, cellBase, nC, cwMax, chMax);
+                    ++ex->launches;
+                }
+                l0 = l1;
+            }
         }
     }
     if (prof) CUDA_TRY(ex, cudaEventRecord(ex->ev[2], s));
@@ -2477,6 +2510,8 @@ int orbx_extract_batch(orbx_extractor *ex, const uint8_t *const *images, int bat
     int result = ORBX_OK;
     for (int b0 = 0; b0 < batch; b0 += ex->maxBatch) {
         const int nb = std::min(ex->maxBatch, batch - b0);
+        const auto tStart = std::chrono::steady_clock::now();
+        ++ex->dbgCalls;
         int rc = prepare(ex, rows, cols, rects, n_rects, lap0, lap1, nb);
         if (rc) return rc;
         const OrbxGeom &G = ex->geom;
@@ -2498,10 +2533,20 @@ int orbx_extract_batch(orbx_extractor *ex, const uint8_t *const *images, int bat
         int chunkLen[ORBX_MAX_CHUNKS];
         int nChunks = 0;
         if (nb >= 256) {
-            chunkLen[nChunks++] = nb / 32;
-            chunkLen[nChunks++] = nb * 3 / 32;
-            int left = nb - chunkLen[0] - chunkLen[1];
-            for (int i = ex->nSteady; i > 0; --i) { const int c = (left + i - 1) / i; chunkLen[nChunks++] = c; left -= c; }
+            // plan in 1024ths of the batch (developer knob ORBX_CHUNK_PLAN="32,96,..." overrides it)
+            int plan[ORBX_MAX_CHUNKS], nPlan = 0;
+            if (const char *e = getenv("ORBX_CHUNK_PLAN")) {
+                for (const char *q = e; *q && nPlan < ORBX_MAX_CHUNKS;) { plan[nPlan++] = atoi(q); while (*q && *q != ',') ++q; if (*q == ',') ++q; }
+            } else {
+                plan[nPlan++] = 32; plan[nPlan++] = 96;
+                for (int i = 0; i < ex->nSteady; ++i) plan[nPlan++] = (1024 - 128) / ex->nSteady;
+            }
+            int left = nb;
+            for (int i = 0; i < nPlan && left > 0; ++i) {
+                const int c = i == nPlan - 1 ? left : std::min(left, std::max(1, (int)((long long)nb * plan[i] / 1024)));
+                chunkLen[nChunks++] = c; left -= c;
+            }
+            if (left > 0) chunkLen[nChunks - 1] += left;
         } else {
             const int parts = nb >= 64 ? 4 : 1;
             int left = nb;
@@ -2520,6 +2565,7 @@ int orbx_extract_batch(orbx_extractor *ex, const uint8_t *const *images, int bat
             uint8_t *lvl0 = ex->d_pyr + (size_t)c0 * G.frameBytes + G.lv[0].off;
             if (contiguous && step == (size_t)cols && G.lv[0].pitch == cols) {
                 // frames are back to back and rows are dense: one strided copy for the whole chunk
+                if (!(getenv("ORBX_DEBUG_SKIP_H2D") && ex->dbgCalls > 2))   // developer aid: reuse the frames the first calls copied in
                 CUDA_TRY(ex, cudaMemcpy2DAsync(lvl0, (size_t)G.frameBytes, images[b0 + c0], (size_t)rows * cols, (size_t)rows * cols, cn,
                                                cudaMemcpyHostToDevice, sIn));
             } else if (contiguous && step == (size_t)cols) {
@@ -2553,16 +2599,20 @@ int orbx_extract_batch(orbx_extractor *ex, const uint8_t *const *images, int bat
             CUDA_TRY(ex, cudaStreamWaitEvent(sOut, ex->evOut[k], 0));
             CUDA_TRY(ex, cudaMemcpyAsync(ex->h_nOut + c0, ex->d_nOut + c0, cn * sizeof(int), cudaMemcpyDeviceToHost, sOut));
             CUDA_TRY(ex, cudaMemcpyAsync(ex->h_mono + c0, ex->d_mono + c0, cn * sizeof(int), cudaMemcpyDeviceToHost, sOut));
+            if (!getenv("ORBX_DEBUG_SKIP_D2H")) {
             CUDA_TRY(ex, cudaMemcpyAsync(kps + ((size_t)b0 + c0) * cap, ex->d_kps + (size_t)c0 * cap, (size_t)cn * cap * sizeof(orbx_keypoint),
                                          cudaMemcpyDeviceToHost, sOut));
             CUDA_TRY(ex, cudaMemcpyAsync(desc + ((size_t)b0 + c0) * cap * 32, ex->d_desc + (size_t)c0 * cap * 32, (size_t)cn * cap * 32,
                                          cudaMemcpyDeviceToHost, sOut));
+            }
         }
+        const auto tEnq = std::chrono::steady_clock::now();
         CUDA_TRY(ex, cudaStreamSynchronize(sOut));
         for (int i = 0; i < ex->nSide; ++i) CUDA_TRY(ex, cudaStreamSynchronize(ex->sSide[i]));
         CUDA_TRY(ex, cudaStreamSynchronize(sC));
         if (getenv("ORBX_DEBUG_CHUNKS") && nChunks > 1) {   // developer aid: when each chunk's copy-in and kernels finished
-            fprintf(stderr, "[orbx chunks]");
+            fprintf(stderr, "[orbx chunks] host enqueue %.2f ms, total %.2f ms;", std::chrono::duration<double, std::milli>(tEnq - tStart).count(),
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tStart).count());
             for (int k = 1; k < nChunks; ++k) {
                 float a = 0, c = 0;
                 cudaEventElapsedTime(&a, ex->evIn[0], ex->evIn[k]);
