@@ -471,6 +471,32 @@ thread_local std::string tl_merr;
 
 }  // namespace
 
+// Frame::UndistortKeyPoints / ComputeImageBounds (src/Frame.cc:749-811): cv::undistortPoints(pts, K, D, R = I, P = K).
+// One thread per point; double precision, every operation individually rounded (the library is built -fmad=false),
+// five fixed-point iterations like OpenCV's default criteria.  xy points at the first float of the first (x, y) pair;
+// consecutive points are strideFloats apart (2 for packed pairs, 7 for cv::KeyPoint records).
+struct UndistortK { double fx, fy, cx, cy, k[14]; };
+__global__ void k_undistort(const float *__restrict__ xy, int strideIn, int n, UndistortK K, float *__restrict__ out, int strideOut) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double *k = K.k;
+    const double ifx = 1.0 / K.fx, ify = 1.0 / K.fy;
+    double x = ((double)xy[(size_t)i * strideIn] - K.cx) * ifx, y = ((double)xy[(size_t)i * strideIn + 1] - K.cy) * ify;
+    const double x0 = x, y0 = y;
+    for (int j = 0; j < 5; ++j) {
+        const double r2 = x * x + y * y;
+        const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+        if (icdist < 0) { x = x0; y = y0; break; }
+        const double dX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+        const double dY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+        x = (x0 - dX) * icdist;
+        y = (y0 - dY) * icdist;
+    }
+    const double xx = K.fx * x + 0.0 * y + K.cx, yy = 0.0 * x + K.fy * y + K.cy, ww = 1.0 / (0.0 * x + 0.0 * y + 1.0);
+    out[(size_t)i * strideOut] = (float)(xx * ww);
+    out[(size_t)i * strideOut + 1] = (float)(yy * ww);
+}
+
 struct orbx_matcher {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -826,6 +852,76 @@ int orbx_stereo_tail(orbx_matcher *m, const float *u_left, const float *u_right,
     MCUDA_TRY(m, cudaMemcpyAsync(mv_depth, ddp, (size_t)n_left * 4, cudaMemcpyDeviceToHost, s));
     MCUDA_TRY(m, cudaMemcpyAsync(n_kept, dn, 4, cudaMemcpyDeviceToHost, s));
     MCUDA_TRY(m, cudaStreamSynchronize(s));
+    return ORBX_OK;
+}
+
+static UndistortK make_undistort(float fx, float fy, float cx, float cy, const float *D, int nd) {
+    UndistortK K;
+    K.fx = fx; K.fy = fy; K.cx = cx; K.cy = cy;
+    for (int i = 0; i < 14; ++i) K.k[i] = i < nd ? (double)D[i] : 0.0;
+    return K;
+}
+
+int orbx_undistort_points_device(orbx_matcher *m, const float *d_xy, int stride_in, int n, float fx, float fy, float cx, float cy,
+                                 const float *dist_coef, int n_coef, float *d_out, int stride_out) {
+    if (!m) return ORBX_ERR_ARG;
+    if (n < 0 || stride_in < 2 || stride_out < 2 || n_coef < 0 || n_coef > 14 || (n_coef > 0 && !dist_coef) || (n > 0 && (!d_xy || !d_out))) {
+        m->err = "orbx_undistort_points_device: bad argument";
+        return ORBX_ERR_ARG;
+    }
+    if (n == 0) return ORBX_OK;
+    MCUDA_TRY(m, cudaSetDevice(m->device));
+    if (n_coef == 0 || dist_coef[0] == 0.0f) {          // mvKeysUn = mvKeys (src/Frame.cc:751-755)
+        if (d_out != d_xy || stride_in != stride_out)
+            MCUDA_TRY(m, cudaMemcpy2DAsync(d_out, (size_t)stride_out * 4, d_xy, (size_t)stride_in * 4, 8, n, cudaMemcpyDeviceToDevice, m->stream));
+        return ORBX_OK;
+    }
+    k_undistort<<<(n + 127) / 128, 128, 0, m->stream>>>(d_xy, stride_in, n, make_undistort(fx, fy, cx, cy, dist_coef, n_coef), d_out, stride_out);
+    MCUDA_TRY(m, cudaGetLastError());
+    return ORBX_OK;
+}
+
+int orbx_undistort_keypoints(orbx_matcher *m, const orbx_keypoint *kps, int n, float fx, float fy, float cx, float cy, const float *dist_coef,
+                             int n_coef, orbx_keypoint *kps_un) {
+    if (!m) return ORBX_ERR_ARG;
+    if (n < 0 || n_coef < 0 || n_coef > 14 || (n_coef > 0 && !dist_coef) || (n > 0 && (!kps || !kps_un))) { m->err = "orbx_undistort_keypoints: bad argument"; return ORBX_ERR_ARG; }
+    if (n == 0) return ORBX_OK;
+    MCUDA_TRY(m, cudaSetDevice(m->device));
+    const size_t bytes = (size_t)n * sizeof(orbx_keypoint);
+    int rc = stage(m, al256(bytes));
+    if (rc) return rc;
+    float *d = (float *)m->d_buf;
+    MCUDA_TRY(m, cudaMemcpyAsync(d, kps, bytes, cudaMemcpyHostToDevice, m->stream));
+    rc = orbx_undistort_points_device(m, d, 7, n, fx, fy, cx, cy, dist_coef, n_coef, d, 7);      // in place: only pt changes
+    if (rc) return rc;
+    MCUDA_TRY(m, cudaMemcpyAsync(kps_un, d, bytes, cudaMemcpyDeviceToHost, m->stream));
+    MCUDA_TRY(m, cudaStreamSynchronize(m->stream));
+    return ORBX_OK;
+}
+
+int orbx_image_bounds(orbx_matcher *m, int cols, int rows, float fx, float fy, float cx, float cy, const float *dist_coef, int n_coef,
+                      float *bounds4) {
+    if (!m) return ORBX_ERR_ARG;
+    if (!bounds4 || n_coef < 0 || n_coef > 14 || (n_coef > 0 && !dist_coef)) { m->err = "orbx_image_bounds: bad argument"; return ORBX_ERR_ARG; }
+    if (n_coef == 0 || dist_coef[0] == 0.0f) {          // src/Frame.cc:804-810
+        bounds4[0] = 0.f; bounds4[1] = (float)cols; bounds4[2] = 0.f; bounds4[3] = (float)rows;
+        return ORBX_OK;
+    }
+    MCUDA_TRY(m, cudaSetDevice(m->device));
+    int rc = stage(m, 256);
+    if (rc) return rc;
+    const float c[8] = {0.f, 0.f, (float)cols, 0.f, 0.f, (float)rows, (float)cols, (float)rows};
+    float u[8];
+    float *d = (float *)m->d_buf;
+    MCUDA_TRY(m, cudaMemcpyAsync(d, c, sizeof(c), cudaMemcpyHostToDevice, m->stream));
+    rc = orbx_undistort_points_device(m, d, 2, 4, fx, fy, cx, cy, dist_coef, n_coef, d + 8, 2);
+    if (rc) return rc;
+    MCUDA_TRY(m, cudaMemcpyAsync(u, d + 8, sizeof(u), cudaMemcpyDeviceToHost, m->stream));
+    MCUDA_TRY(m, cudaStreamSynchronize(m->stream));
+    bounds4[0] = u[0] < u[4] ? u[0] : u[4];
+    bounds4[1] = u[2] > u[6] ? u[2] : u[6];
+    bounds4[2] = u[1] < u[3] ? u[1] : u[3];
+    bounds4[3] = u[5] > u[7] ? u[5] : u[7];
     return ORBX_OK;
 }
 

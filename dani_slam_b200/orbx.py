@@ -85,6 +85,9 @@ def lib() -> C.CDLL:
     L.orbx_stereo_tail.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, f32, f32, vp, vp, vp]
     L.orbx_search_for_initialization.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, f32, i32, vp, vp]
     L.orbx_rot_hist_filter_device.argtypes = [vp, vp, vp, i32, vp]
+    L.orbx_undistort_keypoints.argtypes = [vp, vp, i32, f32, f32, f32, f32, vp, i32, vp]
+    L.orbx_undistort_points_device.argtypes = [vp, vp, i32, i32, f32, f32, f32, f32, vp, i32, vp, i32]
+    L.orbx_image_bounds.argtypes = [vp, i32, i32, f32, f32, f32, f32, vp, i32, vp]
     L.orbx_descriptor_distance.restype = i32
     L.orbx_descriptor_distance.argtypes = [vp, vp]
     L.orbx_vocab_create_from_nodes.restype = vp
@@ -402,6 +405,24 @@ class ORBmatcher:
         return n.value, ur, dp
 
     # device-pointer forms (ints), asynchronous on stream()
+    def UndistortKeyPoints(self, kps, K, distCoef):
+        """`Frame::UndistortKeyPoints` (src/Frame.cc:749-782): keypoint records with `pt` undistorted (K = (fx, fy, cx, cy))."""
+        kps = np.ascontiguousarray(kps, KP_DTYPE); D = np.ascontiguousarray(distCoef, np.float32)
+        out = np.zeros_like(kps)
+        self._chk(self.L.orbx_undistort_keypoints(self.h, _p(kps), len(kps), *[float(v) for v in K], _p(D), len(D), _p(out)))
+        return out
+
+    def undistort_points_device(self, d_xy, stride_in, n, K, distCoef, d_out, stride_out):
+        D = np.ascontiguousarray(distCoef, np.float32)
+        self._chk(self.L.orbx_undistort_points_device(self.h, d_xy, stride_in, n, *[float(v) for v in K], _p(D), len(D), d_out, stride_out))
+
+    def ComputeImageBounds(self, cols, rows, K, distCoef):
+        """`Frame::ComputeImageBounds` (src/Frame.cc:784-811) → (mnMinX, mnMaxX, mnMinY, mnMaxY)."""
+        D = np.ascontiguousarray(distCoef, np.float32)
+        b = np.zeros(4, np.float32)
+        self._chk(self.L.orbx_image_bounds(self.h, int(cols), int(rows), *[float(v) for v in K], _p(D), len(D), _p(b)))
+        return b
+
     def knn2_device(self, d_q, nq, d_db, ndb, idx_base, d_idx, d_dist):
         self._chk(self.L.orbx_hamming_knn2_device(self.h, d_q, nq, d_db, ndb, idx_base, d_idx, d_dist))
 

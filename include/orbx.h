@@ -177,6 +177,18 @@ int orbx_features_in_area(orbx_matcher *m, const float *keypoints_xy, const int3
 int orbx_stereo_tail(orbx_matcher *m, const float *u_left, const float *u_right, int n_left, int n_right, const int32_t *idx,
                      const int32_t *dist, const uint8_t *keep, float mbf, float mb, float *mvu_right, float *mv_depth,
                      int32_t *n_kept);
+/* Frame::UndistortKeyPoints (src/Frame.cc:749-782): kps_un = kps with pt replaced by cv::undistortPoints(pt, K, D, I, K);
+ * a plain copy when D[0] == 0 (:751).  dist_coef = k1 k2 p1 p2 [k3 …] (n_coef <= 14).  HOST buffers; bit-identical to
+ * cv2's result. */
+int orbx_undistort_keypoints(orbx_matcher *m, const orbx_keypoint *kps, int n, float fx, float fy, float cx, float cy, const float *dist_coef,
+                             int n_coef, orbx_keypoint *kps_un);
+/* Same on DEVICE (x, y) pairs that are stride_in / stride_out floats apart (2 = packed pairs, 7 = keypoint records, e.g.
+ * the array orbx_extract_batch_device wrote); asynchronous on the matcher's stream; in place is allowed. */
+int orbx_undistort_points_device(orbx_matcher *m, const float *d_xy, int stride_in, int n, float fx, float fy, float cx, float cy,
+                                 const float *dist_coef, int n_coef, float *d_out, int stride_out);
+/* Frame::ComputeImageBounds (src/Frame.cc:784-811): bounds4 = mnMinX, mnMaxX, mnMinY, mnMaxY. */
+int orbx_image_bounds(orbx_matcher *m, int cols, int rows, float fx, float fy, float cx, float cy, const float *dist_coef, int n_coef,
+                      float *bounds4);
 /* ORBmatcher::DescriptorDistance for one pair on the host (inline popcount; no device involved). */
 int orbx_descriptor_distance(const uint8_t *a, const uint8_t *b);
 

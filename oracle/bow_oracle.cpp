@@ -184,6 +184,48 @@ int orc_bow_transform(void *vp, const uint8_t *desc, int n, int levelsup, uint32
     return 0;
 }
 
+// ---- cv::undistortPoints as Frame::UndistortKeyPoints / ComputeImageBounds call it (src/Frame.cc:749-811) ----
+// OpenCV is not vendored; restated from its documented model (distortion k1 k2 p1 p2 k3 [k4 k5 k6 s1..s4], five fixed-point
+// iterations in double precision, then P = K) and pinned bit-for-bit against cv2 4.13.0 in tests/test_undistort.py.
+static void undistort_one(double px, double py, double fx, double fy, double cx, double cy, const double *k, float *ox, float *oy) {
+    const double ifx = 1.0 / fx, ify = 1.0 / fy;
+    double x = (px - cx) * ifx, y = (py - cy) * ify;
+    const double x0 = x, y0 = y;
+    for (int j = 0; j < 5; ++j) {
+        const double r2 = x * x + y * y;
+        const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+        if (icdist < 0) { x = x0; y = y0; break; }      // test for a zero crossing of the rational model
+        const double dX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+        const double dY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+        x = (x0 - dX) * icdist;
+        y = (y0 - dY) * icdist;
+    }
+    const double xx = fx * x + 0.0 * y + cx, yy = 0.0 * x + fy * y + cy, ww = 1.0 / (0.0 * x + 0.0 * y + 1.0);
+    *ox = (float)(xx * ww);
+    *oy = (float)(yy * ww);
+}
+
+void orc_undistort_points(const float *xy, int n, float fx, float fy, float cx, float cy, const float *D, int nd, float *out) {
+    if (nd <= 0 || D[0] == 0.0f) { memcpy(out, xy, (size_t)n * 8); return; }
+    double k[14] = {0};
+    for (int i = 0; i < nd && i < 14; ++i) k[i] = D[i];
+    for (int i = 0; i < n; ++i) undistort_one(xy[2 * i], xy[2 * i + 1], fx, fy, cx, cy, k, &out[2 * i], &out[2 * i + 1]);
+}
+
+void orc_image_bounds(int cols, int rows, float fx, float fy, float cx, float cy, const float *D, int nd, float *bounds) {
+    if (nd > 0 && D[0] != 0.0f) {
+        const float c[8] = {0.f, 0.f, (float)cols, 0.f, 0.f, (float)rows, (float)cols, (float)rows};
+        float u[8];
+        orc_undistort_points(c, 4, fx, fy, cx, cy, D, nd, u);
+        bounds[0] = u[0] < u[4] ? u[0] : u[4];      // min(x0, x2)
+        bounds[1] = u[2] > u[6] ? u[2] : u[6];      // max(x1, x3)
+        bounds[2] = u[1] < u[3] ? u[1] : u[3];      // min(y0, y1)
+        bounds[3] = u[5] > u[7] ? u[5] : u[7];      // max(y2, y3)
+    } else {
+        bounds[0] = 0.f; bounds[1] = (float)cols; bounds[2] = 0.f; bounds[3] = (float)rows;
+    }
+}
+
 double orc_bow_score_l1(const uint32_t *ids1, const double *v1, int n1, const uint32_t *ids2, const double *v2, int n2) {
     double score = 0;
     int i = 0, j = 0;

@@ -81,6 +81,8 @@ def lib() -> C.CDLL:
         L.orc_vocab_nodes.argtypes = [vp]
         L.orc_bow_transform.restype = i32
         L.orc_bow_transform.argtypes = [vp, vp, i32, i32] + [vp] * 9
+        L.orc_undistort_points.argtypes = [vp, i32, f32, f32, f32, f32, vp, i32, vp]
+        L.orc_image_bounds.argtypes = [i32, i32, f32, f32, f32, f32, vp, i32, vp]
         L.orc_bow_score_l1.restype = C.c_double
         L.orc_bow_score_l1.argtypes = [vp, vp, i32, vp, vp, i32]
         _lib = L
@@ -284,3 +286,17 @@ def bow_score_l1(ids1, v1, ids2, v2):
     ids1 = np.ascontiguousarray(ids1, np.uint32); ids2 = np.ascontiguousarray(ids2, np.uint32)
     v1 = np.ascontiguousarray(v1, np.float64); v2 = np.ascontiguousarray(v2, np.float64)
     return lib().orc_bow_score_l1(_p(ids1), _p(v1), len(ids1), _p(ids2), _p(v2), len(ids2))
+
+
+def undistort_points(xy, fx, fy, cx, cy, D):
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2); D = np.ascontiguousarray(D, np.float32)
+    out = np.zeros_like(xy)
+    lib().orc_undistort_points(_p(xy), len(xy), float(fx), float(fy), float(cx), float(cy), _p(D), len(D), _p(out))
+    return out
+
+
+def image_bounds(cols, rows, fx, fy, cx, cy, D):
+    D = np.ascontiguousarray(D, np.float32)
+    b = np.zeros(4, np.float32)
+    lib().orc_image_bounds(int(cols), int(rows), float(fx), float(fy), float(cx), float(cy), _p(D), len(D), _p(b))
+    return b

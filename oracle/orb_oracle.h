@@ -89,6 +89,12 @@ int orc_features_in_area(const float *xy, const int32_t *octave, int n, float mi
 int orc_stereo_tail(const float *uL, const float *uR, int nL, int nR, const int32_t *idx, const int32_t *dist,
                     const uint8_t *keep, float mbf, float mb, float *uRight, float *depth);
 
+/* Frame::UndistortKeyPoints / ComputeImageBounds (src/Frame.cc:749-811): cv::undistortPoints(pts, K, D, R = I, P = K) on n (x, y)
+ * float pairs; D has nd = 4 or 5 (or up to 14) coefficients; returns immediately with a copy when D[0] == 0 (:751).
+ * bounds[4] = mnMinX, mnMaxX, mnMinY, mnMaxY from the four image corners. */
+void orc_undistort_points(const float *xy, int n, float fx, float fy, float cx, float cy, const float *D, int nd, float *out);
+void orc_image_bounds(int cols, int rows, float fx, float fy, float cx, float cy, const float *D, int nd, float *bounds);
+
 /* ---- bag of words (bow_oracle.cpp): DBoW2 TemplatedVocabulary::transform as Frame::ComputeBoW calls it ---- */
 /* node stream like loadFromTextFile (TemplatedVocabulary.h:1378-1420): node i+1 has parent[i] (0 = root), leaf flag, 32-byte descriptor, weight */
 void *orc_vocab_from_nodes(const int32_t *parent, const uint8_t *is_leaf, const uint8_t *desc, const double *weight, int n_nodes,
