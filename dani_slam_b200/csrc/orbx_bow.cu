@@ -432,6 +432,7 @@ int orbx_bow_transform(orbx_vocab *v, const uint8_t *desc, int n, int levelsup, 
     }
     *n_bow = 0; *n_fv = 0; fv_off[0] = 0;
     if (n == 0) return ORBX_OK;
+    if (n > 16384) { v->err = "orbx_bow: more than 16384 descriptors per image"; return ORBX_ERR_CAPACITY; }
     std::lock_guard<std::mutex> lk(v->mu);
     VCUDA_TRY(v, cudaSetDevice(v->device));
     if (n > v->workCap) {
@@ -454,7 +455,7 @@ int orbx_bow_transform(orbx_vocab *v, const uint8_t *desc, int n, int levelsup, 
         v->workCap = n;
     }
     cudaStream_t s = v->stream;
-    const int cap = v->workCap;
+    const int cap = n;                       // one image: rows are sized by this call, not by the largest one seen
     int counts[3] = {n, 0, 0};
     VCUDA_TRY(v, cudaMemcpyAsync(v->w_counts, counts, sizeof(counts), cudaMemcpyHostToDevice, s));
     VCUDA_TRY(v, cudaMemcpyAsync(v->w_desc, desc, (size_t)n * 32, cudaMemcpyHostToDevice, s));

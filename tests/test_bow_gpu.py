@@ -119,3 +119,30 @@ def test_orbvoc_sized_tree_properties():
     assert np.array_equal(t2["bow_ids"], t["bow_ids"])
     orc = oracle.Vocabulary(voc=voc)
     _same(orc.transform(q[:2000], 4), dev.transform(q[:2000], 4))
+
+
+def test_vocabulary_shared_between_threads_and_capacity_error():
+    """The reference shares one const vocabulary between Tracking, LocalMapping and LoopClosing threads: concurrent
+    transform calls on one handle must give the single-threaded results.  More than 16384 descriptors per image is a
+    capacity error, not a crash."""
+    import threading
+    voc = synth.vocabulary(k=10, L=4, seed=51)
+    dev = orbx.ORBVocabulary().from_nodes(voc)
+    orc = oracle.Vocabulary(voc=voc)
+    qs = [synth.vocabulary_queries(voc, 700 + 37 * i, seed=i) for i in range(8)]
+    want = [orc.transform(q, 4) for q in qs]
+    got = [None] * len(qs)
+
+    def work(i):
+        for _ in range(5):
+            got[i] = dev.transform(qs[i], 4)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(qs))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for w, g in zip(want, got):
+        _same(w, g)
+    with pytest.raises(orbx.OrbxError) as e:
+        dev.transform(synth.vocabulary_queries(voc, 20000, seed=3), 4)
+    assert e.value.code == orbx.ERR_CAPACITY
+    _same(want[0], dev.transform(qs[0], 4))          # the handle stays usable

@@ -256,6 +256,21 @@ def test_legacy_quadtree_kernel_gives_the_same_result(orbx_mod, oracle_mod, monk
     assert mono == rmono and k.tobytes() == rk.tobytes() and np.array_equal(d, rd)
 
 
+def test_single_phase_fast_kernel_gives_the_same_result(orbx_mod, oracle_mod, monkeypatch):
+    """ORBX_FAST_V1=1 selects the earlier FAST kernel that evaluates the exact measure at every pixel: an independent
+    implementation of the same step, kept as a cross-check of the two-phase kernel."""
+    from dani_slam_b200 import synth
+    monkeypatch.setenv("ORBX_FAST_V1", "1")
+    ref = oracle_mod.Extractor(1000, 1.2, 8, 20, 7)
+    ex = orbx_mod.ORBextractor(1000, 1.2, 8, 20, 7, max_width=640, max_height=480)
+    for img in (synth.parity_frame(62), synth.throughput_frame(63)):
+        mono, k, d = ex(img, None, (0, 0))
+        rc, rk, rd, rmono = ref.extract(img)
+        for l in range(8):
+            assert sha(_xyz(ex.candidates(l))) == sha(_xyz(ref.candidates(l))), l
+        assert mono == rmono and k.tobytes() == rk.tobytes() and np.array_equal(d, rd)
+
+
 def test_left_right_extractors_run_concurrently_in_two_threads(orbx_mod, oracle_mod):
     """The reference extracts the left and right image in two std::threads with two extractor instances
     (src/Frame.cc:124-127); handles share no mutable state, so results must not depend on the interleaving."""
