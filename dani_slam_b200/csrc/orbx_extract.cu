@@ -498,19 +498,37 @@ __device__ __forceinline__ int fast_exact_entries(const uint8_t *roi, uint8_t *s
     return nN;
 }
 
-// One launch per pyramid level (cells cellBase .. cellBase+nCellsL of the cell table): shared memory is sized for that
-// level's own cell size, which is what bounds the number of resident warps.
+// A launch covers a range of the cell table whose cells need about the same shared memory ("slot" = the per-warp
+// footprint for cells up to cw × ch).  The few much taller cells of the small top levels ride along as "tall" cells that
+// take tallSlots adjacent slots each (the warps in between stay idle); their blocks come first in the grid so that
+// their longer per-cell latency overlaps the bulk of the work instead of forming a tail.
+struct FastRange {
+    int cellBase, nCells, cw, ch;                 // regular cells: one warp and one slot each
+    int tallBase, nTall, tallCw, tallCh;          // tall cells
+    int tallSlots, nTallBlocks;
+};
 template <int WPB>
-__global__ void __launch_bounds__(WPB * 32) k_fast_cells(ExParams p, int cellBase, int nCellsL, int maxCw, int maxCh) {
+__global__ void __launch_bounds__(WPB * 32) k_fast_cells(ExParams p, FastRange R) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const OrbxGeom &g = *p.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cl = blockIdx.x * WPB + warp, b = blockIdx.y;
-    if (cl >= nCellsL) return;  // warps are independent: no block-level barrier below
-    const int c = cellBase + cl;
+    const int b = blockIdx.y;
+    const size_t slotBytes = (size_t)fast_smem_layout(R.cw, R.ch, 1).total2;
+    int c, maxCw, maxCh;
+    if ((int)blockIdx.x < R.nTallBlocks) {
+        const int perBlock = WPB / R.tallSlots;
+        if (warp % R.tallSlots != 0 || warp / R.tallSlots >= perBlock) return;
+        const int cl = blockIdx.x * perBlock + warp / R.tallSlots;
+        if (cl >= R.nTall) return;
+        c = R.tallBase + cl; maxCw = R.tallCw; maxCh = R.tallCh;
+    } else {
+        const int cl = (blockIdx.x - R.nTallBlocks) * WPB + warp;
+        if (cl >= R.nCells) return;  // warps are independent: no block-level barrier below
+        c = R.cellBase + cl; maxCw = R.cw; maxCh = R.ch;
+    }
     const OrbxCell cell = p.cells[c];
     const FastSmem L = fast_smem_layout(maxCw, maxCh, 1);
-    uint8_t *base = smem_raw + (size_t)warp * L.total2;
+    uint8_t *base = smem_raw + (size_t)warp * slotBytes;
     uint8_t *roi = base + L.roiOff;
     uint8_t *score = base + L.scoreOff;
     uint16_t *queue = reinterpret_cast<uint16_t *>(base + L.entryOff);
@@ -2214,12 +2232,14 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
                 ++ex->launches;
             }
         } else {
-            // Consecutive levels whose cells need about the same shared memory (within 20 %) share a launch: the small
-            // top levels have much taller cells (2 rows of cells cover the level) and would otherwise set the per-warp
+            // Consecutive levels whose cells need about the same shared memory (within 20 %) form a group: the small top
+            // levels have much taller cells (2 rows of cells cover the level) and would otherwise set the per-warp
             // footprint, hence the resident warps, for everybody.
-            int l0 = 0;
-            while (l0 < G.nlevels) {
-                int cwMax = 0, chMax = 0, l1 = l0, nC = 0;
+            struct Grp { int cellBase, nCells, cw, ch; size_t need; };
+            Grp grp[ORBX_MAX_LEVELS];
+            int nGrp = 0;
+            for (int l0 = 0; l0 < G.nlevels;) {
+                int cwMax = 0, chMax = 0, l1 = l0, nC = 0, cellBase = -1;
                 size_t lo = 0, hi = 0;
                 for (; l1 < G.nlevels; ++l1) {
                     const OrbxLevel &V = G.lv[l1];
@@ -2228,17 +2248,32 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
                     if (nC > 0 && (std::max(hi, need) * 5 > std::min(lo, need) * 6)) break;
                     lo = nC ? std::min(lo, need) : need; hi = std::max(hi, need);
                     cwMax = std::max(cwMax, V.wCell + 6); chMax = std::max(chMax, V.hCell + 6);
+                    if (cellBase < 0) cellBase = V.cellBase;
                     nC += V.nCells;
                 }
-                if (nC > 0) {
-                    int cellBase = -1;
-                    for (int l = l0; l < l1 && cellBase < 0; ++l) if (G.lv[l].nCells > 0) cellBase = G.lv[l].cellBase;
-                    const size_t smem = (size_t)fast_smem_layout(cwMax, chMax, 1).total2 * WPB;
-                    if (smem > 48 * 1024) CUDA_TRY(ex, cudaFuncSetAttribute(k_fast_cells<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    k_fast_cells<WPB><<<dim3((nC + WPB - 1) / WPB, batch), WPB * 32, smem, s>>>(P, cellBase, nC, cwMax, chMax);
-                    ++ex->launches;
-                }
+                if (nC > 0) grp[nGrp++] = Grp{cellBase, nC, cwMax, chMax, (size_t)fast_smem_layout(cwMax, chMax, 1).total2};
                 l0 = l1;
+            }
+            // the usual shape is one big group plus a small group of tall cells: one launch, tall cells on several slots
+            bool merged = false;
+            if (nGrp == 2 && grp[1].nCells * 8 <= grp[0].nCells) {
+                const int slots = (int)((grp[1].need + grp[0].need - 1) / grp[0].need);
+                if (slots <= WPB) {
+                    FastRange R{grp[0].cellBase, grp[0].nCells, grp[0].cw, grp[0].ch, grp[1].cellBase, grp[1].nCells, grp[1].cw, grp[1].ch, slots, 0};
+                    R.nTallBlocks = (grp[1].nCells + WPB / slots - 1) / (WPB / slots);
+                    const size_t smem = grp[0].need * WPB;
+                    if (smem > 48 * 1024) CUDA_TRY(ex, cudaFuncSetAttribute(k_fast_cells<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    k_fast_cells<WPB><<<dim3(R.nTallBlocks + (R.nCells + WPB - 1) / WPB, batch), WPB * 32, smem, s>>>(P, R);
+                    ++ex->launches;
+                    merged = true;
+                }
+            }
+            for (int i = 0; i < nGrp && !merged; ++i) {
+                FastRange R{grp[i].cellBase, grp[i].nCells, grp[i].cw, grp[i].ch, 0, 0, grp[i].cw, grp[i].ch, 1, 0};
+                const size_t smem = grp[i].need * WPB;
+                if (smem > 48 * 1024) CUDA_TRY(ex, cudaFuncSetAttribute(k_fast_cells<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_fast_cells<WPB><<<dim3((R.nCells + WPB - 1) / WPB, batch), WPB * 32, smem, s>>>(P, R);
+                ++ex->launches;
             }
         }
     }
