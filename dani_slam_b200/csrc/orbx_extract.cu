@@ -1894,7 +1894,6 @@ struct orbx_extractor {
     unsigned *d_best = nullptr; size_t bestCap = 0;
     int *d_cellPrefix = nullptr; size_t cellPrefixCap = 0;
     int *d_deep = nullptr;
-    long long *d_dbg = nullptr;
     uint8_t *d_stage = nullptr; size_t stageCap = 0;   // packed H2D staging when the level-0 pitch is padded
     int lastBatch = 0;
     bool lastIn0Internal = true;
@@ -2472,7 +2471,6 @@ orbx_extractor *orbx_create(int nfeatures, float scale_factor, int nlevels, int 
     CREATE_TRY(cudaMalloc((void **)&ex->d_deep, (size_t)max_batch * ORBX_MAX_LEVELS * sizeof(int)));
     ex->useHistQuadtree = getenv("ORBX_LEGACY_QUADTREE") == nullptr;
     ex->fastV1 = getenv("ORBX_FAST_V1") != nullptr;
-    if (getenv("ORBX_DEBUG_TIMELINE")) { CREATE_TRY(cudaMalloc((void **)&ex->d_dbg, 32 * sizeof(long long))); CREATE_TRY(cudaMemset(ex->d_dbg, 0, 32 * sizeof(long long))); }
     CREATE_TRY(cudaMalloc((void **)&ex->d_nOut, (size_t)max_batch * sizeof(int)));
     CREATE_TRY(cudaMalloc((void **)&ex->d_mono, (size_t)max_batch * sizeof(int)));
     CREATE_TRY(cudaHostAlloc((void **)&ex->h_nOut, (size_t)max_batch * sizeof(int), cudaHostAllocDefault));
@@ -2493,7 +2491,7 @@ void orbx_destroy(orbx_extractor *ex) {
     if (ex->stream) cudaStreamSynchronize(ex->stream);
     void *ptrs[] = {ex->d_geom, ex->d_cells, ex->d_tiles, ex->d_tabX, ex->d_tabY, ex->d_tabXOff, ex->d_tabYOff,
                     ex->d_pattern, ex->d_patternF, ex->d_pyr, ex->d_blur, ex->d_slots, ex->d_ptNode, ex->d_ptXY, ex->d_cellCnt,
-                    ex->d_sel, ex->d_work, ex->d_selCnt, ex->d_workCnt, ex->d_hist, ex->d_finalPos, ex->d_best, ex->d_cellPrefix, ex->d_deep, ex->d_dbg, ex->d_stage, ex->d_kps, ex->d_desc, ex->d_nOut, ex->d_mono};
+                    ex->d_sel, ex->d_work, ex->d_selCnt, ex->d_workCnt, ex->d_hist, ex->d_finalPos, ex->d_best, ex->d_cellPrefix, ex->d_deep, ex->d_stage, ex->d_kps, ex->d_desc, ex->d_nOut, ex->d_mono};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ex->h_nOut) cudaFreeHost(ex->h_nOut);
     if (ex->h_mono) cudaFreeHost(ex->h_mono);
@@ -2702,13 +2700,6 @@ int orbx_debug_deep_count(orbx_extractor *ex) {
     return n;
 }
 
-// developer hook (ORBX_DEBUG_TIMELINE=1): clock64 stamps of the level-0 quadtree block of frame 0; out[31] = count
-int orbx_debug_timeline(orbx_extractor *ex, long long *out32) {
-    if (!ex || !out32 || !ex->d_dbg) return ORBX_ERR_ARG;
-    CUDA_TRY(ex, cudaStreamSynchronize(ex->stream));
-    CUDA_TRY(ex, cudaMemcpy(out32, ex->d_dbg, 32 * sizeof(long long), cudaMemcpyDeviceToHost));
-    return ORBX_OK;
-}
 
 int orbx_set_profiling(orbx_extractor *ex, int on) {
     if (!ex) return ORBX_ERR_ARG;

@@ -235,10 +235,6 @@ int orbx_bow_transform_batch_device(orbx_vocab *v, const uint8_t *d_desc, size_t
  * the general quadtree kernel (trees deeper than its table); -1 if the histogram kernel is disabled. */
 int orbx_debug_deep_count(orbx_extractor *ex);
 
-/* Developer hook (set ORBX_DEBUG_TIMELINE=1 before orbx_create): clock64 stamps taken by the level-0 quadtree
- * block of frame 0 at its phase boundaries; out32[31] = number of stamps. */
-int orbx_debug_timeline(orbx_extractor *ex, long long *out32);
-
 /* Test hook: the device/host port of libstdc++ std::sort used by the quadtree (see stdsort_port.h),
  * run on the host; perm_out = resulting order of original indices. */
 void orbx_debug_sort_nodes(const int32_t *sizes, const int32_t *ulx, int n, int32_t *perm_out);
