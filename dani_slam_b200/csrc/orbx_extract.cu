@@ -92,7 +92,8 @@ __device__ __forceinline__ const uint8_t *level_ptr(const ExParams &p, const Orb
 struct PyrArgs {             // everything by value: no dependent global loads before the pixel loads
     const uint8_t *src; long long srcStride; int sp, sw, sh;
     uint8_t *dst; long long dstStride; int dp, dw, dh;
-    const int2 *tabX, *tabY;
+    const int2 *tabX, *tabY;         // per destination column {source column, a0 | a1<<16}; per row {i0 | i1<<16 (clamped source rows), b0 | b1<<16}
+    const int2 *tileX, *tileY;       // per tile column {first staged source column (16-aligned) | 16-byte chunks<<16, rcp of the chunks}; per tile row {first source row, rows}
     int tilesX, srcRows, srcPitch;   // shared-memory source tile: srcRows × srcPitch bytes (pitch multiple of 16)
 };
 __global__ void __launch_bounds__(256) k_pyr_level(PyrArgs a) {
@@ -104,20 +105,16 @@ __global__ void __launch_bounds__(256) k_pyr_level(PyrArgs a) {
     const int x0 = tx * PYR_TW, y0 = ty * PYR_TH;
     const int tid = threadIdx.x;
     const uint8_t *S = a.src + (long long)b * a.srcStride;
-    const int sp = a.sp, sw = a.sw, sh = a.sh;
-    const int yLast = min(y0 + PYR_TH, a.dh) - 1, xLast = min(x0 + PYR_TW, a.dw) - 1;
-    const int r0 = min(max(a.tabY[y0].x, 0), sh - 1);
-    const int r1 = min(max(a.tabY[yLast].x + 1, 0), sh - 1);
-    const int nR = min(r1 - r0 + 1, a.srcRows);
-    const int c0a = a.tabX[x0].x & ~15;
-    const int cLast = min(a.tabX[xLast].x + 1, sw - 1);
-    const int nChunks = min((cLast - c0a) / 16 + 1, a.srcPitch / 16);
+    const int sp = a.sp, sw = a.sw;
+    const int2 tX = a.tileX[tx], tY = a.tileY[ty];       // tile geometry, precomputed on the host
+    const int c0a = tX.x & 0xffff, nChunks = tX.x >> 16, r0 = tY.x, nR = tY.y;
+    const uint32_t rcpChunks = (uint32_t)tX.y;           // (i * rcp) >> 16 == i / nChunks for i < 32768
     const bool aligned = ((((unsigned long long)S | (unsigned)sp) & 15ull) == 0);
     // phase 0: stage the source tile with 16-byte loads
     {
         const int rowBytes = aligned ? min(sp, (sw + 15) & ~15) : sw;
         for (int i = tid; i < nR * nChunks; i += 256) {
-            const int r = i / nChunks, c = i - r * nChunks;
+            const int r = (int)(((uint32_t)i * rcpChunks) >> 16), c = i - r * nChunks;
             const int gx = c0a + 16 * c;
             uint4 v = make_uint4(0, 0, 0, 0);
             if (gx < rowBytes) {
@@ -153,30 +150,31 @@ __global__ void __launch_bounds__(256) k_pyr_level(PyrArgs a) {
         }
     }
     __syncthreads();
-    // phase 2: thread owns 4 destination columns, two output rows
+    // phase 2: thread owns 4 destination columns of four output rows (8 rows apart); all quantities are non-negative
+    // (coefficients 0..2048, sums < 2^16), so the arithmetic shifts of the reference are plain unsigned shifts
     {
         const int cx = (tid & 31) * 4;
         const int gx = x0 + cx;
         if (gx < a.dw) {
-            uint8_t *Dp = a.dst + (long long)b * a.dstStride + gx;
+            const int yy0 = tid >> 5;
+            uint8_t *Dp = a.dst + (long long)b * a.dstStride + (long long)(y0 + yy0) * a.dp + gx;
+            const long long rowStep = 8ll * a.dp;
+            const int2 *tyP = a.tabY + y0 + yy0;
 #pragma unroll
-            for (int k = 0; k < PYR_TH / 8; ++k) {
-                const int yy = (tid >> 5) + 8 * k, gy = y0 + yy;
-                if (gy < a.dh) {
-                    const int2 ty2 = a.tabY[gy];
-                    const int i0 = min(max(ty2.x, 0), sh - 1) - r0, i1 = min(max(ty2.x + 1, 0), sh - 1) - r0;
-                    const int b0 = (short)(ty2.y & 0xffff), b1 = (short)(ty2.y >> 16);
+            for (int k = 0; k < PYR_TH / 8; ++k, Dp += rowStep) {
+                if (y0 + yy0 + 8 * k < a.dh) {
+                    const int2 ty2 = tyP[8 * k];
+                    const uint32_t rows = (uint32_t)ty2.x, cf = (uint32_t)ty2.y;
+                    const int i0 = (int)(rows & 0xffffu) - r0, i1 = (int)(rows >> 16) - r0;
+                    const uint32_t b0 = cf & 0xffffu, b1 = cf >> 16;
                     const uint2 u0 = *reinterpret_cast<const uint2 *>(&H[i0][cx]);
                     const uint2 u1 = *reinterpret_cast<const uint2 *>(&H[i1][cx]);
-                    const int h0[4] = {(int)(u0.x & 0xffff), (int)(u0.x >> 16), (int)(u0.y & 0xffff), (int)(u0.y >> 16)};
-                    const int h1[4] = {(int)(u1.x & 0xffff), (int)(u1.x >> 16), (int)(u1.y & 0xffff), (int)(u1.y >> 16)};
-                    uint32_t out = 0;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int v = (((b0 * h0[i]) >> 16) + ((b1 * h1[i]) >> 16) + 2) >> 2;
-                        out |= (uint32_t)(v & 0xff) << (8 * i);
-                    }
-                    *reinterpret_cast<uint32_t *>(Dp + (long long)gy * a.dp) = out;  // pitch multiple of 128: padding is writable
+                    const uint32_t v0 = (((b0 * (u0.x & 0xffffu)) >> 16) + ((b1 * (u1.x & 0xffffu)) >> 16) + 2u) >> 2;
+                    const uint32_t v1 = (((b0 * (u0.x >> 16)) >> 16) + ((b1 * (u1.x >> 16)) >> 16) + 2u) >> 2;
+                    const uint32_t v2 = (((b0 * (u0.y & 0xffffu)) >> 16) + ((b1 * (u1.y & 0xffffu)) >> 16) + 2u) >> 2;
+                    const uint32_t v3 = (((b0 * (u0.y >> 16)) >> 16) + ((b1 * (u1.y >> 16)) >> 16) + 2u) >> 2;
+                    // v <= 255: bytes are packed by multiply-add (no masks needed)
+                    *reinterpret_cast<uint32_t *>(Dp) = v0 + (v1 << 8) + (v2 << 16) + (v3 << 24);  // pitch multiple of 128: padding is writable
                 }
             }
         }
@@ -1882,7 +1880,7 @@ struct orbx_extractor {
     int curLap0 = 0, curLap1 = 0;
     std::vector<int> curRects;
     bool geomDirty = true;
-    int h_tabXOff[ORBX_MAX_LEVELS] = {0}, h_tabYOff[ORBX_MAX_LEVELS] = {0};
+    int h_tabXOff[ORBX_MAX_LEVELS] = {0}, h_tabYOff[ORBX_MAX_LEVELS] = {0}, h_tileXOff[ORBX_MAX_LEVELS] = {0}, h_tileYOff[ORBX_MAX_LEVELS] = {0};
     std::vector<OrbxCell> h_cells;
     std::vector<BlurTile> h_tiles;
     int maxSlotCap = 0, nodeCapMax = 0, maxCellsLevel = 0, maxIni = 1;
@@ -2044,7 +2042,7 @@ int upload_tables(orbx_extractor *ex) {
     OrbxGeom &G = ex->geom;
     // resize tables: identical arithmetic to cv::resize's coefficient set-up
     std::vector<int2> tx, ty;
-    std::vector<int> txo(ORBX_MAX_LEVELS, 0), tyo(ORBX_MAX_LEVELS, 0);
+    std::vector<int> txo(ORBX_MAX_LEVELS, 0), tyo(ORBX_MAX_LEVELS, 0), tileXo(ORBX_MAX_LEVELS, 0), tileYo(ORBX_MAX_LEVELS, 0);
     for (int l = 1; l < G.nlevels; ++l) {
         const int sw = G.lv[l - 1].w, sh = G.lv[l - 1].h, dw = G.lv[l].w, dh = G.lv[l].h;
         txo[l] = (int)tx.size();
@@ -2065,10 +2063,30 @@ int upload_tables(orbx_extractor *ex) {
             int s = (int)floorf(f);
             f -= s;
             const int b0 = (short)cv_round_f((1.f - f) * 2048.f), b1 = (short)cv_round_f(f * 2048.f);
-            ty.push_back(make_int2(s, (b0 & 0xffff) | (b1 << 16)));
+            const int i0 = std::min(std::max(s, 0), sh - 1), i1 = std::min(std::max(s + 1, 0), sh - 1);   // rows are clamped, weights are not (A1)
+            ty.push_back(make_int2(i0 | (i1 << 16), (b0 & 0xffff) | (b1 << 16)));
+        }
+        // per-tile geometry of k_pyr_level (what its prologue would otherwise derive from the tables)
+        const int tilesX = (dw + PYR_TW - 1) / PYR_TW, tilesY = (dh + PYR_TH - 1) / PYR_TH;
+        const int srcRows = (int)ceil((PYR_TH - 1) * (double)sh / dh) + 4;
+        const int srcPitch = 16 * ((int)ceil(((PYR_TW - 1) * (double)sw / dw + 18.0) / 16.0) + 1);
+        tileXo[l] = (int)tx.size();
+        for (int t = 0; t < tilesX; ++t) {
+            const int x0 = t * PYR_TW, xLast = std::min(x0 + PYR_TW, dw) - 1;
+            const int c0a = tx[txo[l] + x0].x & ~15;
+            const int cLast = std::min(tx[txo[l] + xLast].x + 1, sw - 1);
+            const int nChunks = std::min((cLast - c0a) / 16 + 1, srcPitch / 16);
+            tx.push_back(make_int2(c0a | (nChunks << 16), (65536 + nChunks - 1) / nChunks));
+        }
+        tileYo[l] = (int)ty.size();
+        for (int t = 0; t < tilesY; ++t) {
+            const int y0 = t * PYR_TH, yLast = std::min(y0 + PYR_TH, dh) - 1;
+            const int r0 = ty[tyo[l] + y0].x & 0xffff;
+            const int r1 = (ty[tyo[l] + yLast].x >> 16) & 0xffff;
+            ty.push_back(make_int2(r0, std::min(r1 - r0 + 1, srcRows)));
         }
     }
-    for (int l = 0; l < ORBX_MAX_LEVELS; ++l) { ex->h_tabXOff[l] = txo[l]; ex->h_tabYOff[l] = tyo[l]; }
+    for (int l = 0; l < ORBX_MAX_LEVELS; ++l) { ex->h_tabXOff[l] = txo[l]; ex->h_tabYOff[l] = tyo[l]; ex->h_tileXOff[l] = tileXo[l]; ex->h_tileYOff[l] = tileYo[l]; }
     int rc;
     if ((rc = ensure(ex, ex->d_tabX, ex->tabXCap, std::max<size_t>(tx.size(), 1)))) return rc;
     if ((rc = ensure(ex, ex->d_tabY, ex->tabYCap, std::max<size_t>(ty.size(), 1)))) return rc;
@@ -2213,6 +2231,7 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
         A.sw = G.lv[l - 1].w; A.sh = G.lv[l - 1].h;
         A.dst = P.pyr + G.lv[l].off; A.dstStride = G.frameBytes; A.dp = G.lv[l].pitch; A.dw = G.lv[l].w; A.dh = G.lv[l].h;
         A.tabX = ex->d_tabX + ex->h_tabXOff[l]; A.tabY = ex->d_tabY + ex->h_tabYOff[l];
+        A.tileX = ex->d_tabX + ex->h_tileXOff[l]; A.tileY = ex->d_tabY + ex->h_tileYOff[l];
         A.tilesX = tilesX; A.srcRows = srcRows; A.srcPitch = srcPitch;
         k_pyr_level<<<dim3(tilesX * tilesY, batch), 256, smem, s>>>(A);
         ++ex->launches;

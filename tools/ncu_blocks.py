@@ -8,7 +8,7 @@ h = rows[1]
 ie = h.index('Instructions Executed'); src = h.index('Source'); ws = h.index('L1 Wavefronts Shared'); wi = h.index('L1 Wavefronts Shared Ideal'); smp = h.index('# Samples')
 data = []; seen = set()
 for r in rows[2:]:
-    if r[0] in seen: continue
+    if len(r) <= ie or r[0] in seen: continue
     seen.add(r[0])
     try: n = int(r[ie])
     except ValueError: continue
