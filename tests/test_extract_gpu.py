@@ -310,6 +310,44 @@ def test_other_pyramid_shapes(orbx_mod, oracle_mod):
         assert rc == 0 and mono == rmono and k.tobytes() == rk.tobytes() and np.array_equal(d, rd), (nf, sfac, nl, ini, mn)
 
 
+def test_randomised_geometries_and_parameters(orbx_mod, oracle_mod):
+    """48 seeded draws of image size (down to the smallest a pyramid accepts), feature count, level count, scale factor,
+    thresholds, lapping window and dynamic rectangles; content mixes noise, ramps, flats and dots.  Small and odd sizes
+    produce one-cell levels, clipped cells narrower than the FAST ring and cells of very different heights in one launch."""
+    from dani_slam_b200 import synth
+    rng = np.random.default_rng(2024)
+    done = 0
+    for case in range(48):
+        nl = int(rng.integers(1, 9))
+        sfac = float(rng.choice([1.1, 1.2, 1.25, 1.4, 1.7]))
+        w = int(rng.integers(70, 420)); h = int(rng.integers(70, 330))
+        nf = int(rng.choice([40, 200, 700, 1500]))
+        ini = int(rng.integers(8, 40)); mn = int(rng.integers(3, ini + 1))
+        kind = case % 4
+        if kind == 0:
+            img = synth.parity_frame(case, w, h)
+        elif kind == 1:
+            img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        elif kind == 2:
+            yy, xx = np.mgrid[0:h, 0:w]
+            img = ((int(rng.integers(3, 15)) * xx + int(rng.integers(3, 15)) * yy) % 256).astype(np.uint8)
+        else:
+            img = synth.throughput_frame(case, w, h)
+        rects = [(int(rng.integers(0, w)), int(rng.integers(0, h)), int(rng.integers(5, 90)), int(rng.integers(5, 90))) for _ in range(int(rng.integers(0, 3)))]
+        lap = [(0, 0), (0, 1000), (w // 3, 2 * w // 3)][case % 3]
+        try:
+            ex = orbx_mod.ORBextractor(nf, sfac, nl, ini, mn, max_width=w, max_height=h)
+            ex.mvDynamicArea = rects
+            mono, k, d = ex(img, None, lap)
+        except orbx_mod.OrbxError as e:
+            assert e.code == orbx_mod.ERR_GEOMETRY or "orbx_create: image too" in str(e), (case, e)   # geometries the reference itself faults on
+            continue
+        rc, rk, rd, rmono = oracle_mod.Extractor(nf, sfac, nl, ini, mn).extract(img, rects=rects, lap=lap, cap=nf + 400)
+        assert rc == 0 and mono == rmono and k.tobytes() == rk.tobytes() and np.array_equal(d, rd), (case, w, h, nf, sfac, nl, ini, mn)
+        done += 1
+    assert done >= 30
+
+
 def test_many_seeded_frames_statistical_parity(orbx_mod, oracle_mod):
     """256 seeded frames (throughput + parity generators, three lapping windows): every keypoint record and
     descriptor equals the oracle's.  Rare paths (rounding of rotated taps at .5, std::sort tie permutations at the
