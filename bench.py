@@ -201,6 +201,31 @@ def run_reference(args, rank):
 
 
 # ----------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local_rank: int) -> None:
+    """One process per GPU: run on the CPUs of the GPU's NUMA node, so that the pinned host buffers (first touch) and the
+    copy submissions stay local to the GPU's PCIe root.  Best effort: does nothing when sysfs has no NUMA information."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local_rank)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        bus = bus[-12:] if len(bus) > 12 else bus                   # sysfs uses a 4-digit PCI domain
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        if node < 0 or len(nodes) < 2:
+            return
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b_ = part.partition("-")
+            cpus.update(range(int(a), int(b_ or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            print(f"[bench] rank {local_rank}: GPU {bus} on NUMA node {node}, bound to {len(cpus)} CPUs", file=sys.stderr)
+    except Exception as e:  # noqa: BLE001
+        print(f"[bench] NUMA binding skipped: {e}", file=sys.stderr)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -232,6 +257,10 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", str(29400 + os.getpid() % 500), os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
 
+    # NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION; rank 0's stdout must be the one JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
+    bind_to_gpu_numa_node(local_rank)
     import torch
     import torch.distributed as td
     from dani_slam_b200 import orbx, sharded
