@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(256) k_pyr_level(PyrArgs a) {
 struct FastSmem {
     int roiPitch, scorePitch;
     int roiOff, scoreOff, listOff, queueOff, total;     // v1 kernel
-    int entryOff, bothOff, total2;                      // two-phase kernel
+    int entryOff, bothOff, total2, qCap;                // two-phase kernel (qCap = entries the queue holds)
 };
 __host__ __device__ inline FastSmem fast_smem_layout(int maxCw, int maxCh, int maxSlotCap) {
     FastSmem s;
@@ -208,10 +208,13 @@ __host__ __device__ inline FastSmem fast_smem_layout(int maxCw, int maxCh, int m
     s.listOff = s.scoreOff + s.scorePitch * (maxCh - 6 + 2);
     s.queueOff = s.listOff + 4 * maxSlotCap;             // u16 per 4-pixel group: groups whose score word is non-zero
     s.total = (s.queueOff + 2 * G * (maxCh - 6) + 15) & ~15;
-    // two-phase kernel: u16 entry per interior pixel (worst case: every pixel passes the compass test), twice
+    // two-phase kernel: the entry queue holds half of the cell's pixels (a third pass the compass test on corner-dense
+    // frames); a cell that needs more is handed to the single-phase kernel (k_fast_cells_v1), like the quadtree's deep
+    // fallback — shared memory per warp decides how many warps an SM holds
     const int nPix = 4 * G * (maxCh - 6);
+    s.qCap = (nPix / 2 + 1) & ~1;
     s.entryOff = (s.listOff + 3) & ~3;
-    s.bothOff = s.entryOff + 2 * nPix + 4;
+    s.bothOff = s.entryOff + 2 * s.qCap + 4;
     s.total2 = (s.bothOff + 2 * FAST_BOTH_CAP + 15) & ~15;
     return s;
 }
@@ -273,16 +276,11 @@ __device__ __forceinline__ uint32_t fast_pair_score(const Row3 (&R)[7], uint32_t
     return __vmaxu2(M, biasT2) - biasT2;                                      // max(M - lowTh, 0) per half
 }
 
-template <int WPB>
-__global__ void __launch_bounds__(WPB * 32) k_fast_cells_v1(ExParams p, int maxSlotCap) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+// single-phase FAST of one cell by one warp (`base` = the warp's shared memory, fast_smem_layout(...).total bytes)
+__device__ void fast_cell_v1(const ExParams &p, int maxSlotCap, int c, int b, uint8_t *base, int lane) {
     const OrbxGeom &g = *p.g;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c = blockIdx.x * WPB + warp, b = blockIdx.y;
-    if (c >= g.nCellsTotal) return;  // warps are independent: no block-level barrier below
     const OrbxCell cell = p.cells[c];
     const FastSmem L = fast_smem_layout(g.maxCw, g.maxCh, maxSlotCap);
-    uint8_t *base = smem_raw + (size_t)warp * L.total;
     uint8_t *roi = base + L.roiOff;
     uint8_t *score = base + L.scoreOff;
     uint32_t *list = reinterpret_cast<uint32_t *>(base + L.listOff);
@@ -424,6 +422,30 @@ __global__ void __launch_bounds__(WPB * 32) k_fast_cells_v1(ExParams p, int maxS
     if (lane == 0) *cntOut = m;
 }
 
+// every cell of the cell table (ORBX_FAST_V1=1: cross-check of the two-phase kernel)
+template <int WPB>
+__global__ void __launch_bounds__(WPB * 32) k_fast_cells_v1(ExParams p, int maxSlotCap) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * WPB + warp, b = blockIdx.y;
+    if (c >= p.g->nCellsTotal) return;  // warps are independent: no block-level barrier
+    fast_cell_v1(p, maxSlotCap, c, b, smem_raw + (size_t)warp * fast_smem_layout(p.g->maxCw, p.g->maxCh, maxSlotCap).total, lane);
+}
+// the cells the two-phase kernel could not hold (list of (frame, cell) appended by k_fast_cells); a small fixed grid
+// whose warps stride over the list, so that the usual empty list costs one short launch
+template <int WPB>
+__global__ void __launch_bounds__(WPB * 32) k_fast_cells_v1_list(ExParams p, int maxSlotCap, const int2 *list, const int *count) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *base = smem_raw + (size_t)warp * fast_smem_layout(p.g->maxCw, p.g->maxCh, maxSlotCap).total;
+    const int n = *count;
+    for (int i = blockIdx.x * WPB + warp; i < n; i += gridDim.x * WPB) {
+        const int2 e = list[i];
+        fast_cell_v1(p, maxSlotCap, e.y, e.x, base, lane);
+        __syncwarp();
+    }
+}
+
 // ---- two-phase FAST: compass pre-test on every pixel, exact measure only for the pixels that pass ----
 // An arc of 9 contiguous ring pixels contains at least one of every opposite pair {k, k+8}, so
 //   A = max_arcs min_k (v - r_k) <= min(max(v-r0, v-r8), max(v-r4, v-r12))   (and the same for B with r - v):
@@ -504,9 +526,11 @@ struct FastRange {
     int cellBase, nCells, cw, ch;                 // regular cells: one warp and one slot each
     int tallBase, nTall, tallCw, tallCh;          // tall cells
     int tallSlots, nTallBlocks;
+    int2 *denseList; int *denseN;                 // (frame, cell) pairs whose candidates overflow the entry queue
 };
 template <int WPB>
-__global__ void __launch_bounds__(WPB * 32) k_fast_cells(ExParams p, FastRange R) {
+__global__ void __launch_bounds__(WPB * 32, 2048 / (WPB * 32 * 2)) k_fast_cells(ExParams p, FastRange R) {   // ≤ 64 registers: 32 warps per SM
+
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const OrbxGeom &g = *p.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -588,6 +612,7 @@ __global__ void __launch_bounds__(WPB * 32) k_fast_cells(ExParams p, FastRange R
     const uint32_t lastMask = nValidLast >= 4 ? 0x80808080u : (0x80808080u & ((1u << (8 * nValidLast)) - 1u));
     uint32_t *out = p.slots + (long long)b * g.slotsTotal + cell.slot;
     int m = 0;
+    bool dense = false;
     // the reference runs cv::FAST at iniThFAST and, when that leaves nothing after NMS, again at minThFAST (:826-846)
     for (int attempt = 0; attempt < 2; ++attempt) {
         const int t = attempt == 0 ? g.iniTh : g.minTh;
@@ -634,12 +659,14 @@ __global__ void __launch_bounds__(WPB * 32) k_fast_cells(ExParams p, FastRange R
             }
             const int cnt = __popc(pm);
             const uint32_t b0 = __ballot_sync(0xffffffffu, cnt & 1), b1 = __ballot_sync(0xffffffffu, cnt & 2), b2 = __ballot_sync(0xffffffffu, cnt & 4);
+            const int nNew = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+            if (nE + nNew > L.qCap) { dense = true; break; }      // warp-uniform: more corners than the queue holds
             uint16_t *qa = queue + nE + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
             if (pm & 0x80u) *qa++ = (uint16_t)((uint32_t)off | ((tq << 8) & 0xc000u));
             if (pm & 0x8000u) *qa++ = (uint16_t)((uint32_t)(off + 1) | (tq & 0xc000u));
             if (pm & 0x800000u) *qa++ = (uint16_t)((uint32_t)(off + 2) | ((tq >> 8) & 0xc000u));
             if (pm & 0x80000000u) *qa = (uint16_t)((uint32_t)(off + 3) | ((tq >> 16) & 0xc000u));
-            nE += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+            nE += nNew;
             if (__any_sync(0xffffffffu, bo != 0)) {   // rare: pixels that pass on both sides get their B side done first
                 const int cb = __popc(bo);
                 const uint32_t c0 = __ballot_sync(0xffffffffu, cb & 1), c1 = __ballot_sync(0xffffffffu, cb & 2), c2 = __ballot_sync(0xffffffffu, cb & 4);
@@ -652,6 +679,7 @@ __global__ void __launch_bounds__(WPB * 32) k_fast_cells(ExParams p, FastRange R
             lg += stepGroups; off += stepOff;
             if (lg >= G) { lg -= G; off += wrapOff; }
         }
+        if (dense) break;
         __syncwarp();
         // phase 2: exact measure of the entries (B sides of two-sided pixels first, then everything else)
         if (nB > 0) {
@@ -682,7 +710,10 @@ __global__ void __launch_bounds__(WPB * 32) k_fast_cells(ExParams p, FastRange R
         if (m > 0) break;
         __syncwarp();
     }
-    if (lane == 0) *cntOut = m;
+    if (lane == 0) {
+        if (dense) R.denseList[atomicAdd(R.denseN, 1)] = make_int2(b, c);    // the single-phase kernel redoes this cell
+        else *cntOut = m;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1892,6 +1923,10 @@ struct orbx_extractor {
     unsigned *d_best = nullptr; size_t bestCap = 0;
     int *d_cellPrefix = nullptr; size_t cellPrefixCap = 0;
     int *d_deep = nullptr;
+    int *d_dense = nullptr;        // per run (indexed by its first frame): cells the two-phase FAST kernel handed to the single-phase one
+    int2 *d_denseList = nullptr; size_t denseListCap = 0;
+    std::vector<int> denseSlots;   // counters the last public call used
+    int nSM = 148;
     uint8_t *d_stage = nullptr; size_t stageCap = 0;   // packed H2D staging when the level-0 pitch is padded
     int lastBatch = 0;
     bool lastIn0Internal = true;
@@ -2134,6 +2169,7 @@ int ensure_buffers(orbx_extractor *ex, int batch) {
     if ((rc = ensure(ex, ex->d_finalPos, ex->finalPosCap, B * (size_t)G.nlevels * (size_t)ex->maxIni * QT_TREE))) return rc;
     if ((rc = ensure(ex, ex->d_best, ex->bestCap, B * (size_t)std::max(G.selTotal, 1)))) return rc;
     if ((rc = ensure(ex, ex->d_cellPrefix, ex->cellPrefixCap, B * (size_t)std::max(G.nCellsTotal, 1)))) return rc;
+    if ((rc = ensure(ex, ex->d_denseList, ex->denseListCap, B * (size_t)std::max(G.nCellsTotal, 1)))) return rc;
     size_t selNeed = B * (size_t)std::max(G.selTotal, 1);
     if (selNeed > ex->selCap || !ex->d_sel) {
         if (ex->d_sel) cudaFree(ex->d_sel);
@@ -2250,6 +2286,11 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
                 ++ex->launches;
             }
         } else {
+            // dense-cell list of this run: frames [f, f+batch) own the list rows f*nCells.. and the counter at index f
+            int2 *denseList = ex->d_denseList + f * (size_t)G.nCellsTotal;
+            int *denseN = ex->d_dense + f;
+            CUDA_TRY(ex, cudaMemsetAsync(denseN, 0, sizeof(int), s));
+            ex->denseSlots.push_back((int)f);
             // Consecutive levels whose cells need about the same shared memory (within 20 %) form a group: the small top
             // levels have much taller cells (2 rows of cells cover the level) and would otherwise set the per-warp
             // footprint, hence the resident warps, for everybody.
@@ -2277,7 +2318,7 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
             if (nGrp == 2 && grp[1].nCells * 8 <= grp[0].nCells) {
                 const int slots = (int)((grp[1].need + grp[0].need - 1) / grp[0].need);
                 if (slots <= WPB) {
-                    FastRange R{grp[0].cellBase, grp[0].nCells, grp[0].cw, grp[0].ch, grp[1].cellBase, grp[1].nCells, grp[1].cw, grp[1].ch, slots, 0};
+                    FastRange R{grp[0].cellBase, grp[0].nCells, grp[0].cw, grp[0].ch, grp[1].cellBase, grp[1].nCells, grp[1].cw, grp[1].ch, slots, 0, denseList, denseN};
                     R.nTallBlocks = (grp[1].nCells + WPB / slots - 1) / (WPB / slots);
                     const size_t smem = grp[0].need * WPB;
                     if (smem > 48 * 1024) CUDA_TRY(ex, cudaFuncSetAttribute(k_fast_cells<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -2287,10 +2328,18 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
                 }
             }
             for (int i = 0; i < nGrp && !merged; ++i) {
-                FastRange R{grp[i].cellBase, grp[i].nCells, grp[i].cw, grp[i].ch, 0, 0, grp[i].cw, grp[i].ch, 1, 0};
+                FastRange R{grp[i].cellBase, grp[i].nCells, grp[i].cw, grp[i].ch, 0, 0, grp[i].cw, grp[i].ch, 1, 0, denseList, denseN};
                 const size_t smem = grp[i].need * WPB;
                 if (smem > 48 * 1024) CUDA_TRY(ex, cudaFuncSetAttribute(k_fast_cells<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 k_fast_cells<WPB><<<dim3((R.nCells + WPB - 1) / WPB, batch), WPB * 32, smem, s>>>(P, R);
+                ++ex->launches;
+            }
+            // cells with more corner candidates than the two-phase kernel's queue holds go to the single-phase kernel
+            if (G.nCellsTotal > 0) {
+                const FastSmem L1 = fast_smem_layout(G.maxCw, G.maxCh, ex->maxSlotCap);
+                const size_t smem = (size_t)L1.total * WPB;
+                if (smem > 48 * 1024) CUDA_TRY(ex, cudaFuncSetAttribute(k_fast_cells_v1_list<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_fast_cells_v1_list<WPB><<<2 * ex->nSM, WPB * 32, smem, s>>>(P, ex->maxSlotCap, denseList, denseN);
                 ++ex->launches;
             }
         }
@@ -2376,6 +2425,7 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
 int run_batch(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, int in0Pitch, int batch, orbx_keypoint *d_kps,
               uint8_t *d_desc, int cap, int *d_nOut, int *d_mono) {
     ex->lastBatch = 0;
+    ex->denseSlots.clear();
     const int nSub = ex->profiling ? 1 : (batch >= 128 ? ex->nSub : (batch >= 32 ? 2 : 1));
     if (nSub == 1) return run_pipeline(ex, in0, in0Stride, in0Pitch, batch, d_kps, d_desc, cap, d_nOut, d_mono);
     cudaStream_t *side = ex->sSide;
@@ -2461,6 +2511,7 @@ orbx_extractor *orbx_create(int nfeatures, float scale_factor, int nlevels, int 
     CREATE_TRY(cudaStreamCreateWithFlags(&ex->sH2D, cudaStreamNonBlocking));
     CREATE_TRY(cudaStreamCreateWithFlags(&ex->sD2H, cudaStreamNonBlocking));
     for (int i = 0; i < ORBX_MAX_SIDE; ++i) CREATE_TRY(cudaStreamCreateWithFlags(&ex->sSide[i], cudaStreamNonBlocking));
+    { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) ex->nSM = v; }
     if (const char *e = getenv("ORBX_NSIDE")) ex->nSide = std::min(ORBX_MAX_SIDE, std::max(1, atoi(e)));        // developer knobs
     if (const char *e = getenv("ORBX_NSUB")) ex->nSub = std::min(16, std::max(1, atoi(e)));
     if (const char *e = getenv("ORBX_NSTEADY")) ex->nSteady = std::min(ORBX_MAX_CHUNKS - 2, std::max(1, atoi(e)));
@@ -2488,6 +2539,8 @@ orbx_extractor *orbx_create(int nfeatures, float scale_factor, int nlevels, int 
     CREATE_TRY(cudaMalloc((void **)&ex->d_selCnt, (size_t)max_batch * ORBX_MAX_LEVELS * sizeof(int)));
     CREATE_TRY(cudaMalloc((void **)&ex->d_workCnt, (size_t)max_batch * sizeof(int)));
     CREATE_TRY(cudaMalloc((void **)&ex->d_deep, (size_t)max_batch * ORBX_MAX_LEVELS * sizeof(int)));
+    CREATE_TRY(cudaMalloc((void **)&ex->d_dense, (size_t)max_batch * sizeof(int)));
+    CREATE_TRY(cudaMemset(ex->d_dense, 0, (size_t)max_batch * sizeof(int)));
     ex->useHistQuadtree = getenv("ORBX_LEGACY_QUADTREE") == nullptr;
     ex->fastV1 = getenv("ORBX_FAST_V1") != nullptr;
     CREATE_TRY(cudaMalloc((void **)&ex->d_nOut, (size_t)max_batch * sizeof(int)));
@@ -2510,7 +2563,7 @@ void orbx_destroy(orbx_extractor *ex) {
     if (ex->stream) cudaStreamSynchronize(ex->stream);
     void *ptrs[] = {ex->d_geom, ex->d_cells, ex->d_tiles, ex->d_tabX, ex->d_tabY, ex->d_tabXOff, ex->d_tabYOff,
                     ex->d_pattern, ex->d_patternF, ex->d_pyr, ex->d_blur, ex->d_slots, ex->d_ptNode, ex->d_ptXY, ex->d_cellCnt,
-                    ex->d_sel, ex->d_work, ex->d_selCnt, ex->d_workCnt, ex->d_hist, ex->d_finalPos, ex->d_best, ex->d_cellPrefix, ex->d_deep, ex->d_stage, ex->d_kps, ex->d_desc, ex->d_nOut, ex->d_mono};
+                    ex->d_sel, ex->d_work, ex->d_selCnt, ex->d_workCnt, ex->d_hist, ex->d_finalPos, ex->d_best, ex->d_cellPrefix, ex->d_deep, ex->d_dense, ex->d_denseList, ex->d_stage, ex->d_kps, ex->d_desc, ex->d_nOut, ex->d_mono};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ex->h_nOut) cudaFreeHost(ex->h_nOut);
     if (ex->h_mono) cudaFreeHost(ex->h_mono);
@@ -2643,7 +2696,7 @@ int orbx_extract_batch(orbx_extractor *ex, const uint8_t *const *images, int bat
             CUDA_TRY(ex, cudaEventRecord(ex->evIn[k], sIn));
             CUDA_TRY(ex, cudaStreamWaitEvent(sK, ex->evIn[k], 0));
             ex->lastIn0Internal = true;
-            if (c0 == 0) ex->lastBatch = 0;
+            if (c0 == 0) { ex->lastBatch = 0; ex->denseSlots.clear(); }
             rc = run_pipeline(ex, lvl0, G.frameBytes, G.lv[0].pitch, cn, ex->d_kps + (size_t)c0 * cap, ex->d_desc + (size_t)c0 * cap * 32, cap,
                               ex->d_nOut + c0, ex->d_mono + c0, c0, sK == sC ? nullptr : sK);
             if (rc) return rc;
@@ -2719,6 +2772,20 @@ int orbx_debug_deep_count(orbx_extractor *ex) {
     return n;
 }
 
+
+// test hook: cells of the last batch call that the two-phase FAST kernel handed to the single-phase kernel
+int orbx_debug_dense_count(orbx_extractor *ex) {
+    if (!ex || !ex->d_dense) return ORBX_ERR_ARG;
+    if (ex->fastV1) return -1;
+    if (cudaSetDevice(ex->device) != cudaSuccess || cudaStreamSynchronize(ex->stream) != cudaSuccess) return ORBX_ERR_CUDA;
+    int n = 0;
+    for (int slot : ex->denseSlots) {
+        int v = 0;
+        if (cudaMemcpy(&v, ex->d_dense + slot, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return ORBX_ERR_CUDA;
+        n += v;
+    }
+    return n;
+}
 
 int orbx_set_profiling(orbx_extractor *ex, int on) {
     if (!ex) return ORBX_ERR_ARG;

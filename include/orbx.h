@@ -235,6 +235,10 @@ int orbx_bow_transform_batch_device(orbx_vocab *v, const uint8_t *d_desc, size_t
  * the general quadtree kernel (trees deeper than its table); -1 if the histogram kernel is disabled. */
 int orbx_debug_deep_count(orbx_extractor *ex);
 
+/* Test hook: number of FAST cells of the last batch call whose corner candidates did not fit the two-phase kernel's queue
+ * and were redone by the single-phase kernel; -1 when ORBX_FAST_V1 routes everything through the latter. */
+int orbx_debug_dense_count(orbx_extractor *ex);
+
 /* Test hook: the device/host port of libstdc++ std::sort used by the quadtree (see stdsort_port.h),
  * run on the host; perm_out = resulting order of original indices. */
 void orbx_debug_sort_nodes(const int32_t *sizes, const int32_t *ulx, int n, int32_t *perm_out);

@@ -189,10 +189,19 @@ def test_fast_two_sided_pixels_and_dense_corner_fields(orbx_mod, oracle_mod):
             assert sha(_xyz(ex.candidates(l))) == sha(_xyz(ref.candidates(l))), (i, l)
         assert mono == rmono and k.tobytes() == rk.tobytes() and np.array_equal(d, rd), i
     # and in one batch (different cells of a launch take different paths)
-    n, mono, kps, desc = ex.__class__(1500, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=len(frames)).extract_batch(np.stack(frames))
+    exb = ex.__class__(1500, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=len(frames))
+    n, mono, kps, desc = exb.extract_batch(np.stack(frames))
     for i, f in enumerate(frames):
         rc, rk, rd, rmono = ref.extract(f, cap=2000)
         assert n[i] == len(rk) and kps[i, : n[i]].tobytes() == rk.tobytes() and np.array_equal(desc[i, : n[i]], rd), i
+    # cells with more candidates than the two-phase kernel's queue holds were redone by the single-phase kernel …
+    import ctypes
+    exb.L.orbx_debug_dense_count.argtypes = [ctypes.c_void_p]
+    assert exb.L.orbx_debug_dense_count(exb.h) > 50
+    # … and ordinary frames never take that path
+    from dani_slam_b200 import synth
+    exb.extract_batch(np.stack([synth.throughput_frame(s, W, H) for s in range(8)]))
+    assert exb.L.orbx_debug_dense_count(exb.h) == 0
 
 
 def test_full_size_4k_frame(orbx_mod, oracle_mod):
