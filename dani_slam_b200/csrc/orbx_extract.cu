@@ -1899,7 +1899,7 @@ struct orbx_extractor {
     int quota[ORBX_MAX_LEVELS];
     int umax[ORBX_HALF_PATCH + 1];
     cudaStream_t stream = nullptr, sH2D = nullptr, sD2H = nullptr, sSide[ORBX_MAX_SIDE] = {};
-    int nSide = 2, nSub = 4, nSteady = 8;     // side streams in use, sub-batches of the device path, steady chunks of the host path
+    int nSide = 2, nSub = 4, nSteady = 0;     // side streams in use, sub-batches of the device path, steady chunks of the host path
     cudaEvent_t evFork = nullptr, evJoin[ORBX_MAX_SIDE] = {};
     cudaEvent_t evIn[ORBX_MAX_CHUNKS] = {}, evOut[ORBX_MAX_CHUNKS] = {};
     std::string err;
@@ -2643,8 +2643,10 @@ int orbx_extract_batch(orbx_extractor *ex, const uint8_t *const *images, int bat
             if (const char *e = getenv("ORBX_CHUNK_PLAN")) {
                 for (const char *q = e; *q && nPlan < ORBX_MAX_CHUNKS;) { plan[nPlan++] = atoi(q); while (*q && *q != ',') ++q; if (*q == ',') ++q; }
             } else {
+                // steady chunks of about 90 frames (fewer would starve the kernels early, more loses launch efficiency)
+                const int nSteady = ex->nSteady > 0 ? ex->nSteady : std::min(8, std::max(2, (nb - nb / 8 + 89) / 90));
                 plan[nPlan++] = 32; plan[nPlan++] = 96;
-                for (int i = 0; i < ex->nSteady; ++i) plan[nPlan++] = (1024 - 128) / ex->nSteady;
+                for (int i = 0; i < nSteady; ++i) plan[nPlan++] = (1024 - 128) / nSteady;
             }
             int left = nb;
             for (int i = 0; i < nPlan && left > 0; ++i) {
