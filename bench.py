@@ -435,7 +435,25 @@ def main():
         match = {"metric": "hamming_knn2_gpairs_per_s", "value": gpairs, "unit": "Gpairs/s", "nq": nq, "ndb": ndb,
                  "scaling": "strong", "ms_per_step": ms_m / Km, "steps": Km,
                  "collective": "all_gather of per-shard top-2 (nq*2*2 int32)" if dist_on else None,
-                 "popc_per_s": 8 * gpairs * 1e9}
+                 "popc_per_s": 8 * gpairs * 1e9, "cpu_baseline": None}
+        if world == 1 and not args.no_cpu:
+            # the oracle's popcount kNN on all host cores over a DB slice (the scan is linear in the DB length)
+            from oracle import oracle as _orc
+            cores = os.cpu_count() or 1
+            h_q = d_q.cpu().numpy()
+            slice_rows = min(ndb, 400_000)
+            h_db = d_db[:slice_rows].cpu().numpy()
+            t0 = time.time(); reps = 0
+            while time.time() - t0 < 4.0:
+                cidx, cdist = _orc.knn2(h_q, h_db, nthreads=cores)
+                reps += 1
+            dt = time.time() - t0
+            gi, gd = sm.local_top2(d_q, d_db[:slice_rows].contiguous(), 0)
+            torch.cuda.synchronize(dev)
+            same = bool(np.array_equal(gi.cpu().numpy().reshape(-1, 2), cidx) and np.array_equal(gd.cpu().numpy().reshape(-1, 2), cdist))
+            match["cpu_baseline"] = {"value": nq * slice_rows * reps / dt / 1e9, "unit": "Gpairs/s", "cores": cores, "kind": "port",
+                                     "sample": f"{nq} queries x {slice_rows} DB rows, {reps} passes in {dt:.1f}s on {cores} threads (oracle popcount kNN); "
+                                               f"GPU result on the same slice identical: {same}"}
         del d_db
 
     # ---------------- bag-of-words transform of the extracted descriptors (`bow`) ----------------
