@@ -435,7 +435,11 @@ def main():
         match = {"metric": "hamming_knn2_gpairs_per_s", "value": gpairs, "unit": "Gpairs/s", "nq": nq, "ndb": ndb,
                  "scaling": "strong", "ms_per_step": ms_m / Km, "steps": Km,
                  "collective": "all_gather of per-shard top-2 (nq*2*2 int32)" if dist_on else None,
-                 "popc_per_s": 8 * gpairs * 1e9, "cpu_baseline": None}
+                 "popc_per_s": 8 * gpairs * 1e9, "cpu_baseline": None,
+                 "roofline": {"bound": "int-popc", "achieved": 8 * gpairs * 1e9 / world, "peak": 15.3 * 148 * 1.965e9, "unit": "POPC/s per GPU",
+                              "frac": 8 * gpairs * 1e9 / world / (15.3 * 148 * 1.965e9),
+                              "note": "algorithmic 8 POPC.32 per pair against the measured POPC rate (15.3 lanes/clk/SM, profiles/microbench_pipes_b200.txt); "
+                                      "above 1 because the kernel's carry-save adders issue 5 POPC per pair"}}
         if world == 1 and not args.no_cpu:
             # the oracle's popcount kNN on all host cores over a DB slice (the scan is linear in the DB length)
             from oracle import oracle as _orc
