@@ -4,8 +4,9 @@
 //
 // Pipeline for a batch of B equally sized frames (one launch per stage, grid.y = frame):
 //   K1 k_pyr_level   ×(L-1)  ComputePyramid :1209-1234 — bilinear 8U resize, 11-bit fixed point
-//   K2 k_fast_cells          cell loop :781-869 — one warp per 35-px cell: FAST-9 score map in smem,
-//                            cell-local NMS, iniTh/minTh retry, row-major ordered candidate list
+//   K2 k_fast_cells          cell loop :781-869 — one warp per 35-px cell, two phases: compass pre-test on every pixel,
+//                            exact FAST-9 measure only for the queued (pixel, side) entries; cell-local NMS, iniTh/minTh
+//                            retry, row-major ordered candidate list (k_fast_cells_v1_list redoes over-full cells)
 //   K3 k_qt_* / k_quadtree   DANI filter :871-907 + DistributeOctTree :555-779 — candidates classified once
 //                            into a quadtree histogram, exact list-order emulation on node counts incl.
 //                            libstdc++ sort ties, general single-kernel version as fallback
@@ -184,8 +185,11 @@ __global__ void __launch_bounds__(256) k_pyr_level(PyrArgs a) {
 // ------------------------------------------------------------------------------------------------
 // K2: FAST-9_16 per cell (cv::FAST + NMS on the cell ROI).  One warp per cell.
 //
-// The exact FAST score of EVERY interior pixel is computed without any data-dependent branch, two
-// pixels per instruction, with Blackwell's packed 3-input min/max (VIMNMX3.U16x2, the DPX family):
+// Two kernels share the staging and the score formulation.  The single-phase one (fast_cell_v1: ORBX_FAST_V1
+// cross-check and the fallback for over-full cells) computes the exact FAST score of EVERY interior pixel without
+// any data-dependent branch, two pixels per instruction; the production kernel k_fast_cells further down first
+// discards the pixels that fail the compass bound and evaluates the exact measure only for the rest.  Both use
+// Blackwell's packed 3-input min/max (VIMNMX3.U16x2, the DPX family):
 //   M = max( v − min_k max(ring[k..k+8]),  max_k min(ring[k..k+8]) − v )      (k circular over 16)
 // which equals OpenCV's max-over-arcs-of-min|diff| (A4) because min_arc(v−r) = v − max_arc(r).
 // A window of 9 is max3(max3(r0,r1,r2), max3(r3,r4,r5), max3(r6,r7,r8)): 32 instructions per polarity
