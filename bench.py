@@ -257,9 +257,11 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", str(29400 + os.getpid() % 500), os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
 
-    # NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION; rank 0's stdout must be the one JSON line
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # rank 0's stdout must be the one JSON line, but NCCL prints its version banner there when the first communicator is
+    # created: everything written to fd 1 goes to stderr until the line is printed
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     bind_to_gpu_numa_node(local_rank)
     import torch
     import torch.distributed as td
@@ -540,6 +542,8 @@ def main():
             "match": match,
             "bow": bow,
         }
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
         print(json.dumps(line), flush=True)
     if dist_on:
         td.destroy_process_group()
