@@ -53,8 +53,6 @@ struct ExParams {
     const OrbxCell *cells;
     const int2 *tabX;         // per level ≥1: {src index, a0 | a1<<16} per destination column
     const int2 *tabY;
-    const int *tabXOff;       // offsets of each level's table
-    const int *tabYOff;
     uint32_t *slots;          // per cell candidate slots: x | y<<8 | score<<16 (cell-ROI coords)
     int *cellCnt;             // candidates per cell
     float2 *ptXY;             // per slot: drifted (x,y) relative to the 16-px border
@@ -69,7 +67,6 @@ struct ExParams {
     int *nOut;
     int *monoIdx;
     const int8_t *pattern;    // 1024 bytes
-    const float4 *patternF;   // 256 × (x0, y0, x1, y1)
 };
 
 __device__ __forceinline__ const uint8_t *level_ptr(const ExParams &p, const OrbxGeom &g, int l, int b,
@@ -1940,9 +1937,7 @@ struct orbx_extractor {
     OrbxCell *d_cells = nullptr; size_t cellsCap = 0;
     BlurTile *d_tiles = nullptr; size_t tilesCap = 0;
     int2 *d_tabX = nullptr, *d_tabY = nullptr; size_t tabXCap = 0, tabYCap = 0;
-    int *d_tabXOff = nullptr, *d_tabYOff = nullptr;
     int8_t *d_pattern = nullptr;
-    float4 *d_patternF = nullptr;
     uint8_t *d_pyr = nullptr, *d_blur = nullptr; size_t pyrCap = 0;
     uint32_t *d_slots = nullptr; uint32_t *d_ptNode = nullptr; float2 *d_ptXY = nullptr; size_t slotsCap = 0;
     int *d_cellCnt = nullptr; size_t cellCntCap = 0;
@@ -2134,8 +2129,6 @@ int upload_tables(orbx_extractor *ex) {
     cudaStream_t s = ex->stream;
     if (!tx.empty()) CUDA_TRY(ex, cudaMemcpyAsync(ex->d_tabX, tx.data(), tx.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
     if (!ty.empty()) CUDA_TRY(ex, cudaMemcpyAsync(ex->d_tabY, ty.data(), ty.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(ex, cudaMemcpyAsync(ex->d_tabXOff, txo.data(), ORBX_MAX_LEVELS * sizeof(int), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(ex, cudaMemcpyAsync(ex->d_tabYOff, tyo.data(), ORBX_MAX_LEVELS * sizeof(int), cudaMemcpyHostToDevice, s));
     if (!ex->h_cells.empty())
         CUDA_TRY(ex, cudaMemcpyAsync(ex->d_cells, ex->h_cells.data(), ex->h_cells.size() * sizeof(OrbxCell), cudaMemcpyHostToDevice, s));
     if (!ex->h_tiles.empty())
@@ -2243,14 +2236,13 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
     P.in0 = in0; P.in0Stride = in0Stride; P.in0Pitch = in0Pitch;
     P.pyr = ex->d_pyr + f * G.frameBytes; P.blur = ex->d_blur + f * G.frameBytes;
     P.cells = ex->d_cells;
-    P.tabX = ex->d_tabX; P.tabY = ex->d_tabY; P.tabXOff = ex->d_tabXOff; P.tabYOff = ex->d_tabYOff;
+    P.tabX = ex->d_tabX; P.tabY = ex->d_tabY;
     P.slots = ex->d_slots + f * G.slotsTotal; P.cellCnt = ex->d_cellCnt + f * G.nCellsTotal;
     P.ptXY = ex->d_ptXY + f * G.slotsTotal; P.ptNode = ex->d_ptNode + f * G.slotsTotal;
     P.sel = ex->d_sel + f * G.selTotal; P.selCnt = ex->d_selCnt + f * G.nlevels;
     P.work = ex->d_work + f * G.selTotal; P.workCnt = ex->d_workCnt + f;
     P.kps = d_kps; P.desc = d_desc; P.cap = cap; P.nOut = d_nOut; P.monoIdx = d_mono;
     P.pattern = ex->d_pattern;
-    P.patternF = ex->d_patternF;
     cudaStream_t s = onStream ? onStream : ex->stream;
     const bool prof = ex->profiling && !onStream;
     if (prof) {
@@ -2527,15 +2519,9 @@ orbx_extractor *orbx_create(int nfeatures, float scale_factor, int nlevels, int 
         CREATE_TRY(cudaEventCreateWithFlags(&ex->evOut[i], evFlags));
     }
     CREATE_TRY(cudaMalloc((void **)&ex->d_geom, sizeof(OrbxGeom)));
-    CREATE_TRY(cudaMalloc((void **)&ex->d_tabXOff, ORBX_MAX_LEVELS * sizeof(int)));
-    CREATE_TRY(cudaMalloc((void **)&ex->d_tabYOff, ORBX_MAX_LEVELS * sizeof(int)));
     CREATE_TRY(cudaMalloc((void **)&ex->d_pattern, 1024));
     CREATE_TRY(cudaMemcpy(ex->d_pattern, h_pattern, 1024, cudaMemcpyHostToDevice));
     {
-        std::vector<float> pf(1024);
-        for (int i = 0; i < 1024; ++i) pf[i] = (float)h_pattern[i];
-        CREATE_TRY(cudaMalloc((void **)&ex->d_patternF, 1024 * sizeof(float)));
-        CREATE_TRY(cudaMemcpy(ex->d_patternF, pf.data(), 1024 * sizeof(float), cudaMemcpyHostToDevice));
         static const int kUmax15[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
         for (int i = 0; i <= ORBX_HALF_PATCH; ++i)
             if (ex->umax[i] != kUmax15[i]) return fail("orbx_create: umax table differs from the compiled-in HALF_PATCH_SIZE=15 table");
@@ -2565,8 +2551,8 @@ void orbx_destroy(orbx_extractor *ex) {
     if (!ex) return;
     cudaSetDevice(ex->device);
     if (ex->stream) cudaStreamSynchronize(ex->stream);
-    void *ptrs[] = {ex->d_geom, ex->d_cells, ex->d_tiles, ex->d_tabX, ex->d_tabY, ex->d_tabXOff, ex->d_tabYOff,
-                    ex->d_pattern, ex->d_patternF, ex->d_pyr, ex->d_blur, ex->d_slots, ex->d_ptNode, ex->d_ptXY, ex->d_cellCnt,
+    void *ptrs[] = {ex->d_geom, ex->d_cells, ex->d_tiles, ex->d_tabX, ex->d_tabY,
+                    ex->d_pattern, ex->d_pyr, ex->d_blur, ex->d_slots, ex->d_ptNode, ex->d_ptXY, ex->d_cellCnt,
                     ex->d_sel, ex->d_work, ex->d_selCnt, ex->d_workCnt, ex->d_hist, ex->d_finalPos, ex->d_best, ex->d_cellPrefix, ex->d_deep, ex->d_dense, ex->d_denseList, ex->d_stage, ex->d_kps, ex->d_desc, ex->d_nOut, ex->d_mono};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ex->h_nOut) cudaFreeHost(ex->h_nOut);
