@@ -146,3 +146,14 @@ def test_vocabulary_shared_between_threads_and_capacity_error():
         dev.transform(synth.vocabulary_queries(voc, 20000, seed=3), 4)
     assert e.value.code == orbx.ERR_CAPACITY
     _same(want[0], dev.transform(qs[0], 4))          # the handle stays usable
+
+
+def test_transform_matches_golden_dbow2_vectors():
+    """Golden vectors written by the reference's own DBoW2 (tools/gen_golden_bow.py)."""
+    from test_bow_oracle import GOLDEN, golden_case
+    assert len(GOLDEN) >= 5
+    for path in GOLDEN:
+        g, voc, q, levelsup = golden_case(path)
+        t = orbx.ORBVocabulary().from_nodes(voc).transform(q, levelsup)
+        for k in ("word_id", "bow_ids", "bow_vals", "fv_nodes", "fv_off", "fv_idx"):
+            assert np.array_equal(t[k], g[k]), (os.path.basename(path), k)

@@ -82,3 +82,33 @@ def test_oracle_properties():
         assert np.all(np.diff(t["fv_idx"][a:b].astype(np.int64)) > 0)    # feature order inside a node
     # node ids are the ancestors at level L - levelsup = 1: children of the root
     assert set(t["fv_nodes"]) <= set(np.flatnonzero(voc["parent"] == 0) + 1)
+
+
+# ---- golden vectors produced by the reference's own DBoW2 (tools/gen_golden_bow.py); usable without oracle/_ref ----
+import glob
+import hashlib
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bow_*.npz")))
+
+
+def golden_case(path):
+    g = np.load(path)
+    vargs = eval(str(g["vargs"]))          # a dict literal written by the generator script
+    voc = synth.vocabulary(**vargs)
+    q = synth.vocabulary_queries(voc, int(g["nq"]), seed=vargs["seed"] + 1)
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    assert sha(np.concatenate([voc["parent"].view(np.uint8), voc["is_leaf"], voc["desc"].ravel(), voc["weight"].view(np.uint8)])) == str(g["voc_sha"]), "vocabulary generator drifted"
+    assert sha(q) == str(g["q_sha"]), "query generator drifted"
+    return g, voc, q, int(g["levelsup"])
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=lambda p: os.path.basename(p)[4:-4])
+def test_oracle_matches_golden_dbow2_vectors(path):
+    g, voc, q, levelsup = golden_case(path)
+    o = oracle.Vocabulary(voc=voc).transform(q, levelsup)
+    for k in ("word_id", "bow_ids", "bow_vals", "fv_nodes", "fv_off", "fv_idx"):
+        assert np.array_equal(o[k], g[k]), k
+
+
+def test_golden_set_is_present():
+    assert len(GOLDEN) >= 5

@@ -64,3 +64,31 @@ def test_cuda_matches_oracle(orbx_mod, cam):
     m.undistort_points_device(d_in.data_ptr(), 2, len(pts), Kf, Df, d_out.data_ptr(), 2)
     m.sync()
     assert np.array_equal(d_out.cpu().numpy().view(np.uint32), oracle.undistort_points(pts, *Kf, Df).view(np.uint32))
+
+
+import glob
+import os
+
+UND_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "undistort_*.npz")))
+
+
+@pytest.mark.parametrize("path", UND_GOLDEN, ids=lambda p: os.path.basename(p)[10:-4])
+def test_oracle_matches_golden_cv2_vectors(path):
+    g = np.load(path)
+    K, D = g["K"], g["D"]
+    assert np.array_equal(oracle.undistort_points(g["pts"], *K, D).view(np.uint32), g["undistorted"].view(np.uint32))
+    assert np.array_equal(oracle.image_bounds(int(g["size"][0]), int(g["size"][1]), *K, D), g["bounds"])
+
+
+@pytest.mark.gpu
+def test_cuda_matches_golden_cv2_vectors(orbx_mod):
+    assert len(UND_GOLDEN) >= 3
+    m = orbx_mod.ORBmatcher()
+    for path in UND_GOLDEN:
+        g = np.load(path)
+        K, D, pts = tuple(g["K"]), g["D"], g["pts"]
+        kps = np.zeros(len(pts), orbx_mod.KP_DTYPE)
+        kps["x"], kps["y"] = pts[:, 0], pts[:, 1]
+        un = m.UndistortKeyPoints(kps, K, D)
+        assert np.array_equal(np.stack([un["x"], un["y"]], 1).view(np.uint32), g["undistorted"].view(np.uint32)), path
+        assert np.array_equal(m.ComputeImageBounds(int(g["size"][0]), int(g["size"][1]), K, D), g["bounds"]), path
