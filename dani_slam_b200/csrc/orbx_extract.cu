@@ -1902,6 +1902,10 @@ struct orbx_extractor {
     cudaStream_t stream = nullptr, sH2D = nullptr, sD2H = nullptr, sSide[ORBX_MAX_SIDE] = {};
     int nSide = 2, nSub = 4, nSteady = 0;     // side streams in use, sub-batches of the device path, steady chunks of the host path
     cudaEvent_t evFork = nullptr, evJoin[ORBX_MAX_SIDE] = {};
+    // the blur only needs the pyramid: it runs on a partner stream next to FAST + quadtree (index 0: main stream, 1+i: side i)
+    cudaStream_t sAux[ORBX_MAX_SIDE + 1] = {};
+    cudaEvent_t evPyrDone[ORBX_MAX_SIDE + 1] = {}, evBlurDone[ORBX_MAX_SIDE + 1] = {};
+    bool overlapBlur = true;
     cudaEvent_t evIn[ORBX_MAX_CHUNKS] = {}, evOut[ORBX_MAX_CHUNKS] = {};
     std::string err;
     long long launches = 0;
@@ -2341,6 +2345,19 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
         }
     }
     if (prof) CUDA_TRY(ex, cudaEventRecord(ex->ev[2], s));
+    // K5 early, on the partner stream: the blurred levels depend on the pyramid only; started once FAST is done, the
+    // instruction-bound blur fills the SMs while the latency-bound quadtree kernels run
+    int aux = -1;
+    if (!prof && ex->overlapBlur) {
+        aux = 0;
+        for (int i = 0; i < ORBX_MAX_SIDE; ++i) if (onStream && onStream == ex->sSide[i]) aux = 1 + i;
+        CUDA_TRY(ex, cudaEventRecord(ex->evPyrDone[aux], s));
+        CUDA_TRY(ex, cudaStreamWaitEvent(ex->sAux[aux], ex->evPyrDone[aux], 0));
+        dim3 grdB((unsigned)ex->h_tiles.size(), batch);
+        k_blur<<<grdB, dim3(64, BLUR_STRIPS), 0, ex->sAux[aux]>>>(P, ex->d_tiles);
+        ++ex->launches;
+        CUDA_TRY(ex, cudaEventRecord(ex->evBlurDone[aux], ex->sAux[aux]));
+    }
     // K3
     {
         const QtSmem L = qt_smem_layout(ex->nodeCapMax, ex->maxCellsLevel);
@@ -2395,11 +2412,13 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
     k_assemble<<<batch, 256, 0, s>>>(P);
     ++ex->launches;
     if (prof) CUDA_TRY(ex, cudaEventRecord(ex->ev[4], s));
-    // K5
-    {
+    // K5 (serial form; see above for the overlapped one)
+    if (aux < 0) {
         dim3 grd((unsigned)ex->h_tiles.size(), batch);
         k_blur<<<grd, dim3(64, BLUR_STRIPS), 0, s>>>(P, ex->d_tiles);
         ++ex->launches;
+    } else {
+        CUDA_TRY(ex, cudaStreamWaitEvent(s, ex->evBlurDone[aux], 0));
     }
     if (prof) CUDA_TRY(ex, cudaEventRecord(ex->ev[5], s));
     // K4 + K6
@@ -2513,6 +2532,12 @@ orbx_extractor *orbx_create(int nfeatures, float scale_factor, int nlevels, int 
     if (const char *e = getenv("ORBX_NSTEADY")) ex->nSteady = std::min(ORBX_MAX_CHUNKS - 2, std::max(1, atoi(e)));
     CREATE_TRY(cudaEventCreateWithFlags(&ex->evFork, cudaEventDisableTiming));
     for (int i = 0; i < ORBX_MAX_SIDE; ++i) CREATE_TRY(cudaEventCreateWithFlags(&ex->evJoin[i], cudaEventDisableTiming));
+    for (int i = 0; i <= ORBX_MAX_SIDE; ++i) {
+        CREATE_TRY(cudaStreamCreateWithFlags(&ex->sAux[i], cudaStreamNonBlocking));
+        CREATE_TRY(cudaEventCreateWithFlags(&ex->evPyrDone[i], cudaEventDisableTiming));
+        CREATE_TRY(cudaEventCreateWithFlags(&ex->evBlurDone[i], cudaEventDisableTiming));
+    }
+    ex->overlapBlur = getenv("ORBX_SERIAL_BLUR") == nullptr;
     for (int i = 0; i < ORBX_MAX_CHUNKS; ++i) {
         const unsigned evFlags = getenv("ORBX_DEBUG_CHUNKS") ? cudaEventDefault : cudaEventDisableTiming;
         CREATE_TRY(cudaEventCreateWithFlags(&ex->evIn[i], evFlags));
@@ -2561,6 +2586,11 @@ void orbx_destroy(orbx_extractor *ex) {
     for (int i = 0; i < ORBX_MAX_CHUNKS; ++i) { if (ex->evIn[i]) cudaEventDestroy(ex->evIn[i]); if (ex->evOut[i]) cudaEventDestroy(ex->evOut[i]); }
     if (ex->evFork) cudaEventDestroy(ex->evFork);
     for (int i = 0; i < ORBX_MAX_SIDE; ++i) if (ex->evJoin[i]) cudaEventDestroy(ex->evJoin[i]);
+    for (int i = 0; i <= ORBX_MAX_SIDE; ++i) {
+        if (ex->sAux[i]) { cudaStreamSynchronize(ex->sAux[i]); cudaStreamDestroy(ex->sAux[i]); }
+        if (ex->evPyrDone[i]) cudaEventDestroy(ex->evPyrDone[i]);
+        if (ex->evBlurDone[i]) cudaEventDestroy(ex->evBlurDone[i]);
+    }
     for (int i = 0; i < ORBX_MAX_SIDE; ++i) if (ex->sSide[i]) { cudaStreamSynchronize(ex->sSide[i]); cudaStreamDestroy(ex->sSide[i]); }
     if (ex->sH2D) cudaStreamDestroy(ex->sH2D);
     if (ex->sD2H) cudaStreamDestroy(ex->sD2H);
