@@ -1781,7 +1781,7 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 }
 
 template <int WPB>
-__global__ void __launch_bounds__(WPB * 32) k_orient_desc(ExParams p) {
+__global__ void __launch_bounds__(WPB * 32, 2048 / (WPB * 32)) k_orient_desc(ExParams p) {
     const OrbxGeom &g = *p.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * WPB + warp, b = blockIdx.y;
