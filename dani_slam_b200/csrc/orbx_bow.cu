@@ -59,7 +59,7 @@ __device__ __forceinline__ int ham256(const uint4 &a0, const uint4 &a1, const ui
 // indexed b*cap + i.  leaf = leaf node id (weight lookup later), nodeOut = ancestor at level L - levelsup (0 when the
 // leaf is shallower or the level is <= 0).
 template <int GS>
-__global__ void __launch_bounds__(256) k_bow_descend(BowTree t, const uint8_t *__restrict__ desc, size_t descStride, const int *__restrict__ nPer,
+__global__ void __launch_bounds__(256, 8) k_bow_descend(BowTree t, const uint8_t *__restrict__ desc, size_t descStride, const int *__restrict__ nPer,
                                                      int cap, int levelsup, uint32_t *__restrict__ wordOut, uint32_t *__restrict__ nodeOut,
                                                      int *__restrict__ leafOut) {
     const int b = blockIdx.y;
