@@ -786,12 +786,12 @@ __host__ __device__ inline QtSmem qt_smem_layout(int nodeCap, int maxCellsLevel)
 
 // quadrant of a point inside a node (DivideNode :480-536): children n1..n4 = 0..3.
 // halfX = ceil(static_cast<float>(UR.x-UL.x)/2) of a non-negative int < 2^24 is exactly (w+1)>>1.
-__device__ __forceinline__ int qt_quadrant(short4 bx, float x, float y) {
+__host__ __device__ __forceinline__ int qt_quadrant(short4 bx, float x, float y) {
     const int hx = (bx.y - bx.x + 1) >> 1, hy = (bx.w - bx.z + 1) >> 1;
     const float xm = (float)(bx.x + hx), ym = (float)(bx.z + hy);
     return (x < xm ? 0 : 1) + (y < ym ? 0 : 2);
 }
-__device__ __forceinline__ short4 qt_child_box(short4 bx, int q) {  // box = {x0, x1, y0, y1}
+__host__ __device__ __forceinline__ short4 qt_child_box(short4 bx, int q) {  // box = {x0, x1, y0, y1}
     const int hx = (bx.y - bx.x + 1) >> 1, hy = (bx.w - bx.z + 1) >> 1;
     const short xm = (short)(bx.x + hx), ym = (short)(bx.z + hy);
     short4 c;
@@ -1159,6 +1159,7 @@ struct QtTables {               // per-handle device tables of the fast path (in
     unsigned *best;             // [frame][selTotal] best (response<<24 | 0xffffff-order) per final node
     int *cellPrefix;            // [frame][nCellsTotal] exclusive prefix of the cell counts inside their level
     int *deep;                  // [frame][level] 1 = the general kernel must redo this pair
+    const unsigned short *pathLut;   // per level: spread x-path codes per (root, floor x) and spread y-path codes per floor y
     int maxIni;
 };
 
@@ -1254,11 +1255,19 @@ __global__ void __launch_bounds__(128) k_qt_classify(ExParams p, QtTables t) {
         bx.z = 0;
         bx.w = (short)rootH;
         unsigned code = (unsigned)bin;
+        if (LV.lutW > 0) {
+            // The x and y decisions of the six splits are independent, and every split coordinate is an integer, so
+            // (x < xm) == (floor(x) < xm): the path is a table lookup on the integer parts (a coordinate the drift
+            // pushed just below 0 takes the leftmost path like 0 does).
+            const int xi = min(max((int)floorf(x), 0), LV.lutW - 1), yi = min(max((int)floorf(y), 0), LV.lutH - 1);
+            code = code * 4096u + t.pathLut[LV.lutX + bin * LV.lutW + xi] + t.pathLut[LV.lutY + yi];
+        } else {
 #pragma unroll
-        for (int d = 0; d < QT_DMAX; ++d) {
-            const int q = qt_quadrant(bx, x, y);
-            bx = qt_child_box(bx, q);
-            code = code * 4u + (unsigned)q;
+            for (int d = 0; d < QT_DMAX; ++d) {
+                const int q = qt_quadrant(bx, x, y);
+                bx = qt_child_box(bx, q);
+                code = code * 4u + (unsigned)q;
+            }
         }
         ptNode[i] = (code & 0xffffu) | ((e >> 16) << 16);
         if (tabled) atomicAdd(&hist[code], 1u);
@@ -1918,6 +1927,8 @@ struct orbx_extractor {
     bool geomDirty = true;
     int h_tabXOff[ORBX_MAX_LEVELS] = {0}, h_tabYOff[ORBX_MAX_LEVELS] = {0}, h_tileXOff[ORBX_MAX_LEVELS] = {0}, h_tileYOff[ORBX_MAX_LEVELS] = {0};
     std::vector<OrbxCell> h_cells;
+    std::vector<unsigned short> h_pathLut;   // quadtree path tables of all levels
+    unsigned short *d_pathLut = nullptr; size_t pathLutCap = 0;
     std::vector<BlurTile> h_tiles;
     int maxSlotCap = 0, nodeCapMax = 0, maxCellsLevel = 0, maxIni = 1;
     bool useHistQuadtree = true;
@@ -1992,6 +2003,7 @@ int build_geometry(orbx_extractor *ex, int rows, int cols) {
     memcpy(G.umax, ex->umax, sizeof(G.umax));
     ex->h_cells.clear();
     ex->h_tiles.clear();
+    ex->h_pathLut.clear();
     long long off = 0, slot = 0;
     int cellBase = 0, selBase = 0;
     ex->maxSlotCap = 1; ex->nodeCapMax = 8; ex->maxCellsLevel = 1; ex->maxIni = 1;
@@ -2057,6 +2069,28 @@ int build_geometry(orbx_extractor *ex, int rows, int cols) {
         if (V.nIni < 1) { ex->err = "image too tall: quadtree would have no root node (reference faults)"; return ORBX_ERR_GEOMETRY; }
         V.hX = (float)rw / (float)V.nIni;
         ex->maxIni = std::max(ex->maxIni, std::min(V.nIni, QT_MAX_INI));
+        // quadtree path tables (k_qt_classify): the six split decisions per integer x (per root) and per integer y
+        V.lutW = V.lutH = V.lutX = V.lutY = 0;
+        if (V.nIni <= QT_MAX_INI && rw > 0 && rh > 0) {
+            V.lutW = rw; V.lutH = rh;
+            V.lutX = (int)ex->h_pathLut.size();
+            for (int bin = 0; bin < V.nIni; ++bin)
+                for (int xi = 0; xi < rw; ++xi) {
+                    short4 bx;
+                    bx.x = (short)(int)(V.hX * (float)bin); bx.y = (short)(int)(V.hX * (float)(bin + 1)); bx.z = 0; bx.w = (short)rh;
+                    unsigned code = 0;
+                    for (int d = 0; d < QT_DMAX; ++d) { const int q = qt_quadrant(bx, (float)xi, 0.f) & 1; bx = qt_child_box(bx, q); code = code * 4u + (unsigned)q; }
+                    ex->h_pathLut.push_back((unsigned short)code);
+                }
+            V.lutY = (int)ex->h_pathLut.size();
+            for (int yi = 0; yi < rh; ++yi) {
+                short4 bx;
+                bx.x = 0; bx.y = (short)rw; bx.z = 0; bx.w = (short)rh;
+                unsigned code = 0;
+                for (int d = 0; d < QT_DMAX; ++d) { const int q = qt_quadrant(bx, 0.f, (float)yi) & 2; bx = qt_child_box(bx, q); code = code * 4u + (unsigned)q; }
+                ex->h_pathLut.push_back((unsigned short)code);
+            }
+        }
         V.nodeCap = std::max(4 * V.nIni, V.quota + 4) + 4;
         if (V.nodeCap > 60000) { ex->err = "nfeatures too large (quadtree node index is 16-bit)"; return ORBX_ERR_ARG; }
         ex->nodeCapMax = std::max(ex->nodeCapMax, V.nodeCap);
@@ -2130,11 +2164,14 @@ int upload_tables(orbx_extractor *ex) {
     if ((rc = ensure(ex, ex->d_tabY, ex->tabYCap, std::max<size_t>(ty.size(), 1)))) return rc;
     if ((rc = ensure(ex, ex->d_cells, ex->cellsCap, std::max<size_t>(ex->h_cells.size(), 1)))) return rc;
     if ((rc = ensure(ex, ex->d_tiles, ex->tilesCap, std::max<size_t>(ex->h_tiles.size(), 1)))) return rc;
+    if ((rc = ensure(ex, ex->d_pathLut, ex->pathLutCap, std::max<size_t>(ex->h_pathLut.size(), 1)))) return rc;
     cudaStream_t s = ex->stream;
     if (!tx.empty()) CUDA_TRY(ex, cudaMemcpyAsync(ex->d_tabX, tx.data(), tx.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
     if (!ty.empty()) CUDA_TRY(ex, cudaMemcpyAsync(ex->d_tabY, ty.data(), ty.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
     if (!ex->h_cells.empty())
         CUDA_TRY(ex, cudaMemcpyAsync(ex->d_cells, ex->h_cells.data(), ex->h_cells.size() * sizeof(OrbxCell), cudaMemcpyHostToDevice, s));
+    if (!ex->h_pathLut.empty())
+        CUDA_TRY(ex, cudaMemcpyAsync(ex->d_pathLut, ex->h_pathLut.data(), ex->h_pathLut.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, s));
     if (!ex->h_tiles.empty())
         CUDA_TRY(ex, cudaMemcpyAsync(ex->d_tiles, ex->h_tiles.data(), ex->h_tiles.size() * sizeof(BlurTile), cudaMemcpyHostToDevice, s));
     CUDA_TRY(ex, cudaStreamSynchronize(s));  // the host vectors above are about to go out of scope
@@ -2374,6 +2411,7 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
         T.best = ex->d_best + f * G.selTotal;
         T.cellPrefix = ex->d_cellPrefix + f * G.nCellsTotal;
         T.deep = ex->d_deep + f * G.nlevels;
+        T.pathLut = ex->d_pathLut;
         if (useHist) {
             const size_t smemP = (size_t)(ex->maxCellsLevel + 1 + QT_THREADS + 2) * sizeof(int);
             if (smemP > 48 * 1024) CUDA_TRY(ex, cudaFuncSetAttribute(k_qt_prefix<QT_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemP));
@@ -2576,7 +2614,7 @@ void orbx_destroy(orbx_extractor *ex) {
     if (!ex) return;
     cudaSetDevice(ex->device);
     if (ex->stream) cudaStreamSynchronize(ex->stream);
-    void *ptrs[] = {ex->d_geom, ex->d_cells, ex->d_tiles, ex->d_tabX, ex->d_tabY,
+    void *ptrs[] = {ex->d_geom, ex->d_cells, ex->d_tiles, ex->d_pathLut, ex->d_tabX, ex->d_tabY,
                     ex->d_pattern, ex->d_pyr, ex->d_blur, ex->d_slots, ex->d_ptNode, ex->d_ptXY, ex->d_cellCnt,
                     ex->d_sel, ex->d_work, ex->d_selCnt, ex->d_workCnt, ex->d_hist, ex->d_finalPos, ex->d_best, ex->d_cellPrefix, ex->d_deep, ex->d_dense, ex->d_denseList, ex->d_stage, ex->d_kps, ex->d_desc, ex->d_nOut, ex->d_mono};
     for (void *p : ptrs) if (p) cudaFree(p);

@@ -33,6 +33,7 @@ struct OrbxLevel {
     int nIni;                   // quadtree roots (:558)
     float hX;                   // (:560)
     int nodeCap;                // quadtree node capacity
+    int lutX, lutY, lutW, lutH; // quadtree path tables: offsets into the u16 table array and their extents (lutW = 0: none)
     int selBase, selCap;        // selected-keypoint list of this level inside the frame's list
 };
 
