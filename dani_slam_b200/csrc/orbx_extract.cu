@@ -1247,8 +1247,11 @@ __global__ void __launch_bounds__(128) k_qt_classify(ExParams p, QtTables t) {
             ptNode[i] = ORBX_NODE_ERASED;
             continue;
         }
-        int bin = (int)__fdiv_rn(x, hX);  // vpIniNodes[kp.pt.x/hX] (:584)
-        bin = min(max(bin, 0), nIni - 1);
+        int bin = 0;
+        if (nIni > 1) {                       // with a single root the clamp below makes every candidate land in it
+            bin = (int)__fdiv_rn(x, hX);      // vpIniNodes[kp.pt.x/hX] (:584)
+            bin = min(max(bin, 0), nIni - 1);
+        }
         short4 bx;
         bx.x = (short)(int)__fmul_rn(hX, (float)bin);
         bx.y = (short)(int)__fmul_rn(hX, (float)(bin + 1));
