@@ -1936,6 +1936,9 @@ struct orbx_extractor {
     int maxSlotCap = 0, nodeCapMax = 0, maxCellsLevel = 0, maxIni = 1;
     bool useHistQuadtree = true;
     int dbgCalls = 0;
+    // developer knobs, read from the environment once in orbx_create
+    bool dbgChunks = false, dbgSkipH2D = false, dbgSkipD2H = false;
+    std::string chunkPlan;
     bool fastV1 = false;            // ORBX_FAST_V1: single-phase FAST kernel (every pixel gets the exact measure)
     unsigned *d_hist = nullptr; size_t histCap = 0;
     unsigned short *d_finalPos = nullptr; size_t finalPosCap = 0;
@@ -2579,8 +2582,12 @@ orbx_extractor *orbx_create(int nfeatures, float scale_factor, int nlevels, int 
         CREATE_TRY(cudaEventCreateWithFlags(&ex->evBlurDone[i], cudaEventDisableTiming));
     }
     ex->overlapBlur = getenv("ORBX_SERIAL_BLUR") == nullptr;
+    ex->dbgChunks = getenv("ORBX_DEBUG_CHUNKS") != nullptr;
+    ex->dbgSkipH2D = getenv("ORBX_DEBUG_SKIP_H2D") != nullptr;
+    ex->dbgSkipD2H = getenv("ORBX_DEBUG_SKIP_D2H") != nullptr;
+    if (const char *e = getenv("ORBX_CHUNK_PLAN")) ex->chunkPlan = e;
     for (int i = 0; i < ORBX_MAX_CHUNKS; ++i) {
-        const unsigned evFlags = getenv("ORBX_DEBUG_CHUNKS") ? cudaEventDefault : cudaEventDisableTiming;
+        const unsigned evFlags = ex->dbgChunks ? cudaEventDefault : cudaEventDisableTiming;
         CREATE_TRY(cudaEventCreateWithFlags(&ex->evIn[i], evFlags));
         CREATE_TRY(cudaEventCreateWithFlags(&ex->evOut[i], evFlags));
     }
@@ -2701,8 +2708,8 @@ int orbx_extract_batch(orbx_extractor *ex, const uint8_t *const *images, int bat
         if (nb >= 256) {
             // plan in 1024ths of the batch (developer knob ORBX_CHUNK_PLAN="32,96,..." overrides it)
             int plan[ORBX_MAX_CHUNKS], nPlan = 0;
-            if (const char *e = getenv("ORBX_CHUNK_PLAN")) {
-                for (const char *q = e; *q && nPlan < ORBX_MAX_CHUNKS;) { plan[nPlan++] = atoi(q); while (*q && *q != ',') ++q; if (*q == ',') ++q; }
+            if (!ex->chunkPlan.empty()) {
+                for (const char *q = ex->chunkPlan.c_str(); *q && nPlan < ORBX_MAX_CHUNKS;) { plan[nPlan++] = atoi(q); while (*q && *q != ',') ++q; if (*q == ',') ++q; }
             } else {
                 // steady chunks of about 90 frames (fewer would starve the kernels early, more loses launch efficiency)
                 const int nSteady = ex->nSteady > 0 ? ex->nSteady : std::min(8, std::max(2, (nb - nb / 8 + 89) / 90));
@@ -2733,7 +2740,7 @@ int orbx_extract_batch(orbx_extractor *ex, const uint8_t *const *images, int bat
             uint8_t *lvl0 = ex->d_pyr + (size_t)c0 * G.frameBytes + G.lv[0].off;
             if (contiguous && step == (size_t)cols && G.lv[0].pitch == cols) {
                 // frames are back to back and rows are dense: one strided copy for the whole chunk
-                if (!(getenv("ORBX_DEBUG_SKIP_H2D") && ex->dbgCalls > 2))   // developer aid: reuse the frames the first calls copied in
+                if (!(ex->dbgSkipH2D && ex->dbgCalls > 2))   // developer aid: reuse the frames the first calls copied in
                 CUDA_TRY(ex, cudaMemcpy2DAsync(lvl0, (size_t)G.frameBytes, images[b0 + c0], (size_t)rows * cols, (size_t)rows * cols, cn,
                                                cudaMemcpyHostToDevice, sIn));
             } else if (contiguous && step == (size_t)cols) {
@@ -2767,7 +2774,7 @@ int orbx_extract_batch(orbx_extractor *ex, const uint8_t *const *images, int bat
             CUDA_TRY(ex, cudaStreamWaitEvent(sOut, ex->evOut[k], 0));
             CUDA_TRY(ex, cudaMemcpyAsync(ex->h_nOut + c0, ex->d_nOut + c0, cn * sizeof(int), cudaMemcpyDeviceToHost, sOut));
             CUDA_TRY(ex, cudaMemcpyAsync(ex->h_mono + c0, ex->d_mono + c0, cn * sizeof(int), cudaMemcpyDeviceToHost, sOut));
-            if (!getenv("ORBX_DEBUG_SKIP_D2H")) {
+            if (!ex->dbgSkipD2H) {
             CUDA_TRY(ex, cudaMemcpyAsync(kps + ((size_t)b0 + c0) * cap, ex->d_kps + (size_t)c0 * cap, (size_t)cn * cap * sizeof(orbx_keypoint),
                                          cudaMemcpyDeviceToHost, sOut));
             CUDA_TRY(ex, cudaMemcpyAsync(desc + ((size_t)b0 + c0) * cap * 32, ex->d_desc + (size_t)c0 * cap * 32, (size_t)cn * cap * 32,
@@ -2778,7 +2785,7 @@ int orbx_extract_batch(orbx_extractor *ex, const uint8_t *const *images, int bat
         CUDA_TRY(ex, cudaStreamSynchronize(sOut));
         for (int i = 0; i < ex->nSide; ++i) CUDA_TRY(ex, cudaStreamSynchronize(ex->sSide[i]));
         CUDA_TRY(ex, cudaStreamSynchronize(sC));
-        if (getenv("ORBX_DEBUG_CHUNKS") && nChunks > 1) {   // developer aid: when each chunk's copy-in and kernels finished
+        if (ex->dbgChunks && nChunks > 1) {   // developer aid: when each chunk's copy-in and kernels finished
             fprintf(stderr, "[orbx chunks] host enqueue %.2f ms, total %.2f ms;", std::chrono::duration<double, std::milli>(tEnq - tStart).count(),
                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tStart).count());
             for (int k = 1; k < nChunks; ++k) {
