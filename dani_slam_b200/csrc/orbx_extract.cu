@@ -1912,7 +1912,7 @@ struct orbx_extractor {
     int quota[ORBX_MAX_LEVELS];
     int umax[ORBX_HALF_PATCH + 1];
     cudaStream_t stream = nullptr, sH2D = nullptr, sD2H = nullptr, sSide[ORBX_MAX_SIDE] = {};
-    int nSide = 2, nSub = 4, nSteady = 0;     // side streams in use, sub-batches of the device path, steady chunks of the host path
+    int nSide = 2, nSub = 0, nSteady = 0;     // side streams in use, sub-batches of the device path, steady chunks of the host path
     cudaEvent_t evFork = nullptr, evJoin[ORBX_MAX_SIDE] = {};
     // the blur only needs the pyramid: it runs on a partner stream next to FAST + quadtree (index 0: main stream, 1+i: side i)
     cudaStream_t sAux[ORBX_MAX_SIDE + 1] = {};
@@ -2485,7 +2485,8 @@ int run_batch(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, int i
               uint8_t *d_desc, int cap, int *d_nOut, int *d_mono) {
     ex->lastBatch = 0;
     ex->denseSlots.clear();
-    const int nSub = ex->profiling ? 1 : (batch >= 128 ? ex->nSub : (batch >= 32 ? 2 : 1));
+    // sub-batches of at least ~128 frames (smaller launches lose more to fixed latencies than the overlap gains)
+    const int nSub = ex->profiling ? 1 : (ex->nSub > 0 ? (batch >= 2 * ex->nSub ? ex->nSub : 1) : std::min(4, std::max(batch >= 32 ? 2 : 1, batch / 128)));
     if (nSub == 1) return run_pipeline(ex, in0, in0Stride, in0Pitch, batch, d_kps, d_desc, cap, d_nOut, d_mono);
     cudaStream_t *side = ex->sSide;
     const int nSide = ex->nSide;
