@@ -34,7 +34,7 @@ LEVELS, SCALE, INI_TH, MIN_TH = 8, 1.2, 20, 7
 # BASELINE.json configs (frame shape, nFeatures, default frames per GPU per step).  `tum1` is the configuration the
 # headline metric is quoted on (640×480, 1000 keypoints, TUM1.yaml); the others are extra measurements.
 WORKLOADS = {
-    "tum1": (640, 480, 1000, 1024),
+    "tum1": (640, 480, 1000, 2048),
     "euroc": (752, 480, 1200, 512),
     "kitti": (1241, 376, 2000, 256),
     "4k": (3840, 2160, 8000, 64),
