@@ -61,6 +61,21 @@ struct OrbxWork {               // one selected keypoint, handed from k_assemble
     int level, cx, cy, out;
 };
 
+// Every entry point runs on its handle's device and leaves the calling thread's current device as it found it
+// (host applications such as torch keep their own notion of the current device).
+struct OrbxDeviceGuard {
+    int prev = -1;
+    cudaError_t status = cudaSuccess;
+    explicit OrbxDeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        if (prev != dev) status = cudaSetDevice(dev);
+        if (prev == dev) prev = -1;                 // nothing to restore
+    }
+    ~OrbxDeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    OrbxDeviceGuard(const OrbxDeviceGuard &) = delete;
+    OrbxDeviceGuard &operator=(const OrbxDeviceGuard &) = delete;
+};
+
 inline int orbx_align_up(int v, int a) { return (v + a - 1) / a * a; }
 inline long long orbx_align_up_ll(long long v, long long a) { return (v + a - 1) / a * a; }
 

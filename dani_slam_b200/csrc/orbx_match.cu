@@ -167,20 +167,39 @@ __global__ void k_ratio(const int32_t *dist, int nq, double ratio, uint8_t *keep
     keep[i] = (d1 != INT_MAX) && ((double)(float)d0 < __dmul_rn((double)(float)d1, ratio));
 }
 
-// best / second-best over explicit candidate lists; one thread per query
-__global__ void k_top2_lists(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ db, const int32_t *__restrict__ cand,
-                             const int32_t *__restrict__ off, int32_t *bestIdx, int32_t *bestDist, int32_t *secondDist) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// best / second-best over explicit candidate lists (the a12 loops, src/ORBmatcher.cc:84-121): one warp per query, lanes stride
+// over the list; the two smallest (distance, list position) keys reproduce the scalar loop's strict '<' (first candidate wins
+// ties).  The loop starts from bestDist = bestDist2 = 256, so a distance of 256 is never recorded.  secondIdx is the candidate
+// whose octave the reference keeps as bestLevel2 (:110, :117).
+__device__ __forceinline__ void warp_top2(unsigned long long &a, unsigned long long &b) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long oa = __shfl_xor_sync(0xffffffffu, a, o), ob = __shfl_xor_sync(0xffffffffu, b, o);
+        top2_insert(oa, a, b);
+        top2_insert(ob, a, b);
+    }
+}
+__global__ void __launch_bounds__(256) k_top2_lists(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ db,
+                                                    const int32_t *__restrict__ cand, const int32_t *__restrict__ off, int32_t *bestIdx,
+                                                    int32_t *bestDist, int32_t *secondIdx, int32_t *secondDist) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= nq) return;
     const uint4 a0 = q[2 * (long long)i], a1 = q[2 * (long long)i + 1];
-    int b = 256, s = 256, bi = -1;
-    for (int c = off[i]; c < off[i + 1]; ++c) {
+    const unsigned long long NONE = ~0ull;
+    unsigned long long a = NONE, b = NONE;
+    const int c0 = off[i], c1 = off[i + 1];
+    for (int c = c0 + lane; c < c1; c += 32) {
         const int t = cand[c];
         const int d = ham256(a0, a1, db[2 * (long long)t], db[2 * (long long)t + 1]);
-        if (d < b) { s = b; b = d; bi = t; }
-        else if (d < s) s = d;
+        if (d < 256) top2_insert(((unsigned long long)(unsigned)d << 32) | (unsigned)(c - c0), a, b);
     }
-    bestIdx[i] = bi; bestDist[i] = b; secondDist[i] = s;
+    warp_top2(a, b);
+    if (lane == 0) {
+        bestIdx[i] = a == NONE ? -1 : cand[c0 + (int)(a & 0xffffffffu)];
+        bestDist[i] = a == NONE ? 256 : (int)(a >> 32);
+        secondIdx[i] = b == NONE ? -1 : cand[c0 + (int)(b & 0xffffffffu)];
+        secondDist[i] = b == NONE ? 256 : (int)(b >> 32);
+    }
 }
 
 // rotation histogram + three maxima (one block)
@@ -384,9 +403,11 @@ __global__ void k_grid_sort_cells(const int *cellOff, int *items) {
 template <bool FILL>
 __global__ void k_area_query(const float2 *xy, const int32_t *octave, const int *cellOff, const int *items, float minX, float minY,
                              float wInv, float hInv, const float *queries, int nq, int minLevel, int maxLevel, int *cnt,
-                             const int *outOff, int32_t *out) {
+                             const int *outOff, int32_t *out, const int32_t *qLevels = nullptr, const uint8_t *qActive = nullptr) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
+    if (qActive && !qActive[q]) { if (!FILL) cnt[q] = 0; return; }       // callers that skip queries (level1 > 0, points not in view …)
+    if (qLevels) { minLevel = qLevels[2 * q]; maxLevel = qLevels[2 * q + 1]; }
     const float x = queries[3 * q], y = queries[3 * q + 1], r = queries[3 * q + 2];
     const int x0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, minX), r), wInv)));
     const int x1 = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, minX), r), wInv)));
@@ -415,6 +436,79 @@ __global__ void k_area_query(const float2 *xy, const int32_t *octave, const int 
             }
     }
     if (!FILL) cnt[q] = n;
+}
+
+// ---- ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, …) (src/ORBmatcher.cc:43-213), frames with Nleft == -1 ----
+// Stage 1 (parallel, one warp per map point): Hamming distance of the map point's descriptor to every keypoint of its
+// GetFeaturesInArea list; candidates that fail the right-image check of :92-97 (a per-candidate, order-independent test)
+// get the marker 0xffff.
+__global__ void __launch_bounds__(256) k_sbp_dist(const uint4 *__restrict__ mpDesc, int m, const uint4 *__restrict__ desc,
+                                                  const int32_t *__restrict__ cand, const int32_t *__restrict__ off,
+                                                  const float *__restrict__ uRight, const float *__restrict__ projXR,
+                                                  const float *__restrict__ radius, uint16_t *__restrict__ distOut) {
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (j >= m) return;
+    const int c0 = off[j], c1 = off[j + 1];
+    if (c0 == c1) return;
+    const uint4 a0 = mpDesc[2 * (long long)j], a1 = mpDesc[2 * (long long)j + 1];
+    const float xr = uRight ? projXR[j] : 0.f, rad = radius[j];
+    for (int c = c0 + lane; c < c1; c += 32) {
+        const int idx = cand[c];
+        int d = ham256(a0, a1, desc[2 * (long long)idx], desc[2 * (long long)idx + 1]);
+        if (uRight) {
+            const float ur = uRight[idx];
+            if (ur > 0.f && fabsf(__fsub_rn(xr, ur)) > rad) d = 0xffff;
+        }
+        distOut[c] = (uint16_t)d;
+    }
+}
+// Stage 2 (ordered replay, ONE warp): map points are visited in order because an accepted match attaches the map point to its
+// keypoint and later map points skip keypoints whose map point has observations (:88-90).  Per map point the lanes scan the
+// stored distances, drop occupied keypoints, and shuffle-reduce the two smallest (distance, list position) keys = the scalar
+// loop's best / second best; then the level-aware ratio rule of :123-128.  obs[] = Observations() of the map point attached to
+// each keypoint (-1: none), updated as matches are accepted.
+__global__ void __launch_bounds__(32) k_sbp_replay(int m, const uint8_t *__restrict__ active, const int32_t *__restrict__ mpObs,
+                                                   const int32_t *__restrict__ cand, const int32_t *__restrict__ off,
+                                                   const uint16_t *__restrict__ dist, const int32_t *__restrict__ octave, int n,
+                                                   float nnratio, int32_t *obs, int32_t *assigned, int32_t *nMatchesOut) {
+    const int lane = threadIdx.x;
+    for (int i = lane; i < n; i += 32) assigned[i] = -1;
+    __syncwarp();
+    const unsigned long long NONE = ~0ull;
+    int nmatches = 0;
+    for (int j = 0; j < m; ++j) {
+        if (!active[j]) continue;
+        const int c0 = off[j], c1 = off[j + 1];
+        if (c0 == c1) continue;
+        unsigned long long a = NONE, b = NONE;
+        for (int c = c0 + lane; c < c1; c += 32) {
+            const int d = dist[c];
+            if (d >= 256) continue;                               // right-image check failed, or 256 (never below the initial 256)
+            if (obs[cand[c]] > 0) continue;
+            top2_insert(((unsigned long long)(unsigned)d << 32) | (unsigned)(c - c0), a, b);
+        }
+        warp_top2(a, b);
+        if (a == NONE) continue;
+        const int bestDist = (int)(a >> 32), bestIdx = cand[c0 + (int)(a & 0xffffffffu)];
+        if (bestDist > 100) continue;                             // TH_HIGH (:124)
+        const int bestLevel = octave[bestIdx];
+        const int bestDist2 = b == NONE ? 256 : (int)(b >> 32);
+        const int bestLevel2 = b == NONE ? -1 : octave[cand[c0 + (int)(b & 0xffffffffu)]];
+        const float lim = __fmul_rn(nnratio, (float)bestDist2);
+        if (bestLevel == bestLevel2 && (float)bestDist > lim) continue;
+        if (bestLevel != bestLevel2 || (float)bestDist <= lim) {
+            ++nmatches;
+            __syncwarp();
+            if (lane == 0) { obs[bestIdx] = mpObs[j]; assigned[bestIdx] = j; }
+            __syncwarp();
+        }
+    }
+    if (lane == 0) *nMatchesOut = nmatches;
+}
+// vbPrevMatched update of SearchForInitialization (src/ORBmatcher.cc:754-756)
+__global__ void k_update_prev(const int32_t *m12, int n1, const float2 *xy2, float2 *prev) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n1 && m12[i] >= 0) prev[i] = xy2[m12[i]];
 }
 
 // ---- stereo association tail (src/Frame.cc:862-914) over the kNN + ratio matches; one block ----
@@ -503,6 +597,7 @@ struct orbx_matcher {
     std::string err;
     uint2 *d_partial = nullptr; size_t partialCap = 0;
     uint8_t *d_buf = nullptr; size_t bufCap = 0;  // staging for the host-buffer entry points
+    uint8_t *d_buf2 = nullptr; size_t buf2Cap = 0; // second arena: candidate lists whose size is only known after a count pass
     int nSM = 148;
 };
 
@@ -524,7 +619,38 @@ int stage(orbx_matcher *m, size_t bytes) {
     m->bufCap = bytes;
     return ORBX_OK;
 }
+int stage2(orbx_matcher *m, size_t bytes) {
+    if (bytes <= m->buf2Cap && m->d_buf2) return ORBX_OK;
+    if (m->d_buf2) cudaFree(m->d_buf2);
+    m->d_buf2 = nullptr; m->buf2Cap = 0;
+    bytes += bytes / 2;                                 // list sizes vary from call to call: grow with headroom
+    MCUDA_TRY(m, cudaMalloc((void **)&m->d_buf2, bytes));
+    m->buf2Cap = bytes;
+    return ORBX_OK;
+}
 inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// Bump allocator over the staging arena (all blocks 256-byte aligned).
+struct Carver {
+    uint8_t *p;
+    template <typename T> T *take(size_t count) { T *r = reinterpret_cast<T *>(p); p += al256(count * sizeof(T)); return r; }
+};
+
+// Frame::AssignFeaturesToGrid on the device (src/Frame.cc:387-418): cellOff[GRID_CELLS + 1] + items[n] in push_back order.
+// dCnt / dOff / dFill are GRID_CELLS + 1 ints each and contiguous.
+int grid_build(orbx_matcher *m, const float2 *dxy, int n, float minX, float minY, float wInv, float hInv, int *dCnt, int *dOff, int *dFill,
+               int *dItems) {
+    cudaStream_t s = m->stream;
+    MCUDA_TRY(m, cudaMemsetAsync(dCnt, 0, 3 * al256((GRID_CELLS + 1) * 4), s));
+    if (n > 0) k_grid_count<<<(n + 255) / 256, 256, 0, s>>>(dxy, n, minX, minY, wInv, hInv, dCnt);
+    k_scan_excl<<<1, 1024, 0, s>>>(dCnt, GRID_CELLS, dOff);
+    if (n > 0) {
+        k_grid_fill<<<(n + 255) / 256, 256, 0, s>>>(dxy, n, minX, minY, wInv, hInv, dOff, dFill, dItems);
+        k_grid_sort_cells<<<(GRID_CELLS + 255) / 256, 256, 0, s>>>(dOff, dItems);
+    }
+    MCUDA_TRY(m, cudaGetLastError());
+    return ORBX_OK;
+}
 }  // namespace
 
 extern "C" {
@@ -549,10 +675,11 @@ orbx_matcher *orbx_matcher_create(int device) {
 
 void orbx_matcher_destroy(orbx_matcher *m) {
     if (!m) return;
-    cudaSetDevice(m->device);
+    OrbxDeviceGuard dg_(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     if (m->d_partial) cudaFree(m->d_partial);
     if (m->d_buf) cudaFree(m->d_buf);
+    if (m->d_buf2) cudaFree(m->d_buf2);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -561,6 +688,7 @@ const char *orbx_matcher_last_error(const orbx_matcher *m) { return m ? m->err.c
 void *orbx_matcher_stream(orbx_matcher *m) { return m ? (void *)m->stream : nullptr; }
 int orbx_matcher_sync(orbx_matcher *m) {
     if (!m) return ORBX_ERR_ARG;
+    OrbxDeviceGuard dg_(m->device); MCUDA_TRY(m, dg_.status);
     MCUDA_TRY(m, cudaStreamSynchronize(m->stream));
     return ORBX_OK;
 }
@@ -574,7 +702,7 @@ int orbx_hamming_knn2_device(orbx_matcher *m, const uint8_t *d_q, int nq, const 
         return ORBX_ERR_ARG;
     }
     if (nq == 0) return ORBX_OK;
-    MCUDA_TRY(m, cudaSetDevice(m->device));
+    OrbxDeviceGuard dg_(m->device); MCUDA_TRY(m, dg_.status);
     // queries per block tile: R·256; pick R so small problems still spread over the SMs
     const int R = nq > 2 * KNN_THREADS ? 4 : (nq > KNN_THREADS ? 2 : 1);
     const int qTiles = (nq + KNN_THREADS * R - 1) / (KNN_THREADS * R);
@@ -608,7 +736,7 @@ int orbx_knn2_merge_device(orbx_matcher *m, const int32_t *d_idx_all, const int3
         return ORBX_ERR_ARG;
     }
     if (nq == 0) return ORBX_OK;
-    MCUDA_TRY(m, cudaSetDevice(m->device));
+    OrbxDeviceGuard dg_(m->device); MCUDA_TRY(m, dg_.status);
     k_knn2_merge_shards<<<(nq * 32 + 255) / 256, 256, 0, m->stream>>>(d_idx_all, d_dist_all, n_shards, nq, d_idx, d_dist);
     MCUDA_TRY(m, cudaGetLastError());
     return ORBX_OK;
@@ -622,7 +750,7 @@ int orbx_hamming_knn2(orbx_matcher *m, const uint8_t *query, int nq, const uint8
         return ORBX_ERR_ARG;
     }
     if (nq == 0) return ORBX_OK;
-    MCUDA_TRY(m, cudaSetDevice(m->device));
+    OrbxDeviceGuard dg_(m->device); MCUDA_TRY(m, dg_.status);
     const size_t qB = al256((size_t)nq * 32), dB = al256((size_t)ndb * 32 + 32), oB = al256((size_t)nq * 8);
     int rc = stage(m, qB + dB + 2 * oB);
     if (rc) return rc;
@@ -641,6 +769,7 @@ int orbx_hamming_knn2(orbx_matcher *m, const uint8_t *query, int nq, const uint8
 int orbx_ratio_test_device(orbx_matcher *m, const int32_t *d_dist, int nq, double ratio, uint8_t *d_keep) {
     if (!m) return ORBX_ERR_ARG;
     if (nq <= 0) return ORBX_OK;
+    OrbxDeviceGuard dg_(m->device); MCUDA_TRY(m, dg_.status);
     k_ratio<<<(nq + 255) / 256, 256, 0, m->stream>>>(d_dist, nq, ratio, d_keep);
     MCUDA_TRY(m, cudaGetLastError());
     return ORBX_OK;
@@ -650,7 +779,7 @@ int orbx_ratio_test(orbx_matcher *m, const int32_t *dist, int nq, double ratio, 
     if (!m) return ORBX_ERR_ARG;
     if (nq < 0 || (nq > 0 && (!dist || !keep))) { m->err = "orbx_ratio_test: bad argument"; return ORBX_ERR_ARG; }
     if (nq == 0) return ORBX_OK;
-    MCUDA_TRY(m, cudaSetDevice(m->device));
+    OrbxDeviceGuard dg_(m->device); MCUDA_TRY(m, dg_.status);
     const size_t dB = al256((size_t)nq * 8);
     int rc = stage(m, dB + al256(nq));
     if (rc) return rc;
@@ -666,7 +795,7 @@ int orbx_ratio_test(orbx_matcher *m, const int32_t *dist, int nq, double ratio, 
 
 int orbx_hamming_top2_lists(orbx_matcher *m, const uint8_t *query, int nq, const uint8_t *train, int64_t ndb,
                             const int32_t *cand, const int32_t *cand_off, int32_t *best_idx, int32_t *best_dist,
-                            int32_t *second_dist) {
+                            int32_t *second_idx, int32_t *second_dist) {
     if (!m) return ORBX_ERR_ARG;
     if (nq < 0 || ndb < 0 || (nq > 0 && (!query || !cand_off || !best_idx || !best_dist || !second_dist))) {
         m->err = "orbx_hamming_top2_lists: bad argument";
@@ -674,30 +803,28 @@ int orbx_hamming_top2_lists(orbx_matcher *m, const uint8_t *query, int nq, const
     }
     if (nq == 0) return ORBX_OK;
     const int nc = cand_off[nq];
+    if (nc > 0 && !cand) { m->err = "orbx_hamming_top2_lists: bad argument"; return ORBX_ERR_ARG; }
     for (int i = 0; i < nc; ++i)
         if (cand[i] < 0 || cand[i] >= ndb) { m->err = "orbx_hamming_top2_lists: candidate index out of range"; return ORBX_ERR_ARG; }
-    MCUDA_TRY(m, cudaSetDevice(m->device));
+    OrbxDeviceGuard dg_(m->device); MCUDA_TRY(m, dg_.status);
     const size_t qB = al256((size_t)nq * 32), dB = al256((size_t)ndb * 32 + 32), cB = al256((size_t)std::max(nc, 1) * 4),
                  oB = al256((size_t)(nq + 1) * 4);
-    int rc = stage(m, qB + dB + cB + 4 * oB);
+    int rc = stage(m, qB + dB + cB + 5 * oB);
     if (rc) return rc;
-    uint8_t *p = m->d_buf;
-    uint8_t *dq = p; p += qB;
-    uint8_t *dd = p; p += dB;
-    int32_t *dc = (int32_t *)p; p += cB;
-    int32_t *doff = (int32_t *)p; p += oB;
-    int32_t *dbi = (int32_t *)p; p += oB;
-    int32_t *dbd = (int32_t *)p; p += oB;
-    int32_t *dsd = (int32_t *)p;
+    Carver cv{m->d_buf};
+    uint8_t *dq = cv.take<uint8_t>((size_t)nq * 32), *dd = cv.take<uint8_t>((size_t)ndb * 32 + 32);
+    int32_t *dc = cv.take<int32_t>(std::max(nc, 1)), *doff = cv.take<int32_t>(nq + 1);
+    int32_t *dbi = cv.take<int32_t>(nq + 1), *dbd = cv.take<int32_t>(nq + 1), *dsi = cv.take<int32_t>(nq + 1), *dsd = cv.take<int32_t>(nq + 1);
     cudaStream_t s = m->stream;
     MCUDA_TRY(m, cudaMemcpyAsync(dq, query, (size_t)nq * 32, cudaMemcpyHostToDevice, s));
     if (ndb > 0) MCUDA_TRY(m, cudaMemcpyAsync(dd, train, (size_t)ndb * 32, cudaMemcpyHostToDevice, s));
     if (nc > 0) MCUDA_TRY(m, cudaMemcpyAsync(dc, cand, (size_t)nc * 4, cudaMemcpyHostToDevice, s));
     MCUDA_TRY(m, cudaMemcpyAsync(doff, cand_off, (size_t)(nq + 1) * 4, cudaMemcpyHostToDevice, s));
-    k_top2_lists<<<(nq + 127) / 128, 128, 0, s>>>((const uint4 *)dq, nq, (const uint4 *)dd, dc, doff, dbi, dbd, dsd);
+    k_top2_lists<<<(nq * 32 + 255) / 256, 256, 0, s>>>((const uint4 *)dq, nq, (const uint4 *)dd, dc, doff, dbi, dbd, dsi, dsd);
     MCUDA_TRY(m, cudaGetLastError());
     MCUDA_TRY(m, cudaMemcpyAsync(best_idx, dbi, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
     MCUDA_TRY(m, cudaMemcpyAsync(best_dist, dbd, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+    if (second_idx) MCUDA_TRY(m, cudaMemcpyAsync(second_idx, dsi, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
     MCUDA_TRY(m, cudaMemcpyAsync(second_dist, dsd, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
     MCUDA_TRY(m, cudaStreamSynchronize(s));
     return ORBX_OK;
@@ -717,7 +844,7 @@ int orbx_search_for_initialization(orbx_matcher *m, const uint8_t *desc1, const 
     const int nc = cand_off[n1];
     for (int i = 0; i < nc; ++i)
         if (cand[i] < 0 || cand[i] >= n2) { m->err = "orbx_search_for_initialization: candidate index out of range"; return ORBX_ERR_ARG; }
-    MCUDA_TRY(m, cudaSetDevice(m->device));
+    OrbxDeviceGuard dg_(m->device); MCUDA_TRY(m, dg_.status);
     const size_t d1B = al256((size_t)n1 * 32), d2B = al256((size_t)n2 * 32 + 32), a1B = al256((size_t)n1 * 4), a2B = al256((size_t)n2 * 4 + 4),
                  cB = al256((size_t)std::max(nc, 1) * 4), oB = al256((size_t)(n1 + 1) * 4);
     int rc = stage(m, d1B + d2B + 2 * a1B + a2B + cB + oB + a1B /*m12*/ + 2 * a2B /*m21, matchedDist*/ + al256(n1) + 256);
@@ -760,7 +887,7 @@ int orbx_features_in_area(orbx_matcher *m, const float *keypoints_xy, const int3
         m->err = "orbx_features_in_area: bad argument";
         return ORBX_ERR_ARG;
     }
-    MCUDA_TRY(m, cudaSetDevice(m->device));
+    OrbxDeviceGuard dg_(m->device); MCUDA_TRY(m, dg_.status);
     const float wInv = (float)GRID_COLS / (float)(max_x - min_x), hInv = (float)GRID_ROWS / (float)(max_y - min_y);
     const size_t xyB = al256((size_t)std::max(n, 1) * 8), ocB = al256((size_t)std::max(n, 1) * 4), cellB = al256((GRID_CELLS + 1) * 4),
                  itB = al256((size_t)std::max(n, 1) * 4), qB = al256((size_t)std::max(nq, 1) * 12), qcB = al256((size_t)(nq + 1) * 4);
@@ -827,7 +954,7 @@ int orbx_stereo_tail(orbx_matcher *m, const float *u_left, const float *u_right,
     }
     *n_kept = 0;
     if (n_left == 0) return ORBX_OK;
-    MCUDA_TRY(m, cudaSetDevice(m->device));
+    OrbxDeviceGuard dg_(m->device); MCUDA_TRY(m, dg_.status);
     const size_t lB = al256((size_t)n_left * 4), rB = al256((size_t)std::max(n_right, 1) * 4), iB = al256((size_t)n_left * 8), kB = al256(n_left);
     int rc = stage(m, 3 * lB + rB + 2 * iB + kB + 256);
     if (rc) return rc;
@@ -870,7 +997,7 @@ int orbx_undistort_points_device(orbx_matcher *m, const float *d_xy, int stride_
         return ORBX_ERR_ARG;
     }
     if (n == 0) return ORBX_OK;
-    MCUDA_TRY(m, cudaSetDevice(m->device));
+    OrbxDeviceGuard dg_(m->device); MCUDA_TRY(m, dg_.status);
     if (n_coef == 0 || dist_coef[0] == 0.0f) {          // mvKeysUn = mvKeys (src/Frame.cc:751-755)
         if (d_out != d_xy || stride_in != stride_out)
             MCUDA_TRY(m, cudaMemcpy2DAsync(d_out, (size_t)stride_out * 4, d_xy, (size_t)stride_in * 4, 8, n, cudaMemcpyDeviceToDevice, m->stream));
@@ -886,7 +1013,7 @@ int orbx_undistort_keypoints(orbx_matcher *m, const orbx_keypoint *kps, int n, f
     if (!m) return ORBX_ERR_ARG;
     if (n < 0 || n_coef < 0 || n_coef > 14 || (n_coef > 0 && !dist_coef) || (n > 0 && (!kps || !kps_un))) { m->err = "orbx_undistort_keypoints: bad argument"; return ORBX_ERR_ARG; }
     if (n == 0) return ORBX_OK;
-    MCUDA_TRY(m, cudaSetDevice(m->device));
+    OrbxDeviceGuard dg_(m->device); MCUDA_TRY(m, dg_.status);
     const size_t bytes = (size_t)n * sizeof(orbx_keypoint);
     int rc = stage(m, al256(bytes));
     if (rc) return rc;
@@ -907,7 +1034,7 @@ int orbx_image_bounds(orbx_matcher *m, int cols, int rows, float fx, float fy, f
         bounds4[0] = 0.f; bounds4[1] = (float)cols; bounds4[2] = 0.f; bounds4[3] = (float)rows;
         return ORBX_OK;
     }
-    MCUDA_TRY(m, cudaSetDevice(m->device));
+    OrbxDeviceGuard dg_(m->device); MCUDA_TRY(m, dg_.status);
     int rc = stage(m, 256);
     if (rc) return rc;
     const float c[8] = {0.f, 0.f, (float)cols, 0.f, 0.f, (float)rows, (float)cols, (float)rows};
@@ -928,6 +1055,7 @@ int orbx_image_bounds(orbx_matcher *m, int cols, int rows, float fx, float fy, f
 int orbx_rot_hist_filter_device(orbx_matcher *m, const float *d_a, const float *d_b, int n, uint8_t *d_keep) {
     if (!m) return ORBX_ERR_ARG;
     if (n <= 0) return ORBX_OK;
+    OrbxDeviceGuard dg_(m->device); MCUDA_TRY(m, dg_.status);
     k_rot_hist<<<1, 256, 0, m->stream>>>(d_a, d_b, n, d_keep);
     MCUDA_TRY(m, cudaGetLastError());
     return ORBX_OK;
@@ -937,7 +1065,7 @@ int orbx_rot_hist_filter(orbx_matcher *m, const float *angle_a, const float *ang
     if (!m) return ORBX_ERR_ARG;
     if (n < 0 || (n > 0 && (!angle_a || !angle_b || !keep))) { m->err = "orbx_rot_hist_filter: bad argument"; return ORBX_ERR_ARG; }
     if (n == 0) return ORBX_OK;
-    MCUDA_TRY(m, cudaSetDevice(m->device));
+    OrbxDeviceGuard dg_(m->device); MCUDA_TRY(m, dg_.status);
     const size_t aB = al256((size_t)n * 4);
     int rc = stage(m, 2 * aB + al256(n));
     if (rc) return rc;
@@ -949,6 +1077,181 @@ int orbx_rot_hist_filter(orbx_matcher *m, const float *angle_a, const float *ang
     if (rc) return rc;
     MCUDA_TRY(m, cudaMemcpyAsync(keep, dk, n, cudaMemcpyDeviceToHost, m->stream));
     MCUDA_TRY(m, cudaStreamSynchronize(m->stream));
+    return ORBX_OK;
+}
+
+int orbx_search_by_projection(orbx_matcher *m, const orbx_keypoint *keypoints_un, const uint8_t *descriptors, int n, const float *u_right,
+                              const int32_t *kp_obs, const float *bounds4, const float *scale_factors, int n_levels, const float *mp_proj5,
+                              const int32_t *mp_level, const uint8_t *mp_flags, const int32_t *mp_obs, const uint8_t *mp_desc, int n_mp,
+                              float nnratio, float th, int far_points, float th_far, int32_t *assigned, int32_t *n_matches) {
+    if (!m) return ORBX_ERR_ARG;
+    if (n < 0 || n_mp < 0 || n_levels < 1 || !bounds4 || !scale_factors || !n_matches || (n > 0 && (!keypoints_un || !descriptors || !assigned)) ||
+        (n_mp > 0 && (!mp_proj5 || !mp_level || !mp_flags || !mp_obs || !mp_desc)) || !(bounds4[2] > bounds4[0]) || !(bounds4[3] > bounds4[1])) {
+        m->err = "orbx_search_by_projection: bad argument";
+        return ORBX_ERR_ARG;
+    }
+    *n_matches = 0;
+    for (int i = 0; i < n; ++i) assigned[i] = -1;
+    if (n == 0 || n_mp == 0) return ORBX_OK;
+    // per map point, on the host (a handful of scalar operations each): the skip tests of :52-59, the search radius of
+    // :64-69 / :215-221 and the level band nPredictedLevel-1 … nPredictedLevel of :72
+    std::vector<float> q((size_t)n_mp * 3), rad(n_mp), xr(n_mp);
+    std::vector<int32_t> lv((size_t)n_mp * 2);
+    std::vector<uint8_t> act(n_mp);
+    const bool bFactor = th != 1.0;
+    for (int j = 0; j < n_mp; ++j) {
+        const int L = mp_level[j];
+        bool a = (mp_flags[j] & 1) && !(mp_flags[j] & 2) && !(far_points && mp_proj5[5 * j + 4] > th_far);
+        if (a && (L < 0 || L >= n_levels)) { m->err = "orbx_search_by_projection: predicted level out of range"; return ORBX_ERR_ARG; }
+        float r = (mp_proj5[5 * j + 3] > 0.998) ? 2.5f : 4.0f;
+        if (bFactor) r *= th;
+        const float rs = a ? r * scale_factors[L] : 0.f;
+        q[3 * j] = mp_proj5[5 * j]; q[3 * j + 1] = mp_proj5[5 * j + 1]; q[3 * j + 2] = rs;
+        rad[j] = rs; xr[j] = mp_proj5[5 * j + 2];
+        lv[2 * j] = L - 1; lv[2 * j + 1] = L;
+        act[j] = a;
+    }
+    std::vector<float> xy((size_t)n * 2);
+    std::vector<int32_t> oc(n), obs(n, -1);
+    for (int i = 0; i < n; ++i) { xy[2 * i] = keypoints_un[i].x; xy[2 * i + 1] = keypoints_un[i].y; oc[i] = keypoints_un[i].octave; }
+    if (kp_obs) obs.assign(kp_obs, kp_obs + n);
+    OrbxDeviceGuard dg_(m->device); MCUDA_TRY(m, dg_.status);
+    const float minX = bounds4[0], minY = bounds4[1];
+    const float wInv = (float)GRID_COLS / (float)(bounds4[2] - bounds4[0]), hInv = (float)GRID_ROWS / (float)(bounds4[3] - bounds4[1]);
+    const size_t cellB = al256((GRID_CELLS + 1) * 4);
+    int rc = stage(m, al256((size_t)n * 8) + 5 * al256((size_t)n * 4) + al256((size_t)n * 32 + 32) + 3 * cellB + al256((size_t)n_mp * 12) +
+                          al256((size_t)n_mp * 8) + 3 * al256((size_t)n_mp * 4) + al256(n_mp) + al256((size_t)n_mp * 32 + 32) +
+                          2 * al256((size_t)(n_mp + 1) * 4) + 256);
+    if (rc) return rc;
+    Carver cv{m->d_buf};
+    float2 *dxy = cv.take<float2>(n);
+    int32_t *doc = cv.take<int32_t>(n), *dobs = cv.take<int32_t>(n), *dasg = cv.take<int32_t>(n);
+    float *dur = cv.take<float>(n);
+    int *dItems = cv.take<int>(n);
+    uint8_t *ddesc = cv.take<uint8_t>((size_t)n * 32 + 32);
+    int *dCnt = (int *)cv.p; cv.p += cellB;
+    int *dOff = (int *)cv.p; cv.p += cellB;
+    int *dFill = (int *)cv.p; cv.p += cellB;
+    float *dq = cv.take<float>((size_t)n_mp * 3);
+    int32_t *dlv = cv.take<int32_t>((size_t)n_mp * 2);
+    float *drad = cv.take<float>(n_mp), *dxr = cv.take<float>(n_mp);
+    int32_t *dmobs = cv.take<int32_t>(n_mp);
+    uint8_t *dact = cv.take<uint8_t>(n_mp);
+    uint8_t *dmdesc = cv.take<uint8_t>((size_t)n_mp * 32 + 32);
+    int *dqCnt = cv.take<int>(n_mp + 1), *dqOff = cv.take<int>(n_mp + 1);
+    int32_t *dn = cv.take<int32_t>(1);
+    cudaStream_t s = m->stream;
+    MCUDA_TRY(m, cudaMemcpyAsync(dxy, xy.data(), (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(doc, oc.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(dobs, obs.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    if (u_right) MCUDA_TRY(m, cudaMemcpyAsync(dur, u_right, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(ddesc, descriptors, (size_t)n * 32, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(dq, q.data(), (size_t)n_mp * 12, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(dlv, lv.data(), (size_t)n_mp * 8, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(drad, rad.data(), (size_t)n_mp * 4, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(dxr, xr.data(), (size_t)n_mp * 4, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(dmobs, mp_obs, (size_t)n_mp * 4, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(dact, act.data(), (size_t)n_mp, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(dmdesc, mp_desc, (size_t)n_mp * 32, cudaMemcpyHostToDevice, s));
+    rc = grid_build(m, dxy, n, minX, minY, wInv, hInv, dCnt, dOff, dFill, dItems);
+    if (rc) return rc;
+    k_area_query<false><<<(n_mp + 127) / 128, 128, 0, s>>>(dxy, doc, dOff, dItems, minX, minY, wInv, hInv, dq, n_mp, 0, 0, dqCnt, nullptr, nullptr, dlv, dact);
+    k_scan_excl<<<1, 1024, 0, s>>>(dqCnt, n_mp, dqOff);
+    int total = 0;
+    MCUDA_TRY(m, cudaMemcpyAsync(&total, dqOff + n_mp, 4, cudaMemcpyDeviceToHost, s));
+    MCUDA_TRY(m, cudaStreamSynchronize(s));
+    if (total > 0) {
+        rc = stage2(m, al256((size_t)total * 4) + al256((size_t)total * 2));
+        if (rc) return rc;
+        int32_t *dcand = (int32_t *)m->d_buf2;
+        uint16_t *ddist = (uint16_t *)(m->d_buf2 + al256((size_t)total * 4));
+        k_area_query<true><<<(n_mp + 127) / 128, 128, 0, s>>>(dxy, doc, dOff, dItems, minX, minY, wInv, hInv, dq, n_mp, 0, 0, nullptr, dqOff, dcand, dlv, dact);
+        k_sbp_dist<<<(n_mp * 32 + 255) / 256, 256, 0, s>>>((const uint4 *)dmdesc, n_mp, (const uint4 *)ddesc, dcand, dqOff, u_right ? dur : nullptr, dxr, drad, ddist);
+        k_sbp_replay<<<1, 32, 0, s>>>(n_mp, dact, dmobs, dcand, dqOff, ddist, doc, n, nnratio, dobs, dasg, dn);
+        MCUDA_TRY(m, cudaGetLastError());
+        MCUDA_TRY(m, cudaMemcpyAsync(assigned, dasg, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+        MCUDA_TRY(m, cudaMemcpyAsync(n_matches, dn, 4, cudaMemcpyDeviceToHost, s));
+        MCUDA_TRY(m, cudaStreamSynchronize(s));
+    }
+    return ORBX_OK;
+}
+
+int orbx_search_for_initialization_frames(orbx_matcher *m, const orbx_keypoint *kps1, const uint8_t *desc1, int n1, const orbx_keypoint *kps2,
+                                          const uint8_t *desc2, int n2, const float *bounds4, float *prev_matched_xy, int window_size,
+                                          float nnratio, int check_orientation, int32_t *matches12, int32_t *n_matches) {
+    if (!m) return ORBX_ERR_ARG;
+    if (n1 < 0 || n2 < 0 || !bounds4 || !n_matches || (n1 > 0 && (!kps1 || !desc1 || !prev_matched_xy || !matches12)) || (n2 > 0 && (!kps2 || !desc2)) ||
+        !(bounds4[2] > bounds4[0]) || !(bounds4[3] > bounds4[1])) {
+        m->err = "orbx_search_for_initialization_frames: bad argument";
+        return ORBX_ERR_ARG;
+    }
+    *n_matches = 0;
+    for (int i = 0; i < n1; ++i) matches12[i] = -1;
+    if (n1 == 0 || n2 == 0) return ORBX_OK;
+    // F2.GetFeaturesInArea(vbPrevMatched[i1].x, vbPrevMatched[i1].y, windowSize, level1, level1) for level1 == 0 (:661-666)
+    std::vector<float> q((size_t)n1 * 3), a1(n1), a2(n2), xy2((size_t)n2 * 2);
+    std::vector<int32_t> o1(n1), o2(n2);
+    std::vector<uint8_t> act(n1);
+    for (int i = 0; i < n1; ++i) {
+        q[3 * i] = prev_matched_xy[2 * i]; q[3 * i + 1] = prev_matched_xy[2 * i + 1]; q[3 * i + 2] = (float)window_size;
+        a1[i] = kps1[i].angle; o1[i] = kps1[i].octave; act[i] = kps1[i].octave <= 0;
+    }
+    for (int i = 0; i < n2; ++i) { xy2[2 * i] = kps2[i].x; xy2[2 * i + 1] = kps2[i].y; a2[i] = kps2[i].angle; o2[i] = kps2[i].octave; }
+    OrbxDeviceGuard dg_(m->device); MCUDA_TRY(m, dg_.status);
+    const float minX = bounds4[0], minY = bounds4[1];
+    const float wInv = (float)GRID_COLS / (float)(bounds4[2] - bounds4[0]), hInv = (float)GRID_ROWS / (float)(bounds4[3] - bounds4[1]);
+    const size_t cellB = al256((GRID_CELLS + 1) * 4);
+    int rc = stage(m, al256((size_t)n1 * 32) + al256((size_t)n2 * 32 + 32) + 4 * al256((size_t)n1 * 4) + al256(n1) * 2 + al256((size_t)n1 * 12) +
+                          al256((size_t)n1 * 8) + 2 * al256((size_t)(n1 + 1) * 4) + al256((size_t)n2 * 8) + 5 * al256((size_t)n2 * 4) + 3 * cellB + 512);
+    if (rc) return rc;
+    Carver cv{m->d_buf};
+    uint8_t *dd1 = cv.take<uint8_t>((size_t)n1 * 32), *dd2 = cv.take<uint8_t>((size_t)n2 * 32 + 32);
+    float *da1 = cv.take<float>(n1);
+    int32_t *do1 = cv.take<int32_t>(n1), *dm12 = cv.take<int32_t>(n1);
+    int8_t *dbin = cv.take<int8_t>(n1);
+    uint8_t *dact = cv.take<uint8_t>(n1);
+    float *dq = cv.take<float>((size_t)n1 * 3);
+    float2 *dprev = cv.take<float2>(n1);
+    int *dqCnt = cv.take<int>(n1 + 1), *dqOff = cv.take<int>(n1 + 1);
+    float2 *dxy2 = cv.take<float2>(n2);
+    float *da2 = cv.take<float>(n2);
+    int32_t *do2 = cv.take<int32_t>(n2), *dm21 = cv.take<int32_t>(n2), *dmd = cv.take<int32_t>(n2);
+    int *dItems = cv.take<int>(n2);
+    int *dCnt = (int *)cv.p; cv.p += cellB;
+    int *dOff = (int *)cv.p; cv.p += cellB;
+    int *dFill = (int *)cv.p; cv.p += cellB;
+    int32_t *dn = cv.take<int32_t>(1);
+    cudaStream_t s = m->stream;
+    MCUDA_TRY(m, cudaMemcpyAsync(dd1, desc1, (size_t)n1 * 32, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(dd2, desc2, (size_t)n2 * 32, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(da1, a1.data(), (size_t)n1 * 4, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(do1, o1.data(), (size_t)n1 * 4, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(dact, act.data(), (size_t)n1, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(dq, q.data(), (size_t)n1 * 12, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(dprev, prev_matched_xy, (size_t)n1 * 8, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(dxy2, xy2.data(), (size_t)n2 * 8, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(da2, a2.data(), (size_t)n2 * 4, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(do2, o2.data(), (size_t)n2 * 4, cudaMemcpyHostToDevice, s));
+    rc = grid_build(m, dxy2, n2, minX, minY, wInv, hInv, dCnt, dOff, dFill, dItems);
+    if (rc) return rc;
+    k_area_query<false><<<(n1 + 127) / 128, 128, 0, s>>>(dxy2, do2, dOff, dItems, minX, minY, wInv, hInv, dq, n1, 0, 0, dqCnt, nullptr, nullptr, nullptr, dact);
+    k_scan_excl<<<1, 1024, 0, s>>>(dqCnt, n1, dqOff);
+    int total = 0;
+    MCUDA_TRY(m, cudaMemcpyAsync(&total, dqOff + n1, 4, cudaMemcpyDeviceToHost, s));
+    MCUDA_TRY(m, cudaStreamSynchronize(s));
+    rc = stage2(m, al256((size_t)std::max(total, 1) * 4));
+    if (rc) return rc;
+    int32_t *dcand = (int32_t *)m->d_buf2;
+    if (total > 0)
+        k_area_query<true><<<(n1 + 127) / 128, 128, 0, s>>>(dxy2, do2, dOff, dItems, minX, minY, wInv, hInv, dq, n1, 0, 0, nullptr, dqOff, dcand, nullptr, dact);
+    k_search_init<<<1, 32, 0, s>>>((const uint4 *)dd1, da1, do1, n1, (const uint4 *)dd2, da2, n2, dcand, dqOff, nnratio, check_orientation,
+                                   dm12, dm21, dmd, dbin, dn);
+    k_update_prev<<<(n1 + 255) / 256, 256, 0, s>>>(dm12, n1, dxy2, dprev);
+    MCUDA_TRY(m, cudaGetLastError());
+    MCUDA_TRY(m, cudaMemcpyAsync(matches12, dm12, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(prev_matched_xy, dprev, (size_t)n1 * 8, cudaMemcpyDeviceToHost, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(n_matches, dn, 4, cudaMemcpyDeviceToHost, s));
+    MCUDA_TRY(m, cudaStreamSynchronize(s));
     return ORBX_OK;
 }
 

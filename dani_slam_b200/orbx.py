@@ -79,7 +79,9 @@ def lib() -> C.CDLL:
     L.orbx_knn2_merge_device.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     L.orbx_ratio_test.argtypes = [vp, vp, i32, f64, vp]
     L.orbx_ratio_test_device.argtypes = [vp, vp, i32, f64, vp]
-    L.orbx_hamming_top2_lists.argtypes = [vp, vp, i32, vp, i64, vp, vp, vp, vp, vp]
+    L.orbx_hamming_top2_lists.argtypes = [vp, vp, i32, vp, i64, vp, vp, vp, vp, vp, vp]
+    L.orbx_search_by_projection.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, f32, f32, i32, f32, vp, vp]
+    L.orbx_search_for_initialization_frames.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, vp, i32, f32, i32, vp, vp]
     L.orbx_rot_hist_filter.argtypes = [vp, vp, vp, i32, vp]
     L.orbx_features_in_area.argtypes = [vp, vp, vp, i32, f32, f32, f32, f32, vp, i32, i32, i32, vp, vp, i32, vp]
     L.orbx_stereo_tail.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, f32, f32, vp, vp, vp]
@@ -352,9 +354,43 @@ class ORBmatcher:
         cand = np.ascontiguousarray(cand, np.int32)
         off = np.ascontiguousarray(cand_off, np.int32)
         assert len(off) == len(q) + 1
-        bi, bd, sd = (np.zeros(len(q), np.int32) for _ in range(3))
-        self._chk(self.L.orbx_hamming_top2_lists(self.h, _p(q), len(q), _p(t), len(t), _p(cand), _p(off), _p(bi), _p(bd), _p(sd)))
-        return bi, bd, sd
+        bi, bd, si, sd = (np.zeros(len(q), np.int32) for _ in range(4))
+        self._chk(self.L.orbx_hamming_top2_lists(self.h, _p(q), len(q), _p(t), len(t), _p(cand), _p(off), _p(bi), _p(bd), _p(si), _p(sd)))
+        return bi, bd, si, sd
+
+    def SearchByProjection(self, F, mp_proj5, mp_level, mp_flags, mp_obs, mp_desc, th=3.0, bFarPoints=False, thFarPoints=50.0):
+        """`ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, th, bFarPoints, thFarPoints)`
+        (src/ORBmatcher.cc:43-213, Nleft == -1 frames).  F is a dict with the Frame members the function reads: `mvKeysUn`
+        (keypoint records), `mDescriptors`, `bounds` = (mnMinX, mnMinY, mnMaxX, mnMaxY), `mvScaleFactors`, optional `mvuRight` and
+        `kp_obs` (Observations() of the map point attached to each keypoint, -1 = none).  → (nmatches, assigned[n])."""
+        kps = np.ascontiguousarray(F["mvKeysUn"], KP_DTYPE); desc = np.ascontiguousarray(F["mDescriptors"], np.uint8).reshape(-1, 32)
+        b = np.ascontiguousarray(F["bounds"], np.float32); sf = np.ascontiguousarray(F["mvScaleFactors"], np.float32)
+        ur = None if F.get("mvuRight") is None else np.ascontiguousarray(F["mvuRight"], np.float32)
+        ko = None if F.get("kp_obs") is None else np.ascontiguousarray(F["kp_obs"], np.int32)
+        p5 = np.ascontiguousarray(mp_proj5, np.float32).reshape(-1, 5); lv = np.ascontiguousarray(mp_level, np.int32)
+        fl = np.ascontiguousarray(mp_flags, np.uint8); ob = np.ascontiguousarray(mp_obs, np.int32)
+        md = np.ascontiguousarray(mp_desc, np.uint8).reshape(-1, 32)
+        assert len(desc) == len(kps) and len(lv) == len(fl) == len(ob) == len(md) == len(p5)
+        out = np.full(len(kps), -1, np.int32)
+        n = C.c_int32(0)
+        self._chk(self.L.orbx_search_by_projection(self.h, _p(kps), _p(desc), len(kps), _p(ur), _p(ko), _p(b), _p(sf), len(sf), _p(p5), _p(lv), _p(fl),
+                                                   _p(ob), _p(md), len(p5), float(self.mfNNratio), float(th), int(bFarPoints), float(thFarPoints),
+                                                   _p(out), C.byref(n)))
+        return n.value, out
+
+    def SearchForInitializationFrames(self, kps1, desc1, kps2, desc2, bounds, vbPrevMatched, windowSize=10):
+        """`ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)` (src/ORBmatcher.cc:644-759), whole
+        function incl. F2's grid query → (nmatches, vnMatches12, vbPrevMatched updated)."""
+        k1 = np.ascontiguousarray(kps1, KP_DTYPE); k2 = np.ascontiguousarray(kps2, KP_DTYPE)
+        d1 = np.ascontiguousarray(desc1, np.uint8).reshape(-1, 32); d2 = np.ascontiguousarray(desc2, np.uint8).reshape(-1, 32)
+        b = np.ascontiguousarray(bounds, np.float32)
+        prev = np.array(vbPrevMatched, np.float32).reshape(-1, 2).copy()
+        assert len(prev) == len(k1) == len(d1) and len(k2) == len(d2)
+        m12 = np.full(len(k1), -1, np.int32)
+        n = C.c_int32(0)
+        self._chk(self.L.orbx_search_for_initialization_frames(self.h, _p(k1), _p(d1), len(k1), _p(k2), _p(d2), len(k2), _p(b), _p(prev), int(windowSize),
+                                                               float(self.mfNNratio), int(self.mbCheckOrientation), _p(m12), C.byref(n)))
+        return n.value, m12, prev
 
     def rot_hist_filter(self, angle_a, angle_b):
         a = np.ascontiguousarray(angle_a, np.float32)

@@ -188,3 +188,89 @@ def vocabulary_queries(voc: dict, n: int, seed: int = 11, flips: int = 60) -> np
         for b in rng.choice(256, size=int(rng.integers(0, flips + 1)), replace=False):
             src[i, b >> 3] ^= np.uint8(1 << (b & 7))
     return src
+
+
+# ---- matcher scenes (SearchForInitialization / SearchByProjection / stereo association) ----
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+
+
+def _flip_bits(rows: np.ndarray, rng: np.random.Generator, max_flips: int) -> np.ndarray:
+    out = rows.copy()
+    for i in range(len(out)):
+        for bit in rng.choice(256, size=int(rng.integers(0, max_flips + 1)), replace=False):
+            out[i, bit >> 3] ^= np.uint8(1 << (bit & 7))
+    return out
+
+
+def keypoint_records(n: int, seed: int, width: float = 640.0, height: float = 480.0, levels: int = 8, integer_frac: float = 0.3,
+                     spill: float = 4.0) -> np.ndarray:
+    """n keypoint records (28-byte cv::KeyPoint layout) scattered over the image (a few outside it, like undistorted keypoints;
+    a fraction on integer / half-cell coordinates so the 64×48 grid's round() sees exact .5 cases)."""
+    rng = np.random.default_rng(seed)
+    k = np.zeros(n, KP_DTYPE)
+    k["x"] = rng.uniform(-spill, width + spill, n).astype(np.float32)
+    k["y"] = rng.uniform(-spill, height + spill, n).astype(np.float32)
+    snap = rng.random(n) < integer_frac
+    k["x"][snap] = np.round(k["x"][snap]); k["y"][snap] = np.round(k["y"][snap])
+    if n > 40:
+        k["x"][:16] = (np.arange(16) * (width / 64) + width / 128).astype(np.float32)      # exactly half a grid cell
+        k["y"][16:32] = (np.arange(16) * (height / 48) + height / 96).astype(np.float32)
+    k["octave"] = rng.choice(levels, n, p=np.array([1.2 ** -i for i in range(levels)]) / sum(1.2 ** -i for i in range(levels)))
+    k["angle"] = rng.uniform(0, 360, n).astype(np.float32)
+    k["size"] = 31.0
+    k["response"] = rng.integers(7, 120, n).astype(np.float32)
+    k["class_id"] = -1
+    return k
+
+
+def init_scene(n1: int, n2: int, seed: int, width: float = 640.0, height: float = 480.0, max_shift: float = 30.0, max_flips: int = 70):
+    """Two frames for SearchForInitialization: frame 2 holds moved, noisy copies of frame-1 keypoints (plus clutter), so windows
+    overlap, train keypoints get locked and stolen, and rotations cluster in a few histogram bins."""
+    rng = np.random.default_rng(seed)
+    k1 = keypoint_records(n1, seed * 7 + 1, width, height)
+    d1 = rng.integers(0, 256, (n1, 32), dtype=np.uint8)
+    k2 = keypoint_records(n2, seed * 7 + 2, width, height)
+    d2 = rng.integers(0, 256, (n2, 32), dtype=np.uint8)
+    src = rng.integers(0, n1, n2) if n1 else np.zeros(n2, np.int64)
+    copy = rng.random(n2) < 0.8 if n1 else np.zeros(n2, bool)
+    k2["x"][copy] = (k1["x"][src[copy]] + rng.uniform(-max_shift, max_shift, copy.sum())).astype(np.float32)
+    k2["y"][copy] = (k1["y"][src[copy]] + rng.uniform(-max_shift, max_shift, copy.sum())).astype(np.float32)
+    k2["octave"][copy] = np.maximum(0, k1["octave"][src[copy]] + rng.integers(-1, 2, copy.sum()))
+    k2["angle"][copy] = ((k1["angle"][src[copy]] - rng.choice([0.0, 2.0, 14.99, 15.0, 31.0, 200.0], copy.sum(), p=[.5, .2, .05, .05, .1, .1])) % 360).astype(np.float32)
+    d2[copy] = _flip_bits(d1[src[copy]], rng, max_flips)
+    if n2 > 8 and n1 > 8:                                                  # identical descriptors next to each other: ties
+        d2[1] = d2[0]; k2["x"][1] = k2["x"][0] + 1; k2["y"][1] = k2["y"][0]
+    return k1, d1, k2, d2
+
+
+def projection_scene(n: int, m: int, seed: int, width: float = 640.0, height: float = 480.0, levels: int = 8, stereo: bool = False):
+    """A frame (n keypoints) and m projected map points for SearchByProjection(Frame&, vector<MapPoint*>&): map points are noisy
+    copies of frame keypoints at the same or the next level (so best / second-best fall on equal and on different levels), several
+    map points compete for the same keypoint, some keypoints already hold a map point with or without observations."""
+    rng = np.random.default_rng(seed)
+    k = keypoint_records(n, seed * 5 + 3, width, height, levels)
+    d = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    if n > 20:                                                             # near-duplicate neighbours: ratio test on / across levels
+        for i in range(0, min(n - 1, 400), 2):
+            k["x"][i + 1] = k["x"][i] + np.float32(rng.uniform(-2, 2)); k["y"][i + 1] = k["y"][i] + np.float32(rng.uniform(-2, 2))
+            k["octave"][i + 1] = k["octave"][i] if rng.random() < 0.5 else min(levels - 1, k["octave"][i] + 1)
+            d[i + 1] = _flip_bits(d[i:i + 1], rng, 12)[0]
+    sf = np.cumprod(np.r_[np.float32(1.0), np.full(levels - 1, np.float32(1.2), np.float32)]).astype(np.float32)
+    src = rng.integers(0, n, m) if n else np.zeros(m, np.int64)
+    p5 = np.zeros((m, 5), np.float32)
+    if n:
+        p5[:, 0] = k["x"][src] + rng.uniform(-3, 3, m); p5[:, 1] = k["y"][src] + rng.uniform(-3, 3, m)
+    p5[:, 3] = rng.choice([0.9999, 0.99, 0.998, 0.5], m).astype(np.float32)
+    p5[:, 4] = rng.uniform(0.5, 80, m)
+    lvl = (np.minimum(levels - 1, k["octave"][src] + rng.integers(0, 2, m)) if n else np.zeros(m)).astype(np.int32)
+    flags = (1 | (2 * (rng.random(m) < 0.03))).astype(np.uint8)
+    flags[rng.random(m) < 0.05] &= 0xFE
+    obs = rng.choice([0, 1, 3, 7], m, p=[.1, .3, .3, .3]).astype(np.int32)
+    md = _flip_bits(d[src], rng, 90) if n else rng.integers(0, 256, (m, 32), dtype=np.uint8)
+    kp_obs = rng.choice([-1, -1, -1, 0, 2], n).astype(np.int32)
+    u_right = None
+    if stereo:
+        u_right = np.where(rng.random(n) < 0.7, k["x"] - rng.uniform(0.5, 40, n), -1.0).astype(np.float32)
+        if n:
+            p5[:, 2] = u_right[src] + rng.choice([0.0, 1.0, 6.0, 30.0], m)
+    return dict(kps=k, desc=d, scale_factors=sf, mp_proj5=p5, mp_level=lvl, mp_flags=flags, mp_obs=obs, mp_desc=md, kp_obs=kp_obs, u_right=u_right)

@@ -1,6 +1,9 @@
 /* ORBmatcher_orbx.h — the Hamming inner loops of the reference's ORBmatcher (src/ORBmatcher.cc) and of
  * Frame::ComputeStereoFishEyeMatches (src/Frame.cc:1060-1100) on the GPU, as a small C++ class over orbx.h.
  *
+ * The reference-named class ORB_SLAM3::ORBmatcher (constructor, DescriptorDistance(cv::Mat, cv::Mat), SearchForInitialization,
+ * SearchByProjection over Frame / MapPoint) is include/ORBmatcher.h; this header holds the array-level building blocks.
+ *
  * Scope (SURVEY.md §8a rows a11–a15): DescriptorDistance, best/second-best search over candidate lists,
  * ratio tests, the rotation-histogram filter and the brute-force k=2 kNN.  The eleven SearchBy… and Fuse entry
  * points keep their projection geometry in the reference's src/ORBmatcher.cc (out of scope: pointer-chasing
@@ -50,11 +53,12 @@ public:
     // best / second-best distances over per-query candidate lists (the loops at :84-140, :273-325, :812-864).
     bool Top2OverCandidates(const unsigned char* query, int nq, const unsigned char* train, long long ntrain,
                             const std::vector<int>& cand, const std::vector<int>& candOffsets,
-                            std::vector<int>& bestIdx, std::vector<int>& bestDist, std::vector<int>& secondDist)
+                            std::vector<int>& bestIdx, std::vector<int>& bestDist, std::vector<int>& secondIdx, std::vector<int>& secondDist)
     {
-        bestIdx.assign(nq, -1); bestDist.assign(nq, 256); secondDist.assign(nq, 256);
+        // secondIdx → the keypoint whose octave is bestLevel2 in the level-aware ratio rule (:101-128)
+        bestIdx.assign(nq, -1); bestDist.assign(nq, 256); secondIdx.assign(nq, -1); secondDist.assign(nq, 256);
         return orbx_hamming_top2_lists(Ctx(), query, nq, train, ntrain, cand.data(), candOffsets.data(),
-                                       bestIdx.data(), bestDist.data(), secondDist.data()) == ORBX_OK;
+                                       bestIdx.data(), bestDist.data(), secondIdx.data(), secondDist.data()) == ORBX_OK;
     }
 
     // Rotation-consistency filter (:345-352 + ComputeThreeMaxima :2008-2049): keep[i]=0 for matches to drop.

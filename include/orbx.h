@@ -143,12 +143,31 @@ int orbx_knn2_merge_device(orbx_matcher *m, const int32_t *d_idx_all, const int3
 int orbx_ratio_test(orbx_matcher *m, const int32_t *dist, int nq, double ratio, uint8_t *keep);
 int orbx_ratio_test_device(orbx_matcher *m, const int32_t *d_dist, int nq, double ratio, uint8_t *d_keep);
 
-/* Best / second-best over explicit candidate lists (the a12 loops): query i is compared with train
- * rows cand[cand_off[i] .. cand_off[i+1]); strict '<' (first candidate wins ties); defaults 256.
- * HOST buffers. */
+/* Best / second-best over explicit candidate lists (the a12 loops, src/ORBmatcher.cc:84-121 and its siblings): query i is
+ * compared with train rows cand[cand_off[i] .. cand_off[i+1]); strict '<' (first candidate wins ties); the loop starts from
+ * 256 / 256 like the reference, so best_dist / second_dist default to 256 and a distance of 256 is never recorded.
+ * second_idx (may be NULL) is the train row of the second best (-1: none) — the keypoint whose octave the reference keeps as
+ * bestLevel2 for the level-aware ratio rule of :123-128.  HOST buffers. */
 int orbx_hamming_top2_lists(orbx_matcher *m, const uint8_t *query, int nq, const uint8_t *train, int64_t ndb,
-                            const int32_t *cand, const int32_t *cand_off, int32_t *best_idx,
-                            int32_t *best_dist, int32_t *second_dist);
+                            const int32_t *cand, const int32_t *cand_off, int32_t *best_idx, int32_t *best_dist,
+                            int32_t *second_idx, int32_t *second_dist);
+/* ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, th, bFarPoints, thFarPoints)
+ * (src/ORBmatcher.cc:43-213) for frames with Nleft == -1 (monocular, rectified stereo, RGB-D), whole function: the window
+ * query F.GetFeaturesInArea(projX, projY, r·scale[level], level-1, level), the occupied-keypoint and right-image skips
+ * (:88-97), the level-aware best / second-best loop and ratio rule (:101-128), and the in-order attachment of map points to
+ * keypoints (later map points see earlier attachments).
+ *   frame:      keypoints_un = F.mvKeysUn (n records), descriptors n×32, u_right = F.mvuRight (NULL: all -1), kp_obs[i] =
+ *               F.mvpMapPoints[i]->Observations(), -1 for a null pointer (NULL: all -1), bounds4 = mnMinX, mnMinY, mnMaxX,
+ *               mnMaxY, scale_factors = F.mvScaleFactors (n_levels entries)
+ *   map points: mp_proj5 = n_mp × {mTrackProjX, mTrackProjY, mTrackProjXR, mTrackViewCos, mTrackDepth}, mp_level =
+ *               mnTrackScaleLevel, mp_flags bit 0 = mbTrackInView, bit 1 = isBad(), mp_obs = Observations(), mp_desc =
+ *               GetDescriptor() rows
+ *   out:        assigned[i] = index of the map point the call wrote into F.mvpMapPoints[i], or -1; *n_matches = return value
+ * HOST buffers. */
+int orbx_search_by_projection(orbx_matcher *m, const orbx_keypoint *keypoints_un, const uint8_t *descriptors, int n, const float *u_right,
+                              const int32_t *kp_obs, const float *bounds4, const float *scale_factors, int n_levels, const float *mp_proj5,
+                              const int32_t *mp_level, const uint8_t *mp_flags, const int32_t *mp_obs, const uint8_t *mp_desc, int n_mp,
+                              float nnratio, float th, int far_points, float th_far, int32_t *assigned, int32_t *n_matches);
 /* Rotation-consistency filter: bin = round((a-b [+360]) / 30) (quirk Q10), keep matches in the three
  * fullest bins subject to the 0.1·max rule.  HOST / DEVICE buffers; n matches. */
 int orbx_rot_hist_filter(orbx_matcher *m, const float *angle_a, const float *angle_b, int n, uint8_t *keep);
@@ -162,6 +181,13 @@ int orbx_search_for_initialization(orbx_matcher *m, const uint8_t *desc1, const 
                                    int n1, const uint8_t *desc2, const float *angle2, int n2, const int32_t *cand,
                                    const int32_t *cand_off, float nnratio, int check_orientation, int32_t *matches12,
                                    int32_t *n_matches);
+/* ORBmatcher::SearchForInitialization(Frame &F1, Frame &F2, vbPrevMatched, vnMatches12, windowSize) (src/ORBmatcher.cc:644-759),
+ * whole function: F2's 64×48 grid, the window query per level-0 keypoint of F1, the ordered replay above and the vbPrevMatched
+ * update of :754-756.  kps1 / kps2 = mvKeysUn of both frames, bounds4 = mnMinX, mnMinY, mnMaxX, mnMaxY, prev_matched_xy =
+ * vbPrevMatched (n1×2, updated in place).  HOST buffers. */
+int orbx_search_for_initialization_frames(orbx_matcher *m, const orbx_keypoint *kps1, const uint8_t *desc1, int n1, const orbx_keypoint *kps2,
+                                          const uint8_t *desc2, int n2, const float *bounds4, float *prev_matched_xy, int window_size,
+                                          float nnratio, int check_orientation, int32_t *matches12, int32_t *n_matches);
 /* Frame::AssignFeaturesToGrid + Frame::GetFeaturesInArea (src/Frame.cc:387-418, :659-738; 64×48 grid,
  * include/Frame.h:52-53) for a batch of queries: keypoints_xy = n×{x,y} (mvKeysUn), octave[n], image bounds
  * (mnMinX, mnMinY, mnMaxX, mnMaxY), queries = nq×{x, y, r}.  cand_off[nq+1] and cand[*total_out] are the

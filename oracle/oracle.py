@@ -62,7 +62,10 @@ def lib() -> C.CDLL:
         L.orc_descriptor_distance.argtypes = [vp, vp]
         L.orc_knn2.argtypes = [vp, i32, vp, C.c_int64, vp, vp, i32]
         L.orc_ratio_test.argtypes = [vp, i32, C.c_double, vp]
-        L.orc_top2_lists.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
+        L.orc_top2_lists.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
+        L.orc_search_by_projection.restype = i32
+        L.orc_search_by_projection.argtypes = [vp, vp, vp, i32, vp, vp, f32, f32, f32, f32, vp, vp, vp, vp, vp, vp, i32, f32, f32, i32, f32, vp]
+        L.orc_three_maxima.argtypes = [vp, i32, vp]
         L.orc_rot_hist_filter.argtypes = [vp, vp, i32, vp]
         L.orc_features_in_area.restype = i32
         L.orc_features_in_area.argtypes = [vp, vp, i32, f32, f32, f32, f32, vp, i32, i32, i32, vp, vp, i32]
@@ -203,9 +206,33 @@ def sort_nodes(sizes, ulx):
 def top2_lists(q, db, cand, off):
     q = np.ascontiguousarray(q, np.uint8); db = np.ascontiguousarray(db, np.uint8)
     cand = np.ascontiguousarray(cand, np.int32); off = np.ascontiguousarray(off, np.int32)
-    bi, bd, sd = (np.zeros(len(q), np.int32) for _ in range(3))
-    lib().orc_top2_lists(_p(q), len(q), _p(db), _p(cand), _p(off), _p(bi), _p(bd), _p(sd))
-    return bi, bd, sd
+    bi, bd, si, sd = (np.zeros(len(q), np.int32) for _ in range(4))
+    lib().orc_top2_lists(_p(q), len(q), _p(db), _p(cand), _p(off), _p(bi), _p(bd), _p(si), _p(sd))
+    return bi, bd, si, sd
+
+
+def search_by_projection(xy, octave, desc, bounds, scale_factors, mp_proj5, mp_level, mp_flags, mp_obs, mp_desc, nnratio=0.8, th=3.0,
+                         far_points=False, th_far=50.0, u_right=None, kp_obs=None):
+    """ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, …), Nleft == -1.  bounds = (minX, minY, maxX, maxY).
+    Returns (nmatches, assigned[n])."""
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2); octave = np.ascontiguousarray(octave, np.int32)
+    desc = np.ascontiguousarray(desc, np.uint8); sf = np.ascontiguousarray(scale_factors, np.float32)
+    p5 = np.ascontiguousarray(mp_proj5, np.float32).reshape(-1, 5); lv = np.ascontiguousarray(mp_level, np.int32)
+    fl = np.ascontiguousarray(mp_flags, np.uint8); ob = np.ascontiguousarray(mp_obs, np.int32); md = np.ascontiguousarray(mp_desc, np.uint8)
+    ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+    ko = None if kp_obs is None else np.ascontiguousarray(kp_obs, np.int32)
+    out = np.zeros(len(xy), np.int32)
+    n = lib().orc_search_by_projection(_p(xy), _p(octave), _p(desc), len(xy), None if ur is None else _p(ur), None if ko is None else _p(ko),
+                                       *[float(b) for b in bounds], _p(sf), _p(p5), _p(lv), _p(fl), _p(ob), _p(md), len(p5), float(nnratio),
+                                       float(th), int(far_points), float(th_far), _p(out))
+    return n, out
+
+
+def three_maxima(counts):
+    counts = np.ascontiguousarray(counts, np.int32)
+    ind = np.zeros(3, np.int32)
+    lib().orc_three_maxima(_p(counts), len(counts), _p(ind))
+    return tuple(int(v) for v in ind)
 
 
 def rot_hist_filter(a, b):

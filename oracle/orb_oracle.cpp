@@ -734,16 +734,19 @@ void orc_ratio_test(const int32_t *dist, int nq, double ratio, uint8_t *keep) {
 
 void orc_top2_lists(const uint8_t *q, int nq, const uint8_t *db, const int32_t *cand,
                     const int32_t *cand_off, int32_t *best_idx, int32_t *best_dist,
-                    int32_t *second_dist) {
-    // ORBmatcher.cc:84-140 shape: strict '<' so the first candidate wins ties; INT default 256
+                    int32_t *second_idx, int32_t *second_dist) {
+    // ORBmatcher.cc:84-121 shape: strict '<' so the first candidate wins ties; defaults 256 (a distance of 256
+    // can therefore never be recorded).  second_idx is the candidate whose octave the reference keeps as
+    // bestLevel2 (:110, :117); -1 when no second candidate was recorded.
     for (int i = 0; i < nq; ++i) {
-        int b = 256, s = 256, bi = -1;
+        int b = 256, s = 256, bi = -1, si = -1;
         for (int c = cand_off[i]; c < cand_off[i + 1]; ++c) {
             const int d = orc_descriptor_distance(q + (size_t)i * 32, db + (size_t)cand[c] * 32);
-            if (d < b) { s = b; b = d; bi = cand[c]; }
-            else if (d < s) s = d;
+            if (d < b) { s = b; si = bi; b = d; bi = cand[c]; }
+            else if (d < s) { s = d; si = cand[c]; }
         }
         best_idx[i] = bi; best_dist[i] = b; second_dist[i] = s;
+        if (second_idx) second_idx[i] = si;
     }
 }
 
@@ -758,6 +761,14 @@ static void three_maxima(const std::vector<int> *h, int L, int &i1, int &i2, int
     }
     if (m2 < 0.1f * (float)m1) { i2 = -1; i3 = -1; }
     else if (m3 < 0.1f * (float)m1) { i3 = -1; }
+}
+
+void orc_three_maxima(const int32_t *counts, int L, int32_t *ind) {
+    std::vector<std::vector<int>> h(L);
+    for (int i = 0; i < L; ++i) h[i].assign(counts[i], 0);
+    int a = -1, b = -1, c = -1;
+    three_maxima(h.data(), L, a, b, c);
+    ind[0] = a; ind[1] = b; ind[2] = c;
 }
 
 static inline int rot_bin(float a, float b) {
@@ -859,6 +870,55 @@ int orc_features_in_area(const float *xy, const int32_t *octave, int n, float mi
         cand_off[q + 1] = total;
     }
     return total;
+}
+
+// ---- ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th, bFarPoints, thFarPoints) (src/ORBmatcher.cc:43-213),
+// frames with Nleft == -1 (monocular, rectified stereo, RGB-D) ----
+// Frame: xy = mvKeysUn[i].pt, octave, 32-byte descriptors, u_right = mvuRight (NULL: all -1), kp_obs[i] = Observations() of the
+// map point already attached to keypoint i (-1: null pointer; NULL: all -1).  Map points (m rows, processed in order):
+// proj5 = {mTrackProjX, mTrackProjY, mTrackProjXR, mTrackViewCos, mTrackDepth}, level = mnTrackScaleLevel, flags bit0 =
+// mbTrackInView, bit1 = isBad(), n_obs = Observations().  assigned[i] = map point written into mvpMapPoints[i], or -1.
+int orc_search_by_projection(const float *xy, const int32_t *octave, const uint8_t *desc, int n, const float *u_right, const int32_t *kp_obs,
+                             float minX, float minY, float maxX, float maxY, const float *scale_factors, const float *mp_proj5,
+                             const int32_t *mp_level, const uint8_t *mp_flags, const int32_t *mp_obs, const uint8_t *mp_desc, int m,
+                             float nnratio, float th, int far_points, float th_far, int32_t *assigned) {
+    int nmatches = 0;
+    std::vector<int> obs(n, -1);
+    if (kp_obs) obs.assign(kp_obs, kp_obs + n);
+    for (int i = 0; i < n; ++i) assigned[i] = -1;
+    const bool bFactor = th != 1.0;                                            // :47
+    std::vector<int32_t> off(2), cand(std::max(n, 1));
+    for (int j = 0; j < m; ++j) {
+        if (!(mp_flags[j] & 1)) continue;                                      // :52 (mbTrackInViewR is false when Nleft == -1)
+        if (far_points && mp_proj5[5 * j + 4] > th_far) continue;              // :55
+        if (mp_flags[j] & 2) continue;                                         // :58
+        const int lvl = mp_level[j];
+        float r = (mp_proj5[5 * j + 3] > 0.998) ? 2.5f : 4.0f;                 // :215-221 (float against the double literal)
+        if (bFactor) r *= th;                                                  // :68-69
+        const float q[3] = {mp_proj5[5 * j], mp_proj5[5 * j + 1], r * scale_factors[lvl]};
+        const int total = orc_features_in_area(xy, octave, n, minX, minY, maxX, maxY, q, 1, lvl - 1, lvl, off.data(), cand.data(), n);
+        if (total == 0) continue;                                              // :74
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int c = 0; c < total; ++c) {
+            const int idx = cand[c];
+            if (obs[idx] > 0) continue;                                        // :88-90
+            if (u_right && u_right[idx] > 0) {                                 // :92-97
+                const float er = std::fabs(mp_proj5[5 * j + 2] - u_right[idx]);
+                if (er > r * scale_factors[lvl]) continue;
+            }
+            const int dist = orc_descriptor_distance(mp_desc + (size_t)j * 32, desc + (size_t)idx * 32);
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = octave[idx]; bestIdx = idx; }
+            else if (dist < bestDist2) { bestLevel2 = octave[idx]; bestDist2 = dist; }
+        }
+        if (bestDist <= 100) {                                                 // :124 TH_HIGH
+            if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
+            if (bestLevel != bestLevel2 || bestDist <= nnratio * bestDist2) {
+                assigned[bestIdx] = j; obs[bestIdx] = mp_obs[j];               // :130: mvpMapPoints[bestIdx] = pMP
+                ++nmatches;
+            }
+        }
+    }
+    return nmatches;
 }
 
 // ---- stereo association tail (src/Frame.cc:862-914) fed by the Hamming kNN + Lowe ratio of :1078-1085 ----

@@ -74,8 +74,9 @@ void orc_ratio_test(const int32_t *dist, int nq, double ratio, uint8_t *keep);
 /* top-2 over explicit candidate lists (ORBmatcher.cc:84-140 style): best, second distance, best idx */
 void orc_top2_lists(const uint8_t *q, int nq, const uint8_t *db, const int32_t *cand,
                     const int32_t *cand_off, int32_t *best_idx, int32_t *best_dist,
-                    int32_t *second_dist);
+                    int32_t *second_idx /* may be NULL */, int32_t *second_dist);
 /* rotation histogram + ComputeThreeMaxima filter (ORBmatcher.cc:345-352, :2008-2049, :725-748) */
+void orc_three_maxima(const int32_t *counts, int L, int32_t *ind3); /* ORBmatcher.cc:2008-2049 on list sizes */
 void orc_rot_hist_filter(const float *angle_a, const float *angle_b, int n, uint8_t *keep);
 /* SearchForInitialization core (ORBmatcher.cc:644-759) with explicit candidate lists. */
 int orc_search_init(const uint8_t *d1, const float *ang1, const int32_t *oct1, int n1,
@@ -86,6 +87,11 @@ int orc_search_init(const uint8_t *d1, const float *ang1, const int32_t *oct1, i
 int orc_features_in_area(const float *xy, const int32_t *octave, int n, float minX, float minY, float maxX, float maxY,
                          const float *queries, int nq, int minLevel, int maxLevel, int32_t *cand_off, int32_t *cand, int cap);
 /* stereo association tail (src/Frame.cc:862-914) over kNN+ratio matches; returns number of stereo points kept */
+/* SearchByProjection(Frame&, vector<MapPoint*>&, …) for Nleft == -1 frames (ORBmatcher.cc:43-213) */
+int orc_search_by_projection(const float *xy, const int32_t *octave, const uint8_t *desc, int n, const float *u_right, const int32_t *kp_obs,
+                             float minX, float minY, float maxX, float maxY, const float *scale_factors, const float *mp_proj5,
+                             const int32_t *mp_level, const uint8_t *mp_flags, const int32_t *mp_obs, const uint8_t *mp_desc, int m,
+                             float nnratio, float th, int far_points, float th_far, int32_t *assigned);
 int orc_stereo_tail(const float *uL, const float *uR, int nL, int nR, const int32_t *idx, const int32_t *dist,
                     const uint8_t *keep, float mbf, float mb, float *uRight, float *depth);
 

@@ -138,3 +138,105 @@ class Vocabulary:
         ids1 = np.ascontiguousarray(ids1, np.uint32); ids2 = np.ascontiguousarray(ids2, np.uint32)
         v1 = np.ascontiguousarray(v1, np.float64); v2 = np.ascontiguousarray(v2, np.float64)
         return self.L.ref_bow_score(self.h, _p(ids1), _p(v1), len(ids1), _p(ids2), _p(v2), len(ids2))
+
+
+# ---- the reference's own matcher / Frame-grid functions, by line range (oracle/_ref/libref_match.so) ----
+SO_MATCH = os.path.join(_here, "_ref", "libref_match.so")
+_lib_match = None
+
+
+def match_available() -> bool:
+    return os.path.exists(SO_MATCH)
+
+
+def lib_match():
+    global _lib_match
+    if _lib_match is None:
+        _build_oracle()
+        L = C.CDLL(SO_MATCH)
+        vp, i32, f32 = C.c_void_p, C.c_int, C.c_float
+        L.refm_constants.argtypes = [vp, vp, vp]
+        L.refm_descriptor_distance.restype = i32
+        L.refm_descriptor_distance.argtypes = [vp, vp]
+        L.refm_three_maxima.argtypes = [vp, i32, vp]
+        L.refm_features_in_area.restype = i32
+        L.refm_features_in_area.argtypes = [vp, i32, vp, vp, i32, i32, i32, vp, vp, i32]
+        L.refm_search_init.restype = i32
+        L.refm_search_init.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp, i32, f32, i32, vp]
+        L.refm_search_by_projection.restype = i32
+        L.refm_search_by_projection.argtypes = [vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, f32, f32, i32, f32, vp]
+        L.refm_stereo_tail.restype = i32
+        L.refm_stereo_tail.argtypes = [vp, i32, vp, i32, vp, vp, vp, i32, f32, f32, vp, vp]
+        _lib_match = L
+    return _lib_match
+
+
+def _kps(kps):
+    kps = np.ascontiguousarray(kps)
+    assert kps.dtype == KP_DTYPE
+    return kps
+
+
+def _bounds(bounds):
+    return np.ascontiguousarray(bounds, np.float32)          # (minX, minY, maxX, maxY)
+
+
+def match_constants():
+    a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+    lib_match().refm_constants(C.byref(a), C.byref(b), C.byref(c))
+    return dict(TH_LOW=a.value, TH_HIGH=b.value, HISTO_LENGTH=c.value)
+
+
+def descriptor_distance(a, b):
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return lib_match().refm_descriptor_distance(_p(a), _p(b))
+
+
+def three_maxima(counts):
+    counts = np.ascontiguousarray(counts, np.int32)
+    ind = np.zeros(3, np.int32)
+    lib_match().refm_three_maxima(_p(counts), len(counts), _p(ind))
+    return tuple(int(v) for v in ind)
+
+
+def features_in_area(kps, bounds, queries, min_level=-1, max_level=-1):
+    kps = _kps(kps); b = _bounds(bounds)
+    q = np.ascontiguousarray(queries, np.float32).reshape(-1, 3)
+    off = np.zeros(len(q) + 1, np.int32)
+    total = lib_match().refm_features_in_area(_p(kps), len(kps), _p(b), _p(q), len(q), min_level, max_level, _p(off), None, 0)
+    cand = np.zeros(max(total, 1), np.int32)
+    lib_match().refm_features_in_area(_p(kps), len(kps), _p(b), _p(q), len(q), min_level, max_level, _p(off), _p(cand), total)
+    return off, cand[:total]
+
+
+def search_for_initialization(kps1, desc1, kps2, desc2, bounds, prev_xy, window=100, nnratio=0.9, check_ori=True):
+    kps1 = _kps(kps1); kps2 = _kps(kps2); b = _bounds(bounds)
+    d1 = np.ascontiguousarray(desc1, np.uint8); d2 = np.ascontiguousarray(desc2, np.uint8)
+    prev = np.array(prev_xy, np.float32).reshape(-1, 2).copy()
+    m12 = np.zeros(len(kps1), np.int32)
+    n = lib_match().refm_search_init(_p(kps1), _p(d1), len(kps1), _p(kps2), _p(d2), len(kps2), _p(b), _p(prev), int(window), float(nnratio),
+                                     int(check_ori), _p(m12))
+    return n, m12, prev
+
+
+def search_by_projection(kps, desc, bounds, scale_factors, mp_proj5, mp_level, mp_flags, mp_obs, mp_desc, nnratio=0.8, th=3.0, far_points=False,
+                         th_far=50.0, u_right=None, kp_obs=None):
+    kps = _kps(kps); b = _bounds(bounds); desc = np.ascontiguousarray(desc, np.uint8)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    p5 = np.ascontiguousarray(mp_proj5, np.float32).reshape(-1, 5); lv = np.ascontiguousarray(mp_level, np.int32)
+    fl = np.ascontiguousarray(mp_flags, np.uint8); ob = np.ascontiguousarray(mp_obs, np.int32); md = np.ascontiguousarray(mp_desc, np.uint8)
+    ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+    ko = np.full(len(kps), -1, np.int32) if kp_obs is None else np.ascontiguousarray(kp_obs, np.int32)
+    out = np.zeros(len(kps), np.int32)
+    n = lib_match().refm_search_by_projection(_p(kps), _p(desc), len(kps), None if ur is None else _p(ur), _p(ko), _p(b), _p(sf), len(sf), _p(p5),
+                                              _p(lv), _p(fl), _p(ob), _p(md), len(p5), float(nnratio), float(th), int(far_points), float(th_far),
+                                              _p(out))
+    return n, out
+
+
+def stereo_tail(u_left, u_right, iL, iR, match_distance, mbf, mb):
+    uL = np.ascontiguousarray(u_left, np.float32); uR = np.ascontiguousarray(u_right, np.float32)
+    iL = np.ascontiguousarray(iL, np.int32); iR = np.ascontiguousarray(iR, np.int32); md = np.ascontiguousarray(match_distance, np.float32)
+    ur = np.zeros(len(uL), np.float32); dp = np.zeros(len(uL), np.float32)
+    n = lib_match().refm_stereo_tail(_p(uL), len(uL), _p(uR), len(uR), _p(iL), _p(iR), _p(md), len(iL), float(mbf), float(mb), _p(ur), _p(dp))
+    return n, ur, dp

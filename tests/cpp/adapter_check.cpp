@@ -3,14 +3,19 @@
 // result with the reference's own ORBextractor.cc (oracle/_ref) when that library is linked in.
 // With a 4th argument (a vocabulary in the ORBvoc text format) it also runs include/ORBVocabulary_orbx.h like
 // Frame::ComputeBoW (src/Frame.cc:739-747) and compares with the reference's own DBoW2 (oracle/_ref/libref_bow.so).
+// It then fills two Frames from two extractions and calls ORB_SLAM3::ORBmatcher::SearchForInitialization / SearchByProjection of the
+// drop-in include/ORBmatcher.h like src/Tracking.cc:2512 and :3447 do, comparing with the reference's own function bodies
+// (oracle/_ref/libref_match.so, WITH_REF_MATCH).
 // Usage: adapter_check <width> <height> <seed> [vocabulary.txt]   (prints "OK n mono" or a diagnostic; exit code 0/1)
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <vector>
 
 #include "ORBextractor.h"
+#include "ORBmatcher.h"        // the drop-in class (reference signatures), compiled with -DORBX_MATCHER_HOT_PATH_ONLY against tests/cpp/shim/Frame.h
 #include "ORBmatcher_orbx.h"
 #include "ORBVocabulary_orbx.h"
 
@@ -18,6 +23,11 @@ extern "C" {
 void *ref_create(int, float, int, int, int);
 void ref_destroy(void *);
 int ref_extract(void *, const uint8_t *, int, int, size_t, const int32_t *, int, int, int, orc_keypoint *, uint8_t *, int, int *, int *);
+#ifdef WITH_REF_MATCH
+int refm_search_init(const orc_keypoint *, const uint8_t *, int, const orc_keypoint *, const uint8_t *, int, const float *, float *, int, float, int, int32_t *);
+int refm_search_by_projection(const orc_keypoint *, const uint8_t *, int, const float *, const int32_t *, const float *, const float *, int, const float *,
+                              const int32_t *, const uint8_t *, const int32_t *, const uint8_t *, int, float, float, int, float, int32_t *);
+#endif
 #ifdef WITH_REF_BOW
 void *ref_vocab_load_text(const char *);
 void ref_vocab_free(void *);
@@ -65,6 +75,77 @@ int main(int argc, char **argv) {
     for (int i = 0; i < rn; ++i)
         if (dist[2 * i] != 0) { printf("FAIL self match %d\n", i); return 1; }
     if (ORB_SLAM3::ORBmatcherDevice::DescriptorDistance(desc.ptr(0), desc.ptr(0)) != 0) { printf("FAIL distance\n"); return 1; }
+    // ---- the drop-in ORBmatcher on two Frames: frame 2 = the same scene moved by (7, 3) pixels ----
+    {
+        cv::Mat img2(H, W, CV_8UC1);
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) img2.at<uchar>(y, x) = img.at<uchar>(std::min(H - 1, std::max(0, y - 3)), std::min(W - 1, std::max(0, x - 7)));
+        ORB_SLAM3::ORBextractor ex2(1000, 1.2f, 8, 20, 7);
+        std::vector<cv::KeyPoint> keys2;
+        cv::Mat desc2;
+        std::vector<int> lap0 = {0, 0};
+        if (ex2(img2, mask, keys2, desc2, lap0) < 0) { printf("FAIL second extraction\n"); return 1; }
+        ORB_SLAM3::Frame F1, F2;
+        ORB_SLAM3::Frame *Fs[2] = {&F1, &F2};
+        for (int f = 0; f < 2; ++f) {
+            ORB_SLAM3::Frame &F = *Fs[f];
+            F.mvKeysUn = f == 0 ? keys : keys2; F.mvKeys = F.mvKeysUn;
+            F.N = (int)F.mvKeysUn.size();
+            F.mDescriptors = f == 0 ? desc : desc2;
+            F.mvpMapPoints.assign(F.N, nullptr);
+            F.mvuRight.assign(F.N, -1.0f);
+            F.mnMinX = 0; F.mnMinY = 0; F.mnMaxX = (float)W; F.mnMaxY = (float)H;
+            F.mvScaleFactors = ex.GetScaleFactors();
+        }
+        const float bounds[4] = {0, 0, (float)W, (float)H};
+        (void)bounds;
+        std::vector<cv::Point2f> prev(F1.N);
+        for (int i = 0; i < F1.N; ++i) prev[i] = F1.mvKeysUn[i].pt;
+        std::vector<cv::Point2f> prevRef = prev;
+        std::vector<int> m12;
+        ORB_SLAM3::ORBmatcher matcher(0.9f, true);                       // src/Tracking.cc:2511
+        const int nm = matcher.SearchForInitialization(F1, F2, prev, m12, 100);
+        if (nm < 20) { printf("FAIL SearchForInitialization found %d matches\n", nm); return 1; }
+        if (ORB_SLAM3::ORBmatcher::DescriptorDistance(desc.row(0), desc.row(0)) != 0 || ORB_SLAM3::ORBmatcher::TH_LOW != 50) { printf("FAIL matcher statics\n"); return 1; }
+#ifdef WITH_REF_MATCH
+        std::vector<int32_t> rm12(F1.N);
+        const int rnm = refm_search_init((const orc_keypoint *)F1.mvKeysUn.data(), desc.ptr(0), F1.N, (const orc_keypoint *)F2.mvKeysUn.data(), desc2.ptr(0), F2.N,
+                                         bounds, (float *)prevRef.data(), 100, 0.9f, 1, rm12.data());
+        if (rnm != nm || memcmp(rm12.data(), m12.data(), (size_t)F1.N * 4) != 0 || memcmp(prevRef.data(), prev.data(), (size_t)F1.N * 8) != 0) {
+            printf("FAIL SearchForInitialization differs from the reference (%d vs %d)\n", nm, rnm); return 1;
+        }
+#endif
+        // map points = frame-2 keypoints projected into frame 1 (two per keypoint region so that keypoints are contested)
+        const int M = F2.N;
+        std::vector<ORB_SLAM3::MapPoint> mps(M);
+        std::vector<ORB_SLAM3::MapPoint *> vp(M);
+        std::vector<float> p5(5 * (size_t)M);
+        std::vector<int32_t> lvl(M), obs(M), kpObs(F1.N, -1);
+        std::vector<uint8_t> flg(M);
+        for (int j = 0; j < M; ++j) {
+            ORB_SLAM3::MapPoint &p = mps[j];
+            p.mTrackProjX = F2.mvKeysUn[j].pt.x - 7 + (j % 3) - 1; p.mTrackProjY = F2.mvKeysUn[j].pt.y - 3; p.mTrackProjXR = -1;
+            p.mTrackViewCos = (j % 4) ? 0.9995f : 0.9f; p.mTrackDepth = 10.f + j % 50;
+            p.mnTrackScaleLevel = F2.mvKeysUn[j].octave; p.mbTrackInView = (j % 17) != 0; p.bad = (j % 29) == 0; p.nObs = j % 3;
+            p.desc = desc2.row(j);
+            vp[j] = &p;
+            p5[5 * j] = p.mTrackProjX; p5[5 * j + 1] = p.mTrackProjY; p5[5 * j + 2] = p.mTrackProjXR; p5[5 * j + 3] = p.mTrackViewCos; p5[5 * j + 4] = p.mTrackDepth;
+            lvl[j] = p.mnTrackScaleLevel; obs[j] = p.nObs; flg[j] = (uint8_t)((p.mbTrackInView ? 1 : 0) | (p.bad ? 2 : 0));
+        }
+        ORB_SLAM3::ORBmatcher tracker(0.8f);                             // src/Tracking.cc:3447
+        const int np = tracker.SearchByProjection(F1, vp, 3, true, 40.0f);
+        if (np < 20) { printf("FAIL SearchByProjection found %d matches\n", np); return 1; }
+#ifdef WITH_REF_MATCH
+        std::vector<int32_t> asg(F1.N);
+        const int rnp = refm_search_by_projection((const orc_keypoint *)F1.mvKeysUn.data(), desc.ptr(0), F1.N, nullptr, kpObs.data(), bounds, F1.mvScaleFactors.data(),
+                                                  (int)F1.mvScaleFactors.size(), p5.data(), lvl.data(), flg.data(), obs.data(), desc2.ptr(0), M, 0.8f, 3.f, 1, 40.0f, asg.data());
+        if (rnp != np) { printf("FAIL SearchByProjection count %d vs reference %d\n", np, rnp); return 1; }
+        for (int i = 0; i < F1.N; ++i) {
+            const int got = F1.mvpMapPoints[i] ? (int)(F1.mvpMapPoints[i] - mps.data()) : -1;
+            if (got != asg[i]) { printf("FAIL SearchByProjection keypoint %d: map point %d vs reference %d\n", i, got, asg[i]); return 1; }
+        }
+#endif
+    }
     // vocabulary: BowVector / FeatureVector of the extracted descriptors, levelsup 4 as in Frame::ComputeBoW
     if (argc > 4) {
         typedef std::map<unsigned int, double> BowVector;                         // DBoW2::BowVector's base

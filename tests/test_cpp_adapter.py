@@ -10,7 +10,8 @@ import pytest
 from conftest import ROOT
 
 SRC = os.path.join(ROOT, "tests", "cpp", "adapter_check.cpp")
-INC = ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle", "shim")]
+INC = ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle", "shim"), "-I" + os.path.join(ROOT, "tests", "cpp", "shim"),
+       "-DORBX_MATCHER_HOT_PATH_ONLY"]      # the out-of-scope ORBmatcher members need the reference's KeyFrame / Sophus headers
 
 
 def test_adapters_compile_against_the_opencv_shim():
@@ -25,8 +26,10 @@ def test_cpp_adapter_matches_reference_source(tmp_path, orbx_mod):
     exe = str(tmp_path / "adapter_check")
     libdirs = [os.path.join(ROOT, "dani_slam_b200"), ref_dir, os.path.join(ROOT, "oracle")]
     with_bow = os.path.exists(os.path.join(ref_dir, "libref_bow.so"))
-    subprocess.check_call(["g++", "-std=c++17", "-O2"] + (["-DWITH_REF_BOW"] if with_bow else []) + INC + [SRC, "-o", exe] +
-                          ["-L" + d for d in libdirs] + ["-lorbx", "-lref_orb"] + (["-lref_bow"] if with_bow else []) +
+    with_match = os.path.exists(os.path.join(ref_dir, "libref_match.so"))
+    subprocess.check_call(["g++", "-std=c++17", "-O2"] + (["-DWITH_REF_BOW"] if with_bow else []) + (["-DWITH_REF_MATCH"] if with_match else []) + INC +
+                          [SRC, "-o", exe] + ["-L" + d for d in libdirs] + ["-lorbx", "-lref_orb"] + (["-lref_bow"] if with_bow else []) +
+                          (["-lref_match"] if with_match else []) +
                           ["-lorb_oracle", "-Wl,-rpath," + ":".join(libdirs)])
     from dani_slam_b200 import synth
     voc_path = str(tmp_path / "voc.txt")

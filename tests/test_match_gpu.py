@@ -78,12 +78,32 @@ def test_top2_lists_vs_oracle(orbx_mod, oracle_mod):
     q, db = synth.knn_case(400, 3000, seed=8, planted_frac=0.5)
     lens = rng.integers(0, 60, 400)
     lens[:5] = 0
+    lens[7] = max(lens[7], 3)
     off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
     cand = rng.integers(0, 3000, off[-1]).astype(np.int32)
-    bi, bd, sd = orbx_mod.ORBmatcher().top2_lists(q, db, cand, off)
-    rbi, rbd, rsd = oracle_mod.top2_lists(q, db, cand, off)
-    assert np.array_equal(bi, rbi) and np.array_equal(bd, rbd) and np.array_equal(sd, rsd)
-    assert (bi[:5] == -1).all() and (bd[:5] == 256).all()
+    q[7] = ~db[cand[off[7]]]                                               # a distance of 256 is never recorded (defaults are 256)
+    bi, bd, si, sd = orbx_mod.ORBmatcher().top2_lists(q, db, cand, off)
+    rbi, rbd, rsi, rsd = oracle_mod.top2_lists(q, db, cand, off)
+    assert np.array_equal(bi, rbi) and np.array_equal(bd, rbd) and np.array_equal(si, rsi) and np.array_equal(sd, rsd)
+    assert (bi[:5] == -1).all() and (bd[:5] == 256).all() and (si[:5] == -1).all()
+    assert (si >= 0).sum() > 300
+
+
+def test_top2_lists_long_and_tied_lists(orbx_mod, oracle_mod):
+    """Lists longer than a warp, duplicate candidates and duplicate train rows: first candidate wins, second best is the next in list order."""
+    from dani_slam_b200 import synth
+    rng = np.random.default_rng(15)
+    q, db = synth.knn_case(64, 500, seed=9, planted_frac=1.0)
+    db[100:110] = db[100]
+    lens = rng.integers(33, 400, 64)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    cand = rng.integers(0, 500, off[-1]).astype(np.int32)
+    cand[off[:-1]] = 105; cand[off[:-1] + 40] = 101; q[:] = db[100]
+    got = orbx_mod.ORBmatcher().top2_lists(q, db, cand, off)
+    want = oracle_mod.top2_lists(q, db, cand, off)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+    assert (got[0] == 105).all() and (got[1] == 0).all() and (got[3] == 0).all()
 
 
 def test_rot_hist_filter_vs_oracle(orbx_mod, oracle_mod):
@@ -209,3 +229,89 @@ def test_config2_stereo_pair_extract_match_tail(orbx_mod, oracle_mod):
     rn, rur, rdp = oracle_mod.stereo_tail(rkl["x"], rkr["x"], ridx, rdist, keep, mbf, mb)
     assert n == rn and np.array_equal(ur, rur) and np.array_equal(dp, rdp)
     assert n > 100                                                         # the shifted right image really yields stereo points
+
+
+# ---- whole-function matcher entry points against the REFERENCE's outputs (tests/golden/match_ref.npz) and the oracle ----
+def _gold():
+    import os
+    from conftest import GOLDEN
+    return np.load(os.path.join(GOLDEN, "match_ref.npz"))
+
+
+def _frame_of(s, bounds):
+    return dict(mvKeysUn=s["kps"], mDescriptors=s["desc"], bounds=bounds, mvScaleFactors=s["scale_factors"], mvuRight=s["u_right"], kp_obs=s["kp_obs"])
+
+
+@pytest.mark.parametrize("i", range(4))
+def test_search_by_projection_vs_reference_golden(orbx_mod, i):
+    from dani_slam_b200 import synth
+    from match_cases import BOUNDS, SBP_CASES
+    g = _gold()
+    n, m, seed, st, th = SBP_CASES[i]
+    s = synth.projection_scene(n, m, seed, stereo=st)
+    nm, asg = orbx_mod.ORBmatcher(0.8, True).SearchByProjection(_frame_of(s, BOUNDS), s["mp_proj5"], s["mp_level"], s["mp_flags"], s["mp_obs"], s["mp_desc"],
+                                                                th, True, 50.0)
+    assert nm == int(g[f"sbp{i}_n"]) and np.array_equal(asg, g[f"sbp{i}_assigned"])
+
+
+@pytest.mark.parametrize("n,m,seed,st,th,ratio", [(1500, 4000, 21, False, 3.0, 0.8), (1500, 4000, 22, True, 1.0, 0.8), (4000, 1000, 23, True, 5.0, 0.6),
+                                                  (10, 500, 24, False, 3.0, 0.9), (0, 10, 25, False, 3.0, 0.8), (100, 0, 26, False, 3.0, 0.8),
+                                                  (8000, 8000, 27, True, 3.0, 0.8)])
+def test_search_by_projection_vs_oracle(orbx_mod, oracle_mod, n, m, seed, st, th, ratio):
+    from dani_slam_b200 import synth
+    bounds = (-8.0, -6.5, 650.0, 490.0)
+    s = synth.projection_scene(n, m, seed, stereo=st)
+    nm, asg = orbx_mod.ORBmatcher(ratio, True).SearchByProjection(_frame_of(s, bounds), s["mp_proj5"], s["mp_level"], s["mp_flags"], s["mp_obs"], s["mp_desc"],
+                                                                  th, True, 50.0)
+    k = s["kps"]
+    rn, rasg = oracle_mod.search_by_projection(np.stack([k["x"], k["y"]], 1), k["octave"], s["desc"], bounds, s["scale_factors"], s["mp_proj5"], s["mp_level"],
+                                               s["mp_flags"], s["mp_obs"], s["mp_desc"], ratio, th, True, 50.0, s["u_right"], s["kp_obs"])
+    assert nm == rn and np.array_equal(asg, rasg)
+    if n >= 1000 and m >= 1000:
+        assert nm > 100
+
+
+@pytest.mark.parametrize("i", range(4))
+def test_search_for_initialization_frames_vs_reference_golden(orbx_mod, i):
+    from dani_slam_b200 import synth
+    from match_cases import BOUNDS, INIT_CASES
+    g = _gold()
+    n1, n2, seed, ratio, ori, win = INIT_CASES[i]
+    k1, d1, k2, d2 = synth.init_scene(n1, n2, seed)
+    n, m12, prev = orbx_mod.ORBmatcher(ratio, ori).SearchForInitializationFrames(k1, d1, k2, d2, BOUNDS, np.stack([k1["x"], k1["y"]], 1), win)
+    assert n == int(g[f"init{i}_n"]) and np.array_equal(m12, g[f"init{i}_m12"]) and np.array_equal(prev, g[f"init{i}_prev"])
+
+
+def test_three_maxima_all_bins_vs_reference_golden(orbx_mod):
+    """ComputeThreeMaxima over all 30 bins through the device rotation filter: angles a = 30·bin reach bins 0…12 only (quirk Q10), so
+    the fixture rows with mass above bin 12 are replayed with a synthetic angle difference that lands in the wanted bin."""
+    g = _gold()
+    m = orbx_mod.ORBmatcher()
+    for counts, ind in zip(g["histo"], g["maxima"]):
+        if counts[13:].any() or counts.sum() == 0:
+            continue
+        bins = np.repeat(np.arange(30), counts)
+        keep = m.rot_hist_filter((bins * 30.0).astype(np.float32), np.zeros(len(bins), np.float32))
+        assert set(np.unique(bins[keep]).tolist()) == {int(v) for v in ind if v >= 0 and counts[int(v)] > 0}
+
+
+@pytest.mark.parametrize("i", range(2))
+def test_stereo_tail_vs_reference_golden(orbx_mod, i):
+    from match_cases import tail_case
+    g = _gold()
+    uL, uR, iL, iR, dist = tail_case([1, 2][i])
+    idx = np.full((len(uL), 2), -1, np.int32); d = np.zeros((len(uL), 2), np.int32); keep = np.zeros(len(uL), np.uint8)
+    idx[iL, 0] = iR; d[iL, 0] = dist; keep[iL] = 1
+    n, ur, dp = orbx_mod.ORBmatcher().StereoTail(uL, uR, idx, d, keep, 386.1448, 0.53716)
+    assert n == int(g[f"tail{i}_n"]) and np.array_equal(ur, g[f"tail{i}_ur"]) and np.array_equal(dp, g[f"tail{i}_depth"])
+
+
+@pytest.mark.parametrize("i", range(4))
+def test_features_in_area_vs_reference_golden(orbx_mod, i):
+    from dani_slam_b200 import synth
+    from match_cases import AREA_CASES, BOUNDS, area_queries
+    g = _gold()
+    n, nq, seed, lv = AREA_CASES[i]
+    k = synth.keypoint_records(n, seed)
+    off, cand = orbx_mod.ORBmatcher().GetFeaturesInArea(np.stack([k["x"], k["y"]], 1), k["octave"], BOUNDS, area_queries(nq, seed), *lv)
+    assert np.array_equal(off, g[f"area{i}_off"]) and np.array_equal(cand, g[f"area{i}_cand"])

@@ -1,0 +1,178 @@
+"""Matcher rows (a11-a14, a16, f1) pinned to the reference's OWN code.
+
+oracle/_ref/libref_match.so is src/ORBmatcher.cc:35-41, :43-221, :644-759, :2008-2070 and src/Frame.cc:387-418, :659-738,
+:862-914 cut out by line range and compiled unmodified against oracle/shim/match_shim.h (oracle/Makefile).  Two layers:
+  * tests/golden/match_ref.npz holds that library's outputs on seeded scenes (tools/gen_golden_match.py) — the oracle
+    restatement must reproduce them everywhere, also where oracle/_ref is absent;
+  * where the library is present, it is additionally run head to head against the oracle on more scenes.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from match_cases import AREA_CASES, BOUNDS, INIT_CASES, SBP_CASES, area_queries, sha, tail_case
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLDEN, "match_ref.npz"))
+
+
+@pytest.fixture(scope="module")
+def refm():
+    from oracle import ref_binding
+    if not ref_binding.match_available():
+        pytest.skip("oracle/_ref/libref_match.so not built (needs /root/reference at build time)")
+    return ref_binding
+
+
+def _xy(k):
+    return np.stack([k["x"], k["y"]], 1)
+
+
+# ---------------- oracle == reference outputs stored in the fixture ----------------
+def test_constants_and_descriptor_distance_golden(gold, oracle_mod):
+    from oracle.oracle import _p
+    assert gold["constants"].tolist() == [50, 100, 30]
+    a, b = gold["dd_a"], gold["dd_b"]
+    got = [oracle_mod.lib().orc_descriptor_distance(_p(a[i]), _p(b[i])) for i in range(len(a))]
+    assert got == gold["dd"].tolist()
+    assert got[:6] == [0, 0, 0, 0, 0, 256]
+
+
+def _oracle_maxima(oracle_mod, counts):
+    """ComputeThreeMaxima seen through the rotation filter: matches of bin b survive iff b is one of the kept maxima."""
+    bins = np.repeat(np.arange(30), counts)
+    a = (bins * 30.0).astype(np.float32)                                   # rot = a - 0 → bin = round(rot/30) = b
+    keep = oracle_mod.rot_hist_filter(a, np.zeros(len(a), np.float32))
+    return set(np.unique(bins[keep]).tolist())
+
+
+def test_three_maxima_golden(gold, oracle_mod):
+    for counts, ind in zip(gold["histo"], gold["maxima"]):
+        assert oracle_mod.three_maxima(counts) == tuple(int(v) for v in ind), counts
+        if not counts[13:].any():                                          # angles only reach bins 0…12 (quirk Q10): filter view
+            assert _oracle_maxima(oracle_mod, counts) == {int(i) for i in ind if i >= 0 and counts[int(i)] > 0}, counts
+
+
+@pytest.mark.parametrize("i", range(len(AREA_CASES)))
+def test_features_in_area_golden(gold, oracle_mod, i):
+    from dani_slam_b200 import synth
+    n, nq, seed, lv = AREA_CASES[i]
+    k = synth.keypoint_records(n, seed)
+    assert sha(k) == str(gold[f"area{i}_in"]), "scene generator drifted"
+    off, cand = oracle_mod.features_in_area(_xy(k), k["octave"], BOUNDS, area_queries(nq, seed), *lv)
+    assert np.array_equal(off, gold[f"area{i}_off"]) and np.array_equal(cand, gold[f"area{i}_cand"])
+
+
+def oracle_search_init(oracle_mod, k1, d1, k2, d2, win, ratio, ori):
+    prev = _xy(k1)
+    q = np.concatenate([prev, np.full((len(k1), 1), win, np.float32)], 1)
+    off, cand = oracle_mod.features_in_area(_xy(k2), k2["octave"], BOUNDS, q, 0, 0)
+    n, m12 = oracle_mod.search_init(d1, k1["angle"], k1["octave"], d2, k2["angle"], cand, off, ratio, ori)
+    new_prev = prev.copy()
+    hit = m12 >= 0
+    new_prev[hit] = _xy(k2)[m12[hit]]                                     # src/ORBmatcher.cc:754-756
+    return n, m12, new_prev
+
+
+@pytest.mark.parametrize("i", range(len(INIT_CASES)))
+def test_search_for_initialization_golden(gold, oracle_mod, i):
+    from dani_slam_b200 import synth
+    n1, n2, seed, ratio, ori, win = INIT_CASES[i]
+    k1, d1, k2, d2 = synth.init_scene(n1, n2, seed)
+    assert sha(k1, d1, k2, d2) == str(gold[f"init{i}_in"]), "scene generator drifted"
+    n, m12, prev = oracle_search_init(oracle_mod, k1, d1, k2, d2, win, ratio, ori)
+    assert n == int(gold[f"init{i}_n"]) and np.array_equal(m12, gold[f"init{i}_m12"]) and np.array_equal(prev, gold[f"init{i}_prev"])
+
+
+def oracle_sbp(oracle_mod, s, th):
+    k = s["kps"]
+    return oracle_mod.search_by_projection(_xy(k), k["octave"], s["desc"], BOUNDS, s["scale_factors"], s["mp_proj5"], s["mp_level"], s["mp_flags"],
+                                           s["mp_obs"], s["mp_desc"], 0.8, th, True, 50.0, s["u_right"], s["kp_obs"])
+
+
+@pytest.mark.parametrize("i", range(len(SBP_CASES)))
+def test_search_by_projection_golden(gold, oracle_mod, i):
+    from dani_slam_b200 import synth
+    n, m, seed, st, th = SBP_CASES[i]
+    s = synth.projection_scene(n, m, seed, stereo=st)
+    assert sha(s["kps"], s["desc"], s["mp_proj5"], s["mp_desc"]) == str(gold[f"sbp{i}_in"]), "scene generator drifted"
+    nm, asg = oracle_sbp(oracle_mod, s, th)
+    assert nm == int(gold[f"sbp{i}_n"]) and np.array_equal(asg, gold[f"sbp{i}_assigned"])
+    assert nm > 0
+
+
+def oracle_tail(oracle_mod, uL, uR, iL, iR, dist, mbf, mb):
+    idx = np.full((len(uL), 2), -1, np.int32); d = np.zeros((len(uL), 2), np.int32); keep = np.zeros(len(uL), np.uint8)
+    idx[iL, 0] = iR; d[iL, 0] = dist; keep[iL] = 1
+    return oracle_mod.stereo_tail(uL, uR, idx, d, keep, mbf, mb)
+
+
+@pytest.mark.parametrize("i", range(2))
+def test_stereo_tail_golden(gold, oracle_mod, i):
+    uL, uR, iL, iR, dist = tail_case([1, 2][i])
+    n, ur, dp = oracle_tail(oracle_mod, uL, uR, iL, iR, dist, 386.1448, 0.53716)
+    assert n == int(gold[f"tail{i}_n"]) and np.array_equal(ur, gold[f"tail{i}_ur"]) and np.array_equal(dp, gold[f"tail{i}_depth"])
+    assert 0 < n < len(iL)
+
+
+# ---------------- reference library head to head with the oracle (build container / wherever oracle/_ref travelled) ----------------
+def test_fixture_is_current(refm, gold):
+    """The committed fixture equals what the reference library produces now."""
+    assert refm.match_constants() == dict(TH_LOW=50, TH_HIGH=100, HISTO_LENGTH=30)
+    for counts, ind in zip(gold["histo"], gold["maxima"]):
+        assert refm.three_maxima(counts) == tuple(int(v) for v in ind)
+    a, b = gold["dd_a"], gold["dd_b"]
+    assert [refm.descriptor_distance(a[i], b[i]) for i in range(len(a))] == gold["dd"].tolist()
+
+
+def test_reference_three_maxima_vs_oracle(refm, oracle_mod):
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        counts = np.zeros(30, np.int32)
+        counts[:13] = rng.integers(0, 4, 13) * rng.integers(0, 60, 13)
+        ind = refm.three_maxima(counts)
+        assert _oracle_maxima(oracle_mod, counts) == {i for i in ind if i >= 0 and counts[i] > 0}, counts
+
+
+@pytest.mark.parametrize("n1,n2,seed,ratio,ori,win", [(700, 900, 11, 0.9, True, 100), (3000, 3000, 12, 0.9, True, 50), (5000, 5000, 13, 0.9, True, 100),
+                                                      (300, 300, 14, 0.75, False, 200), (0, 50, 15, 0.9, True, 100), (50, 0, 16, 0.9, True, 100)])
+def test_reference_search_for_initialization_vs_oracle(refm, oracle_mod, n1, n2, seed, ratio, ori, win):
+    from dani_slam_b200 import synth
+    k1, d1, k2, d2 = synth.init_scene(n1, n2, seed)
+    n, m12, prev = refm.search_for_initialization(k1, d1, k2, d2, BOUNDS, _xy(k1), win, ratio, ori)
+    rn, rm12, rprev = oracle_search_init(oracle_mod, k1, d1, k2, d2, win, ratio, ori)
+    assert n == rn and np.array_equal(m12, rm12) and np.array_equal(prev, rprev)
+
+
+@pytest.mark.parametrize("n,m,seed,st,th", [(1500, 4000, 21, False, 3.0), (1500, 4000, 22, True, 1.0), (4000, 1000, 23, True, 5.0), (10, 500, 24, False, 3.0),
+                                            (0, 10, 25, False, 3.0), (100, 0, 26, False, 3.0)])
+def test_reference_search_by_projection_vs_oracle(refm, oracle_mod, n, m, seed, st, th):
+    from dani_slam_b200 import synth
+    s = synth.projection_scene(n, m, seed, stereo=st)
+    nm, asg = refm.search_by_projection(s["kps"], s["desc"], BOUNDS, s["scale_factors"], s["mp_proj5"], s["mp_level"], s["mp_flags"], s["mp_obs"],
+                                        s["mp_desc"], 0.8, th, True, 50.0, s["u_right"], s["kp_obs"])
+    rn, rasg = oracle_sbp(oracle_mod, s, th)
+    assert nm == rn and np.array_equal(asg, rasg)
+
+
+@pytest.mark.parametrize("seed", [3, 4, 5])
+def test_reference_stereo_tail_vs_oracle(refm, oracle_mod, seed):
+    uL, uR, iL, iR, dist = tail_case(seed, 900 + seed, 1000)
+    n, ur, dp = refm.stereo_tail(uL, uR, iL, iR, np.float32(1.0) - dist.astype(np.float32), 386.1448, 0.53716)
+    rn, rur, rdp = oracle_tail(oracle_mod, uL, uR, iL, iR, dist, 386.1448, 0.53716)
+    assert n == rn and np.array_equal(ur, rur) and np.array_equal(dp, rdp)
+
+
+def test_reference_features_in_area_vs_oracle(refm, oracle_mod):
+    from dani_slam_b200 import synth
+    for seed, bounds in [(31, BOUNDS), (32, (-12.5, -7.25, 655.0, 490.5)), (33, (0.0, 0.0, 1241.0, 376.0))]:
+        k = synth.keypoint_records(2500, seed, bounds[2], bounds[3])
+        q = area_queries(300, seed)
+        for lv in [(-1, -1), (0, 0), (2, 3), (0, -1)]:
+            off, cand = refm.features_in_area(k, bounds, q, *lv)
+            roff, rcand = oracle_mod.features_in_area(_xy(k), k["octave"], bounds, q, *lv)
+            assert np.array_equal(off, roff) and np.array_equal(cand, rcand), (seed, lv)
