@@ -200,6 +200,83 @@ def run_reference(args, rank):
     return 0
 
 
+def measure_latency(orbx, device, frames, args):
+    """orbx_extract — the call Frame::ExtractORB makes once per image (src/Frame.cc:420-427) — on ONE frame held in pageable host
+    memory (a cv::Mat-like buffer), timed per call on the host clock around the C-ABI call: copy in, ~17 kernels, copy out, one
+    synchronisation.  Mono: 1000 calls.  Stereo: two handles called from two threads at the same time (src/Frame.cc:124-127), the
+    pair timed from the common start to the later finish."""
+    import ctypes as C
+    L = orbx.lib()
+    cap = NFEAT + 2 * LEVELS + 8
+    n_calls = args.latency_calls
+
+    class One:
+        def __init__(self, img):
+            self.img = np.array(img, copy=True)                              # ordinary (pageable) memory
+            self.h = L.orbx_create(NFEAT, SCALE, LEVELS, INI_TH, MIN_TH, device, W_IMG, H_IMG, 1)
+            if not self.h:
+                raise SystemExit("orbx_create failed: " + L.orbx_last_error(None).decode())
+            self.kps = np.zeros(cap, orbx.KP_DTYPE); self.desc = np.zeros((cap, 32), np.uint8)
+            self.n, self.mono = C.c_int(0), C.c_int(0)
+            self.args = (self.h, self.img.ctypes.data_as(C.c_void_p), H_IMG, W_IMG, W_IMG, None, 0, 0, 1000, self.kps.ctypes.data_as(C.c_void_p),
+                         self.desc.ctypes.data_as(C.c_void_p), cap, C.byref(self.n), C.byref(self.mono))
+
+        def call(self):
+            rc = L.orbx_extract(*self.args)
+            if rc != 0:
+                raise SystemExit(f"orbx_extract failed: {rc} {L.orbx_last_error(self.h)}")
+
+        def close(self):
+            L.orbx_destroy(self.h)
+
+    def pct(a):
+        a = np.sort(np.asarray(a, np.float64)) / 1000.0                      # ns → µs
+        return {"p50_us": float(a[len(a) // 2]), "p99_us": float(a[min(len(a) - 1, int(len(a) * 0.99))]), "min_us": float(a[0]),
+                "mean_us": float(a.mean()), "calls": int(len(a))}
+
+    left, right = One(frames[0]), One(frames[1 % len(frames)])
+    for _ in range(20):
+        left.call(); right.call()
+    mono = []
+    for _ in range(n_calls):
+        t0 = time.perf_counter_ns(); left.call(); mono.append(time.perf_counter_ns() - t0)
+    n_kp = left.n.value
+    # stereo pair: two threads released together by a barrier per iteration
+    n_pairs = max(50, n_calls // 2)
+    bar = threading.Barrier(3)
+    def side(o):
+        for _ in range(n_pairs):
+            bar.wait(); o.call(); bar.wait()
+    ths = [threading.Thread(target=side, args=(o,)) for o in (left, right)]
+    for t in ths:
+        t.start()
+    pair = []
+    for _ in range(n_pairs):
+        bar.wait(); t0 = time.perf_counter_ns(); bar.wait(); pair.append(time.perf_counter_ns() - t0)
+    for t in ths:
+        t.join()
+    left.close(); right.close()
+    out = {"api": "orbx_extract (one 640x480-class frame in pageable host memory → keypoints + descriptors in host memory), per call on the host clock",
+           "workload": f"{W_IMG}x{H_IMG}_nf{NFEAT}", "keypoints": n_kp, "mono": pct(mono), "stereo_pair_two_threads": pct(pair),
+           "note": "stereo: a Python thread barrier releases both callers, so the pair figure includes its wake-up jitter", "cpu_reference": None}
+    if not args.no_cpu:
+        from oracle import oracle as _orc
+        kind, make = "port", (lambda: _orc.Extractor(NFEAT, SCALE, LEVELS, INI_TH, MIN_TH))
+        try:
+            from oracle import ref_binding
+            if ref_binding.available():
+                kind, make = "reference", (lambda: ref_binding.Extractor(NFEAT, SCALE, LEVELS, INI_TH, MIN_TH))
+        except Exception:
+            pass
+        cx = make()
+        cx.extract(frames[0])
+        ts = []
+        for i in range(12):
+            t0 = time.perf_counter_ns(); cx.extract(frames[i % len(frames)]); ts.append(time.perf_counter_ns() - t0)
+        out["cpu_reference"] = {"ms_per_frame_1_thread": float(np.median(ts)) / 1e6, "kind": kind, "sample": "median of 12 frames, one thread"}
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------
 def bind_to_gpu_numa_node(local_rank: int) -> None:
     """One process per GPU: run on the CPUs of the GPU's NUMA node, so that the pinned host buffers (first touch) and the
@@ -213,6 +290,15 @@ def bind_to_gpu_numa_node(local_rank: int) -> None:
         node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
         nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
         if node < 0 or len(nodes) < 2:
+            # one NUMA node (or none reported): give every rank its own contiguous slice of the allowed cores instead, so that the
+            # copy-submitting threads of the ranks do not migrate over each other
+            world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+            allowed = sorted(os.sched_getaffinity(0))
+            if world > 1 and len(allowed) >= 2 * world:
+                per = len(allowed) // world
+                mine = set(allowed[local_rank * per:(local_rank + 1) * per])
+                os.sched_setaffinity(0, mine)
+                print(f"[bench] rank {local_rank}: single NUMA node, bound to cores {min(mine)}-{max(mine)}", file=sys.stderr)
             return
         cpus = set()
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
@@ -238,6 +324,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--match-db", type=int, default=10_000_000)
     ap.add_argument("--no-bow", action="store_true", help="skip the bag-of-words section")
+    ap.add_argument("--no-latency", action="store_true", help="skip the single-frame latency section")
+    ap.add_argument("--latency-calls", type=int, default=1000)
     ap.add_argument("--bow-levels", type=int, default=6, help="depth of the synthetic k=10 vocabulary (ORBvoc: 6)")
     args = ap.parse_args()
     default_batch = set_workload(args.workload)
@@ -296,7 +384,7 @@ def main():
         return float(t.item())
 
     B, K, Wm = args.batch, args.steps, args.warmup
-    cap = NFEAT + 64
+    cap = NFEAT + 2 * LEVELS + 8            # a level can overshoot its quota by at most 2
     frames = make_frames(B, rank * B)
     h_frames = torch.from_numpy(frames).pin_memory()
     d_frames = h_frames.to(dev)
@@ -366,7 +454,30 @@ def main():
     e2e_value = frames_total / t_e2e
     n_avg = float(out_n.mean())
     h2d = B * H_IMG * W_IMG
-    d2h = int(B * (out_n.max() * 60) + 8 * B)
+    d2h = int(B * cap * 60 + 8 * B)        # the call copies cap-strided keypoint (28 B) and descriptor (32 B) rows + n_out, mono_index
+
+    # transfer ceiling of the host path: the same copies on the same streams with the same chunking, no kernels
+    def step_copy():
+        rc = ex.L.orbx_copy_only_batch(ex.h, img_ptrs, B, H_IMG, W_IMG, W_IMG, out_k.ctypes.data_as(C.c_void_p), out_d.ctypes.data_as(C.c_void_p), cap)
+        if rc != 0:
+            raise SystemExit(f"orbx_copy_only_batch failed: {rc} {ex.L.orbx_last_error(ex.h)}")
+
+    for _ in range(2):
+        step_copy()
+    barrier()
+    Kc = max(3, min(K, 10))
+    t0 = time.perf_counter()
+    for _ in range(Kc):
+        step_copy()
+    torch.cuda.synchronize(dev)
+    t_copy = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    copy_ceiling = world * B * Kc / t_copy
+
+    # ---------------- single-frame latency of the drop-in call (`latency`; BASELINE config 1, rank 0 only) ----------------
+    latency = None
+    if rank == 0 and not args.no_latency:
+        latency = measure_latency(orbx, local_rank, frames, args)
 
     # ---------------- per-stage device time → roofline of the dominant kernel ----------------
     ex.set_profiling(True)
@@ -398,6 +509,21 @@ def main():
                 "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": per_call[dominant],
                 "stage_ms_per_batch": per_call, "stage_share": {k: v / max(sum(per_call.values()), 1e-9) for k, v in per_call.items()}}
     pipeline_gbs = B_ALG_FRAME * (value / world) / 1e9
+    # instruction-issue view of the same kernel: thread instructions per frame from the committed ncu capture (profiles/issue.json,
+    # smsp__thread_inst_executed.sum per frame) × frames per launch ÷ the launch time measured here, against 128 lanes/clk/SM
+    roofline_issue = None
+    try:
+        iss = json.load(open(os.path.join(ROOT, "profiles", "issue.json")))
+        if args.workload == "tum1" and iss.get(dominant) and per_call[dominant] > 0:
+            clk = float(clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0) * 1e6
+            peak_i = 148 * 128 * clk
+            ach = float(iss[dominant]) * B / (per_call[dominant] / 1000.0)
+            roofline_issue = {"bound": "issue", "kernel": dominant, "achieved": ach, "peak": peak_i, "unit": "thread-instructions/s", "frac": ach / peak_i,
+                              "thread_inst_per_frame": float(iss[dominant]), "thread_inst_per_pixel": float(iss[dominant]) / SUM_P,
+                              "peak_source": "148 SMs x 4 schedulers x 32 lanes x median SM clock of this run",
+                              "source": iss.get("source")}
+    except Exception:
+        pass
     roofline_pipeline = {"bound": "hbm", "achieved": pipeline_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": pipeline_gbs / peak_gbs,
                          "algorithmic_bytes_per_frame": B_ALG_FRAME}
 
@@ -419,7 +545,8 @@ def main():
         def step_match():
             if dist_on:
                 return sm.knn2(d_q, d_db, lo, group)
-            return sm.local_top2(d_q, d_db, lo)
+            rec = sm.local_top2(d_q, d_db, lo)
+            return rec[0], rec[1]
 
         for _ in range(2):
             step_match()
@@ -434,14 +561,44 @@ def main():
         barrier()
         ms_m = max_over_ranks(m0.elapsed_time(m1))
         gpairs = nq * ndb * Km / (ms_m / 1000.0) / 1e9
+        # parity of the sharded result on this hardware: rank 0 rebuilds the whole database from the per-rank seeds, scans it
+        # unsharded on its own GPU, and every rank's merged (idx, dist) must equal that scan bit for bit
+        parity = None
+        if dist_on:
+            full = []
+            if rank == 0:
+                for r in range(world):
+                    rlo, rhi = sharded.shard_bounds(ndb, r, world)
+                    gr = torch.Generator(device=dev)
+                    gr.manual_seed(1234 + r)
+                    full.append(torch.randint(0, 256, (rhi - rlo, 32), dtype=torch.uint8, device=dev, generator=gr))
+                rec = sm.local_top2(d_q, torch.cat(full), 0)
+                ref_rec = torch.stack([rec[0], rec[1]]).contiguous()
+                del full
+            else:
+                ref_rec = torch.empty((2, nq, 2), dtype=torch.int32, device=dev)
+            td.broadcast(ref_rec, src=0)
+            same = torch.tensor([int(torch.equal(ref_rec[0], idx) and torch.equal(ref_rec[1], dist))], dtype=torch.int32, device=dev)
+            td.all_reduce(same, op=td.ReduceOp.MIN)
+            parity = bool(same.item())
+        pk = {}
+        try:
+            pk = json.load(open(os.path.join(ROOT, "profiles", "pipe_peaks.json")))
+        except Exception:
+            pass
+        popc_peak = float(pk.get("popc_lanes_per_clk_per_sm", 16.0)) * float(pk.get("sm_count", 148)) * 1e6 * float(clocks.get("sm_max_mhz") or 1965.0)
         match = {"metric": "hamming_knn2_gpairs_per_s", "value": gpairs, "unit": "Gpairs/s", "nq": nq, "ndb": ndb,
                  "scaling": "strong", "ms_per_step": ms_m / Km, "steps": Km,
-                 "collective": "all_gather of per-shard top-2 (nq*2*2 int32)" if dist_on else None,
+                 "collective": "one all_gather of the packed per-shard top-2 record (nq*2*2 int32 = 32 KB per rank)" if dist_on else None,
+                 "parity": parity,
+                 "parity_note": "sharded result of every rank == rank 0's unsharded scan of the whole DB (indices and distances)" if dist_on else
+                                "single GPU: see cpu_baseline.sample and tests/test_match_gpu.py::test_config4_full_size_vs_oracle",
                  "popc_per_s": 8 * gpairs * 1e9, "cpu_baseline": None,
-                 "roofline": {"bound": "int-popc", "achieved": 8 * gpairs * 1e9 / world, "peak": 15.3 * 148 * 1.965e9, "unit": "POPC/s per GPU",
-                              "frac": 8 * gpairs * 1e9 / world / (15.3 * 148 * 1.965e9),
-                              "note": "algorithmic 8 POPC.32 per pair against the measured POPC rate (15.3 lanes/clk/SM, profiles/microbench_pipes_b200.txt); "
-                                      "above 1 because the kernel's carry-save adders issue 5 POPC per pair"}}
+                 "roofline": {"bound": "int-popc", "issued": 5 * gpairs * 1e9 / world, "achieved": 8 * gpairs * 1e9 / world, "peak": popc_peak,
+                              "unit": "POPC/s per GPU", "frac_issued": 5 * gpairs * 1e9 / world / popc_peak, "frac": 8 * gpairs * 1e9 / world / popc_peak,
+                              "peak_source": "profiles/pipe_peaks.json (register-resident POPC microbenchmark, lanes/clk/SM) x 148 SMs x sm_max_mhz",
+                              "note": "`issued` = the 5 POPC.32 per pair the carry-save kernel executes (the honest pipe utilisation); `achieved` = the "
+                                      "algorithmic 8 POPC.32 per pair of SURVEY.md §8(d), which exceeds the pipe's peak because 3 of 8 are folded into LOP3"}}
         if world == 1 and not args.no_cpu:
             # the oracle's popcount kNN on all host cores over a DB slice (the scan is linear in the DB length)
             from oracle import oracle as _orc
@@ -454,9 +611,9 @@ def main():
                 cidx, cdist = _orc.knn2(h_q, h_db, nthreads=cores)
                 reps += 1
             dt = time.time() - t0
-            gi, gd = sm.local_top2(d_q, d_db[:slice_rows].contiguous(), 0)
+            grec = sm.local_top2(d_q, d_db[:slice_rows].contiguous(), 0)
             torch.cuda.synchronize(dev)
-            same = bool(np.array_equal(gi.cpu().numpy().reshape(-1, 2), cidx) and np.array_equal(gd.cpu().numpy().reshape(-1, 2), cdist))
+            same = bool(np.array_equal(grec[0].cpu().numpy(), cidx) and np.array_equal(grec[1].cpu().numpy(), cdist))
             match["cpu_baseline"] = {"value": nq * slice_rows * reps / dt / 1e9, "unit": "Gpairs/s", "cores": cores, "kind": "port",
                                      "sample": f"{nq} queries x {slice_rows} DB rows, {reps} passes in {dt:.1f}s on {cores} threads (oracle popcount kNN); "
                                                f"GPU result on the same slice identical: {same}"}
@@ -534,9 +691,14 @@ def main():
                        "keypoints_per_frame": n_avg},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "orbx_extract_batch (host pinned buffers, H2D + D2H inside the timed region)"},
+                    "api": "orbx_extract_batch (host pinned buffers, H2D + D2H inside the timed region)",
+                    "copy_ceiling_frames_per_s": copy_ceiling,
+                    "copy_ceiling_note": "orbx_copy_only_batch: the same bytes over the same streams and chunks with no kernel launched, all ranks at once; "
+                                         f"{(h2d + d2h) * copy_ceiling / B / 1e9:.1f} GB/s over PCIe in total"},
+            "latency": latency,
             "gpu_launches": int(launches),
             "roofline": roofline,
+            "roofline_issue": roofline_issue,
             "roofline_pipeline": roofline_pipeline,
             "cpu_baseline": cpu_baseline,
             "match": match,

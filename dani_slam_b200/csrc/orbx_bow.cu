@@ -25,7 +25,7 @@
 #include <string>
 #include <vector>
 
-#include "../../include/orbx.h"
+#include "orbx_internal.h"
 
 namespace {
 
@@ -278,7 +278,8 @@ orbx_vocab *upload(const HostTree &T, int k, int L, int scoring, int weighting, 
     if (v->maxChildren >= 65536) { tl_vocab_error = "orbx_vocab: more than 65535 children under one node"; delete v; return nullptr; }
     auto fail = [&](const char *what, cudaError_t e) { tl_vocab_error = std::string(what) + ": " + cudaGetErrorString(e); cudaGetLastError(); orbx_vocab_destroy(v); return (orbx_vocab *)nullptr; };
     cudaError_t e;
-    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
+    OrbxDeviceGuard dg_(device);
+    if ((e = dg_.status) != cudaSuccess) return fail("cudaSetDevice", e);
     if ((e = cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
     if ((e = cudaMalloc((void **)&v->d_desc, (size_t)v->nNodes * 32)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMalloc((void **)&v->d_childOff, (size_t)(v->nNodes + 1) * sizeof(int))) != cudaSuccess) return fail("cudaMalloc", e);
@@ -374,7 +375,7 @@ orbx_vocab *orbx_vocab_load_text(const char *path, int device) {
 
 void orbx_vocab_destroy(orbx_vocab *v) {
     if (!v) return;
-    cudaSetDevice(v->device);
+    OrbxDeviceGuard dg_(v->device);
     if (v->stream) { cudaStreamSynchronize(v->stream); cudaStreamDestroy(v->stream); }
     void *bufs[] = {v->d_desc, v->d_childOff, v->d_child, v->d_wordId, v->d_weight, v->w_desc, v->w_word, v->w_node, v->w_bowIds, v->w_fvNodes,
                     v->w_fvIdx, v->w_leaf, v->w_fvOff, v->w_counts, v->w_bowVals, v->b_leaf};
@@ -410,7 +411,7 @@ int orbx_bow_transform_batch_device(orbx_vocab *v, const uint8_t *d_desc, size_t
         return ORBX_ERR_ARG;
     }
     std::lock_guard<std::mutex> lk(v->mu);
-    VCUDA_TRY(v, cudaSetDevice(v->device));
+    OrbxDeviceGuard dg_(v->device); VCUDA_TRY(v, dg_.status);
     const size_t need = (size_t)batch * cap;
     if (need > v->b_leafCap) {
         VCUDA_TRY(v, cudaStreamSynchronize(v->stream));
@@ -434,7 +435,7 @@ int orbx_bow_transform(orbx_vocab *v, const uint8_t *desc, int n, int levelsup, 
     if (n == 0) return ORBX_OK;
     if (n > 16384) { v->err = "orbx_bow: more than 16384 descriptors per image"; return ORBX_ERR_CAPACITY; }
     std::lock_guard<std::mutex> lk(v->mu);
-    VCUDA_TRY(v, cudaSetDevice(v->device));
+    OrbxDeviceGuard dg_(v->device); VCUDA_TRY(v, dg_.status);
     if (n > v->workCap) {
         VCUDA_TRY(v, cudaStreamSynchronize(v->stream));
         void **bufs[] = {(void **)&v->w_desc, (void **)&v->w_word, (void **)&v->w_node, (void **)&v->w_bowIds, (void **)&v->w_fvNodes,

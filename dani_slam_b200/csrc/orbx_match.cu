@@ -135,14 +135,17 @@ __global__ void __launch_bounds__(256) k_knn2_merge_partials(const uint2 *__rest
 }
 
 // merge of per-shard (idx, dist) top-2 lists, e.g. after an all-gather across GPUs
+// (shard g's lists start shardStride int32 after shard g-1's: 2·nq for two separate arrays, 4·nq for the packed
+// {idx[nq×2], dist[nq×2]} records of orbx_knn2_merge_packed_device)
 __global__ void __launch_bounds__(256) k_knn2_merge_shards(const int32_t *__restrict__ idxAll, const int32_t *__restrict__ distAll,
-                                                           int nShards, int nq, int32_t *__restrict__ idx, int32_t *__restrict__ dist) {
+                                                           int nShards, int nq, long long shardStride, int32_t *__restrict__ idx,
+                                                           int32_t *__restrict__ dist) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= nq) return;
     const unsigned long long NONE = ~0ull;
     unsigned long long a = NONE, b = NONE;
     for (int e = lane; e < 2 * nShards; e += 32) {
-        const long long o = ((long long)(e >> 1) * nq + warp) * 2 + (e & 1);
+        const long long o = (long long)(e >> 1) * shardStride + (long long)warp * 2 + (e & 1);
         const int32_t i = idxAll[o], d = distAll[o];
         if (i >= 0) top2_insert(((unsigned long long)(uint32_t)d << 32) | (uint32_t)i, a, b);
     }
@@ -664,7 +667,8 @@ orbx_matcher *orbx_matcher_create(int device) {
     }
     orbx_matcher *m = new orbx_matcher;
     m->device = device;
-    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    OrbxDeviceGuard dg_(device);
+    if (dg_.status != cudaSuccess || cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) {
         tl_merr = "orbx_matcher_create: cannot create a stream";
         delete m;
         return nullptr;
@@ -737,7 +741,19 @@ int orbx_knn2_merge_device(orbx_matcher *m, const int32_t *d_idx_all, const int3
     }
     if (nq == 0) return ORBX_OK;
     OrbxDeviceGuard dg_(m->device); MCUDA_TRY(m, dg_.status);
-    k_knn2_merge_shards<<<(nq * 32 + 255) / 256, 256, 0, m->stream>>>(d_idx_all, d_dist_all, n_shards, nq, d_idx, d_dist);
+    k_knn2_merge_shards<<<(nq * 32 + 255) / 256, 256, 0, m->stream>>>(d_idx_all, d_dist_all, n_shards, nq, 2LL * nq, d_idx, d_dist);
+    MCUDA_TRY(m, cudaGetLastError());
+    return ORBX_OK;
+}
+
+int orbx_knn2_merge_packed_device(orbx_matcher *m, const int32_t *d_packed_all, int n_shards, int nq, int32_t *d_idx, int32_t *d_dist) {
+    if (!m || n_shards < 1 || nq < 0 || (nq > 0 && (!d_packed_all || !d_idx || !d_dist))) {
+        if (m) m->err = "orbx_knn2_merge_packed_device: bad argument";
+        return ORBX_ERR_ARG;
+    }
+    if (nq == 0) return ORBX_OK;
+    OrbxDeviceGuard dg_(m->device); MCUDA_TRY(m, dg_.status);
+    k_knn2_merge_shards<<<(nq * 32 + 255) / 256, 256, 0, m->stream>>>(d_packed_all, d_packed_all + 2LL * nq, n_shards, nq, 4LL * nq, d_idx, d_dist);
     MCUDA_TRY(m, cudaGetLastError());
     return ORBX_OK;
 }

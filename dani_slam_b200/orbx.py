@@ -77,6 +77,8 @@ def lib() -> C.CDLL:
     L.orbx_hamming_knn2.argtypes = [vp, vp, i32, vp, i64, vp, vp]
     L.orbx_hamming_knn2_device.argtypes = [vp, vp, i32, vp, i64, i64, vp, vp]
     L.orbx_knn2_merge_device.argtypes = [vp, vp, vp, i32, i32, vp, vp]
+    L.orbx_knn2_merge_packed_device.argtypes = [vp, vp, i32, i32, vp, vp]
+    L.orbx_copy_only_batch.argtypes = [vp, vp, i32, i32, i32, sz, vp, vp, i32]
     L.orbx_ratio_test.argtypes = [vp, vp, i32, f64, vp]
     L.orbx_ratio_test_device.argtypes = [vp, vp, i32, f64, vp]
     L.orbx_hamming_top2_lists.argtypes = [vp, vp, i32, vp, i64, vp, vp, vp, vp, vp, vp]
@@ -464,6 +466,9 @@ class ORBmatcher:
 
     def merge_device(self, d_idx_all, d_dist_all, n_shards, nq, d_idx, d_dist):
         self._chk(self.L.orbx_knn2_merge_device(self.h, d_idx_all, d_dist_all, n_shards, nq, d_idx, d_dist))
+
+    def merge_packed_device(self, d_packed_all, n_shards, nq, d_idx, d_dist):
+        self._chk(self.L.orbx_knn2_merge_packed_device(self.h, d_packed_all, n_shards, nq, d_idx, d_dist))
 
     def sync(self):
         self._chk(self.L.orbx_matcher_sync(self.h))

@@ -3,7 +3,7 @@
 * frame-batch extraction: frames are independent → contiguous split of the batch, NO collective.
 * DB-sharded Hamming kNN: the descriptor database is split into contiguous index ranges (so that
   "lower train index wins ties" stays a lexicographic minimum on (dist, global idx)); every rank computes
-  its local top-2 with global indices, ONE all-gather of nq×2×(idx, dist) int32 follows (NCCL over NVLink
+  its local top-2 with global indices, ONE all-gather of the packed record {idx[nq×2], dist[nq×2]} int32 follows (NCCL over NVLink
   on GPUs, gloo in the CPU tests), then every rank merges the G×2 candidates per query.
 
 torch is used only for device memory, streams and the collective; the compute is liborbx's kernels
@@ -23,30 +23,28 @@ def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def allgather_top2(idx, dist, group=None):
-    """All-gather the per-rank local top-2 tensors (nq×2 int32 each) → (world×nq×2, world×nq×2)."""
+def allgather_top2(rec, group=None):
+    """ONE all-gather of the per-rank local top-2 record `rec` = [2, nq, 2] int32 (plane 0: global indices, plane 1:
+    distances) → [world, 2, nq, 2]."""
     import torch
     import torch.distributed as td
     world = td.get_world_size(group)
-    nq = idx.shape[0]
-    # output = concatenation along dim 0 (the layout both NCCL and gloo accept), viewed as [world, nq, 2]
-    idx_all = torch.empty((world * nq,) + tuple(idx.shape[1:]), dtype=idx.dtype, device=idx.device)
-    dist_all = torch.empty((world * nq,) + tuple(dist.shape[1:]), dtype=dist.dtype, device=dist.device)
-    td.all_gather_into_tensor(idx_all, idx.contiguous(), group=group)
-    td.all_gather_into_tensor(dist_all, dist.contiguous(), group=group)
-    return idx_all.view(world, nq, *idx.shape[1:]), dist_all.view(world, nq, *dist.shape[1:])
+    rec = rec.contiguous()
+    # output = concatenation along dim 0 (the layout both NCCL and gloo accept), viewed as [world, 2, nq, 2]
+    out = torch.empty((world * rec.shape[0],) + tuple(rec.shape[1:]), dtype=rec.dtype, device=rec.device)
+    td.all_gather_into_tensor(out, rec, group=group)
+    return out.view(world, *rec.shape)
 
 
 def sharded_knn2(query, db_shard, shard_lo: int, local_top2: Callable, merge: Callable, group=None):
     """Global top-2 of `query` against a database split across the ranks of `group`.
 
-    local_top2(query, db_shard, idx_base) -> (idx[nq,2], dist[nq,2]) with GLOBAL indices (idx_base added),
-    missing neighbours = (-1, INT32_MAX);  merge(idx_all[G,nq,2], dist_all[G,nq,2]) -> (idx, dist).
+    local_top2(query, db_shard, idx_base) -> rec[2, nq, 2] int32: plane 0 = GLOBAL indices (idx_base added), plane 1 =
+    distances, missing neighbours = (-1, INT32_MAX);  merge(rec_all[G, 2, nq, 2]) -> (idx[nq,2], dist[nq,2]).
     The result is bit-identical to the unsharded search, ties included.
     """
-    idx, dist = local_top2(query, db_shard, shard_lo)
-    idx_all, dist_all = allgather_top2(idx, dist, group)
-    return merge(idx_all, dist_all)
+    rec = local_top2(query, db_shard, shard_lo)
+    return merge(allgather_top2(rec, group))
 
 
 class CudaShardedMatcher:
@@ -63,20 +61,19 @@ class CudaShardedMatcher:
     def local_top2(self, d_query, d_db, idx_base: int):
         torch = self.torch
         nq, ndb = d_query.shape[0], d_db.shape[0]
-        idx = torch.empty((nq, 2), dtype=torch.int32, device=self.dev)
-        dist = torch.empty((nq, 2), dtype=torch.int32, device=self.dev)
+        rec = torch.empty((2, nq, 2), dtype=torch.int32, device=self.dev)
         self._ext.wait_stream(torch.cuda.current_stream(self.dev))
-        self.m.knn2_device(d_query.data_ptr(), nq, d_db.data_ptr(), ndb, idx_base, idx.data_ptr(), dist.data_ptr())
+        self.m.knn2_device(d_query.data_ptr(), nq, d_db.data_ptr(), ndb, idx_base, rec[0].data_ptr(), rec[1].data_ptr())
         torch.cuda.current_stream(self.dev).wait_stream(self._ext)
-        return idx, dist
+        return rec
 
-    def merge(self, idx_all, dist_all):
+    def merge(self, rec_all):
         torch = self.torch
-        G, nq = idx_all.shape[0], idx_all.shape[1]
+        G, nq = rec_all.shape[0], rec_all.shape[2]
         idx = torch.empty((nq, 2), dtype=torch.int32, device=self.dev)
         dist = torch.empty((nq, 2), dtype=torch.int32, device=self.dev)
         self._ext.wait_stream(torch.cuda.current_stream(self.dev))
-        self.m.merge_device(idx_all.data_ptr(), dist_all.data_ptr(), G, nq, idx.data_ptr(), dist.data_ptr())
+        self.m.merge_packed_device(rec_all.data_ptr(), G, nq, idx.data_ptr(), dist.data_ptr())
         torch.cuda.current_stream(self.dev).wait_stream(self._ext)
         return idx, dist
 

@@ -11,6 +11,8 @@
  *  - mvImagePyramid is NOT refreshed on every call (nothing in the reference reads it outside the extractor):
  *    call MaterializePyramid() — or set mbMaterializePyramid — to copy the levels back, with the reference's
  *    19-px REFLECT_101 border, as ROI views exactly like src/ORBextractor.cc:1216-1217;
+ *  - -1 is returned for an empty image only, as in the reference; a missing CUDA device, a failed allocation or a CUDA error
+ *    throws std::runtime_error (there is no CPU fallback, and a dead GPU must not look like a blank frame);
  *  - ORBX_DEVICE (environment) selects the CUDA device, default 0; the handle is created for the first
  *    image size it sees and re-created if a larger image arrives.
  */
@@ -20,6 +22,8 @@
 #include <cstdlib>
 #include <iostream>
 #include <list>
+#include <stdexcept>
+#include <string>
 #include <vector>
 
 #include <opencv2/opencv.hpp>
@@ -52,7 +56,8 @@ public:
         const char* dev = std::getenv("ORBX_DEVICE");
         mDevice = dev ? std::atoi(dev) : 0;
         mvImagePyramid.resize(nlevels);
-        EnsureHandle(640, 480);
+        if(!EnsureHandle(640, 480))
+            Fail("orbx_create");
     }
 
     ~ORBextractor(){ if(mpHandle) orbx_destroy(mpHandle); }
@@ -168,13 +173,17 @@ protected:
 
     int Fail(const char* what)
     {
-        // The reference has no error path besides -1; CUDA failures are reported and surface as "no features".
-        std::cerr << "[ORBextractor/orbx] " << what << " failed: " << orbx_last_error(mpHandle) << std::endl;
-        return -1;
+        // -1 means "empty image" to the callers (src/ORBextractor.cc:1129): a missing device, a failed allocation or a CUDA error
+        // must not look like a blank frame.  The reference has no recoverable error path either, so this throws.
+        const std::string msg = std::string("[ORBextractor/orbx] ") + what + " failed: " + orbx_last_error(mpHandle);
+        std::cerr << msg << std::endl;
+        throw std::runtime_error(msg);
     }
 
     std::vector<float> Param(int which)
     {
+        if(!mpHandle)
+            Fail("orbx_params (no device handle)");
         std::vector<float> v[4];
         for(auto& x : v) x.resize(nlevels);
         orbx_params(mpHandle, v[0].data(), v[1].data(), v[2].data(), v[3].data(), nullptr);

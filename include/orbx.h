@@ -60,7 +60,10 @@ int orbx_params(const orbx_extractor *ex, float *scale_factors, float *inv_scale
  * (src/ORBextractor.cc:1125-1207) for one HOST image (8-bit, 1 channel, `step` bytes per row).
  * rects_xywh = mvDynamicArea (include/ORBextractor.h:84) as n_rects×{x,y,w,h} in level-0 pixels;
  * lap0/lap1 = vLappingArea[0..1].  Writes *n_out keypoints (28-byte records) and *n_out×32 descriptor
- * bytes into caller buffers of capacity `cap` rows; *mono_index = the reference's return value. */
+ * bytes into caller buffers of capacity `cap` rows; *mono_index = the reference's return value.
+ * This is the latency path (one call per frame, src/Frame.cc:420-427): the image is staged through page-locked memory owned
+ * by the handle, all outputs return in one copy, the call synchronises once, and from the third call with the same (rows,
+ * cols, cap) the copies and kernels replay as one CUDA graph (ORBX_NO_GRAPH in the environment keeps eager launches). */
 int orbx_extract(orbx_extractor *ex, const uint8_t *image, int rows, int cols, size_t step,
                  const int32_t *rects_xywh, int n_rects, int lap0, int lap1, orbx_keypoint *keypoints,
                  uint8_t *descriptors, int cap, int *n_out, int *mono_index);
@@ -73,6 +76,12 @@ int orbx_extract_batch(orbx_extractor *ex, const uint8_t *const *images, int bat
                        size_t step, const int32_t *rects_xywh, int n_rects, int lap0, int lap1,
                        orbx_keypoint *keypoints, uint8_t *descriptors, int cap, int32_t *n_out,
                        int32_t *mono_index);
+
+/* Measurement aid for the call above: moves exactly the bytes orbx_extract_batch moves (the frames in, cap-strided
+ * keypoint and descriptor arrays out) over the same streams with the same chunking, and launches no kernel.  The outputs
+ * are undefined.  bench.py reports the result as the transfer ceiling of the host path. */
+int orbx_copy_only_batch(orbx_extractor *ex, const uint8_t *const *images, int batch, int rows, int cols, size_t step,
+                         orbx_keypoint *keypoints, uint8_t *descriptors, int cap);
 
 /* Device-resident batch: d_images = `batch` frames already in HBM (frame b at d_images + b*frame_stride,
  * rows of `step` bytes); outputs are DEVICE buffers of the same shapes as above.  Runs asynchronously on
@@ -139,6 +148,9 @@ int orbx_hamming_knn2_device(orbx_matcher *m, const uint8_t *d_query, int nq, co
  * the global top-2 by lexicographic (dist, idx) order — equals the unsharded result bit for bit. */
 int orbx_knn2_merge_device(orbx_matcher *m, const int32_t *d_idx_all, const int32_t *d_dist_all,
                            int n_shards, int nq, int32_t *d_idx, int32_t *d_dist);
+/* Same for PACKED per-shard records: shard g holds {idx[nq×2], dist[nq×2]} back to back (4·nq int32), which is what ONE
+ * all-gather of the per-shard result moves when orbx_hamming_knn2_device wrote d_idx = rec, d_dist = rec + 2·nq. */
+int orbx_knn2_merge_packed_device(orbx_matcher *m, const int32_t *d_packed_all, int n_shards, int nq, int32_t *d_idx, int32_t *d_dist);
 /* Frame.cc:1085: keep[i] = (two neighbours) && (float)d0 < (float)d1 * ratio(double).  HOST / DEVICE buffers. */
 int orbx_ratio_test(orbx_matcher *m, const int32_t *dist, int nq, double ratio, uint8_t *keep);
 int orbx_ratio_test_device(orbx_matcher *m, const int32_t *d_dist, int nq, double ratio, uint8_t *d_keep);

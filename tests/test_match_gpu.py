@@ -144,6 +144,20 @@ def test_large_db_properties(orbx_mod, oracle_mod):
     assert np.array_equal(idx[sample], ridx) and np.array_equal(dist[sample], rdist)
 
 
+def test_config4_full_size_vs_oracle(orbx_mod, oracle_mod):
+    """BASELINE config 4 at its stated size: 2000 queries × 10 M descriptors (320 MB), k = 2, ratio 0.7 — every index, every
+    distance and every ratio decision equals the oracle's full scan on all host cores."""
+    from dani_slam_b200 import synth
+    nq, ndb = 2000, 10_000_000
+    q, db = synth.knn_case(nq, ndb, seed=1234, planted_frac=0.01, dup_rows=4)
+    m = orbx_mod.ORBmatcher(0.7, True)
+    idx, dist = m.knnMatch(q, db)
+    ridx, rdist = oracle_mod.knn2(q, db, nthreads=os.cpu_count() or 8)
+    assert np.array_equal(idx, ridx) and np.array_equal(dist, rdist)
+    assert np.array_equal(m.ratio_test(dist, 0.7), oracle_mod.ratio_test(rdist, 0.7))
+    assert (dist[:20, 0] <= 40).all() and m.ratio_test(dist, 0.7)[:20].all()   # planted queries find their rows and pass the ratio test
+
+
 def _init_case(n1, n2, seed, dense):
     """Two keypoint sets where set 1 holds noisy copies of set-2 descriptors; candidate lists overlap heavily
     so that train keypoints get locked and stolen (src/ORBmatcher.cc:683-710)."""

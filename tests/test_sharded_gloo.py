@@ -40,10 +40,11 @@ def _worker(rank, world, port, ndb, out):
         def local_top2(qq, shard, base):
             i, d = oracle.knn2(qq, shard)
             i = np.where(i >= 0, i + base, -1).astype(np.int32)
-            return torch.from_numpy(i), torch.from_numpy(d)
+            return torch.from_numpy(np.stack([i, d.astype(np.int32)]))     # the packed record [2, nq, 2]
 
-        def merge(ia, da):
-            i, d = _merge_np(ia.numpy(), da.numpy())
+        def merge(rec_all):
+            a = rec_all.numpy()
+            i, d = _merge_np(a[:, 0], a[:, 1])
             return torch.from_numpy(i), torch.from_numpy(d)
 
         idx, dist = sharded.sharded_knn2(q, db[lo:hi], lo, local_top2, merge)
