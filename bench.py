@@ -542,9 +542,12 @@ def main():
         mstream = torch.cuda.ExternalStream(sm.m.stream(), device=dev)
         group = None
 
+        if dist_on:
+            sm.init_comm()                       # orbx_comm over NCCL: the collective runs inside the C ABI (orbx_knn2_sharded)
+
         def step_match():
             if dist_on:
-                return sm.knn2(d_q, d_db, lo, group)
+                return sm.knn2_cabi(d_q, d_db, lo)
             rec = sm.local_top2(d_q, d_db, lo)
             return rec[0], rec[1]
 
@@ -589,7 +592,7 @@ def main():
         popc_peak = float(pk.get("popc_lanes_per_clk_per_sm", 16.0)) * float(pk.get("sm_count", 148)) * 1e6 * float(clocks.get("sm_max_mhz") or 1965.0)
         match = {"metric": "hamming_knn2_gpairs_per_s", "value": gpairs, "unit": "Gpairs/s", "nq": nq, "ndb": ndb,
                  "scaling": "strong", "ms_per_step": ms_m / Km, "steps": Km,
-                 "collective": "one all_gather of the packed per-shard top-2 record (nq*2*2 int32 = 32 KB per rank)" if dist_on else None,
+                 "collective": "orbx_knn2_sharded (C ABI): one ncclAllGather of the packed per-shard top-2 record (nq*2*2 int32 = 32 KB per rank)" if dist_on else None,
                  "parity": parity,
                  "parity_note": "sharded result of every rank == rank 0's unsharded scan of the whole DB (indices and distances)" if dist_on else
                                 "single GPU: see cpu_baseline.sample and tests/test_match_gpu.py::test_config4_full_size_vs_oracle",

@@ -18,6 +18,7 @@
 // -fmad=false), so results are bit-identical to the CPU oracle.  No tensor cores: no stage is a
 // dense contraction.  The 19-px REFLECT_101 border of mvImagePyramid is never read by this path
 //  and is materialised lazily on the host by orbx_get_pyramid.
+#include <cuda.h>            // CUtensorMap (the encoder itself is fetched through cudaGetDriverEntryPoint: no libcuda link dependency)
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -95,7 +96,7 @@ struct PyrArgs {             // everything by value: no dependent global loads b
     int tilesX, srcRows, srcPitch;   // shared-memory source tile: srcRows × srcPitch bytes (pitch multiple of 16)
 };
 __global__ void __launch_bounds__(256) k_pyr_level(PyrArgs a) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    extern __shared__ __align__(128) uint8_t smem_raw[];
     uint8_t *T = smem_raw;                                                        // source tile
     uint16_t (*H)[PYR_TW] = reinterpret_cast<uint16_t (*)[PYR_TW]>(smem_raw + a.srcRows * a.srcPitch);   // horizontal sums
     const int b = blockIdx.y;
@@ -193,17 +194,18 @@ __global__ void __launch_bounds__(256) k_pyr_level(PyrArgs a) {
 // for all 16 arcs.  A lane owns 4 horizontally adjacent pixels (two u16x2 pairs); ring samples are
 // carved out of three aligned 32-bit shared-memory words per row with PRMT.
 // ------------------------------------------------------------------------------------------------
-#define FAST_BOTH_CAP 256   // two-sided pixels wait here; flushed (B side evaluated) whenever fewer than 128 slots remain
 struct FastSmem {
     int roiPitch, scorePitch;
     int roiOff, scoreOff, listOff, queueOff, total;     // v1 kernel
-    int entryOff, bothOff, total2, qCap;                // two-phase kernel (qCap = entries the queue holds)
+    int entryOff, maskOff, barOff, total2, qCap;        // two-phase kernel (qCap = entries the queue holds)
 };
 __host__ __device__ inline FastSmem fast_smem_layout(int maxCw, int maxCh, int maxSlotCap) {
     FastSmem s;
     const int G = (maxCw - 6 + 3) / 4;      // 4-pixel groups per interior row
-    s.roiPitch = 4 * G + 8;                 // ROI column x lives at byte x+1; a group reads bytes 4g..4g+11
-    s.scorePitch = 4 * G + 8;               // interior column c lives at byte c+4
+    // ROI column x lives at byte x+1; a group reads bytes 4g..4g+11.  The pitch is a multiple of 16 bytes so that a TMA box
+    // (inner extent = pitch) can fill the ROI.
+    s.roiPitch = (4 * G + 8 + 15) & ~15;
+    s.scorePitch = s.roiPitch;              // interior column c lives at byte c+4
     s.roiOff = 0;
     s.scoreOff = s.roiOff + s.roiPitch * maxCh;
     s.listOff = s.scoreOff + s.scorePitch * (maxCh - 6 + 2);
@@ -215,9 +217,36 @@ __host__ __device__ inline FastSmem fast_smem_layout(int maxCw, int maxCh, int m
     const int nPix = 4 * G * (maxCh - 6);
     s.qCap = (nPix / 2 + 1) & ~1;
     s.entryOff = (s.listOff + 3) & ~3;
-    s.bothOff = s.entryOff + 2 * s.qCap + 4;
-    s.total2 = (s.bothOff + 2 * FAST_BOTH_CAP + 15) & ~15;
+    s.maskOff = s.entryOff + 2 * s.qCap + 4;             // one pass-mask byte per 4-pixel group, padded to 128 groups per lane quartet
+    s.barOff = (s.maskOff + G * (maxCh - 6) + 128 + 7) & ~7;   // the warp's mbarrier (TMA completion)
+    s.total2 = (s.barOff + 8 + 127) & ~127;              // slots are 128-byte aligned (TMA destination)
     return s;
+}
+
+// ---- TMA (cp.async.bulk.tensor) + mbarrier helpers: one elected lane issues a box load, the warp waits on the barrier ----
+struct OrbxTmaMaps { CUtensorMap m[ORBX_MAX_LEVELS]; };   // one rank-3 map (x bytes, y rows, frame) per pyramid level
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "ORBX_MBAR_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra ORBX_MBAR_DONE_%=;\n"
+        "bra ORBX_MBAR_WAIT_%=;\n"
+        "ORBX_MBAR_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y, int z) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
 }
 
 struct Row3 { uint32_t w0, w1, w2; };
@@ -426,7 +455,7 @@ __device__ void fast_cell_v1(const ExParams &p, int maxSlotCap, int c, int b, ui
 // every cell of the cell table (ORBX_FAST_V1=1: cross-check of the two-phase kernel)
 template <int WPB>
 __global__ void __launch_bounds__(WPB * 32) k_fast_cells_v1(ExParams p, int maxSlotCap) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    extern __shared__ __align__(128) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c = blockIdx.x * WPB + warp, b = blockIdx.y;
     if (c >= p.g->nCellsTotal) return;  // warps are independent: no block-level barrier
@@ -436,7 +465,7 @@ __global__ void __launch_bounds__(WPB * 32) k_fast_cells_v1(ExParams p, int maxS
 // whose warps stride over the list, so that the usual empty list costs one short launch
 template <int WPB>
 __global__ void __launch_bounds__(WPB * 32) k_fast_cells_v1_list(ExParams p, int maxSlotCap, const int2 *list, const int *count) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    extern __shared__ __align__(128) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t *base = smem_raw + (size_t)warp * fast_smem_layout(p.g->maxCw, p.g->maxCh, maxSlotCap).total;
     const int n = *count;
@@ -470,13 +499,18 @@ __device__ __forceinline__ uint32_t fast_window_minmax(const uint32_t (&r)[16]) 
     return __vminu2(lo, nmx[15]);
 }
 
-// exact measure for the entries of q[0..nE): writes max(M_side - t, 0) into the score map.  PUSH: compact the
-// offsets of the non-zero results, in order, into q itself (in place: position <= entries consumed) and return
-// their count.  Entry: bits 0-13 ROI byte offset of the pixel, bit 14 "other side already in the map", bit 15 side.
+// exact measure for the entries of q[0..nE): writes max(M - t, 0) into the score map.  PUSH: compact the offsets of the
+// non-zero results, in order, into q itself (in place: position <= entries consumed) and return their count.
+// Entry: bits 0-13 ROI byte offset of the pixel, bit 15 side (0: the darker-ring side A, 1: the brighter-ring side B; a pixel
+// that passes the compass test on both sides comes as side A).  In x-space (x = r for side A, 255 - r for side B, same for
+// the centre) both sides are "centre minus the smallest 9-window maximum", and the OTHER side's compass bound is
+// min(max(x0,x8), max(x4,x12)) - centre: the rare pixel where that also exceeds t gets the other side evaluated too (a
+// warp-uniform branch) and keeps the larger measure, which is the two-sided FAST score.
 template <bool PUSH>
 __device__ __forceinline__ int fast_exact_entries(const uint8_t *roi, uint8_t *score, uint16_t *q, int nE, int rp, uint32_t biasT2, int lane) {
     int nN = 0;
     const int rp2 = 2 * rp, rp3 = 3 * rp;
+    const uint32_t kT = 0x80ff80ffu - biasT2;         // (0x8000 - t - 1) per half
     for (int i0 = 0; i0 < nE; i0 += 64) {
         // lane i takes entries i0+i and i0+32+i: the 32 entries one LDS serves are consecutive in row-major order
         // (they span ~3 ROI rows), which keeps shared-memory bank conflicts low
@@ -499,13 +533,20 @@ __device__ __forceinline__ int fast_exact_entries(const uint8_t *roi, uint8_t *s
 #undef ORBX_RING
         const uint32_t lo = fast_window_minmax(r);
         const uint32_t M = (v2 + 0x01000100u) - lo;              // M_side + 256 per half, in [1, 511]
-        const uint32_t val2 = __vmaxu2(M, biasT2) - biasT2;      // max(M_side - t, 0)
-        uint32_t val0 = val2 & 0xffffu, val1 = val2 >> 16;
-        uint8_t *s0 = score + o0 - rp2, *s1 = score + o1 - rp2;  // score pitch == ROI pitch, two rows up
-        if (e0 & 0x4000u) val0 = max(val0, (uint32_t)*s0);
-        if (e1 & 0x4000u) val1 = max(val1, (uint32_t)*s1);
-        if (ok0) *s0 = (uint8_t)val0;
-        if (ok1) *s1 = (uint8_t)val1;
+        uint32_t val2 = __vmaxu2(M, biasT2) - biasT2;            // max(M_side - t, 0)
+        // the other side's compass bound: bit 15 of a half ⇔ bound > t
+        const uint32_t two = ((__vminu2(__vmaxu2(r[0], r[8]), __vmaxu2(r[4], r[12])) + kT) - v2) & 0x80008000u;
+        if (__any_sync(0xffffffffu, two != 0)) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) r[k] ^= 0x00ff00ffu;    // 255 - x per half
+            const uint32_t lo2 = fast_window_minmax(r);
+            const uint32_t M2 = ((v2 ^ 0x00ff00ffu) + 0x01000100u) - lo2;
+            const uint32_t alt = (__vmaxu2(M2, biasT2) - biasT2) & ((two >> 15) * 0xffffu);
+            val2 = __vmaxu2(val2, alt);
+        }
+        const uint32_t val0 = val2 & 0xffffu, val1 = val2 >> 16;
+        if (ok0) score[o0 - rp2] = (uint8_t)val0;                // score pitch == ROI pitch, two rows up
+        if (ok1) score[o1 - rp2] = (uint8_t)val1;
         if (PUSH) {
             const bool k0 = ok0 && val0 != 0, k1 = ok1 && val1 != 0;
             const uint32_t b0 = __ballot_sync(0xffffffffu, k0), b1 = __ballot_sync(0xffffffffu, k1);
@@ -528,11 +569,14 @@ struct FastRange {
     int tallBase, nTall, tallCw, tallCh;          // tall cells
     int tallSlots, nTallBlocks;
     int2 *denseList; int *denseN;                 // (frame, cell) pairs whose candidates overflow the entry queue
+    int useTma;                                   // ROI staging by TMA box loads (maps[level], box = ROI pitch × the level's cell height)
+    int boxRows[ORBX_MAX_LEVELS];                 // box height of each level's map
 };
-template <int WPB>
-__global__ void __launch_bounds__(WPB * 32, 2048 / (WPB * 32 * 2)) k_fast_cells(ExParams p, FastRange R) {   // ≤ 64 registers: 32 warps per SM
+// RP: compile-time ROI pitch (0 = take it from the layout at run time); the usual cells need 48 or 64 bytes per row
+template <int WPB, int RP>
+__global__ void __launch_bounds__(WPB * 32, 2048 / (WPB * 32 * 2)) k_fast_cells(ExParams p, const __grid_constant__ FastRange R, const __grid_constant__ OrbxTmaMaps maps) {   // ≤ 64 registers: 32 warps per SM
 
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    extern __shared__ __align__(128) uint8_t smem_raw[];
     const OrbxGeom &g = *p.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
@@ -555,7 +599,7 @@ __global__ void __launch_bounds__(WPB * 32, 2048 / (WPB * 32 * 2)) k_fast_cells(
     uint8_t *roi = base + L.roiOff;
     uint8_t *score = base + L.scoreOff;
     uint16_t *queue = reinterpret_cast<uint16_t *>(base + L.entryOff);
-    uint16_t *both = reinterpret_cast<uint16_t *>(base + L.bothOff);
+    uint8_t *gmask = base + L.maskOff;
 
     int pitch;
     const uint8_t *img = level_ptr(p, g, cell.level, b, pitch);
@@ -566,8 +610,18 @@ __global__ void __launch_bounds__(WPB * 32, 2048 / (WPB * 32 * 2)) k_fast_cells(
         if (lane == 0) *cntOut = 0;
         return;
     }
-    const int rp = L.roiPitch;   // == score pitch
+    const int rp = RP ? RP : L.roiPitch;   // == score pitch
     // stage the ROI: column x at byte x+1 so that every 4-pixel group is word aligned
+    uint64_t *bar = reinterpret_cast<uint64_t *>(base + L.barOff);
+    if (R.useTma) {
+        // one TMA box per cell: rp bytes × the level's cell height starting at (x0 - 1, y0) of frame b; bytes beyond the ROI (and
+        // beyond the image: zero-filled) are never read.  The zeroing of the score map below overlaps the transfer.
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            mbar_expect_tx(bar, (uint32_t)(rp * R.boxRows[cell.level]));
+            tma_load_3d(roi, &maps.m[cell.level], bar, cell.x0 - 1, cell.y0, b);
+        }
+    } else {
     const uint8_t *src = img + (long long)cell.y0 * pitch + cell.x0;
     if (((((unsigned long long)img) | (unsigned)pitch) & 3ull) == 0) {
         // aligned 32-bit loads: shared-memory word k of a row holds image columns x0-1+4k .. x0+2+4k, i.e. the two
@@ -592,6 +646,7 @@ __global__ void __launch_bounds__(WPB * 32, 2048 / (WPB * 32 * 2)) k_fast_cells(
         for (int y = 0; y < ch; ++y)
             for (int x = lane; x < cw; x += 32) roi[y * rp + x + 1] = src[(long long)y * pitch + x];
     }
+    }
     // zero the score map: pixels that never pass the compass test and the 1-px frame ("outside the cell interior
     // counts 0") must read 0 in the NMS
     {
@@ -600,6 +655,7 @@ __global__ void __launch_bounds__(WPB * 32, 2048 / (WPB * 32 * 2)) k_fast_cells(
         for (int i = lane; i < nw; i += 32) s32[i] = 0;
     }
     __syncwarp();
+    if (R.useTma) mbar_wait(bar, 0);         // the ROI has landed (the barrier completes its first phase)
 
     const int G = (iw + 3) >> 2;             // 4-pixel groups per interior row (≤ 19 for cells ≤ 75 px wide)
     const int nGroups = G * ih;              // groups of the cell in row-major order: lane work items
@@ -609,6 +665,7 @@ __global__ void __launch_bounds__(WPB * 32, 2048 / (WPB * 32 * 2)) k_fast_cells(
     const int rp3 = 3 * rp;
     const int stepRows = 32 / G, stepGroups = 32 - stepRows * G;          // 32 groups further on
     const int stepOff = stepRows * rp + 4 * stepGroups, wrapOff = rp - 4 * G;
+    const int K = (((nGroups + 31) >> 5) + 1) & ~1;                        // groups per lane in phase 1b (even: the count pass reads pairs)
     const int nValidLast = iw - 4 * (G - 1);                               // valid pixels of a row's last group (1..4)
     const uint32_t lastMask = nValidLast >= 4 ? 0x80808080u : (0x80808080u & ((1u << (8 * nValidLast)) - 1u));
     uint32_t *out = p.slots + (long long)b * g.slotsTotal + cell.slot;
@@ -621,72 +678,84 @@ __global__ void __launch_bounds__(WPB * 32, 2048 / (WPB * 32 * 2)) k_fast_cells(
         const uint32_t biasT2 = (uint32_t)(256 + t) * 0x10001u;
         const uint32_t kT = (uint32_t)(0x8000 - t - 1) * 0x10001u;
 
-        // phase 1: compass test, entries in row-major pixel order.  Lane state (lg, off) of group gi = i0 + lane is
-        // advanced incrementally: +32 groups = +stepRows rows and +stepGroups groups, with one conditional row wrap.
-        int nE = 0, nB = 0;
-        int lg = lane - (int)(((uint32_t)lane * rcpG) >> 16) * G;
-        int off = ((int)(((uint32_t)lane * rcpG) >> 16) + 3) * rp + 4 * lg + 4;    // ROI byte of the group's first pixel
-        for (int i0 = 0; i0 < nGroups; i0 += 32) {
-            if (nB > FAST_BOTH_CAP - 128) {           // warp-uniform: make room for this iteration's two-sided pixels
-                __syncwarp();
-                fast_exact_entries<false>(roi, score, both, nB, rp, biasT2, lane);
-                __syncwarp();
-                nB = 0;
-            }
-            uint32_t pm = 0, tq = 0, bo = 0;     // per pixel i: bit 8i+7 (pass / side B) and 8i+6 (two-sided)
-            if (i0 + lane < nGroups) {
-                const uint8_t *cp = roi + off;
-                Row3 Cn = ld_row3(cp - 4), Tp, Bt;
-                Tp.w1 = *reinterpret_cast<const uint32_t *>(cp - rp3);
-                Bt.w1 = *reinterpret_cast<const uint32_t *>(cp + rp3);
-                Tp.w0 = Tp.w2 = Bt.w0 = Bt.w2 = 0;
-                uint32_t XA[2], XB[2];
+        // phase 1a: compass test of every 4-pixel group; the pass bits (low nibble: side A of pixels 0-3, high nibble: side B) go
+        // to one byte per group, nothing is compacted here.  Lane state (lg, off) of group gi = i0 + lane is advanced
+        // incrementally: +32 groups = +stepRows rows and +stepGroups groups, with one conditional row wrap.
+        {
+            int lg = lane - (int)(((uint32_t)lane * rcpG) >> 16) * G;
+            int off = ((int)(((uint32_t)lane * rcpG) >> 16) + 3) * rp + 4 * lg + 4;    // ROI byte of the group's first pixel
+            for (int i0 = 0; i0 < nGroups; i0 += 32) {
+                if (i0 + lane < nGroups) {
+                    const uint8_t *cp = roi + off;
+                    Row3 Cn = ld_row3(cp - 4), Tp, Bt;
+                    Tp.w1 = *reinterpret_cast<const uint32_t *>(cp - rp3);
+                    Bt.w1 = *reinterpret_cast<const uint32_t *>(cp + rp3);
+                    Tp.w0 = Tp.w2 = Bt.w0 = Bt.w2 = 0;
+                    uint32_t XA[2], XB[2];
 #pragma unroll
-                for (int P = 0; P < 2; ++P) {
-                    const uint32_t v2 = P ? pair_at<6>(Cn) : pair_at<4>(Cn);
-                    const uint32_t r0 = P ? pair_at<6>(Bt) : pair_at<4>(Bt), r8 = P ? pair_at<6>(Tp) : pair_at<4>(Tp);
-                    const uint32_t r4 = P ? pair_at<9>(Cn) : pair_at<7>(Cn), r12 = P ? pair_at<3>(Cn) : pair_at<1>(Cn);
-                    const uint32_t hiMin = __vmaxu2(__vminu2(r0, r8), __vminu2(r4, r12));   // A-side bound: v - hiMin
-                    const uint32_t loMax = __vminu2(__vmaxu2(r0, r8), __vmaxu2(r4, r12));   // B-side bound: loMax - v
-                    XA[P] = (v2 + kT) - hiMin;       // bit 15 of a half ⇔ bound > t (no borrow crosses the halves)
-                    XB[P] = (loMax + kT) - v2;
+                    for (int P = 0; P < 2; ++P) {
+                        const uint32_t v2 = P ? pair_at<6>(Cn) : pair_at<4>(Cn);
+                        const uint32_t r0 = P ? pair_at<6>(Bt) : pair_at<4>(Bt), r8 = P ? pair_at<6>(Tp) : pair_at<4>(Tp);
+                        const uint32_t r4 = P ? pair_at<9>(Cn) : pair_at<7>(Cn), r12 = P ? pair_at<3>(Cn) : pair_at<1>(Cn);
+                        const uint32_t hiMin = __vmaxu2(__vminu2(r0, r8), __vminu2(r4, r12));   // A-side bound: v - hiMin
+                        const uint32_t loMax = __vminu2(__vmaxu2(r0, r8), __vmaxu2(r4, r12));   // B-side bound: loMax - v
+                        XA[P] = (v2 + kT) - hiMin;       // bit 15 of a half ⇔ bound > t (no borrow crosses the halves)
+                        XB[P] = (loMax + kT) - v2;
+                    }
+                    const uint32_t colMask = lg == G - 1 ? lastMask : 0x80808080u;
+                    const uint32_t pA = __byte_perm(XA[0], XA[1], 0x7531u) & colMask;   // high bytes of the four halves: px0..px3
+                    const uint32_t pB = __byte_perm(XB[0], XB[1], 0x7531u) & colMask;
+                    // bits 7, 15, 23, 31 → one nibble: (x >> 7) · (1 + 2^7 + 2^14 + 2^21) lines them up at bits 21-24 without carries
+                    const uint32_t nA = (((pA >> 7) * 0x00204081u) >> 21) & 0xfu, nB4 = (((pB >> 7) * 0x00204081u) >> 17) & 0xf0u;
+                    gmask[i0 + lane] = (uint8_t)(nA | nB4);
                 }
-                const uint32_t colMask = lg == G - 1 ? lastMask : 0x80808080u;
-                const uint32_t pA = __byte_perm(XA[0], XA[1], 0x7531u);       // high bytes of the four halves: px0..px3
-                const uint32_t pB = __byte_perm(XB[0], XB[1], 0x7531u);
-                pm = (pA | pB) & colMask;
-                bo = pA & pB & colMask;
-                tq = (pm & ~pA) | (bo >> 1);         // entry flag bits of pixel i at 8i+7 (side) and 8i+6 (two-sided)
+                lg += stepGroups; off += stepOff;
+                if (lg >= G) { lg -= G; off += wrapOff; }
             }
-            const int cnt = __popc(pm);
-            const uint32_t b0 = __ballot_sync(0xffffffffu, cnt & 1), b1 = __ballot_sync(0xffffffffu, cnt & 2), b2 = __ballot_sync(0xffffffffu, cnt & 4);
-            const int nNew = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
-            if (nE + nNew > L.qCap) { dense = true; break; }      // warp-uniform: more corners than the queue holds
-            uint16_t *qa = queue + nE + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
-            if (pm & 0x80u) *qa++ = (uint16_t)((uint32_t)off | ((tq << 8) & 0xc000u));
-            if (pm & 0x8000u) *qa++ = (uint16_t)((uint32_t)(off + 1) | (tq & 0xc000u));
-            if (pm & 0x800000u) *qa++ = (uint16_t)((uint32_t)(off + 2) | ((tq >> 8) & 0xc000u));
-            if (pm & 0x80000000u) *qa = (uint16_t)((uint32_t)(off + 3) | ((tq >> 16) & 0xc000u));
-            nE += nNew;
-            if (__any_sync(0xffffffffu, bo != 0)) {   // rare: pixels that pass on both sides get their B side done first
-                const int cb = __popc(bo);
-                const uint32_t c0 = __ballot_sync(0xffffffffu, cb & 1), c1 = __ballot_sync(0xffffffffu, cb & 2), c2 = __ballot_sync(0xffffffffu, cb & 4);
-                int ab = nB + __popc(c0 & lt) + 2 * __popc(c1 & lt) + 4 * __popc(c2 & lt);
+            for (int i = nGroups + lane; i < 32 * K; i += 32) gmask[i] = 0;       // padding groups of the last lanes
+        }
+        __syncwarp();
+        // phase 1b: every passing pixel becomes one queue entry, in row-major pixel order.  Each lane owns K consecutive groups,
+        // so one warp scan of the per-lane counts places everything.
+        int nE = 0;
+        {
+            const int g0 = min(lane * K, nGroups), g1 = min(g0 + K, nGroups);
+            int cnt = 0;
+            {
+                const uint16_t *gw = reinterpret_cast<const uint16_t *>(gmask) + lane * (K >> 1);   // K is even
+                for (int w = 0; w < (K >> 1); ++w) {
+                    const uint32_t mk2 = gw[w];                                    // two groups at a time
+                    cnt += __popc((mk2 | (mk2 >> 4)) & 0x0f0fu);
+                }
+            }
+            int incl = cnt;
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if ((bo >> (8 * i + 7)) & 1u) both[ab++] = (uint16_t)((uint32_t)(off + i) | 0x8000u);
-                nB += __popc(c0) + 2 * __popc(c1) + 4 * __popc(c2);
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
             }
-            lg += stepGroups; off += stepOff;
-            if (lg >= G) { lg -= G; off += wrapOff; }
+            nE = __shfl_sync(0xffffffffu, incl, 31);
+            if (nE > L.qCap) { dense = true; break; }             // warp-uniform: more corners than the queue holds
+            uint16_t *qa = queue + (incl - cnt);
+            const int yi0 = (int)(((uint32_t)g0 * rcpG) >> 16);
+            int lg = g0 - yi0 * G;
+            uint32_t off = (uint32_t)((yi0 + 3) * rp + 4 * lg + 4);
+            for (int gq = g0; gq < g1; ++gq) {
+                const uint32_t mk = gmask[gq];
+                if (mk) {
+                    const uint32_t any = mk | (mk >> 4);
+                    const uint32_t sideB = ~mk << 15;             // bit 15+i set: pixel i does not pass on side A (so it is a side-B entry)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if ((any >> i) & 1u) *qa++ = (uint16_t)((off + i) | ((sideB >> i) & 0x8000u));
+                }
+                ++lg; off += 4;
+                if (lg == G) { lg = 0; off += (uint32_t)wrapOff; }
+            }
         }
         if (dense) break;
         __syncwarp();
-        // phase 2: exact measure of the entries (B sides of two-sided pixels first, then everything else)
-        if (nB > 0) {
-            fast_exact_entries<false>(roi, score, both, nB, rp, biasT2, lane);
-            __syncwarp();
-        }
+        // phase 2: exact measure of the entries
         const int nN = fast_exact_entries<true>(roi, score, queue, nE, rp, biasT2, lane);
         __syncwarp();
         // phase 3: cell-local 3×3 strict NMS of the corners, survivors in row-major order straight to the slots
@@ -833,7 +902,7 @@ __device__ __forceinline__ void qt_for_points(const uint32_t *ptNode, const floa
 // FAST score (bits 23:16) | quadrant scratch (bits 31:30), or ORBX_NODE_ERASED.
 template <int NT>
 __global__ void __launch_bounds__(NT) k_quadtree(ExParams p, int nodeCapMax, int maxCellsLevel, const int *onlyFlagged) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    extern __shared__ __align__(128) uint8_t smem_raw[];
     const OrbxGeom &g = *p.g;
     const int l = blockIdx.x, b = blockIdx.y;
     if (onlyFlagged && !onlyFlagged[b * g.nlevels + l]) return;   // the histogram kernel already produced this (frame, level)
@@ -1165,7 +1234,7 @@ struct QtTables {               // per-handle device tables of the fast path (in
 
 template <int NT>
 __global__ void __launch_bounds__(NT) k_qt_prefix(ExParams p, QtTables t, int maxCellsLevel) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    extern __shared__ __align__(128) uint8_t smem_raw[];
     int *prefix = reinterpret_cast<int *>(smem_raw);
     int *scratch = prefix + maxCellsLevel + 1;
     const OrbxGeom &g = *p.g;
@@ -1279,7 +1348,7 @@ __global__ void __launch_bounds__(128) k_qt_classify(ExParams p, QtTables t) {
 
 template <int NT>
 __global__ void __launch_bounds__(NT) k_qt_nodes(ExParams p, QtTables t, int nodeCapMax) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    extern __shared__ __align__(128) uint8_t smem_raw[];
     const OrbxGeom &g = *p.g;
     const int l = blockIdx.x, b = blockIdx.y;
     const OrbxLevel &LV = g.lv[l];
@@ -1960,6 +2029,7 @@ struct orbx_extractor {
     int oneRows = -1, oneCols = -1, oneCap = -1, oneWarm = 0;
     long long oneLaunches = 0;
     bool useGraph = true;
+    bool useTma = true;             // ORBX_NO_TMA: stage tiles with ordinary loads (same results; cross-check and fallback)
 
     // device buffers (sized for maxW × maxH × maxBatch at create)
     OrbxGeom *d_geom = nullptr;
@@ -2265,6 +2335,33 @@ int prepare(orbx_extractor *ex, int rows, int cols, const int32_t *rects, int nR
     return ensure_buffers(ex, batch);
 }
 
+// ---- TMA tensor maps (host): cuTensorMapEncodeTiled through the runtime's driver entry point ----
+typedef CUresult (*PFN_orbxTmaEncode)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                      const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_orbxTmaEncode tma_encoder() {
+    static PFN_orbxTmaEncode fn = [] {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); f = nullptr; }
+        return (PFN_orbxTmaEncode)f;
+    }();
+    return fn;
+}
+// rank-3 u8 map (x bytes, y rows, frame) over `batch` planes of w×h bytes with the given row pitch and plane stride, box = boxW × boxH × 1.
+// false when the layout does not meet TMA's rules (16-byte aligned base, pitch and stride; box ≤ 256 per dimension): the caller then
+// stages with ordinary loads.
+bool tma_encode_level(CUtensorMap *out, const void *base, int w, int h, int batch, long long pitch, long long planeStride, int boxW, int boxH) {
+    PFN_orbxTmaEncode fn = tma_encoder();
+    if (!fn) return false;
+    if (((uintptr_t)base & 15) || (pitch & 15) || (planeStride & 15) || (boxW & 15) || boxW < 16 || boxW > 256 || boxH < 1 || boxH > 256 || w < 1 || h < 1) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)std::max(batch, 1)};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)planeStride};
+    const cuuint32_t box[3] = {(cuuint32_t)boxW, (cuuint32_t)boxH, 1u};
+    const cuuint32_t es[3] = {1u, 1u, 1u};
+    return fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int harvest_stage_times(orbx_extractor *ex) {
     if (!ex->evPending) return ORBX_OK;
     CUDA_TRY(ex, cudaEventSynchronize(ex->ev[6]));
@@ -2344,7 +2441,7 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
             // Consecutive levels whose cells need about the same shared memory (within 20 %) form a group: the small top
             // levels have much taller cells (2 rows of cells cover the level) and would otherwise set the per-warp
             // footprint, hence the resident warps, for everybody.
-            struct Grp { int cellBase, nCells, cw, ch; size_t need; };
+            struct Grp { int cellBase, nCells, cw, ch; size_t need; int l0, l1; };
             Grp grp[ORBX_MAX_LEVELS];
             int nGrp = 0;
             for (int l0 = 0; l0 < G.nlevels;) {
@@ -2354,15 +2451,50 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
                     const OrbxLevel &V = G.lv[l1];
                     if (V.nCells <= 0) continue;
                     const size_t need = (size_t)fast_smem_layout(V.wCell + 6, V.hCell + 6, 1).total2;
-                    if (nC > 0 && (std::max(hi, need) * 5 > std::min(lo, need) * 6)) break;
+                    // (up to kFreeSlot bytes per warp the register file, not shared memory, limits the resident warps: no need to split)
+                    const size_t kFreeSlot = 7000;
+                    if (nC > 0 && std::max(hi, need) > kFreeSlot && (std::max(hi, need) * 5 > std::min(lo, need) * 6)) break;
                     lo = nC ? std::min(lo, need) : need; hi = std::max(hi, need);
                     cwMax = std::max(cwMax, V.wCell + 6); chMax = std::max(chMax, V.hCell + 6);
                     if (cellBase < 0) cellBase = V.cellBase;
                     nC += V.nCells;
                 }
-                if (nC > 0) grp[nGrp++] = Grp{cellBase, nC, cwMax, chMax, (size_t)fast_smem_layout(cwMax, chMax, 1).total2};
+                if (nC > 0) grp[nGrp++] = Grp{cellBase, nC, cwMax, chMax, (size_t)fast_smem_layout(cwMax, chMax, 1).total2, l0, l1};
                 l0 = l1;
             }
+            // ROI staging by TMA: one map per level, box = the ROI pitch of the level's group × the level's cell height.  Level 0 may be
+            // the caller's own buffer, whose pitch need not meet TMA's alignment rules: then every cell is staged with ordinary loads.
+            OrbxTmaMaps maps;
+            memset(&maps, 0, sizeof(maps));
+            int boxRows[ORBX_MAX_LEVELS] = {0};
+            bool tmaOk = ex->useTma;
+            for (int gi = 0; gi < nGrp && tmaOk; ++gi) {
+                const int rpG = fast_smem_layout(grp[gi].cw, grp[gi].ch, 1).roiPitch;
+                for (int l = grp[gi].l0; l < grp[gi].l1 && tmaOk; ++l) {
+                    const OrbxLevel &V = G.lv[l];
+                    if (V.nCells <= 0) continue;
+                    boxRows[l] = V.hCell + 6;
+                    const uint8_t *base = l == 0 ? P.in0 : P.pyr + V.off;
+                    tmaOk = tma_encode_level(&maps.m[l], base, V.w, V.h, batch, l == 0 ? P.in0Pitch : V.pitch, l == 0 ? P.in0Stride : G.frameBytes, rpG, boxRows[l]);
+                }
+            }
+            auto launch_fast = [&](FastRange R, dim3 grid, size_t smem) -> int {
+                R.useTma = tmaOk ? 1 : 0;
+                for (int l = 0; l < ORBX_MAX_LEVELS; ++l) R.boxRows[l] = boxRows[l];
+                const int rpA = fast_smem_layout(R.cw, R.ch, 1).roiPitch, rpB = R.nTall > 0 ? fast_smem_layout(R.tallCw, R.tallCh, 1).roiPitch : rpA;
+                const int rpSel = rpA == rpB ? rpA : 0;         // compile-time ROI pitch for the two usual widths
+#define ORBX_LAUNCH_FAST(RPV)                                                                                                             \
+                do {                                                                                                                      \
+                    if (smem > 48 * 1024) CUDA_TRY(ex, cudaFuncSetAttribute(k_fast_cells<WPB, RPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                    k_fast_cells<WPB, RPV><<<grid, WPB * 32, smem, s>>>(P, R, maps);                                                       \
+                } while (0)
+                if (rpSel == 48) ORBX_LAUNCH_FAST(48);
+                else if (rpSel == 64) ORBX_LAUNCH_FAST(64);
+                else ORBX_LAUNCH_FAST(0);
+#undef ORBX_LAUNCH_FAST
+                ++ex->launches;
+                return ORBX_OK;
+            };
             // the usual shape is one big group plus a small group of tall cells: one launch, tall cells on several slots
             bool merged = false;
             if (nGrp == 2 && grp[1].nCells * 8 <= grp[0].nCells) {
@@ -2370,19 +2502,15 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
                 if (slots <= WPB) {
                     FastRange R{grp[0].cellBase, grp[0].nCells, grp[0].cw, grp[0].ch, grp[1].cellBase, grp[1].nCells, grp[1].cw, grp[1].ch, slots, 0, denseList, denseN};
                     R.nTallBlocks = (grp[1].nCells + WPB / slots - 1) / (WPB / slots);
-                    const size_t smem = grp[0].need * WPB;
-                    if (smem > 48 * 1024) CUDA_TRY(ex, cudaFuncSetAttribute(k_fast_cells<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    k_fast_cells<WPB><<<dim3(R.nTallBlocks + (R.nCells + WPB - 1) / WPB, batch), WPB * 32, smem, s>>>(P, R);
-                    ++ex->launches;
+                    int rcL = launch_fast(R, dim3(R.nTallBlocks + (R.nCells + WPB - 1) / WPB, batch), grp[0].need * WPB);
+                    if (rcL) return rcL;
                     merged = true;
                 }
             }
             for (int i = 0; i < nGrp && !merged; ++i) {
                 FastRange R{grp[i].cellBase, grp[i].nCells, grp[i].cw, grp[i].ch, 0, 0, grp[i].cw, grp[i].ch, 1, 0, denseList, denseN};
-                const size_t smem = grp[i].need * WPB;
-                if (smem > 48 * 1024) CUDA_TRY(ex, cudaFuncSetAttribute(k_fast_cells<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k_fast_cells<WPB><<<dim3((R.nCells + WPB - 1) / WPB, batch), WPB * 32, smem, s>>>(P, R);
-                ++ex->launches;
+                int rcL = launch_fast(R, dim3((R.nCells + WPB - 1) / WPB, batch), grp[i].need * WPB);
+                if (rcL) return rcL;
             }
             // cells with more corner candidates than the two-phase kernel's queue holds go to the single-phase kernel
             if (G.nCellsTotal > 0) {
@@ -2617,7 +2745,8 @@ orbx_extractor *orbx_create(int nfeatures, float scale_factor, int nlevels, int 
     CREATE_TRY(cudaMemset(ex->d_dense, 0, (size_t)max_batch * sizeof(int)));
     ex->useHistQuadtree = getenv("ORBX_LEGACY_QUADTREE") == nullptr;
     ex->fastV1 = getenv("ORBX_FAST_V1") != nullptr;
-    ex->useGraph = getenv("ORBX_NO_GRAPH") == nullptr;      // same kernels either way; the graph only removes launch overhead
+    ex->useGraph = getenv("ORBX_NO_GRAPH") == nullptr;
+    ex->useTma = getenv("ORBX_NO_TMA") == nullptr;        // same kernels and results; tiles are then staged with ordinary loads      // same kernels either way; the graph only removes launch overhead
     CREATE_TRY(cudaMalloc((void **)&ex->d_nOut, (size_t)max_batch * sizeof(int)));
     CREATE_TRY(cudaMalloc((void **)&ex->d_mono, (size_t)max_batch * sizeof(int)));
     CREATE_TRY(cudaHostAlloc((void **)&ex->h_nOut, (size_t)max_batch * sizeof(int), cudaHostAllocDefault));

@@ -79,6 +79,18 @@ def lib() -> C.CDLL:
     L.orbx_knn2_merge_device.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     L.orbx_knn2_merge_packed_device.argtypes = [vp, vp, i32, i32, vp, vp]
     L.orbx_copy_only_batch.argtypes = [vp, vp, i32, i32, i32, sz, vp, vp, i32]
+    L.orbx_comm_unique_id.argtypes = [vp]
+    L.orbx_comm_create.restype = vp
+    L.orbx_comm_create.argtypes = [i32, i32, vp, i32]
+    L.orbx_comm_create_all.argtypes = [vp, i32, vp]
+    L.orbx_comm_destroy.argtypes = [vp]
+    L.orbx_comm_last_error.restype = C.c_char_p
+    L.orbx_comm_last_error.argtypes = [vp]
+    L.orbx_comm_rank.argtypes = [vp]
+    L.orbx_comm_world.argtypes = [vp]
+    L.orbx_knn2_sharded.argtypes = [vp, vp, vp, i32, vp, i64, i64, vp, vp]
+    L.orbx_knn2_sharded_all.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, vp, vp]
+    L.orbx_extract_batch_multi.argtypes = [vp, i32, vp, i32, i32, i32, sz, vp, i32, i32, i32, vp, vp, i32, vp, vp]
     L.orbx_ratio_test.argtypes = [vp, vp, i32, f64, vp]
     L.orbx_ratio_test_device.argtypes = [vp, vp, i32, f64, vp]
     L.orbx_hamming_top2_lists.argtypes = [vp, vp, i32, vp, i64, vp, vp, vp, vp, vp, vp]
@@ -467,6 +479,12 @@ class ORBmatcher:
     def merge_device(self, d_idx_all, d_dist_all, n_shards, nq, d_idx, d_dist):
         self._chk(self.L.orbx_knn2_merge_device(self.h, d_idx_all, d_dist_all, n_shards, nq, d_idx, d_dist))
 
+    def knn2_sharded(self, comm, d_q, nq, d_db_shard, ndb_shard, idx_base, d_idx, d_dist):
+        """orbx_knn2_sharded: this rank's shard scan + ONE NCCL all-gather of the packed top-2 records + merge (device pointers as ints)."""
+        rc = self.L.orbx_knn2_sharded(self.h, comm.h, d_q, nq, d_db_shard, ndb_shard, idx_base, d_idx, d_dist)
+        if rc != OK:
+            raise OrbxError(rc, self.L.orbx_comm_last_error(comm.h).decode())
+
     def merge_packed_device(self, d_packed_all, n_shards, nq, d_idx, d_dist):
         self._chk(self.L.orbx_knn2_merge_packed_device(self.h, d_packed_all, n_shards, nq, d_idx, d_dist))
 
@@ -475,6 +493,86 @@ class ORBmatcher:
 
     def stream(self):
         return self.L.orbx_matcher_stream(self.h)
+
+
+class Comm:
+    """A rank of the DB-sharded kNN's communicator (orbx_comm: NCCL, bound at run time).  One process per GPU: rank 0 calls
+    `Comm.unique_id()`, ships the 128 bytes to the others, every rank builds `Comm(world, rank, id, device)`.  One process with
+    several GPUs: `Comm.create_all(devices)`."""
+
+    def __init__(self, world=None, rank=None, uid=None, device=0, _handle=None):
+        self.L = lib()
+        if _handle is not None:
+            self.h = _handle
+            return
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(uid))
+        self.h = self.L.orbx_comm_create(int(world), int(rank), buf, int(device))
+        if not self.h:
+            raise OrbxError(ERR_CUDA, self.L.orbx_comm_last_error(None).decode())
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        rc = lib().orbx_comm_unique_id(buf)
+        if rc != OK:
+            raise OrbxError(rc, lib().orbx_comm_last_error(None).decode())
+        return bytes(buf)
+
+    @staticmethod
+    def create_all(devices):
+        L = lib()
+        devs = (C.c_int * len(devices))(*devices)
+        out = (C.c_void_p * len(devices))()
+        rc = L.orbx_comm_create_all(out, len(devices), devs)
+        if rc != OK:
+            raise OrbxError(rc, L.orbx_comm_last_error(None).decode())
+        return [Comm(_handle=out[i]) for i in range(len(devices))]
+
+    @property
+    def rank(self):
+        return self.L.orbx_comm_rank(self.h)
+
+    @property
+    def world(self):
+        return self.L.orbx_comm_world(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.orbx_comm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+
+def knn2_sharded_all(matchers, comms, d_query, nq, d_db, ndb, idx_base, d_idx, d_dist):
+    """orbx_knn2_sharded_all: one thread drives every device of the process (lists indexed by rank; device pointers as ints)."""
+    L = lib()
+    n = len(matchers)
+    arr = lambda vals: (C.c_void_p * n)(*vals)                     # noqa: E731
+    i64 = lambda vals: (C.c_int64 * n)(*vals)                      # noqa: E731
+    rc = L.orbx_knn2_sharded_all(arr([m.h for m in matchers]), arr([c.h for c in comms]), n, arr(d_query), int(nq), arr(d_db), i64(ndb), i64(idx_base),
+                                 arr(d_idx), arr(d_dist))
+    if rc != OK:
+        msg = L.orbx_comm_last_error(None).decode() or "; ".join(L.orbx_comm_last_error(c.h).decode() for c in comms)
+        raise OrbxError(rc, msg)
+
+
+def extract_batch_multi(extractors, images, cap, vLappingArea=(0, 0)):
+    """orbx_extract_batch_multi: `images` [B, H, W] uint8 split over the extractors' devices (contiguous slices, no collective)
+    → (keypoints [B, cap], descriptors [B, cap, 32], n_out [B], mono_index [B])."""
+    L = lib()
+    images = np.ascontiguousarray(images, np.uint8)
+    B, H, W = images.shape
+    n = len(extractors)
+    hs = (C.c_void_p * n)(*[e.h for e in extractors])
+    ptrs = (C.c_void_p * B)(*[images.ctypes.data + b * H * W for b in range(B)])
+    kps = np.zeros((B, cap), KP_DTYPE); desc = np.zeros((B, cap, 32), np.uint8)
+    n_out = np.zeros(B, np.int32); mono = np.zeros(B, np.int32)
+    rc = L.orbx_extract_batch_multi(hs, n, ptrs, B, H, W, W, None, 0, int(vLappingArea[0]), int(vLappingArea[1]), _p(kps), _p(desc), cap, _p(n_out), _p(mono))
+    if rc != OK:
+        raise OrbxError(rc, "; ".join(L.orbx_last_error(e.h).decode() for e in extractors))
+    return kps, desc, n_out, mono
 
 
 class ORBVocabulary:

@@ -79,3 +79,27 @@ class CudaShardedMatcher:
 
     def knn2(self, d_query, d_db_shard, shard_lo: int, group=None):
         return sharded_knn2(d_query, d_db_shard, shard_lo, self.local_top2, self.merge, group)
+
+    # ---- the C-ABI path: orbx_knn2_sharded does the scan, the NCCL all-gather and the merge inside liborbx ----
+    def init_comm(self, group=None):
+        """Builds this rank's orbx communicator; the 128-byte NCCL id travels over torch.distributed (plumbing only)."""
+        import torch.distributed as td
+        from . import orbx
+        torch = self.torch
+        rank, world = td.get_rank(group), td.get_world_size(group)
+        uid = torch.zeros(128, dtype=torch.uint8, device=self.dev)
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(orbx.Comm.unique_id()), dtype=torch.uint8))
+        td.broadcast(uid, src=0, group=group)
+        self.comm = orbx.Comm(world, rank, bytes(uid.cpu().numpy().tobytes()), self.dev.index)
+        return self.comm
+
+    def knn2_cabi(self, d_query, d_db_shard, shard_lo: int):
+        torch = self.torch
+        nq = d_query.shape[0]
+        idx = torch.empty((nq, 2), dtype=torch.int32, device=self.dev)
+        dist = torch.empty((nq, 2), dtype=torch.int32, device=self.dev)
+        self._ext.wait_stream(torch.cuda.current_stream(self.dev))
+        self.m.knn2_sharded(self.comm, d_query.data_ptr(), nq, d_db_shard.data_ptr(), d_db_shard.shape[0], shard_lo, idx.data_ptr(), dist.data_ptr())
+        torch.cuda.current_stream(self.dev).wait_stream(self._ext)
+        return idx, dist

@@ -269,6 +269,39 @@ int orbx_bow_transform_batch_device(orbx_vocab *v, const uint8_t *d_desc, size_t
                                     int levelsup, uint32_t *d_word_id, uint32_t *d_node_id, uint32_t *d_bow_ids, double *d_bow_vals,
                                     int32_t *d_n_bow, uint32_t *d_fv_nodes, int32_t *d_fv_off, uint32_t *d_fv_idx, int32_t *d_n_fv);
 
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU entry points.  Work shards with no data-path collective for frame batches, and with ONE
+ * all-gather of the per-shard top-2 records (NCCL over NVLink / NVSwitch) for the DB-sharded Hamming kNN of BASELINE config 4.
+ * NCCL is bound at run time (libnccl.so.2, or the path in ORBX_NCCL_LIB); hosts that never call these need no NCCL.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct orbx_comm orbx_comm;
+/* One process per GPU: rank 0 obtains the 128-byte id and distributes it by any means, every rank then creates its
+ * communicator on its own device.  NULL / negative on failure (orbx_comm_last_error(NULL)). */
+int orbx_comm_unique_id(uint8_t id128[128]);
+orbx_comm *orbx_comm_create(int world, int rank, const uint8_t id128[128], int device);
+/* One process driving n_devices GPUs (the C++ SLAM host): comms[i] lives on devices[i], rank i of n_devices. */
+int orbx_comm_create_all(orbx_comm **comms, int n_devices, const int *devices);
+void orbx_comm_destroy(orbx_comm *c);
+const char *orbx_comm_last_error(const orbx_comm *c);
+int orbx_comm_rank(const orbx_comm *c);
+int orbx_comm_world(const orbx_comm *c);
+/* BFMatcher.knnMatch(k=2) against a database split into contiguous index ranges over the ranks: this rank scans its shard
+ * (rows idx_base … idx_base+ndb_shard-1 of the whole database), ONE ncclAllGather moves every rank's packed top-2 record
+ * {idx[nq×2], dist[nq×2]} (32 KB at nq = 2000), and every rank merges world×2 candidates per query by (dist, global index) —
+ * bit-identical to the unsharded search, ties included.  DEVICE buffers on the matcher's device; asynchronous on the
+ * matcher's stream.  Collective: every rank of the communicator must call it with the same nq. */
+int orbx_knn2_sharded(orbx_matcher *m, orbx_comm *c, const uint8_t *d_query, int nq, const uint8_t *d_db_shard, int64_t ndb_shard, int64_t idx_base,
+                      int32_t *d_idx, int32_t *d_dist);
+/* Same for one thread that owns all n matchers / communicators of a process (arrays indexed by rank): the local scans are
+ * enqueued on every device, the n all-gathers form one NCCL group, then every device merges. */
+int orbx_knn2_sharded_all(orbx_matcher *const *ms, orbx_comm *const *cs, int n, const uint8_t *const *d_query, int nq, const uint8_t *const *d_db_shard,
+                          const int64_t *ndb_shard, const int64_t *idx_base, int32_t *const *d_idx, int32_t *const *d_dist);
+/* orbx_extract_batch over several devices: handle i (created on its own device) processes the contiguous slice
+ * [i·batch/n, (i+1)·batch/n) of the frames on its own host thread; no collective.  Arguments as orbx_extract_batch. */
+int orbx_extract_batch_multi(orbx_extractor *const *exs, int n_handles, const uint8_t *const *images, int batch, int rows, int cols, size_t step,
+                             const int32_t *rects_xywh, int n_rects, int lap0, int lap1, orbx_keypoint *keypoints, uint8_t *descriptors, int cap,
+                             int32_t *n_out, int32_t *mono_index);
+
 /* Test hook: number of (frame, level) pairs of the last batch call that the histogram quadtree kernel handed to
  * the general quadtree kernel (trees deeper than its table); -1 if the histogram kernel is disabled. */
 int orbx_debug_deep_count(orbx_extractor *ex);

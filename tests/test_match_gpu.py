@@ -155,7 +155,7 @@ def test_config4_full_size_vs_oracle(orbx_mod, oracle_mod):
     ridx, rdist = oracle_mod.knn2(q, db, nthreads=os.cpu_count() or 8)
     assert np.array_equal(idx, ridx) and np.array_equal(dist, rdist)
     assert np.array_equal(m.ratio_test(dist, 0.7), oracle_mod.ratio_test(rdist, 0.7))
-    assert (dist[:20, 0] <= 40).all() and m.ratio_test(dist, 0.7)[:20].all()   # planted queries find their rows and pass the ratio test
+    assert (dist[:20, 0] <= 40).all() and m.ratio_test(dist, 0.7)[4:20].all()  # planted queries find their rows and pass the ratio test (0-3: duplicated rows tie)
 
 
 def _init_case(n1, n2, seed, dense):
