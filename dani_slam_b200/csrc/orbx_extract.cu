@@ -86,6 +86,119 @@ __device__ __forceinline__ const uint8_t *level_ptr(const ExParams &p, const Orb
 // row into shared memory — a destination column keeps its source offset and coefficients in registers;
 // phase 2 combines two of those rows per output row, 4 pixels per thread, one 32-bit store.
 // ------------------------------------------------------------------------------------------------
+// ---- TMA (cp.async.bulk.tensor) + mbarrier helpers: one elected lane issues a box load, the warp waits on the barrier ----
+struct OrbxTmaMaps { CUtensorMap m[ORBX_MAX_LEVELS]; };   // one rank-3 map (x bytes, y rows, frame) per pyramid level
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "ORBX_MBAR_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra ORBX_MBAR_DONE_%=;\n"
+        "bra ORBX_MBAR_WAIT_%=;\n"
+        "ORBX_MBAR_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y, int z) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 (TMA form): one pyramid level, one WARP per strip of 128 destination columns × PYR2_RS destination rows, no block barrier.
+// Lane 0 fetches the strip's source rows with one TMA box load; every lane owns 4 destination columns, whose source bytes all
+// lie in a 8-byte window of the staged row (three aligned words, two PRMT), and walks down the destination rows keeping the
+// horizontal sums of the two current source rows in registers — each source row is filtered exactly once per strip and the
+// intermediate never touches shared memory.  Arithmetic identical to k_pyr_level below.
+// ------------------------------------------------------------------------------------------------
+#define PYR2_RS 16
+struct Pyr2Args {
+    uint8_t *dst; long long dstStride; int dp, dw, dh;
+    const int2 *tabX, *tabY;         // same tables as k_pyr_level
+    int tilesX, nStrips;             // strips = tilesX × ceil(dh / PYR2_RS)
+    int boxW, boxH, slotBytes;       // TMA box (source bytes × source rows per strip), shared memory per warp
+};
+template <int WPB>
+__global__ void __launch_bounds__(WPB * 32) k_pyr_level_tma(Pyr2Args a, const __grid_constant__ CUtensorMap srcMap) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int item = blockIdx.x * WPB + warp, b = blockIdx.y;
+    if (item >= a.nStrips) return;                       // warps are independent
+    const int ty = item / a.tilesX, tx = item - ty * a.tilesX;
+    const int x0 = tx * 128, y0 = ty * PYR2_RS;
+    uint8_t *T = smem_raw + (size_t)warp * a.slotBytes;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(T + a.slotBytes - 8);
+    const int c0 = a.tabX[x0].x;                         // source column of the strip's first destination column
+    // lane yy holds the row table entry of destination row y0+yy (PYR2_RS <= 32)
+    const int2 myRow = a.tabY[min(y0 + min(lane, PYR2_RS - 1), a.dh - 1)];
+    const int r0 = __shfl_sync(0xffffffffu, myRow.x, 0) & 0xffff;     // first source row of the strip
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, (uint32_t)(a.boxW * a.boxH));
+        tma_load_3d(T, &srcMap, bar, c0, r0, b);
+    }
+    // per-lane column constants (while the box is in flight)
+    const int gx = x0 + 4 * lane;
+    const bool act = gx < a.dw;
+    uint32_t coef[4], sel[4];
+    int rel0 = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int2 t = a.tabX[min(gx + j, a.dw - 1)];
+        const int rel = t.x - c0;
+        if (j == 0) rel0 = rel;
+        const uint32_t d = (uint32_t)(rel - rel0);       // 0..5: byte of the window holding S[s0]; S[s0+1] follows (a1 = 0 where s0 is the last column)
+        sel[j] = d | ((d + 1u) << 4);
+        coef[j] = (uint32_t)t.y;                         // a0 | a1 << 16
+    }
+    const uint32_t selWin = 0x3210u + 0x1111u * (uint32_t)(rel0 & 3);
+    const uint8_t *Tw = T + (rel0 & ~3);
+    const int boxW = a.boxW, lastRow = a.boxH - 1;
+    auto hrow = [&](int r, uint32_t (&h)[4]) {
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(Tw + min(r, lastRow) * boxW);
+        const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+        const uint32_t lo = __byte_perm(w0, w1, selWin), hi = __byte_perm(w1, w2, selWin);   // the 8 bytes from S[s0 of column 0]
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = __dp2a_lo(coef[j], __byte_perm(lo, hi, sel[j]), 0u) >> 4;   // (S[s0]*a0 + S[s1]*a1) >> 4
+    };
+    __syncwarp();
+    mbar_wait(bar, 0);
+    uint32_t hA[4], hB[4];
+    int curA = 0;
+    hrow(0, hA);
+    hrow(1, hB);
+    uint8_t *Dp = a.dst + (long long)b * a.dstStride + (long long)y0 * a.dp + gx;
+    const int nRows = min(PYR2_RS, a.dh - y0);
+    for (int yy = 0; yy < nRows; ++yy, Dp += a.dp) {
+        const uint32_t rows = (uint32_t)__shfl_sync(0xffffffffu, myRow.x, yy), cf = (uint32_t)__shfl_sync(0xffffffffu, myRow.y, yy);
+        const int i0 = (int)(rows & 0xffffu) - r0, i1 = (int)(rows >> 16) - r0;
+        while (curA < i0) {                              // warp-uniform: slide the two-row window down
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hA[j] = hB[j];
+            ++curA;
+            hrow(curA + 1, hB);
+        }
+        const uint32_t b0 = cf & 0xffffu, b1 = cf >> 16;
+        const bool same = i1 == i0;                      // clamped at the bottom edge
+        uint32_t out = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t u0 = hA[j], u1 = same ? hA[j] : hB[j];
+            const uint32_t v = (((b0 * u0) >> 16) + ((b1 * u1) >> 16) + 2u) >> 2;
+            out += v << (8 * j);                         // v <= 255: bytes pack by addition
+        }
+        if (act) *reinterpret_cast<uint32_t *>(Dp) = out;   // pitch is a multiple of 128: the padding is writable
+    }
+}
+
 #define PYR_TW 128
 #define PYR_TH 32
 struct PyrArgs {             // everything by value: no dependent global loads before the pixel loads
@@ -221,32 +334,6 @@ __host__ __device__ inline FastSmem fast_smem_layout(int maxCw, int maxCh, int m
     s.barOff = (s.maskOff + G * (maxCh - 6) + 128 + 7) & ~7;   // the warp's mbarrier (TMA completion)
     s.total2 = (s.barOff + 8 + 127) & ~127;              // slots are 128-byte aligned (TMA destination)
     return s;
-}
-
-// ---- TMA (cp.async.bulk.tensor) + mbarrier helpers: one elected lane issues a box load, the warp waits on the barrier ----
-struct OrbxTmaMaps { CUtensorMap m[ORBX_MAX_LEVELS]; };   // one rank-3 map (x bytes, y rows, frame) per pyramid level
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "ORBX_MBAR_WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra ORBX_MBAR_DONE_%=;\n"
-        "bra ORBX_MBAR_WAIT_%=;\n"
-        "ORBX_MBAR_DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y, int z) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                 ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
 }
 
 struct Row3 { uint32_t w0, w1, w2; };
@@ -1963,6 +2050,169 @@ __global__ void k_dbg_sort(orbx_sort::elem_t *a, orbx_sort::elem_t *tmp, int n) 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Classical rectified-stereo association (slot = Frame::ComputeStereoMatches, src/Frame.cc:813-915).
+// This tree replaced the function's matcher by LightGlue, so the algorithm is the restated upstream one (see oracle/
+// orb_oracle.cpp: orc_stereo_rowband — parity unpinned): row band of ±2·scale around every right keypoint, Hamming search
+// within one octave and the disparity range, 11×11 SAD over ±5 px on the keypoint's pyramid level with a parabola fit,
+// disparity gate, median cut at 1.5·1.4·median.  One warp per left keypoint; the band test replaces the per-row index lists
+// (candidates are visited in ascending right index, which is the lists' insertion order, so ties resolve the same way).
+// ------------------------------------------------------------------------------------------------
+struct SmLevels {
+    const uint8_t *L[ORBX_MAX_LEVELS], *R[ORBX_MAX_LEVELS];
+    int pitchL[ORBX_MAX_LEVELS], pitchR[ORBX_MAX_LEVELS], w[ORBX_MAX_LEVELS], h[ORBX_MAX_LEVELS];
+    float sf[ORBX_MAX_LEVELS], inv[ORBX_MAX_LEVELS];
+    int nlevels, nRows;
+};
+// per right keypoint: {first band row, last band row, octave, pt.x bits}
+__global__ void k_sm_prep(const orbx_keypoint *kR, int nR, SmLevels lv, int4 *prep) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nR) return;
+    const orbx_keypoint k = kR[i];
+    const int oct = min(max(k.octave, 0), lv.nlevels - 1);
+    const float r = __fmul_rn(2.0f, lv.sf[oct]);
+    prep[i] = make_int4((int)floorf(__fsub_rn(k.y, r)), (int)ceilf(__fadd_rn(k.y, r)), k.octave, __float_as_int(k.x));
+}
+template <int WPB>
+__global__ void __launch_bounds__(WPB * 32) k_sm_match(const orbx_keypoint *kL, const uint4 *dL, int nL, const int4 *prep, const uint4 *dR, int nR, SmLevels lv,
+                                                       float mbf, float mb, float *uRight, float *depth, int *sadOut) {
+    const int iL = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (iL >= nL) return;
+    const orbx_keypoint k = kL[iL];
+    float ur = -1.f, dp = -1.f;
+    int sadBest = -1;
+    const int levelL = k.octave;
+    const float vL = k.y, uL = k.x;
+    const int row = (int)vL;
+    const float maxD = __fdiv_rn(mbf, mb);
+    const float minU = __fsub_rn(uL, maxD), maxU = uL;      // uL - minD with minD = 0
+    const unsigned long long NONE = ~0ull;
+    unsigned long long best = NONE;
+    if (row >= 0 && row < lv.nRows && !(maxU < 0.f) && levelL >= 0 && levelL < lv.nlevels) {
+        const uint4 a0 = dL[2 * (long long)iL], a1 = dL[2 * (long long)iL + 1];
+        for (int iR = lane; iR < nR; iR += 32) {
+            const int4 c = prep[iR];
+            if (row < c.x || row > c.y) continue;                          // not in this keypoint's row band
+            if (c.z < levelL - 1 || c.z > levelL + 1) continue;
+            const float uR = __int_as_float(c.w);
+            if (!(uR >= minU && uR <= maxU)) continue;
+            const uint4 b0 = dR[2 * (long long)iR], b1 = dR[2 * (long long)iR + 1];
+            const int d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) + __popc(a1.x ^ b1.x) +
+                          __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+            if (d < 100) {                                                 // bestDist starts at TH_HIGH, strict '<'
+                const unsigned long long key = ((unsigned long long)(unsigned)d << 32) | (unsigned)iR;
+                best = key < best ? key : best;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long ob = __shfl_xor_sync(0xffffffffu, best, o);
+        best = ob < best ? ob : best;
+    }
+    if (best != NONE && (int)(best >> 32) < (100 + 50) / 2) {              // thOrbDist
+        const int bestIdxR = (int)(best & 0xffffffffu);
+        const float uR0 = __int_as_float(prep[bestIdxR].w);
+        const float scaleFactor = lv.inv[levelL];
+        const int cu = (int)roundf(__fmul_rn(uL, scaleFactor)), cv = (int)roundf(__fmul_rn(vL, scaleFactor)), cr = (int)roundf(__fmul_rn(uR0, scaleFactor));
+        const int w = 5, Ls = 5;
+        const int wl = lv.w[levelL], hl = lv.h[levelL];
+        // iniu = scaleduR0 + L - w, endu = scaleduR0 + L + w + 1; the other tests keep the windows inside the levels
+        if (!(cr < 0 || cr + Ls + w + 1 >= wl) && cv - w >= 0 && cv + w < hl && cu - w >= 0 && cu + w < wl && cr - Ls - w >= 0) {
+            int acc[11];
+#pragma unroll
+            for (int i = 0; i < 11; ++i) acc[i] = 0;
+            const uint8_t *PL = lv.L[levelL], *PR = lv.R[levelL];
+            const int pl = lv.pitchL[levelL], pr = lv.pitchR[levelL];
+            for (int p = lane; p < 121; p += 32) {
+                const int yy = p / 11, xx = p - yy * 11;
+                const int a = PL[(long long)(cv - w + yy) * pl + (cu - w + xx)];
+                const uint8_t *q = PR + (long long)(cv - w + yy) * pr + (cr - Ls - w + xx);
+#pragma unroll
+                for (int i = 0; i < 11; ++i) acc[i] += abs(a - (int)q[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 11; ++i)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+            int bestSad = INT_MAX, bestinc = 0;
+#pragma unroll
+            for (int i = 0; i < 11; ++i)
+                if (acc[i] < bestSad) { bestSad = acc[i]; bestinc = i - Ls; }
+            if (bestinc != -Ls && bestinc != Ls) {
+                float d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 11; ++i) {           // static indexing keeps acc[] in registers
+                    if (i == Ls + bestinc - 1) d1 = (float)acc[i];
+                    if (i == Ls + bestinc) d2 = (float)acc[i];
+                    if (i == Ls + bestinc + 1) d3 = (float)acc[i];
+                }
+                const float den = __fmul_rn(2.0f, __fsub_rn(__fadd_rn(d1, d3), __fmul_rn(2.0f, d2)));
+                const float deltaR = __fdiv_rn(__fsub_rn(d1, d3), den);
+                if (!(deltaR < -1.f || deltaR > 1.f)) {                    // (a NaN from 0/0 passes both tests, as in the scalar code)
+                    float bestuR = __fmul_rn(lv.sf[levelL], __fadd_rn(__fadd_rn((float)cr, (float)bestinc), deltaR));
+                    float disparity = __fsub_rn(uL, bestuR);
+                    if (disparity >= 0.f && disparity < maxD) {
+                        if (disparity <= 0.f) { disparity = 0.01f; bestuR = __fsub_rn(uL, 0.01f); }
+                        dp = __fdiv_rn(mbf, disparity);
+                        ur = bestuR;
+                        sadBest = bestSad;
+                    }
+                }
+            }
+        }
+    }
+    if (lane == 0) { uRight[iL] = ur; depth[iL] = dp; sadOut[iL] = sadBest; }
+}
+// median cut: the reference sorts (SAD, index) pairs and takes element [size/2]; one block, two 256-bin histograms (SAD < 2^16)
+__global__ void __launch_bounds__(256) k_sm_tail(const int *sad, int nL, float *uRight, float *depth, int *keptOut) {
+    __shared__ int hist[256];
+    __shared__ int s_total, s_hi, s_before, s_med, s_dropped;
+    const int tid = threadIdx.x;
+    hist[tid] = 0;
+    if (tid == 0) { s_total = 0; s_dropped = 0; }
+    __syncthreads();
+    int mine = 0;
+    for (int i = tid; i < nL; i += 256) {
+        const int v = sad[i];
+        if (v >= 0) { atomicAdd(&hist[min(v >> 8, 255)], 1); ++mine; }
+    }
+    atomicAdd(&s_total, mine);
+    __syncthreads();
+    const int total = s_total;
+    if (total == 0) { if (tid == 0) *keptOut = 0; return; }
+    const int kth = total / 2;
+    if (tid == 0) {
+        int acc = 0, b = 0;
+        for (; b < 256; ++b) { if (acc + hist[b] > kth) break; acc += hist[b]; }
+        s_hi = b; s_before = acc;
+    }
+    __syncthreads();
+    const int hi = s_hi;
+    hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < nL; i += 256) {
+        const int v = sad[i];
+        if (v >= 0 && min(v >> 8, 255) == hi) atomicAdd(&hist[v & 255], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int acc = s_before, b = 0;
+        for (; b < 256; ++b) { if (acc + hist[b] > kth) break; acc += hist[b]; }
+        s_med = (hi << 8) | b;
+    }
+    __syncthreads();
+    const float thDist = __fmul_rn(__fmul_rn(1.5f, 1.4f), (float)s_med);
+    int dropped = 0;
+    for (int i = tid; i < nL; i += 256) {
+        const int v = sad[i];
+        if (v >= 0 && !((float)v < thDist)) { uRight[i] = -1.f; depth[i] = -1.f; ++dropped; }
+    }
+    atomicAdd(&s_dropped, dropped);
+    __syncthreads();
+    if (tid == 0) *keptOut = total - s_dropped;
+}
+
 thread_local std::string tl_error;
 
 }  // namespace
@@ -2029,7 +2279,8 @@ struct orbx_extractor {
     int oneRows = -1, oneCols = -1, oneCap = -1, oneWarm = 0;
     long long oneLaunches = 0;
     bool useGraph = true;
-    bool useTma = true;             // ORBX_NO_TMA: stage tiles with ordinary loads (same results; cross-check and fallback)
+    uint8_t *d_sm = nullptr; size_t smCap = 0;     // scratch of orbx_stereo_matches
+    bool useTma = true, useTmaPyr = true;   // ORBX_NO_TMA: stage tiles with ordinary loads (same results; cross-check and fallback)
 
     // device buffers (sized for maxW × maxH × maxBatch at create)
     OrbxGeom *d_geom = nullptr;
@@ -2403,6 +2654,30 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
     }
     // K1
     for (int l = 1; l < G.nlevels; ++l) {
+        // TMA form: one warp per 128 × PYR2_RS strip (needs a 16-byte aligned source; level 0 may be the caller's own buffer)
+        if (ex->useTmaPyr) {
+            const OrbxLevel &SV = G.lv[l - 1], &DV = G.lv[l];
+            Pyr2Args A2;
+            A2.dst = P.pyr + DV.off; A2.dstStride = G.frameBytes; A2.dp = DV.pitch; A2.dw = DV.w; A2.dh = DV.h;
+            A2.tabX = ex->d_tabX + ex->h_tabXOff[l]; A2.tabY = ex->d_tabY + ex->h_tabYOff[l];
+            A2.tilesX = (DV.w + 127) / 128;
+            A2.nStrips = A2.tilesX * ((DV.h + PYR2_RS - 1) / PYR2_RS);
+            A2.boxW = orbx_align_up((int)ceil(127.0 * SV.w / DV.w) + 1 + 12, 16);
+            A2.boxH = (int)ceil((PYR2_RS - 1) * (double)SV.h / DV.h) + 3;
+            A2.slotBytes = orbx_align_up(A2.boxW * A2.boxH + 8, 128);
+            CUtensorMap srcMap;
+            const bool ok = A2.boxW <= 256 && A2.boxH <= 256 &&
+                            tma_encode_level(&srcMap, l == 1 ? P.in0 : P.pyr + SV.off, SV.w, SV.h, batch, l == 1 ? P.in0Pitch : SV.pitch,
+                                             l == 1 ? P.in0Stride : G.frameBytes, A2.boxW, A2.boxH);
+            if (ok) {
+                const int WPB2 = 4;
+                const size_t smem2 = (size_t)A2.slotBytes * WPB2;
+                if (smem2 > 48 * 1024) CUDA_TRY(ex, cudaFuncSetAttribute(k_pyr_level_tma<WPB2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+                k_pyr_level_tma<WPB2><<<dim3((A2.nStrips + WPB2 - 1) / WPB2, batch), WPB2 * 32, smem2, s>>>(A2, srcMap);
+                ++ex->launches;
+                continue;
+            }
+        }
         const int tilesX = (G.lv[l].w + PYR_TW - 1) / PYR_TW, tilesY = (G.lv[l].h + PYR_TH - 1) / PYR_TH;
         const int srcRows = (int)ceil((PYR_TH - 1) * (double)G.lv[l - 1].h / G.lv[l].h) + 4;
         const int srcPitch = 16 * ((int)ceil(((PYR_TW - 1) * (double)G.lv[l - 1].w / G.lv[l].w + 18.0) / 16.0) + 1);
@@ -2746,7 +3021,10 @@ orbx_extractor *orbx_create(int nfeatures, float scale_factor, int nlevels, int 
     ex->useHistQuadtree = getenv("ORBX_LEGACY_QUADTREE") == nullptr;
     ex->fastV1 = getenv("ORBX_FAST_V1") != nullptr;
     ex->useGraph = getenv("ORBX_NO_GRAPH") == nullptr;
-    ex->useTma = getenv("ORBX_NO_TMA") == nullptr;        // same kernels and results; tiles are then staged with ordinary loads      // same kernels either way; the graph only removes launch overhead
+    if (const char *e = getenv("ORBX_NO_TMA")) {          // same results either way; tiles are then staged with ordinary loads ("fast" / "pyr": only that stage)
+        ex->useTma = strcmp(e, "pyr") == 0;
+        ex->useTmaPyr = strcmp(e, "fast") == 0;
+    }      // same kernels either way; the graph only removes launch overhead
     CREATE_TRY(cudaMalloc((void **)&ex->d_nOut, (size_t)max_batch * sizeof(int)));
     CREATE_TRY(cudaMalloc((void **)&ex->d_mono, (size_t)max_batch * sizeof(int)));
     CREATE_TRY(cudaHostAlloc((void **)&ex->h_nOut, (size_t)max_batch * sizeof(int), cudaHostAllocDefault));
@@ -2769,6 +3047,7 @@ void orbx_destroy(orbx_extractor *ex) {
     if (ex->h_in) cudaFreeHost(ex->h_in);
     if (ex->h_single) cudaFreeHost(ex->h_single);
     if (ex->d_single) cudaFree(ex->d_single);
+    if (ex->d_sm) cudaFree(ex->d_sm);
     void *ptrs[] = {ex->d_geom, ex->d_cells, ex->d_tiles, ex->d_pathLut, ex->d_tabX, ex->d_tabY,
                     ex->d_pattern, ex->d_pyr, ex->d_blur, ex->d_slots, ex->d_ptNode, ex->d_ptXY, ex->d_cellCnt,
                     ex->d_sel, ex->d_work, ex->d_selCnt, ex->d_workCnt, ex->d_hist, ex->d_finalPos, ex->d_best, ex->d_cellPrefix, ex->d_deep, ex->d_dense, ex->d_denseList, ex->d_stage, ex->d_kps, ex->d_desc, ex->d_nOut, ex->d_mono};
@@ -3023,6 +3302,7 @@ static int extract_one(orbx_extractor *ex, const uint8_t *image, int rows, int c
         CUDA_TRY(ex, cudaStreamSynchronize(s));
         if (ex->oneExec) { cudaGraphExecDestroy(ex->oneExec); ex->oneExec = nullptr; }
         if (ex->d_single) cudaFree(ex->d_single);
+    if (ex->d_sm) cudaFree(ex->d_sm);
         if (ex->h_single) cudaFreeHost(ex->h_single);
         ex->d_single = ex->h_single = nullptr; ex->singleCap = 0;
         CUDA_TRY(ex, cudaMalloc((void **)&ex->d_single, outBytes));
@@ -3106,6 +3386,76 @@ int orbx_extract(orbx_extractor *ex, const uint8_t *image, int rows, int cols, s
         drain_streams(ex);
     }
     return rc;
+}
+
+int orbx_stereo_matches(orbx_extractor *ex_left, orbx_extractor *ex_right, const orbx_keypoint *kps_left, const uint8_t *desc_left, int n_left,
+                        const orbx_keypoint *kps_right, const uint8_t *desc_right, int n_right, float mbf, float mb, float *mvu_right, float *mv_depth,
+                        int32_t *n_stereo) {
+    if (!ex_left || !ex_right) return ORBX_ERR_ARG;
+    orbx_extractor *ex = ex_left;
+    if (n_left < 0 || n_right < 0 || !n_stereo || (n_left > 0 && (!kps_left || !desc_left || !mvu_right || !mv_depth)) || (n_right > 0 && (!kps_right || !desc_right))) {
+        ex->err = "orbx_stereo_matches: bad argument";
+        return ORBX_ERR_ARG;
+    }
+    *n_stereo = 0;
+    for (int i = 0; i < n_left; ++i) { mvu_right[i] = -1.f; mv_depth[i] = -1.f; }
+    if (n_left == 0 || n_right == 0) return ORBX_OK;
+    if (ex_left->device != ex_right->device || ex_left->nlevels != ex_right->nlevels || ex_left->curRows != ex_right->curRows || ex_left->curCols != ex_right->curCols ||
+        ex_left->lastBatch < 1 || ex_right->lastBatch < 1 || !ex_left->lastIn0Internal || !ex_right->lastIn0Internal) {
+        ex->err = "orbx_stereo_matches: both extractors must hold the pyramid of a host-image call of the same size on the same device";
+        return ORBX_ERR_ARG;
+    }
+    for (int i = 0; i < n_left; ++i) if (kps_left[i].octave < 0 || kps_left[i].octave >= ex->nlevels) { ex->err = "orbx_stereo_matches: octave out of range"; return ORBX_ERR_ARG; }
+    for (int i = 0; i < n_right; ++i) if (kps_right[i].octave < 0 || kps_right[i].octave >= ex->nlevels) { ex->err = "orbx_stereo_matches: octave out of range"; return ORBX_ERR_ARG; }
+    OrbxDeviceGuard dg_(ex->device);
+    CUDA_TRY(ex, dg_.status);
+    CUDA_TRY(ex, cudaStreamSynchronize(ex_right->stream));       // its pyramid is read on the left handle's stream
+    const size_t a256 = 255;
+    const size_t kLB = ((size_t)n_left * sizeof(orbx_keypoint) + a256) & ~a256, kRB = ((size_t)n_right * sizeof(orbx_keypoint) + a256) & ~a256;
+    const size_t dLB = ((size_t)n_left * 32 + a256) & ~a256, dRB = ((size_t)n_right * 32 + a256) & ~a256, pB = ((size_t)n_right * 16 + a256) & ~a256;
+    const size_t oB = ((size_t)n_left * 4 + a256) & ~a256;
+    const size_t need = kLB + kRB + dLB + dRB + pB + 3 * oB + 256;
+    if (need > ex->smCap || !ex->d_sm) {
+        CUDA_TRY(ex, cudaStreamSynchronize(ex->stream));
+        if (ex->d_sm) cudaFree(ex->d_sm);
+        ex->d_sm = nullptr; ex->smCap = 0;
+        CUDA_TRY(ex, cudaMalloc((void **)&ex->d_sm, need));
+        ex->smCap = need;
+    }
+    uint8_t *p = ex->d_sm;
+    orbx_keypoint *dkL = (orbx_keypoint *)p; p += kLB;
+    orbx_keypoint *dkR = (orbx_keypoint *)p; p += kRB;
+    uint8_t *ddL = p; p += dLB;
+    uint8_t *ddR = p; p += dRB;
+    int4 *dprep = (int4 *)p; p += pB;
+    float *dur = (float *)p; p += oB;
+    float *ddp = (float *)p; p += oB;
+    int *dsad = (int *)p; p += oB;
+    int *dn = (int *)p;
+    cudaStream_t s = ex->stream;
+    CUDA_TRY(ex, cudaMemcpyAsync(dkL, kps_left, (size_t)n_left * sizeof(orbx_keypoint), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(ex, cudaMemcpyAsync(dkR, kps_right, (size_t)n_right * sizeof(orbx_keypoint), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(ex, cudaMemcpyAsync(ddL, desc_left, (size_t)n_left * 32, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(ex, cudaMemcpyAsync(ddR, desc_right, (size_t)n_right * 32, cudaMemcpyHostToDevice, s));
+    SmLevels lv;
+    memset(&lv, 0, sizeof(lv));
+    const OrbxGeom &GL = ex_left->geom, &GR = ex_right->geom;
+    lv.nlevels = ex->nlevels; lv.nRows = GL.lv[0].h;
+    for (int l = 0; l < ex->nlevels; ++l) {
+        lv.L[l] = ex_left->d_pyr + GL.lv[l].off; lv.R[l] = ex_right->d_pyr + GR.lv[l].off;     // frame 0 of each handle's last call
+        lv.pitchL[l] = GL.lv[l].pitch; lv.pitchR[l] = GR.lv[l].pitch; lv.w[l] = GL.lv[l].w; lv.h[l] = GL.lv[l].h;
+        lv.sf[l] = ex->sf[l]; lv.inv[l] = ex->inv[l];
+    }
+    k_sm_prep<<<(n_right + 255) / 256, 256, 0, s>>>(dkR, n_right, lv, dprep);
+    k_sm_match<8><<<(n_left + 7) / 8, 256, 0, s>>>(dkL, (const uint4 *)ddL, n_left, dprep, (const uint4 *)ddR, n_right, lv, mbf, mb, dur, ddp, dsad);
+    k_sm_tail<<<1, 256, 0, s>>>(dsad, n_left, dur, ddp, dn);
+    ex->launches += 3;
+    CUDA_TRY(ex, cudaGetLastError());
+    CUDA_TRY(ex, cudaMemcpyAsync(mvu_right, dur, (size_t)n_left * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ex, cudaMemcpyAsync(mv_depth, ddp, (size_t)n_left * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ex, cudaMemcpyAsync(n_stereo, dn, 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ex, cudaStreamSynchronize(s));
+    return ORBX_OK;
 }
 
 int orbx_sync(orbx_extractor *ex) {

@@ -78,6 +78,7 @@ def lib() -> C.CDLL:
     L.orbx_hamming_knn2_device.argtypes = [vp, vp, i32, vp, i64, i64, vp, vp]
     L.orbx_knn2_merge_device.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     L.orbx_knn2_merge_packed_device.argtypes = [vp, vp, i32, i32, vp, vp]
+    L.orbx_stereo_matches.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, f32, f32, vp, vp, vp]
     L.orbx_copy_only_batch.argtypes = [vp, vp, i32, i32, i32, sz, vp, vp, i32]
     L.orbx_comm_unique_id.argtypes = [vp]
     L.orbx_comm_create.restype = vp
@@ -493,6 +494,20 @@ class ORBmatcher:
 
     def stream(self):
         return self.L.orbx_matcher_stream(self.h)
+
+
+def ComputeStereoMatches(exL, exR, kpsL, descL, kpsR, descR, mbf, mb):
+    """The classical `Frame::ComputeStereoMatches` (slot src/Frame.cc:813-915; restated upstream algorithm, see orbx.h) over the pyramids
+    the two extractors hold from their last single-image calls → (n_stereo, mvuRight, mvDepth)."""
+    L = lib()
+    kL = np.ascontiguousarray(kpsL, KP_DTYPE); kR = np.ascontiguousarray(kpsR, KP_DTYPE)
+    dL = np.ascontiguousarray(descL, np.uint8).reshape(-1, 32); dR = np.ascontiguousarray(descR, np.uint8).reshape(-1, 32)
+    ur = np.zeros(len(kL), np.float32); dp = np.zeros(len(kL), np.float32)
+    n = C.c_int32(0)
+    rc = L.orbx_stereo_matches(exL.h, exR.h, _p(kL), _p(dL), len(kL), _p(kR), _p(dR), len(kR), float(mbf), float(mb), _p(ur), _p(dp), C.byref(n))
+    if rc != OK:
+        raise OrbxError(rc, L.orbx_last_error(exL.h).decode())
+    return n.value, ur, dp
 
 
 class Comm:

@@ -153,6 +153,9 @@ public:
         }
     }
 
+    // The C-ABI handle (for orbx_stereo_matches, which reads the two extractors' device-resident pyramids, and for batch calls).
+    orbx_extractor* Handle(){ return mpHandle; }
+
     std::vector<cv::Mat> mvImagePyramid;
     std::vector<cv::Rect2i> mvDynamicArea;
     bool mbMaterializePyramid;

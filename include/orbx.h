@@ -118,6 +118,18 @@ int orbx_get_blurred(orbx_extractor *ex, int frame, int level, uint8_t *dst, siz
 int orbx_get_candidates(orbx_extractor *ex, int frame, int level, orbx_keypoint *out, int cap);
 int orbx_get_selected(orbx_extractor *ex, int frame, int level, orbx_keypoint *out, int cap);
 
+/* Classical rectified-stereo association — the slot of Frame::ComputeStereoMatches (src/Frame.cc:813-915).  This tree fills that
+ * slot with a learned matcher (LightGlue, :822-860), which is out of scope; the entry point below is the published upstream
+ * algorithm of the function (row bands of ±2·scale, Hamming search within one octave and the disparity range, 11×11 SAD
+ * refinement over ±5 px with a parabola fit on the keypoint's pyramid level, disparity gate 0 <= d < mbf/mb, depth = mbf/d,
+ * median cut at 1.5·1.4·median), restated in oracle/orb_oracle.cpp (orc_stereo_rowband; parity unpinned: no reference code to
+ * run).  ex_left / ex_right are the two extractors right after their orbx_extract calls on the left / right image (their
+ * pyramids stay on the device until the next call, like mvImagePyramid, src/ORBextractor.cc:1216); keypoints and
+ * descriptors are what those calls returned.  mvu_right / mv_depth: n_left entries, -1 = no stereo.  HOST buffers. */
+int orbx_stereo_matches(orbx_extractor *ex_left, orbx_extractor *ex_right, const orbx_keypoint *kps_left, const uint8_t *desc_left, int n_left,
+                        const orbx_keypoint *kps_right, const uint8_t *desc_right, int n_right, float mbf, float mb, float *mvu_right, float *mv_depth,
+                        int32_t *n_stereo);
+
 /* Page-locked host memory helpers (cudaHostAlloc / cudaFreeHost). */
 void *orbx_host_alloc(size_t bytes);
 void orbx_host_free(void *p);

@@ -69,6 +69,8 @@ def lib() -> C.CDLL:
         L.orc_rot_hist_filter.argtypes = [vp, vp, i32, vp]
         L.orc_features_in_area.restype = i32
         L.orc_features_in_area.argtypes = [vp, vp, i32, f32, f32, f32, f32, vp, i32, i32, i32, vp, vp, i32]
+        L.orc_stereo_rowband.restype = i32
+        L.orc_stereo_rowband.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, f32, f32, vp, vp]
         L.orc_stereo_tail.restype = i32
         L.orc_stereo_tail.argtypes = [vp, vp, i32, i32, vp, vp, vp, f32, f32, vp, vp]
         L.orc_search_init.restype = i32
@@ -260,6 +262,15 @@ def features_in_area(xy, octave, bounds, queries, min_level=-1, max_level=-1):
     cand = np.zeros(max(total, 1), np.int32)
     lib().orc_features_in_area(_p(xy), _p(octave), len(xy), *[float(b) for b in bounds], _p(queries), len(queries), min_level, max_level, _p(off), _p(cand), total)
     return off, cand[:total]
+
+
+def stereo_rowband(exL, exR, kL, dL, kR, dR, mbf, mb):
+    """Classical ComputeStereoMatches over the pyramids the two oracle extractors hold from their last extract() → (n, mvuRight, mvDepth)."""
+    kL = np.ascontiguousarray(kL, KP_DTYPE); kR = np.ascontiguousarray(kR, KP_DTYPE)
+    dL = np.ascontiguousarray(dL, np.uint8); dR = np.ascontiguousarray(dR, np.uint8)
+    ur = np.zeros(len(kL), np.float32); dp = np.zeros(len(kL), np.float32)
+    n = lib().orc_stereo_rowband(exL.h, exR.h, _p(kL), _p(dL), len(kL), _p(kR), _p(dR), len(kR), float(mbf), float(mb), _p(ur), _p(dp))
+    return n, ur, dp
 
 
 def stereo_tail(uL, uR, idx, dist, keep, mbf, mb):

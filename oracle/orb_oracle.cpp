@@ -921,6 +921,97 @@ int orc_search_by_projection(const float *xy, const int32_t *octave, const uint8
     return nmatches;
 }
 
+// ---- classical rectified-stereo association (slot = Frame::ComputeStereoMatches, src/Frame.cc:813-915) ----
+// PARITY UNPINNED: this tree replaced the function's matcher by LightGlue (src/Frame.cc:822-860), so there is no reference
+// code to compile for it.  What follows restates the published algorithm of the upstream ORB-SLAM3 function of the same name
+// (row bands of ±2·scale around every right keypoint, Hamming search among the band's keypoints within one octave and the
+// disparity range, 11×11 SAD refinement over ±5 px on the keypoint's pyramid level with a parabola fit, disparity gate, and
+// the median cut with the factor 1.5·1.4), ending in the same bookkeeping as this tree's tail (:862-914).  Level images are
+// the unblurred, unpadded pyramid levels of the two extractors (mvImagePyramid).
+int orc_stereo_rowband(const orc_extractor *exL, const orc_extractor *exR, const orc_keypoint *kL, const uint8_t *dL, int nL,
+                       const orc_keypoint *kR, const uint8_t *dR, int nR, float mbf, float mb, float *uRight, float *depth) {
+    for (int i = 0; i < nL; ++i) { uRight[i] = -1.f; depth[i] = -1.f; }
+    if (nL == 0 || nR == 0) return 0;
+    const int thOrbDist = (100 + 50) / 2;                       // (TH_HIGH + TH_LOW) / 2
+    const int nRows = exL->pyr[0].h;
+    std::vector<std::vector<int>> rowIdx(nRows);
+    for (int iR = 0; iR < nR; ++iR) {
+        const float kpY = kR[iR].y;
+        const float r = 2.0f * exR->sf[kR[iR].octave];
+        const int maxr = (int)std::ceil(kpY + r), minr = (int)std::floor(kpY - r);
+        for (int yi = minr; yi <= maxr; ++yi)
+            if (yi >= 0 && yi < nRows) rowIdx[yi].push_back(iR);   // (upstream indexes without the guard; keypoints stay 19 px inside)
+    }
+    const float minZ = mb, minD = 0, maxD = mbf / minZ;
+    std::vector<std::pair<int, int>> vDistIdx;
+    for (int iL = 0; iL < nL; ++iL) {
+        const int levelL = kL[iL].octave;
+        const float vL = kL[iL].y, uL = kL[iL].x;
+        const int row = (int)vL;
+        if (row < 0 || row >= nRows) continue;
+        const std::vector<int> &cands = rowIdx[row];
+        if (cands.empty()) continue;
+        const float minU = uL - maxD, maxU = uL - minD;
+        if (maxU < 0) continue;
+        int bestDist = 100, bestIdxR = 0;                       // TH_HIGH
+        for (int iR : cands) {
+            if (kR[iR].octave < levelL - 1 || kR[iR].octave > levelL + 1) continue;
+            const float uR = kR[iR].x;
+            if (uR >= minU && uR <= maxU) {
+                const int dist = orc_descriptor_distance(dL + (size_t)iL * 32, dR + (size_t)iR * 32);
+                if (dist < bestDist) { bestDist = dist; bestIdxR = iR; }
+            }
+        }
+        if (bestDist >= thOrbDist) continue;
+        // sub-pixel refinement by correlation on the keypoint's level
+        const float uR0 = kR[bestIdxR].x;
+        const float scaleFactor = exL->inv[levelL];
+        const float scaleduL = std::round(uL * scaleFactor), scaledvL = std::round(vL * scaleFactor), scaleduR0 = std::round(uR0 * scaleFactor);
+        const int w = 5, L = 5;
+        const Plane &PL = exL->pyr[levelL], &PR = exR->pyr[levelL];
+        const float iniu = scaleduR0 + L - w, endu = scaleduR0 + L + w + 1;
+        if (iniu < 0 || endu >= PR.w) continue;
+        const int cu = (int)scaleduL, cv = (int)scaledvL, cr = (int)scaleduR0;
+        if (cv - w < 0 || cv + w >= PL.h || cu - w < 0 || cu + w >= PL.w || cr - L - w < 0) continue;   // (windows inside the levels; always true for extractor keypoints)
+        int bestSad = INT_MAX, bestincR = 0;
+        float vDists[2 * 5 + 1];
+        for (int incR = -L; incR <= L; ++incR) {
+            int sad = 0;
+            for (int yy = -w; yy <= w; ++yy) {
+                const uint8_t *a = PL.roi() + (size_t)(cv + yy) * PL.step + (cu - w);
+                const uint8_t *b = PR.roi() + (size_t)(cv + yy) * PR.step + (cr + incR - w);
+                for (int xx = 0; xx <= 2 * w; ++xx) sad += std::abs((int)a[xx] - (int)b[xx]);
+            }
+            if (sad < bestSad) { bestSad = sad; bestincR = incR; }
+            vDists[L + incR] = (float)sad;
+        }
+        if (bestincR == -L || bestincR == L) continue;
+        const float dist1 = vDists[L + bestincR - 1], dist2 = vDists[L + bestincR], dist3 = vDists[L + bestincR + 1];
+        const float deltaR = (dist1 - dist3) / (2.0f * (dist1 + dist3 - 2.0f * dist2));
+        if (deltaR < -1 || deltaR > 1) continue;
+        float bestuR = exL->sf[levelL] * ((float)scaleduR0 + (float)bestincR + deltaR);
+        float disparity = uL - bestuR;
+        if (disparity >= minD && disparity < maxD) {
+            if (disparity <= 0) { disparity = 0.01f; bestuR = uL - 0.01f; }
+            depth[iL] = mbf / disparity;
+            uRight[iL] = bestuR;
+            vDistIdx.push_back(std::make_pair(bestSad, iL));
+        }
+    }
+    if (vDistIdx.empty()) return 0;
+    std::sort(vDistIdx.begin(), vDistIdx.end());
+    const float median = (float)vDistIdx[vDistIdx.size() / 2].first;
+    const float thDist = 1.5f * 1.4f * median;
+    int kept = (int)vDistIdx.size();
+    for (int i = (int)vDistIdx.size() - 1; i >= 0; --i) {
+        if (vDistIdx[i].first < thDist) break;
+        uRight[vDistIdx[i].second] = -1;
+        depth[vDistIdx[i].second] = -1;
+        --kept;
+    }
+    return kept;
+}
+
 // ---- stereo association tail (src/Frame.cc:862-914) fed by the Hamming kNN + Lowe ratio of :1078-1085 ----
 // For every left keypoint i with keep[i]: iR = idx[2i], distance = (float)dist[2i]; disparity gate [0, mbf/mb),
 // depth = mbf/disparity (0.01 when disparity <= 0), then the 1.5·median distance cut.  uRight/depth are N_left

@@ -92,6 +92,9 @@ int orc_search_by_projection(const float *xy, const int32_t *octave, const uint8
                              float minX, float minY, float maxX, float maxY, const float *scale_factors, const float *mp_proj5,
                              const int32_t *mp_level, const uint8_t *mp_flags, const int32_t *mp_obs, const uint8_t *mp_desc, int m,
                              float nnratio, float th, int far_points, float th_far, int32_t *assigned);
+/* classical rectified-stereo association over the two extractors' pyramids (restated upstream algorithm; parity unpinned) */
+int orc_stereo_rowband(const orc_extractor *exL, const orc_extractor *exR, const orc_keypoint *kL, const uint8_t *dL, int nL,
+                       const orc_keypoint *kR, const uint8_t *dR, int nR, float mbf, float mb, float *uRight, float *depth);
 int orc_stereo_tail(const float *uL, const float *uR, int nL, int nR, const int32_t *idx, const int32_t *dist,
                     const uint8_t *keep, float mbf, float mb, float *uRight, float *depth);
 
