@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(WPB * 32) k_pyr_level_tma(Pyr2Args a, const __
     const int x0 = tx * 128, y0 = ty * PYR2_RS;
     uint8_t *T = smem_raw + (size_t)warp * a.slotBytes;
     uint64_t *bar = reinterpret_cast<uint64_t *>(T + a.slotBytes - 8);
-    const int c0 = a.tabX[x0].x;                         // source column of the strip's first destination column
+    const int c0 = a.tabX[x0].x & ~15;                   // the box starts on a 16-byte boundary of the source row (TMA rule), at or before the strip's first source column
     // lane yy holds the row table entry of destination row y0+yy (PYR2_RS <= 32)
     const int2 myRow = a.tabY[min(y0 + min(lane, PYR2_RS - 1), a.dh - 1)];
     const int r0 = __shfl_sync(0xffffffffu, myRow.x, 0) & 0xffff;     // first source row of the strip
@@ -310,15 +310,13 @@ __global__ void __launch_bounds__(256) k_pyr_level(PyrArgs a) {
 struct FastSmem {
     int roiPitch, scorePitch;
     int roiOff, scoreOff, listOff, queueOff, total;     // v1 kernel
-    int entryOff, maskOff, barOff, total2, qCap;        // two-phase kernel (qCap = entries the queue holds)
+    int entryOff, maskOff, total2, qCap;                // two-phase kernel (qCap = entries the queue holds)
 };
 __host__ __device__ inline FastSmem fast_smem_layout(int maxCw, int maxCh, int maxSlotCap) {
     FastSmem s;
     const int G = (maxCw - 6 + 3) / 4;      // 4-pixel groups per interior row
-    // ROI column x lives at byte x+1; a group reads bytes 4g..4g+11.  The pitch is a multiple of 16 bytes so that a TMA box
-    // (inner extent = pitch) can fill the ROI.
-    s.roiPitch = (4 * G + 8 + 15) & ~15;
-    s.scorePitch = s.roiPitch;              // interior column c lives at byte c+4
+    s.roiPitch = 4 * G + 8;                 // ROI column x lives at byte x+1; a group reads bytes 4g..4g+11
+    s.scorePitch = 4 * G + 8;               // interior column c lives at byte c+4
     s.roiOff = 0;
     s.scoreOff = s.roiOff + s.roiPitch * maxCh;
     s.listOff = s.scoreOff + s.scorePitch * (maxCh - 6 + 2);
@@ -331,8 +329,7 @@ __host__ __device__ inline FastSmem fast_smem_layout(int maxCw, int maxCh, int m
     s.qCap = (nPix / 2 + 1) & ~1;
     s.entryOff = (s.listOff + 3) & ~3;
     s.maskOff = s.entryOff + 2 * s.qCap + 4;             // one pass-mask byte per 4-pixel group, padded to 128 groups per lane quartet
-    s.barOff = (s.maskOff + G * (maxCh - 6) + 128 + 7) & ~7;   // the warp's mbarrier (TMA completion)
-    s.total2 = (s.barOff + 8 + 127) & ~127;              // slots are 128-byte aligned (TMA destination)
+    s.total2 = (s.maskOff + G * (maxCh - 6) + 128 + 15) & ~15;
     return s;
 }
 
@@ -656,12 +653,12 @@ struct FastRange {
     int tallBase, nTall, tallCw, tallCh;          // tall cells
     int tallSlots, nTallBlocks;
     int2 *denseList; int *denseN;                 // (frame, cell) pairs whose candidates overflow the entry queue
-    int useTma;                                   // ROI staging by TMA box loads (maps[level], box = ROI pitch × the level's cell height)
-    int boxRows[ORBX_MAX_LEVELS];                 // box height of each level's map
 };
-// RP: compile-time ROI pitch (0 = take it from the layout at run time); the usual cells need 48 or 64 bytes per row
+// RP: compile-time ROI pitch (0 = take it from the layout at run time); the usual cells (35-44 px) need 44, 48 or 52 bytes per row.
+// (The ROI is staged with ordinary loads: a TMA box must start on a 16-byte boundary of the image row — measured on this B200,
+// tools/microbench/tma_probe.cu — which cell ROIs do not; the pyramid and blur tiles, whose origin is free, use TMA.)
 template <int WPB, int RP>
-__global__ void __launch_bounds__(WPB * 32, 2048 / (WPB * 32 * 2)) k_fast_cells(ExParams p, const __grid_constant__ FastRange R, const __grid_constant__ OrbxTmaMaps maps) {   // ≤ 64 registers: 32 warps per SM
+__global__ void __launch_bounds__(WPB * 32, 2048 / (WPB * 32 * 2)) k_fast_cells(ExParams p, const __grid_constant__ FastRange R) {   // ≤ 64 registers: 32 warps per SM
 
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const OrbxGeom &g = *p.g;
@@ -699,16 +696,7 @@ __global__ void __launch_bounds__(WPB * 32, 2048 / (WPB * 32 * 2)) k_fast_cells(
     }
     const int rp = RP ? RP : L.roiPitch;   // == score pitch
     // stage the ROI: column x at byte x+1 so that every 4-pixel group is word aligned
-    uint64_t *bar = reinterpret_cast<uint64_t *>(base + L.barOff);
-    if (R.useTma) {
-        // one TMA box per cell: rp bytes × the level's cell height starting at (x0 - 1, y0) of frame b; bytes beyond the ROI (and
-        // beyond the image: zero-filled) are never read.  The zeroing of the score map below overlaps the transfer.
-        if (lane == 0) {
-            mbar_init(bar, 1);
-            mbar_expect_tx(bar, (uint32_t)(rp * R.boxRows[cell.level]));
-            tma_load_3d(roi, &maps.m[cell.level], bar, cell.x0 - 1, cell.y0, b);
-        }
-    } else {
+    {
     const uint8_t *src = img + (long long)cell.y0 * pitch + cell.x0;
     if (((((unsigned long long)img) | (unsigned)pitch) & 3ull) == 0) {
         // aligned 32-bit loads: shared-memory word k of a row holds image columns x0-1+4k .. x0+2+4k, i.e. the two
@@ -742,7 +730,6 @@ __global__ void __launch_bounds__(WPB * 32, 2048 / (WPB * 32 * 2)) k_fast_cells(
         for (int i = lane; i < nw; i += 32) s32[i] = 0;
     }
     __syncwarp();
-    if (R.useTma) mbar_wait(bar, 0);         // the ROI has landed (the barrier completes its first phase)
 
     const int G = (iw + 3) >> 2;             // 4-pixel groups per interior row (≤ 19 for cells ≤ 75 px wide)
     const int nGroups = G * ih;              // groups of the cell in row-major order: lane work items
@@ -2280,7 +2267,7 @@ struct orbx_extractor {
     long long oneLaunches = 0;
     bool useGraph = true;
     uint8_t *d_sm = nullptr; size_t smCap = 0;     // scratch of orbx_stereo_matches
-    bool useTma = true, useTmaPyr = true;   // ORBX_NO_TMA: stage tiles with ordinary loads (same results; cross-check and fallback)
+    bool useTmaPyr = true;          // ORBX_NO_TMA: stage tiles with ordinary loads (same results; cross-check and fallback)
 
     // device buffers (sized for maxW × maxH × maxBatch at create)
     OrbxGeom *d_geom = nullptr;
@@ -2662,7 +2649,7 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
             A2.tabX = ex->d_tabX + ex->h_tabXOff[l]; A2.tabY = ex->d_tabY + ex->h_tabYOff[l];
             A2.tilesX = (DV.w + 127) / 128;
             A2.nStrips = A2.tilesX * ((DV.h + PYR2_RS - 1) / PYR2_RS);
-            A2.boxW = orbx_align_up((int)ceil(127.0 * SV.w / DV.w) + 1 + 12, 16);
+            A2.boxW = orbx_align_up((int)ceil(127.0 * SV.w / DV.w) + 1 + 12 + 15, 16);
             A2.boxH = (int)ceil((PYR2_RS - 1) * (double)SV.h / DV.h) + 3;
             A2.slotBytes = orbx_align_up(A2.boxW * A2.boxH + 8, 128);
             CUtensorMap srcMap;
@@ -2737,34 +2724,17 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
                 if (nC > 0) grp[nGrp++] = Grp{cellBase, nC, cwMax, chMax, (size_t)fast_smem_layout(cwMax, chMax, 1).total2, l0, l1};
                 l0 = l1;
             }
-            // ROI staging by TMA: one map per level, box = the ROI pitch of the level's group × the level's cell height.  Level 0 may be
-            // the caller's own buffer, whose pitch need not meet TMA's alignment rules: then every cell is staged with ordinary loads.
-            OrbxTmaMaps maps;
-            memset(&maps, 0, sizeof(maps));
-            int boxRows[ORBX_MAX_LEVELS] = {0};
-            bool tmaOk = ex->useTma;
-            for (int gi = 0; gi < nGrp && tmaOk; ++gi) {
-                const int rpG = fast_smem_layout(grp[gi].cw, grp[gi].ch, 1).roiPitch;
-                for (int l = grp[gi].l0; l < grp[gi].l1 && tmaOk; ++l) {
-                    const OrbxLevel &V = G.lv[l];
-                    if (V.nCells <= 0) continue;
-                    boxRows[l] = V.hCell + 6;
-                    const uint8_t *base = l == 0 ? P.in0 : P.pyr + V.off;
-                    tmaOk = tma_encode_level(&maps.m[l], base, V.w, V.h, batch, l == 0 ? P.in0Pitch : V.pitch, l == 0 ? P.in0Stride : G.frameBytes, rpG, boxRows[l]);
-                }
-            }
             auto launch_fast = [&](FastRange R, dim3 grid, size_t smem) -> int {
-                R.useTma = tmaOk ? 1 : 0;
-                for (int l = 0; l < ORBX_MAX_LEVELS; ++l) R.boxRows[l] = boxRows[l];
                 const int rpA = fast_smem_layout(R.cw, R.ch, 1).roiPitch, rpB = R.nTall > 0 ? fast_smem_layout(R.tallCw, R.tallCh, 1).roiPitch : rpA;
                 const int rpSel = rpA == rpB ? rpA : 0;         // compile-time ROI pitch for the two usual widths
 #define ORBX_LAUNCH_FAST(RPV)                                                                                                             \
                 do {                                                                                                                      \
                     if (smem > 48 * 1024) CUDA_TRY(ex, cudaFuncSetAttribute(k_fast_cells<WPB, RPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-                    k_fast_cells<WPB, RPV><<<grid, WPB * 32, smem, s>>>(P, R, maps);                                                       \
+                    k_fast_cells<WPB, RPV><<<grid, WPB * 32, smem, s>>>(P, R);                                                       \
                 } while (0)
-                if (rpSel == 48) ORBX_LAUNCH_FAST(48);
-                else if (rpSel == 64) ORBX_LAUNCH_FAST(64);
+                if (rpSel == 44) ORBX_LAUNCH_FAST(44);
+                else if (rpSel == 48) ORBX_LAUNCH_FAST(48);
+                else if (rpSel == 52) ORBX_LAUNCH_FAST(52);
                 else ORBX_LAUNCH_FAST(0);
 #undef ORBX_LAUNCH_FAST
                 ++ex->launches;
@@ -3021,10 +2991,7 @@ orbx_extractor *orbx_create(int nfeatures, float scale_factor, int nlevels, int 
     ex->useHistQuadtree = getenv("ORBX_LEGACY_QUADTREE") == nullptr;
     ex->fastV1 = getenv("ORBX_FAST_V1") != nullptr;
     ex->useGraph = getenv("ORBX_NO_GRAPH") == nullptr;
-    if (const char *e = getenv("ORBX_NO_TMA")) {          // same results either way; tiles are then staged with ordinary loads ("fast" / "pyr": only that stage)
-        ex->useTma = strcmp(e, "pyr") == 0;
-        ex->useTmaPyr = strcmp(e, "fast") == 0;
-    }      // same kernels either way; the graph only removes launch overhead
+    ex->useTmaPyr = getenv("ORBX_NO_TMA") == nullptr;     // same results either way; tiles are then staged with ordinary loads      // same kernels either way; the graph only removes launch overhead
     CREATE_TRY(cudaMalloc((void **)&ex->d_nOut, (size_t)max_batch * sizeof(int)));
     CREATE_TRY(cudaMalloc((void **)&ex->d_mono, (size_t)max_batch * sizeof(int)));
     CREATE_TRY(cudaHostAlloc((void **)&ex->h_nOut, (size_t)max_batch * sizeof(int), cudaHostAllocDefault));
