@@ -161,9 +161,9 @@ __global__ void __launch_bounds__(WPB * 32) k_pyr_level_tma(Pyr2Args a, const __
     }
     const uint32_t selWin = 0x3210u + 0x1111u * (uint32_t)(rel0 & 3);
     const uint8_t *Tw = T + (rel0 & ~3);
-    const int boxW = a.boxW, lastRow = a.boxH - 1;
-    auto hrow = [&](int r, uint32_t (&h)[4]) {
-        const uint32_t *q = reinterpret_cast<const uint32_t *>(Tw + min(r, lastRow) * boxW);
+    const int boxW = a.boxW;
+    auto hrow = [&](const uint8_t *rowp, uint32_t (&h)[4]) {
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(rowp);
         const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
         const uint32_t lo = __byte_perm(w0, w1, selWin), hi = __byte_perm(w1, w2, selWin);   // the 8 bytes from S[s0 of column 0]
 #pragma unroll
@@ -173,8 +173,9 @@ __global__ void __launch_bounds__(WPB * 32) k_pyr_level_tma(Pyr2Args a, const __
     mbar_wait(bar, 0);
     uint32_t hA[4], hB[4];
     int curA = 0;
-    hrow(0, hA);
-    hrow(1, hB);
+    const uint8_t *rowB = Tw + boxW;                     // staged row of hB (the box holds one row more than the strip needs)
+    hrow(Tw, hA);
+    hrow(rowB, hB);
     uint8_t *Dp = a.dst + (long long)b * a.dstStride + (long long)y0 * a.dp + gx;
     const int nRows = min(PYR2_RS, a.dh - y0);
     for (int yy = 0; yy < nRows; ++yy, Dp += a.dp) {
@@ -184,17 +185,18 @@ __global__ void __launch_bounds__(WPB * 32) k_pyr_level_tma(Pyr2Args a, const __
 #pragma unroll
             for (int j = 0; j < 4; ++j) hA[j] = hB[j];
             ++curA;
-            hrow(curA + 1, hB);
+            rowB += boxW;
+            hrow(rowB, hB);
+        }
+        if (i1 == i0) {                                  // clamped at the bottom edge (warp-uniform, stays so for the rest of the strip)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hB[j] = hA[j];
         }
         const uint32_t b0 = cf & 0xffffu, b1 = cf >> 16;
-        const bool same = i1 == i0;                      // clamped at the bottom edge
-        uint32_t out = 0;
+        uint32_t v[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t u0 = hA[j], u1 = same ? hA[j] : hB[j];
-            const uint32_t v = (((b0 * u0) >> 16) + ((b1 * u1) >> 16) + 2u) >> 2;
-            out += v << (8 * j);                         // v <= 255: bytes pack by addition
-        }
+        for (int j = 0; j < 4; ++j) v[j] = (((b0 * hA[j]) >> 16) + ((b1 * hB[j]) >> 16) + 2u) >> 2;
+        const uint32_t out = v[0] + v[1] * 256u + v[2] * 65536u + v[3] * 16777216u;   // v <= 255: bytes pack by multiply-add
         if (act) *reinterpret_cast<uint32_t *>(Dp) = out;   // pitch is a multiple of 128: the padding is writable
     }
 }
@@ -2003,6 +2005,89 @@ __global__ void __launch_bounds__(WPB * 32, 2048 / (WPB * 32)) k_orient_desc(ExP
     if (lane == 0) p.kps[(long long)b * p.cap + wk.out].angle = angle;
 }
 
+// TMA form of the same kernel: the two patches a keypoint needs — 31 rows of the unblurred level for the moments, 37 rows of the
+// blurred level for the rotated pattern (|offset| <= 18) — arrive as two box loads per warp instead of ~1260 scattered byte
+// loads through L1; all further reads are shared-memory bytes.  A box starts on a 16-byte boundary of the image row, so the
+// patch sits at a per-keypoint byte offset (0..15) inside its box.  Same arithmetic, same results.
+#define OD_AW 48     // unblurred box: 15 (alignment slack) + 31 columns, rounded to 16
+#define OD_AH 31
+#define OD_BW 64     // blurred box: 15 + 37 columns, rounded to 16
+#define OD_BH 37
+#define OD_SLOT 4096 // per-warp shared memory: [A box 1488][pad to 1536][B box 2368][pad][mbarrier]
+template <int WPB>
+__global__ void __launch_bounds__(WPB * 32, 2048 / (WPB * 32)) k_orient_desc_tma(ExParams p, const __grid_constant__ OrbxTmaMaps pyrMaps,
+                                                                                   const __grid_constant__ OrbxTmaMaps blurMaps) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const OrbxGeom &g = *p.g;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * WPB + warp, b = blockIdx.y;
+    if (i >= p.workCnt[b]) return;
+    const OrbxWork wk = p.work[(long long)b * g.selTotal + i];
+    if (wk.out < 0) return;
+    uint8_t *A = smem_raw + (size_t)warp * OD_SLOT, *B = A + 1536;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(A + OD_SLOT - 8);
+    const int xa = (wk.cx - ORBX_HALF_PATCH) & ~15, xb = (wk.cx - 18) & ~15;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, OD_AW * OD_AH + OD_BW * OD_BH);
+        tma_load_3d(A, &pyrMaps.m[wk.level], bar, xa, wk.cy - ORBX_HALF_PATCH, b);
+        tma_load_3d(B, &blurMaps.m[wk.level], bar, xb, wk.cy - 18, b);
+    }
+    // pattern words of this lane's descriptor byte (while the boxes are in flight)
+    const int4 *pat4 = reinterpret_cast<const int4 *>(p.pattern) + lane * 2;   // 8 tests × (x0, y0, x1, y1) int8
+    const int4 q0 = pat4[0], q1 = pat4[1];
+    __syncwarp();
+    mbar_wait(bar, 0);
+    constexpr int UMAX[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+    const int u = lane - ORBX_HALF_PATCH;
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const uint8_t *pr = A + (wk.cx - ORBX_HALF_PATCH - xa) + lane;      // row v = -15 of column u
+        const int au = u < 0 ? -u : u;
+        int colSum = 0;
+#pragma unroll
+        for (int v = -ORBX_HALF_PATCH; v <= ORBX_HALF_PATCH; ++v, pr += OD_AW) {
+            if (au <= UMAX[v < 0 ? -v : v]) {
+                const int val = *pr;
+                colSum += val;
+                m01 += v * val;
+            }
+        }
+        m10 = u * colSum;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+    }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+    const float factorPI = (float)(3.141592653589793238462643383279502884 / 180.f);
+    const float rad = __fmul_rn(angle, factorPI);
+    const float ca = orbx_libm::cosf_glibc(rad), sa = orbx_libm::sinf_glibc(rad);
+    const uint8_t *bl = B + 18 * OD_BW + (wk.cx - xb);                      // the keypoint's pixel inside the blurred box
+    const int words[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    int byte = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int wv = words[j];
+        const float tx0 = (float)(signed char)(wv & 0xff), ty0 = (float)(signed char)((wv >> 8) & 0xff);
+        const float tx1 = (float)(signed char)((wv >> 16) & 0xff), ty1 = (float)(signed char)((wv >> 24) & 0xff);
+        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(tx0, sa), __fmul_rn(ty0, ca)));
+        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(tx0, ca), __fmul_rn(ty0, sa)));
+        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(tx1, sa), __fmul_rn(ty1, ca)));
+        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(tx1, ca), __fmul_rn(ty1, sa)));
+        const int v0 = bl[r0 * OD_BW + c0], v1 = bl[r1 * OD_BW + c1];
+        byte |= (v0 < v1) << j;
+    }
+    uint32_t word = (uint32_t)byte;
+    word |= __shfl_down_sync(0xffffffffu, (uint32_t)byte, 1) << 8;
+    word |= __shfl_down_sync(0xffffffffu, (uint32_t)byte, 2) << 16;
+    word |= __shfl_down_sync(0xffffffffu, (uint32_t)byte, 3) << 24;
+    uint8_t *d = p.desc + ((long long)b * p.cap + wk.out) * 32;
+    if ((lane & 3) == 0) reinterpret_cast<uint32_t *>(d)[lane >> 2] = word;
+    if (lane == 0) p.kps[(long long)b * p.cap + wk.out].angle = angle;
+}
+
 // packed host layout (rows of `cols` bytes, frames back to back) → pitched level-0 planes of the internal pyramid
 __global__ void k_repitch(const uint8_t *__restrict__ packed, int rows, int cols, uint8_t *__restrict__ dst, long long frameBytes, int pitch) {
     const int b = blockIdx.z, y = blockIdx.y;
@@ -2650,7 +2735,7 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
             A2.tilesX = (DV.w + 127) / 128;
             A2.nStrips = A2.tilesX * ((DV.h + PYR2_RS - 1) / PYR2_RS);
             A2.boxW = orbx_align_up((int)ceil(127.0 * SV.w / DV.w) + 1 + 12 + 15, 16);
-            A2.boxH = (int)ceil((PYR2_RS - 1) * (double)SV.h / DV.h) + 3;
+            A2.boxH = (int)ceil((PYR2_RS - 1) * (double)SV.h / DV.h) + 4;
             A2.slotBytes = orbx_align_up(A2.boxW * A2.boxH + 8, 128);
             CUtensorMap srcMap;
             const bool ok = A2.boxW <= 256 && A2.boxH <= 256 &&
@@ -2849,7 +2934,23 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
     {
         const int WPB = 8;
         dim3 grd((G.selTotal + WPB - 1) / WPB, batch);
-        k_orient_desc<WPB><<<grd, WPB * 32, 0, s>>>(P);
+        bool tmaOk = ex->useTmaPyr;
+        OrbxTmaMaps pyrMaps, blurMaps;
+        if (tmaOk) {
+            memset(&pyrMaps, 0, sizeof(pyrMaps)); memset(&blurMaps, 0, sizeof(blurMaps));
+            for (int l = 0; l < G.nlevels && tmaOk; ++l) {
+                const OrbxLevel &V = G.lv[l];
+                tmaOk = tma_encode_level(&pyrMaps.m[l], l == 0 ? P.in0 : P.pyr + V.off, V.w, V.h, batch, l == 0 ? P.in0Pitch : V.pitch,
+                                         l == 0 ? P.in0Stride : G.frameBytes, OD_AW, OD_AH) &&
+                        tma_encode_level(&blurMaps.m[l], P.blur + V.off, V.w, V.h, batch, V.pitch, G.frameBytes, OD_BW, OD_BH);
+            }
+        }
+        if (tmaOk) {
+            const size_t smemO = (size_t)OD_SLOT * WPB;
+            k_orient_desc_tma<WPB><<<grd, WPB * 32, smemO, s>>>(P, pyrMaps, blurMaps);
+        } else {
+            k_orient_desc<WPB><<<grd, WPB * 32, 0, s>>>(P);
+        }
         ++ex->launches;
     }
     if (prof) { CUDA_TRY(ex, cudaEventRecord(ex->ev[6], s)); ex->evPending = true; }
