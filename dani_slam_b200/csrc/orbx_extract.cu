@@ -112,6 +112,11 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
                  ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1 (TMA form): one pyramid level, one WARP per strip of 128 destination columns × PYR2_RS destination rows, no block barrier.
 // Lane 0 fetches the strip's source rows with one TMA box load; every lane owns 4 destination columns, whose source bytes all
@@ -1824,8 +1829,11 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i;
 }
 
-__global__ void __launch_bounds__(64 * BLUR_STRIPS) k_blur(ExParams p, const BlurTile *tiles) {
-    __shared__ __align__(16) uint8_t tile[(BLUR_TH + 6) * BLUR_SP];
+// tmaMask bit l: level l is staged with ONE TMA box per tile (maps.m[l]: rows viewed as 16-byte chunks, box 18 chunks × 38 rows; rows
+// and chunks outside the image arrive as zeros, the ≤ 3 reflected rows at the top / bottom edge are then copied inside shared memory).
+__global__ void __launch_bounds__(64 * BLUR_STRIPS) k_blur(ExParams p, const BlurTile *tiles, const __grid_constant__ OrbxTmaMaps maps, int tmaMask) {
+    __shared__ __align__(128) uint8_t tile[(BLUR_TH + 6) * BLUR_SP];
+    __shared__ __align__(8) uint64_t tileBar;
     const OrbxGeom &g = *p.g;
     const BlurTile T = tiles[blockIdx.x];
     const int b = blockIdx.y;
@@ -1837,6 +1845,26 @@ __global__ void __launch_bounds__(64 * BLUR_STRIPS) k_blur(ExParams p, const Blu
     const int tx0 = T.tx * BLUR_TW, ty0 = T.ty * BLUR_TH;
     const int tid = threadIdx.y * 64 + threadIdx.x;
     const bool aligned = ((((unsigned long long)src | (unsigned)pitch) & 15ull) == 0);
+    if ((tmaMask >> l) & 1) {
+        if (tid == 0) {
+            mbar_init(&tileBar, 1);
+            mbar_expect_tx(&tileBar, (BLUR_TH + 6) * BLUR_SP);
+            tma_load_4d(tile, &maps.m[l], &tileBar, 0, (tx0 - 16) >> 4, ty0 - 3, b);
+        }
+        __syncthreads();                       // the barrier is initialised before anyone polls it
+        mbar_wait(&tileBar, 0);
+        // REFLECT_101 rows above the first / below the last image row (only tiles that touch those edges)
+        if (ty0 == 0 || ty0 + BLUR_TH + 3 > h) {
+            for (int i = tid; i < (BLUR_TH + 6) * (BLUR_SP / 16); i += 64 * BLUR_STRIPS) {
+                const int r = i / (BLUR_SP / 16), c = i - r * (BLUR_SP / 16);
+                const int gy = ty0 + r - 3;
+                if (gy < 0 || (gy >= h && gy <= h + 2)) {
+                    const int sr = reflect101(gy, h) - (ty0 - 3);
+                    *reinterpret_cast<uint4 *>(&tile[r * BLUR_SP + 16 * c]) = *reinterpret_cast<const uint4 *>(&tile[sr * BLUR_SP + 16 * c]);
+                }
+            }
+        }
+    } else
     // stage rows ty0-3 .. ty0+BLUR_TH+2 (reflected), columns tx0-16 .. tx0+BLUR_TW+15 (clipped to the row)
     {
         const int nChunks = BLUR_SP / 16;
@@ -1900,13 +1928,13 @@ __global__ void __launch_bounds__(64 * BLUR_STRIPS) k_blur(ExParams p, const Blu
         if (r >= 6) {
             const int gy = y0 + r - 6;
             if (gy < h) {
-                uint32_t out = 0;
+                uint32_t v[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint32_t v = 18u * (ring[(r - 6) % 7][i] + ring[r % 7][i]) + 34u * (ring[(r - 5) % 7][i] + ring[(r - 1) % 7][i]) +
-                                       48u * (ring[(r - 4) % 7][i] + ring[(r - 2) % 7][i]) + 56u * ring[(r - 3) % 7][i];
-                    out |= ((v + 32768u) >> 16) << (8 * i);
-                }
+                for (int i = 0; i < 4; ++i)
+                    v[i] = 18u * (ring[(r - 6) % 7][i] + ring[r % 7][i]) + 34u * (ring[(r - 5) % 7][i] + ring[(r - 1) % 7][i]) +
+                           48u * (ring[(r - 4) % 7][i] + ring[(r - 2) % 7][i]) + 56u * ring[(r - 3) % 7][i] + 32768u;
+                // (v + 32768) >> 16 is byte 2 of each sum (sums stay below 2^24): three PRMT gather the four output bytes
+                const uint32_t out = __byte_perm(__byte_perm(v[0], v[1], 0x0062u), __byte_perm(v[2], v[3], 0x0062u), 0x5410u);
                 *reinterpret_cast<uint32_t *>(dst + (long long)gy * LV.pitch) = out;
             }
         }
@@ -2685,6 +2713,22 @@ bool tma_encode_level(CUtensorMap *out, const void *base, int w, int h, int batc
               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// rank-4 u8 map that views every row as chunks of 16 bytes: (byte in chunk, chunk, row, frame).  A box of {16, nChunks, rows, 1} lands in
+// shared memory as rows of 16·nChunks bytes — wider than the 256-element limit of one box dimension — and starts on a chunk boundary by
+// construction.  Chunks at or beyond ceil(w / 16) and rows outside [0, h) read as zero.
+bool tma_encode_chunked(CUtensorMap *out, const void *base, int w, int h, int batch, long long pitch, long long planeStride, int boxChunks, int boxRows) {
+    PFN_orbxTmaEncode fn = tma_encoder();
+    if (!fn) return false;
+    if (((uintptr_t)base & 15) || (pitch & 15) || (planeStride & 15) || boxChunks < 1 || boxChunks > 256 || boxRows < 1 || boxRows > 256 || w < 1 || h < 1) return false;
+    if ((long long)((w + 15) / 16) * 16 > pitch) return false;       // the last chunk of a row must lie inside the row's pitch
+    const cuuint64_t dims[4] = {16, (cuuint64_t)((w + 15) / 16), (cuuint64_t)h, (cuuint64_t)std::max(batch, 1)};
+    const cuuint64_t strides[3] = {16, (cuuint64_t)pitch, (cuuint64_t)planeStride};
+    const cuuint32_t box[4] = {16u, (cuuint32_t)boxChunks, (cuuint32_t)boxRows, 1u};
+    const cuuint32_t es[4] = {1u, 1u, 1u, 1u};
+    return fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int harvest_stage_times(orbx_extractor *ex) {
     if (!ex->evPending) return ORBX_OK;
     CUDA_TRY(ex, cudaEventSynchronize(ex->ev[6]));
@@ -2853,6 +2897,17 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
         }
     }
     if (prof) CUDA_TRY(ex, cudaEventRecord(ex->ev[2], s));
+    // blur tiles come in by TMA where the level's layout allows it (level 0 may be the caller's own buffer)
+    OrbxTmaMaps blurSrcMaps;
+    int blurTmaMask = 0;
+    memset(&blurSrcMaps, 0, sizeof(blurSrcMaps));
+    if (ex->useTmaPyr)
+        for (int l = 0; l < G.nlevels; ++l) {
+            const OrbxLevel &V = G.lv[l];
+            if (tma_encode_chunked(&blurSrcMaps.m[l], l == 0 ? P.in0 : P.pyr + V.off, V.w, V.h, batch, l == 0 ? P.in0Pitch : V.pitch,
+                                   l == 0 ? P.in0Stride : G.frameBytes, BLUR_SP / 16, BLUR_TH + 6))
+                blurTmaMask |= 1 << l;
+        }
     // K5 early, on the partner stream: the blurred levels depend on the pyramid only; started once FAST is done, the
     // instruction-bound blur fills the SMs while the latency-bound quadtree kernels run
     int aux = -1;
@@ -2862,7 +2917,7 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
         CUDA_TRY(ex, cudaEventRecord(ex->evPyrDone[aux], s));
         CUDA_TRY(ex, cudaStreamWaitEvent(ex->sAux[aux], ex->evPyrDone[aux], 0));
         dim3 grdB((unsigned)ex->h_tiles.size(), batch);
-        k_blur<<<grdB, dim3(64, BLUR_STRIPS), 0, ex->sAux[aux]>>>(P, ex->d_tiles);
+        k_blur<<<grdB, dim3(64, BLUR_STRIPS), 0, ex->sAux[aux]>>>(P, ex->d_tiles, blurSrcMaps, blurTmaMask);
         ++ex->launches;
         CUDA_TRY(ex, cudaEventRecord(ex->evBlurDone[aux], ex->sAux[aux]));
     }
@@ -2924,7 +2979,7 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
     // K5 (serial form; see above for the overlapped one)
     if (aux < 0) {
         dim3 grd((unsigned)ex->h_tiles.size(), batch);
-        k_blur<<<grd, dim3(64, BLUR_STRIPS), 0, s>>>(P, ex->d_tiles);
+        k_blur<<<grd, dim3(64, BLUR_STRIPS), 0, s>>>(P, ex->d_tiles, blurSrcMaps, blurTmaMask);
         ++ex->launches;
     } else {
         CUDA_TRY(ex, cudaStreamWaitEvent(s, ex->evBlurDone[aux], 0));
