@@ -1,0 +1,275 @@
+// orbx_knn_tc.cu — brute-force Hamming kNN (k = 2) on the 5th-generation tensor cores (tcgen05 / TMEM), sm_100a.
+//
+// For bit vectors q, d ∈ {0,1}^256:  hamming(q, d) = |q| + |d| − 2·(q · d).  The dot products of a tile of 128 queries with a
+// tile of 256 database rows are ONE 128×256×256 integer GEMM: the bits are expanded to 0/1 bytes in shared memory (K-major,
+// 128-byte swizzle — the canonical UMMA operand layout), `tcgen05.mma.kind::i8` accumulates exactly in int32 in tensor memory,
+// and the epilogue reads the accumulators back with `tcgen05.ld`, forms packed (distance << 23 | row) keys and keeps the two
+// smallest per query — the same keys, tie rule (lower row first) and per-chunk partial format as the POPC kernel in
+// orbx_match.cu, whose merge kernel finishes the job.  Results are bit-identical to the POPC path (tests/test_match_gpu.py).
+//
+// One CTA = one tile of 128 queries × one chunk of database rows; warp roles (13 warps):
+//   warp 0        allocates tensor memory; lane 0 issues the MMAs (8 per database tile: K = 8 × 32 bytes) and commits them
+//   warps 1-4     producers: read 256 database rows (32 B each, coalesced), expand them to the swizzled 0/1 byte tile of the
+//                 free stage, compute the rows' popcounts → per-column key bases
+//   warps 5-12    epilogue: two threads per query (column halves), 4 × `tcgen05.ld.32x32b.x32` each, min3 pre-reduction of the
+//                 keys and an exact top-2 insertion only for the 32-column groups that can improve the running second best
+// Three mbarrier pipelines connect them (shared-memory stage full/empty, accumulator full/empty), two stages each.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "orbx_internal.h"
+
+namespace {
+
+constexpr int TC_M = 128;             // queries per CTA
+constexpr int TC_N = 256;             // database rows per MMA tile
+constexpr int TC_KBYTES = 256;        // operand bytes per row (one byte per descriptor bit)
+constexpr int TC_PRODUCERS = 128;     // threads (warps 1-4)
+constexpr int TC_EPILOGUE = 256;      // threads (warps 5-12)
+constexpr int TC_THREADS = 32 + TC_PRODUCERS + TC_EPILOGUE;
+constexpr int TC_A_BYTES = TC_M * TC_KBYTES;            // 32 KB: two K-blocks of [128 rows][128 B]
+constexpr int TC_B_BYTES = TC_N * TC_KBYTES;            // 64 KB per stage: two K-blocks of [256 rows][128 B]
+constexpr int TC_SMEM = TC_A_BYTES + 2 * TC_B_BYTES + 2 * TC_N * 4 + 2048 /* barriers, tmem address, merge buffer */ + 1024 /* alignment slack */;
+constexpr uint32_t TC_IDX_BITS = 23;
+constexpr uint32_t TC_KEY_NONE = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint64_t *b, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive(uint64_t *b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory"); }
+__device__ __forceinline__ void bar_wait(uint64_t *b, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TC_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TC_DONE_%=;\n"
+        "bra TC_WAIT_%=;\n"
+        "TC_DONE_%=:\n"
+        "}\n" ::"r"(s32(b)), "r"(parity) : "memory");
+}
+
+// shared-memory matrix descriptor of a K-major operand slab [rows][128 B] with the 128-byte swizzle: start address (>> 4), leading
+// byte offset unused for swizzled K-major (1), stride byte offset = 8 rows × 128 B = 1024 (>> 4), descriptor version 1 (sm_100),
+// layout type 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smemAddr) {
+    return (uint64_t)((smemAddr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// byte offset of (row r, operand byte c < 128) inside such a slab: 16-byte chunks are XOR-swizzled with the row index modulo 8
+__device__ __forceinline__ uint32_t sw128(uint32_t r, uint32_t c) { return r * 128u + ((((c >> 4) ^ (r & 7u)) << 4) | (c & 15u)); }
+
+// four descriptor bits → four 0/1 bytes: (x · (1 + 2^7 + 2^14 + 2^21)) & 0x01010101 puts bit i into byte i
+__device__ __forceinline__ uint32_t spread4(uint32_t nib) { return ((nib & 0xfu) * 0x00204081u) & 0x01010101u; }
+// one 32-byte descriptor row → 256 operand bytes in the two K-block slabs of a tile (slab k holds operand bytes 128k … 128k+127)
+__device__ __forceinline__ void expand_row(uint8_t *slab0, uint32_t slabStride, uint32_t r, const uint4 &lo, const uint4 &hi) {
+    const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {                 // word i = descriptor bits 32i … 32i+31 = operand bytes 32i … 32i+31
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {             // 16 bits → one 16-byte chunk
+            const uint32_t x = w[i] >> (16 * h);
+            const uint4 v = make_uint4(spread4(x), spread4(x >> 4), spread4(x >> 8), spread4(x >> 12));
+            const uint32_t c = (uint32_t)(32 * i + 16 * h);            // operand byte of the chunk's first element
+            *reinterpret_cast<uint4 *>(slab0 + (c >> 7) * slabStride + sw128(r, c & 127u)) = v;
+        }
+    }
+}
+__device__ __forceinline__ int popc256(const uint4 &lo, const uint4 &hi) {
+    return __popc(lo.x) + __popc(lo.y) + __popc(lo.z) + __popc(lo.w) + __popc(hi.x) + __popc(hi.y) + __popc(hi.z) + __popc(hi.w);
+}
+__device__ __forceinline__ void top2_insert32(uint32_t k, uint32_t &a, uint32_t &b) {
+    const uint32_t hi = max(k, a);
+    a = min(k, a);
+    b = min(b, hi);
+}
+
+// grid (nChunks, ceil(nq / 128)); partial[chunk * nq + q] = {best key, second key} with rows relative to the chunk start
+__global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ db, long long ndb, long long chunkRows,
+                                                           uint2 *__restrict__ partial) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);   // the swizzle atoms need 1024-byte alignment
+    uint8_t *sA = smem;                                         // [2 K-blocks][128][128]
+    uint8_t *sB = smem + TC_A_BYTES;                            // [2 stages][2 K-blocks][256][128]
+    uint32_t *sBase = reinterpret_cast<uint32_t *>(sB + 2 * TC_B_BYTES);      // [2 stages][256]: (|d| << 23) + row of the column
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sBase + 2 * TC_N);          // full[2], empty[2], tfull[2], tempty[2]
+    uint32_t *tmemAddr = reinterpret_cast<uint32_t *>(bars + 8);
+    uint2 *sMerge = reinterpret_cast<uint2 *>(tmemAddr + 2);                  // [128]: the second column half's top-2 per query
+    uint64_t *full = bars, *empty = bars + 2, *tfull = bars + 4, *tempty = bars + 6;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q0 = blockIdx.y * TC_M;
+    const long long row0 = (long long)blockIdx.x * chunkRows;
+    const long long rowsHere = min(chunkRows, ndb - row0);
+    const int nTiles = (int)((rowsHere + TC_N - 1) / TC_N);
+
+    // ---- set-up: barriers, tensor memory, the query tile ----
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            bar_init(&full[s], TC_PRODUCERS);
+            bar_init(&empty[s], 1 + TC_EPILOGUE);               // the MMA commit + every epilogue thread (it reads sBase of the stage)
+            bar_init(&tfull[s], 1);
+            bar_init(&tempty[s], TC_EPILOGUE);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        __syncwarp();                                           // converged again after the tid == 0 branch (.sync.aligned below)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmemAddr)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int r = tid; r < TC_M; r += TC_THREADS) {              // queries beyond nq are zero rows (their results are not written)
+        uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+        if (q0 + r < nq) { lo = q[2 * (long long)(q0 + r)]; hi = q[2 * (long long)(q0 + r) + 1]; }
+        expand_row(sA, TC_M * 128, (uint32_t)r, lo, hi);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes → visible to the tensor core's async proxy
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmemAddr;
+
+    if (warp == 0) {
+        // ---- MMA issuer ----
+        if (lane == 0) {
+            // instruction descriptor (kind::i8): D = s32 (2 << 4), A and B unsigned 8-bit, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+            const uint32_t idesc = (2u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+            const uint32_t aBase = s32(sA);
+            for (int t = 0; t < nTiles; ++t) {
+                const int s = t & 1;
+                const uint32_t ph = (uint32_t)(t >> 1) & 1u;
+                bar_wait(&tempty[s], ph ^ 1u);                  // the epilogue has drained this accumulator
+                bar_wait(&full[s], ph);                         // the producers have filled this stage
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t bBase = s32(sB + s * TC_B_BYTES);
+                const uint32_t d = tmem + (uint32_t)(s * TC_N);
+#pragma unroll
+                for (int k = 0; k < TC_KBYTES / 32; ++k) {      // K = 32 bytes per MMA; 4 steps inside each 128-byte K-block
+                    const uint64_t ad = umma_desc(aBase + (uint32_t)(k >> 2) * (TC_M * 128) + (uint32_t)(k & 3) * 32);
+                    const uint64_t bd = umma_desc(bBase + (uint32_t)(k >> 2) * (TC_N * 128) + (uint32_t)(k & 3) * 32);
+                    const uint32_t acc = k > 0 ? 1u : 0u;
+                    asm volatile(
+                        "{\n"
+                        ".reg .pred p;\n"
+                        "setp.ne.b32 p, %4, 0;\n"
+                        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+                        "}\n" ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
+                }
+                // commits track the completion of everything issued so far: the stage's shared memory is free, the accumulator is full
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&empty[s])) : "memory");
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&tfull[s])) : "memory");
+            }
+        }
+    } else if (warp <= 4) {
+        // ---- producers ----
+        const int pt = tid - 32;                                // 0 … 127
+        for (int t = 0; t < nTiles; ++t) {
+            const int s = t & 1;
+            const uint32_t ph = (uint32_t)(t >> 1) & 1u;
+            bar_wait(&empty[s], ph ^ 1u);
+            uint8_t *slab = sB + s * TC_B_BYTES;
+            uint32_t *base = sBase + s * TC_N;
+            const long long tileRow = (long long)t * TC_N;
+#pragma unroll
+            for (int i = 0; i < TC_N / TC_PRODUCERS; ++i) {
+                const int r = pt + i * TC_PRODUCERS;
+                const long long lr = tileRow + r;               // row inside the chunk
+                uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+                uint32_t kb = TC_KEY_NONE;                      // columns past the end of the chunk never win
+                if (lr < rowsHere) {
+                    lo = db[2 * (row0 + lr)]; hi = db[2 * (row0 + lr) + 1];
+                    kb = ((uint32_t)popc256(lo, hi) << TC_IDX_BITS) + (uint32_t)lr;
+                }
+                expand_row(slab, TC_N * 128, (uint32_t)r, lo, hi);
+                base[r] = kb;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            bar_arrive(&full[s]);
+        }
+    } else {
+        // ---- epilogue: thread = (query row, column half) ----
+        const int et = tid - 32 - TC_PRODUCERS;                 // 0 … 255
+        const int ew = et >> 5;                                 // 0 … 7
+        const int quarter = warp & 3;                           // the TMEM lane quarter this warp may access is fixed by its id
+        const int half = ew >> 2;                               // 0: columns 0-127, 1: columns 128-255 (warps 5-8 / 9-12 cover each quarter once)
+        const int m = quarter * 32 + lane;                      // query row = TMEM lane
+        uint32_t qn23 = 0;
+        if (q0 + m < nq) {
+            const uint4 lo = q[2 * (long long)(q0 + m)], hi = q[2 * (long long)(q0 + m) + 1];
+            qn23 = (uint32_t)popc256(lo, hi) << TC_IDX_BITS;
+        }
+        uint32_t a = TC_KEY_NONE, b = TC_KEY_NONE;
+        for (int t = 0; t < nTiles; ++t) {
+            const int s = t & 1;
+            const uint32_t ph = (uint32_t)(t >> 1) & 1u;
+            bar_wait(&tfull[s], ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t *base = sBase + s * TC_N + half * 128;
+            const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * TC_N + half * 128);
+#pragma unroll 1
+            for (int g = 0; g < 4; ++g) {                       // 32 columns per load
+                uint32_t v[32];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, "
+                    "%22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+                      "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+                      "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+                      "=r"(v[31])
+                    : "r"(taddr + (uint32_t)(g * 32)));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                // key = ((|q| + |d| − 2·dot) << 23) + row = base + (|q| << 23) − (dot << 24); a column past the chunk end keeps key NONE
+                uint32_t kmin = TC_KEY_NONE;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const uint4 bs = *reinterpret_cast<const uint4 *>(base + g * 32 + j);
+                    const uint32_t bsv[4] = {bs.x, bs.y, bs.z, bs.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const uint32_t key = bsv[e] == TC_KEY_NONE ? TC_KEY_NONE : bsv[e] + (qn23 - (v[j + e] << 24));
+                        v[j + e] = key;
+                    }
+                    kmin = min(kmin, min(min(v[j], v[j + 1]), min(v[j + 2], v[j + 3])));
+                }
+                if (kmin < b) {                                 // this group can change the running top-2: exact insertion, in column order
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) top2_insert32(v[j], a, b);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            bar_arrive(&tempty[s]);
+            bar_arrive(&empty[s]);
+        }
+        // merge the two column halves of every query and write the chunk's partial result
+        if (half == 1) sMerge[m] = make_uint2(a, b);
+        asm volatile("bar.sync 1, %0;" ::"r"(TC_EPILOGUE) : "memory");      // named barrier: the 256 epilogue threads only
+        if (half == 0 && q0 + m < nq) {
+            const uint2 o = sMerge[m];
+            top2_insert32(o.x, a, b);
+            top2_insert32(o.y, a, b);
+            partial[(long long)blockIdx.x * nq + (q0 + m)] = make_uint2(a, b);
+        }
+    }
+    // ---- teardown ----
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    }
+}
+
+}  // namespace
+
+// launches the tensor-core kernel for chunks of `chunkRows` rows; partial as for the POPC kernel.  Returns cudaSuccess or the launch error.
+cudaError_t orbx_knn2_tc_launch(const uint8_t *d_q, int nq, const uint8_t *d_db, long long ndb, long long chunkRows, int nChunks, uint2 *d_partial,
+                                cudaStream_t stream) {
+    static bool attrSet = false;
+    if (!attrSet) {
+        cudaError_t e = cudaFuncSetAttribute(k_knn2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+        if (e != cudaSuccess) return e;
+        attrSet = true;
+    }
+    dim3 grid((unsigned)nChunks, (unsigned)((nq + TC_M - 1) / TC_M));
+    k_knn2_tc<<<grid, TC_THREADS, TC_SMEM, stream>>>(reinterpret_cast<const uint4 *>(d_q), nq, reinterpret_cast<const uint4 *>(d_db), ndb, chunkRows, d_partial);
+    return cudaGetLastError();
+}

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <limits.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <string>
@@ -602,7 +603,12 @@ struct orbx_matcher {
     uint8_t *d_buf = nullptr; size_t bufCap = 0;  // staging for the host-buffer entry points
     uint8_t *d_buf2 = nullptr; size_t buf2Cap = 0; // second arena: candidate lists whose size is only known after a count pass
     int nSM = 148;
+    long long tcLaunches = 0;      // tensor-core kNN launches since creation (test / bench evidence)
+    bool useTc = true;             // tensor-core kNN (orbx_knn_tc.cu) for large problems; ORBX_KNN_POPC keeps the POPC kernel (same results)
 };
+
+cudaError_t orbx_knn2_tc_launch(const uint8_t *d_q, int nq, const uint8_t *d_db, long long ndb, long long chunkRows, int nChunks, uint2 *d_partial,
+                                cudaStream_t stream);
 
 namespace {
 #define MCUDA_TRY(m, call)                                                                \
@@ -674,6 +680,7 @@ orbx_matcher *orbx_matcher_create(int device) {
         return nullptr;
     }
     cudaDeviceGetAttribute(&m->nSM, cudaDevAttrMultiProcessorCount, device);
+    m->useTc = getenv("ORBX_KNN_POPC") == nullptr;
     return m;
 }
 
@@ -688,6 +695,7 @@ void orbx_matcher_destroy(orbx_matcher *m) {
     delete m;
 }
 
+long long orbx_debug_knn_tc_launches(const orbx_matcher *m) { return m ? m->tcLaunches : 0; }
 const char *orbx_matcher_last_error(const orbx_matcher *m) { return m ? m->err.c_str() : tl_merr.c_str(); }
 void *orbx_matcher_stream(orbx_matcher *m) { return m ? (void *)m->stream : nullptr; }
 int orbx_matcher_sync(orbx_matcher *m) {
@@ -707,6 +715,27 @@ int orbx_hamming_knn2_device(orbx_matcher *m, const uint8_t *d_q, int nq, const 
     }
     if (nq == 0) return ORBX_OK;
     OrbxDeviceGuard dg_(m->device); MCUDA_TRY(m, dg_.status);
+    if (m->useTc && nq >= 64 && ndb >= 8192) {
+        // tensor-core path: CTAs of 128 queries × one DB chunk; about four waves of CTAs, chunk length a multiple of the 256-row MMA tile
+        const int qTilesTc = (nq + 127) / 128;
+        long long nCh = std::max(1LL, (long long)m->nSM * 4 / qTilesTc);
+        long long chunkRowsTc = (ndb + nCh - 1) / nCh;
+        chunkRowsTc = std::max(256LL, (chunkRowsTc + 255) / 256 * 256);
+        chunkRowsTc = std::min<long long>(chunkRowsTc, ((1LL << KNN_IDX_BITS) - 256) / 256 * 256);
+        const int nChunksTc = (int)((ndb + chunkRowsTc - 1) / chunkRowsTc);
+        const size_t needTc = (size_t)nChunksTc * nq;
+        if (needTc > m->partialCap || !m->d_partial) {
+            if (m->d_partial) { MCUDA_TRY(m, cudaStreamSynchronize(m->stream)); cudaFree(m->d_partial); }
+            m->d_partial = nullptr; m->partialCap = 0;
+            MCUDA_TRY(m, cudaMalloc((void **)&m->d_partial, needTc * sizeof(uint2)));
+            m->partialCap = needTc;
+        }
+        MCUDA_TRY(m, orbx_knn2_tc_launch(d_q, nq, d_db, ndb, chunkRowsTc, nChunksTc, m->d_partial, m->stream));
+        ++m->tcLaunches;
+        k_knn2_merge_partials<<<(nq * 32 + 255) / 256, 256, 0, m->stream>>>(m->d_partial, nq, nChunksTc, chunkRowsTc, idx_base, d_idx, d_dist);
+        MCUDA_TRY(m, cudaGetLastError());
+        return ORBX_OK;
+    }
     // queries per block tile: R·256; pick R so small problems still spread over the SMs
     const int R = nq > 2 * KNN_THREADS ? 4 : (nq > KNN_THREADS ? 2 : 1);
     const int qTiles = (nq + KNN_THREADS * R - 1) / (KNN_THREADS * R);

@@ -75,6 +75,8 @@ def lib() -> C.CDLL:
     L.orbx_matcher_stream.argtypes = [vp]
     L.orbx_matcher_sync.argtypes = [vp]
     L.orbx_hamming_knn2.argtypes = [vp, vp, i32, vp, i64, vp, vp]
+    L.orbx_debug_knn_tc_launches.restype = C.c_longlong
+    L.orbx_debug_knn_tc_launches.argtypes = [vp]
     L.orbx_hamming_knn2_device.argtypes = [vp, vp, i32, vp, i64, i64, vp, vp]
     L.orbx_knn2_merge_device.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     L.orbx_knn2_merge_packed_device.argtypes = [vp, vp, i32, i32, vp, vp]
@@ -485,6 +487,10 @@ class ORBmatcher:
         rc = self.L.orbx_knn2_sharded(self.h, comm.h, d_q, nq, d_db_shard, ndb_shard, idx_base, d_idx, d_dist)
         if rc != OK:
             raise OrbxError(rc, self.L.orbx_comm_last_error(comm.h).decode())
+
+    def tc_launches(self):
+        """Brute-force kNN calls of this matcher that ran on the tensor-core kernel."""
+        return self.L.orbx_debug_knn_tc_launches(self.h)
 
     def merge_packed_device(self, d_packed_all, n_shards, nq, d_idx, d_dist):
         self._chk(self.L.orbx_knn2_merge_packed_device(self.h, d_packed_all, n_shards, nq, d_idx, d_dist))

@@ -149,7 +149,9 @@ void *orbx_matcher_stream(orbx_matcher *m);
 int orbx_matcher_sync(orbx_matcher *m);
 
 /* BFMatcher(NORM_HAMMING).knnMatch(query, train, k=2): idx/dist are nq×2 (ascending distance, ties →
- * lower train index first); missing neighbours (ndb<2) are idx=-1, dist=INT32_MAX.  HOST buffers. */
+ * lower train index first); missing neighbours (ndb<2) are idx=-1, dist=INT32_MAX.  HOST buffers.
+ * Large problems (nq >= 64, ndb >= 8192) run as an integer GEMM on the tensor cores (Hamming = |q| + |d| − 2·q·d over 0/1
+ * bytes, tcgen05.mma.kind::i8, exact), small ones on the POPC kernel; both give identical results. */
 int orbx_hamming_knn2(orbx_matcher *m, const uint8_t *query, int nq, const uint8_t *train, int64_t ndb,
                       int32_t *idx, int32_t *dist);
 /* Same on DEVICE buffers, asynchronous on the matcher's stream.  idx_base is added to every train
@@ -313,6 +315,11 @@ int orbx_knn2_sharded_all(orbx_matcher *const *ms, orbx_comm *const *cs, int n, 
 int orbx_extract_batch_multi(orbx_extractor *const *exs, int n_handles, const uint8_t *const *images, int batch, int rows, int cols, size_t step,
                              const int32_t *rects_xywh, int n_rects, int lap0, int lap1, orbx_keypoint *keypoints, uint8_t *descriptors, int cap,
                              int32_t *n_out, int32_t *mono_index);
+
+/* Test hook: how many brute-force kNN calls of this matcher ran on the tensor-core kernel (csrc/orbx_knn_tc.cu: tcgen05.mma.kind::i8 over 0/1
+ * byte operands, exact int32 accumulation, fused top-2 epilogue; used for nq >= 64 and ndb >= 8192; ORBX_KNN_POPC in the environment
+ * keeps the POPC kernel — same results). */
+long long orbx_debug_knn_tc_launches(const orbx_matcher *m);
 
 /* Test hook: number of (frame, level) pairs of the last batch call that the histogram quadtree kernel handed to
  * the general quadtree kernel (trees deeper than its table); -1 if the histogram kernel is disabled. */

@@ -72,6 +72,25 @@ def test_sharded_merge_equals_unsharded_on_one_gpu(orbx_mod, oracle_mod):
         assert np.array_equal(oi.cpu().numpy(), ridx) and np.array_equal(od.cpu().numpy(), rdist), G
 
 
+@pytest.mark.parametrize("nq,ndb", [(64, 8192), (129, 8193), (2000, 100_003), (500, 262_144 + 255), (3000, 50_000)])
+def test_knn2_tensor_core_kernel_equals_popc_kernel_and_oracle(orbx_mod, oracle_mod, monkeypatch, nq, ndb):
+    """The tcgen05 GEMM path (nq >= 64, ndb >= 8192) and the POPC kernel give the same indices and distances, ties included
+    (duplicate rows, all-zero / all-one descriptors: distance 0 and 256), and both equal the oracle."""
+    from dani_slam_b200 import synth
+    q, db = synth.knn_case(nq, ndb, seed=nq * 7 + ndb, planted_frac=0.2, dup_rows=8)
+    db[5] = 0; db[6] = 255; q[1] = 0; q[2] = 255; db[ndb - 1] = db[ndb // 3]          # extremes and a tie across tiles
+    m = orbx_mod.ORBmatcher(0.7, True)
+    idx, dist = m.knnMatch(q, db)
+    assert m.tc_launches() == 1
+    monkeypatch.setenv("ORBX_KNN_POPC", "1")
+    mp = orbx_mod.ORBmatcher(0.7, True)
+    pidx, pdist = mp.knnMatch(q, db)
+    assert mp.tc_launches() == 0
+    assert np.array_equal(idx, pidx) and np.array_equal(dist, pdist)
+    ridx, rdist = oracle_mod.knn2(q, db, nthreads=8)
+    assert np.array_equal(idx, ridx) and np.array_equal(dist, rdist)
+
+
 def test_top2_lists_vs_oracle(orbx_mod, oracle_mod):
     rng = np.random.default_rng(5)
     from dani_slam_b200 import synth
