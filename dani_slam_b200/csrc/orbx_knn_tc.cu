@@ -7,12 +7,13 @@
 // smallest per query — the same keys, tie rule (lower row first) and per-chunk partial format as the POPC kernel in
 // orbx_match.cu, whose merge kernel finishes the job.  Results are bit-identical to the POPC path (tests/test_match_gpu.py).
 //
-// One CTA = one tile of 128 queries × one chunk of database rows; warp roles (13 warps):
+// One CTA = one tile of 128 queries × one chunk of database rows; warp roles (17 warps):
 //   warp 0        allocates tensor memory; lane 0 issues the MMAs (8 per database tile: K = 8 × 32 bytes) and commits them
-//   warps 1-4     producers: read 256 database rows (32 B each, coalesced), expand them to the swizzled 0/1 byte tile of the
-//                 free stage, compute the rows' popcounts → per-column key bases
-//   warps 5-12    epilogue: two threads per query (column halves), 4 × `tcgen05.ld.32x32b.x32` each, min3 pre-reduction of the
-//                 keys and an exact top-2 insertion only for the 32-column groups that can improve the running second best
+//   warps 1-8     producers: one database row per thread and tile (32 B, coalesced, prefetched one tile ahead), expanded to the
+//                 swizzled 0/1 byte tile of the free stage; the row's popcount goes into the per-column key base
+//   warps 9-16    epilogue: two threads per query (column halves), 4 × `tcgen05.ld.32x32b.x32` each; per column ONE multiply-add
+//                 forms a max-ordered key (2·dot − |d| in the high bits, inverted row below), a max3 tree pre-reduces 32 columns,
+//                 and the exact top-2 insertion runs only for the groups that can improve the running second best
 // Three mbarrier pipelines connect them (shared-memory stage full/empty, accumulator full/empty), two stages each.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -24,12 +25,13 @@ namespace {
 constexpr int TC_M = 128;             // queries per CTA
 constexpr int TC_N = 256;             // database rows per MMA tile
 constexpr int TC_KBYTES = 256;        // operand bytes per row (one byte per descriptor bit)
-constexpr int TC_PRODUCERS = 128;     // threads (warps 1-4)
-constexpr int TC_EPILOGUE = 256;      // threads (warps 5-12)
+constexpr int TC_PRODUCERS = 256;     // threads (warps 1-8): one database row each per tile
+constexpr int TC_EPILOGUE = 256;      // threads (warps 9-16)
 constexpr int TC_THREADS = 32 + TC_PRODUCERS + TC_EPILOGUE;
 constexpr int TC_A_BYTES = TC_M * TC_KBYTES;            // 32 KB: two K-blocks of [128 rows][128 B]
 constexpr int TC_B_BYTES = TC_N * TC_KBYTES;            // 64 KB per stage: two K-blocks of [256 rows][128 B]
 constexpr int TC_SMEM = TC_A_BYTES + 2 * TC_B_BYTES + 2 * TC_N * 4 + 2048 /* barriers, tmem address, merge buffer */ + 1024 /* alignment slack */;
+constexpr uint32_t TC_ROW_BITS = 22;     // rows of a chunk inside the max-ordered keys of the epilogue (chunks hold < 2^22 - 1 rows)
 constexpr uint32_t TC_IDX_BITS = 23;
 constexpr uint32_t TC_KEY_NONE = 0xffffffffu;
 
@@ -54,32 +56,27 @@ __device__ __forceinline__ void bar_wait(uint64_t *b, uint32_t parity) {
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smemAddr) {
     return (uint64_t)((smemAddr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
-// byte offset of (row r, operand byte c < 128) inside such a slab: 16-byte chunks are XOR-swizzled with the row index modulo 8
-__device__ __forceinline__ uint32_t sw128(uint32_t r, uint32_t c) { return r * 128u + ((((c >> 4) ^ (r & 7u)) << 4) | (c & 15u)); }
 
-// four descriptor bits → four 0/1 bytes: (x · (1 + 2^7 + 2^14 + 2^21)) & 0x01010101 puts bit i into byte i
+// four descriptor bits → four 0/1 bytes: (x · (1 + 2^7 + 2^14 + 2^21)) & 0x01010101 puts bit i into byte i.  (A byte → 8-byte table in
+// shared memory was slower: the kernel is bound by shared-memory bandwidth — operand writes plus the tensor core's operand reads.)
 __device__ __forceinline__ uint32_t spread4(uint32_t nib) { return ((nib & 0xfu) * 0x00204081u) & 0x01010101u; }
 // one 32-byte descriptor row → 256 operand bytes in the two K-block slabs of a tile (slab k holds operand bytes 128k … 128k+127)
 __device__ __forceinline__ void expand_row(uint8_t *slab0, uint32_t slabStride, uint32_t r, const uint4 &lo, const uint4 &hi) {
     const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    uint8_t *rowp = slab0 + r * 128u;
+    const uint32_t rx = (r & 7u) << 4;            // 16-byte chunks are XOR-swizzled with the row index modulo 8
 #pragma unroll
     for (int i = 0; i < 8; ++i) {                 // word i = descriptor bits 32i … 32i+31 = operand bytes 32i … 32i+31
 #pragma unroll
         for (int h = 0; h < 2; ++h) {             // 16 bits → one 16-byte chunk
             const uint32_t x = w[i] >> (16 * h);
-            const uint4 v = make_uint4(spread4(x), spread4(x >> 4), spread4(x >> 8), spread4(x >> 12));
             const uint32_t c = (uint32_t)(32 * i + 16 * h);            // operand byte of the chunk's first element
-            *reinterpret_cast<uint4 *>(slab0 + (c >> 7) * slabStride + sw128(r, c & 127u)) = v;
+            *reinterpret_cast<uint4 *>(rowp + (c >> 7) * slabStride + (((c & 127u)) ^ rx)) = make_uint4(spread4(x), spread4(x >> 4), spread4(x >> 8), spread4(x >> 12));
         }
     }
 }
 __device__ __forceinline__ int popc256(const uint4 &lo, const uint4 &hi) {
     return __popc(lo.x) + __popc(lo.y) + __popc(lo.z) + __popc(lo.w) + __popc(hi.x) + __popc(hi.y) + __popc(hi.z) + __popc(hi.w);
-}
-__device__ __forceinline__ void top2_insert32(uint32_t k, uint32_t &a, uint32_t &b) {
-    const uint32_t hi = max(k, a);
-    a = min(k, a);
-    b = min(b, hi);
 }
 
 // grid (nChunks, ceil(nq / 128)); partial[chunk * nq + q] = {best key, second key} with rows relative to the chunk start
@@ -158,29 +155,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const uint4 *__restri
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&tfull[s])) : "memory");
             }
         }
-    } else if (warp <= 4) {
-        // ---- producers ----
-        const int pt = tid - 32;                                // 0 … 127
+    } else if (warp <= 8) {
+        // ---- producers ----  (one row per thread and tile; the next tile's row is fetched while the current one is expanded)
+        const int r = tid - 32;                                 // 0 … 255: the tile row = accumulator column of this thread
+        uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+        if (r < rowsHere) { lo = db[2 * (row0 + r)]; hi = db[2 * (row0 + r) + 1]; }
         for (int t = 0; t < nTiles; ++t) {
             const int s = t & 1;
             const uint32_t ph = (uint32_t)(t >> 1) & 1u;
+            const uint4 clo = lo, chi = hi;
+            const long long lr = (long long)t * TC_N + r;       // row inside the chunk
+            const long long nr = lr + TC_N;
+            lo = make_uint4(0, 0, 0, 0); hi = lo;
+            if (nr < rowsHere) { lo = db[2 * (row0 + nr)]; hi = db[2 * (row0 + nr) + 1]; }
             bar_wait(&empty[s], ph ^ 1u);
-            uint8_t *slab = sB + s * TC_B_BYTES;
-            uint32_t *base = sBase + s * TC_N;
-            const long long tileRow = (long long)t * TC_N;
-#pragma unroll
-            for (int i = 0; i < TC_N / TC_PRODUCERS; ++i) {
-                const int r = pt + i * TC_PRODUCERS;
-                const long long lr = tileRow + r;               // row inside the chunk
-                uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
-                uint32_t kb = TC_KEY_NONE;                      // columns past the end of the chunk never win
-                if (lr < rowsHere) {
-                    lo = db[2 * (row0 + lr)]; hi = db[2 * (row0 + lr) + 1];
-                    kb = ((uint32_t)popc256(lo, hi) << TC_IDX_BITS) + (uint32_t)lr;
-                }
-                expand_row(slab, TC_N * 128, (uint32_t)r, lo, hi);
-                base[r] = kb;
-            }
+            expand_row(sB + s * TC_B_BYTES, TC_N * 128, (uint32_t)r, clo, chi);
+            // key base of the column: (256 − |d|) above the inverted row (larger key = smaller distance, then smaller row); 0 = no row
+            sBase[s * TC_N + r] = lr < rowsHere ? ((uint32_t)(256 - popc256(clo, chi)) << TC_ROW_BITS) + (((1u << TC_ROW_BITS) - 1u) - (uint32_t)lr) : 0u;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             bar_arrive(&full[s]);
         }
@@ -189,14 +180,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const uint4 *__restri
         const int et = tid - 32 - TC_PRODUCERS;                 // 0 … 255
         const int ew = et >> 5;                                 // 0 … 7
         const int quarter = warp & 3;                           // the TMEM lane quarter this warp may access is fixed by its id
-        const int half = ew >> 2;                               // 0: columns 0-127, 1: columns 128-255 (warps 5-8 / 9-12 cover each quarter once)
+        const int half = ew >> 2;                               // 0: columns 0-127, 1: columns 128-255 (warps 9-12 / 13-16 cover each quarter once)
         const int m = quarter * 32 + lane;                      // query row = TMEM lane
-        uint32_t qn23 = 0;
+        int qn = 0;
         if (q0 + m < nq) {
             const uint4 lo = q[2 * (long long)(q0 + m)], hi = q[2 * (long long)(q0 + m) + 1];
-            qn23 = (uint32_t)popc256(lo, hi) << TC_IDX_BITS;
+            qn = popc256(lo, hi);
         }
-        uint32_t a = TC_KEY_NONE, b = TC_KEY_NONE;
+        // running top-2 in MAX order over keys  (2·dot − |d| + 256) << 22 | (2^22 − 1 − row)   (real keys are > 0)
+        uint32_t a = 0, b = 0;
         for (int t = 0; t < nTiles; ++t) {
             const int s = t & 1;
             const uint32_t ph = (uint32_t)(t >> 1) & 1u;
@@ -216,36 +208,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const uint4 *__restri
                       "=r"(v[31])
                     : "r"(taddr + (uint32_t)(g * 32)));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                // key = ((|q| + |d| − 2·dot) << 23) + row = base + (|q| << 23) − (dot << 24); a column past the chunk end keeps key NONE
-                uint32_t kmin = TC_KEY_NONE;
+                // key = dot · 2^23 + base: one multiply-add per column (a column past the chunk end has base 0 and dot 0: key 0 never wins)
+                uint32_t kmax = 0;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     const uint4 bs = *reinterpret_cast<const uint4 *>(base + g * 32 + j);
-                    const uint32_t bsv[4] = {bs.x, bs.y, bs.z, bs.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const uint32_t key = bsv[e] == TC_KEY_NONE ? TC_KEY_NONE : bsv[e] + (qn23 - (v[j + e] << 24));
-                        v[j + e] = key;
-                    }
-                    kmin = min(kmin, min(min(v[j], v[j + 1]), min(v[j + 2], v[j + 3])));
+                    v[j] = v[j] * (1u << (TC_ROW_BITS + 1)) + bs.x; v[j + 1] = v[j + 1] * (1u << (TC_ROW_BITS + 1)) + bs.y;
+                    v[j + 2] = v[j + 2] * (1u << (TC_ROW_BITS + 1)) + bs.z; v[j + 3] = v[j + 3] * (1u << (TC_ROW_BITS + 1)) + bs.w;
+                    kmax = max(max(kmax, max(v[j], v[j + 1])), max(v[j + 2], v[j + 3]));
                 }
-                if (kmin < b) {                                 // this group can change the running top-2: exact insertion, in column order
+                if (kmax > b) {                                 // this group can change the running top-2: exact insertion
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) top2_insert32(v[j], a, b);
+                    for (int j = 0; j < 32; ++j) {
+                        const uint32_t lo2 = min(v[j], a);
+                        a = max(v[j], a);
+                        b = max(b, lo2);
+                    }
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             bar_arrive(&tempty[s]);
             bar_arrive(&empty[s]);
         }
-        // merge the two column halves of every query and write the chunk's partial result
+        // merge the two column halves of every query, convert to the (distance << 23 | row) keys of the merge kernel, write the partial result
         if (half == 1) sMerge[m] = make_uint2(a, b);
         asm volatile("bar.sync 1, %0;" ::"r"(TC_EPILOGUE) : "memory");      // named barrier: the 256 epilogue threads only
         if (half == 0 && q0 + m < nq) {
             const uint2 o = sMerge[m];
-            top2_insert32(o.x, a, b);
-            top2_insert32(o.y, a, b);
-            partial[(long long)blockIdx.x * nq + (q0 + m)] = make_uint2(a, b);
+            uint32_t lo2 = min(o.x, a); a = max(o.x, a); b = max(b, lo2);
+            lo2 = min(o.y, a); a = max(o.y, a); b = max(b, lo2);
+            auto conv = [&](uint32_t k) -> uint32_t {
+                if (k == 0) return TC_KEY_NONE;
+                const uint32_t sc = k >> TC_ROW_BITS, row = ((1u << TC_ROW_BITS) - 1u) - (k & ((1u << TC_ROW_BITS) - 1u));
+                return ((uint32_t)(qn + 256 - (int)sc) << TC_IDX_BITS) | row;          // distance = |q| + |d| − 2·dot = |q| + 256 − score
+            };
+            partial[(long long)blockIdx.x * nq + (q0 + m)] = make_uint2(conv(a), conv(b));
         }
     }
     // ---- teardown ----

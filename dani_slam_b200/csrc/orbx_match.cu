@@ -721,7 +721,7 @@ int orbx_hamming_knn2_device(orbx_matcher *m, const uint8_t *d_q, int nq, const 
         long long nCh = std::max(1LL, (long long)m->nSM * 4 / qTilesTc);
         long long chunkRowsTc = (ndb + nCh - 1) / nCh;
         chunkRowsTc = std::max(256LL, (chunkRowsTc + 255) / 256 * 256);
-        chunkRowsTc = std::min<long long>(chunkRowsTc, ((1LL << KNN_IDX_BITS) - 256) / 256 * 256);
+        chunkRowsTc = std::min<long long>(chunkRowsTc, ((1LL << 22) - 256) / 256 * 256);      // the kernel's keys hold 22 row bits
         const int nChunksTc = (int)((ndb + chunkRowsTc - 1) / chunkRowsTc);
         const size_t needTc = (size_t)nChunksTc * nq;
         if (needTc > m->partialCap || !m->d_partial) {
