@@ -584,24 +584,53 @@ def main():
             same = torch.tensor([int(torch.equal(ref_rec[0], idx) and torch.equal(ref_rec[1], dist))], dtype=torch.int32, device=dev)
             td.all_reduce(same, op=td.ReduceOp.MIN)
             parity = bool(same.item())
+        # the shipped kernel for this size is the tensor-core GEMM (tcgen05.mma.kind::i8 over 0/1 bytes: 2·256 integer ops per pair); the POPC
+        # kernel is timed beside it on rank 0's shard as the cross-check and the previous round's figure
+        tc_used = sm.m.tc_launches() > 0
+        popc_gpairs = None
+        if not dist_on:
+            os.environ["ORBX_KNN_POPC"] = "1"
+            smp = sharded.CudaShardedMatcher(local_rank)
+            del os.environ["ORBX_KNN_POPC"]
+            rec_p = smp.local_top2(d_q, d_db, lo)
+            torch.cuda.synchronize(dev)
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record(torch.cuda.current_stream(dev))
+            for _ in range(2):
+                rec_p = smp.local_top2(d_q, d_db, lo)
+            p1.record(torch.cuda.current_stream(dev))
+            p1.synchronize()
+            popc_gpairs = nq * ndb * 2 / (p0.elapsed_time(p1) / 1000.0) / 1e9
+            popc_same = bool(torch.equal(rec_p[0], idx) and torch.equal(rec_p[1], dist))
         pk = {}
         try:
             pk = json.load(open(os.path.join(ROOT, "profiles", "pipe_peaks.json")))
         except Exception:
             pass
         popc_peak = float(pk.get("popc_lanes_per_clk_per_sm", 16.0)) * float(pk.get("sm_count", 148)) * 1e6 * float(clocks.get("sm_max_mhz") or 1965.0)
+        bf16_peak = float(peaks.get("bf16_tflops", 1590.0))
+        tops = 2 * 256 * gpairs * 1e9 / world / 1e12                    # integer multiply-adds counted as 2 ops, per GPU
         match = {"metric": "hamming_knn2_gpairs_per_s", "value": gpairs, "unit": "Gpairs/s", "nq": nq, "ndb": ndb,
                  "scaling": "strong", "ms_per_step": ms_m / Km, "steps": Km,
+                 "kernel": "k_knn2_tc (tcgen05.mma.kind::i8, TMEM accumulators, fused top-2 epilogue)" if tc_used else "k_knn2_partial (POPC)",
                  "collective": "orbx_knn2_sharded (C ABI): one ncclAllGather of the packed per-shard top-2 record (nq*2*2 int32 = 32 KB per rank)" if dist_on else None,
                  "parity": parity,
                  "parity_note": "sharded result of every rank == rank 0's unsharded scan of the whole DB (indices and distances)" if dist_on else
                                 "single GPU: see cpu_baseline.sample and tests/test_match_gpu.py::test_config4_full_size_vs_oracle",
                  "popc_per_s": 8 * gpairs * 1e9, "cpu_baseline": None,
-                 "roofline": {"bound": "int-popc", "issued": 5 * gpairs * 1e9 / world, "achieved": 8 * gpairs * 1e9 / world, "peak": popc_peak,
-                              "unit": "POPC/s per GPU", "frac_issued": 5 * gpairs * 1e9 / world / popc_peak, "frac": 8 * gpairs * 1e9 / world / popc_peak,
-                              "peak_source": "profiles/pipe_peaks.json (register-resident POPC microbenchmark, lanes/clk/SM) x 148 SMs x sm_max_mhz",
-                              "note": "`issued` = the 5 POPC.32 per pair the carry-save kernel executes (the honest pipe utilisation); `achieved` = the "
-                                      "algorithmic 8 POPC.32 per pair of SURVEY.md §8(d), which exceeds the pipe's peak because 3 of 8 are folded into LOP3"}}
+                 "roofline": {"bound": "tensor", "achieved": tops, "peak": 2 * bf16_peak, "unit": "TOP/s (int8) per GPU", "frac": tops / (2 * bf16_peak),
+                              "frac_of_measured_bf16": tops / bf16_peak,
+                              "peak_source": ("2 x MEASURED_PEAKS.json bf16_tflops (burst; int8 runs at twice the bf16 rate on sm_100a)" if "bf16_tflops" in peaks
+                                              else "2 x fallback 1590 TFLOP/s bf16 (B200_PROFILING.md)"),
+                              "note": "algorithmic work: one 256-term 0/1 dot product per pair = 512 integer ops; ncu: the kernel is bound by shared-memory "
+                                      "bandwidth (operand expansion writes + the tensor core's operand reads), tensor pipe about half busy"},
+                 "popc_kernel": None if popc_gpairs is None else {
+                     "value": popc_gpairs, "unit": "Gpairs/s", "same_result": popc_same,
+                     "roofline": {"bound": "int-popc", "issued": 5 * popc_gpairs * 1e9, "achieved": 8 * popc_gpairs * 1e9, "peak": popc_peak,
+                                  "unit": "POPC/s per GPU", "frac_issued": 5 * popc_gpairs * 1e9 / popc_peak, "frac": 8 * popc_gpairs * 1e9 / popc_peak,
+                                  "peak_source": "profiles/pipe_peaks.json (register-resident POPC microbenchmark, lanes/clk/SM) x 148 SMs x sm_max_mhz",
+                                  "note": "`issued` = the 5 POPC.32 per pair the carry-save kernel executes (the honest pipe utilisation); `achieved` = "
+                                          "the algorithmic 8 POPC.32 per pair of SURVEY.md §8(d)"}}}
         if world == 1 and not args.no_cpu:
             # the oracle's popcount kNN on all host cores over a DB slice (the scan is linear in the DB length)
             from oracle import oracle as _orc
