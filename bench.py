@@ -324,6 +324,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--match-db", type=int, default=10_000_000)
     ap.add_argument("--no-bow", action="store_true", help="skip the bag-of-words section")
+    ap.add_argument("--wc-input", action="store_true", help="host input frames in write-combined pinned memory (e2e / copy-ceiling experiment)")
     ap.add_argument("--no-latency", action="store_true", help="skip the single-frame latency section")
     ap.add_argument("--latency-calls", type=int, default=1000)
     ap.add_argument("--bow-levels", type=int, default=6, help="depth of the synthetic k=10 vocabulary (ORBvoc: 6)")
@@ -426,6 +427,13 @@ def main():
 
     # ---------------- end to end through the host-buffer API (`e2e`) ----------------
     h_imgs = h_frames.numpy()
+    if args.wc_input:
+        import ctypes as _C
+        wc_ptr = orbx.lib().orbx_host_alloc_wc(h_imgs.nbytes)
+        if not wc_ptr:
+            raise SystemExit("orbx_host_alloc_wc failed")
+        _C.memmove(wc_ptr, h_imgs.ctypes.data, h_imgs.nbytes)
+        h_imgs = np.ctypeslib.as_array((_C.c_uint8 * h_imgs.nbytes).from_address(wc_ptr)).reshape(h_imgs.shape)
     ptrs_kps = torch.empty((B, cap, 7), dtype=torch.float32).pin_memory()
     ptrs_desc = torch.empty((B, cap, 32), dtype=torch.uint8).pin_memory()
     out_k = ptrs_kps.numpy().view(np.uint8).reshape(B, cap * 28).view(orbx.KP_DTYPE)
@@ -723,7 +731,7 @@ def main():
                        "keypoints_per_frame": n_avg},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "orbx_extract_batch (host pinned buffers, H2D + D2H inside the timed region)",
+                    "api": "orbx_extract_batch (host pinned buffers, H2D + D2H inside the timed region)" + (", write-combined input" if args.wc_input else ""),
                     "copy_ceiling_frames_per_s": copy_ceiling,
                     "copy_ceiling_note": "orbx_copy_only_batch: the same bytes over the same streams and chunks with no kernel launched, all ranks at once; "
                                          f"{(h2d + d2h) * copy_ceiling / B / 1e9:.1f} GB/s over PCIe in total"},

@@ -3749,6 +3749,11 @@ void *orbx_host_alloc(size_t bytes) {
     if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     return p;
 }
+void *orbx_host_alloc_wc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocWriteCombined) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
 void orbx_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 // ---- test hooks ----

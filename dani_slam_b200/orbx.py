@@ -65,6 +65,8 @@ def lib() -> C.CDLL:
     L.orbx_get_selected.argtypes = [vp, i32, i32, vp, i32]
     L.orbx_host_alloc.restype = vp
     L.orbx_host_alloc.argtypes = [sz]
+    L.orbx_host_alloc_wc.restype = vp
+    L.orbx_host_alloc_wc.argtypes = [sz]
     L.orbx_host_free.argtypes = [vp]
     L.orbx_matcher_create.restype = vp
     L.orbx_matcher_create.argtypes = [i32]

@@ -132,6 +132,8 @@ int orbx_stereo_matches(orbx_extractor *ex_left, orbx_extractor *ex_right, const
 
 /* Page-locked host memory helpers (cudaHostAlloc / cudaFreeHost). */
 void *orbx_host_alloc(size_t bytes);
+/* Same, write-combined (cudaHostAllocWriteCombined): for INPUT buffers the CPU only fills and the GPU only reads. */
+void *orbx_host_alloc_wc(size_t bytes);
 void orbx_host_free(void *p);
 
 /* ---------------------------------------------------------------------------------------------
