@@ -8,7 +8,7 @@
 // the IFUNC-selected variant on FMA hosts (`__sinf_fma`/`__cosf_fma`, libm.so.6 .text 0x7e800 /
 // 0x7e330 in this image) contracts specific multiply-adds.  The operation order and the fused
 // operations below were read from that variant's disassembly, the constants from its
-// `__sincosf_table` (.rodata 0xb8120); tests/test_sincosf.py sweeps every float in [0, 2π] against the
+// `__sincosf_table` (.rodata 0xb8120); tests/test_device_math_gpu.py sweeps every float in [0, 2π] against the
 // host libm, on the CPU (host build of this header) and on the GPU (device build).
 //
 // Works identically as host C++ (std::fma) and CUDA device code (__fma_rn & friends): only IEEE

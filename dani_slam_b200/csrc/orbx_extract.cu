@@ -717,7 +717,7 @@ __global__ void __launch_bounds__(WPB * 32, 2048 / (WPB * 32 * 2)) k_fast_cells(
         const uint32_t rcpW = (65536u + nW - 1) / nW;   // (i*rcpW)>>16 == i/nW for i < 3449 (cells are ≤ 20 words × 76 rows)
         uint32_t *roi32 = reinterpret_cast<uint32_t *>(roi);
         const int rpW = rp >> 2;
-#pragma unroll 4
+#pragma unroll 8
         for (int i = lane; i < items; i += 32) {
             const int y = (int)(((uint32_t)i * rcpW) >> 16), k = i - y * nW;
             const uint32_t *q = gsrc + (long long)y * pitchW + k;
@@ -1347,7 +1347,6 @@ __global__ void __launch_bounds__(128) k_qt_classify(ExParams p, QtTables t) {
     if (nCells == 0) return;
     const int *cellCnt = p.cellCnt + (long long)b * g.nCellsTotal + LV.cellBase;
     const int *prefix = t.cellPrefix + (long long)b * g.nCellsTotal + LV.cellBase;
-    const int nPts = prefix[nCells - 1] + cellCnt[nCells - 1];
     const OrbxCell *cells = p.cells + LV.cellBase;
     const uint32_t *slots = p.slots + (long long)b * g.slotsTotal;
     float2 *ptXY = p.ptXY + (long long)b * g.slotsTotal + LV.slotBase;
@@ -1359,14 +1358,13 @@ __global__ void __launch_bounds__(128) k_qt_classify(ExParams p, QtTables t) {
     const float hX = LV.hX;
     const int nRects = g.nRects;
     const int rootH = LV.maxBY - ORBX_BORDER;
-    for (int i = blockIdx.x * 128 + threadIdx.x; i < nPts; i += QT_CLS_BLOCKS * 128) {
-        int lo = 0, hi = nCells;  // last cell with prefix[c] <= i
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (prefix[mid] <= i) lo = mid; else hi = mid;
-        }
-        const OrbxCell cell = cells[lo];
-        const uint32_t e = slots[cell.slot + (i - prefix[lo])];
+    // one warp per cell (its candidates are consecutive in the order index): the cell record and prefix are read once per warp
+    const int lane = threadIdx.x & 31;
+    for (int ci = blockIdx.x * 4 + (threadIdx.x >> 5); ci < nCells; ci += QT_CLS_BLOCKS * 4)
+    for (int j = lane, cnt = cellCnt[ci]; j < cnt; j += 32) {
+        const OrbxCell cell = cells[ci];
+        const int i = prefix[ci] + j;
+        const uint32_t e = slots[cell.slot + j];
         const int trips = nCells - cell.seq;   // filter passes this cell's keypoints live through (:871-907)
         float x = __fadd_rn((float)(e & 0xff), (float)(cell.cx * LV.wCell));  // pt.x += j*wCell (:863)
         float y = __fadd_rn((float)((e >> 8) & 0xff), (float)(cell.cy * LV.hCell));
