@@ -717,7 +717,7 @@ __global__ void __launch_bounds__(WPB * 32, 2048 / (WPB * 32 * 2)) k_fast_cells(
         const uint32_t rcpW = (65536u + nW - 1) / nW;   // (i*rcpW)>>16 == i/nW for i < 3449 (cells are ≤ 20 words × 76 rows)
         uint32_t *roi32 = reinterpret_cast<uint32_t *>(roi);
         const int rpW = rp >> 2;
-#pragma unroll 8
+#pragma unroll 4
         for (int i = lane; i < items; i += 32) {
             const int y = (int)(((uint32_t)i * rcpW) >> 16), k = i - y * nW;
             const uint32_t *q = gsrc + (long long)y * pitchW + k;

@@ -378,3 +378,34 @@ def test_many_seeded_frames_statistical_parity(orbx_mod, oracle_mod):
         with ThreadPoolExecutor(16) as pool:
             ok = list(pool.map(check, range(0, B, step)))
         assert all(ok), (lap, [i * step for i, v in enumerate(ok) if not v][:10])
+
+
+def test_single_frame_path_graph_replay_and_eager_agree(orbx_mod, oracle_mod, monkeypatch):
+    """orbx_extract replays copy-in + kernels + copy-out as one CUDA graph from the third call with the same geometry: eight calls on
+    alternating frames, changing lapping window, dynamic rectangles and image size (graph re-capture) all equal the oracle, and the
+    eager form (ORBX_NO_GRAPH) gives the same bytes."""
+    from dani_slam_b200 import synth
+    frames = [synth.parity_frame(60 + i, 640, 480) for i in range(3)]
+    small = synth.parity_frame(70, 500, 375)
+    ref = oracle_mod.Extractor(1000, 1.2, 8, 20, 7)
+
+    def run(ex):
+        out = []
+        for k in range(8):
+            img = frames[k % 3]
+            lap = (0, 0) if k < 5 else (200, 400)
+            ex.mvDynamicArea = [(100, 80, 150, 120)] if k == 6 else []
+            out.append((ex(img, None, lap), img, list(ex.mvDynamicArea), lap))
+        out.append((ex(small, None, (0, 0)), small, [], (0, 0)))            # smaller image: new geometry, new graph
+        for k in range(4):
+            out.append((ex(small, None, (0, 0)), small, [], (0, 0)))
+        return out
+
+    got = run(orbx_mod.ORBextractor(1000, 1.2, 8, 20, 7, max_width=640, max_height=480))
+    for (mono, k, d), img, rects, lap in got:
+        rc, rk, rd, rmono = ref.extract(img, rects=rects, lap=lap)
+        assert rc == 0 and mono == rmono and k.tobytes() == rk.tobytes() and np.array_equal(d, rd)
+    monkeypatch.setenv("ORBX_NO_GRAPH", "1")
+    eager = run(orbx_mod.ORBextractor(1000, 1.2, 8, 20, 7, max_width=640, max_height=480))
+    for ((m1, k1, d1), *_), ((m2, k2, d2), *_) in zip(got, eager):
+        assert m1 == m2 and k1.tobytes() == k2.tobytes() and np.array_equal(d1, d2)
