@@ -577,6 +577,14 @@ __global__ void __launch_bounds__(WPB * 32) k_fast_cells_v1_list(ExParams p, int
 // as A, so one packed u16x2 op sequence serves any mix of sides.
 struct FastEntryRing { uint32_t x[16]; uint32_t v; };
 
+// inclusive warp prefix sum: the shuffle's own "source lane in range" predicate guards the add (two instructions per step)
+__device__ __forceinline__ int warp_inclusive_sum(int v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+        asm volatile("{ .reg .s32 t; .reg .pred p; shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff; @p add.s32 %0, %0, t; }" : "+r"(v) : "r"(o));
+    return v;
+}
+
 __device__ __forceinline__ uint32_t fast_window_minmax(const uint32_t (&r)[16]) {
     uint32_t tmx[16];
 #pragma unroll
@@ -690,7 +698,6 @@ __global__ void __launch_bounds__(WPB * 32, 2048 / (WPB * 32 * 2)) k_fast_cells(
     uint8_t *roi = base + L.roiOff;
     uint8_t *score = base + L.scoreOff;
     uint16_t *queue = reinterpret_cast<uint16_t *>(base + L.entryOff);
-    uint8_t *gmask = base + L.maskOff;
 
     int pitch;
     const uint8_t *img = level_ptr(p, g, cell.level, b, pitch);
@@ -746,7 +753,6 @@ __global__ void __launch_bounds__(WPB * 32, 2048 / (WPB * 32 * 2)) k_fast_cells(
     const int rp3 = 3 * rp;
     const int stepRows = 32 / G, stepGroups = 32 - stepRows * G;          // 32 groups further on
     const int stepOff = stepRows * rp + 4 * stepGroups, wrapOff = rp - 4 * G;
-    const int K = (((nGroups + 31) >> 5) + 1) & ~1;                        // groups per lane in phase 1b (even: the count pass reads pairs)
     const int nValidLast = iw - 4 * (G - 1);                               // valid pixels of a row's last group (1..4)
     const uint32_t lastMask = nValidLast >= 4 ? 0x80808080u : (0x80808080u & ((1u << (8 * nValidLast)) - 1u));
     uint32_t *out = p.slots + (long long)b * g.slotsTotal + cell.slot;
@@ -759,13 +765,15 @@ __global__ void __launch_bounds__(WPB * 32, 2048 / (WPB * 32 * 2)) k_fast_cells(
         const uint32_t biasT2 = (uint32_t)(256 + t) * 0x10001u;
         const uint32_t kT = (uint32_t)(0x8000 - t - 1) * 0x10001u;
 
-        // phase 1a: compass test of every 4-pixel group; the pass bits (low nibble: side A of pixels 0-3, high nibble: side B) go
-        // to one byte per group, nothing is compacted here.  Lane state (lg, off) of group gi = i0 + lane is advanced
+        // phase 1: compass test of every 4-pixel group; every passing pixel becomes one queue entry, in row-major pixel order
+        // (one warp scan of the per-lane counts per 32 groups).  Lane state (lg, off) of group gi = i0 + lane is advanced
         // incrementally: +32 groups = +stepRows rows and +stepGroups groups, with one conditional row wrap.
+        int nE = 0;
         {
             int lg = lane - (int)(((uint32_t)lane * rcpG) >> 16) * G;
             int off = ((int)(((uint32_t)lane * rcpG) >> 16) + 3) * rp + 4 * lg + 4;    // ROI byte of the group's first pixel
             for (int i0 = 0; i0 < nGroups; i0 += 32) {
+                uint32_t pm = 0, sb = 0;     // bit 8i+7: pixel i passes / is a side-B entry (does not pass on side A)
                 if (i0 + lane < nGroups) {
                     const uint8_t *cp = roi + off;
                     Row3 Cn = ld_row3(cp - 4), Tp, Bt;
@@ -784,54 +792,25 @@ __global__ void __launch_bounds__(WPB * 32, 2048 / (WPB * 32 * 2)) k_fast_cells(
                         XB[P] = (loMax + kT) - v2;
                     }
                     const uint32_t colMask = lg == G - 1 ? lastMask : 0x80808080u;
-                    const uint32_t pA = __byte_perm(XA[0], XA[1], 0x7531u) & colMask;   // high bytes of the four halves: px0..px3
-                    const uint32_t pB = __byte_perm(XB[0], XB[1], 0x7531u) & colMask;
-                    // bits 7, 15, 23, 31 → one nibble: (x >> 7) · (1 + 2^7 + 2^14 + 2^21) lines them up at bits 21-24 without carries
-                    const uint32_t nA = (((pA >> 7) * 0x00204081u) >> 21) & 0xfu, nB4 = (((pB >> 7) * 0x00204081u) >> 17) & 0xf0u;
-                    gmask[i0 + lane] = (uint8_t)(nA | nB4);
+                    const uint32_t pA = __byte_perm(XA[0], XA[1], 0x7531u);       // high bytes of the four halves: px0..px3
+                    const uint32_t pB = __byte_perm(XB[0], XB[1], 0x7531u);
+                    pm = (pA | pB) & colMask;
+                    sb = pm & ~pA;
+                }
+                if (__any_sync(0xffffffffu, pm != 0)) {
+                    const int cnt = __popc(pm);
+                    const int incl = warp_inclusive_sum(cnt);
+                    const int nNew = __shfl_sync(0xffffffffu, incl, 31);
+                    if (nE + nNew > L.qCap) { dense = true; break; }      // warp-uniform: more corners than the queue holds
+                    uint16_t *qa = queue + (nE + incl - cnt);
+                    if (pm & 0x80u) *qa++ = (uint16_t)((uint32_t)off | ((sb << 8) & 0x8000u));
+                    if (pm & 0x8000u) *qa++ = (uint16_t)((uint32_t)(off + 1) | (sb & 0x8000u));
+                    if (pm & 0x800000u) *qa++ = (uint16_t)((uint32_t)(off + 2) | ((sb >> 8) & 0x8000u));
+                    if (pm & 0x80000000u) *qa = (uint16_t)((uint32_t)(off + 3) | ((sb >> 16) & 0x8000u));
+                    nE += nNew;
                 }
                 lg += stepGroups; off += stepOff;
                 if (lg >= G) { lg -= G; off += wrapOff; }
-            }
-            for (int i = nGroups + lane; i < 32 * K; i += 32) gmask[i] = 0;       // padding groups of the last lanes
-        }
-        __syncwarp();
-        // phase 1b: every passing pixel becomes one queue entry, in row-major pixel order.  Each lane owns K consecutive groups,
-        // so one warp scan of the per-lane counts places everything.
-        int nE = 0;
-        {
-            const int g0 = min(lane * K, nGroups), g1 = min(g0 + K, nGroups);
-            int cnt = 0;
-            {
-                const uint16_t *gw = reinterpret_cast<const uint16_t *>(gmask) + lane * (K >> 1);   // K is even
-                for (int w = 0; w < (K >> 1); ++w) {
-                    const uint32_t mk2 = gw[w];                                    // two groups at a time
-                    cnt += __popc((mk2 | (mk2 >> 4)) & 0x0f0fu);
-                }
-            }
-            int incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            nE = __shfl_sync(0xffffffffu, incl, 31);
-            if (nE > L.qCap) { dense = true; break; }             // warp-uniform: more corners than the queue holds
-            uint16_t *qa = queue + (incl - cnt);
-            const int yi0 = (int)(((uint32_t)g0 * rcpG) >> 16);
-            int lg = g0 - yi0 * G;
-            uint32_t off = (uint32_t)((yi0 + 3) * rp + 4 * lg + 4);
-            for (int gq = g0; gq < g1; ++gq) {
-                const uint32_t mk = gmask[gq];
-                if (mk) {
-                    const uint32_t any = mk | (mk >> 4);
-                    const uint32_t sideB = ~mk << 15;             // bit 15+i set: pixel i does not pass on side A (so it is a side-B entry)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if ((any >> i) & 1u) *qa++ = (uint16_t)((off + i) | ((sideB >> i) & 0x8000u));
-                }
-                ++lg; off += 4;
-                if (lg == G) { lg = 0; off += (uint32_t)wrapOff; }
             }
         }
         if (dense) break;
