@@ -577,6 +577,17 @@ __global__ void __launch_bounds__(WPB * 32) k_fast_cells_v1_list(ExParams p, int
 // as A, so one packed u16x2 op sequence serves any mix of sides.
 struct FastEntryRing { uint32_t x[16]; uint32_t v; };
 
+// ceil(65536 / n) for n < 128: (i * rcp) >> 16 == i / n for i < 3449 — the per-cell divisions of the FAST kernel as one constant load
+struct Rcp16Table { uint32_t v[128]; };
+static constexpr Rcp16Table make_rcp16_table() {
+    Rcp16Table t{};
+    t.v[0] = 0;
+    for (int n = 1; n < 128; ++n) t.v[n] = (65536u + n - 1) / n;
+    return t;
+}
+__constant__ Rcp16Table kRcp16 = make_rcp16_table();
+__device__ __forceinline__ uint32_t rcp16(int n) { return n < 128 ? kRcp16.v[n] : (65536u + n - 1) / n; }
+
 // inclusive warp prefix sum: the shuffle's own "source lane in range" predicate guards the add (two instructions per step)
 __device__ __forceinline__ int warp_inclusive_sum(int v) {
 #pragma unroll
@@ -709,8 +720,10 @@ __global__ void __launch_bounds__(WPB * 32, 2048 / (WPB * 32 * 2)) k_fast_cells(
         return;
     }
     const int rp = RP ? RP : L.roiPitch;   // == score pitch
-    // stage the ROI: column x at byte x+1 so that every 4-pixel group is word aligned
+    // stage the ROI: column x at byte x+1 so that every 4-pixel group is word aligned; the same loop zeroes the score map
+    // (pixels that never pass the compass test and the 1-px frame — "outside the cell interior counts 0" — must read 0 in the NMS)
     {
+    uint32_t *s32 = reinterpret_cast<uint32_t *>(score);
     const uint8_t *src = img + (long long)cell.y0 * pitch + cell.x0;
     if (((((unsigned long long)img) | (unsigned)pitch) & 3ull) == 0) {
         // aligned 32-bit loads: shared-memory word k of a row holds image columns x0-1+4k .. x0+2+4k, i.e. the two
@@ -721,7 +734,7 @@ __global__ void __launch_bounds__(WPB * 32, 2048 / (WPB * 32 * 2)) k_fast_cells(
         const int pitchW = pitch >> 2;
         const int nW = (cw + 4) >> 2;
         const int items = nW * ch;
-        const uint32_t rcpW = (65536u + nW - 1) / nW;   // (i*rcpW)>>16 == i/nW for i < 3449 (cells are ≤ 20 words × 76 rows)
+        const uint32_t rcpW = rcp16(nW);              // (i*rcpW)>>16 == i/nW for i < 3449 (cells are ≤ 20 words × 76 rows)
         uint32_t *roi32 = reinterpret_cast<uint32_t *>(roi);
         const int rpW = rp >> 2;
 #pragma unroll 4
@@ -730,28 +743,24 @@ __global__ void __launch_bounds__(WPB * 32, 2048 / (WPB * 32 * 2)) k_fast_cells(
             const uint32_t *q = gsrc + (long long)y * pitchW + k;
             const uint32_t a = q[0], bq = q[1];
             roi32[y * rpW + k] = __funnelshift_r(a, bq, 8 * mis);
+            if (y < ih + 2) s32[y * rpW + k] = 0;      // the words of the score map the NMS can read (bytes 3 .. iw+4 of a row)
         }
     } else {
         for (int y = 0; y < ch; ++y)
             for (int x = lane; x < cw; x += 32) roi[y * rp + x + 1] = src[(long long)y * pitch + x];
-    }
-    }
-    // zero the score map: pixels that never pass the compass test and the 1-px frame ("outside the cell interior
-    // counts 0") must read 0 in the NMS
-    {
-        uint32_t *s32 = reinterpret_cast<uint32_t *>(score);
         const int nw = (rp * (ih + 2)) >> 2;
         for (int i = lane; i < nw; i += 32) s32[i] = 0;
+    }
     }
     __syncwarp();
 
     const int G = (iw + 3) >> 2;             // 4-pixel groups per interior row (≤ 19 for cells ≤ 75 px wide)
     const int nGroups = G * ih;              // groups of the cell in row-major order: lane work items
-    const uint32_t rcpG = (65536u + G - 1) / G;   // (i*rcpG)>>16 == i/G for i < 3449 (cells are ≤ 19×69 groups)
+    const uint32_t rcpG = rcp16(G);             // (i*rcpG)>>16 == i/G for i < 3449 (cells are ≤ 19×69 groups)
     const uint32_t rcpRp = (uint32_t)((0x100000000ull + (unsigned)rp - 1) / (unsigned)rp);   // umulhi(o, rcpRp) == o/rp
     const uint32_t lt = (1u << lane) - 1u;
     const int rp3 = 3 * rp;
-    const int stepRows = 32 / G, stepGroups = 32 - stepRows * G;          // 32 groups further on
+    const int stepRows = (int)((32u * rcpG) >> 16), stepGroups = 32 - stepRows * G;          // 32 groups further on
     const int stepOff = stepRows * rp + 4 * stepGroups, wrapOff = rp - 4 * G;
     const int nValidLast = iw - 4 * (G - 1);                               // valid pixels of a row's last group (1..4)
     const uint32_t lastMask = nValidLast >= 4 ? 0x80808080u : (0x80808080u & ((1u << (8 * nValidLast)) - 1u));
