@@ -740,7 +740,7 @@ __global__ void __launch_bounds__(WPB * 32, 2048 / (WPB * 32 * 2)) k_fast_cells(
 #pragma unroll 4
         for (int i = lane; i < items; i += 32) {
             const int y = (int)(((uint32_t)i * rcpW) >> 16), k = i - y * nW;
-            const uint32_t *q = gsrc + (long long)y * pitchW + k;
+            const uint32_t *q = gsrc + (uint32_t)(y * pitchW + k);      // 32-bit word index: one wide multiply-add per address
             const uint32_t a = q[0], bq = q[1];
             roi32[y * rpW + k] = __funnelshift_r(a, bq, 8 * mis);
             if (y < ih + 2) s32[y * rpW + k] = 0;      // the words of the score map the NMS can read (bytes 3 .. iw+4 of a row)
