@@ -1898,31 +1898,34 @@ __global__ void __launch_bounds__(64 * BLUR_STRIPS) k_blur(ExParams p, const Blu
     const int y0 = ty0 + threadIdx.y * BLUR_RH;
     if (x >= w || y0 >= h) return;
     const uint32_t KLO = 18u | (34u << 8) | (48u << 16) | (56u << 24), KHI = 48u | (34u << 8) | (18u << 16);
-    uint8_t *dst = p.blur + (long long)b * g.frameBytes + LV.off + x;
+    const int dpitch = LV.pitch;
+    uint8_t *dst = p.blur + (long long)b * g.frameBytes + LV.off + (long long)y0 * dpitch + x;     // walks down one row per output row
     // the 12-byte window x-4 .. x+7 of a staged row = three aligned words (tile column 0 = image column tx0-16)
     const uint32_t *trow = reinterpret_cast<const uint32_t *>(tile) + threadIdx.y * BLUR_RH * (BLUR_SP / 4) + ((x - 4 - (tx0 - 16)) >> 2);
+    // every horizontal sum carries +128: the vertical taps add up to 256, so the vertical sum arrives with its rounding term
+    // 32768 already in place (sums stay below 2^16 horizontally and 2^24 vertically)
+    const uint32_t kRound = 128u;
+    const int nOut = min(BLUR_RH, h - y0);
     uint32_t ring[7][4];
 #pragma unroll
     for (int r = 0; r < BLUR_RH + 6; ++r) {
         const uint32_t w0 = trow[r * (BLUR_SP / 4)], w1 = trow[r * (BLUR_SP / 4) + 1], w2 = trow[r * (BLUR_SP / 4) + 2];
         // pixel i sits at byte 4+i of {w0,w1,w2}; taps are bytes 1+i .. 7+i
         uint32_t *hr = ring[r % 7];
-        hr[0] = __dp4a(__byte_perm(w0, w1, 0x4321u), KLO, __dp4a(__byte_perm(w1, w2, 0x4321u), KHI, 0u));
-        hr[1] = __dp4a(__byte_perm(w0, w1, 0x5432u), KLO, __dp4a(__byte_perm(w1, w2, 0x5432u), KHI, 0u));
-        hr[2] = __dp4a(__byte_perm(w0, w1, 0x6543u), KLO, __dp4a(__byte_perm(w1, w2, 0x6543u), KHI, 0u));
-        hr[3] = __dp4a(w1, KLO, __dp4a(w2, KHI, 0u));
+        hr[0] = __dp4a(__byte_perm(w0, w1, 0x4321u), KLO, __dp4a(__byte_perm(w1, w2, 0x4321u), KHI, kRound));
+        hr[1] = __dp4a(__byte_perm(w0, w1, 0x5432u), KLO, __dp4a(__byte_perm(w1, w2, 0x5432u), KHI, kRound));
+        hr[2] = __dp4a(__byte_perm(w0, w1, 0x6543u), KLO, __dp4a(__byte_perm(w1, w2, 0x6543u), KHI, kRound));
+        hr[3] = __dp4a(w1, KLO, __dp4a(w2, KHI, kRound));
         if (r >= 6) {
-            const int gy = y0 + r - 6;
-            if (gy < h) {
-                uint32_t v[4];
+            uint32_t v[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    v[i] = 18u * (ring[(r - 6) % 7][i] + ring[r % 7][i]) + 34u * (ring[(r - 5) % 7][i] + ring[(r - 1) % 7][i]) +
-                           48u * (ring[(r - 4) % 7][i] + ring[(r - 2) % 7][i]) + 56u * ring[(r - 3) % 7][i] + 32768u;
-                // (v + 32768) >> 16 is byte 2 of each sum (sums stay below 2^24): three PRMT gather the four output bytes
-                const uint32_t out = __byte_perm(__byte_perm(v[0], v[1], 0x0062u), __byte_perm(v[2], v[3], 0x0062u), 0x5410u);
-                *reinterpret_cast<uint32_t *>(dst + (long long)gy * LV.pitch) = out;
-            }
+            for (int i = 0; i < 4; ++i)
+                v[i] = 18u * (ring[(r - 6) % 7][i] + ring[r % 7][i]) + 34u * (ring[(r - 5) % 7][i] + ring[(r - 1) % 7][i]) +
+                       48u * (ring[(r - 4) % 7][i] + ring[(r - 2) % 7][i]) + 56u * ring[(r - 3) % 7][i];
+            // (sum + 32768) >> 16 is byte 2 of each sum: three PRMT gather the four output bytes
+            const uint32_t out = __byte_perm(__byte_perm(v[0], v[1], 0x0062u), __byte_perm(v[2], v[3], 0x0062u), 0x5410u);
+            if (r - 6 < nOut) *reinterpret_cast<uint32_t *>(dst) = out;
+            dst += dpitch;
         }
     }
 }
