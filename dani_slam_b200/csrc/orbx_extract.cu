@@ -1799,8 +1799,9 @@ __global__ void __launch_bounds__(256) k_assemble(ExParams p) {
 // K5: 7×7 Gaussian blur, σ=2, integer separable kernel, REFLECT_101 on the level.
 // The block stages its input tile (+3-row / +16-byte halo) with 16-byte loads into shared memory; a thread
 // then owns 4 adjacent pixels (one 32-bit store) and marches down BLUR_RH rows: per input row it reads
-// three aligned shared-memory words, forms the horizontal sums with two DP4A per pixel (taps 18,34,48,56 |
-// 48,34,18,0) and keeps the last 7 rows of sums in registers (fully unrolled ring) for the vertical pass.
+// three aligned shared-memory words, forms the four horizontal sums with ten DP4A (the tap words slide over the
+// aligned words, nothing is realigned) and keeps the last 7 rows of sums in registers (fully unrolled ring) for
+// the vertical pass.
 // ------------------------------------------------------------------------------------------------
 #define BLUR_TW 256          // pixels per block row-strip (64 threads × 4 px)
 #define BLUR_RH 16           // output rows per thread
@@ -1808,6 +1809,11 @@ __global__ void __launch_bounds__(256) k_assemble(ExParams p) {
 #define BLUR_TH (BLUR_RH * BLUR_STRIPS)
 #define BLUR_SP (BLUR_TW + 32)   // tile pitch: columns x0-16 .. x0+271
 struct BlurTile { short level, tx, ty, pad; };
+__constant__ uint32_t kBlurTaps[10] = {
+    (18u << 8) | (34u << 16) | (48u << 24), 56u | (48u << 8) | (34u << 16) | (18u << 24),                    // pixel 0: words 0, 1
+    (18u << 16) | (34u << 24), 48u | (56u << 8) | (48u << 16) | (34u << 24), 18u,                            // pixel 1: words 0, 1, 2
+    18u << 24, 34u | (48u << 8) | (56u << 16) | (48u << 24), 34u | (18u << 8),                               // pixel 2: words 0, 1, 2
+    18u | (34u << 8) | (48u << 16) | (56u << 24), 48u | (34u << 8) | (18u << 16)};                           // pixel 3: words 1, 2
 
 __device__ __forceinline__ int reflect101(int i, int n) {
     if (n == 1) return 0;
@@ -1897,9 +1903,13 @@ __global__ void __launch_bounds__(64 * BLUR_STRIPS) k_blur(ExParams p, const Blu
     const int x = tx0 + threadIdx.x * 4;
     const int y0 = ty0 + threadIdx.y * BLUR_RH;
     if (x >= w || y0 >= h) return;
-    const uint32_t KLO = 18u | (34u << 8) | (48u << 16) | (56u << 24), KHI = 48u | (34u << 8) | (18u << 16);
+    // tap words (constant bank operands of the DP4As): pixel i = byte 4+i of the 12-byte window, its taps (18,34,48,56,48,34,18)
+    // cover bytes 1+i .. 7+i, i.e. they slide over the three aligned words instead of the bytes being realigned
+    const uint32_t K0A = kBlurTaps[0], K0B = kBlurTaps[1], K1A = kBlurTaps[2], K1B = kBlurTaps[3], K1C = kBlurTaps[4];
+    const uint32_t K2A = kBlurTaps[5], K2B = kBlurTaps[6], K2C = kBlurTaps[7], KLO = kBlurTaps[8], KHI = kBlurTaps[9];
     const int dpitch = LV.pitch;
-    uint8_t *dst = p.blur + (long long)b * g.frameBytes + LV.off + (long long)y0 * dpitch + x;     // walks down one row per output row
+    unsigned long long dst = (unsigned long long)__cvta_generic_to_global(p.blur + (long long)b * g.frameBytes + LV.off + (long long)y0 * dpitch + x);
+    asm volatile("" : "+l"(dst));              // one 64-bit register pair from here on
     // the 12-byte window x-4 .. x+7 of a staged row = three aligned words (tile column 0 = image column tx0-16)
     const uint32_t *trow = reinterpret_cast<const uint32_t *>(tile) + threadIdx.y * BLUR_RH * (BLUR_SP / 4) + ((x - 4 - (tx0 - 16)) >> 2);
     // every horizontal sum carries +128: the vertical taps add up to 256, so the vertical sum arrives with its rounding term
@@ -1912,9 +1922,10 @@ __global__ void __launch_bounds__(64 * BLUR_STRIPS) k_blur(ExParams p, const Blu
         const uint32_t w0 = trow[r * (BLUR_SP / 4)], w1 = trow[r * (BLUR_SP / 4) + 1], w2 = trow[r * (BLUR_SP / 4) + 2];
         // pixel i sits at byte 4+i of {w0,w1,w2}; taps are bytes 1+i .. 7+i
         uint32_t *hr = ring[r % 7];
-        hr[0] = __dp4a(__byte_perm(w0, w1, 0x4321u), KLO, __dp4a(__byte_perm(w1, w2, 0x4321u), KHI, kRound));
-        hr[1] = __dp4a(__byte_perm(w0, w1, 0x5432u), KLO, __dp4a(__byte_perm(w1, w2, 0x5432u), KHI, kRound));
-        hr[2] = __dp4a(__byte_perm(w0, w1, 0x6543u), KLO, __dp4a(__byte_perm(w1, w2, 0x6543u), KHI, kRound));
+        // the taps slide over the three aligned words instead of the bytes being realigned: 10 DP4A, no PRMT
+        hr[0] = __dp4a(w0, K0A, __dp4a(w1, K0B, kRound));
+        hr[1] = __dp4a(w0, K1A, __dp4a(w1, K1B, __dp4a(w2, K1C, kRound)));
+        hr[2] = __dp4a(w0, K2A, __dp4a(w1, K2B, __dp4a(w2, K2C, kRound)));
         hr[3] = __dp4a(w1, KLO, __dp4a(w2, KHI, kRound));
         if (r >= 6) {
             uint32_t v[4];
@@ -1924,8 +1935,10 @@ __global__ void __launch_bounds__(64 * BLUR_STRIPS) k_blur(ExParams p, const Blu
                        48u * (ring[(r - 4) % 7][i] + ring[(r - 2) % 7][i]) + 56u * ring[(r - 3) % 7][i];
             // (sum + 32768) >> 16 is byte 2 of each sum: three PRMT gather the four output bytes
             const uint32_t out = __byte_perm(__byte_perm(v[0], v[1], 0x0062u), __byte_perm(v[2], v[3], 0x0062u), 0x5410u);
-            if (r - 6 < nOut) *reinterpret_cast<uint32_t *>(dst) = out;
-            dst += dpitch;
+            if (r - 6 < nOut) {
+                const unsigned long long q = dst + (unsigned long long)(uint32_t)dpitch * (uint32_t)(r - 6);   // one wide multiply-add
+                asm volatile("st.global.u32 [%0], %1;" ::"l"(q), "r"(out) : "memory");
+            }
         }
     }
 }
