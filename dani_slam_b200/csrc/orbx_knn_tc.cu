@@ -1,8 +1,12 @@
 // orbx_knn_tc.cu — brute-force Hamming kNN (k = 2) on the 5th-generation tensor cores (tcgen05 / TMEM), sm_100a.
 //
 // For bit vectors q, d ∈ {0,1}^256:  hamming(q, d) = |q| + |d| − 2·(q · d).  The dot products of a tile of 128 queries with a
-// tile of 256 database rows are ONE 128×256×256 integer GEMM: the bits are expanded to 0/1 bytes in shared memory (K-major,
-// 128-byte swizzle — the canonical UMMA operand layout), `tcgen05.mma.kind::i8` accumulates exactly in int32 in tensor memory,
+// tile of 256 database rows are ONE 128×256×256 integer GEMM: every bit becomes one unsigned operand byte in shared memory
+// (K-major, 128-byte swizzle — the canonical UMMA operand layout).  The order of the 256 terms of a dot product is free, so
+// operand word j (j = 0…7) of a 32-bit descriptor word x holds the bits j, j+8, j+16, j+24 IN PLACE: a database byte is
+// x & (1 << j) ∈ {0, 2^j} — one AND per four operand bytes, no shifts — and the query byte of the same term is scaled the other
+// way, bit << (7 − j), so that every product is 128·(q bit)·(d bit) and the accumulator is exactly 128·(q · d).
+// `tcgen05.mma.kind::i8` (unsigned × unsigned) accumulates in int32 in tensor memory,
 // and the epilogue reads the accumulators back with `tcgen05.ld`, forms packed (distance << 23 | row) keys and keeps the two
 // smallest per query — the same keys, tie rule (lower row first) and per-chunk partial format as the POPC kernel in
 // orbx_match.cu, whose merge kernel finishes the job.  Results are bit-identical to the POPC path (tests/test_match_gpu.py).
@@ -10,7 +14,7 @@
 // One CTA = one tile of 128 queries × one chunk of database rows; warp roles (17 warps):
 //   warp 0        allocates tensor memory; lane 0 issues the MMAs (8 per database tile: K = 8 × 32 bytes) and commits them
 //   warps 1-8     producers: one database row per thread and tile (32 B, coalesced, prefetched one tile ahead), expanded to the
-//                 swizzled 0/1 byte tile of the free stage; the row's popcount goes into the per-column key base
+//                 swizzled operand tile of the free stage (64 ANDs + 16 16-byte stores); the row's popcount goes into the per-column key base
 //   warps 9-16    epilogue: two threads per query (column halves), 4 × `tcgen05.ld.32x32b.x32` each; per column ONE multiply-add
 //                 forms a max-ordered key (2·dot − |d| in the high bits, inverted row below), a max3 tree pre-reduces 32 columns,
 //                 and the exact top-2 insertion runs only for the groups that can improve the running second best
@@ -57,22 +61,28 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smemAddr) {
     return (uint64_t)((smemAddr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
-// four descriptor bits → four 0/1 bytes: (x · (1 + 2^7 + 2^14 + 2^21)) & 0x01010101 puts bit i into byte i.  (A byte → 8-byte table in
-// shared memory was slower: the kernel is bound by shared-memory bandwidth — operand writes plus the tensor core's operand reads.)
-__device__ __forceinline__ uint32_t spread4(uint32_t nib) { return ((nib & 0xfu) * 0x00204081u) & 0x01010101u; }
-// one 32-byte descriptor row → 256 operand bytes in the two K-block slabs of a tile (slab k holds operand bytes 128k … 128k+127)
-__device__ __forceinline__ void expand_row(uint8_t *slab0, uint32_t slabStride, uint32_t r, const uint4 &lo, const uint4 &hi) {
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// One 32-byte descriptor row → 256 operand bytes in the two K-block slabs of a tile (slab k holds operand bytes 128k … 128k+127).
+// Operand word 8i + j = the bits j, j+8, j+16, j+24 of descriptor word i, left where they are (DB: byte ∈ {0, 2^j}) or moved to
+// bit 7 − j (QUERY: byte ∈ {0, 2^(7−j)}).  rowAddr: shared-window address of the row in slab 0; the 16-byte chunks of a row are
+// XOR-swizzled with the row index modulo 8.
+template <bool QUERY>
+__device__ __forceinline__ void expand_row(uint32_t rowAddr, uint32_t slabStride, uint32_t r, const uint4 &lo, const uint4 &hi) {
     const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-    uint8_t *rowp = slab0 + r * 128u;
-    const uint32_t rx = (r & 7u) << 4;            // 16-byte chunks are XOR-swizzled with the row index modulo 8
+    const uint32_t rx = (r & 7u) << 4;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {                 // word i = descriptor bits 32i … 32i+31 = operand bytes 32i … 32i+31
+    for (int c = 0; c < 16; ++c) {                // chunk c = operand words 4c … 4c+3 = descriptor word c >> 1, j = 4·(c & 1) … +3
+        const uint32_t x = w[c >> 1];
+        const int j0 = 4 * (c & 1);
+        uint32_t o[4];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {             // 16 bits → one 16-byte chunk
-            const uint32_t x = w[i] >> (16 * h);
-            const uint32_t c = (uint32_t)(32 * i + 16 * h);            // operand byte of the chunk's first element
-            *reinterpret_cast<uint4 *>(rowp + (c >> 7) * slabStride + (((c & 127u)) ^ rx)) = make_uint4(spread4(x), spread4(x >> 4), spread4(x >> 8), spread4(x >> 12));
+        for (int k = 0; k < 4; ++k) {
+            const int j = j0 + k;
+            o[k] = QUERY ? ((x >> j) & 0x01010101u) << (7 - j) : x & (0x01010101u << j);
         }
+        sts128(rowAddr + (uint32_t)(c >> 3) * slabStride + (((uint32_t)(c & 7) << 4) ^ rx), o[0], o[1], o[2], o[3]);
     }
 }
 __device__ __forceinline__ int popc256(const uint4 &lo, const uint4 &hi) {
@@ -116,7 +126,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const uint4 *__restri
     for (int r = tid; r < TC_M; r += TC_THREADS) {              // queries beyond nq are zero rows (their results are not written)
         uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
         if (q0 + r < nq) { lo = q[2 * (long long)(q0 + r)]; hi = q[2 * (long long)(q0 + r) + 1]; }
-        expand_row(sA, TC_M * 128, (uint32_t)r, lo, hi);
+        expand_row<true>(s32(sA) + (uint32_t)r * 128u, TC_M * 128, (uint32_t)r, lo, hi);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes → visible to the tensor core's async proxy
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -169,7 +179,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const uint4 *__restri
             lo = make_uint4(0, 0, 0, 0); hi = lo;
             if (nr < rowsHere) { lo = db[2 * (row0 + nr)]; hi = db[2 * (row0 + nr) + 1]; }
             bar_wait(&empty[s], ph ^ 1u);
-            expand_row(sB + s * TC_B_BYTES, TC_N * 128, (uint32_t)r, clo, chi);
+            expand_row<false>(s32(sB) + (uint32_t)(s * TC_B_BYTES) + (uint32_t)r * 128u, TC_N * 128, (uint32_t)r, clo, chi);
             // key base of the column: (256 − |d|) above the inverted row (larger key = smaller distance, then smaller row); 0 = no row
             sBase[s * TC_N + r] = lr < rowsHere ? ((uint32_t)(256 - popc256(clo, chi)) << TC_ROW_BITS) + (((1u << TC_ROW_BITS) - 1u) - (uint32_t)lr) : 0u;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -194,7 +204,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const uint4 *__restri
             const uint32_t ph = (uint32_t)(t >> 1) & 1u;
             bar_wait(&tfull[s], ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t *base = sBase + s * TC_N + half * 128;
+            const uint32_t base = s32(sBase) + (uint32_t)(s * TC_N + half * 128) * 4u;      // shared-window address of the key bases
             const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * TC_N + half * 128);
 #pragma unroll 1
             for (int g = 0; g < 4; ++g) {                       // 32 columns per load
@@ -208,13 +218,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const uint4 *__restri
                       "=r"(v[31])
                     : "r"(taddr + (uint32_t)(g * 32)));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                // key = dot · 2^23 + base: one multiply-add per column (a column past the chunk end has base 0 and dot 0: key 0 never wins)
+                // accumulator = 128 · dot; key = dot · 2^23 + base: one multiply-add per column (a column past the chunk end has base 0
+                // and dot 0: key 0 never wins)
+                constexpr uint32_t kScale = 1u << (TC_ROW_BITS + 1 - 7);
                 uint32_t kmax = 0;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    const uint4 bs = *reinterpret_cast<const uint4 *>(base + g * 32 + j);
-                    v[j] = v[j] * (1u << (TC_ROW_BITS + 1)) + bs.x; v[j + 1] = v[j + 1] * (1u << (TC_ROW_BITS + 1)) + bs.y;
-                    v[j + 2] = v[j + 2] * (1u << (TC_ROW_BITS + 1)) + bs.z; v[j + 3] = v[j + 3] * (1u << (TC_ROW_BITS + 1)) + bs.w;
+                    uint4 bs;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(bs.x), "=r"(bs.y), "=r"(bs.z), "=r"(bs.w) : "r"(base + (uint32_t)(g * 32 + j) * 4u));
+                    v[j] = v[j] * kScale + bs.x; v[j + 1] = v[j + 1] * kScale + bs.y;
+                    v[j + 2] = v[j + 2] * kScale + bs.z; v[j + 3] = v[j + 3] * kScale + bs.w;
                     kmax = max(max(kmax, max(v[j], v[j + 1])), max(v[j + 2], v[j + 3]));
                 }
                 if (kmax > b) {                                 // this group can change the running top-2: exact insertion
@@ -260,12 +273,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const uint4 *__restri
 // launches the tensor-core kernel for chunks of `chunkRows` rows; partial as for the POPC kernel.  Returns cudaSuccess or the launch error.
 cudaError_t orbx_knn2_tc_launch(const uint8_t *d_q, int nq, const uint8_t *d_db, long long ndb, long long chunkRows, int nChunks, uint2 *d_partial,
                                 cudaStream_t stream) {
-    static bool attrSet = false;
-    if (!attrSet) {
-        cudaError_t e = cudaFuncSetAttribute(k_knn2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
-        if (e != cudaSuccess) return e;
-        attrSet = true;
-    }
+    // the opt-in to > 48 KB of dynamic shared memory is per device (a process may drive several)
+    cudaError_t e = cudaFuncSetAttribute(k_knn2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    if (e != cudaSuccess) return e;
     dim3 grid((unsigned)nChunks, (unsigned)((nq + TC_M - 1) / TC_M));
     k_knn2_tc<<<grid, TC_THREADS, TC_SMEM, stream>>>(reinterpret_cast<const uint4 *>(d_q), nq, reinterpret_cast<const uint4 *>(d_db), ndb, chunkRows, d_partial);
     return cudaGetLastError();
