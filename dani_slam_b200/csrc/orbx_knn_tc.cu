@@ -34,7 +34,8 @@ constexpr int TC_EPILOGUE = 256;      // threads (warps 9-16)
 constexpr int TC_THREADS = 32 + TC_PRODUCERS + TC_EPILOGUE;
 constexpr int TC_A_BYTES = TC_M * TC_KBYTES;            // 32 KB: two K-blocks of [128 rows][128 B]
 constexpr int TC_B_BYTES = TC_N * TC_KBYTES;            // 64 KB per stage: two K-blocks of [256 rows][128 B]
-constexpr int TC_SMEM = TC_A_BYTES + 2 * TC_B_BYTES + 2 * TC_N * 4 + 2048 /* barriers, tmem address, merge buffer */ + 1024 /* alignment slack */;
+constexpr int TC_BASE_STAGES = 4;     // key-base ring: written by the producers of tile t, read by its epilogue, reused by tile t + 4
+constexpr int TC_SMEM = TC_A_BYTES + 2 * TC_B_BYTES + TC_BASE_STAGES * TC_N * 4 + 2048 /* barriers, tmem address, merge buffer */ + 1024 /* alignment slack */;
 constexpr uint32_t TC_ROW_BITS = 22;     // rows of a chunk inside the max-ordered keys of the epilogue (chunks hold < 2^22 - 1 rows)
 constexpr uint32_t TC_IDX_BITS = 23;
 constexpr uint32_t TC_KEY_NONE = 0xffffffffu;
@@ -85,6 +86,16 @@ __device__ __forceinline__ void expand_row(uint32_t rowAddr, uint32_t slabStride
         sts128(rowAddr + (uint32_t)(c >> 3) * slabStride + (((uint32_t)(c & 7) << 4) ^ rx), o[0], o[1], o[2], o[3]);
     }
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t (&v)[32], uint32_t taddr) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, "
+        "%22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+          "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+          "=r"(v[31])
+        : "r"(taddr));
+}
 __device__ __forceinline__ int popc256(const uint4 &lo, const uint4 &hi) {
     return __popc(lo.x) + __popc(lo.y) + __popc(lo.z) + __popc(lo.w) + __popc(hi.x) + __popc(hi.y) + __popc(hi.z) + __popc(hi.w);
 }
@@ -96,8 +107,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const uint4 *__restri
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);   // the swizzle atoms need 1024-byte alignment
     uint8_t *sA = smem;                                         // [2 K-blocks][128][128]
     uint8_t *sB = smem + TC_A_BYTES;                            // [2 stages][2 K-blocks][256][128]
-    uint32_t *sBase = reinterpret_cast<uint32_t *>(sB + 2 * TC_B_BYTES);      // [2 stages][256]: (|d| << 23) + row of the column
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sBase + 2 * TC_N);          // full[2], empty[2], tfull[2], tempty[2]
+    uint32_t *sBase = reinterpret_cast<uint32_t *>(sB + 2 * TC_B_BYTES);      // [4][256]: key base of the column (ring over tiles)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sBase + TC_BASE_STAGES * TC_N);          // full[2], empty[2], tfull[2], tempty[2]
     uint32_t *tmemAddr = reinterpret_cast<uint32_t *>(bars + 8);
     uint2 *sMerge = reinterpret_cast<uint2 *>(tmemAddr + 2);                  // [128]: the second column half's top-2 per query
     uint64_t *full = bars, *empty = bars + 2, *tfull = bars + 4, *tempty = bars + 6;
@@ -112,7 +123,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const uint4 *__restri
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
             bar_init(&full[s], TC_PRODUCERS);
-            bar_init(&empty[s], 1 + TC_EPILOGUE);               // the MMA commit + every epilogue thread (it reads sBase of the stage)
+            bar_init(&empty[s], 1);                             // the MMA commit: the tensor core has read the stage
             bar_init(&tfull[s], 1);
             bar_init(&tempty[s], TC_EPILOGUE);
         }
@@ -181,7 +192,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const uint4 *__restri
             bar_wait(&empty[s], ph ^ 1u);
             expand_row<false>(s32(sB) + (uint32_t)(s * TC_B_BYTES) + (uint32_t)r * 128u, TC_N * 128, (uint32_t)r, clo, chi);
             // key base of the column: (256 − |d|) above the inverted row (larger key = smaller distance, then smaller row); 0 = no row
-            sBase[s * TC_N + r] = lr < rowsHere ? ((uint32_t)(256 - popc256(clo, chi)) << TC_ROW_BITS) + (((1u << TC_ROW_BITS) - 1u) - (uint32_t)lr) : 0u;
+            // (ring slot t & 3: its previous user, tile t − 4, was drained before the MMA of tile t − 2 could start, and that MMA's
+            // commit is what freed this shared-memory stage)
+            sBase[(t & (TC_BASE_STAGES - 1)) * TC_N + r] = lr < rowsHere ? ((uint32_t)(256 - popc256(clo, chi)) << TC_ROW_BITS) + (((1u << TC_ROW_BITS) - 1u) - (uint32_t)lr) : 0u;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             bar_arrive(&full[s]);
         }
@@ -204,20 +217,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const uint4 *__restri
             const uint32_t ph = (uint32_t)(t >> 1) & 1u;
             bar_wait(&tfull[s], ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t base = s32(sBase) + (uint32_t)(s * TC_N + half * 128) * 4u;      // shared-window address of the key bases
+            const uint32_t base = s32(sBase) + (uint32_t)((t & (TC_BASE_STAGES - 1)) * TC_N + half * 128) * 4u;      // shared-window address of the key bases
             const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * TC_N + half * 128);
-#pragma unroll 1
-            for (int g = 0; g < 4; ++g) {                       // 32 columns per load
-                uint32_t v[32];
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, "
-                    "%22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
-                      "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
-                      "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
-                      "=r"(v[31])
-                    : "r"(taddr + (uint32_t)(g * 32)));
+            // 32 columns per load, two register sets: the load of the next group is in flight while this one is reduced
+            uint32_t va[32], vb[32];
+            tmem_ld32(va, taddr);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                uint32_t (&v)[32] = (g & 1) ? vb : va;
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (g + 1 < 4) tmem_ld32((g & 1) ? va : vb, taddr + (uint32_t)((g + 1) * 32));
                 // accumulator = 128 · dot; key = dot · 2^23 + base: one multiply-add per column (a column past the chunk end has base 0
                 // and dot 0: key 0 never wins)
                 constexpr uint32_t kScale = 1u << (TC_ROW_BITS + 1 - 7);
@@ -241,7 +250,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const uint4 *__restri
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             bar_arrive(&tempty[s]);
-            bar_arrive(&empty[s]);
         }
         // merge the two column halves of every query, convert to the (distance << 23 | row) keys of the merge kernel, write the partial result
         if (half == 1) sMerge[m] = make_uint2(a, b);
