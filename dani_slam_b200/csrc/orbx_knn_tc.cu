@@ -11,14 +11,18 @@
 // smallest per query — the same keys, tie rule (lower row first) and per-chunk partial format as the POPC kernel in
 // orbx_match.cu, whose merge kernel finishes the job.  Results are bit-identical to the POPC path (tests/test_match_gpu.py).
 //
-// One CTA = one tile of 128 queries × one chunk of database rows; warp roles (17 warps):
+// One CTA = one tile of 128 queries × one chunk of database rows; warp roles (21 warps):
 //   warp 0        allocates tensor memory; lane 0 issues the MMAs (8 per database tile: K = 8 × 32 bytes) and commits them
-//   warps 1-8     producers: one database row per thread and tile (32 B, coalesced, prefetched one tile ahead), expanded to the
-//                 swizzled operand tile of the free stage (64 ANDs + 16 16-byte stores); the row's popcount goes into the per-column key base
-//   warps 9-16    epilogue: two threads per query (column halves), 4 × `tcgen05.ld.32x32b.x32` each; per column ONE multiply-add
-//                 forms a max-ordered key (2·dot − |d| in the high bits, inverted row below), a max3 tree pre-reduces 32 columns,
-//                 and the exact top-2 insertion runs only for the groups that can improve the running second best
-// Three mbarrier pipelines connect them (shared-memory stage full/empty, accumulator full/empty), two stages each.
+//   warps 1-4     producers: two database rows per thread and tile (32 B each, coalesced, prefetched one tile ahead), expanded to the
+//                 swizzled operand tile of the free stage (64 ANDs + 16 16-byte stores per row); the row's popcount goes into the
+//                 per-column key base
+//   warps 5-20    two epilogue groups of 8 warps — even tiles (accumulator 0) and odd tiles (accumulator 1) — so that the read-out of
+//                 one accumulator overlaps the next tile's MMA and the other group's read-out; in a group two threads serve a query
+//                 (column halves), 4 × `tcgen05.ld.32x32b.x32` each, double-buffered; per column ONE multiply-add forms a max-ordered
+//                 key (2·dot − |d| in the high bits, inverted row below), a max3 tree pre-reduces 32 columns, and the exact top-2
+//                 insertion runs only for the groups of columns that can improve the running second best
+// Three mbarrier pipelines connect them (shared-memory stage full/empty, accumulator full/empty), two stages each; the key bases
+// live in a 4-deep ring of their own.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -29,13 +33,13 @@ namespace {
 constexpr int TC_M = 128;             // queries per CTA
 constexpr int TC_N = 256;             // database rows per MMA tile
 constexpr int TC_KBYTES = 256;        // operand bytes per row (one byte per descriptor bit)
-constexpr int TC_PRODUCERS = 256;     // threads (warps 1-8): one database row each per tile
-constexpr int TC_EPILOGUE = 256;      // threads (warps 9-16)
-constexpr int TC_THREADS = 32 + TC_PRODUCERS + TC_EPILOGUE;
+constexpr int TC_PRODUCERS = 128;     // threads (warps 1-4): two database rows each per tile
+constexpr int TC_EPILOGUE = 256;      // threads of ONE epilogue group (warps 5-12: even tiles, warps 13-20: odd tiles)
+constexpr int TC_THREADS = 32 + TC_PRODUCERS + 2 * TC_EPILOGUE;
 constexpr int TC_A_BYTES = TC_M * TC_KBYTES;            // 32 KB: two K-blocks of [128 rows][128 B]
 constexpr int TC_B_BYTES = TC_N * TC_KBYTES;            // 64 KB per stage: two K-blocks of [256 rows][128 B]
 constexpr int TC_BASE_STAGES = 4;     // key-base ring: written by the producers of tile t, read by its epilogue, reused by tile t + 4
-constexpr int TC_SMEM = TC_A_BYTES + 2 * TC_B_BYTES + TC_BASE_STAGES * TC_N * 4 + 2048 /* barriers, tmem address, merge buffer */ + 1024 /* alignment slack */;
+constexpr int TC_SMEM = TC_A_BYTES + 2 * TC_B_BYTES + TC_BASE_STAGES * TC_N * 4 + 4096 /* barriers, tmem address, merge buffer */ + 1024 /* alignment slack */;
 constexpr uint32_t TC_ROW_BITS = 22;     // rows of a chunk inside the max-ordered keys of the epilogue (chunks hold < 2^22 - 1 rows)
 constexpr uint32_t TC_IDX_BITS = 23;
 constexpr uint32_t TC_KEY_NONE = 0xffffffffu;
@@ -110,7 +114,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const uint4 *__restri
     uint32_t *sBase = reinterpret_cast<uint32_t *>(sB + 2 * TC_B_BYTES);      // [4][256]: key base of the column (ring over tiles)
     uint64_t *bars = reinterpret_cast<uint64_t *>(sBase + TC_BASE_STAGES * TC_N);          // full[2], empty[2], tfull[2], tempty[2]
     uint32_t *tmemAddr = reinterpret_cast<uint32_t *>(bars + 8);
-    uint2 *sMerge = reinterpret_cast<uint2 *>(tmemAddr + 2);                  // [128]: the second column half's top-2 per query
+    uint2 *sMerge = reinterpret_cast<uint2 *>(tmemAddr + 2);                  // [3][128]: the top-2 of the other (group, column half) threads of a query
     uint64_t *full = bars, *empty = bars + 2, *tfull = bars + 4, *tempty = bars + 6;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -176,34 +180,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const uint4 *__restri
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&tfull[s])) : "memory");
             }
         }
-    } else if (warp <= 8) {
-        // ---- producers ----  (one row per thread and tile; the next tile's row is fetched while the current one is expanded)
-        const int r = tid - 32;                                 // 0 … 255: the tile row = accumulator column of this thread
-        uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
-        if (r < rowsHere) { lo = db[2 * (row0 + r)]; hi = db[2 * (row0 + r) + 1]; }
+    } else if (warp <= 4) {
+        // ---- producers ----  (rows r and r + 128 of every tile; the next tile's rows are fetched while the current ones are expanded)
+        const int r = tid - 32;                                 // 0 … 127
+        uint4 lo[2], hi[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            lo[h] = make_uint4(0, 0, 0, 0); hi[h] = lo[h];
+            if (r + 128 * h < rowsHere) { lo[h] = db[2 * (row0 + r + 128 * h)]; hi[h] = db[2 * (row0 + r + 128 * h) + 1]; }
+        }
         for (int t = 0; t < nTiles; ++t) {
             const int s = t & 1;
             const uint32_t ph = (uint32_t)(t >> 1) & 1u;
-            const uint4 clo = lo, chi = hi;
-            const long long lr = (long long)t * TC_N + r;       // row inside the chunk
-            const long long nr = lr + TC_N;
-            lo = make_uint4(0, 0, 0, 0); hi = lo;
-            if (nr < rowsHere) { lo = db[2 * (row0 + nr)]; hi = db[2 * (row0 + nr) + 1]; }
+            uint4 clo[2], chi[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                clo[h] = lo[h]; chi[h] = hi[h];
+                const long long nr = (long long)(t + 1) * TC_N + r + 128 * h;
+                lo[h] = make_uint4(0, 0, 0, 0); hi[h] = lo[h];
+                if (nr < rowsHere) { lo[h] = db[2 * (row0 + nr)]; hi[h] = db[2 * (row0 + nr) + 1]; }
+            }
             bar_wait(&empty[s], ph ^ 1u);
-            expand_row<false>(s32(sB) + (uint32_t)(s * TC_B_BYTES) + (uint32_t)r * 128u, TC_N * 128, (uint32_t)r, clo, chi);
-            // key base of the column: (256 − |d|) above the inverted row (larger key = smaller distance, then smaller row); 0 = no row
-            // (ring slot t & 3: its previous user, tile t − 4, was drained before the MMA of tile t − 2 could start, and that MMA's
-            // commit is what freed this shared-memory stage)
-            sBase[(t & (TC_BASE_STAGES - 1)) * TC_N + r] = lr < rowsHere ? ((uint32_t)(256 - popc256(clo, chi)) << TC_ROW_BITS) + (((1u << TC_ROW_BITS) - 1u) - (uint32_t)lr) : 0u;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t rr = (uint32_t)(r + 128 * h);    // the tile row = accumulator column
+                const long long lr = (long long)t * TC_N + rr;  // row inside the chunk
+                expand_row<false>(s32(sB) + (uint32_t)(s * TC_B_BYTES) + rr * 128u, TC_N * 128, rr, clo[h], chi[h]);
+                // key base of the column: (256 − |d|) above the inverted row (larger key = smaller distance, then smaller row); 0 = no row
+                // (ring slot t & 3: its previous user, tile t − 4, was drained before the MMA of tile t − 2 could start, and that MMA's
+                // commit is what freed this shared-memory stage)
+                sBase[(t & (TC_BASE_STAGES - 1)) * TC_N + rr] =
+                    lr < rowsHere ? ((uint32_t)(256 - popc256(clo[h], chi[h])) << TC_ROW_BITS) + (((1u << TC_ROW_BITS) - 1u) - (uint32_t)lr) : 0u;
+            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             bar_arrive(&full[s]);
         }
     } else {
         // ---- epilogue: thread = (query row, column half) ----
-        const int et = tid - 32 - TC_PRODUCERS;                 // 0 … 255
-        const int ew = et >> 5;                                 // 0 … 7
+        const int et = tid - 32 - TC_PRODUCERS;                 // 0 … 511
+        const int grp = et >> 8;                                // 0: even tiles, 1: odd tiles
+        const int ew = (et >> 5) & 7;                           // warp inside the group
         const int quarter = warp & 3;                           // the TMEM lane quarter this warp may access is fixed by its id
-        const int half = ew >> 2;                               // 0: columns 0-127, 1: columns 128-255 (warps 9-12 / 13-16 cover each quarter once)
+        const int half = ew >> 2;                               // 0: columns 0-127, 1: columns 128-255 (four consecutive warps cover each quarter once)
         const int m = quarter * 32 + lane;                      // query row = TMEM lane
         int qn = 0;
         if (q0 + m < nq) {
@@ -212,8 +230,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const uint4 *__restri
         }
         // running top-2 in MAX order over keys  (2·dot − |d| + 256) << 22 | (2^22 − 1 − row)   (real keys are > 0)
         uint32_t a = 0, b = 0;
-        for (int t = 0; t < nTiles; ++t) {
-            const int s = t & 1;
+        for (int t = grp; t < nTiles; t += 2) {
+            const int s = grp;                                  // == t & 1
             const uint32_t ph = (uint32_t)(t >> 1) & 1u;
             bar_wait(&tfull[s], ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -252,12 +270,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const uint4 *__restri
             bar_arrive(&tempty[s]);
         }
         // merge the two column halves of every query, convert to the (distance << 23 | row) keys of the merge kernel, write the partial result
-        if (half == 1) sMerge[m] = make_uint2(a, b);
-        asm volatile("bar.sync 1, %0;" ::"r"(TC_EPILOGUE) : "memory");      // named barrier: the 256 epilogue threads only
-        if (half == 0 && q0 + m < nq) {
-            const uint2 o = sMerge[m];
-            uint32_t lo2 = min(o.x, a); a = max(o.x, a); b = max(b, lo2);
-            lo2 = min(o.y, a); a = max(o.y, a); b = max(b, lo2);
+        const int part = grp * 2 + half;                        // the four threads of a query: part 0 merges
+        if (part > 0) sMerge[(part - 1) * TC_M + m] = make_uint2(a, b);
+        asm volatile("bar.sync 1, %0;" ::"r"(2 * TC_EPILOGUE) : "memory");   // named barrier: the 512 epilogue threads only
+        if (part == 0 && q0 + m < nq) {
+#pragma unroll
+            for (int o3 = 0; o3 < 3; ++o3) {
+                const uint2 o = sMerge[o3 * TC_M + m];
+                uint32_t lo2 = min(o.x, a); a = max(o.x, a); b = max(b, lo2);
+                lo2 = min(o.y, a); a = max(o.y, a); b = max(b, lo2);
+            }
             auto conv = [&](uint32_t k) -> uint32_t {
                 if (k == 0) return TC_KEY_NONE;
                 const uint32_t sc = k >> TC_ROW_BITS, row = ((1u << TC_ROW_BITS) - 1u) - (k & ((1u << TC_ROW_BITS) - 1u));
