@@ -1,28 +1,29 @@
 // orbx_knn_tc.cu — brute-force Hamming kNN (k = 2) on the 5th-generation tensor cores (tcgen05 / TMEM), sm_100a.
 //
-// For bit vectors q, d ∈ {0,1}^256:  hamming(q, d) = |q| + |d| − 2·(q · d).  The dot products of a tile of 128 queries with a
-// tile of 256 database rows are ONE 128×256×256 integer GEMM: every bit becomes one unsigned operand byte in shared memory
-// (K-major, 128-byte swizzle — the canonical UMMA operand layout).  The order of the 256 terms of a dot product is free, so
-// operand word j (j = 0…7) of a 32-bit descriptor word x holds the bits j, j+8, j+16, j+24 IN PLACE: a database byte is
-// x & (1 << j) ∈ {0, 2^j} — one AND per four operand bytes, no shifts — and the query byte of the same term is scaled the other
-// way, bit << (7 − j), so that every product is 128·(q bit)·(d bit) and the accumulator is exactly 128·(q · d).
-// `tcgen05.mma.kind::i8` (unsigned × unsigned) accumulates in int32 in tensor memory,
-// and the epilogue reads the accumulators back with `tcgen05.ld`, forms packed (distance << 23 | row) keys and keeps the two
-// smallest per query — the same keys, tie rule (lower row first) and per-chunk partial format as the POPC kernel in
-// orbx_match.cu, whose merge kernel finishes the job.  Results are bit-identical to the POPC path (tests/test_match_gpu.py).
+// For bit vectors q, d ∈ {0,1}^256:  hamming(q, d) = |q| + |d| − 2·(q · d) = |q| − Σ_k (2·q_k − 1)·d_k.  The sums of a tile of 128
+// queries with a tile of 256 database rows are ONE 128×256×256 integer GEMM with the queries as ±1 and the database rows as 0/1:
+// every bit becomes one operand byte in shared memory (K-major, 128-byte swizzle — the canonical UMMA operand layout).  The order
+// of the 256 terms is free, so operand word j (j = 0…7) of a 32-bit descriptor word x holds the bits j, j+8, j+16, j+24 IN PLACE:
+// a database byte is x & (1 << j) ∈ {0, 2^j} (j = 7: one shift down, 2^6) — one AND per four operand bytes — and the query byte
+// of the same term carries the inverse scale, ±2^(6−j) (j = 7: ±1), so that every product is ±64·(d bit) and the accumulator is
+// exactly 64·(2·(q · d) − |d|): the database popcount never has to be computed.  `tcgen05.mma.kind::i8` (signed × unsigned)
+// accumulates in int32 in tensor memory, and the epilogue reads the accumulators back with `tcgen05.ld`.  Larger accumulator =
+// smaller distance: a max3 tree over the raw accumulators of 32 columns decides whether the group can touch the running top-2
+// of the query at all; only then are the packed (score, inverted row) keys formed and inserted.  Tie rule (lower row first) and
+// per-chunk partial format are those of the POPC kernel in orbx_match.cu, whose merge kernel finishes the job.  Results are
+// bit-identical to the POPC path (tests/test_match_gpu.py).
 //
 // One CTA = one tile of 128 queries × one chunk of database rows; warp roles (21 warps):
 //   warp 0        allocates tensor memory; lane 0 issues the MMAs (8 per database tile: K = 8 × 32 bytes) and commits them
 //   warps 1-4     producers: two database rows per thread and tile (32 B each, coalesced, prefetched one tile ahead), expanded to the
-//                 swizzled operand tile of the free stage (64 ANDs + 16 16-byte stores per row); the row's popcount goes into the
-//                 per-column key base
+//                 swizzled operand tile of the free stage (64 ANDs, 8 shifts and 16 16-byte stores per row)
 //   warps 5-20    two epilogue groups of 8 warps — even tiles (accumulator 0) and odd tiles (accumulator 1) — so that the read-out of
 //                 one accumulator overlaps the next tile's MMA and the other group's read-out; in a group two threads serve a query
-//                 (column halves), 4 × `tcgen05.ld.32x32b.x32` each, double-buffered; per column ONE multiply-add forms a max-ordered
-//                 key (2·dot − |d| in the high bits, inverted row below), a max3 tree pre-reduces 32 columns, and the exact top-2
-//                 insertion runs only for the groups of columns that can improve the running second best
-// Three mbarrier pipelines connect them (shared-memory stage full/empty, accumulator full/empty), two stages each; the key bases
-// live in a 4-deep ring of their own.
+//                 (column halves), 4 × `tcgen05.ld.32x32b.x32` each, double-buffered; 16 max3 per 32 columns on the raw
+//                 accumulators, and only a group whose best score reaches the running second best of one of the warp's queries
+//                 forms its keys ((score << 22) + inverted row, one multiply-add and one add per column) and runs the exact top-2
+//                 insertion
+// Three mbarrier pipelines connect them (shared-memory stage full/empty, accumulator full/empty), two stages each.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -38,11 +39,11 @@ constexpr int TC_EPILOGUE = 256;      // threads of ONE epilogue group (warps 5-
 constexpr int TC_THREADS = 32 + TC_PRODUCERS + 2 * TC_EPILOGUE;
 constexpr int TC_A_BYTES = TC_M * TC_KBYTES;            // 32 KB: two K-blocks of [128 rows][128 B]
 constexpr int TC_B_BYTES = TC_N * TC_KBYTES;            // 64 KB per stage: two K-blocks of [256 rows][128 B]
-constexpr int TC_BASE_STAGES = 4;     // key-base ring: written by the producers of tile t, read by its epilogue, reused by tile t + 4
-constexpr int TC_SMEM = TC_A_BYTES + 2 * TC_B_BYTES + TC_BASE_STAGES * TC_N * 4 + 4096 /* barriers, tmem address, merge buffer */ + 1024 /* alignment slack */;
+constexpr int TC_SMEM = TC_A_BYTES + 2 * TC_B_BYTES + 4096 /* barriers, tmem address, merge buffer */ + 1024 /* alignment slack */;
 constexpr uint32_t TC_ROW_BITS = 22;     // rows of a chunk inside the max-ordered keys of the epilogue (chunks hold < 2^22 - 1 rows)
 constexpr uint32_t TC_IDX_BITS = 23;
 constexpr uint32_t TC_KEY_NONE = 0xffffffffu;
+constexpr int TC_NONE = (int)0x80000000;       // "no candidate" in the signed max-ordered keys of the epilogue (real keys are >= -2^30)
 
 __device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bar_init(uint64_t *b, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(count) : "memory"); }
@@ -70,11 +71,12 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 // One 32-byte descriptor row → 256 operand bytes in the two K-block slabs of a tile (slab k holds operand bytes 128k … 128k+127).
-// Operand word 8i + j = the bits j, j+8, j+16, j+24 of descriptor word i, left where they are (DB: byte ∈ {0, 2^j}) or moved to
-// bit 7 − j (QUERY: byte ∈ {0, 2^(7−j)}).  rowAddr: shared-window address of the row in slab 0; the 16-byte chunks of a row are
-// XOR-swizzled with the row index modulo 8.
+// Operand word 8i + j = the bits j, j+8, j+16, j+24 of descriptor word i.  DB: the bits stay where they are, byte ∈ {0, 2^j}
+// (j = 7: shifted down once, {0, 2^6}).  QUERY: byte = +s for a set bit, −s for a clear one, s = 2^(6−j) (j = 7: 1); a query
+// beyond nq (zero = true) is all-zero bytes.  rowAddr: shared-window address of the row in slab 0; the 16-byte chunks of a row
+// are XOR-swizzled with the row index modulo 8.
 template <bool QUERY>
-__device__ __forceinline__ void expand_row(uint32_t rowAddr, uint32_t slabStride, uint32_t r, const uint4 &lo, const uint4 &hi) {
+__device__ __forceinline__ void expand_row(uint32_t rowAddr, uint32_t slabStride, uint32_t r, const uint4 &lo, const uint4 &hi, bool zero = false) {
     const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
     const uint32_t rx = (r & 7u) << 4;
 #pragma unroll
@@ -85,7 +87,13 @@ __device__ __forceinline__ void expand_row(uint32_t rowAddr, uint32_t slabStride
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int j = j0 + k;
-            o[k] = QUERY ? ((x >> j) & 0x01010101u) << (7 - j) : x & (0x01010101u << j);
+            if (QUERY) {
+                const uint32_t sc = j < 7 ? (1u << (6 - j)) : 1u;
+                const uint32_t M = ((x >> j) & 0x01010101u) * 255u;                              // 0xff in the bytes of set bits
+                o[k] = zero ? 0u : (M & (0x01010101u * sc)) | (~M & (0x01010101u * (256u - sc)));   // +s | −s as two's-complement bytes
+            } else {
+                o[k] = j < 7 ? x & (0x01010101u << j) : (x >> 1) & 0x40404040u;
+            }
         }
         sts128(rowAddr + (uint32_t)(c >> 3) * slabStride + (((uint32_t)(c & 7) << 4) ^ rx), o[0], o[1], o[2], o[3]);
     }
@@ -111,8 +119,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const uint4 *__restri
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);   // the swizzle atoms need 1024-byte alignment
     uint8_t *sA = smem;                                         // [2 K-blocks][128][128]
     uint8_t *sB = smem + TC_A_BYTES;                            // [2 stages][2 K-blocks][256][128]
-    uint32_t *sBase = reinterpret_cast<uint32_t *>(sB + 2 * TC_B_BYTES);      // [4][256]: key base of the column (ring over tiles)
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sBase + TC_BASE_STAGES * TC_N);          // full[2], empty[2], tfull[2], tempty[2]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + 2 * TC_B_BYTES);         // full[2], empty[2], tfull[2], tempty[2]
     uint32_t *tmemAddr = reinterpret_cast<uint32_t *>(bars + 8);
     uint2 *sMerge = reinterpret_cast<uint2 *>(tmemAddr + 2);                  // [3][128]: the top-2 of the other (group, column half) threads of a query
     uint64_t *full = bars, *empty = bars + 2, *tfull = bars + 4, *tempty = bars + 6;
@@ -141,7 +148,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const uint4 *__restri
     for (int r = tid; r < TC_M; r += TC_THREADS) {              // queries beyond nq are zero rows (their results are not written)
         uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
         if (q0 + r < nq) { lo = q[2 * (long long)(q0 + r)]; hi = q[2 * (long long)(q0 + r) + 1]; }
-        expand_row<true>(s32(sA) + (uint32_t)r * 128u, TC_M * 128, (uint32_t)r, lo, hi);
+        expand_row<true>(s32(sA) + (uint32_t)r * 128u, TC_M * 128, (uint32_t)r, lo, hi, q0 + r >= nq);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes → visible to the tensor core's async proxy
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -152,8 +159,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const uint4 *__restri
     if (warp == 0) {
         // ---- MMA issuer ----
         if (lane == 0) {
-            // instruction descriptor (kind::i8): D = s32 (2 << 4), A and B unsigned 8-bit, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-            const uint32_t idesc = (2u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+            // instruction descriptor (kind::i8): D = s32 (2 << 4), A signed 8-bit (1 << 7), B unsigned 8-bit, both K-major, N >> 3 at bit 17,
+            // M >> 4 at bit 24
+            const uint32_t idesc = (2u << 4) | (1u << 7) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
             const uint32_t aBase = s32(sA);
             for (int t = 0; t < nTiles; ++t) {
                 const int s = t & 1;
@@ -204,13 +212,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const uint4 *__restri
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const uint32_t rr = (uint32_t)(r + 128 * h);    // the tile row = accumulator column
-                const long long lr = (long long)t * TC_N + rr;  // row inside the chunk
                 expand_row<false>(s32(sB) + (uint32_t)(s * TC_B_BYTES) + rr * 128u, TC_N * 128, rr, clo[h], chi[h]);
-                // key base of the column: (256 − |d|) above the inverted row (larger key = smaller distance, then smaller row); 0 = no row
-                // (ring slot t & 3: its previous user, tile t − 4, was drained before the MMA of tile t − 2 could start, and that MMA's
-                // commit is what freed this shared-memory stage)
-                sBase[(t & (TC_BASE_STAGES - 1)) * TC_N + rr] =
-                    lr < rowsHere ? ((uint32_t)(256 - popc256(clo[h], chi[h])) << TC_ROW_BITS) + (((1u << TC_ROW_BITS) - 1u) - (uint32_t)lr) : 0u;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             bar_arrive(&full[s]);
@@ -228,15 +230,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const uint4 *__restri
             const uint4 lo = q[2 * (long long)(q0 + m)], hi = q[2 * (long long)(q0 + m) + 1];
             qn = popc256(lo, hi);
         }
-        // running top-2 in MAX order over keys  (2·dot − |d| + 256) << 22 | (2^22 − 1 − row)   (real keys are > 0)
-        uint32_t a = 0, b = 0;
+        // running top-2 in signed MAX order over keys  (score << 22) + (2^22 − 1 − row),  score = 2·dot − |d| = accumulator / 64
+        int a = TC_NONE, b = TC_NONE;
         for (int t = grp; t < nTiles; t += 2) {
             const int s = grp;                                  // == t & 1
             const uint32_t ph = (uint32_t)(t >> 1) & 1u;
             bar_wait(&tfull[s], ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t base = s32(sBase) + (uint32_t)((t & (TC_BASE_STAGES - 1)) * TC_N + half * 128) * 4u;      // shared-window address of the key bases
             const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * TC_N + half * 128);
+            const long long col0 = (long long)t * TC_N + half * 128;          // chunk row of this thread's first column
             // 32 columns per load, two register sets: the load of the next group is in flight while this one is reduced
             uint32_t va[32], vb[32];
             tmem_ld32(va, taddr);
@@ -245,23 +247,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const uint4 *__restri
                 uint32_t (&v)[32] = (g & 1) ? vb : va;
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (g + 1 < 4) tmem_ld32((g & 1) ? va : vb, taddr + (uint32_t)((g + 1) * 32));
-                // accumulator = 128 · dot; key = dot · 2^23 + base: one multiply-add per column (a column past the chunk end has base 0
-                // and dot 0: key 0 never wins)
-                constexpr uint32_t kScale = 1u << (TC_ROW_BITS + 1 - 7);
-                uint32_t kmax = 0;
+                int vmax = (int)v[0];
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    uint4 bs;
-                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(bs.x), "=r"(bs.y), "=r"(bs.z), "=r"(bs.w) : "r"(base + (uint32_t)(g * 32 + j) * 4u));
-                    v[j] = v[j] * kScale + bs.x; v[j + 1] = v[j + 1] * kScale + bs.y;
-                    v[j + 2] = v[j + 2] * kScale + bs.z; v[j + 3] = v[j + 3] * kScale + bs.w;
-                    kmax = max(max(kmax, max(v[j], v[j + 1])), max(v[j + 2], v[j + 3]));
-                }
-                if (kmax > b) {                                 // this group can change the running top-2: exact insertion
+                for (int j = 1; j < 32; ++j) vmax = max(vmax, (int)v[j]);
+                // can a column of the group enter the top-2?  Its key is below (accumulator << 16) + 2^22; the threshold is exact up to
+                // the row bits, so ties on the score take the exact path too.  (b = TC_NONE: everything passes.)
+                if (vmax >= (b >> 16)) {
+                    const long long lr0 = col0 + g * 32;
+                    const int nValid = (int)min(32LL, rowsHere - lr0);          // columns past the end of the chunk hold no row
+                    const int inv0 = (int)(((1u << TC_ROW_BITS) - 1u) - (uint32_t)lr0);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const uint32_t lo2 = min(v[j], a);
-                        a = max(v[j], a);
+                        const int key = j < nValid ? (int)v[j] * (1 << (TC_ROW_BITS - 6)) + (inv0 - j) : TC_NONE;
+                        const int lo2 = min(key, a);
+                        a = max(key, a);
                         b = max(b, lo2);
                     }
                 }
@@ -269,21 +268,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const uint4 *__restri
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             bar_arrive(&tempty[s]);
         }
-        // merge the two column halves of every query, convert to the (distance << 23 | row) keys of the merge kernel, write the partial result
+        // merge the four (tile parity, column half) results of every query, convert to the (distance << 23 | row) keys of the merge kernel,
+        // write the partial result
         const int part = grp * 2 + half;                        // the four threads of a query: part 0 merges
-        if (part > 0) sMerge[(part - 1) * TC_M + m] = make_uint2(a, b);
+        if (part > 0) sMerge[(part - 1) * TC_M + m] = make_uint2((uint32_t)a, (uint32_t)b);
         asm volatile("bar.sync 1, %0;" ::"r"(2 * TC_EPILOGUE) : "memory");   // named barrier: the 512 epilogue threads only
         if (part == 0 && q0 + m < nq) {
 #pragma unroll
             for (int o3 = 0; o3 < 3; ++o3) {
                 const uint2 o = sMerge[o3 * TC_M + m];
-                uint32_t lo2 = min(o.x, a); a = max(o.x, a); b = max(b, lo2);
-                lo2 = min(o.y, a); a = max(o.y, a); b = max(b, lo2);
+                int lo2 = min((int)o.x, a); a = max((int)o.x, a); b = max(b, lo2);
+                lo2 = min((int)o.y, a); a = max((int)o.y, a); b = max(b, lo2);
             }
-            auto conv = [&](uint32_t k) -> uint32_t {
-                if (k == 0) return TC_KEY_NONE;
-                const uint32_t sc = k >> TC_ROW_BITS, row = ((1u << TC_ROW_BITS) - 1u) - (k & ((1u << TC_ROW_BITS) - 1u));
-                return ((uint32_t)(qn + 256 - (int)sc) << TC_IDX_BITS) | row;          // distance = |q| + |d| − 2·dot = |q| + 256 − score
+            auto conv = [&](int k) -> uint32_t {
+                if (k == TC_NONE) return TC_KEY_NONE;
+                const int sc = k >> TC_ROW_BITS;                                        // arithmetic shift: the score, exactly
+                const uint32_t row = ((1u << TC_ROW_BITS) - 1u) - ((uint32_t)k & ((1u << TC_ROW_BITS) - 1u));
+                return ((uint32_t)(qn - sc) << TC_IDX_BITS) | row;                     // distance = |q| + |d| − 2·dot = |q| − score
             };
             partial[(long long)blockIdx.x * nq + (q0 + m)] = make_uint2(conv(a), conv(b));
         }
