@@ -247,21 +247,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const uint4 *__restri
                 uint32_t (&v)[32] = (g & 1) ? vb : va;
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (g + 1 < 4) tmem_ld32((g & 1) ? va : vb, taddr + (uint32_t)((g + 1) * 32));
-                int vmax = (int)v[0];
+                // maxima of the four octets of columns and of the group
+                int m8[4];
 #pragma unroll
-                for (int j = 1; j < 32; ++j) vmax = max(vmax, (int)v[j]);
-                // can a column of the group enter the top-2?  Its key is below (accumulator << 16) + 2^22; the threshold is exact up to
-                // the row bits, so ties on the score take the exact path too.  (b = TC_NONE: everything passes.)
-                if (vmax >= (b >> 16)) {
+                for (int o = 0; o < 4; ++o) {
+                    int mx = max(max((int)v[8 * o], (int)v[8 * o + 1]), (int)v[8 * o + 2]);
+                    mx = max(max(mx, (int)v[8 * o + 3]), (int)v[8 * o + 4]);
+                    mx = max(max(mx, (int)v[8 * o + 5]), (int)v[8 * o + 6]);
+                    m8[o] = max(mx, (int)v[8 * o + 7]);
+                }
+                const int vmax = max(max(m8[0], m8[1]), max(m8[2], m8[3]));
+                // Can a column enter the top-2?  Only with a score above the running second best's: this thread meets its rows in
+                // increasing order, so a later row never wins a tie.  thr = the smallest accumulator (64 · score) that qualifies
+                // (b = TC_NONE: everything does); b only grows, so a stale thr is merely conservative.
+                const int thr = ((b >> TC_ROW_BITS) + 1) * 64;
+                if (vmax >= thr) {
                     const long long lr0 = col0 + g * 32;
                     const int nValid = (int)min(32LL, rowsHere - lr0);          // columns past the end of the chunk hold no row
                     const int inv0 = (int)(((1u << TC_ROW_BITS) - 1u) - (uint32_t)lr0);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int key = j < nValid ? (int)v[j] * (1 << (TC_ROW_BITS - 6)) + (inv0 - j) : TC_NONE;
-                        const int lo2 = min(key, a);
-                        a = max(key, a);
-                        b = max(b, lo2);
+                    for (int o = 0; o < 4; ++o) {
+                        if (m8[o] >= thr) {
+#pragma unroll
+                            for (int j = 8 * o; j < 8 * o + 8; ++j) {
+                                const int key = j < nValid ? (int)v[j] * (1 << (TC_ROW_BITS - 6)) + (inv0 - j) : TC_NONE;
+                                const int lo2 = min(key, a);
+                                a = max(key, a);
+                                b = max(b, lo2);
+                            }
+                        }
                     }
                 }
             }
