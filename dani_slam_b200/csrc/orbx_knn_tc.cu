@@ -36,7 +36,8 @@ constexpr int TC_N = 256;             // database rows per MMA tile
 constexpr int TC_KBYTES = 256;        // operand bytes per row (one byte per descriptor bit)
 constexpr int TC_PRODUCERS = 128;     // threads (warps 1-4): two database rows each per tile
 constexpr int TC_EPILOGUE = 256;      // threads of ONE epilogue group (warps 5-12: even tiles, warps 13-20: odd tiles)
-constexpr int TC_THREADS = 32 + TC_PRODUCERS + 2 * TC_EPILOGUE;
+constexpr int TC_GROUPS = 1;           // epilogue groups: 1 = every tile by the same 8 warps, 2 = even / odd tiles by 8 warps each
+constexpr int TC_THREADS = 32 + TC_PRODUCERS + TC_GROUPS * TC_EPILOGUE;
 constexpr int TC_A_BYTES = TC_M * TC_KBYTES;            // 32 KB: two K-blocks of [128 rows][128 B]
 constexpr int TC_B_BYTES = TC_N * TC_KBYTES;            // 64 KB per stage: two K-blocks of [256 rows][128 B]
 constexpr int TC_SMEM = TC_A_BYTES + 2 * TC_B_BYTES + 4096 /* barriers, tmem address, merge buffer */ + 1024 /* alignment slack */;
@@ -232,8 +233,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const uint4 *__restri
         }
         // running top-2 in signed MAX order over keys  (score << 22) + (2^22 − 1 − row),  score = 2·dot − |d| = accumulator / 64
         int a = TC_NONE, b = TC_NONE;
-        for (int t = grp; t < nTiles; t += 2) {
-            const int s = grp;                                  // == t & 1
+        for (int t = grp; t < nTiles; t += TC_GROUPS) {
+            const int s = t & 1;
             const uint32_t ph = (uint32_t)(t >> 1) & 1u;
             bar_wait(&tfull[s], ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -284,12 +285,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const uint4 *__restri
         }
         // merge the four (tile parity, column half) results of every query, convert to the (distance << 23 | row) keys of the merge kernel,
         // write the partial result
-        const int part = grp * 2 + half;                        // the four threads of a query: part 0 merges
+        const int part = grp * 2 + half;                        // the threads of a query: part 0 merges
         if (part > 0) sMerge[(part - 1) * TC_M + m] = make_uint2((uint32_t)a, (uint32_t)b);
-        asm volatile("bar.sync 1, %0;" ::"r"(2 * TC_EPILOGUE) : "memory");   // named barrier: the 512 epilogue threads only
+        asm volatile("bar.sync 1, %0;" ::"r"(TC_GROUPS * TC_EPILOGUE) : "memory");   // named barrier: the epilogue threads only
         if (part == 0 && q0 + m < nq) {
 #pragma unroll
-            for (int o3 = 0; o3 < 3; ++o3) {
+            for (int o3 = 0; o3 < 2 * TC_GROUPS - 1; ++o3) {
                 const uint2 o = sMerge[o3 * TC_M + m];
                 int lo2 = min((int)o.x, a); a = max((int)o.x, a); b = max(b, lo2);
                 lo2 = min((int)o.y, a); a = max((int)o.y, a); b = max(b, lo2);
