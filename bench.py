@@ -626,12 +626,14 @@ def main():
                  "parity_note": "sharded result of every rank == rank 0's unsharded scan of the whole DB (indices and distances)" if dist_on else
                                 "single GPU: see cpu_baseline.sample and tests/test_match_gpu.py::test_config4_full_size_vs_oracle",
                  "popc_per_s": 8 * gpairs * 1e9, "cpu_baseline": None,
-                 "roofline": {"bound": "tensor", "achieved": tops, "peak": 2 * bf16_peak, "unit": "TOP/s (int8) per GPU", "frac": tops / (2 * bf16_peak),
-                              "frac_of_measured_bf16": tops / bf16_peak,
-                              "peak_source": ("2 x MEASURED_PEAKS.json bf16_tflops (burst; int8 runs at twice the bf16 rate on sm_100a)" if "bf16_tflops" in peaks
-                                              else "2 x fallback 1590 TFLOP/s bf16 (B200_PROFILING.md)"),
-                              "note": "algorithmic work: one 256-term 0/1 dot product per pair = 512 integer ops; ncu: the kernel is bound by shared-memory "
-                                      "bandwidth (operand expansion writes + the tensor core's operand reads), tensor pipe about half busy"},
+                 "roofline": {"bound": "tensor", "achieved": tops, "peak": 4500.0, "unit": "TOP/s (int8) per GPU", "frac": tops / 4500.0,
+                              "peak_source": "nominal dense 8-bit tensor rate of B200 (B200_PROFILING.md: 4.5 POP/s; MEASURED_PEAKS.json holds no 8-bit "
+                                             "figure)",
+                              "frac_of_2x_measured_bf16": tops / (2 * bf16_peak),
+                              "measured_bf16_tflops": bf16_peak,
+                              "note": "algorithmic work: one 256-term dot product per pair = 512 integer ops.  The cuBLAS bf16 GEMM of MEASURED_PEAKS.json "
+                                      "reaches 0.73 of ITS nominal rate on this pool; twice that figure is given beside the nominal 8-bit peak.  ncu "
+                                      "(profiles/ncu_knn_tc_r02.txt): tensor pipe active for about 0.8 of the kernel"},
                  "popc_kernel": None if popc_gpairs is None else {
                      "value": popc_gpairs, "unit": "Gpairs/s", "same_result": popc_same,
                      "roofline": {"bound": "int-popc", "issued": 5 * popc_gpairs * 1e9, "achieved": 8 * popc_gpairs * 1e9, "peak": popc_peak,

@@ -1701,6 +1701,41 @@ __global__ void __launch_bounds__(128) k_qt_attach(ExParams p, QtTables t) {
     }
 }
 
+// attach + select in one block per (level, frame): the per-node maxima live in shared memory (no global atomics, one launch less)
+template <int NT>
+__global__ void __launch_bounds__(NT) k_qt_attach_select(ExParams p, QtTables t) {
+    extern __shared__ __align__(16) unsigned s_best[];
+    const OrbxGeom &g = *p.g;
+    const int l = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    if (t.deep[b * g.nlevels + l]) return;           // the general kernel wrote this level's list itself
+    const OrbxLevel &LV = g.lv[l];
+    const int size = p.selCnt[b * g.nlevels + l];
+    for (int i = tid; i < size; i += NT) s_best[i] = 0;
+    __syncthreads();
+    const int nCells = LV.nCells;
+    if (nCells > 0) {
+        const int nPts = t.cellPrefix[(long long)b * g.nCellsTotal + LV.cellBase + nCells - 1] + p.cellCnt[(long long)b * g.nCellsTotal + LV.cellBase + nCells - 1];
+        const uint32_t *ptNode = p.ptNode + (long long)b * g.slotsTotal + LV.slotBase;
+        const unsigned short *finalPos = t.finalPos + ((long long)b * g.nlevels + l) * (long long)t.maxIni * QT_TREE;
+        for (int i = tid; i < nPts; i += NT) {
+            const uint32_t v = ptNode[i];
+            if (v == ORBX_NODE_ERASED) continue;
+            const unsigned pos = finalPos[v & 0xffffu];
+            // first maximum in insertion order wins: larger key = larger response, then smaller order index
+            if (pos) atomicMax(&s_best[pos - 1], (((v >> 16) & 0xffu) << 24) | (0xffffffu - (unsigned)i));
+        }
+    }
+    __syncthreads();
+    const float2 *ptXY = p.ptXY + (long long)b * g.slotsTotal + LV.slotBase;
+    float4 *sel = p.sel + (long long)b * g.selTotal + LV.selBase;
+    for (int i = tid; i < size; i += NT) {
+        const unsigned k = s_best[i];
+        const float2 xy = ptXY[0xffffffu - (k & 0xffffffu)];
+        // :919-923 — add the border back; response = FAST score
+        sel[i] = make_float4(__fadd_rn(xy.x, (float)ORBX_BORDER), __fadd_rn(xy.y, (float)ORBX_BORDER), (float)(k >> 24), 0.f);
+    }
+}
+
 __global__ void __launch_bounds__(128) k_qt_select(ExParams p, QtTables t) {
     const OrbxGeom &g = *p.g;
     const int l = blockIdx.x, b = blockIdx.y;
@@ -2965,10 +3000,16 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
         }
         ++ex->launches;
         if (useHist) {
-            dim3 grdC(QT_CLS_BLOCKS, G.nlevels, batch);
-            k_qt_attach<<<grdC, 128, 0, s>>>(P, T);
-            k_qt_select<<<grd, 128, 0, s>>>(P, T);
-            ex->launches += 2;
+            const size_t smemS = (size_t)ex->nodeCapMax * sizeof(unsigned);
+            if (smemS <= 48 * 1024) {
+                k_qt_attach_select<512><<<grd, 512, smemS, s>>>(P, T);
+                ++ex->launches;
+            } else {
+                dim3 grdC(QT_CLS_BLOCKS, G.nlevels, batch);
+                k_qt_attach<<<grdC, 128, 0, s>>>(P, T);
+                k_qt_select<<<grd, 128, 0, s>>>(P, T);
+                ex->launches += 2;
+            }
         } else {
             CUDA_TRY(ex, cudaMemsetAsync(T.deep, 0, (size_t)batch * G.nlevels * sizeof(int), s));
         }
