@@ -170,6 +170,14 @@ def cpu_extract_fps(frames: np.ndarray, threads: int, seconds: float, use_ref: b
     return sum(done) / dt, sum(done), dt, kind
 
 
+def bench_config(args, world, B):
+    """The `config` object of the JSON line: the workload and its sharding, nothing measured — identical for this arm and for
+    `--impl reference` (the driver compares the two)."""
+    return {"workload": f"{args.workload}_{W_IMG}x{H_IMG}_nf{NFEAT}_8lv_fast20_7", "frames_per_gpu_per_step": B,
+            "global_batch": world * B, "parallelism": f"frame-batch x{world} (no collective)",
+            "l2": f"inputs {B * H_IMG * W_IMG / 1e6:.0f} MB + {B * SUM_P * 2 / 1e6:.0f} MB of pyramid planes touched per step > 126 MB L2 (no flush needed)"}
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's own CPU implementation of the path on the host cores."""
     if rank != 0:
@@ -190,9 +198,10 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "orb_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * tot_t / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"{args.workload}_{W_IMG}x{H_IMG}_nf{NFEAT}_8lv_fast20_7", "frames_per_step": tot_frames / max(args.steps, 1)},
+        "config": bench_config(args, max(1, args.gpus), args.batch),
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind,
-                         "sample": f"{tot_frames} frames of the bench workload over {args.steps} steps of {per_step}s, one frame per thread"},
+                         "sample": f"{tot_frames} frames of the bench workload over {args.steps} steps of {per_step}s "
+                                   f"({tot_frames / max(args.steps, 1):.0f} frames per step), one frame per thread"},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -727,10 +736,8 @@ def main():
             "metric": "orb_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": f"{args.workload}_{W_IMG}x{H_IMG}_nf{NFEAT}_8lv_fast20_7", "frames_per_gpu_per_step": B,
-                       "global_batch": world * B, "parallelism": f"frame-batch x{world} (no collective)",
-                       "l2": f"inputs {B * H_IMG * W_IMG / 1e6:.0f} MB + {B * SUM_P * 2 / 1e6:.0f} MB of pyramid planes touched per step > 126 MB L2 (no flush needed)",
-                       "keypoints_per_frame": n_avg},
+            "config": bench_config(args, world, B),
+            "keypoints_per_frame": n_avg,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "orbx_extract_batch (host pinned buffers, H2D + D2H inside the timed region)" + (", write-combined input" if args.wc_input else ""),
