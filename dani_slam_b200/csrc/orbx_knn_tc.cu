@@ -13,16 +13,15 @@
 // per-chunk partial format are those of the POPC kernel in orbx_match.cu, whose merge kernel finishes the job.  Results are
 // bit-identical to the POPC path (tests/test_match_gpu.py).
 //
-// One CTA = one tile of 128 queries × one chunk of database rows; warp roles (21 warps):
+// One CTA = one tile of 128 queries × one chunk of database rows; warp roles (13 warps; TC_GROUPS = 2 adds a second epilogue group):
 //   warp 0        allocates tensor memory; lane 0 issues the MMAs (8 per database tile: K = 8 × 32 bytes) and commits them
 //   warps 1-4     producers: two database rows per thread and tile (32 B each, coalesced, prefetched one tile ahead), expanded to the
 //                 swizzled operand tile of the free stage (64 ANDs, 8 shifts and 16 16-byte stores per row)
-//   warps 5-20    two epilogue groups of 8 warps — even tiles (accumulator 0) and odd tiles (accumulator 1) — so that the read-out of
-//                 one accumulator overlaps the next tile's MMA and the other group's read-out; in a group two threads serve a query
-//                 (column halves), 4 × `tcgen05.ld.32x32b.x32` each, double-buffered; 16 max3 per 32 columns on the raw
-//                 accumulators, and only a group whose best score reaches the running second best of one of the warp's queries
-//                 forms its keys ((score << 22) + inverted row, one multiply-add and one add per column) and runs the exact top-2
-//                 insertion
+//   warps 5-12    the epilogue group: two threads serve a query (column halves), 4 × `tcgen05.ld.32x32b.x32` each, double-buffered,
+//                 while the tensor core fills the other accumulator stage; 16 max3 per 32 columns on the raw accumulators, and only
+//                 an octet whose best score beats the running second best of the thread's query forms its keys ((score << 22) +
+//                 inverted row, one multiply-add per column) and runs the exact top-2 insertion.  (One group of 8 warps keeps up
+//                 with the tensor core; with two groups — even / odd tiles — the extra spinning warps cost more than they gave.)
 // Three mbarrier pipelines connect them (shared-memory stage full/empty, accumulator full/empty), two stages each.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -35,7 +34,7 @@ constexpr int TC_M = 128;             // queries per CTA
 constexpr int TC_N = 256;             // database rows per MMA tile
 constexpr int TC_KBYTES = 256;        // operand bytes per row (one byte per descriptor bit)
 constexpr int TC_PRODUCERS = 128;     // threads (warps 1-4): two database rows each per tile
-constexpr int TC_EPILOGUE = 256;      // threads of ONE epilogue group (warps 5-12: even tiles, warps 13-20: odd tiles)
+constexpr int TC_EPILOGUE = 256;      // threads of ONE epilogue group (warps 5-12; a second group would be warps 13-20)
 constexpr int TC_GROUPS = 1;           // epilogue groups: 1 = every tile by the same 8 warps, 2 = even / odd tiles by 8 warps each
 constexpr int TC_THREADS = 32 + TC_PRODUCERS + TC_GROUPS * TC_EPILOGUE;
 constexpr int TC_A_BYTES = TC_M * TC_KBYTES;            // 32 KB: two K-blocks of [128 rows][128 B]
