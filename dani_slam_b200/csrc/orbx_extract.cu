@@ -2970,18 +2970,25 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
                                    l == 0 ? P.in0Stride : G.frameBytes, BLUR_SP / 16, BLUR_TH + 6))
                 blurTmaMask |= 1 << l;
         }
-    // K5 early, on the partner stream: the blurred levels depend on the pyramid only; started once FAST is done, the
-    // instruction-bound blur fills the SMs while the latency-bound quadtree kernels run
+    // After FAST the pipeline forks: the latency-bound quadtree chain (+ assemble) goes to the partner stream, which has the
+    // HIGHEST stream priority — its blocks are dispatched as soon as they are ready — while the instruction-bound blur (it depends
+    // on the pyramid only) stays on this stream and fills the issue slots the quadtree kernels leave idle.  (ORBX_BLUR_ON_AUX: the
+    // earlier arrangement, blur on an equal-priority partner stream, where the block scheduler ran the two mostly back to back.)
     int aux = -1;
+    cudaStream_t sQ = s;
     if (!prof && ex->overlapBlur) {
         aux = 0;
         for (int i = 0; i < ORBX_MAX_SIDE; ++i) if (onStream && onStream == ex->sSide[i]) aux = 1 + i;
         CUDA_TRY(ex, cudaEventRecord(ex->evPyrDone[aux], s));
         CUDA_TRY(ex, cudaStreamWaitEvent(ex->sAux[aux], ex->evPyrDone[aux], 0));
+#ifdef ORBX_BLUR_ON_AUX
         dim3 grdB((unsigned)ex->h_tiles.size(), batch);
         k_blur<<<grdB, dim3(64, BLUR_STRIPS), 0, ex->sAux[aux]>>>(P, ex->d_tiles, blurSrcMaps, blurTmaMask);
         ++ex->launches;
         CUDA_TRY(ex, cudaEventRecord(ex->evBlurDone[aux], ex->sAux[aux]));
+#else
+        sQ = ex->sAux[aux];
+#endif
     }
     // K3
     {
@@ -3003,53 +3010,59 @@ int run_pipeline(orbx_extractor *ex, const uint8_t *in0, long long in0Stride, in
         if (useHist) {
             const size_t smemP = (size_t)(ex->maxCellsLevel + 1 + QT_THREADS + 2) * sizeof(int);
             if (smemP > 48 * 1024) CUDA_TRY(ex, cudaFuncSetAttribute(k_qt_prefix<QT_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemP));
-            k_qt_prefix<QT_THREADS><<<grd, QT_THREADS, smemP, s>>>(P, T, ex->maxCellsLevel);
+            k_qt_prefix<QT_THREADS><<<grd, QT_THREADS, smemP, sQ>>>(P, T, ex->maxCellsLevel);
             dim3 grdC(QT_CLS_BLOCKS, G.nlevels, batch);
-            k_qt_classify<<<grdC, 128, 0, s>>>(P, T);
+            k_qt_classify<<<grdC, 128, 0, sQ>>>(P, T);
             if (big) {
                 if (smemN > 48 * 1024) CUDA_TRY(ex, cudaFuncSetAttribute(k_qt_nodes<QT_THREADS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemN));
-                k_qt_nodes<QT_THREADS_BIG><<<grd, QT_THREADS_BIG, smemN, s>>>(P, T, ex->nodeCapMax);
+                k_qt_nodes<QT_THREADS_BIG><<<grd, QT_THREADS_BIG, smemN, sQ>>>(P, T, ex->nodeCapMax);
             } else {
                 if (smemN > 48 * 1024) CUDA_TRY(ex, cudaFuncSetAttribute(k_qt_nodes<QT_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemN));
-                k_qt_nodes<QT_THREADS><<<grd, QT_THREADS, smemN, s>>>(P, T, ex->nodeCapMax);
+                k_qt_nodes<QT_THREADS><<<grd, QT_THREADS, smemN, sQ>>>(P, T, ex->nodeCapMax);
             }
             ex->launches += 3;
         }
         // general kernel: everything when the fast path is off, otherwise only the flagged (frame, level) pairs
         if (big) {
             if (L.total > 48 * 1024) CUDA_TRY(ex, cudaFuncSetAttribute(k_quadtree<QT_THREADS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-            k_quadtree<QT_THREADS_BIG><<<grd, QT_THREADS_BIG, L.total, s>>>(P, ex->nodeCapMax, ex->maxCellsLevel, useHist ? T.deep : nullptr);
+            k_quadtree<QT_THREADS_BIG><<<grd, QT_THREADS_BIG, L.total, sQ>>>(P, ex->nodeCapMax, ex->maxCellsLevel, useHist ? T.deep : nullptr);
         } else {
             if (L.total > 48 * 1024) CUDA_TRY(ex, cudaFuncSetAttribute(k_quadtree<QT_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-            k_quadtree<QT_THREADS><<<grd, QT_THREADS, L.total, s>>>(P, ex->nodeCapMax, ex->maxCellsLevel, useHist ? T.deep : nullptr);
+            k_quadtree<QT_THREADS><<<grd, QT_THREADS, L.total, sQ>>>(P, ex->nodeCapMax, ex->maxCellsLevel, useHist ? T.deep : nullptr);
         }
         ++ex->launches;
         if (useHist) {
             const size_t smemS = (size_t)ex->nodeCapMax * sizeof(unsigned);
             if (smemS <= 48 * 1024) {
-                k_qt_attach_select<512><<<grd, 512, smemS, s>>>(P, T);
+                k_qt_attach_select<512><<<grd, 512, smemS, sQ>>>(P, T);
                 ++ex->launches;
             } else {
                 dim3 grdC(QT_CLS_BLOCKS, G.nlevels, batch);
-                k_qt_attach<<<grdC, 128, 0, s>>>(P, T);
-                k_qt_select<<<grd, 128, 0, s>>>(P, T);
+                k_qt_attach<<<grdC, 128, 0, sQ>>>(P, T);
+                k_qt_select<<<grd, 128, 0, sQ>>>(P, T);
                 ex->launches += 2;
             }
         } else {
-            CUDA_TRY(ex, cudaMemsetAsync(T.deep, 0, (size_t)batch * G.nlevels * sizeof(int), s));
+            CUDA_TRY(ex, cudaMemsetAsync(T.deep, 0, (size_t)batch * G.nlevels * sizeof(int), sQ));
         }
     }
     if (prof) CUDA_TRY(ex, cudaEventRecord(ex->ev[3], s));
     // K7
-    k_assemble<<<batch, 256, 0, s>>>(P);
+    k_assemble<<<batch, 256, 0, sQ>>>(P);
     ++ex->launches;
     if (prof) CUDA_TRY(ex, cudaEventRecord(ex->ev[4], s));
-    // K5 (serial form; see above for the overlapped one)
+    // K5
     if (aux < 0) {
         dim3 grd((unsigned)ex->h_tiles.size(), batch);
         k_blur<<<grd, dim3(64, BLUR_STRIPS), 0, s>>>(P, ex->d_tiles, blurSrcMaps, blurTmaMask);
         ++ex->launches;
     } else {
+#ifndef ORBX_BLUR_ON_AUX
+        CUDA_TRY(ex, cudaEventRecord(ex->evBlurDone[aux], sQ));       // quadtree chain + assemble done
+        dim3 grd((unsigned)ex->h_tiles.size(), batch);
+        k_blur<<<grd, dim3(64, BLUR_STRIPS), 0, s>>>(P, ex->d_tiles, blurSrcMaps, blurTmaMask);
+        ++ex->launches;
+#endif
         CUDA_TRY(ex, cudaStreamWaitEvent(s, ex->evBlurDone[aux], 0));
     }
     if (prof) CUDA_TRY(ex, cudaEventRecord(ex->ev[5], s));
@@ -3190,7 +3203,13 @@ orbx_extractor *orbx_create(int nfeatures, float scale_factor, int nlevels, int 
     CREATE_TRY(cudaEventCreateWithFlags(&ex->evFork, cudaEventDisableTiming));
     for (int i = 0; i < ORBX_MAX_SIDE; ++i) CREATE_TRY(cudaEventCreateWithFlags(&ex->evJoin[i], cudaEventDisableTiming));
     for (int i = 0; i <= ORBX_MAX_SIDE; ++i) {
+#ifdef ORBX_BLUR_ON_AUX
         CREATE_TRY(cudaStreamCreateWithFlags(&ex->sAux[i], cudaStreamNonBlocking));
+#else
+        { int least = 0, greatest = 0;                     // numerically lowest = highest priority
+          CREATE_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+          CREATE_TRY(cudaStreamCreateWithPriority(&ex->sAux[i], cudaStreamNonBlocking, greatest)); }
+#endif
         CREATE_TRY(cudaEventCreateWithFlags(&ex->evPyrDone[i], cudaEventDisableTiming));
         CREATE_TRY(cudaEventCreateWithFlags(&ex->evBlurDone[i], cudaEventDisableTiming));
     }
