@@ -684,7 +684,7 @@ struct FastRange {
 // (The ROI is staged with ordinary loads: a TMA box must start on a 16-byte boundary of the image row — measured on this B200,
 // tools/microbench/tma_probe.cu — which cell ROIs do not; the pyramid and blur tiles, whose origin is free, use TMA.)
 #ifndef FAST_GPL
-#define FAST_GPL 4     // 4-pixel groups per lane and iteration of the compass loop (measured on B200: 1 → 4.35 ms, 2 → 4.26 ms, 4 → 4.23 ms per 2048 frames)
+#define FAST_GPL 4     // rounds of 32 four-pixel groups per iteration of the compass loop (1 … 4: the per-round counts share one scan word)
 #endif
 template <int WPB, int RP>
 __global__ void __launch_bounds__(WPB * 32, 2048 / (WPB * 32 * 2)) k_fast_cells(ExParams p, const __grid_constant__ FastRange R) {   // ≤ 64 registers: 32 warps per SM
@@ -763,7 +763,7 @@ __global__ void __launch_bounds__(WPB * 32, 2048 / (WPB * 32 * 2)) k_fast_cells(
     const uint32_t rcpRp = (uint32_t)((0x100000000ull + (unsigned)rp - 1) / (unsigned)rp);   // umulhi(o, rcpRp) == o/rp
     const uint32_t lt = (1u << lane) - 1u;
     const int rp3 = 3 * rp;
-    const int stepRows = (int)(((uint32_t)(32 * FAST_GPL) * rcpG) >> 16), stepGroups = 32 * FAST_GPL - stepRows * G;   // 32·FAST_GPL groups further on
+    const int stepRows = (int)((32u * rcpG) >> 16), stepGroups = 32 - stepRows * G;          // 32 groups further on
     const int stepOff = stepRows * rp + 4 * stepGroups, wrapOff = rp - 4 * G;
     const int nValidLast = iw - 4 * (G - 1);                               // valid pixels of a row's last group (1..4)
     const uint32_t lastMask = nValidLast >= 4 ? 0x80808080u : (0x80808080u & ((1u << (8 * nValidLast)) - 1u));
@@ -778,73 +778,73 @@ __global__ void __launch_bounds__(WPB * 32, 2048 / (WPB * 32 * 2)) k_fast_cells(
         const uint32_t kT = (uint32_t)(0x8000 - t - 1) * 0x10001u;
 
         // phase 1: compass test of every 4-pixel group; every passing pixel becomes one queue entry, in row-major pixel order.
-        // A lane takes FAST_GPL consecutive groups per iteration, so one warp scan of the per-lane counts and one round of loop
-        // bookkeeping serve 4·FAST_GPL pixels.  Lane state (lg, off) of its first group gi = i0 + FAST_GPL·lane is advanced
-        // incrementally: +32·FAST_GPL groups = +stepRows rows and +stepGroups groups, with one conditional row wrap.
+        // One iteration covers FAST_GPL rounds of 32 consecutive groups (round h: group i0 + 32·h + lane, so the lanes of a load
+        // read consecutive words — no bank conflicts); the per-round counts of a lane travel as the bytes of ONE word through ONE
+        // warp scan (a round has at most 128 passing pixels, so no byte overflows), and one round of loop bookkeeping serves
+        // 128·FAST_GPL pixels.  Lane state (lg, off) of group i0 + lane advances by 32 groups per round: +stepRows rows and
+        // +stepGroups groups, with one conditional row wrap.
         int nE = 0;
         {
-            const int row0 = (int)(((uint32_t)(FAST_GPL * lane) * rcpG) >> 16);
-            int lg = FAST_GPL * lane - row0 * G;
+            const int row0 = (int)(((uint32_t)lane * rcpG) >> 16);
+            int lg = lane - row0 * G;
             int off = (row0 + 3) * rp + 4 * lg + 4;    // ROI byte of the group's first pixel
             for (int i0 = 0; i0 < nGroups; i0 += 32 * FAST_GPL) {
                 uint32_t pm[FAST_GPL], sb[FAST_GPL];         // bit 8i+7: pixel i passes / is a side-B entry (does not pass on side A)
                 int offs[FAST_GPL];
-                {
-                    int lgh = lg, offh = off;
 #pragma unroll
-                    for (int h = 0; h < FAST_GPL; ++h) {
-                        const bool lastInRow = lgh == G - 1;
-                        offs[h] = offh;
-                        pm[h] = 0; sb[h] = 0;
-                        if (i0 + FAST_GPL * lane + h < nGroups) {
-                            const uint8_t *cp = roi + offh;
-                            Row3 Cn = ld_row3(cp - 4), Tp, Bt;
-                            Tp.w1 = *reinterpret_cast<const uint32_t *>(cp - rp3);
-                            Bt.w1 = *reinterpret_cast<const uint32_t *>(cp + rp3);
-                            Tp.w0 = Tp.w2 = Bt.w0 = Bt.w2 = 0;
-                            uint32_t XA[2], XB[2];
+                for (int h = 0; h < FAST_GPL; ++h) {
+                    offs[h] = off;
+                    pm[h] = 0; sb[h] = 0;
+                    if (i0 + 32 * h + lane < nGroups) {
+                        const uint8_t *cp = roi + off;
+                        Row3 Cn = ld_row3(cp - 4), Tp, Bt;
+                        Tp.w1 = *reinterpret_cast<const uint32_t *>(cp - rp3);
+                        Bt.w1 = *reinterpret_cast<const uint32_t *>(cp + rp3);
+                        Tp.w0 = Tp.w2 = Bt.w0 = Bt.w2 = 0;
+                        uint32_t XA[2], XB[2];
 #pragma unroll
-                            for (int P = 0; P < 2; ++P) {
-                                const uint32_t v2 = P ? pair_at<6>(Cn) : pair_at<4>(Cn);
-                                const uint32_t r0 = P ? pair_at<6>(Bt) : pair_at<4>(Bt), r8 = P ? pair_at<6>(Tp) : pair_at<4>(Tp);
-                                const uint32_t r4 = P ? pair_at<9>(Cn) : pair_at<7>(Cn), r12 = P ? pair_at<3>(Cn) : pair_at<1>(Cn);
-                                const uint32_t hiMin = __vmaxu2(__vminu2(r0, r8), __vminu2(r4, r12));   // A-side bound: v - hiMin
-                                const uint32_t loMax = __vminu2(__vmaxu2(r0, r8), __vmaxu2(r4, r12));   // B-side bound: loMax - v
-                                XA[P] = (v2 + kT) - hiMin;       // bit 15 of a half ⇔ bound > t (no borrow crosses the halves)
-                                XB[P] = (loMax + kT) - v2;
-                            }
-                            const uint32_t colMask = lastInRow ? lastMask : 0x80808080u;
-                            const uint32_t pA = __byte_perm(XA[0], XA[1], 0x7531u);       // high bytes of the four halves: px0..px3
-                            const uint32_t pB = __byte_perm(XB[0], XB[1], 0x7531u);
-                            pm[h] = (pA | pB) & colMask;
-                            sb[h] = pm[h] & ~pA;
+                        for (int P = 0; P < 2; ++P) {
+                            const uint32_t v2 = P ? pair_at<6>(Cn) : pair_at<4>(Cn);
+                            const uint32_t r0 = P ? pair_at<6>(Bt) : pair_at<4>(Bt), r8 = P ? pair_at<6>(Tp) : pair_at<4>(Tp);
+                            const uint32_t r4 = P ? pair_at<9>(Cn) : pair_at<7>(Cn), r12 = P ? pair_at<3>(Cn) : pair_at<1>(Cn);
+                            const uint32_t hiMin = __vmaxu2(__vminu2(r0, r8), __vminu2(r4, r12));   // A-side bound: v - hiMin
+                            const uint32_t loMax = __vminu2(__vmaxu2(r0, r8), __vmaxu2(r4, r12));   // B-side bound: loMax - v
+                            XA[P] = (v2 + kT) - hiMin;       // bit 15 of a half ⇔ bound > t (no borrow crosses the halves)
+                            XB[P] = (loMax + kT) - v2;
                         }
-                        offh += lastInRow ? wrapOff + 4 : 4;      // the lane's next group: one to the right, or the first of the next row
-                        lgh = lastInRow ? 0 : lgh + 1;
+                        const uint32_t colMask = lg == G - 1 ? lastMask : 0x80808080u;
+                        const uint32_t pA = __byte_perm(XA[0], XA[1], 0x7531u);       // high bytes of the four halves: px0..px3
+                        const uint32_t pB = __byte_perm(XB[0], XB[1], 0x7531u);
+                        pm[h] = (pA | pB) & colMask;
+                        sb[h] = pm[h] & ~pA;
                     }
+                    lg += stepGroups; off += stepOff;        // 32 groups further on
+                    if (lg >= G) { lg -= G; off += wrapOff; }
                 }
                 uint32_t anyPm = pm[0];
 #pragma unroll
                 for (int h = 1; h < FAST_GPL; ++h) anyPm |= pm[h];
                 if (__any_sync(0xffffffffu, anyPm != 0)) {
-                    int cnt = 0;
+                    uint32_t cnts = 0;                       // byte h: this lane's passing pixels of round h
 #pragma unroll
-                    for (int h = 0; h < FAST_GPL; ++h) cnt += __popc(pm[h]);
-                    const int incl = warp_inclusive_sum(cnt);
-                    const int nNew = __shfl_sync(0xffffffffu, incl, 31);
+                    for (int h = 0; h < FAST_GPL; ++h) cnts |= (uint32_t)__popc(pm[h]) << (8 * h);
+                    const uint32_t incl = (uint32_t)warp_inclusive_sum((int)cnts);
+                    const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+                    const int nNew = __dp4a(tot, 0x01010101u, 0u);
                     if (nE + nNew > L.qCap) { dense = true; break; }      // warp-uniform: more corners than the queue holds
-                    uint16_t *qa = queue + (nE + incl - cnt);
+                    const uint32_t excl = incl - cnts;
+                    int base = nE;
 #pragma unroll
                     for (int h = 0; h < FAST_GPL; ++h) {
+                        uint16_t *qa = queue + (base + (int)((excl >> (8 * h)) & 0xffu));
                         if (pm[h] & 0x80u) *qa++ = (uint16_t)((uint32_t)offs[h] | ((sb[h] << 8) & 0x8000u));
                         if (pm[h] & 0x8000u) *qa++ = (uint16_t)((uint32_t)(offs[h] + 1) | (sb[h] & 0x8000u));
                         if (pm[h] & 0x800000u) *qa++ = (uint16_t)((uint32_t)(offs[h] + 2) | ((sb[h] >> 8) & 0x8000u));
                         if (pm[h] & 0x80000000u) *qa++ = (uint16_t)((uint32_t)(offs[h] + 3) | ((sb[h] >> 16) & 0x8000u));
+                        base += (int)((tot >> (8 * h)) & 0xffu);
                     }
                     nE += nNew;
                 }
-                lg += stepGroups; off += stepOff;
-                if (lg >= G) { lg -= G; off += wrapOff; }
             }
         }
         if (dense) break;
