@@ -138,3 +138,30 @@ def test_synth_frames_are_deterministic():
     assert not np.array_equal(a, synth.throughput_frame(6))
     q, db = synth.knn_case(50, 1000, seed=3)
     assert q.shape == (50, 32) and db.shape == (1000, 32)
+
+
+def test_reference_arm_prints_the_contract_line_with_the_product_arms_config():
+    """`bench.py --impl reference` (the reference's own CPU path on the host cores): one JSON line, `impl: reference`, the SAME
+    `config` object the product arm prints for this workload (the driver compares them), a `cpu_baseline` describing the run and
+    an `e2e` with no transfers.  No GPU involved."""
+    import json
+    import subprocess
+    import sys
+    import types
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "orb_frames_per_s" and line["unit"] == "frames/s"
+    assert line["higher_is_better"] is True and line["dtype"] == "u8" and line["value"] > 0
+    assert line["e2e"] == {"value": line["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["gpu_launches"] == 0
+    sys.path.insert(0, root)
+    import bench
+    default_batch = bench.set_workload("tum1")
+    assert line["config"] == bench.bench_config(types.SimpleNamespace(workload="tum1"), 1, default_batch)
