@@ -4,7 +4,7 @@
 The reference ships no fixtures for this path, so the vectors are produced here from the
 REAL OpenCV primitives of the container's cv2 wheel driven by the reference's orchestration as restated
 in oracle/cv2_oracle.py (which needs only libstdc++'s std::sort from the C++ oracle for the quadtree's
-tie order).  Run in the build container:  python tools/gen_golden.py
+tie order).  Run in the build container:  python tools/gen_golden.py [case ...]
 Each .npz holds, for one seeded synthetic frame: the frame parameters, SHA-256 digests of every pyramid
 level (padded), blurred level, per-level candidate and selected lists, and the final keypoints (28-byte
 records) + descriptors in full.  Matching cases hold cv2.BFMatcher(NORM_HAMMING).knnMatch(k=2) results.
@@ -30,6 +30,7 @@ CASES = [
     ("kitti_s1", "throughput", 1, 1241, 376, 2000, [], (0, 0)),
     ("euroc_lap_s2", "throughput", 2, 752, 480, 1200, [], (200, 500)),
     ("small_s9", "parity", 9, 320, 240, 500, [], (0, 0)),
+    ("uhd_s4", "throughput", 4, 3840, 2160, 8000, [], (0, 0)),        # BASELINE config 5 at full size
 ]
 
 
@@ -45,7 +46,10 @@ def main():
     import cv2
     os.makedirs(OUT, exist_ok=True)
     L = oracle.lib()
+    only = set(sys.argv[1:])                      # optional: regenerate just the named cases
     for name, kind, seed, W, H, nf, rects, lap in CASES:
+        if only and name not in only:
+            continue
         img = frame_for(kind, seed, W, H)
         taps = {}
         kps, desc, mono = cv2_oracle.extract(L, img, nf, 1.2, 8, 20, 7, rects=rects, lap=lap, taps=taps)
@@ -64,6 +68,8 @@ def main():
         d.update(pyr_sha=np.array(pyr), blur_sha=np.array(blur), cand_sha=np.array(cand), sel_sha=np.array(sel))
         np.savez_compressed(os.path.join(OUT, f"extract_{name}.npz"), **d)
         print(name, len(kps), mono)
+    if only and "knn" not in only:
+        return
     # matching: real cv2 BFMatcher on a planted/tie-heavy case
     q, db = synth.knn_case(300, 20000, seed=1234, planted_frac=0.1)
     bf = cv2.BFMatcher(cv2.NORM_HAMMING)
