@@ -509,6 +509,86 @@ __global__ void __launch_bounds__(32) k_sbp_replay(int m, const uint8_t *__restr
     }
     if (lane == 0) *nMatchesOut = nmatches;
 }
+// ---- ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (src/ORBmatcher.cc:222-425), frames with Nleft == -1 ----
+// The host has already merged the two feature vectors: query j is keyframe feature qKF[j] (in the walk's order: common nodes
+// ascending, then the node's stored order; features without a good map point left out) and its candidates are fIdx[qC0[j] .. qC1[j])
+// — the frame's features of the same vocabulary node.  ONE warp replays the queries in order because a frame feature that received
+// a map point is skipped by every later query (:281-282); per query the lanes share the candidate scan (occupancy test, Hamming
+// distance) and shuffle-reduce the two smallest (distance, list position) keys = the scalar loop's strict-'<' best / second best.
+// Then TH_LOW and the fp32 ratio test (:331-333), the rotation histogram (:346-353) and, at the end, the purge of the matches
+// outside the three fullest bins (:404-422).
+__global__ void __launch_bounds__(32) k_search_by_bow(const uint4 *__restrict__ kfDesc, const float *__restrict__ kfAng,
+                                                      const uint4 *__restrict__ fDesc, const float *__restrict__ fAng, int nF,
+                                                      const int32_t *__restrict__ qKF, const int32_t *__restrict__ qC0,
+                                                      const int32_t *__restrict__ qC1, int nQ, const int32_t *__restrict__ fIdx,
+                                                      float nnratio, int checkOri, int32_t *assigned, int8_t *binOf, int32_t *nMatchesOut) {
+    const int lane = threadIdx.x;
+    __shared__ int hist[30];
+    __shared__ int sel[3];
+    for (int i = lane; i < 30; i += 32) hist[i] = 0;
+    for (int i = lane; i < nF; i += 32) { assigned[i] = -1; binOf[i] = -1; }
+    __syncwarp();
+    const unsigned long long NONE = ~0ull;
+    int nmatches = 0;
+    for (int j = 0; j < nQ; ++j) {
+        const int kf = qKF[j], c0 = qC0[j], c1 = qC1[j];
+        const uint4 qa = kfDesc[2 * (long long)kf], qb = kfDesc[2 * (long long)kf + 1];
+        unsigned long long a = NONE, b = NONE;
+        for (int c = c0 + lane; c < c1; c += 32) {
+            const int t = fIdx[c];
+            if (assigned[t] >= 0) continue;                                   // :281-282
+            const int d = ham256(qa, qb, fDesc[2 * (long long)t], fDesc[2 * (long long)t + 1]);
+            if (d < 256) top2_insert(((unsigned long long)(unsigned)d << 32) | (unsigned)(c - c0), a, b);
+        }
+        warp_top2(a, b);
+        if (a == NONE) continue;
+        const int best = (int)(a >> 32), best2 = b == NONE ? 256 : (int)(b >> 32);
+        if (best <= 50 && (float)best < __fmul_rn(nnratio, (float)best2)) {   // TH_LOW, fp32 ratio
+            const int bestIdx = fIdx[c0 + (int)(a & 0xffffffffu)];
+            __syncwarp();
+            if (lane == 0) {
+                assigned[bestIdx] = kf;
+                if (checkOri) {
+                    float rot = __fsub_rn(kfAng[kf], fAng[bestIdx]);
+                    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                    int bin = (int)roundf(__fmul_rn(rot, 1.0f / 30));
+                    if (bin == 30) bin = 0;
+                    bin = min(max(bin, 0), 29);
+                    binOf[bestIdx] = (int8_t)bin;
+                    ++hist[bin];
+                }
+            }
+            __syncwarp();
+            ++nmatches;
+        }
+    }
+    if (checkOri) {
+        __syncwarp();
+        if (lane == 0) {  // ComputeThreeMaxima (:2008-2049)
+            int m1 = 0, m2 = 0, m3 = 0, i1 = -1, i2 = -1, i3 = -1;
+            for (int i = 0; i < 30; ++i) {
+                const int sz = hist[i];
+                if (sz > m1) { m3 = m2; m2 = m1; m1 = sz; i3 = i2; i2 = i1; i1 = i; }
+                else if (sz > m2) { m3 = m2; m2 = sz; i3 = i2; i2 = i; }
+                else if (sz > m3) { m3 = sz; i3 = i; }
+            }
+            if ((float)m2 < __fmul_rn(0.1f, (float)m1)) { i2 = -1; i3 = -1; }
+            else if ((float)m3 < __fmul_rn(0.1f, (float)m1)) { i3 = -1; }
+            sel[0] = i1; sel[1] = i2; sel[2] = i3;
+        }
+        __syncwarp();
+        int removed = 0;
+        for (int i = lane; i < nF; i += 32) {
+            if (assigned[i] < 0) continue;
+            const int bin = binOf[i];
+            if (bin != sel[0] && bin != sel[1] && bin != sel[2]) { assigned[i] = -1; ++removed; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
+        nmatches -= removed;
+    }
+    if (lane == 0) *nMatchesOut = nmatches;
+}
 // vbPrevMatched update of SearchForInitialization (src/ORBmatcher.cc:754-756)
 __global__ void k_update_prev(const int32_t *m12, int n1, const float2 *xy2, float2 *prev) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1218,6 +1298,75 @@ int orbx_search_by_projection(orbx_matcher *m, const orbx_keypoint *keypoints_un
         MCUDA_TRY(m, cudaMemcpyAsync(n_matches, dn, 4, cudaMemcpyDeviceToHost, s));
         MCUDA_TRY(m, cudaStreamSynchronize(s));
     }
+    return ORBX_OK;
+}
+
+int orbx_search_by_bow(orbx_matcher *m, const uint8_t *kf_desc, const float *kf_angle, int n_kf, const uint8_t *kf_mp, const int32_t *kf_nodes,
+                       const int32_t *kf_off, const int32_t *kf_idx, int kf_nn, const uint8_t *f_desc, const float *f_angle, int n_f,
+                       const int32_t *f_nodes, const int32_t *f_off, const int32_t *f_idx, int f_nn, float nnratio, int check_orientation,
+                       int32_t *assigned, int32_t *n_matches) {
+    if (!m) return ORBX_ERR_ARG;
+    if (n_kf < 0 || n_f < 0 || kf_nn < 0 || f_nn < 0 || !n_matches || (n_f > 0 && (!f_desc || !f_angle || !assigned)) ||
+        (n_kf > 0 && (!kf_desc || !kf_angle || !kf_mp)) || (kf_nn > 0 && (!kf_nodes || !kf_off || !kf_idx)) ||
+        (f_nn > 0 && (!f_nodes || !f_off || !f_idx))) {
+        m->err = "orbx_search_by_bow: bad argument";
+        return ORBX_ERR_ARG;
+    }
+    *n_matches = 0;
+    for (int i = 0; i < n_f; ++i) assigned[i] = -1;
+    if (n_kf == 0 || n_f == 0 || kf_nn == 0 || f_nn == 0) return ORBX_OK;
+    // the merge walk over the two node-sorted feature vectors (:243-402; lower_bound = skipping ahead), on the host: it only
+    // touches node ids.  Queries = keyframe features with a good map point (:256-260), candidates = the frame's list of that node.
+    std::vector<int32_t> qKF, qC0, qC1;
+    const int nIdxF = f_off[f_nn];
+    for (int a = 0, b = 0; a < kf_nn && b < f_nn;) {
+        if (kf_nodes[a] == f_nodes[b]) {
+            for (int i = kf_off[a]; i < kf_off[a + 1]; ++i) {
+                const int kf = kf_idx[i];
+                if (kf < 0 || kf >= n_kf) { m->err = "orbx_search_by_bow: keyframe feature index out of range"; return ORBX_ERR_ARG; }
+                if (kf_mp[kf] != 1) continue;
+                qKF.push_back(kf); qC0.push_back(f_off[b]); qC1.push_back(f_off[b + 1]);
+            }
+            ++a; ++b;
+        } else if (kf_nodes[a] < f_nodes[b]) {
+            ++a;
+        } else {
+            ++b;
+        }
+    }
+    for (int i = 0; i < nIdxF; ++i)
+        if (f_idx[i] < 0 || f_idx[i] >= n_f) { m->err = "orbx_search_by_bow: frame feature index out of range"; return ORBX_ERR_ARG; }
+    const int nQ = (int)qKF.size();
+    if (nQ == 0 || nIdxF == 0) return ORBX_OK;
+    OrbxDeviceGuard dg_(m->device); MCUDA_TRY(m, dg_.status);
+    int rc = stage(m, al256((size_t)n_kf * 32 + 32) + al256((size_t)n_kf * 4) + al256((size_t)n_f * 32 + 32) + 2 * al256((size_t)n_f * 4) + al256(n_f) +
+                          3 * al256((size_t)nQ * 4) + al256((size_t)nIdxF * 4) + 512);
+    if (rc) return rc;
+    Carver cv{m->d_buf};
+    uint8_t *dkd = cv.take<uint8_t>((size_t)n_kf * 32 + 32);
+    float *dka = cv.take<float>(n_kf);
+    uint8_t *dfd = cv.take<uint8_t>((size_t)n_f * 32 + 32);
+    float *dfa = cv.take<float>(n_f);
+    int32_t *dasg = cv.take<int32_t>(n_f);
+    int8_t *dbin = cv.take<int8_t>(n_f);
+    int32_t *dqKF = cv.take<int32_t>(nQ), *dqC0 = cv.take<int32_t>(nQ), *dqC1 = cv.take<int32_t>(nQ);
+    int32_t *dfi = cv.take<int32_t>(nIdxF);
+    int32_t *dn = cv.take<int32_t>(1);
+    cudaStream_t s = m->stream;
+    MCUDA_TRY(m, cudaMemcpyAsync(dkd, kf_desc, (size_t)n_kf * 32, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(dka, kf_angle, (size_t)n_kf * 4, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(dfd, f_desc, (size_t)n_f * 32, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(dfa, f_angle, (size_t)n_f * 4, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(dqKF, qKF.data(), (size_t)nQ * 4, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(dqC0, qC0.data(), (size_t)nQ * 4, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(dqC1, qC1.data(), (size_t)nQ * 4, cudaMemcpyHostToDevice, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(dfi, f_idx, (size_t)nIdxF * 4, cudaMemcpyHostToDevice, s));
+    k_search_by_bow<<<1, 32, 0, s>>>((const uint4 *)dkd, dka, (const uint4 *)dfd, dfa, n_f, dqKF, dqC0, dqC1, nQ, dfi, nnratio, check_orientation ? 1 : 0,
+                                     dasg, dbin, dn);
+    MCUDA_TRY(m, cudaGetLastError());
+    MCUDA_TRY(m, cudaMemcpyAsync(assigned, dasg, (size_t)n_f * 4, cudaMemcpyDeviceToHost, s));
+    MCUDA_TRY(m, cudaMemcpyAsync(n_matches, dn, 4, cudaMemcpyDeviceToHost, s));
+    MCUDA_TRY(m, cudaStreamSynchronize(s));
     return ORBX_OK;
 }
 

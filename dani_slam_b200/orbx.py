@@ -100,6 +100,7 @@ def lib() -> C.CDLL:
     L.orbx_ratio_test_device.argtypes = [vp, vp, i32, f64, vp]
     L.orbx_hamming_top2_lists.argtypes = [vp, vp, i32, vp, i64, vp, vp, vp, vp, vp, vp]
     L.orbx_search_by_projection.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, f32, f32, i32, f32, vp, vp]
+    L.orbx_search_by_bow.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, i32, f32, i32, vp, vp]
     L.orbx_search_for_initialization_frames.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, vp, i32, f32, i32, vp, vp]
     L.orbx_rot_hist_filter.argtypes = [vp, vp, vp, i32, vp]
     L.orbx_features_in_area.argtypes = [vp, vp, vp, i32, f32, f32, f32, f32, vp, i32, i32, i32, vp, vp, i32, vp]
@@ -395,6 +396,23 @@ class ORBmatcher:
         self._chk(self.L.orbx_search_by_projection(self.h, _p(kps), _p(desc), len(kps), _p(ur), _p(ko), _p(b), _p(sf), len(sf), _p(p5), _p(lv), _p(fl),
                                                    _p(ob), _p(md), len(p5), float(self.mfNNratio), float(th), int(bFarPoints), float(thFarPoints),
                                                    _p(out), C.byref(n)))
+        return n.value, out
+
+    def SearchByBoW(self, KF, F):
+        """`ORBmatcher::SearchByBoW(KeyFrame *pKF, Frame &F, vector<MapPoint*> &vpMapPointMatches)` (src/ORBmatcher.cc:222-425,
+        Nleft == -1 frames).  KF is a dict with `mDescriptors`, `angles` (mvKeysUn[i].angle), `map_points` (0 = null, 1 = good,
+        2 = isBad()) and `mFeatVec` = (nodes, off, idx) CSR over ascending node ids; F a dict with `mDescriptors`, `angles`
+        (mvKeys[i].angle) and `mFeatVec`.  → (nmatches, assigned[n_f]): the keyframe feature whose map point each frame feature got."""
+        kd = np.ascontiguousarray(KF["mDescriptors"], np.uint8).reshape(-1, 32); ka = np.ascontiguousarray(KF["angles"], np.float32)
+        km = np.ascontiguousarray(KF["map_points"], np.uint8)
+        fd = np.ascontiguousarray(F["mDescriptors"], np.uint8).reshape(-1, 32); fa = np.ascontiguousarray(F["angles"], np.float32)
+        kn, ko, ki = (np.ascontiguousarray(v, np.int32) for v in KF["mFeatVec"])
+        fn, fo, fi = (np.ascontiguousarray(v, np.int32) for v in F["mFeatVec"])
+        assert len(ka) == len(km) == len(kd) and len(fa) == len(fd) and len(ko) == len(kn) + 1 and len(fo) == len(fn) + 1
+        out = np.full(len(fd), -1, np.int32)
+        n = C.c_int32(0)
+        self._chk(self.L.orbx_search_by_bow(self.h, _p(kd), _p(ka), len(kd), _p(km), _p(kn), _p(ko), _p(ki), len(kn), _p(fd), _p(fa), len(fd),
+                                            _p(fn), _p(fo), _p(fi), len(fn), float(self.mfNNratio), int(self.mbCheckOrientation), _p(out), C.byref(n)))
         return n.value, out
 
     def SearchForInitializationFrames(self, kps1, desc1, kps2, desc2, bounds, vbPrevMatched, windowSize=10):

@@ -274,3 +274,40 @@ def projection_scene(n: int, m: int, seed: int, width: float = 640.0, height: fl
         if n:
             p5[:, 2] = u_right[src] + rng.choice([0.0, 1.0, 6.0, 30.0], m)
     return dict(kps=k, desc=d, scale_factors=sf, mp_proj5=p5, mp_level=lvl, mp_flags=flags, mp_obs=obs, mp_desc=md, kp_obs=kp_obs, u_right=u_right)
+
+
+def bow_scene(n_kf: int, n_f: int, seed: int, n_nodes: int = 40, max_flips: int = 60):
+    """A keyframe and a frame for SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&): frame features are noisy copies of keyframe
+    features (same vocabulary node most of the time), several keyframe features compete for one frame feature (the ordered walk
+    decides), identical descriptors sit next to each other (ties), some keyframe features hold no or a bad map point, a few nodes
+    exist on one side only (the lower_bound jumps), rotations cluster in a few histogram bins.
+    Returns dict(kf_kps, kf_desc, kf_mp, kf_fv, f_kps, f_desc, f_fv) with fv = (nodes, off, idx) CSR over ascending node ids."""
+    rng = np.random.default_rng(seed)
+    kk = keypoint_records(n_kf, seed * 11 + 1)
+    kd = rng.integers(0, 256, (n_kf, 32), dtype=np.uint8)
+    fk = keypoint_records(n_f, seed * 11 + 2)
+    fd = rng.integers(0, 256, (n_f, 32), dtype=np.uint8)
+    kf_node = rng.integers(0, n_nodes, n_kf) * 3 + 5                      # node ids are sparse
+    f_node = rng.integers(0, n_nodes + 4, n_f) * 3 + 5                    # a few nodes only the frame has
+    if n_kf and n_f:
+        src = rng.integers(0, n_kf, n_f)
+        copy = rng.random(n_f) < 0.75
+        fd[copy] = _flip_bits(kd[src[copy]], rng, max_flips)
+        f_node[copy] = np.where(rng.random(copy.sum()) < 0.9, kf_node[src[copy]], f_node[copy])
+        fk["angle"][copy] = ((kk["angle"][src[copy]] - rng.choice([0.0, 3.0, 14.99, 15.0, 45.0, 180.0], copy.sum(), p=[.5, .2, .05, .05, .1, .1])) % 360).astype(np.float32)
+        if n_f > 8:                                                        # exact duplicates in one node: first in list order wins
+            fd[1] = fd[0]; f_node[1] = f_node[0]
+        if n_kf > 8:                                                       # two keyframe features with the same descriptor compete
+            kd[1] = kd[0]; kf_node[1] = kf_node[0]
+    kf_mp = rng.choice([0, 1, 1, 1, 1, 1, 2], n_kf).astype(np.uint8)
+
+    def csr(node, n):
+        order = rng.permutation(n)                                         # stored order inside a node is not sorted by index
+        nodes = np.unique(node) if n else np.zeros(0, np.int64)
+        off = [0]; idx = []
+        for v in nodes:
+            members = [int(i) for i in order if node[i] == v]
+            idx += members; off.append(len(idx))
+        return nodes.astype(np.int32), np.asarray(off, np.int32), np.asarray(idx, np.int32)
+
+    return dict(kf_kps=kk, kf_desc=kd, kf_mp=kf_mp, kf_fv=csr(kf_node, n_kf), f_kps=fk, f_desc=fd, f_fv=csr(f_node, n_f))

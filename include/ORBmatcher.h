@@ -8,13 +8,14 @@
  *   ORBmatcher(nnratio, checkOri)                                   src/ORBmatcher.cc:39-41
  *   static DescriptorDistance(const cv::Mat&, const cv::Mat&)       src/ORBmatcher.cc:2054-2070   (host popcount, no launch)
  *   SearchByProjection(Frame&, const vector<MapPoint*>&, th, …)     src/ORBmatcher.cc:43-213      → orbx_search_by_projection
+ *   SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)              src/ORBmatcher.cc:222-425     → orbx_search_by_bow
  *   SearchForInitialization(Frame&, Frame&, …, windowSize)          src/ORBmatcher.cc:644-759     → orbx_search_for_initialization_frames
  *   TH_LOW / TH_HIGH / HISTO_LENGTH                                 src/ORBmatcher.cc:35-37
  *
- * The other members (SearchByBoW, SearchForTriangulation, SearchBySim3, Fuse and the three remaining
+ * The other members (SearchByBoW between two keyframes, SearchForTriangulation, SearchBySim3, Fuse and the three remaining
  * SearchByProjection overloads) are projection geometry over KeyFrame / MapPoint pointers and stay in the
  * reference's own src/ORBmatcher.cc (out of scope); they are only DECLARED here, exactly as in the
- * reference, and their inner loops call the DescriptorDistance above.  INTEGRATION.md shows the three ranges of
+ * reference, and their inner loops call the DescriptorDistance above.  INTEGRATION.md shows the four ranges of
  * src/ORBmatcher.cc a maintainer fences off (`#ifndef ORBX_DROPIN`) so that each function has one definition.
  *
  * Matchers are stack objects constructed per call in the reference (src/Tracking.cc:2511,2747 …), so the
@@ -131,13 +132,49 @@ public:
         return nmatches;
     }
 
+#if !defined(ORBX_MATCHER_HOT_PATH_ONLY) || defined(ORBX_SHIM_FRAME_H)   // needs the complete KeyFrame type (KeyFrame.h, or the test stand-in)
+    // Search matches between MapPoints in a KeyFrame and ORB in a Frame.
+    // Brute force constrained to ORB that belong to the same vocabulary node (at a certain level)
+    // Used in Relocalisation and Loop Detection
+    int SearchByBoW(KeyFrame *pKF, Frame &F, std::vector<MapPoint*> &vpMapPointMatches)
+    {
+        if(F.Nleft != -1 || pKF->mpCamera2)
+            throw std::runtime_error("ORBmatcher::SearchByBoW: two-camera frames (Nleft != -1) are not on the device path");
+        const std::vector<MapPoint*> vpMapPointsKF = pKF->GetMapPointMatches();
+        const int nKF = (int)vpMapPointsKF.size(), nF = F.N;
+        vpMapPointMatches = std::vector<MapPoint*>(nF, static_cast<MapPoint*>(NULL));      // :226
+        if(nKF == 0 || nF == 0) return 0;
+        std::vector<unsigned char> mp(nKF);
+        std::vector<float> angKF(nKF), angF(nF);
+        for(int i=0; i<nKF; i++)
+        {
+            MapPoint* pMP = vpMapPointsKF[i];
+            mp[i] = !pMP ? 0 : (pMP->isBad() ? 2 : 1);                                     // :256-260
+            angKF[i] = pKF->mvKeysUn[i].angle;                                              // :338
+        }
+        for(int i=0; i<nF; i++) angF[i] = F.mvKeys[i].angle;                                // :345
+        std::vector<int> kn, ko(1, 0), ki, fn, fo(1, 0), fi;
+        Flatten(pKF->mFeatVec, kn, ko, ki);
+        Flatten(F.mFeatVec, fn, fo, fi);
+        std::vector<unsigned char> rowsKF, rowsF;
+        std::vector<int> assigned(nF, -1);
+        int nmatches = 0;
+        Check(orbx_search_by_bow(Ctx(), Rows(pKF->mDescriptors, nKF, rowsKF), angKF.data(), nKF, mp.data(), kn.data(), ko.data(), ki.data(), (int)kn.size(),
+                                 Rows(F.mDescriptors, nF, rowsF), angF.data(), nF, fn.data(), fo.data(), fi.data(), (int)fn.size(), mfNNratio,
+                                 mbCheckOrientation ? 1 : 0, assigned.data(), &nmatches),
+              "SearchByBoW");
+        for(int i=0; i<nF; i++)
+            if(assigned[i] >= 0) vpMapPointMatches[i] = vpMapPointsKF[assigned[i]];        // :335
+        return nmatches;
+    }
+#endif
+
 #ifndef ORBX_MATCHER_HOT_PATH_ONLY
     // ---- out of scope: declared exactly as in the reference, defined by the reference's src/ORBmatcher.cc ----
     int SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono);
     int SearchByProjection(Frame &CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*> &sAlreadyFound, const float th, const int ORBdist);
     int SearchByProjection(KeyFrame* pKF, Sophus::Sim3<float> &Scw, const std::vector<MapPoint*> &vpPoints, std::vector<MapPoint*> &vpMatched, int th, float ratioHamming=1.0);
     int SearchByProjection(KeyFrame* pKF, Sophus::Sim3<float> &Scw, const std::vector<MapPoint*> &vpPoints, const std::vector<KeyFrame*> &vpPointsKFs, std::vector<MapPoint*> &vpMatched, std::vector<KeyFrame*> &vpMatchedKF, int th, float ratioHamming=1.0);
-    int SearchByBoW(KeyFrame *pKF, Frame &F, std::vector<MapPoint*> &vpMapPointMatches);
     int SearchByBoW(KeyFrame *pKF1, KeyFrame* pKF2, std::vector<MapPoint*> &vpMatches12);
     int SearchForTriangulation(KeyFrame *pKF1, KeyFrame* pKF2,
                                std::vector<std::pair<size_t, size_t> > &vMatchedPairs, const bool bOnlyStereo, const bool bCoarse = false);
@@ -186,6 +223,17 @@ private:
     static void Check(int rc, const char* what)
     {
         if(rc != ORBX_OK) throw std::runtime_error(std::string("ORBmatcher::") + what + ": " + orbx_matcher_last_error(CtxNoThrow()));
+    }
+    // DBoW2::FeatureVector (a std::map<NodeId, std::vector<unsigned int>>) as CSR: ascending node ids, offsets, feature indices
+    template <class FV>
+    static void Flatten(const FV &fv, std::vector<int> &nodes, std::vector<int> &off, std::vector<int> &idx)
+    {
+        for(typename FV::const_iterator it = fv.begin(); it != fv.end(); ++it)
+        {
+            nodes.push_back((int)it->first);
+            idx.insert(idx.end(), it->second.begin(), it->second.end());
+            off.push_back((int)idx.size());
+        }
     }
     // n descriptor rows of 32 bytes as one contiguous block (mDescriptors is continuous in the reference; copy if a view is not)
     static const unsigned char* Rows(const cv::Mat &D, int n, std::vector<unsigned char> &scratch)

@@ -196,6 +196,20 @@ int orbx_search_by_projection(orbx_matcher *m, const orbx_keypoint *keypoints_un
                               const int32_t *kp_obs, const float *bounds4, const float *scale_factors, int n_levels, const float *mp_proj5,
                               const int32_t *mp_level, const uint8_t *mp_flags, const int32_t *mp_obs, const uint8_t *mp_desc, int n_mp,
                               float nnratio, float th, int far_points, float th_far, int32_t *assigned, int32_t *n_matches);
+/* ORBmatcher::SearchByBoW(KeyFrame *pKF, Frame &F, vector<MapPoint*> &vpMapPointMatches) (src/ORBmatcher.cc:222-425), frames with
+ * Nleft == -1, whole function: the walk over the vocabulary nodes both feature vectors share, per keyframe feature with a good map
+ * point the best / second-best scan over the frame's features of the same node that hold no match yet (ordered: an earlier match
+ * removes its frame feature from every later scan, :281-282), TH_LOW, the fp32 ratio test, and the rotation-histogram purge.
+ *   keyframe:  kf_desc n_kf×32 = pKF->mDescriptors, kf_angle = pKF->mvKeysUn[i].angle, kf_mp[i] = 0: GetMapPointMatches()[i] is null,
+ *              1: a good map point, 2: isBad(); feature vector pKF->mFeatVec as CSR: kf_nodes[kf_nn] ascending node ids, kf_off[kf_nn+1],
+ *              kf_idx[] the feature indices of each node in their stored order
+ *   frame:     f_desc n_f×32 = F.mDescriptors, f_angle = F.mvKeys[i].angle, F.mFeatVec as CSR (f_nodes, f_off, f_idx)
+ *   out:       assigned[i] = keyframe feature whose map point the call leaves in vpMapPointMatches[i], or -1; *n_matches = return value
+ * HOST buffers. */
+int orbx_search_by_bow(orbx_matcher *m, const uint8_t *kf_desc, const float *kf_angle, int n_kf, const uint8_t *kf_mp, const int32_t *kf_nodes,
+                       const int32_t *kf_off, const int32_t *kf_idx, int kf_nn, const uint8_t *f_desc, const float *f_angle, int n_f,
+                       const int32_t *f_nodes, const int32_t *f_off, const int32_t *f_idx, int f_nn, float nnratio, int check_orientation,
+                       int32_t *assigned, int32_t *n_matches);
 /* Rotation-consistency filter: bin = round((a-b [+360]) / 30) (quirk Q10), keep matches in the three
  * fullest bins subject to the 0.1·max rule.  HOST / DEVICE buffers; n matches. */
 int orbx_rot_hist_filter(orbx_matcher *m, const float *angle_a, const float *angle_b, int n, uint8_t *keep);

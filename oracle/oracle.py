@@ -65,6 +65,8 @@ def lib() -> C.CDLL:
         L.orc_top2_lists.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
         L.orc_search_by_projection.restype = i32
         L.orc_search_by_projection.argtypes = [vp, vp, vp, i32, vp, vp, f32, f32, f32, f32, vp, vp, vp, vp, vp, vp, i32, f32, f32, i32, f32, vp]
+        L.orc_search_by_bow.restype = i32
+        L.orc_search_by_bow.argtypes = [vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, i32, f32, i32, vp]
         L.orc_three_maxima.argtypes = [vp, i32, vp]
         L.orc_rot_hist_filter.argtypes = [vp, vp, i32, vp]
         L.orc_features_in_area.restype = i32
@@ -227,6 +229,19 @@ def search_by_projection(xy, octave, desc, bounds, scale_factors, mp_proj5, mp_l
     n = lib().orc_search_by_projection(_p(xy), _p(octave), _p(desc), len(xy), None if ur is None else _p(ur), None if ko is None else _p(ko),
                                        *[float(b) for b in bounds], _p(sf), _p(p5), _p(lv), _p(fl), _p(ob), _p(md), len(p5), float(nnratio),
                                        float(th), int(far_points), float(th_far), _p(out))
+    return n, out
+
+
+def search_by_bow(kf_desc, kf_angle, kf_mp, kf_fv, f_desc, f_angle, f_fv, nnratio=0.7, check_ori=True):
+    """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&), Nleft == -1; fv = (nodes, off, idx) CSR.
+    Returns (nmatches, assigned[n_f]) — assigned[i] = keyframe feature whose map point the frame feature received, or -1."""
+    kd = np.ascontiguousarray(kf_desc, np.uint8); ka = np.ascontiguousarray(kf_angle, np.float32); km = np.ascontiguousarray(kf_mp, np.uint8)
+    fd = np.ascontiguousarray(f_desc, np.uint8); fa = np.ascontiguousarray(f_angle, np.float32)
+    kn, ko, ki = (np.ascontiguousarray(v, np.int32) for v in kf_fv)
+    fn, fo, fi = (np.ascontiguousarray(v, np.int32) for v in f_fv)
+    out = np.zeros(len(fd), np.int32)
+    n = lib().orc_search_by_bow(_p(kd), _p(ka), len(kd), _p(km), _p(kn), _p(ko), _p(ki), len(kn), _p(fd), _p(fa), len(fd), _p(fn), _p(fo), _p(fi),
+                                len(fn), float(nnratio), int(check_ori), _p(out))
     return n, out
 
 

@@ -921,6 +921,57 @@ int orc_search_by_projection(const float *xy, const int32_t *octave, const uint8
     return nmatches;
 }
 
+// ---- ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (src/ORBmatcher.cc:222-425), frames with Nleft == -1 ----
+// Both feature vectors as CSR over ascending vocabulary node ids (DBoW2::FeatureVector is a std::map): nodes[nn], off[nn+1], idx[].
+// kf_mp[i]: 0 = keyframe feature i holds no map point, 1 = a good one, 2 = a bad one.  The walk is ordered: a frame feature that
+// already received a map point is skipped by every later keyframe feature (:281-282).  assigned[i] = keyframe feature whose map
+// point was written to vpMapPointMatches[i], or -1 (also after the rotation purge of :404-422).  Returns nmatches.
+int orc_search_by_bow(const uint8_t *kf_desc, const float *kf_angle, int n_kf, const uint8_t *kf_mp, const int32_t *kf_nodes, const int32_t *kf_off,
+                      const int32_t *kf_idx, int kf_nn, const uint8_t *f_desc, const float *f_angle, int n_f, const int32_t *f_nodes,
+                      const int32_t *f_off, const int32_t *f_idx, int f_nn, float nnratio, int check_ori, int32_t *assigned) {
+    (void)n_kf;
+    for (int i = 0; i < n_f; ++i) assigned[i] = -1;
+    int nmatches = 0;
+    std::vector<int> rotHist[30];
+    int a = 0, b = 0;
+    while (a < kf_nn && b < f_nn) {                                            // :243
+        if (kf_nodes[a] == f_nodes[b]) {
+            for (int iKF = kf_off[a]; iKF < kf_off[a + 1]; ++iKF) {
+                const int realIdxKF = kf_idx[iKF];
+                if (kf_mp[realIdxKF] != 1) continue;                           // :256-260 (null pointer or isBad())
+                int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+                for (int iF = f_off[b]; iF < f_off[b + 1]; ++iF) {
+                    const int realIdxF = f_idx[iF];
+                    if (assigned[realIdxF] >= 0) continue;                     // :281-282
+                    const int dist = orc_descriptor_distance(kf_desc + (size_t)realIdxKF * 32, f_desc + (size_t)realIdxF * 32);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = realIdxF; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                // :331-358; the right-camera half (:360-388) needs bestDist1R <= TH_LOW, which stays 256 when Nleft == -1
+                if (bestDist1 <= 50 && (float)bestDist1 < nnratio * (float)bestDist2) {
+                    assigned[bestIdxF] = realIdxKF;
+                    if (check_ori) rotHist[rot_bin(kf_angle[realIdxKF], f_angle[bestIdxF])].push_back(bestIdxF);
+                    ++nmatches;
+                }
+            }
+            ++a; ++b;
+        } else if (kf_nodes[a] < f_nodes[b]) {
+            while (a < kf_nn && kf_nodes[a] < f_nodes[b]) ++a;                 // lower_bound(Fit->first)
+        } else {
+            while (b < f_nn && f_nodes[b] < kf_nodes[a]) ++b;
+        }
+    }
+    if (check_ori) {                                                           // :404-422
+        int i1 = -1, i2 = -1, i3 = -1;
+        three_maxima(rotHist, 30, i1, i2, i3);
+        for (int i = 0; i < 30; ++i) {
+            if (i == i1 || i == i2 || i == i3) continue;
+            for (int j : rotHist[i]) { assigned[j] = -1; --nmatches; }
+        }
+    }
+    return nmatches;
+}
+
 // ---- classical rectified-stereo association (slot = Frame::ComputeStereoMatches, src/Frame.cc:813-915) ----
 // PARITY UNPINNED: this tree replaced the function's matcher by LightGlue (src/Frame.cc:822-860), so there is no reference
 // code to compile for it.  What follows restates the published algorithm of the upstream ORB-SLAM3 function of the same name

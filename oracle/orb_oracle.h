@@ -92,6 +92,10 @@ int orc_search_by_projection(const float *xy, const int32_t *octave, const uint8
                              float minX, float minY, float maxX, float maxY, const float *scale_factors, const float *mp_proj5,
                              const int32_t *mp_level, const uint8_t *mp_flags, const int32_t *mp_obs, const uint8_t *mp_desc, int m,
                              float nnratio, float th, int far_points, float th_far, int32_t *assigned);
+/* SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) for Nleft == -1 frames (ORBmatcher.cc:222-425); feature vectors as CSR */
+int orc_search_by_bow(const uint8_t *kf_desc, const float *kf_angle, int n_kf, const uint8_t *kf_mp, const int32_t *kf_nodes, const int32_t *kf_off,
+                      const int32_t *kf_idx, int kf_nn, const uint8_t *f_desc, const float *f_angle, int n_f, const int32_t *f_nodes,
+                      const int32_t *f_off, const int32_t *f_idx, int f_nn, float nnratio, int check_ori, int32_t *assigned);
 /* classical rectified-stereo association over the two extractors' pyramids (restated upstream algorithm; parity unpinned) */
 int orc_stereo_rowband(const orc_extractor *exL, const orc_extractor *exR, const orc_keypoint *kL, const uint8_t *dL, int nL,
                        const orc_keypoint *kR, const uint8_t *dR, int nR, float mbf, float mb, float *uRight, float *depth);

@@ -165,6 +165,8 @@ def lib_match():
         L.refm_search_init.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp, i32, f32, i32, vp]
         L.refm_search_by_projection.restype = i32
         L.refm_search_by_projection.argtypes = [vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, f32, f32, i32, f32, vp]
+        L.refm_search_by_bow.restype = i32
+        L.refm_search_by_bow.argtypes = [vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, i32, f32, i32, vp]
         L.refm_stereo_tail.restype = i32
         L.refm_stereo_tail.argtypes = [vp, i32, vp, i32, vp, vp, vp, i32, f32, f32, vp, vp]
         _lib_match = L
@@ -231,6 +233,18 @@ def search_by_projection(kps, desc, bounds, scale_factors, mp_proj5, mp_level, m
     n = lib_match().refm_search_by_projection(_p(kps), _p(desc), len(kps), None if ur is None else _p(ur), _p(ko), _p(b), _p(sf), len(sf), _p(p5),
                                               _p(lv), _p(fl), _p(ob), _p(md), len(p5), float(nnratio), float(th), int(far_points), float(th_far),
                                               _p(out))
+    return n, out
+
+
+def search_by_bow(kf_kps, kf_desc, kf_mp, kf_fv, f_kps, f_desc, f_fv, nnratio=0.7, check_ori=True):
+    """The reference's own SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (src/ORBmatcher.cc:222-425); fv = (nodes, off, idx) CSR."""
+    kk = _kps(kf_kps); fk = _kps(f_kps)
+    kd = np.ascontiguousarray(kf_desc, np.uint8); km = np.ascontiguousarray(kf_mp, np.uint8); fd = np.ascontiguousarray(f_desc, np.uint8)
+    kn, ko, ki = (np.ascontiguousarray(v, np.int32) for v in kf_fv)
+    fn, fo, fi = (np.ascontiguousarray(v, np.int32) for v in f_fv)
+    out = np.zeros(len(fk), np.int32)
+    n = lib_match().refm_search_by_bow(_p(kk), _p(kd), len(kk), _p(km), _p(kn), _p(ko), _p(ki), len(kn), _p(fk), _p(fd), len(fk), _p(fn), _p(fo),
+                                       _p(fi), len(fn), float(nnratio), int(check_ori), _p(out))
     return n, out
 
 

@@ -27,7 +27,15 @@ struct DMatch {
 
 using namespace std;  // include/Frame.h:47
 
+// DBoW2::FeatureVector is a std::map<NodeId, std::vector<unsigned int>> (Thirdparty/DBoW2/DBoW2/FeatureVector.h:23-24); SearchByBoW only
+// walks it (begin / end / lower_bound, ->first, ->second)
+namespace DBoW2 {
+class FeatureVector : public std::map<unsigned int, std::vector<unsigned int>> {};
+}  // namespace DBoW2
+
 namespace ORB_SLAM3 {
+
+class GeometricCamera;   // only ever compared against null on this path (mpCamera2)
 
 class MapPoint {
 public:
@@ -65,6 +73,21 @@ public:
     float mnMinX = 0, mnMaxX = 0, mnMinY = 0, mnMaxY = 0;         // static in the reference
     std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];
     std::vector<std::size_t> mGridRight[FRAME_GRID_COLS][FRAME_GRID_ROWS];
+    DBoW2::FeatureVector mFeatVec;                                 // include/Frame.h:215
+    GeometricCamera *mpCamera2 = nullptr;                          // include/Frame.h:321
+};
+
+// the KeyFrame members SearchByBoW(KeyFrame*, Frame&, …) touches (include/KeyFrame.h:218,331-340,366,377-378,391; src/ORBmatcher.cc:222-425)
+class KeyFrame {
+public:
+    std::vector<MapPoint *> GetMapPointMatches() { return mps; }
+    DBoW2::FeatureVector mFeatVec;
+    cv::Mat mDescriptors;
+    std::vector<cv::KeyPoint> mvKeys, mvKeysRight, mvKeysUn;
+    int NLeft = -1, NRight = -1;
+    GeometricCamera *mpCamera2 = nullptr;
+    // shim state
+    std::vector<MapPoint *> mps;
 };
 
 }  // namespace ORB_SLAM3

@@ -6,6 +6,7 @@
 //   src/ORBmatcher.cc:35-41      TH_HIGH / TH_LOW / HISTO_LENGTH, constructor
 //   src/ORBmatcher.cc:43-221     SearchByProjection(Frame&, vector<MapPoint*>&, th, bFarPoints, thFarPoints) — the
 //                                level-aware best/second-best loop of :84-140 — and RadiusByViewingCos
+//   src/ORBmatcher.cc:222-425    SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) — the candidate-list top-2 loop of :264-325 inside its ordered walk
 //   src/ORBmatcher.cc:644-759    SearchForInitialization
 //   src/ORBmatcher.cc:2008-2070  ComputeThreeMaxima, DescriptorDistance
 //   src/Frame.cc:387-418         AssignFeaturesToGrid
@@ -16,6 +17,7 @@
 namespace ORB_SLAM3 {
 #include "gen/orbmatcher_35_41.inc"
 #include "gen/orbmatcher_43_221.inc"
+#include "gen/orbmatcher_222_425.inc"
 #include "gen/orbmatcher_644_759.inc"
 #include "gen/orbmatcher_2008_2070.inc"
 #include "gen/frame_387_418.inc"
@@ -136,6 +138,37 @@ int refm_search_by_projection(const orc_keypoint *kps, const uint8_t *desc, int 
         MapPoint *p = F.mvpMapPoints[i];
         assigned[i] = (p && p >= mps.data() && p < mps.data() + m) ? (int32_t)(p - mps.data()) : -1;
     }
+    return nm;
+}
+
+// SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&), frames with Nleft == -1 and one camera.  Both feature vectors arrive as CSR
+// (ascending node ids, per node the feature indices in their stored order).  kf_mp[i]: 0 = no map point at keyframe feature i,
+// 1 = a good one, 2 = a bad one (isBad()).  assigned[n_f] = keyframe feature whose map point ended in vpMapPointMatches[i], or -1.
+static void fill_fv(DBoW2::FeatureVector &fv, const int32_t *nodes, const int32_t *off, const int32_t *idx, int nn) {
+    for (int k = 0; k < nn; ++k) fv[(unsigned)nodes[k]] = std::vector<unsigned int>(idx + off[k], idx + off[k + 1]);
+}
+int refm_search_by_bow(const orc_keypoint *kf_kps, const uint8_t *kf_desc, int n_kf, const uint8_t *kf_mp, const int32_t *kf_nodes,
+                       const int32_t *kf_off, const int32_t *kf_idx, int kf_nn, const orc_keypoint *f_kps, const uint8_t *f_desc, int n_f,
+                       const int32_t *f_nodes, const int32_t *f_off, const int32_t *f_idx, int f_nn, float nnratio, int check_ori,
+                       int32_t *assigned) {
+    const float bounds[4] = {0.f, 0.f, 640.f, 480.f};      // the grid plays no part here
+    Frame F;
+    fill_frame(F, f_kps, f_desc, n_f, bounds);
+    fill_fv(F.mFeatVec, f_nodes, f_off, f_idx, f_nn);
+    ORB_SLAM3::KeyFrame KF;
+    KF.mvKeysUn.resize(n_kf);
+    for (int i = 0; i < n_kf; ++i) memcpy(&KF.mvKeysUn[i], &kf_kps[i], sizeof(cv::KeyPoint));
+    KF.mvKeys = KF.mvKeysUn;
+    KF.mDescriptors = wrap_desc(kf_desc, n_kf);
+    fill_fv(KF.mFeatVec, kf_nodes, kf_off, kf_idx, kf_nn);
+    std::vector<MapPoint> mps(n_kf);
+    KF.mps.assign(n_kf, nullptr);
+    for (int i = 0; i < n_kf; ++i)
+        if (kf_mp[i]) { mps[i].bad = kf_mp[i] == 2; KF.mps[i] = &mps[i]; }
+    std::vector<MapPoint *> matches;
+    ORBmatcher matcher(nnratio, check_ori != 0);
+    const int nm = matcher.SearchByBoW(&KF, F, matches);
+    for (int i = 0; i < n_f; ++i) assigned[i] = matches[i] ? (int32_t)(matches[i] - mps.data()) : -1;
     return nm;
 }
 

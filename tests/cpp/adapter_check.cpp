@@ -27,6 +27,8 @@ int ref_extract(void *, const uint8_t *, int, int, size_t, const int32_t *, int,
 int refm_search_init(const orc_keypoint *, const uint8_t *, int, const orc_keypoint *, const uint8_t *, int, const float *, float *, int, float, int, int32_t *);
 int refm_search_by_projection(const orc_keypoint *, const uint8_t *, int, const float *, const int32_t *, const float *, const float *, int, const float *,
                               const int32_t *, const uint8_t *, const int32_t *, const uint8_t *, int, float, float, int, float, int32_t *);
+int refm_search_by_bow(const orc_keypoint *, const uint8_t *, int, const uint8_t *, const int32_t *, const int32_t *, const int32_t *, int, const orc_keypoint *,
+                       const uint8_t *, int, const int32_t *, const int32_t *, const int32_t *, int, float, int, int32_t *);
 #endif
 #ifdef WITH_REF_BOW
 void *ref_vocab_load_text(const char *);
@@ -145,6 +147,39 @@ int main(int argc, char **argv) {
             if (got != asg[i]) { printf("FAIL SearchByProjection keypoint %d: map point %d vs reference %d\n", i, got, asg[i]); return 1; }
         }
 #endif
+    // SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (src/Tracking.cc:2747 / :3724 style): the first extraction as the keyframe, the second
+    // as the frame, feature vectors = a coarse quantisation of the descriptors so that matching features mostly share a node
+    {
+        ORB_SLAM3::KeyFrame KF;
+        ORB_SLAM3::Frame F;
+        KF.mvKeysUn = keys; KF.mvKeys = keys; KF.mDescriptors = desc;
+        F.mvKeysUn = keys2; F.mvKeys = keys2; F.N = (int)keys2.size(); F.mDescriptors = desc2;
+        std::vector<ORB_SLAM3::MapPoint> mps(keys.size());
+        KF.mps.assign(keys.size(), nullptr);
+        std::vector<uint8_t> kfmp(keys.size());
+        for (size_t i = 0; i < keys.size(); ++i) {
+            kfmp[i] = (uint8_t)((i % 11) == 0 ? 0 : ((i % 23) == 0 ? 2 : 1));
+            if (kfmp[i]) { mps[i].bad = kfmp[i] == 2; KF.mps[i] = &mps[i]; }
+            KF.mFeatVec[(unsigned)(keys[i].octave * 8 + ((int)keys[i].pt.y * 8 / H))].push_back((unsigned)i);
+        }
+        for (size_t i = 0; i < keys2.size(); ++i) F.mFeatVec[(unsigned)(keys2[i].octave * 8 + ((int)keys2[i].pt.y * 8 / H))].push_back((unsigned)i);
+        std::vector<ORB_SLAM3::MapPoint *> matches;
+        ORB_SLAM3::ORBmatcher reloc(0.75f, true);                        // src/Tracking.cc:3685
+        const int nb = reloc.SearchByBoW(&KF, F, matches);
+        if (nb < 10 || (int)matches.size() != F.N) { printf("FAIL SearchByBoW found %d matches\n", nb); return 1; }
+#ifdef WITH_REF_MATCH
+        std::vector<int32_t> kn, ko(1, 0), ki, fn, fo(1, 0), fi, asg(F.N);
+        for (auto &e : KF.mFeatVec) { kn.push_back((int32_t)e.first); ki.insert(ki.end(), e.second.begin(), e.second.end()); ko.push_back((int32_t)ki.size()); }
+        for (auto &e : F.mFeatVec) { fn.push_back((int32_t)e.first); fi.insert(fi.end(), e.second.begin(), e.second.end()); fo.push_back((int32_t)fi.size()); }
+        const int rnb = refm_search_by_bow((const orc_keypoint *)keys.data(), desc.ptr(0), (int)keys.size(), kfmp.data(), kn.data(), ko.data(), ki.data(), (int)kn.size(),
+                                           (const orc_keypoint *)keys2.data(), desc2.ptr(0), F.N, fn.data(), fo.data(), fi.data(), (int)fn.size(), 0.75f, 1, asg.data());
+        if (rnb != nb) { printf("FAIL SearchByBoW count %d vs reference %d\n", nb, rnb); return 1; }
+        for (int i = 0; i < F.N; ++i) {
+            const int got = matches[i] ? (int)(matches[i] - mps.data()) : -1;
+            if (got != asg[i]) { printf("FAIL SearchByBoW frame feature %d: keyframe feature %d vs reference %d\n", i, got, asg[i]); return 1; }
+        }
+#endif
+    }
     }
     // vocabulary: BowVector / FeatureVector of the extracted descriptors, levelsup 4 as in Frame::ComputeBoW
     if (argc > 4) {

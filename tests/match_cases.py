@@ -7,6 +7,7 @@ import numpy as np
 BOUNDS = (0.0, 0.0, 640.0, 480.0)
 INIT_CASES = [(500, 300, 1, 0.9, True, 100), (2000, 2500, 2, 0.9, True, 100), (800, 50, 3, 0.6, False, 100), (1500, 1500, 6, 0.9, True, 30)]
 SBP_CASES = [(2000, 1500, 1, False, 1.0), (1000, 3000, 2, True, 3.0), (50, 20, 3, False, 3.0), (3000, 3000, 5, True, 1.0)]
+BOW_CASES = [(1000, 1200, 1, 0.7, True), (2000, 2000, 2, 0.75, True), (800, 900, 3, 0.9, False), (40, 40, 6, 0.6, True)]   # n_kf, n_f, seed, ratio, checkOri
 AREA_CASES = [(3000, 500, 1, (-1, -1)), (3000, 500, 2, (0, 0)), (800, 300, 3, (1, 4)), (2000, 400, 4, (-1, 2))]
 
 

@@ -348,3 +348,34 @@ def test_features_in_area_vs_reference_golden(orbx_mod, i):
     k = synth.keypoint_records(n, seed)
     off, cand = orbx_mod.ORBmatcher().GetFeaturesInArea(np.stack([k["x"], k["y"]], 1), k["octave"], BOUNDS, area_queries(nq, seed), *lv)
     assert np.array_equal(off, g[f"area{i}_off"]) and np.array_equal(cand, g[f"area{i}_cand"])
+
+
+def _bow_sides(s):
+    KF = dict(mDescriptors=s["kf_desc"], angles=s["kf_kps"]["angle"], map_points=s["kf_mp"], mFeatVec=s["kf_fv"])
+    F = dict(mDescriptors=s["f_desc"], angles=s["f_kps"]["angle"], mFeatVec=s["f_fv"])
+    return KF, F
+
+
+@pytest.mark.parametrize("i", range(4))
+def test_search_by_bow_vs_reference_golden(orbx_mod, i):
+    """orbx_search_by_bow == the stored outputs of the reference's own SearchByBoW(KeyFrame*, Frame&, …) (src/ORBmatcher.cc:222-425)"""
+    from dani_slam_b200 import synth
+    from match_cases import BOW_CASES
+    g = _gold()
+    nk, nf, seed, ratio, ori = BOW_CASES[i]
+    KF, F = _bow_sides(synth.bow_scene(nk, nf, seed))
+    nm, asg = orbx_mod.ORBmatcher(ratio, ori).SearchByBoW(KF, F)
+    assert nm == int(g[f"bow{i}_n"]) and np.array_equal(asg, g[f"bow{i}_assigned"])
+
+
+@pytest.mark.parametrize("nk,nf,seed,ratio,ori", [(1500, 1400, 31, 0.7, True), (1000, 900, 32, 0.9, False), (0, 50, 33, 0.7, True), (50, 0, 34, 0.7, True),
+                                                  (5000, 5000, 35, 0.75, True), (600, 600, 36, 1.0, True), (33, 31, 37, 0.6, True)])
+def test_search_by_bow_vs_oracle(orbx_mod, oracle_mod, nk, nf, seed, ratio, ori):
+    from dani_slam_b200 import synth
+    s = synth.bow_scene(nk, nf, seed, n_nodes=40 if nk < 3000 else 120)
+    KF, F = _bow_sides(s)
+    nm, asg = orbx_mod.ORBmatcher(ratio, ori).SearchByBoW(KF, F)
+    rn, rasg = oracle_mod.search_by_bow(s["kf_desc"], s["kf_kps"]["angle"], s["kf_mp"], s["kf_fv"], s["f_desc"], s["f_kps"]["angle"], s["f_fv"], ratio, ori)
+    assert nm == rn and np.array_equal(asg, rasg)
+    if nk >= 1000 and nf >= 900:
+        assert nm > 100

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN
-from match_cases import AREA_CASES, BOUNDS, INIT_CASES, SBP_CASES, area_queries, sha, tail_case
+from match_cases import AREA_CASES, BOUNDS, INIT_CASES, BOW_CASES, SBP_CASES, area_queries, sha, tail_case
 
 
 @pytest.fixture(scope="module")
@@ -176,3 +176,55 @@ def test_reference_features_in_area_vs_oracle(refm, oracle_mod):
             off, cand = refm.features_in_area(k, bounds, q, *lv)
             roff, rcand = oracle_mod.features_in_area(_xy(k), k["octave"], bounds, q, *lv)
             assert np.array_equal(off, roff) and np.array_equal(cand, rcand), (seed, lv)
+
+
+def oracle_bow(oracle_mod, s, ratio, ori):
+    return oracle_mod.search_by_bow(s["kf_desc"], s["kf_kps"]["angle"], s["kf_mp"], s["kf_fv"], s["f_desc"], s["f_kps"]["angle"], s["f_fv"], ratio, ori)
+
+
+@pytest.mark.parametrize("i", range(len(BOW_CASES)))
+def test_search_by_bow_golden(gold, oracle_mod, i):
+    """oracle == the stored outputs of the reference's own SearchByBoW(KeyFrame*, Frame&, …) (src/ORBmatcher.cc:222-425)"""
+    from dani_slam_b200 import synth
+    nk, nf, seed, ratio, ori = BOW_CASES[i]
+    s = synth.bow_scene(nk, nf, seed)
+    assert sha(s["kf_kps"], s["kf_desc"], s["kf_mp"], *s["kf_fv"], s["f_kps"], s["f_desc"], *s["f_fv"]) == str(gold[f"bow{i}_in"]), "scene generator drifted"
+    nm, asg = oracle_bow(oracle_mod, s, ratio, ori)
+    assert nm == int(gold[f"bow{i}_n"]) and np.array_equal(asg, gold[f"bow{i}_assigned"])
+    assert nm > 0 and nm == int((asg >= 0).sum())
+
+
+@pytest.mark.parametrize("nk,nf,seed,ratio,ori", [(300, 280, 11, 0.7, True), (1500, 1400, 12, 0.7, True), (1000, 900, 13, 0.9, False), (0, 50, 14, 0.7, True),
+                                                  (50, 0, 15, 0.7, True), (3000, 3000, 17, 0.75, True), (600, 600, 18, 1.0, True)])
+def test_reference_search_by_bow_vs_oracle(refm, oracle_mod, nk, nf, seed, ratio, ori):
+    """the reference's own source, run here, head to head with the oracle; the scenes make keyframe features compete for frame
+    features, so the ordered skip of :281-282 decides (an order-free top-2 would differ: checked below)"""
+    from dani_slam_b200 import synth
+    s = synth.bow_scene(nk, nf, seed)
+    rn, ra = refm.search_by_bow(s["kf_kps"], s["kf_desc"], s["kf_mp"], s["kf_fv"], s["f_kps"], s["f_desc"], s["f_fv"], ratio, ori)
+    on, oa = oracle_bow(oracle_mod, s, ratio, ori)
+    assert rn == on and np.array_equal(ra, oa)
+    if nk >= 1000 and nf >= 900:
+        assert rn > 100
+        # how many keyframe features had their unconstrained best candidate taken by an earlier one: the walk's order matters
+        taken = 0
+        kn, ko, ki = s["kf_fv"]; fn, fo, fi = s["f_fv"]
+        fpos = {int(v): j for j, v in enumerate(fn)}
+        seen = set()
+        for a, node in enumerate(kn):
+            if int(node) not in fpos:
+                continue
+            b = fpos[int(node)]
+            cands = fi[fo[b]:fo[b + 1]]
+            if len(cands) == 0:
+                continue
+            for kf in ki[ko[a]:ko[a + 1]]:
+                if s["kf_mp"][kf] != 1:
+                    continue
+                d = np.unpackbits(s["kf_desc"][kf][None, :] ^ s["f_desc"][cands], axis=1).sum(1)
+                best = int(cands[int(np.argmin(d))])
+                if best in seen:
+                    taken += 1
+                if oa[best] == kf:
+                    seen.add(best)
+        assert taken > 0

@@ -17,7 +17,7 @@ from dani_slam_b200 import synth  # noqa: E402
 from oracle import ref_binding as R  # noqa: E402
 
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from match_cases import AREA_CASES, BOUNDS, INIT_CASES, SBP_CASES, area_queries, histo_cases, sha, tail_case  # noqa: E402
+from match_cases import AREA_CASES, BOUNDS, BOW_CASES, INIT_CASES, SBP_CASES, area_queries, histo_cases, sha, tail_case  # noqa: E402
 
 
 def main():
@@ -47,6 +47,11 @@ def main():
                                          s["mp_desc"], 0.8, th, True, 50.0, s["u_right"], s["kp_obs"])
         out[f"sbp{i}_in"] = np.array(sha(s["kps"], s["desc"], s["mp_proj5"], s["mp_desc"]), dtype="U64")
         out[f"sbp{i}_n"] = np.int32(nm); out[f"sbp{i}_assigned"] = asg
+    for i, (nk, nf, seed, ratio, ori) in enumerate(BOW_CASES):
+        s = synth.bow_scene(nk, nf, seed)
+        nm, asg = R.search_by_bow(s["kf_kps"], s["kf_desc"], s["kf_mp"], s["kf_fv"], s["f_kps"], s["f_desc"], s["f_fv"], ratio, ori)
+        out[f"bow{i}_in"] = np.array(sha(s["kf_kps"], s["kf_desc"], s["kf_mp"], *s["kf_fv"], s["f_kps"], s["f_desc"], *s["f_fv"]), dtype="U64")
+        out[f"bow{i}_n"] = np.int32(nm); out[f"bow{i}_assigned"] = asg
     for i, seed in enumerate([1, 2]):
         uL, uR, iL, iR, dist = tail_case(seed)
         # the reference's matcher in this slot reports a similarity (distance = 1 - match.distance, src/Frame.cc:891); feeding
