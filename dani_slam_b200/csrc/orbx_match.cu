@@ -516,12 +516,13 @@ __global__ void __launch_bounds__(32) k_sbp_replay(int m, const uint8_t *__restr
 // a map point is skipped by every later query (:281-282); per query the lanes share the candidate scan (occupancy test, Hamming
 // distance) and shuffle-reduce the two smallest (distance, list position) keys = the scalar loop's strict-'<' best / second best.
 // Then TH_LOW and the fp32 ratio test (:331-333), the rotation histogram (:346-353) and, at the end, the purge of the matches
-// outside the three fullest bins (:404-422).
+// outside the three fullest bins (:404-422).  SearchByBoW(KeyFrame*, KeyFrame*, …) (:760-901) is the same walk with the strict threshold
+// (thLow = 49) and candidate lists already reduced to the second keyframe's features with a good map point.
 __global__ void __launch_bounds__(32) k_search_by_bow(const uint4 *__restrict__ kfDesc, const float *__restrict__ kfAng,
                                                       const uint4 *__restrict__ fDesc, const float *__restrict__ fAng, int nF,
                                                       const int32_t *__restrict__ qKF, const int32_t *__restrict__ qC0,
                                                       const int32_t *__restrict__ qC1, int nQ, const int32_t *__restrict__ fIdx,
-                                                      float nnratio, int checkOri, int32_t *assigned, int8_t *binOf, int32_t *nMatchesOut) {
+                                                      float nnratio, int thLow, int checkOri, int32_t *assigned, int8_t *binOf, int32_t *nMatchesOut) {
     const int lane = threadIdx.x;
     __shared__ int hist[30];
     __shared__ int sel[3];
@@ -543,7 +544,7 @@ __global__ void __launch_bounds__(32) k_search_by_bow(const uint4 *__restrict__ 
         warp_top2(a, b);
         if (a == NONE) continue;
         const int best = (int)(a >> 32), best2 = b == NONE ? 256 : (int)(b >> 32);
-        if (best <= 50 && (float)best < __fmul_rn(nnratio, (float)best2)) {   // TH_LOW, fp32 ratio
+        if (best <= thLow && (float)best < __fmul_rn(nnratio, (float)best2)) {   // TH_LOW (<= 50 for a frame, < 50 between keyframes), fp32 ratio
             const int bestIdx = fIdx[c0 + (int)(a & 0xffffffffu)];
             __syncwarp();
             if (lane == 0) {
@@ -1301,14 +1302,16 @@ int orbx_search_by_projection(orbx_matcher *m, const orbx_keypoint *keypoints_un
     return ORBX_OK;
 }
 
-int orbx_search_by_bow(orbx_matcher *m, const uint8_t *kf_desc, const float *kf_angle, int n_kf, const uint8_t *kf_mp, const int32_t *kf_nodes,
+// f_mp == nullptr: SearchByBoW(KeyFrame*, Frame&, …), assigned[n_f] by frame feature.  f_mp != nullptr: SearchByBoW(KeyFrame*, KeyFrame*, …):
+// candidates need a good map point, strict threshold; `assigned` is still indexed by the second side (the callers below invert it).
+static int search_by_bow_impl(orbx_matcher *m, const uint8_t *kf_desc, const float *kf_angle, int n_kf, const uint8_t *kf_mp, const int32_t *kf_nodes,
                        const int32_t *kf_off, const int32_t *kf_idx, int kf_nn, const uint8_t *f_desc, const float *f_angle, int n_f,
-                       const int32_t *f_nodes, const int32_t *f_off, const int32_t *f_idx, int f_nn, float nnratio, int check_orientation,
-                       int32_t *assigned, int32_t *n_matches) {
+                       const uint8_t *f_mp, const int32_t *f_nodes, const int32_t *f_off, const int32_t *f_idx_in, int f_nn, float nnratio,
+                       int check_orientation, int32_t *assigned, int32_t *n_matches) {
     if (!m) return ORBX_ERR_ARG;
     if (n_kf < 0 || n_f < 0 || kf_nn < 0 || f_nn < 0 || !n_matches || (n_f > 0 && (!f_desc || !f_angle || !assigned)) ||
         (n_kf > 0 && (!kf_desc || !kf_angle || !kf_mp)) || (kf_nn > 0 && (!kf_nodes || !kf_off || !kf_idx)) ||
-        (f_nn > 0 && (!f_nodes || !f_off || !f_idx))) {
+        (f_nn > 0 && (!f_nodes || !f_off || !f_idx_in))) {
         m->err = "orbx_search_by_bow: bad argument";
         return ORBX_ERR_ARG;
     }
@@ -1318,6 +1321,20 @@ int orbx_search_by_bow(orbx_matcher *m, const uint8_t *kf_desc, const float *kf_
     // the merge walk over the two node-sorted feature vectors (:243-402; lower_bound = skipping ahead), on the host: it only
     // touches node ids.  Queries = keyframe features with a good map point (:256-260), candidates = the frame's list of that node.
     std::vector<int32_t> qKF, qC0, qC1;
+    for (int i = 0; i < f_off[f_nn]; ++i)
+        if (f_idx_in[i] < 0 || f_idx_in[i] >= n_f) { m->err = "orbx_search_by_bow: feature index of the second side out of range"; return ORBX_ERR_ARG; }
+    // between keyframes a candidate needs a good map point of its own (:819-826): drop the others from the lists, order kept
+    std::vector<int32_t> fOffK, fIdxK;
+    if (f_mp) {
+        fOffK.assign(1, 0);
+        for (int b = 0; b < f_nn; ++b) {
+            for (int i = f_off[b]; i < f_off[b + 1]; ++i)
+                if (f_mp[f_idx_in[i]] == 1) fIdxK.push_back(f_idx_in[i]);
+            fOffK.push_back((int32_t)fIdxK.size());
+        }
+        f_off = fOffK.data();
+    }
+    const int32_t *f_idx = f_mp ? fIdxK.data() : f_idx_in;
     const int nIdxF = f_off[f_nn];
     for (int a = 0, b = 0; a < kf_nn && b < f_nn;) {
         if (kf_nodes[a] == f_nodes[b]) {
@@ -1334,8 +1351,6 @@ int orbx_search_by_bow(orbx_matcher *m, const uint8_t *kf_desc, const float *kf_
             ++b;
         }
     }
-    for (int i = 0; i < nIdxF; ++i)
-        if (f_idx[i] < 0 || f_idx[i] >= n_f) { m->err = "orbx_search_by_bow: frame feature index out of range"; return ORBX_ERR_ARG; }
     const int nQ = (int)qKF.size();
     if (nQ == 0 || nIdxF == 0) return ORBX_OK;
     OrbxDeviceGuard dg_(m->device); MCUDA_TRY(m, dg_.status);
@@ -1361,12 +1376,36 @@ int orbx_search_by_bow(orbx_matcher *m, const uint8_t *kf_desc, const float *kf_
     MCUDA_TRY(m, cudaMemcpyAsync(dqC0, qC0.data(), (size_t)nQ * 4, cudaMemcpyHostToDevice, s));
     MCUDA_TRY(m, cudaMemcpyAsync(dqC1, qC1.data(), (size_t)nQ * 4, cudaMemcpyHostToDevice, s));
     MCUDA_TRY(m, cudaMemcpyAsync(dfi, f_idx, (size_t)nIdxF * 4, cudaMemcpyHostToDevice, s));
-    k_search_by_bow<<<1, 32, 0, s>>>((const uint4 *)dkd, dka, (const uint4 *)dfd, dfa, n_f, dqKF, dqC0, dqC1, nQ, dfi, nnratio, check_orientation ? 1 : 0,
-                                     dasg, dbin, dn);
+    k_search_by_bow<<<1, 32, 0, s>>>((const uint4 *)dkd, dka, (const uint4 *)dfd, dfa, n_f, dqKF, dqC0, dqC1, nQ, dfi, nnratio, f_mp ? 49 : 50,
+                                     check_orientation ? 1 : 0, dasg, dbin, dn);
     MCUDA_TRY(m, cudaGetLastError());
     MCUDA_TRY(m, cudaMemcpyAsync(assigned, dasg, (size_t)n_f * 4, cudaMemcpyDeviceToHost, s));
     MCUDA_TRY(m, cudaMemcpyAsync(n_matches, dn, 4, cudaMemcpyDeviceToHost, s));
     MCUDA_TRY(m, cudaStreamSynchronize(s));
+    return ORBX_OK;
+}
+
+int orbx_search_by_bow(orbx_matcher *m, const uint8_t *kf_desc, const float *kf_angle, int n_kf, const uint8_t *kf_mp, const int32_t *kf_nodes,
+                       const int32_t *kf_off, const int32_t *kf_idx, int kf_nn, const uint8_t *f_desc, const float *f_angle, int n_f,
+                       const int32_t *f_nodes, const int32_t *f_off, const int32_t *f_idx, int f_nn, float nnratio, int check_orientation,
+                       int32_t *assigned, int32_t *n_matches) {
+    return search_by_bow_impl(m, kf_desc, kf_angle, n_kf, kf_mp, kf_nodes, kf_off, kf_idx, kf_nn, f_desc, f_angle, n_f, nullptr, f_nodes, f_off, f_idx, f_nn,
+                              nnratio, check_orientation, assigned, n_matches);
+}
+
+int orbx_search_by_bow_keyframes(orbx_matcher *m, const uint8_t *desc1, const float *angle1, int n1, const uint8_t *mp1, const int32_t *nodes1,
+                                 const int32_t *off1, const int32_t *idx1, int nn1, const uint8_t *desc2, const float *angle2, int n2,
+                                 const uint8_t *mp2, const int32_t *nodes2, const int32_t *off2, const int32_t *idx2, int nn2, float nnratio,
+                                 int check_orientation, int32_t *matches12, int32_t *n_matches) {
+    if (!m) return ORBX_ERR_ARG;
+    if (n1 < 0 || n2 < 0 || !n_matches || (n1 > 0 && !matches12) || (n2 > 0 && !mp2)) { m->err = "orbx_search_by_bow_keyframes: bad argument"; return ORBX_ERR_ARG; }
+    for (int i = 0; i < n1; ++i) matches12[i] = -1;
+    std::vector<int32_t> by2((size_t)std::max(n2, 1), -1);
+    const int rc = search_by_bow_impl(m, desc1, angle1, n1, mp1, nodes1, off1, idx1, nn1, desc2, angle2, n2, mp2, nodes2, off2, idx2, nn2, nnratio,
+                                      check_orientation, by2.data(), n_matches);
+    if (rc) return rc;
+    for (int j = 0; j < n2; ++j)
+        if (by2[j] >= 0) matches12[by2[j]] = j;                // every feature of keyframe 2 is matched at most once (vbMatched2)
     return ORBX_OK;
 }
 

@@ -101,6 +101,7 @@ def lib() -> C.CDLL:
     L.orbx_hamming_top2_lists.argtypes = [vp, vp, i32, vp, i64, vp, vp, vp, vp, vp, vp]
     L.orbx_search_by_projection.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, f32, f32, i32, f32, vp, vp]
     L.orbx_search_by_bow.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, i32, f32, i32, vp, vp]
+    L.orbx_search_by_bow_keyframes.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, vp, i32, f32, i32, vp, vp]
     L.orbx_search_for_initialization_frames.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, vp, i32, f32, i32, vp, vp]
     L.orbx_rot_hist_filter.argtypes = [vp, vp, vp, i32, vp]
     L.orbx_features_in_area.argtypes = [vp, vp, vp, i32, f32, f32, f32, f32, vp, i32, i32, i32, vp, vp, i32, vp]
@@ -413,6 +414,23 @@ class ORBmatcher:
         n = C.c_int32(0)
         self._chk(self.L.orbx_search_by_bow(self.h, _p(kd), _p(ka), len(kd), _p(km), _p(kn), _p(ko), _p(ki), len(kn), _p(fd), _p(fa), len(fd),
                                             _p(fn), _p(fo), _p(fi), len(fn), float(self.mfNNratio), int(self.mbCheckOrientation), _p(out), C.byref(n)))
+        return n.value, out
+
+    def SearchByBoWKeyFrames(self, KF1, KF2):
+        """`ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint*> &vpMatches12)` (src/ORBmatcher.cc:760-901).  Both sides
+        are dicts like KF in SearchByBoW.  → (nmatches, matches12[n1]): the feature of keyframe 2 whose map point each feature of keyframe 1 got."""
+        d1 = np.ascontiguousarray(KF1["mDescriptors"], np.uint8).reshape(-1, 32); a1 = np.ascontiguousarray(KF1["angles"], np.float32)
+        m1 = np.ascontiguousarray(KF1["map_points"], np.uint8)
+        d2 = np.ascontiguousarray(KF2["mDescriptors"], np.uint8).reshape(-1, 32); a2 = np.ascontiguousarray(KF2["angles"], np.float32)
+        m2 = np.ascontiguousarray(KF2["map_points"], np.uint8)
+        n1, o1, i1 = (np.ascontiguousarray(v, np.int32) for v in KF1["mFeatVec"])
+        n2, o2, i2 = (np.ascontiguousarray(v, np.int32) for v in KF2["mFeatVec"])
+        assert len(a1) == len(m1) == len(d1) and len(a2) == len(m2) == len(d2) and len(o1) == len(n1) + 1 and len(o2) == len(n2) + 1
+        out = np.full(len(d1), -1, np.int32)
+        n = C.c_int32(0)
+        self._chk(self.L.orbx_search_by_bow_keyframes(self.h, _p(d1), _p(a1), len(d1), _p(m1), _p(n1), _p(o1), _p(i1), len(n1), _p(d2), _p(a2), len(d2),
+                                                      _p(m2), _p(n2), _p(o2), _p(i2), len(n2), float(self.mfNNratio), int(self.mbCheckOrientation),
+                                                      _p(out), C.byref(n)))
         return n.value, out
 
     def SearchForInitializationFrames(self, kps1, desc1, kps2, desc2, bounds, vbPrevMatched, windowSize=10):

@@ -310,4 +310,6 @@ def bow_scene(n_kf: int, n_f: int, seed: int, n_nodes: int = 40, max_flips: int 
             idx += members; off.append(len(idx))
         return nodes.astype(np.int32), np.asarray(off, np.int32), np.asarray(idx, np.int32)
 
-    return dict(kf_kps=kk, kf_desc=kd, kf_mp=kf_mp, kf_fv=csr(kf_node, n_kf), f_kps=fk, f_desc=fd, f_fv=csr(f_node, n_f))
+    kf_fv, f_fv = csr(kf_node, n_kf), csr(f_node, n_f)
+    f_mp = rng.choice([0, 1, 1, 1, 1, 1, 2], n_f).astype(np.uint8)     # used when the second side is a keyframe too (SearchByBoW(KF, KF))
+    return dict(kf_kps=kk, kf_desc=kd, kf_mp=kf_mp, kf_fv=kf_fv, f_kps=fk, f_desc=fd, f_fv=f_fv, f_mp=f_mp)

@@ -9,13 +9,14 @@
  *   static DescriptorDistance(const cv::Mat&, const cv::Mat&)       src/ORBmatcher.cc:2054-2070   (host popcount, no launch)
  *   SearchByProjection(Frame&, const vector<MapPoint*>&, th, …)     src/ORBmatcher.cc:43-213      → orbx_search_by_projection
  *   SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)              src/ORBmatcher.cc:222-425     → orbx_search_by_bow
+ *   SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&)           src/ORBmatcher.cc:760-901     → orbx_search_by_bow_keyframes
  *   SearchForInitialization(Frame&, Frame&, …, windowSize)          src/ORBmatcher.cc:644-759     → orbx_search_for_initialization_frames
  *   TH_LOW / TH_HIGH / HISTO_LENGTH                                 src/ORBmatcher.cc:35-37
  *
- * The other members (SearchByBoW between two keyframes, SearchForTriangulation, SearchBySim3, Fuse and the three remaining
+ * The other members (SearchForTriangulation, SearchBySim3, Fuse and the three remaining
  * SearchByProjection overloads) are projection geometry over KeyFrame / MapPoint pointers and stay in the
  * reference's own src/ORBmatcher.cc (out of scope); they are only DECLARED here, exactly as in the
- * reference, and their inner loops call the DescriptorDistance above.  INTEGRATION.md shows the four ranges of
+ * reference, and their inner loops call the DescriptorDistance above.  INTEGRATION.md shows the five ranges of
  * src/ORBmatcher.cc a maintainer fences off (`#ifndef ORBX_DROPIN`) so that each function has one definition.
  *
  * Matchers are stack objects constructed per call in the reference (src/Tracking.cc:2511,2747 …), so the
@@ -167,6 +168,34 @@ public:
             if(assigned[i] >= 0) vpMapPointMatches[i] = vpMapPointsKF[assigned[i]];        // :335
         return nmatches;
     }
+
+    // Matching for triangulating / merging between two keyframes constrained to the same vocabulary node (Loop Closing, Merging)
+    int SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, std::vector<MapPoint*> &vpMatches12)
+    {
+        if(pKF1->NLeft != -1 || pKF2->NLeft != -1)
+            throw std::runtime_error("ORBmatcher::SearchByBoW: two-camera keyframes (NLeft != -1) are not on the device path");
+        const std::vector<MapPoint*> vpMapPoints1 = pKF1->GetMapPointMatches(), vpMapPoints2 = pKF2->GetMapPointMatches();
+        const int n1 = (int)vpMapPoints1.size(), n2 = (int)vpMapPoints2.size();
+        vpMatches12 = std::vector<MapPoint*>(n1, static_cast<MapPoint*>(NULL));            // :772
+        if(n1 == 0 || n2 == 0) return 0;
+        std::vector<unsigned char> mp1(n1), mp2(n2);
+        std::vector<float> ang1(n1), ang2(n2);
+        for(int i=0; i<n1; i++){ MapPoint* p = vpMapPoints1[i]; mp1[i] = !p ? 0 : (p->isBad() ? 2 : 1); ang1[i] = pKF1->mvKeysUn[i].angle; }
+        for(int i=0; i<n2; i++){ MapPoint* p = vpMapPoints2[i]; mp2[i] = !p ? 0 : (p->isBad() ? 2 : 1); ang2[i] = pKF2->mvKeysUn[i].angle; }
+        std::vector<int> an, ao(1, 0), ai, bn, bo(1, 0), bi;
+        Flatten(pKF1->mFeatVec, an, ao, ai);
+        Flatten(pKF2->mFeatVec, bn, bo, bi);
+        std::vector<unsigned char> rows1, rows2;
+        std::vector<int> m12(n1, -1);
+        int nmatches = 0;
+        Check(orbx_search_by_bow_keyframes(Ctx(), Rows(pKF1->mDescriptors, n1, rows1), ang1.data(), n1, mp1.data(), an.data(), ao.data(), ai.data(), (int)an.size(),
+                                           Rows(pKF2->mDescriptors, n2, rows2), ang2.data(), n2, mp2.data(), bn.data(), bo.data(), bi.data(), (int)bn.size(),
+                                           mfNNratio, mbCheckOrientation ? 1 : 0, m12.data(), &nmatches),
+              "SearchByBoW");
+        for(int i=0; i<n1; i++)
+            if(m12[i] >= 0) vpMatches12[i] = vpMapPoints2[m12[i]];                         // :847
+        return nmatches;
+    }
 #endif
 
 #ifndef ORBX_MATCHER_HOT_PATH_ONLY
@@ -175,7 +204,6 @@ public:
     int SearchByProjection(Frame &CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*> &sAlreadyFound, const float th, const int ORBdist);
     int SearchByProjection(KeyFrame* pKF, Sophus::Sim3<float> &Scw, const std::vector<MapPoint*> &vpPoints, std::vector<MapPoint*> &vpMatched, int th, float ratioHamming=1.0);
     int SearchByProjection(KeyFrame* pKF, Sophus::Sim3<float> &Scw, const std::vector<MapPoint*> &vpPoints, const std::vector<KeyFrame*> &vpPointsKFs, std::vector<MapPoint*> &vpMatched, std::vector<KeyFrame*> &vpMatchedKF, int th, float ratioHamming=1.0);
-    int SearchByBoW(KeyFrame *pKF1, KeyFrame* pKF2, std::vector<MapPoint*> &vpMatches12);
     int SearchForTriangulation(KeyFrame *pKF1, KeyFrame* pKF2,
                                std::vector<std::pair<size_t, size_t> > &vMatchedPairs, const bool bOnlyStereo, const bool bCoarse = false);
     int SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint *> &vpMatches12, const Sophus::Sim3f &S12, const float th);

@@ -210,6 +210,15 @@ int orbx_search_by_bow(orbx_matcher *m, const uint8_t *kf_desc, const float *kf_
                        const int32_t *kf_off, const int32_t *kf_idx, int kf_nn, const uint8_t *f_desc, const float *f_angle, int n_f,
                        const int32_t *f_nodes, const int32_t *f_off, const int32_t *f_idx, int f_nn, float nnratio, int check_orientation,
                        int32_t *assigned, int32_t *n_matches);
+/* ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint*> &vpMatches12) (src/ORBmatcher.cc:760-901), whole function:
+ * as above between two keyframes — a candidate of keyframe 2 needs a good map point of its own and leaves the scans once matched
+ * (vbMatched2), the threshold is bestDist1 < TH_LOW.  mp1 / mp2 as kf_mp, feature vectors as CSR.
+ *   out: matches12[i] = feature of keyframe 2 whose map point the call leaves in vpMatches12[i], or -1; *n_matches = return value
+ * HOST buffers. */
+int orbx_search_by_bow_keyframes(orbx_matcher *m, const uint8_t *desc1, const float *angle1, int n1, const uint8_t *mp1, const int32_t *nodes1,
+                                 const int32_t *off1, const int32_t *idx1, int nn1, const uint8_t *desc2, const float *angle2, int n2,
+                                 const uint8_t *mp2, const int32_t *nodes2, const int32_t *off2, const int32_t *idx2, int nn2, float nnratio,
+                                 int check_orientation, int32_t *matches12, int32_t *n_matches);
 /* Rotation-consistency filter: bin = round((a-b [+360]) / 30) (quirk Q10), keep matches in the three
  * fullest bins subject to the 0.1·max rule.  HOST / DEVICE buffers; n matches. */
 int orbx_rot_hist_filter(orbx_matcher *m, const float *angle_a, const float *angle_b, int n, uint8_t *keep);

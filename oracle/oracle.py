@@ -67,6 +67,8 @@ def lib() -> C.CDLL:
         L.orc_search_by_projection.argtypes = [vp, vp, vp, i32, vp, vp, f32, f32, f32, f32, vp, vp, vp, vp, vp, vp, i32, f32, f32, i32, f32, vp]
         L.orc_search_by_bow.restype = i32
         L.orc_search_by_bow.argtypes = [vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, i32, f32, i32, vp]
+        L.orc_search_by_bow_kf.restype = i32
+        L.orc_search_by_bow_kf.argtypes = [vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, vp, i32, f32, i32, vp]
         L.orc_three_maxima.argtypes = [vp, i32, vp]
         L.orc_rot_hist_filter.argtypes = [vp, vp, i32, vp]
         L.orc_features_in_area.restype = i32
@@ -242,6 +244,18 @@ def search_by_bow(kf_desc, kf_angle, kf_mp, kf_fv, f_desc, f_angle, f_fv, nnrati
     out = np.zeros(len(fd), np.int32)
     n = lib().orc_search_by_bow(_p(kd), _p(ka), len(kd), _p(km), _p(kn), _p(ko), _p(ki), len(kn), _p(fd), _p(fa), len(fd), _p(fn), _p(fo), _p(fi),
                                 len(fn), float(nnratio), int(check_ori), _p(out))
+    return n, out
+
+
+def search_by_bow_kf(desc1, angle1, mp1, fv1, desc2, angle2, mp2, fv2, nnratio=0.7, check_ori=True):
+    """ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&) → (nmatches, matches12[n1])"""
+    d1 = np.ascontiguousarray(desc1, np.uint8); a1 = np.ascontiguousarray(angle1, np.float32); m1 = np.ascontiguousarray(mp1, np.uint8)
+    d2 = np.ascontiguousarray(desc2, np.uint8); a2 = np.ascontiguousarray(angle2, np.float32); m2 = np.ascontiguousarray(mp2, np.uint8)
+    n1, o1, i1 = (np.ascontiguousarray(v, np.int32) for v in fv1)
+    n2, o2, i2 = (np.ascontiguousarray(v, np.int32) for v in fv2)
+    out = np.zeros(len(d1), np.int32)
+    n = lib().orc_search_by_bow_kf(_p(d1), _p(a1), len(d1), _p(m1), _p(n1), _p(o1), _p(i1), len(n1), _p(d2), _p(a2), len(d2), _p(m2), _p(n2), _p(o2),
+                                   _p(i2), len(n2), float(nnratio), int(check_ori), _p(out))
     return n, out
 
 

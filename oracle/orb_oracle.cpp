@@ -972,6 +972,56 @@ int orc_search_by_bow(const uint8_t *kf_desc, const float *kf_angle, int n_kf, c
     return nmatches;
 }
 
+// ---- ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint*> &vpMatches12) (src/ORBmatcher.cc:760-901) ----
+// Differences to the frame variant above: a candidate needs a good map point of its own and must not be matched yet (vbMatched2,
+// :819-823), the threshold is bestDist1 < TH_LOW (strict, :843), the result is indexed by the FIRST keyframe's feature.
+// matches12[i] = feature of keyframe 2 whose map point ends in vpMatches12[i], or -1.
+int orc_search_by_bow_kf(const uint8_t *desc1, const float *angle1, int n1, const uint8_t *mp1, const int32_t *nodes1, const int32_t *off1,
+                         const int32_t *idx1, int nn1, const uint8_t *desc2, const float *angle2, int n2, const uint8_t *mp2, const int32_t *nodes2,
+                         const int32_t *off2, const int32_t *idx2, int nn2, float nnratio, int check_ori, int32_t *matches12) {
+    for (int i = 0; i < n1; ++i) matches12[i] = -1;
+    std::vector<char> matched2(std::max(n2, 1), 0);
+    int nmatches = 0;
+    std::vector<int> rotHist[30];
+    int a = 0, b = 0;
+    while (a < nn1 && b < nn2) {
+        if (nodes1[a] == nodes2[b]) {
+            for (int i1 = off1[a]; i1 < off1[a + 1]; ++i1) {
+                const int q = idx1[i1];
+                if (mp1[q] != 1) continue;                                     // :801-805
+                int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+                for (int i2 = off2[b]; i2 < off2[b + 1]; ++i2) {
+                    const int t = idx2[i2];
+                    if (matched2[t] || mp2[t] != 1) continue;                  // :819-826
+                    const int dist = orc_descriptor_distance(desc1 + (size_t)q * 32, desc2 + (size_t)t * 32);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = t; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                if (bestDist1 < 50 && (float)bestDist1 < nnratio * (float)bestDist2) {   // :843-845
+                    matches12[q] = bestIdx2;
+                    matched2[bestIdx2] = 1;
+                    if (check_ori) rotHist[rot_bin(angle1[q], angle2[bestIdx2])].push_back(q);
+                    ++nmatches;
+                }
+            }
+            ++a; ++b;
+        } else if (nodes1[a] < nodes2[b]) {
+            while (a < nn1 && nodes1[a] < nodes2[b]) ++a;
+        } else {
+            while (b < nn2 && nodes2[b] < nodes1[a]) ++b;
+        }
+    }
+    if (check_ori) {
+        int i1 = -1, i2 = -1, i3 = -1;
+        three_maxima(rotHist, 30, i1, i2, i3);
+        for (int i = 0; i < 30; ++i) {
+            if (i == i1 || i == i2 || i == i3) continue;
+            for (int j : rotHist[i]) { matches12[j] = -1; --nmatches; }
+        }
+    }
+    return nmatches;
+}
+
 // ---- classical rectified-stereo association (slot = Frame::ComputeStereoMatches, src/Frame.cc:813-915) ----
 // PARITY UNPINNED: this tree replaced the function's matcher by LightGlue (src/Frame.cc:822-860), so there is no reference
 // code to compile for it.  What follows restates the published algorithm of the upstream ORB-SLAM3 function of the same name

@@ -96,6 +96,10 @@ int orc_search_by_projection(const float *xy, const int32_t *octave, const uint8
 int orc_search_by_bow(const uint8_t *kf_desc, const float *kf_angle, int n_kf, const uint8_t *kf_mp, const int32_t *kf_nodes, const int32_t *kf_off,
                       const int32_t *kf_idx, int kf_nn, const uint8_t *f_desc, const float *f_angle, int n_f, const int32_t *f_nodes,
                       const int32_t *f_off, const int32_t *f_idx, int f_nn, float nnratio, int check_ori, int32_t *assigned);
+/* SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&) (ORBmatcher.cc:760-901) */
+int orc_search_by_bow_kf(const uint8_t *desc1, const float *angle1, int n1, const uint8_t *mp1, const int32_t *nodes1, const int32_t *off1,
+                         const int32_t *idx1, int nn1, const uint8_t *desc2, const float *angle2, int n2, const uint8_t *mp2, const int32_t *nodes2,
+                         const int32_t *off2, const int32_t *idx2, int nn2, float nnratio, int check_ori, int32_t *matches12);
 /* classical rectified-stereo association over the two extractors' pyramids (restated upstream algorithm; parity unpinned) */
 int orc_stereo_rowband(const orc_extractor *exL, const orc_extractor *exR, const orc_keypoint *kL, const uint8_t *dL, int nL,
                        const orc_keypoint *kR, const uint8_t *dR, int nR, float mbf, float mb, float *uRight, float *depth);

@@ -167,6 +167,8 @@ def lib_match():
         L.refm_search_by_projection.argtypes = [vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, f32, f32, i32, f32, vp]
         L.refm_search_by_bow.restype = i32
         L.refm_search_by_bow.argtypes = [vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, i32, f32, i32, vp]
+        L.refm_search_by_bow_kf.restype = i32
+        L.refm_search_by_bow_kf.argtypes = [vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, vp, i32, f32, i32, vp]
         L.refm_stereo_tail.restype = i32
         L.refm_stereo_tail.argtypes = [vp, i32, vp, i32, vp, vp, vp, i32, f32, f32, vp, vp]
         _lib_match = L
@@ -245,6 +247,19 @@ def search_by_bow(kf_kps, kf_desc, kf_mp, kf_fv, f_kps, f_desc, f_fv, nnratio=0.
     out = np.zeros(len(fk), np.int32)
     n = lib_match().refm_search_by_bow(_p(kk), _p(kd), len(kk), _p(km), _p(kn), _p(ko), _p(ki), len(kn), _p(fk), _p(fd), len(fk), _p(fn), _p(fo),
                                        _p(fi), len(fn), float(nnratio), int(check_ori), _p(out))
+    return n, out
+
+
+def search_by_bow_kf(kps1, desc1, mp1, fv1, kps2, desc2, mp2, fv2, nnratio=0.7, check_ori=True):
+    """The reference's own SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&) (src/ORBmatcher.cc:760-901)"""
+    k1 = _kps(kps1); k2 = _kps(kps2)
+    d1 = np.ascontiguousarray(desc1, np.uint8); m1 = np.ascontiguousarray(mp1, np.uint8)
+    d2 = np.ascontiguousarray(desc2, np.uint8); m2 = np.ascontiguousarray(mp2, np.uint8)
+    n1, o1, i1 = (np.ascontiguousarray(v, np.int32) for v in fv1)
+    n2, o2, i2 = (np.ascontiguousarray(v, np.int32) for v in fv2)
+    out = np.zeros(len(k1), np.int32)
+    n = lib_match().refm_search_by_bow_kf(_p(k1), _p(d1), len(k1), _p(m1), _p(n1), _p(o1), _p(i1), len(n1), _p(k2), _p(d2), len(k2), _p(m2), _p(n2),
+                                          _p(o2), _p(i2), len(n2), float(nnratio), int(check_ori), _p(out))
     return n, out
 
 

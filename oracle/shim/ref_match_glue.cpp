@@ -8,6 +8,7 @@
 //                                level-aware best/second-best loop of :84-140 — and RadiusByViewingCos
 //   src/ORBmatcher.cc:222-425    SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) — the candidate-list top-2 loop of :264-325 inside its ordered walk
 //   src/ORBmatcher.cc:644-759    SearchForInitialization
+//   src/ORBmatcher.cc:760-901    SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&)
 //   src/ORBmatcher.cc:2008-2070  ComputeThreeMaxima, DescriptorDistance
 //   src/Frame.cc:387-418         AssignFeaturesToGrid
 //   src/Frame.cc:659-738         GetFeaturesInArea, PosInGrid
@@ -19,6 +20,7 @@ namespace ORB_SLAM3 {
 #include "gen/orbmatcher_43_221.inc"
 #include "gen/orbmatcher_222_425.inc"
 #include "gen/orbmatcher_644_759.inc"
+#include "gen/orbmatcher_760_901.inc"
 #include "gen/orbmatcher_2008_2070.inc"
 #include "gen/frame_387_418.inc"
 #include "gen/frame_659_738.inc"
@@ -169,6 +171,34 @@ int refm_search_by_bow(const orc_keypoint *kf_kps, const uint8_t *kf_desc, int n
     ORBmatcher matcher(nnratio, check_ori != 0);
     const int nm = matcher.SearchByBoW(&KF, F, matches);
     for (int i = 0; i < n_f; ++i) assigned[i] = matches[i] ? (int32_t)(matches[i] - mps.data()) : -1;
+    return nm;
+}
+
+// SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint*> &vpMatches12) (one camera per keyframe).  mp1 / mp2 as kf_mp above;
+// matches12[n1] = feature of keyframe 2 whose map point ended in vpMatches12[i], or -1.
+static void fill_kf(ORB_SLAM3::KeyFrame &KF, std::vector<MapPoint> &mps, const orc_keypoint *kps, const uint8_t *desc, int n, const uint8_t *mp,
+                    const int32_t *nodes, const int32_t *off, const int32_t *idx, int nn) {
+    KF.mvKeysUn.resize(n);
+    for (int i = 0; i < n; ++i) memcpy(&KF.mvKeysUn[i], &kps[i], sizeof(cv::KeyPoint));
+    KF.mvKeys = KF.mvKeysUn;
+    KF.mDescriptors = wrap_desc(desc, n);
+    fill_fv(KF.mFeatVec, nodes, off, idx, nn);
+    mps.assign(n, MapPoint());
+    KF.mps.assign(n, nullptr);
+    for (int i = 0; i < n; ++i)
+        if (mp[i]) { mps[i].bad = mp[i] == 2; KF.mps[i] = &mps[i]; }
+}
+int refm_search_by_bow_kf(const orc_keypoint *kps1, const uint8_t *desc1, int n1, const uint8_t *mp1, const int32_t *nodes1, const int32_t *off1,
+                          const int32_t *idx1, int nn1, const orc_keypoint *kps2, const uint8_t *desc2, int n2, const uint8_t *mp2,
+                          const int32_t *nodes2, const int32_t *off2, const int32_t *idx2, int nn2, float nnratio, int check_ori, int32_t *matches12) {
+    ORB_SLAM3::KeyFrame K1, K2;
+    std::vector<MapPoint> m1, m2;
+    fill_kf(K1, m1, kps1, desc1, n1, mp1, nodes1, off1, idx1, nn1);
+    fill_kf(K2, m2, kps2, desc2, n2, mp2, nodes2, off2, idx2, nn2);
+    std::vector<MapPoint *> matches;
+    ORBmatcher matcher(nnratio, check_ori != 0);
+    const int nm = matcher.SearchByBoW(&K1, &K2, matches);
+    for (int i = 0; i < n1; ++i) matches12[i] = matches[i] ? (int32_t)(matches[i] - m2.data()) : -1;
     return nm;
 }
 

@@ -29,6 +29,8 @@ int refm_search_by_projection(const orc_keypoint *, const uint8_t *, int, const 
                               const int32_t *, const uint8_t *, const int32_t *, const uint8_t *, int, float, float, int, float, int32_t *);
 int refm_search_by_bow(const orc_keypoint *, const uint8_t *, int, const uint8_t *, const int32_t *, const int32_t *, const int32_t *, int, const orc_keypoint *,
                        const uint8_t *, int, const int32_t *, const int32_t *, const int32_t *, int, float, int, int32_t *);
+int refm_search_by_bow_kf(const orc_keypoint *, const uint8_t *, int, const uint8_t *, const int32_t *, const int32_t *, const int32_t *, int, const orc_keypoint *,
+                          const uint8_t *, int, const uint8_t *, const int32_t *, const int32_t *, const int32_t *, int, float, int, int32_t *);
 #endif
 #ifdef WITH_REF_BOW
 void *ref_vocab_load_text(const char *);
@@ -177,6 +179,30 @@ int main(int argc, char **argv) {
         for (int i = 0; i < F.N; ++i) {
             const int got = matches[i] ? (int)(matches[i] - mps.data()) : -1;
             if (got != asg[i]) { printf("FAIL SearchByBoW frame feature %d: keyframe feature %d vs reference %d\n", i, got, asg[i]); return 1; }
+        }
+#endif
+        // SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&) (src/LoopClosing.cc:592-593 style): the frame becomes a second keyframe
+        ORB_SLAM3::KeyFrame KF2;
+        KF2.mvKeysUn = keys2; KF2.mvKeys = keys2; KF2.mDescriptors = desc2; KF2.mFeatVec = F.mFeatVec;
+        std::vector<ORB_SLAM3::MapPoint> mps2(keys2.size());
+        KF2.mps.assign(keys2.size(), nullptr);
+        std::vector<uint8_t> kfmp2(keys2.size());
+        for (size_t i = 0; i < keys2.size(); ++i) {
+            kfmp2[i] = (uint8_t)((i % 7) == 0 ? 0 : ((i % 19) == 0 ? 2 : 1));
+            if (kfmp2[i]) { mps2[i].bad = kfmp2[i] == 2; KF2.mps[i] = &mps2[i]; }
+        }
+        std::vector<ORB_SLAM3::MapPoint *> m12;
+        const int nk = reloc.SearchByBoW(&KF, &KF2, m12);
+        if (nk < 10 || m12.size() != keys.size()) { printf("FAIL SearchByBoW(KF, KF) found %d matches\n", nk); return 1; }
+#ifdef WITH_REF_MATCH
+        std::vector<int32_t> r12(keys.size());
+        const int rnk = refm_search_by_bow_kf((const orc_keypoint *)keys.data(), desc.ptr(0), (int)keys.size(), kfmp.data(), kn.data(), ko.data(), ki.data(), (int)kn.size(),
+                                              (const orc_keypoint *)keys2.data(), desc2.ptr(0), (int)keys2.size(), kfmp2.data(), fn.data(), fo.data(), fi.data(),
+                                              (int)fn.size(), 0.75f, 1, r12.data());
+        if (rnk != nk) { printf("FAIL SearchByBoW(KF, KF) count %d vs reference %d\n", nk, rnk); return 1; }
+        for (size_t i = 0; i < keys.size(); ++i) {
+            const int got = m12[i] ? (int)(m12[i] - mps2.data()) : -1;
+            if (got != r12[i]) { printf("FAIL SearchByBoW(KF, KF) feature %zu: %d vs reference %d\n", i, got, r12[i]); return 1; }
         }
 #endif
     }

@@ -379,3 +379,30 @@ def test_search_by_bow_vs_oracle(orbx_mod, oracle_mod, nk, nf, seed, ratio, ori)
     assert nm == rn and np.array_equal(asg, rasg)
     if nk >= 1000 and nf >= 900:
         assert nm > 100
+
+
+@pytest.mark.parametrize("i", range(4))
+def test_search_by_bow_keyframes_vs_reference_golden(orbx_mod, i):
+    """orbx_search_by_bow_keyframes == the stored outputs of the reference's own SearchByBoW(KeyFrame*, KeyFrame*, …) (src/ORBmatcher.cc:760-901)"""
+    from dani_slam_b200 import synth
+    from match_cases import BOW_CASES
+    g = _gold()
+    nk, nf, seed, ratio, ori = BOW_CASES[i]
+    s = synth.bow_scene(nk, nf, seed)
+    K1, K2 = _bow_sides(s)
+    K2["map_points"] = s["f_mp"]
+    nm, m12 = orbx_mod.ORBmatcher(ratio, ori).SearchByBoWKeyFrames(K1, K2)
+    assert nm == int(g[f"bowkf{i}_n"]) and np.array_equal(m12, g[f"bowkf{i}_m12"])
+
+
+@pytest.mark.parametrize("nk,nf,seed,ratio,ori", [(1500, 1400, 41, 0.7, True), (1000, 900, 42, 0.9, False), (0, 50, 43, 0.7, True), (50, 0, 44, 0.7, True),
+                                                  (5000, 5000, 45, 0.75, True), (33, 31, 47, 0.6, True)])
+def test_search_by_bow_keyframes_vs_oracle(orbx_mod, oracle_mod, nk, nf, seed, ratio, ori):
+    from dani_slam_b200 import synth
+    s = synth.bow_scene(nk, nf, seed, n_nodes=40 if nk < 3000 else 120)
+    K1, K2 = _bow_sides(s)
+    K2["map_points"] = s["f_mp"]
+    nm, m12 = orbx_mod.ORBmatcher(ratio, ori).SearchByBoWKeyFrames(K1, K2)
+    rn, r12 = oracle_mod.search_by_bow_kf(s["kf_desc"], s["kf_kps"]["angle"], s["kf_mp"], s["kf_fv"], s["f_desc"], s["f_kps"]["angle"], s["f_mp"], s["f_fv"],
+                                          ratio, ori)
+    assert nm == rn and np.array_equal(m12, r12)

@@ -228,3 +228,34 @@ def test_reference_search_by_bow_vs_oracle(refm, oracle_mod, nk, nf, seed, ratio
                 if oa[best] == kf:
                     seen.add(best)
         assert taken > 0
+
+
+def oracle_bow_kf(oracle_mod, s, ratio, ori):
+    return oracle_mod.search_by_bow_kf(s["kf_desc"], s["kf_kps"]["angle"], s["kf_mp"], s["kf_fv"], s["f_desc"], s["f_kps"]["angle"], s["f_mp"], s["f_fv"],
+                                       ratio, ori)
+
+
+@pytest.mark.parametrize("i", range(len(BOW_CASES)))
+def test_search_by_bow_keyframes_golden(gold, oracle_mod, i):
+    """oracle == the stored outputs of the reference's own SearchByBoW(KeyFrame*, KeyFrame*, …) (src/ORBmatcher.cc:760-901)"""
+    from dani_slam_b200 import synth
+    nk, nf, seed, ratio, ori = BOW_CASES[i]
+    s = synth.bow_scene(nk, nf, seed)
+    assert sha(s["kf_kps"], s["kf_desc"], s["kf_mp"], *s["kf_fv"], s["f_kps"], s["f_desc"], s["f_mp"], *s["f_fv"]) == str(gold[f"bowkf{i}_in"])
+    nm, m12 = oracle_bow_kf(oracle_mod, s, ratio, ori)
+    assert nm == int(gold[f"bowkf{i}_n"]) and np.array_equal(m12, gold[f"bowkf{i}_m12"])
+    assert nm > 0 and nm == int((m12 >= 0).sum())
+
+
+@pytest.mark.parametrize("nk,nf,seed,ratio,ori", [(300, 280, 11, 0.7, True), (1500, 1400, 12, 0.7, True), (1000, 900, 13, 0.9, False), (0, 50, 14, 0.7, True),
+                                                  (50, 0, 15, 0.7, True), (3000, 3000, 17, 0.75, True), (600, 600, 18, 1.0, True)])
+def test_reference_search_by_bow_keyframes_vs_oracle(refm, oracle_mod, nk, nf, seed, ratio, ori):
+    from dani_slam_b200 import synth
+    s = synth.bow_scene(nk, nf, seed)
+    rn, r12 = refm.search_by_bow_kf(s["kf_kps"], s["kf_desc"], s["kf_mp"], s["kf_fv"], s["f_kps"], s["f_desc"], s["f_mp"], s["f_fv"], ratio, ori)
+    on, o12 = oracle_bow_kf(oracle_mod, s, ratio, ori)
+    assert rn == on and np.array_equal(r12, o12)
+    if nk >= 1000 and nf >= 900:
+        assert rn > 100
+        got = o12[o12 >= 0]
+        assert len(np.unique(got)) == len(got) and np.all(s["f_mp"][got] == 1) and np.all(s["kf_mp"][o12 >= 0] == 1)

@@ -52,6 +52,11 @@ def main():
         nm, asg = R.search_by_bow(s["kf_kps"], s["kf_desc"], s["kf_mp"], s["kf_fv"], s["f_kps"], s["f_desc"], s["f_fv"], ratio, ori)
         out[f"bow{i}_in"] = np.array(sha(s["kf_kps"], s["kf_desc"], s["kf_mp"], *s["kf_fv"], s["f_kps"], s["f_desc"], *s["f_fv"]), dtype="U64")
         out[f"bow{i}_n"] = np.int32(nm); out[f"bow{i}_assigned"] = asg
+    for i, (nk, nf, seed, ratio, ori) in enumerate(BOW_CASES):
+        s = synth.bow_scene(nk, nf, seed)
+        nm, m12 = R.search_by_bow_kf(s["kf_kps"], s["kf_desc"], s["kf_mp"], s["kf_fv"], s["f_kps"], s["f_desc"], s["f_mp"], s["f_fv"], ratio, ori)
+        out[f"bowkf{i}_in"] = np.array(sha(s["kf_kps"], s["kf_desc"], s["kf_mp"], *s["kf_fv"], s["f_kps"], s["f_desc"], s["f_mp"], *s["f_fv"]), dtype="U64")
+        out[f"bowkf{i}_n"] = np.int32(nm); out[f"bowkf{i}_m12"] = m12
     for i, seed in enumerate([1, 2]):
         uL, uR, iL, iR, dist = tail_case(seed)
         # the reference's matcher in this slot reports a similarity (distance = 1 - match.distance, src/Frame.cc:891); feeding
