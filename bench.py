@@ -282,8 +282,43 @@ def measure_latency(orbx, device, frames, args):
         ts = []
         for i in range(12):
             t0 = time.perf_counter_ns(); cx.extract(frames[i % len(frames)]); ts.append(time.perf_counter_ns() - t0)
-        out["cpu_reference"] = {"ms_per_frame_1_thread": float(np.median(ts)) / 1e6, "kind": kind, "sample": "median of 12 frames, one thread"}
+        out["cpu_reference"] = {"ms_per_frame_1_thread": float(np.median(ts)) / 1e6, "kind": kind, "sample": "median of 12 frames, one thread",
+                                "cv2_primitives_ms_per_frame_1_thread": cv2_primitives_ms(frames),
+                                "cv2_note": "the real OpenCV (cv2 wheel, SIMD builds) primitives of the path alone on one thread — 7 resizes, 8 borders, "
+                                            "FAST-9 with NMS on every level at iniThFAST, 8 Gaussian blurs; no quadtree, orientation or descriptors. "
+                                            "The reference arm runs the oracle's scalar restatements of these primitives under the reference's own "
+                                            "ORBextractor.cc, so an OpenCV-linked build of the reference would sit between the two figures"}
     return out
+
+
+def cv2_primitives_ms(frames, seconds=1.5):
+    """Context for the CPU baseline: how long the REAL OpenCV primitives of the path take on one thread.  None without cv2."""
+    try:
+        import cv2
+        return _cv2_primitives_ms(cv2, frames, seconds)
+    except Exception:                                  # a reported context figure must never take the bench down
+        return None
+
+
+def _cv2_primitives_ms(cv2, frames, seconds):
+    cv2.setNumThreads(1)
+    fast = cv2.FastFeatureDetector_create(INI_TH, True, cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+    sizes, sf = [], np.float32(1.0)
+    for _ in range(LEVELS):
+        inv = np.float32(1.0) / sf
+        sizes.append((int(np.rint(np.float32(W_IMG) * inv)), int(np.rint(np.float32(H_IMG) * inv))))
+        sf = np.float32(float(sf) * float(np.float32(SCALE)))
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds or n < 3:
+        lv = [np.ascontiguousarray(frames[n % len(frames)])]
+        for l in range(1, LEVELS):
+            lv.append(cv2.resize(lv[-1], sizes[l], interpolation=cv2.INTER_LINEAR))
+        for l in range(LEVELS):
+            cv2.copyMakeBorder(lv[l], 19, 19, 19, 19, cv2.BORDER_REFLECT_101)
+            fast.detect(lv[l], None)
+            cv2.GaussianBlur(lv[l], (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101)
+        n += 1
+    return 1000.0 * (time.perf_counter() - t0) / n
 
 
 # ----------------------------------------------------------------------------------------------------
